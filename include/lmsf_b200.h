@@ -1,0 +1,201 @@
+/*
+ * lmsf_b200.h — C ABI of the B200-native LiDAR scan-to-map registration hot path.
+ *
+ * Drop-in boundary for Robot-WH/LMSF-Slam (src/MultiSensorFusionEstimator3D,
+ * paths below are relative to its include/ directory).  Every entry point is
+ * extern "C", takes plain pointers and sizes (caller-owned HOST buffers unless
+ * the name ends in _dev) and returns an int status: 0 = OK, <0 = error
+ * (lmsf_strerror).  The reference's three seams return void and have no error
+ * convention (registration_base.hpp:31-33, process_base.hpp:37,
+ * Filter/filter_base.hpp:34); the C++ adapters in lmsf_b200_adapters.hpp log a
+ * non-zero status and leave the output untouched, which is what the reference
+ * does on failure (edgeSurfFeatureRegistration.hpp:221-225).
+ *
+ * There is NO CPU fallback behind this ABI: every call runs hand-written
+ * sm_100a CUDA kernels on the context's device and fails with
+ * LMSF_ERR_NO_DEVICE when none is usable.
+ *
+ * A context is one LiDAR's worth of state (one CUDA stream, pre-sized device
+ * arenas, the local-map index, the tracker state).  Contexts share nothing
+ * and may be used concurrently from different threads, one thread per context
+ * at a time — the reference runs one processor/tracker instance per LiDAR
+ * under `omp parallel for` (System/ML_System.hpp:137-141,248-256).
+ *
+ * Layouts: a point is 4 packed floats {x, y, z, intensity}; a pose is 7
+ * doubles {qx, qy, qz, qw, tx, ty, tz} — the parameter block layout of
+ * ceres_edgeSurfFeatureRegistration.hpp:38-40.
+ */
+#ifndef LMSF_B200_H_
+#define LMSF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMSF_OK 0
+#define LMSF_ERR_INVALID (-1)   /* bad argument */
+#define LMSF_ERR_NO_DEVICE (-2) /* no usable CUDA device: there is no CPU path */
+#define LMSF_ERR_CUDA (-3)      /* a CUDA call failed; see lmsf_last_cuda_error */
+#define LMSF_ERR_CAPACITY (-4)  /* input larger than the context was sized for */
+#define LMSF_ERR_STATE (-5)     /* call order (e.g. register before map_set) */
+
+#define LMSF_KIND_EDGE 0 /* "loam_edge" */
+#define LMSF_KIND_SURF 1 /* "loam_surf" */
+
+#define LMSF_SOLVER_GN 0      /* EdgeSurfFeatureRegistration (edgeSurfFeatureRegistration.hpp:27) */
+#define LMSF_SOLVER_HUBER_LM 1 /* CeresEdgeSurfFeatureRegistration (factory default, ML_SystemFactory.hpp:189) */
+
+typedef struct lmsf_ctx lmsf_ctx;
+
+/* Construction parameters.  Defaults (lmsf_params_default) are the constants
+ * the reference hard-codes; the comment gives the file:line of each. */
+typedef struct {
+  int32_t n_scans;           /* 16; 16|32|64 (ML_SystemFactory.hpp:197, LOAMFeatureProcessor_base.hpp:309-340) */
+  float min_range;           /* 2    (ML_SystemFactory.hpp:197) */
+  float max_range;           /* 80 */
+  float edge_thresh;         /* 1.0  (LOAMFeatureProcessor_base.hpp:37) */
+  int32_t remove_bad_points; /* 1    (LOAMFeatureProcessor_base.hpp:38) */
+  int32_t max_points;        /* capacity of one sweep, default 262144 */
+  int32_t window;            /* 10   sliding-window keyframes (ndt_test.yaml:18) */
+  int32_t solver;            /* LMSF_SOLVER_HUBER_LM */
+  float map_leaf_edge;       /* 0 = raw concatenation (shipped tracker); >0 voxel-filter the map */
+  float map_leaf_surf;
+  float scan_leaf_edge;      /* 0 = off; >0 voxel-filter scan features before registration */
+  float scan_leaf_surf;
+  int32_t gn_max_iters;      /* 10   (edgeSurfFeatureRegistration.hpp:65) */
+  int32_t lm_outer_start;    /* 10, decremented before every solve, floor 2 (ceres_...:46,100-101) */
+  int32_t lm_inner_iters;    /* 4    (ceres_...:118) */
+  float huber_delta;         /* 0.1  (ceres_...:107) */
+  double kf_trans;           /* 0.3 m   (LidarTrackerLocalMap.hpp:65) */
+  double kf_rot;             /* 0.1 rad */
+  double kf_time;            /* 10 s */
+  int32_t max_map_points;    /* capacity of one local map; default window * max_points */
+  int32_t oracle_knn_mode;   /* ignored by the CUDA library (oracle: 0 kd-tree, 1 brute force) */
+  int32_t oracle_threads;    /* ignored by the CUDA library */
+  int32_t reserved[9];
+} lmsf_params;
+
+typedef struct {
+  int32_t outer_iters;       /* outer iterations executed */
+  int32_t n_edge_matched;    /* accepted correspondences in the last outer iteration */
+  int32_t n_surf_matched;
+  int32_t converged;         /* GN: broke on the convergence test (edgeSurf...:326) */
+  int32_t degenerate;        /* GN: isDegenerate (edgeSurf...:290) */
+  int32_t lm_steps_total;    /* LM: trust-region iterations over all outer iterations */
+  int32_t lm_steps_accepted;
+  int32_t pad;
+  double final_cost;         /* GN: 0.5*sum r^2 of last iteration; LM: 0.5*sum rho(r^2) */
+} lmsf_reg_stats;
+
+typedef struct {
+  int32_t n_edge, n_surf;    /* features extracted from this sweep */
+  int32_t keyframe;          /* 0 none, 1 motion, 2 time (LidarTrackerLocalMap.hpp:239-262) */
+  int32_t map_edge, map_surf; /* local-map sizes after this step */
+  int32_t first;             /* 1 on the initialising sweep (LidarTrackerLocalMap.hpp:111-121) */
+  lmsf_reg_stats reg;
+} lmsf_track_stats;
+
+/* ---- lifetime ------------------------------------------------------- */
+int lmsf_params_default(lmsf_params* p);
+int lmsf_ctx_create(int device, const lmsf_params* p, lmsf_ctx** out);
+void lmsf_ctx_destroy(lmsf_ctx* c);
+const char* lmsf_strerror(int code);
+const char* lmsf_last_cuda_error(lmsf_ctx* c);
+/* number of kernels this context has launched so far (bench.py gpu_launches) */
+int64_t lmsf_launch_count(lmsf_ctx* c);
+/* raw cudaStream_t of the context, for CUDA-event timing on the launching stream */
+void* lmsf_stream(lmsf_ctx* c);
+
+/* ---- seam 1: feature extraction ------------------------------------ */
+/* Replaces LOAMFeatureProcessorBase::Process (FeatureExtract/LOAMFeatureProcessor_base.hpp:59-126):
+ * splitScan :290-343, checkBadEdgePoint :216-282, curvature :97-118,
+ * featureExtractionFromSector :145-207.  label_out (optional, n bytes):
+ * 0 = neither, 1 = "loam_edge", 2 = "loam_surf".  edge_xyzi / surf_xyzi
+ * receive the clouds in the reference's order (rings 0..R-1, sectors 0..5;
+ * edges by descending curvature, surfs by ascending curvature); each must
+ * have room for n points. */
+int lmsf_extract_features(lmsf_ctx* c, const float* xyzi, int n, uint8_t* label_out,
+                          float* edge_xyzi, int* n_edge, float* surf_xyzi, int* n_surf);
+
+/* ---- seam 2: voxel-grid filter -------------------------------------- */
+/* Replaces FilterBase::Filter with a pcl::VoxelGrid (Filter/filter_base.hpp:34-45,
+ * Filter/voxel_grid.hpp:25-29, factory/processing/pointcloud/filter/filter_factory.hpp:36-41).
+ * out_xyzi needs room for n points; voxel_of_point (optional, n ints) receives
+ * the output row each input point was averaged into (-1 for a non-finite point). */
+int lmsf_voxel_downsample(lmsf_ctx* c, const float* xyzi, int n, float leaf, float* out_xyzi,
+                          int* n_out, int32_t* voxel_of_point);
+
+/* ---- seam 3: registration ------------------------------------------- */
+/* = RegistrationBase::SetInputSource (registration/registration_base.hpp:31): upload a
+ * local map and build its kNN index (replaces pcl::KdTreeFLANN::setInputCloud,
+ * FeatureMatch/FeatureMatchBase.hpp:40-44).  An empty map is ignored like
+ * ceres_edgeSurfFeatureRegistration.hpp:58. */
+int lmsf_map_set(lmsf_ctx* c, int kind, const float* xyzi, int n);
+/* Test hook for nearestKSearch(point, 5) (EdgeFeatureMatch.hpp:38, surfFeatureMatch.hpp:37).
+ * Neighbours are ascending by (squared distance, index); only neighbours with
+ * squared distance < 1.0 (FeatureMatchBase.hpp:29) are reported, the rest of
+ * the five slots hold idx -1 and d2 +inf — the matchers reject such queries. */
+int lmsf_knn5(lmsf_ctx* c, int kind, const float* q_xyz, int nq, int32_t* idx5, float* d2_5);
+/* Test hook for EdgeFeatureMatch::Match (EdgeFeatureMatch.hpp:33-87) / SurfFeatureMatch::Match
+ * (surfFeatureMatch.hpp:32-87) on world-frame fp32 points.  out10 per query:
+ * kind 0: {nx,ny,nz, r, ax,ay,az, bx,by,bz}; kind 1: {nx,ny,nz, r, D, 0,0,0,0,0}. */
+int lmsf_match(lmsf_ctx* c, int kind, const float* q_xyz, int nq, uint8_t* ok, double* out10);
+/* = SetInputTarget + Solve (registration_base.hpp:32-33): pose holds the
+ * prediction on entry and the result on return.  solver: LMSF_SOLVER_*; the
+ * Huber-LM outer-iteration budget is context state, as in the reference. */
+int lmsf_register(lmsf_ctx* c, const float* edge_xyzi, int n_e, const float* surf_xyzi, int n_s,
+                  int solver, double pose[7], lmsf_reg_stats* st);
+/* CeresEdgeSurfFeatureRegistration::SetMaxIteration / reset of the stateful budget */
+int lmsf_set_lm_outer(lmsf_ctx* c, int count);
+
+/* ---- a6: scan-to-map tracker, device resident ----------------------- */
+/* = LOAMFeatureProcessorBase::Process followed by LidarTrackerLocalMap::Solve
+ * (LidarTracker/LidarTrackerLocalMap.hpp:107-160): prediction, registration,
+ * keyframe test :239-262, local-map update and index rebuild :205-232.
+ * delta: in = caller's motion prior (identity {0,0,0,1,0,0,0} = use the
+ * constant-velocity model), out = motion increment.  pose_out = curr_pose_. */
+int lmsf_tracker_step(lmsf_ctx* c, const float* xyzi, int n, double stamp, double delta[7],
+                      double pose_out[7], lmsf_track_stats* st);
+/* Same, with the sweep already resident in device memory (d_xyzi is a device
+ * pointer on the context's device). */
+int lmsf_tracker_step_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp, double delta[7],
+                          double pose_out[7], lmsf_track_stats* st);
+/* Same, fed with features instead of a raw sweep — the exact argument of
+ * LidarTrackerLocalMap::Solve. */
+int lmsf_tracker_step_features(lmsf_ctx* c, const float* edge_xyzi, int n_e, const float* surf_xyzi,
+                               int n_s, double stamp, double delta[7], double pose_out[7],
+                               lmsf_track_stats* st);
+int lmsf_tracker_reset(lmsf_ctx* c);
+/* = LidarTrackerLocalMap::RegistrationLocalMap (:168-177) as used for an auxiliary
+ * LiDAR against the primary's map (System/ML_System.hpp:304): extract features
+ * from xyzi and register them against this tracker's current local map. */
+int lmsf_tracker_register_aux(lmsf_ctx* c, const float* xyzi, int n, double pose[7],
+                              lmsf_reg_stats* st);
+/* = LidarTrackerLocalMap::GetLocalMap (:184-192) */
+int lmsf_get_map(lmsf_ctx* c, int kind, float* xyzi, int cap, int* n);
+
+/* ---- device memory helpers for callers that keep sweeps resident ---- */
+int lmsf_dev_alloc(lmsf_ctx* c, int64_t bytes, void** d_ptr);
+int lmsf_dev_free(lmsf_ctx* c, void* d_ptr);
+int lmsf_dev_upload(lmsf_ctx* c, void* d_dst, const void* h_src, int64_t bytes);
+
+/* ---- per-stage device timing (CUDA events on the context's stream) -- */
+#define LMSF_STAGE_EXTRACT 0
+#define LMSF_STAGE_MATCH 1    /* kNN + PCA/plane + residual (dominant kernel) */
+#define LMSF_STAGE_SOLVE 2    /* LM/GN evaluation + reduction + 6x6 step kernels */
+#define LMSF_STAGE_MAP 3      /* local-map update + index rebuild */
+#define LMSF_STAGE_VOXEL 4
+#define LMSF_N_STAGES 5
+/* enable = 1 records events around every stage (adds host syncs at query time only) */
+int lmsf_profile_enable(lmsf_ctx* c, int enable);
+/* accumulated milliseconds and launch counts per stage since the last reset;
+ * bytes = algorithmic bytes of the match kernel launches (16*(F+M)+216 each) */
+int lmsf_profile_read(lmsf_ctx* c, double ms[LMSF_N_STAGES], int64_t launches[LMSF_N_STAGES],
+                      double* match_alg_bytes, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMSF_B200_H_ */

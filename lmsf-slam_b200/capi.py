@@ -1,0 +1,360 @@
+"""ctypes binding of the C ABI declared in include/lmsf_b200.h.
+
+The binding is generic over (shared-library path, symbol prefix) because the CPU
+oracle under oracle/ deliberately exports the same entry points with the prefix
+``lmsf_oracle_`` (oracle/lmsf_oracle.h) so the parity tests can drive both through
+one wrapper.  This package itself only ever loads the CUDA library
+(``csrc/liblmsf_b200.so``); pointing the binding at the oracle is done by
+tests/, bench.py's cpu_baseline leg and __graft_entry__.smoke() alone.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+KIND_EDGE, KIND_SURF = 0, 1
+SOLVER_GN, SOLVER_HUBER_LM = 0, 1
+N_STAGES = 5
+STAGE_NAMES = ("extract", "match", "solve", "map", "voxel")
+
+
+class Params(C.Structure):
+    """lmsf_params (include/lmsf_b200.h) — same layout as lmsf_oracle_params."""
+
+    _fields_ = [
+        ("n_scans", C.c_int32),
+        ("min_range", C.c_float),
+        ("max_range", C.c_float),
+        ("edge_thresh", C.c_float),
+        ("remove_bad_points", C.c_int32),
+        ("max_points", C.c_int32),
+        ("window", C.c_int32),
+        ("solver", C.c_int32),
+        ("map_leaf_edge", C.c_float),
+        ("map_leaf_surf", C.c_float),
+        ("scan_leaf_edge", C.c_float),
+        ("scan_leaf_surf", C.c_float),
+        ("gn_max_iters", C.c_int32),
+        ("lm_outer_start", C.c_int32),
+        ("lm_inner_iters", C.c_int32),
+        ("huber_delta", C.c_float),
+        ("kf_trans", C.c_double),
+        ("kf_rot", C.c_double),
+        ("kf_time", C.c_double),
+        ("max_map_points", C.c_int32),
+        ("oracle_knn_mode", C.c_int32),
+        ("oracle_threads", C.c_int32),
+        ("reserved", C.c_int32 * 9),
+    ]
+
+
+class RegStats(C.Structure):
+    _fields_ = [
+        ("outer_iters", C.c_int32),
+        ("n_edge_matched", C.c_int32),
+        ("n_surf_matched", C.c_int32),
+        ("converged", C.c_int32),
+        ("degenerate", C.c_int32),
+        ("lm_steps_total", C.c_int32),
+        ("lm_steps_accepted", C.c_int32),
+        ("pad", C.c_int32),
+        ("final_cost", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad"}
+
+
+class TrackStats(C.Structure):
+    _fields_ = [
+        ("n_edge", C.c_int32),
+        ("n_surf", C.c_int32),
+        ("keyframe", C.c_int32),
+        ("map_edge", C.c_int32),
+        ("map_surf", C.c_int32),
+        ("first", C.c_int32),
+        ("reg", RegStats),
+    ]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reg"}
+        d["reg"] = self.reg.as_dict()
+        return d
+
+
+class LmsfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"lmsf error {code}: {msg}")
+        self.code = code
+
+
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+_intp = C.POINTER(C.c_int)
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f32p)
+
+
+def _xyzi(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("expected an (n, 4) float32 XYZI array")
+    return a
+
+
+IDENTITY_POSE = (0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0)
+
+
+class Library:
+    """One loaded shared library exporting the ABI under `prefix`."""
+
+    # symbols every implementation of the ABI exports (name without prefix)
+    COMMON = (
+        "params_default", "ctx_create", "ctx_destroy", "strerror", "extract_features",
+        "voxel_downsample", "map_set", "knn5", "match", "register", "set_lm_outer",
+        "tracker_step", "tracker_step_features", "tracker_reset", "tracker_register_aux", "get_map",
+    )
+    # symbols only the CUDA library exports
+    DEVICE_ONLY = (
+        "last_cuda_error", "launch_count", "stream", "tracker_step_dev", "dev_alloc", "dev_free",
+        "dev_upload", "profile_enable", "profile_read",
+    )
+
+    def __init__(self, path: str, prefix: str = "lmsf_"):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} is missing: build it first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "There is no CPU fallback behind this ABI.")
+        self.path = path
+        self.prefix = prefix
+        self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL if False else C.DEFAULT_MODE)
+        self.is_device = prefix == "lmsf_"
+        f = self.fn
+        f("strerror").restype = C.c_char_p
+        f("ctx_destroy").restype = None
+        if self.is_device:
+            f("last_cuda_error").restype = C.c_char_p
+            f("launch_count").restype = C.c_int64
+            f("stream").restype = C.c_void_p
+            f("tracker_step_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, _f64p, _f64p,
+                                              C.POINTER(TrackStats)]
+            f("dev_alloc").argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+            f("dev_free").argtypes = [C.c_void_p, C.c_void_p]
+            f("dev_upload").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+            f("launch_count").argtypes = [C.c_void_p]
+            f("stream").argtypes = [C.c_void_p]
+            f("last_cuda_error").argtypes = [C.c_void_p]
+            f("profile_enable").argtypes = [C.c_void_p, C.c_int]
+            f("profile_read").argtypes = [C.c_void_p, _f64p, C.POINTER(C.c_int64), _f64p, C.c_int]
+        f("ctx_create").argtypes = [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]
+        f("ctx_destroy").argtypes = [C.c_void_p]
+        f("extract_features").argtypes = [C.c_void_p, _f32p, C.c_int, _u8p, _f32p, _intp, _f32p, _intp]
+        f("voxel_downsample").argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, _f32p, _intp, _i32p]
+        f("map_set").argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int]
+        f("knn5").argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int, _i32p, _f32p]
+        f("match").argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int, _u8p, _f64p]
+        f("register").argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, C.c_int, C.c_int, _f64p, C.POINTER(RegStats)]
+        f("set_lm_outer").argtypes = [C.c_void_p, C.c_int]
+        f("tracker_step").argtypes = [C.c_void_p, _f32p, C.c_int, C.c_double, _f64p, _f64p, C.POINTER(TrackStats)]
+        f("tracker_step_features").argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, C.c_int, C.c_double, _f64p, _f64p,
+                                               C.POINTER(TrackStats)]
+        f("tracker_reset").argtypes = [C.c_void_p]
+        f("tracker_register_aux").argtypes = [C.c_void_p, _f32p, C.c_int, _f64p, C.POINTER(RegStats)]
+        f("get_map").argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int, _intp]
+
+    def fn(self, name):
+        return getattr(self.dll, self.prefix + name)
+
+    def has(self, name) -> bool:
+        try:
+            self.fn(name)
+            return True
+        except AttributeError:
+            return False
+
+    def default_params(self) -> Params:
+        p = Params()
+        rc = self.fn("params_default")(C.byref(p))
+        if rc:
+            raise LmsfError(rc, "params_default")
+        return p
+
+    def context(self, device: int = 0, **overrides) -> "Context":
+        return Context(self, device, **overrides)
+
+
+class Context:
+    """One LiDAR's context (lmsf_ctx): stream, arenas, local-map index, tracker state."""
+
+    def __init__(self, lib: Library, device: int = 0, **overrides):
+        self.lib = lib
+        self.params = lib.default_params()
+        for k, v in overrides.items():
+            if not hasattr(self.params, k):
+                raise AttributeError(f"lmsf_params has no field {k}")
+            setattr(self.params, k, v)
+        self._h = C.c_void_p()
+        rc = lib.fn("ctx_create")(device, C.byref(self.params), C.byref(self._h))
+        if rc:
+            raise LmsfError(rc, lib.fn("strerror")(rc).decode())
+
+    def close(self):
+        if self._h:
+            self.lib.fn("ctx_destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc:
+            msg = self.lib.fn("strerror")(rc).decode()
+            if self.lib.is_device and rc == -3:
+                msg += ": " + self.lib.fn("last_cuda_error")(self._h).decode()
+            raise LmsfError(rc, msg)
+
+    # -- seam 1
+    def extract_features(self, xyzi):
+        a = _xyzi(xyzi)
+        n = a.shape[0]
+        lab = np.zeros(n, np.uint8)
+        e = np.empty((max(n, 1), 4), np.float32)
+        s = np.empty((max(n, 1), 4), np.float32)
+        ne, ns = C.c_int(0), C.c_int(0)
+        self._chk(self.lib.fn("extract_features")(self._h, _fp(a), n, lab.ctypes.data_as(_u8p), _fp(e), C.byref(ne),
+                                                  _fp(s), C.byref(ns)))
+        return lab, e[: ne.value].copy(), s[: ns.value].copy()
+
+    # -- seam 2
+    def voxel_downsample(self, xyzi, leaf: float, want_membership: bool = True):
+        a = _xyzi(xyzi)
+        n = a.shape[0]
+        out = np.empty((max(n, 1), 4), np.float32)
+        mem = np.empty(max(n, 1), np.int32) if want_membership else None
+        no = C.c_int(0)
+        self._chk(self.lib.fn("voxel_downsample")(self._h, _fp(a), n, float(leaf), _fp(out), C.byref(no),
+                                                  mem.ctypes.data_as(_i32p) if mem is not None else None))
+        return out[: no.value].copy(), (mem[:n].copy() if mem is not None else None)
+
+    # -- seam 3
+    def map_set(self, kind: int, xyzi):
+        a = _xyzi(xyzi)
+        self._chk(self.lib.fn("map_set")(self._h, kind, _fp(a), a.shape[0]))
+
+    def knn5(self, kind: int, q_xyz):
+        q = np.ascontiguousarray(q_xyz, dtype=np.float32).reshape(-1, 3)
+        nq = q.shape[0]
+        idx = np.empty((max(nq, 1), 5), np.int32)
+        d2 = np.empty((max(nq, 1), 5), np.float32)
+        self._chk(self.lib.fn("knn5")(self._h, kind, _fp(q), nq, idx.ctypes.data_as(_i32p), _fp(d2)))
+        return idx[:nq], d2[:nq]
+
+    def match(self, kind: int, q_xyz):
+        q = np.ascontiguousarray(q_xyz, dtype=np.float32).reshape(-1, 3)
+        nq = q.shape[0]
+        ok = np.zeros(max(nq, 1), np.uint8)
+        out = np.zeros((max(nq, 1), 10), np.float64)
+        self._chk(self.lib.fn("match")(self._h, kind, _fp(q), nq, ok.ctypes.data_as(_u8p),
+                                       out.ctypes.data_as(_f64p)))
+        return ok[:nq].astype(bool), out[:nq]
+
+    def register(self, edge, surf, pose=IDENTITY_POSE, solver: int | None = None):
+        e, s = _xyzi(edge), _xyzi(surf)
+        p = np.array(pose, dtype=np.float64)
+        st = RegStats()
+        sv = self.params.solver if solver is None else solver
+        self._chk(self.lib.fn("register")(self._h, _fp(e), e.shape[0], _fp(s), s.shape[0], sv,
+                                          p.ctypes.data_as(_f64p), C.byref(st)))
+        return p, st.as_dict()
+
+    def set_lm_outer(self, count: int):
+        self._chk(self.lib.fn("set_lm_outer")(self._h, count))
+
+    # -- tracker
+    def tracker_step(self, xyzi, stamp: float, delta=IDENTITY_POSE):
+        a = _xyzi(xyzi)
+        d = np.array(delta, dtype=np.float64)
+        p = np.zeros(7, np.float64)
+        st = TrackStats()
+        self._chk(self.lib.fn("tracker_step")(self._h, _fp(a), a.shape[0], float(stamp), d.ctypes.data_as(_f64p),
+                                              p.ctypes.data_as(_f64p), C.byref(st)))
+        return p, d, st.as_dict()
+
+    def tracker_step_dev(self, d_ptr: int, n: int, stamp: float, delta=IDENTITY_POSE):
+        d = np.array(delta, dtype=np.float64)
+        p = np.zeros(7, np.float64)
+        st = TrackStats()
+        self._chk(self.lib.fn("tracker_step_dev")(self._h, C.c_void_p(d_ptr), n, float(stamp),
+                                                  d.ctypes.data_as(_f64p), p.ctypes.data_as(_f64p), C.byref(st)))
+        return p, d, st.as_dict()
+
+    def tracker_step_features(self, edge, surf, stamp: float, delta=IDENTITY_POSE):
+        e, s = _xyzi(edge), _xyzi(surf)
+        d = np.array(delta, dtype=np.float64)
+        p = np.zeros(7, np.float64)
+        st = TrackStats()
+        self._chk(self.lib.fn("tracker_step_features")(self._h, _fp(e), e.shape[0], _fp(s), s.shape[0], float(stamp),
+                                                       d.ctypes.data_as(_f64p), p.ctypes.data_as(_f64p),
+                                                       C.byref(st)))
+        return p, d, st.as_dict()
+
+    def tracker_reset(self):
+        self._chk(self.lib.fn("tracker_reset")(self._h))
+
+    def tracker_register_aux(self, xyzi, pose):
+        a = _xyzi(xyzi)
+        p = np.array(pose, dtype=np.float64)
+        st = RegStats()
+        self._chk(self.lib.fn("tracker_register_aux")(self._h, _fp(a), a.shape[0], p.ctypes.data_as(_f64p),
+                                                      C.byref(st)))
+        return p, st.as_dict()
+
+    def get_map(self, kind: int):
+        n = C.c_int(0)
+        self._chk(self.lib.fn("get_map")(self._h, kind, None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        self._chk(self.lib.fn("get_map")(self._h, kind, _fp(out), out.shape[0], C.byref(n)))
+        return out[: n.value].copy()
+
+    # -- device-only helpers
+    def launch_count(self) -> int:
+        return int(self.lib.fn("launch_count")(self._h))
+
+    def stream(self) -> int:
+        return int(self.lib.fn("stream")(self._h) or 0)
+
+    def dev_upload_new(self, arr) -> int:
+        a = np.ascontiguousarray(arr)
+        ptr = C.c_void_p()
+        self._chk(self.lib.fn("dev_alloc")(self._h, a.nbytes, C.byref(ptr)))
+        self._chk(self.lib.fn("dev_upload")(self._h, ptr, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return int(ptr.value)
+
+    def dev_free(self, ptr: int):
+        self._chk(self.lib.fn("dev_free")(self._h, C.c_void_p(ptr)))
+
+    def profile_enable(self, on: bool = True):
+        self._chk(self.lib.fn("profile_enable")(self._h, int(on)))
+
+    def profile_read(self, reset: bool = True):
+        ms = (C.c_double * N_STAGES)()
+        ln = (C.c_int64 * N_STAGES)()
+        by = C.c_double(0)
+        self._chk(self.lib.fn("profile_read")(self._h, ms, ln, C.byref(by), int(reset)))
+        return ({STAGE_NAMES[i]: ms[i] for i in range(N_STAGES)}, {STAGE_NAMES[i]: ln[i] for i in range(N_STAGES)},
+                by.value)

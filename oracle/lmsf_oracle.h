@@ -1,0 +1,118 @@
+/*
+ * lmsf_oracle.h — C interface of the CPU ORACLE.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a CPU restatement of the reference's
+ * scan-to-map hot path (Robot-WH/LMSF-Slam, src/MultiSensorFusionEstimator3D),
+ * used as the checker by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs.  Nothing under lmsf-slam_b200/ may
+ * include, link or call it.
+ *
+ * PARITY UNPINNED: the reference holds no golden vectors, known-answer tests or
+ * fixtures for this path (its two test main()s assert nothing and their PCD
+ * inputs are not in the tree), the tree does not compile as shipped (Map/ is
+ * git-ignored) and its third-party arithmetic (PCL, FLANN, Eigen, Ceres) is
+ * neither vendored nor version-pinned, so the oracle cannot be checked against
+ * reference outputs.  It is anchored instead on (i) the reference source text,
+ * cited per function in lmsf_oracle.cpp, (ii) numpy / scipy cross-checks of its
+ * linear algebra and of its Huber-LM solve (tests/), (iii) the reference's
+ * vendored nanoflann 1.3.2 (compiled from /root/reference into oracle/_ref) as
+ * an independent exact-kNN check.
+ *
+ * The entry points mirror include/lmsf_b200.h one to one (prefix lmsf_oracle_)
+ * so that the parity tests drive both through the same ctypes wrapper; the
+ * structs have the same layout as lmsf_params / lmsf_reg_stats /
+ * lmsf_track_stats.
+ */
+#ifndef LMSF_ORACLE_H_
+#define LMSF_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lmsf_oracle_ctx lmsf_oracle_ctx;
+
+typedef struct {
+  int32_t n_scans;
+  float min_range, max_range, edge_thresh;
+  int32_t remove_bad_points;
+  int32_t max_points;
+  int32_t window;
+  int32_t solver; /* 0 = Gauss-Newton, 1 = Huber-LM (Ceres semantics) */
+  float map_leaf_edge, map_leaf_surf;
+  float scan_leaf_edge, scan_leaf_surf;
+  int32_t gn_max_iters;
+  int32_t lm_outer_start;
+  int32_t lm_inner_iters;
+  float huber_delta;
+  double kf_trans, kf_rot, kf_time;
+  int32_t max_map_points;
+  int32_t knn_mode; /* 0 = kd-tree (leaf 15), 1 = brute force */
+  int32_t threads;  /* OpenMP threads over features in the match loops; <=1 = serial (the reference) */
+  int32_t reserved[9];
+} lmsf_oracle_params;
+
+typedef struct {
+  int32_t outer_iters;
+  int32_t n_edge_matched, n_surf_matched;
+  int32_t converged, degenerate;
+  int32_t lm_steps_total, lm_steps_accepted;
+  int32_t pad;
+  double final_cost;
+} lmsf_oracle_reg_stats;
+
+typedef struct {
+  int32_t n_edge, n_surf;
+  int32_t keyframe;
+  int32_t map_edge, map_surf;
+  int32_t first;
+  lmsf_oracle_reg_stats reg;
+} lmsf_oracle_track_stats;
+
+int lmsf_oracle_params_default(lmsf_oracle_params* p);
+int lmsf_oracle_ctx_create(int device, const lmsf_oracle_params* p, lmsf_oracle_ctx** out);
+void lmsf_oracle_ctx_destroy(lmsf_oracle_ctx* c);
+const char* lmsf_oracle_strerror(int code);
+
+int lmsf_oracle_extract_features(lmsf_oracle_ctx* c, const float* xyzi, int n, uint8_t* label_out,
+                                 float* edge_xyzi, int* n_edge, float* surf_xyzi, int* n_surf);
+int lmsf_oracle_voxel_downsample(lmsf_oracle_ctx* c, const float* xyzi, int n, float leaf,
+                                 float* out_xyzi, int* n_out, int32_t* voxel_of_point);
+int lmsf_oracle_map_set(lmsf_oracle_ctx* c, int kind, const float* xyzi, int n);
+int lmsf_oracle_knn5(lmsf_oracle_ctx* c, int kind, const float* q_xyz, int nq, int32_t* idx5,
+                     float* d2_5);
+int lmsf_oracle_match(lmsf_oracle_ctx* c, int kind, const float* q_xyz, int nq, uint8_t* ok,
+                      double* out10);
+int lmsf_oracle_register(lmsf_oracle_ctx* c, const float* edge_xyzi, int n_e,
+                         const float* surf_xyzi, int n_s, int solver, double pose[7],
+                         lmsf_oracle_reg_stats* st);
+int lmsf_oracle_set_lm_outer(lmsf_oracle_ctx* c, int count);
+int lmsf_oracle_tracker_step(lmsf_oracle_ctx* c, const float* xyzi, int n, double stamp,
+                             double delta[7], double pose_out[7], lmsf_oracle_track_stats* st);
+int lmsf_oracle_tracker_step_features(lmsf_oracle_ctx* c, const float* edge_xyzi, int n_e,
+                                      const float* surf_xyzi, int n_s, double stamp,
+                                      double delta[7], double pose_out[7],
+                                      lmsf_oracle_track_stats* st);
+int lmsf_oracle_tracker_reset(lmsf_oracle_ctx* c);
+int lmsf_oracle_tracker_register_aux(lmsf_oracle_ctx* c, const float* xyzi, int n, double pose[7],
+                                     lmsf_oracle_reg_stats* st);
+int lmsf_oracle_get_map(lmsf_oracle_ctx* c, int kind, float* xyzi, int cap, int* n);
+
+/* small-algebra test hooks (checked against numpy in tests/) */
+int lmsf_oracle_symeig3(const double a[9], double w[3], double v[9]);
+int lmsf_oracle_symeig6(const double a[36], double w[6], double v[36]);
+int lmsf_oracle_lstsq53(const double a[15], const double b[5], double x[3]);
+int lmsf_oracle_solve6(const double a[36], const double b[6], double x[6]);
+int lmsf_oracle_se3_exp(const double d[6], double q[4], double t[3]);
+/* one Ceres-style Huber-LM solve on explicit residual blocks (tests compare it
+ * with a numpy restatement): edge blocks {pl(3), a(3), b(3)}, surf blocks
+ * {pl(3), n(3), D}; x = {qx,qy,qz,qw,tx,ty,tz} in/out. */
+int lmsf_oracle_lm_solve(const double* edge9, int n_e, const double* surf7, int n_s, double huber,
+                         int max_iters, double x[7], int* steps, int* accepted, double* cost);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

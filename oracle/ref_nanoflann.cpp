@@ -1,0 +1,45 @@
+// ref_nanoflann.cpp — thin C wrapper that instantiates the REFERENCE'S OWN vendored
+// nanoflann 1.3.2 (include/Algorithm/PointClouds/processing/GlobalDescriptor/scanContext/
+// nanoflann.hpp, compiled where it lies under /root/reference; never copied) as a 3-D
+// exact kd-tree with the L2_Simple metric (nanoflann.hpp:423-446, same fp32 accumulation
+// order as FLANN's L2_Simple used by pcl::KdTreeFLANN) and leaf size 15.
+//
+// TEST INFRASTRUCTURE ONLY: output goes to oracle/_ref/ and is used by tests/ to
+// cross-check the oracle's kNN.  Built by oracle/Makefile when /root/reference exists.
+#include <cstddef>
+#include <cstdint>
+#include <limits>
+#include <vector>
+
+#include "nanoflann.hpp"
+
+namespace {
+struct Cloud {
+  const float* p;
+  size_t n;
+  inline size_t kdtree_get_point_count() const { return n; }
+  inline float kdtree_get_pt(const size_t idx, const size_t dim) const { return p[idx * 4 + dim]; }
+  template <class BBOX>
+  bool kdtree_get_bbox(BBOX&) const { return false; }
+};
+typedef nanoflann::KDTreeSingleIndexAdaptor<nanoflann::L2_Simple_Adaptor<float, Cloud>, Cloud, 3> Tree;
+}  // namespace
+
+extern "C" int ref_nanoflann_knn5(const float* xyzi, int n, const float* q_xyz, int nq, int32_t* idx5, float* d2_5) {
+  Cloud cloud{xyzi, (size_t)n};
+  Tree tree(3, cloud, nanoflann::KDTreeSingleIndexAdaptorParams(15));
+  tree.buildIndex();
+  for (int i = 0; i < nq; ++i) {
+    size_t idx[5];
+    float d2[5];
+    nanoflann::KNNResultSet<float> rs(5);
+    rs.init(idx, d2);
+    tree.findNeighbors(rs, q_xyz + 3 * i, nanoflann::SearchParams(10));
+    size_t found = rs.size();
+    for (size_t k = 0; k < 5; ++k) {
+      idx5[5 * i + k] = k < found ? (int32_t)idx[k] : -1;
+      d2_5[5 * i + k] = k < found ? d2[k] : std::numeric_limits<float>::infinity();
+    }
+  }
+  return 0;
+}
