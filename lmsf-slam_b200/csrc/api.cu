@@ -1,0 +1,631 @@
+// api.cu — the C ABI (include/lmsf_b200.h): context lifetime, the three seams, and the
+// scan-to-map tracker (LidarTracker/LidarTrackerLocalMap.hpp:107-262) whose point data never
+// leaves the device: one H2D copy per sweep in, 7+ doubles out.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace lm {
+
+// ------------------------------------------------------------------ profiling
+StageScope::StageScope(Ctx* c_, int s) : c(c_), stage(s), l0(c_->launches) {
+  if (!c->prof) return;
+  auto take = [&]() {
+    cudaEvent_t e = nullptr;
+    if (!c->ev_pool.empty()) {
+      e = c->ev_pool.back();
+      c->ev_pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  };
+  a = take();
+  b = take();
+  cudaEventRecord(a, c->stream);
+}
+StageScope::~StageScope() {
+  c->prof_launch[stage] += c->launches - l0;
+  if (!a) return;
+  cudaEventRecord(b, c->stream);
+  c->spans.push_back(Ctx::Span{stage, a, b});
+}
+
+// pcl::transformPointCloud(cloud, out, Matrix4d) (LidarTrackerLocalMap.hpp:217): double math, float store
+struct Rigid12 {
+  double R[9], t[3];
+};
+__global__ void __launch_bounds__(256) k_transform(const float4* __restrict__ in, const int* __restrict__ counts,
+                                                   int kind, Rigid12 T, float4* __restrict__ out) {
+  const int n_e = counts[0];
+  const int n = kind ? counts[1] : n_e;
+  const float4* src = in + (kind ? n_e : 0);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = src[i];
+  double x = p.x, y = p.y, z = p.z;
+  float4 o;
+  o.x = (float)(T.R[0] * x + T.R[1] * y + T.R[2] * z + T.t[0]);
+  o.y = (float)(T.R[3] * x + T.R[4] * y + T.R[5] * z + T.t[1]);
+  o.z = (float)(T.R[6] * x + T.R[7] * y + T.R[8] * z + T.t[2]);
+  o.w = p.w;
+  out[i] = o;
+}
+
+static int set_counts(Ctx* c, int n_e, int n_s) {
+  c->h_ints[40] = n_e;
+  c->h_ints[41] = n_s;
+  LM_CUDA(cudaMemcpyAsync(c->ex.counts, c->h_ints + 40, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  c->n_edge = n_e;
+  c->n_surf = n_s;
+  return LMSF_OK;
+}
+
+static int fetch_counts(Ctx* c) {
+  LM_CUDA(cudaMemcpyAsync(c->h_ints + 32, c->ex.counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  c->n_edge = c->h_ints[32];
+  c->n_surf = c->h_ints[33];
+  return LMSF_OK;
+}
+
+// choose the cloud the index is built over (raw window or its voxel-filtered copy) and build
+static int index_window(Ctx* c, int kind) {
+  MapIndex& m = c->map[kind];
+  int total = 0;
+  for (int f : m.frame_n) total += f;
+  float leaf = kind ? c->prm.map_leaf_surf : c->prm.map_leaf_edge;
+  int n = total;
+  if (leaf > 0.f && total > 0) {
+    LM_TRY(voxel_run(c, m.win, total, leaf, m.vox, &n, nullptr));
+    m.cat = m.vox;
+  } else {
+    m.cat = m.win;
+  }
+  if (n == 0) return LMSF_OK;  // an empty source is ignored (ceres_edgeSurfFeatureRegistration.hpp:58)
+  return map_build(c, m, n);
+}
+
+// updateLocalMap (LidarTrackerLocalMap.hpp:205-232) over the sliding-window local map (the reference's
+// PointCloudLocalMapBase is missing from its tree; contract inferred, SURVEY.md §8 a6'):
+// type 1 = AddFrameForMotion (append, evict the oldest beyond `window`), 2 = AddFrameForTime
+// (replace the newest frame).  c->n_edge / c->n_surf must be valid on the host.
+static int update_map(Ctx* c, const rigid& T, int type) {
+  Rigid12 T12;
+  for (int i = 0; i < 9; ++i) T12.R[i] = T.R[i];
+  for (int i = 0; i < 3; ++i) T12.t[i] = T.t[i];
+  for (int kind = 0; kind < 2; ++kind) {
+    int nk = kind ? c->n_surf : c->n_edge;
+    if (nk == 0) continue;
+    MapIndex& m = c->map[kind];
+    {
+      StageScope scope(c, LMSF_STAGE_MAP);
+      int total = 0;
+      for (int f : m.frame_n) total += f;
+      int drop = 0;
+      if (type == 1) {
+        if ((int)m.frame_n.size() + 1 > c->prm.window) drop = m.frame_n.front();
+      } else if (!m.frame_n.empty()) {
+        total -= m.frame_n.back();
+        m.frame_n.pop_back();
+      }
+      int kept = total - drop;
+      if (kept + nk > m.cap) return LMSF_ERR_CAPACITY;
+      if (drop > 0) {
+        LM_CUDA(cudaMemcpyAsync(m.win_alt, m.win + drop, (size_t)kept * sizeof(float4), cudaMemcpyDeviceToDevice,
+                                c->stream));
+        float4* t = m.win;
+        m.win = m.win_alt;
+        m.win_alt = t;
+        m.frame_n.erase(m.frame_n.begin());
+      }
+      LM_LAUNCH(c, k_transform, div_up(nk, 256), 256, 0, c->d_feat, c->ex.counts, kind, T12, m.win + kept);
+      m.frame_n.push_back(nk);
+    }
+    LM_TRY(index_window(c, kind));
+  }
+  return LMSF_OK;
+}
+
+// needUpdataLocalMap (LidarTrackerLocalMap.hpp:239-262)
+static int need_update(Ctx* c, const rigid& curr, double stamp) {
+  if (stamp - c->last_kf_time > c->prm.kf_time) return 2;
+  rigid d = rigid_mul(rigid_inv(c->last_kf), curr);
+  double dt = sqrt(d.t[0] * d.t[0] + d.t[1] * d.t[1] + d.t[2] * d.t[2]);
+  quat q = mat_to_quat(d.R);
+  double n = sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  double da = acos(q.w / n) * 2;
+  if (dt > c->prm.kf_trans || da > c->prm.kf_rot) return 1;
+  return 0;
+}
+
+static int next_lm_outer(Ctx* c) {
+  if (c->lm_count > 2) c->lm_count--;  // ceres_edgeSurfFeatureRegistration.hpp:100-101
+  return c->lm_count;
+}
+
+static int run_solver(Ctx* c, int solver, double pose[7], lmsf_reg_stats* st, int upper) {
+  int outer = (solver == LMSF_SOLVER_GN) ? c->prm.gn_max_iters : next_lm_outer(c);
+  return solve_run(c, solver, pose, st, upper, outer);
+}
+
+// optional voxel filter of the scan features (off by default); needs the counts on the host
+static int scan_filter(Ctx* c) {
+  const float le = c->prm.scan_leaf_edge, ls = c->prm.scan_leaf_surf;
+  if (!(le > 0.f) && !(ls > 0.f)) return LMSF_OK;
+  LM_TRY(fetch_counts(c));
+  const int ne = c->n_edge, ns = c->n_surf;
+  if (ne + ns == 0) return LMSF_OK;
+  LM_CUDA(cudaMemcpyAsync(c->d_tmp, c->d_feat, (size_t)(ne + ns) * sizeof(float4), cudaMemcpyDeviceToDevice,
+                          c->stream));
+  int ne2 = ne, ns2 = ns;
+  if (le > 0.f) LM_TRY(voxel_run(c, c->d_tmp, ne, le, c->d_feat, &ne2, nullptr));
+  if (ls > 0.f) {
+    LM_TRY(voxel_run(c, c->d_tmp + ne, ns, ls, c->d_feat + ne2, &ns2, nullptr));
+  } else if (ne2 != ne) {
+    LM_CUDA(cudaMemcpyAsync(c->d_feat + ne2, c->d_tmp + ne, (size_t)ns * sizeof(float4), cudaMemcpyDeviceToDevice,
+                            c->stream));
+  }
+  return set_counts(c, ne2, ns2);
+}
+
+// LidarTrackerLocalMap::Solve (:107-160); features already in d_feat, counts on the device
+static int tracker_core(Ctx* c, int upper, double stamp, double delta[7], double pose_out[7], lmsf_track_stats* out) {
+  lmsf_track_stats s;
+  memset(&s, 0, sizeof s);
+  LM_TRY(scan_filter(c));
+  if (!c->init) {
+    LM_TRY(fetch_counts(c));
+    LM_TRY(update_map(c, rigid_identity(), 1));
+    c->curr = c->prev = c->motion = c->last_kf = rigid_identity();
+    c->last_kf_time = stamp;
+    c->init = true;
+    s.first = 1;
+    s.keyframe = 1;
+  } else {
+    bool ident = delta[0] == 0 && delta[1] == 0 && delta[2] == 0 && delta[3] == 1 && delta[4] == 0 && delta[5] == 0 &&
+                 delta[6] == 0;
+    c->curr = ident ? rigid_mul(c->prev, c->motion) : rigid_mul(c->prev, rigid_from_pose(delta));
+    double p[7];
+    rigid_to_pose(c->curr, p);  // Quaterniond(T.rotation())
+    LM_TRY(run_solver(c, c->prm.solver, p, &s.reg, upper));  // leaves n_edge / n_surf on the host
+    c->curr = rigid_from_pose(p);  // T.linear() = q.toRotationMatrix()
+    c->motion = rigid_mul(rigid_inv(c->prev), c->curr);
+    rigid_to_pose(c->motion, delta);
+    c->prev = c->curr;
+    int ut = need_update(c, c->curr, stamp);
+    s.keyframe = ut;
+    if (ut) {
+      c->last_kf = c->curr;
+      c->last_kf_time = stamp;
+      LM_TRY(update_map(c, c->curr, ut));
+    }
+  }
+  s.n_edge = c->n_edge;
+  s.n_surf = c->n_surf;
+  s.map_edge = c->map[0].n_host;
+  s.map_surf = c->map[1].n_host;
+  rigid_to_pose(c->curr, pose_out);
+  if (out) *out = s;
+  return LMSF_OK;
+}
+
+static int upload_features(Ctx* c, const float* edge, int n_e, const float* surf, int n_s) {
+  if (n_e < 0 || n_s < 0 || (n_e > 0 && !edge) || (n_s > 0 && !surf)) return LMSF_ERR_INVALID;
+  if (n_e + n_s > c->prm.max_points) return LMSF_ERR_CAPACITY;
+  if (n_e) memcpy(c->h_pts, edge, (size_t)n_e * sizeof(float4));
+  if (n_s) memcpy(c->h_pts + n_e, surf, (size_t)n_s * sizeof(float4));
+  if (n_e + n_s)
+    LM_CUDA(cudaMemcpyAsync(c->d_feat, c->h_pts, (size_t)(n_e + n_s) * sizeof(float4), cudaMemcpyHostToDevice,
+                            c->stream));
+  return set_counts(c, n_e, n_s);
+}
+
+static int upload_sweep(Ctx* c, const float* xyzi, int n) {
+  if (n < 0 || (n > 0 && !xyzi)) return LMSF_ERR_INVALID;
+  if (n > c->prm.max_points) return LMSF_ERR_CAPACITY;
+  if (n) {
+    memcpy(c->h_pts, xyzi, (size_t)n * sizeof(float4));
+    LM_CUDA(cudaMemcpyAsync(c->d_sweep, c->h_pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  }
+  return LMSF_OK;
+}
+
+static void destroy(Ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto& sp : c->spans) {
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  extract_free(c);
+  voxel_free(c);
+  solve_free(c);
+  map_free(c->map[0]);
+  map_free(c->map[1]);
+  cudaFree(c->d_sweep);
+  cudaFree(c->d_feat);
+  cudaFree(c->d_tmp);
+  cudaFreeHost(c->h_pts);
+  cudaFreeHost(c->h_pose);
+  cudaFreeHost(c->h_ints);
+  cudaFreeHost(c->h_state);
+  if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+static int create(Ctx* c) {
+  size_t cap = (size_t)c->prm.max_points;
+  LM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  LM_CUDA(cudaMalloc(&c->d_sweep, cap * sizeof(float4)));
+  LM_CUDA(cudaMalloc(&c->d_feat, cap * sizeof(float4)));
+  LM_CUDA(cudaMalloc(&c->d_tmp, cap * sizeof(float4)));
+  LM_CUDA(cudaMallocHost(&c->h_pts, cap * sizeof(float4)));
+  LM_CUDA(cudaMallocHost(&c->h_pose, 16 * sizeof(double)));
+  LM_CUDA(cudaMallocHost(&c->h_ints, 64 * sizeof(int)));
+  LM_CUDA(cudaMallocHost(&c->h_state, sizeof(SolveState)));
+  LM_TRY(extract_alloc(c));
+  LM_TRY(voxel_alloc(c));
+  LM_TRY(solve_alloc(c));
+  LM_TRY(map_alloc(c, c->map[0], c->prm.max_map_points));
+  LM_TRY(map_alloc(c, c->map[1], c->prm.max_map_points));
+  c->curr = c->prev = c->motion = c->last_kf = rigid_identity();
+  c->lm_count = c->prm.lm_outer_start;
+  return LMSF_OK;
+}
+
+}  // namespace lm
+
+using namespace lm;
+
+#define ENTER(c)                      \
+  if (!(c)) return LMSF_ERR_INVALID;  \
+  if (cudaSetDevice((c)->device) != cudaSuccess) return LMSF_ERR_NO_DEVICE
+
+extern "C" {
+
+int lmsf_params_default(lmsf_params* p) {
+  if (!p) return LMSF_ERR_INVALID;
+  memset(p, 0, sizeof *p);
+  p->n_scans = 16;
+  p->min_range = 2.f;
+  p->max_range = 80.f;
+  p->edge_thresh = 1.f;
+  p->remove_bad_points = 1;
+  p->max_points = 262144;
+  p->window = 10;
+  p->solver = LMSF_SOLVER_HUBER_LM;
+  p->gn_max_iters = 10;
+  p->lm_outer_start = 10;
+  p->lm_inner_iters = 4;
+  p->huber_delta = 0.1f;
+  p->kf_trans = 0.3;
+  p->kf_rot = 0.1;
+  p->kf_time = 10.0;
+  p->max_map_points = 0;
+  p->oracle_knn_mode = 0;
+  p->oracle_threads = 1;
+  return LMSF_OK;
+}
+
+int lmsf_ctx_create(int device, const lmsf_params* p, lmsf_ctx** out) {
+  if (!p || !out) return LMSF_ERR_INVALID;
+  *out = nullptr;
+  if (p->n_scans != 16 && p->n_scans != 32 && p->n_scans != 64) return LMSF_ERR_INVALID;
+  if (p->max_points <= 0 || p->window <= 0 || p->lm_inner_iters < 0 || p->gn_max_iters < 0) return LMSF_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LMSF_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return LMSF_ERR_NO_DEVICE;
+  lmsf_ctx* c = new (std::nothrow) lmsf_ctx();
+  if (!c) return LMSF_ERR_INVALID;
+  c->device = device;
+  c->prm = *p;
+  if (c->prm.max_map_points <= 0) {
+    long long m = (long long)c->prm.window * c->prm.max_points;
+    c->prm.max_map_points = (int)(m > 16777216LL ? 16777216LL : m);
+  }
+  int rc = create(c);
+  if (rc != LMSF_OK) {
+    static thread_local std::string keep;
+    keep = c->last_error;
+    fprintf(stderr, "lmsf_ctx_create: %s\n", keep.c_str());
+    destroy(c);
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return LMSF_OK;
+}
+
+void lmsf_ctx_destroy(lmsf_ctx* c) {
+  if (!c) return;
+  destroy(c);
+  delete c;
+}
+
+const char* lmsf_strerror(int code) {
+  switch (code) {
+    case LMSF_OK: return "ok";
+    case LMSF_ERR_INVALID: return "invalid argument";
+    case LMSF_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU path)";
+    case LMSF_ERR_CUDA: return "CUDA error";
+    case LMSF_ERR_CAPACITY: return "input exceeds the capacity the context was created with";
+    case LMSF_ERR_STATE: return "call out of order (no local map set)";
+    default: return "unknown error";
+  }
+}
+
+const char* lmsf_last_cuda_error(lmsf_ctx* c) { return c ? c->last_error.c_str() : ""; }
+int64_t lmsf_launch_count(lmsf_ctx* c) { return c ? c->launches : 0; }
+void* lmsf_stream(lmsf_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int lmsf_extract_features(lmsf_ctx* c, const float* xyzi, int n, uint8_t* label_out, float* edge_xyzi, int* n_edge,
+                          float* surf_xyzi, int* n_surf) {
+  ENTER(c);
+  LM_TRY(upload_sweep(c, xyzi, n));
+  LM_TRY(extract_run(c, c->d_sweep, n));
+  LM_TRY(fetch_counts(c));
+  const int ne = c->n_edge, ns = c->n_surf;
+  if (label_out && n) LM_CUDA(cudaMemcpyAsync(label_out, c->ex.label, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  if (edge_xyzi && ne)
+    LM_CUDA(cudaMemcpyAsync(edge_xyzi, c->d_feat, (size_t)ne * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  if (surf_xyzi && ns)
+    LM_CUDA(cudaMemcpyAsync(surf_xyzi, c->d_feat + ne, (size_t)ns * sizeof(float4), cudaMemcpyDeviceToHost,
+                            c->stream));
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  if (n_edge) *n_edge = ne;
+  if (n_surf) *n_surf = ns;
+  return LMSF_OK;
+}
+
+int lmsf_voxel_downsample(lmsf_ctx* c, const float* xyzi, int n, float leaf, float* out_xyzi, int* n_out,
+                          int32_t* voxel_of_point) {
+  ENTER(c);
+  if (n < 0 || !(leaf > 0.f) || !n_out || (n > 0 && !xyzi)) return LMSF_ERR_INVALID;
+  if (n > c->vox_cap) return LMSF_ERR_CAPACITY;
+  *n_out = 0;
+  if (n == 0) return LMSF_OK;
+  // staged through pageable->device copies in chunks of the pinned buffer
+  const int chunk = c->prm.max_points;
+  for (int o = 0; o < n; o += chunk) {
+    int m = (n - o < chunk) ? n - o : chunk;
+    memcpy(c->h_pts, xyzi + 4 * (size_t)o, (size_t)m * sizeof(float4));
+    LM_CUDA(cudaMemcpyAsync(c->v_in + o, c->h_pts, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    LM_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  int nv = 0;
+  LM_TRY(voxel_run(c, c->v_in, n, leaf, c->v_out, &nv, voxel_of_point ? c->v_member : nullptr));
+  if (out_xyzi && nv)
+    LM_CUDA(cudaMemcpyAsync(out_xyzi, c->v_out, (size_t)nv * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  if (voxel_of_point)
+    LM_CUDA(cudaMemcpyAsync(voxel_of_point, c->v_member, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  *n_out = nv;
+  return LMSF_OK;
+}
+
+int lmsf_map_set(lmsf_ctx* c, int kind, const float* xyzi, int n) {
+  ENTER(c);
+  if (kind < 0 || kind > 1 || n < 0 || (n > 0 && !xyzi)) return LMSF_ERR_INVALID;
+  if (n == 0) return LMSF_OK;  // ceres_edgeSurfFeatureRegistration.hpp:58
+  MapIndex& m = c->map[kind];
+  if (n > m.cap) return LMSF_ERR_CAPACITY;
+  const int chunk = c->prm.max_points;
+  for (int o = 0; o < n; o += chunk) {
+    int k = (n - o < chunk) ? n - o : chunk;
+    memcpy(c->h_pts, xyzi + 4 * (size_t)o, (size_t)k * sizeof(float4));
+    LM_CUDA(cudaMemcpyAsync(m.win + o, c->h_pts, (size_t)k * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    LM_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  m.frame_n.assign(1, n);
+  m.cat = m.win;  // SetInputSource takes the cloud as given: no map voxel filter on this path
+  return map_build(c, m, n);
+}
+
+int lmsf_knn5(lmsf_ctx* c, int kind, const float* q_xyz, int nq, int32_t* idx5, float* d2_5) {
+  ENTER(c);
+  if (kind < 0 || kind > 1 || nq < 0 || (nq > 0 && (!q_xyz || !idx5 || !d2_5))) return LMSF_ERR_INVALID;
+  if (!c->map[kind].ready) return LMSF_ERR_STATE;
+  float* d_q = nullptr;
+  int* d_i = nullptr;
+  float* d_d = nullptr;
+  if (nq == 0) return LMSF_OK;
+  LM_CUDA(cudaMalloc(&d_q, (size_t)nq * 12));
+  LM_CUDA(cudaMalloc(&d_i, (size_t)nq * 20));
+  LM_CUDA(cudaMalloc(&d_d, (size_t)nq * 20));
+  int rc = LMSF_OK;
+  do {
+    if (cudaMemcpyAsync(d_q, q_xyz, (size_t)nq * 12, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+      rc = LMSF_ERR_CUDA;
+      break;
+    }
+    rc = knn_hook(c, kind, d_q, nq, d_i, d_d);
+    if (rc) break;
+    cudaMemcpyAsync(idx5, d_i, (size_t)nq * 20, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(d2_5, d_d, (size_t)nq * 20, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      c->last_error = cudaGetErrorString(cudaGetLastError());
+      rc = LMSF_ERR_CUDA;
+    }
+  } while (0);
+  cudaFree(d_q);
+  cudaFree(d_i);
+  cudaFree(d_d);
+  return rc;
+}
+
+int lmsf_match(lmsf_ctx* c, int kind, const float* q_xyz, int nq, uint8_t* ok, double* out10) {
+  ENTER(c);
+  if (kind < 0 || kind > 1 || nq < 0 || (nq > 0 && (!q_xyz || !ok || !out10))) return LMSF_ERR_INVALID;
+  if (!c->map[kind].ready) return LMSF_ERR_STATE;
+  if (nq == 0) return LMSF_OK;
+  float* d_q = nullptr;
+  uint8_t* d_ok = nullptr;
+  double* d_o = nullptr;
+  LM_CUDA(cudaMalloc(&d_q, (size_t)nq * 12));
+  LM_CUDA(cudaMalloc(&d_ok, (size_t)nq));
+  LM_CUDA(cudaMalloc(&d_o, (size_t)nq * 80));
+  int rc = LMSF_OK;
+  do {
+    if (cudaMemcpyAsync(d_q, q_xyz, (size_t)nq * 12, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+      rc = LMSF_ERR_CUDA;
+      break;
+    }
+    rc = match_hook(c, kind, d_q, nq, d_ok, d_o);
+    if (rc) break;
+    cudaMemcpyAsync(ok, d_ok, (size_t)nq, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(out10, d_o, (size_t)nq * 80, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      c->last_error = cudaGetErrorString(cudaGetLastError());
+      rc = LMSF_ERR_CUDA;
+    }
+  } while (0);
+  cudaFree(d_q);
+  cudaFree(d_ok);
+  cudaFree(d_o);
+  return rc;
+}
+
+int lmsf_register(lmsf_ctx* c, const float* edge_xyzi, int n_e, const float* surf_xyzi, int n_s, int solver,
+                  double pose[7], lmsf_reg_stats* st) {
+  ENTER(c);
+  if (!pose || (solver != LMSF_SOLVER_GN && solver != LMSF_SOLVER_HUBER_LM)) return LMSF_ERR_INVALID;
+  LM_TRY(upload_features(c, edge_xyzi, n_e, surf_xyzi, n_s));
+  return run_solver(c, solver, pose, st, n_e + n_s);
+}
+
+int lmsf_set_lm_outer(lmsf_ctx* c, int count) {
+  ENTER(c);
+  if (count < 0) return LMSF_ERR_INVALID;
+  c->lm_count = count;
+  return LMSF_OK;
+}
+
+int lmsf_tracker_step(lmsf_ctx* c, const float* xyzi, int n, double stamp, double delta[7], double pose_out[7],
+                      lmsf_track_stats* st) {
+  ENTER(c);
+  if (!delta || !pose_out) return LMSF_ERR_INVALID;
+  LM_TRY(upload_sweep(c, xyzi, n));
+  LM_TRY(extract_run(c, c->d_sweep, n));
+  return tracker_core(c, n, stamp, delta, pose_out, st);
+}
+
+int lmsf_tracker_step_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp, double delta[7], double pose_out[7],
+                          lmsf_track_stats* st) {
+  ENTER(c);
+  if (!delta || !pose_out || n < 0 || (n > 0 && !d_xyzi)) return LMSF_ERR_INVALID;
+  LM_TRY(extract_run(c, (const float4*)d_xyzi, n));
+  return tracker_core(c, n, stamp, delta, pose_out, st);
+}
+
+int lmsf_tracker_step_features(lmsf_ctx* c, const float* edge_xyzi, int n_e, const float* surf_xyzi, int n_s,
+                               double stamp, double delta[7], double pose_out[7], lmsf_track_stats* st) {
+  ENTER(c);
+  if (!delta || !pose_out) return LMSF_ERR_INVALID;
+  LM_TRY(upload_features(c, edge_xyzi, n_e, surf_xyzi, n_s));
+  return tracker_core(c, n_e + n_s, stamp, delta, pose_out, st);
+}
+
+int lmsf_tracker_reset(lmsf_ctx* c) {
+  ENTER(c);
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  c->init = false;
+  for (int k = 0; k < 2; ++k) {
+    c->map[k].frame_n.clear();
+    c->map[k].ready = false;
+    c->map[k].n_host = 0;
+    c->map[k].cat = c->map[k].win;
+  }
+  c->curr = c->prev = c->motion = c->last_kf = rigid_identity();
+  c->lm_count = c->prm.lm_outer_start;
+  return LMSF_OK;
+}
+
+int lmsf_tracker_register_aux(lmsf_ctx* c, const float* xyzi, int n, double pose[7], lmsf_reg_stats* st) {
+  ENTER(c);
+  if (!pose) return LMSF_ERR_INVALID;
+  LM_TRY(upload_sweep(c, xyzi, n));
+  LM_TRY(extract_run(c, c->d_sweep, n));
+  LM_TRY(scan_filter(c));
+  rigid T = rigid_from_pose(pose);  // Solve(Isometry3d&): quaternion <-> matrix round trip
+  double p[7];
+  rigid_to_pose(T, p);
+  LM_TRY(run_solver(c, c->prm.solver, p, st, n));
+  T = rigid_from_pose(p);
+  rigid_to_pose(T, pose);
+  return LMSF_OK;
+}
+
+int lmsf_get_map(lmsf_ctx* c, int kind, float* xyzi, int cap, int* n) {
+  ENTER(c);
+  if (kind < 0 || kind > 1 || !n) return LMSF_ERR_INVALID;
+  const MapIndex& m = c->map[kind];
+  *n = m.n_host;
+  if (!xyzi) return LMSF_OK;
+  if (cap < m.n_host) return LMSF_ERR_CAPACITY;
+  if (m.n_host) {
+    LM_CUDA(cudaMemcpyAsync(xyzi, m.cat, (size_t)m.n_host * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    LM_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return LMSF_OK;
+}
+
+int lmsf_dev_alloc(lmsf_ctx* c, int64_t bytes, void** d_ptr) {
+  ENTER(c);
+  if (bytes <= 0 || !d_ptr) return LMSF_ERR_INVALID;
+  LM_CUDA(cudaMalloc(d_ptr, (size_t)bytes));
+  return LMSF_OK;
+}
+
+int lmsf_dev_free(lmsf_ctx* c, void* d_ptr) {
+  ENTER(c);
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  LM_CUDA(cudaFree(d_ptr));
+  return LMSF_OK;
+}
+
+int lmsf_dev_upload(lmsf_ctx* c, void* d_dst, const void* h_src, int64_t bytes) {
+  ENTER(c);
+  if (!d_dst || !h_src || bytes < 0) return LMSF_ERR_INVALID;
+  LM_CUDA(cudaMemcpyAsync(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  return LMSF_OK;
+}
+
+int lmsf_profile_enable(lmsf_ctx* c, int enable) {
+  ENTER(c);
+  c->prof = enable != 0;
+  return LMSF_OK;
+}
+
+int lmsf_profile_read(lmsf_ctx* c, double ms[LMSF_N_STAGES], int64_t launches[LMSF_N_STAGES], double* match_alg_bytes,
+                      int reset) {
+  ENTER(c);
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& sp : c->spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) c->prof_ms[sp.stage] += t;
+    c->ev_pool.push_back(sp.a);
+    c->ev_pool.push_back(sp.b);
+  }
+  c->spans.clear();
+  for (int i = 0; i < LMSF_N_STAGES; ++i) {
+    if (ms) ms[i] = c->prof_ms[i];
+    if (launches) launches[i] = c->prof_launch[i];
+  }
+  if (match_alg_bytes) *match_alg_bytes = c->match_bytes;
+  if (reset) {
+    for (int i = 0; i < LMSF_N_STAGES; ++i) {
+      c->prof_ms[i] = 0;
+      c->prof_launch[i] = 0;
+    }
+    c->match_bytes = 0;
+  }
+  return LMSF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+// common.cuh — context layout, launch/err helpers shared by the .cu files of liblmsf_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lmsf_b200.h"
+#include "dmath.cuh"
+
+namespace lm {
+
+// ---------------------------------------------------------------- errors
+#define LM_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      c->last_error = std::string(#call) + ": " + cudaGetErrorString(e__);                    \
+      return LMSF_ERR_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+#define LM_TRY(expr)          \
+  do {                        \
+    int rc__ = (expr);        \
+    if (rc__ != LMSF_OK) return rc__; \
+  } while (0)
+
+// launch on the context's stream and count it
+#define LM_LAUNCH(c, kern, grid, block, smem, ...)                    \
+  do {                                                                \
+    kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);      \
+    (c)->launches++;                                                  \
+  } while (0)
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- feature extraction state
+struct ExtractBufs {
+  int cap = 0;        // max points per sweep
+  int nblk_cap = 0;   // ceil(cap / RING_BLOCK)
+  int* ring_id = nullptr;      // [cap] ring of each input point or -1
+  int* blk_cnt = nullptr;      // [64][nblk_cap] per-block ring histogram -> exclusive offsets
+  int* ring_cnt = nullptr;     // [64] points per ring
+  int* ring_off = nullptr;     // [65] exclusive offsets of rings in ring order
+  float4* ring_pts = nullptr;  // [cap] points grouped by ring, firing order kept
+  int* ring_src = nullptr;     // [cap] original index of ring_pts[i]
+  double* curv = nullptr;      // [cap] curvature by ring-order position
+  int* sorted = nullptr;       // [cap] per sector: ring-local ids ascending by (curvature, id)
+  double* sort_key = nullptr;  // [2*cap] global scratch for sectors too long for shared memory
+  int* sort_val = nullptr;     // [2*cap]
+  uint8_t* flag = nullptr;     // [cap] disable flags for rings too long for shared memory
+  uint8_t* btype = nullptr;    // [cap] bad-point classes, same
+  uint8_t* is_edge = nullptr;  // [cap] by ring-order position
+  int* edge_ids = nullptr;     // [64*6*20] picked edges per sector in pick order
+  int* sec_cnt = nullptr;      // [64*6] edges picked per sector
+  uint8_t* label = nullptr;    // [cap] by original index
+  int* counts = nullptr;       // [4] n_edge, n_surf, n_valid
+};
+
+// ---------------------------------------------------------------- local-map index
+// One coarse cell (edge = 1 m, the kNN radius) of the hash grid.  32 bytes so a
+// probe is a single 32-byte sector.
+struct __align__(32) CellRec {
+  unsigned long long key;   // packed relative cell coords, ~0 = empty slot
+  unsigned long long mask;  // occupancy of the 4x4x4 fine sub-cells (0.25 m)
+  int start, end;           // range in the cell-sorted point array
+  int fine_base;            // first entry of this cell in fine_start[]
+  int pad;
+};
+
+struct MapDev {  // device-visible description of one map index (lives in device memory)
+  int n;              // points in the sorted array (finite points of the map)
+  int min_c[3];       // coarse cell coords of the bbox minimum
+  int dim[3];         // coarse cells per axis
+  int bits[3];        // bits per axis in the packed key
+  unsigned table_mask;  // slots - 1
+  int n_fine;         // occupied fine cells
+};
+
+struct MapIndex {
+  int cap = 0;
+  int n_host = 0;            // points in cat (host copy of the count)
+  bool ready = false;
+  float4* win = nullptr;     // [cap] raw sliding window: keyframe clouds concatenated oldest -> newest
+  float4* win_alt = nullptr; // [cap] double buffer used when the oldest frame is evicted
+  float4* vox = nullptr;     // [cap] voxel-filtered window (only when a map leaf size is set)
+  float4* cat = nullptr;     // not owned: win or vox — the map cloud the index is built over
+  float4* sorted = nullptr;  // [cap] cell-sorted copy, .w = bit pattern of the original index
+  unsigned long long* keys = nullptr;      // [cap]
+  unsigned long long* keys_alt = nullptr;  // [cap]
+  int* vals = nullptr;                     // [cap]
+  int* vals_alt = nullptr;                 // [cap]
+  int* fine_start = nullptr;               // [cap+1]
+  uint8_t* flags = nullptr;                // [cap]
+  CellRec* table = nullptr;                // [table_cap]
+  unsigned table_cap = 0;
+  MapDev* dev = nullptr;     // device copy
+  MapDev host;               // host mirror (after build)
+  std::vector<int> frame_n;  // sliding window frame sizes, oldest first
+};
+
+// ---------------------------------------------------------------- solver state (device resident)
+#define LM_NSUM 30  // 21 (H upper) + 6 (g) + cost + rows + edge rows
+struct SolveState {
+  double x[7];        // current pose estimate {qx,qy,qz,qw,tx,ty,tz}
+  double cand[7];     // LM candidate
+  double H[36], g[6]; // normal equations at x
+  double cost;        // cost at x
+  double scale[6];    // Jacobi column scaling of this solve
+  double radius, decrease;
+  double model_change;
+  double x_norm;
+  double gn_map[36];  // GN degeneracy remap
+  int n_edge_ok, n_surf_ok;
+  int gn_done, gn_degenerate, gn_iters;
+  int lm_active;      // inner loop still running
+  int lm_iter;        // trust-region iterations used in this solve
+  int lm_invalid;
+  int lm_steps_total, lm_steps_accepted;
+  unsigned ticket;    // last-block-done counter
+  int pad;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  lmsf_params prm;
+  std::string last_error;
+  int64_t launches = 0;
+
+  // sweep + features
+  float4* d_sweep = nullptr;   // [max_points]
+  float4* d_feat = nullptr;    // [max_points] edges first, then surfs
+  float4* d_tmp = nullptr;     // [max_points] scratch (transformed frame / voxel input)
+  ExtractBufs ex;
+  MapIndex map[2];
+
+  // per-feature match records (7 doubles SoA) + validity
+  double* d_rec = nullptr;     // [7][max_points]
+  uint8_t* d_ok = nullptr;     // [max_points]
+  double* d_partial = nullptr; // [grid][LM_NSUM]
+  int partial_blocks = 0;
+  SolveState* d_state = nullptr;
+
+  // voxel scratch (sized for max(max_points, max_map_points))
+  int vox_cap = 0;
+  unsigned long long* v_keys = nullptr;
+  unsigned long long* v_keys_alt = nullptr;
+  int* v_vals = nullptr;
+  int* v_vals_alt = nullptr;
+  int* v_heads = nullptr;
+  uint8_t* v_flags = nullptr;
+  float4* v_sorted = nullptr;
+  float4* v_in = nullptr;
+  float4* v_out = nullptr;
+  int* v_member = nullptr;
+  void* v_params = nullptr;  // VoxelParams on device
+  unsigned* d_bbox = nullptr;  // [8] ordered-uint min/max + finite count
+
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+
+  // pinned host staging
+  float4* h_pts = nullptr;     // [max_points]
+  double* h_pose = nullptr;    // [16]
+  int* h_ints = nullptr;       // [64]
+  SolveState* h_state = nullptr;
+
+  // tracker (LidarTrackerLocalMap members)
+  bool init = false;
+  rigid prev, curr, motion, last_kf;
+  double last_kf_time = 0;
+  int lm_count = 10;
+  int n_edge = 0, n_surf = 0;  // features currently in d_feat
+
+  // profiling
+  bool prof = false;
+  struct Span {
+    int stage;
+    cudaEvent_t a, b;
+  };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> ev_pool;
+  double prof_ms[LMSF_N_STAGES] = {0, 0, 0, 0, 0};
+  int64_t prof_launch[LMSF_N_STAGES] = {0, 0, 0, 0, 0};
+  double match_bytes = 0;
+};
+
+struct StageScope {  // records CUDA events around a stage when profiling is on
+  Ctx* c;
+  int stage;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int64_t l0;
+  StageScope(Ctx* c_, int s);
+  ~StageScope();
+};
+
+// ---- implemented in extract.cu
+int extract_alloc(Ctx* c);
+void extract_free(Ctx* c);
+// sweep in c->d_sweep (n points) -> c->d_feat (edges, then surfs), counts in ex.counts, labels in ex.label
+int extract_run(Ctx* c, const float4* d_in, int n);
+
+// ---- implemented in voxel.cu
+int voxel_alloc(Ctx* c);
+void voxel_free(Ctx* c);
+// device in -> device out; *n_out read back (synchronises the stream)
+int voxel_run(Ctx* c, const float4* d_in, int n, float leaf, float4* d_out, int* n_out, int* d_member);
+
+// ---- implemented in mapindex.cu
+int map_alloc(Ctx* c, MapIndex& m, int cap);
+void map_free(MapIndex& m);
+// (re)build the hash-grid index over m.cat[0..n)
+int map_build(Ctx* c, MapIndex& m, int n);
+
+// ---- implemented in match.cu
+int solve_alloc(Ctx* c);
+void solve_free(Ctx* c);
+int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2);
+int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double* d_out10);
+// features in c->d_feat (counts in c->ex.counts on the device; `upper` bounds their sum on the
+// host); enqueues the whole solve, reads pose + statistics back (one stream sync)
+int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* st, int upper, int outer_count);
+
+}  // namespace lm
+
+struct lmsf_ctx : lm::Ctx {};

@@ -1,0 +1,767 @@
+// match.cu — correspondence search, residuals/Jacobians, normal-equation reduction and the
+// device-resident Gauss-Newton / Huber-LM loops.
+//
+//   k_match     one thread per scan feature: pointAssociateToMap (fp64 -> fp32,
+//               edgeSurfFeatureRegistration.hpp:342-350), exact 5-NN (knn.cuh),
+//               EdgeFeatureMatch::Match (FeatureMatch/EdgeFeatureMatch.hpp:33-87: 3x3 scatter,
+//               symmetric eigen, line test, point-to-line residual and gradient) or
+//               SurfFeatureMatch::Match (surfFeatureMatch.hpp:32-87: 5x3 least squares plane,
+//               0.2 m validity, signed distance truncated to float), then the 1x6 Jacobian row of
+//               the selected solver and a warp-shuffle + block-tree reduction of J^T J / J^T r.
+//               The last block to finish sums the per-block partials in a fixed order and runs the
+//               6x6 step: GNOptimization (edgeSurfFeatureRegistration.hpp:218-330) or the first
+//               trust-region proposal of the Ceres-style Huber-LM.
+//   k_lm_eval   re-evaluates the stored correspondences at the LM candidate (se3PointEdgeFactor
+//               ceres_factor/edge_factor.hpp:33-61, se3PointSurfFactor surf_factor.hpp:32-56,
+//               HuberLoss(0.1) ceres_edgeSurfFeatureRegistration.hpp:107), same reduction; its last
+//               block accepts / rejects the step and proposes the next one.
+// No host round trip happens inside a solve: iteration control lives in SolveState on the device,
+// and every kernel of the pre-enqueued sequence exits at once when its phase is over.
+#include <float.h>
+
+#include "common.cuh"
+#include "knn.cuh"
+
+namespace lm {
+
+static constexpr int MATCH_BLOCK = 128;
+static constexpr int MATCH_WARPS = MATCH_BLOCK / 32;
+
+struct SolveParams {
+  int solver;        // LMSF_SOLVER_*
+  int iter;          // GN iteration index / LM outer index
+  int lm_max_iters;  // 4
+  int gn_min_rows;   // 10
+  double huber;      // 0.1
+};
+
+struct MapPair {
+  MapView edge, surf;
+  const float4* edge_cat;  // map clouds in map order (neighbour coordinates by original index)
+  const float4* surf_cat;
+};
+
+// ------------------------------------------------------------------ geometry of one match
+// EdgeFeatureMatch::Match :44-84 given the five neighbours (ascending) and the fp32 world point
+__device__ __forceinline__ bool fit_edge(const float4* __restrict__ cat, const Top5& nb, float px, float py, float pz,
+                                         d3& n_out, double& r_out, d3& a_out, d3& b_out) {
+  d3 pt[5];
+  d3 c = mk3(0, 0, 0);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    float4 q = __ldg(&cat[nb.id[j]]);
+    pt[j] = mk3((double)q.x, (double)q.y, (double)q.z);
+    c = add3(c, pt[j]);
+  }
+  c = mk3(c.x / 5.0, c.y / 5.0, c.z / 5.0);
+  double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    d3 z = sub3(pt[j], c);
+    double zz[3] = {z.x, z.y, z.z};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) S[r * 3 + cc] = S[r * 3 + cc] + zz[r] * zz[cc];
+  }
+  double w[3], V[9];
+  jacobi_eig<3>(S, w, V);
+  if (!(w[2] > 3 * w[1])) return false;
+  d3 u = mk3(V[2], V[5], V[8]);
+  d3 a = add3(scl3(0.1, u), c);
+  d3 b = add3(scl3(-0.1, u), c);
+  d3 p = mk3((double)px, (double)py, (double)pz);
+  d3 nu = crs3(sub3(p, a), sub3(p, b));
+  d3 de = sub3(a, b);
+  double den = nrm3(de);
+  r_out = nrm3(nu) / den;
+  d3 g = crs3(de, nu);
+  double gn = nrm3(g);
+  n_out = (gn > 0.0) ? mk3(g.x / gn, g.y / gn, g.z / gn) : g;
+  a_out = a;
+  b_out = b;
+  return true;
+}
+
+// SurfFeatureMatch::Match :44-85
+__device__ __forceinline__ bool fit_surf(const float4* __restrict__ cat, const Top5& nb, float px, float py, float pz,
+                                         d3& n_out, double& D_out, double& r_out) {
+  double A[15], B[5] = {-1, -1, -1, -1, -1}, nn[3];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    float4 q = __ldg(&cat[nb.id[j]]);
+    A[j * 3 + 0] = q.x;
+    A[j * 3 + 1] = q.y;
+    A[j * 3 + 2] = q.z;
+  }
+  cpqr_solve<5, 3>(A, B, nn);
+  d3 n = mk3(nn[0], nn[1], nn[2]);
+  double len = nrm3(n);
+  double D = 1 / len;
+  n = mk3(n.x / len, n.y / len, n.z / len);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    if (fabs(n.x * A[j * 3 + 0] + n.y * A[j * 3 + 1] + n.z * A[j * 3 + 2] + D) > 0.2) return false;
+  }
+  d3 p = mk3((double)px, (double)py, (double)pz);
+  float distance = (float)(dot3(n, p) + D);
+  r_out = fabs((double)distance);
+  if (distance >= 0) {
+    n_out = n;
+    D_out = D;
+  } else {
+    n_out = mk3(-n.x, -n.y, -n.z);
+    D_out = -D;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------ accumulation
+struct Acc {
+  double v[LM_NSUM];  // H upper triangle row-major (21), g (6), cost, rows, edge rows
+};
+
+__device__ __forceinline__ void acc_zero(Acc& a) {
+#pragma unroll
+  for (int i = 0; i < LM_NSUM; ++i) a.v[i] = 0.0;
+}
+
+__device__ __forceinline__ void acc_row(Acc& a, const double* J, double r, double cost) {
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 6; ++j) a.v[k++] += J[i] * J[j];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) a.v[21 + i] += J[i] * r;
+  a.v[27] += cost;
+  a.v[28] += 1.0;
+}
+
+// ceres::HuberLoss + Corrector with rho'' <= 0: residual and Jacobian scaled by sqrt(rho')
+__device__ __forceinline__ void huber_apply(double a, double r, double& rho0, double& scale) {
+  double s = r * r, b = a * a;
+  if (s > b) {
+    double sr = sqrt(s);
+    rho0 = 2 * a * sr - b;
+    double rho1 = fmax(DBL_MIN, a / sr);
+    scale = sqrt(rho1);
+  } else {
+    rho0 = s;
+    scale = 1.0;
+  }
+}
+
+// se3PointEdgeFactor (edge_factor.hpp:39-57): residual and local Jacobian at (q,t)
+__device__ __forceinline__ void edge_factor(const quat& q, d3 t, d3 pl, d3 a, d3 b, double huber, Acc& acc) {
+  d3 lp = add3(qrot(q, pl), t);
+  d3 nu = crs3(sub3(lp, a), sub3(lp, b));
+  d3 de = sub3(a, b);
+  double den = nrm3(de), nun = nrm3(nu);
+  double r = nun / den;
+  d3 u = mk3(nu.x / nun, nu.y / nun, nu.z / nun);
+  d3 g = crs3(de, u);
+  d3 jr = crs3(lp, g);
+  double J[6] = {jr.x / den, jr.y / den, jr.z / den, g.x / den, g.y / den, g.z / den};
+  double rho0, sc;
+  huber_apply(huber, r, rho0, sc);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) J[i] = sc * J[i];
+  acc_row(acc, J, sc * r, 0.5 * rho0);
+}
+
+// se3PointSurfFactor (surf_factor.hpp:37-52)
+__device__ __forceinline__ void surf_factor(const quat& q, d3 t, d3 pl, d3 n, double D, double huber, Acc& acc) {
+  d3 lp = add3(qrot(q, pl), t);
+  double r = dot3(n, lp) + D;
+  d3 jr = crs3(lp, n);
+  double J[6] = {jr.x, jr.y, jr.z, n.x, n.y, n.z};
+  double rho0, sc;
+  huber_apply(huber, r, rho0, sc);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) J[i] = sc * J[i];
+  acc_row(acc, J, sc * r, 0.5 * rho0);
+}
+
+// GNOptimization row (edgeSurfFeatureRegistration.hpp:236-266): J = grad^T [-R skew(p) | I], float residual
+__device__ __forceinline__ void gn_row(const double* R, d3 pl, d3 grad, double res, Acc& acc) {
+  float residual = (float)res;
+  double sk[9] = {0, -pl.z, pl.y, pl.z, 0, -pl.x, -pl.y, pl.x, 0};
+  double A[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      A[i * 3 + j] = -(R[i * 3 + 0] * sk[0 * 3 + j] + R[i * 3 + 1] * sk[1 * 3 + j] + R[i * 3 + 2] * sk[2 * 3 + j]);
+  double J[6];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) J[j] = grad.x * A[0 * 3 + j] + grad.y * A[1 * 3 + j] + grad.z * A[2 * 3 + j];
+  J[3] = grad.x;
+  J[4] = grad.y;
+  J[5] = grad.z;
+  double rr = residual;
+  acc_row(acc, J, rr, 0.5 * rr * rr);
+}
+
+// warp-shuffle + block tree; returns true in the last block to finish, with the grid total in `tot`
+__device__ __forceinline__ bool reduce_grid(const Acc& acc, double* __restrict__ partial, SolveState* __restrict__ st,
+                                            double* tot /* shared [LM_NSUM] */) {
+  __shared__ double wsum[MATCH_WARPS][LM_NSUM];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < LM_NSUM; ++k) {
+    double x = acc.v[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if (lane == 0) wsum[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < LM_NSUM) {
+    double x = 0.0;
+#pragma unroll
+    for (int w = 0; w < MATCH_WARPS; ++w) x += wsum[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * LM_NSUM + threadIdx.x] = x;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(&st->ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return false;
+  __threadfence();
+  // fixed-order final sum: 4 strided sub-sums per quantity, combined in order
+  __shared__ double part[MATCH_WARPS][32];
+  {
+    int k = lane, p = warp;
+    double x = 0.0;
+    if (k < LM_NSUM)
+      for (unsigned b = p; b < gridDim.x; b += MATCH_WARPS) x += __ldcg(&partial[(size_t)b * LM_NSUM + k]);
+    part[p][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < LM_NSUM) {
+    double x = 0.0;
+#pragma unroll
+    for (int p = 0; p < MATCH_WARPS; ++p) x += part[p][threadIdx.x];
+    tot[threadIdx.x] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) st->ticket = 0u;
+  return true;
+}
+
+__device__ __forceinline__ void unpack_normal(const double* tot, double* H, double* g) {
+  int k = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) {
+      H[i * 6 + j] = tot[k];
+      H[j * 6 + i] = tot[k];
+      ++k;
+    }
+  for (int i = 0; i < 6; ++i) g[i] = tot[21 + i];
+}
+
+__device__ __forceinline__ double norm7(const double* x) {
+  double s = 0;
+  for (int i = 0; i < 7; ++i) s += x[i] * x[i];
+  return sqrt(s);
+}
+
+// ------------------------------------------------------------------ 6x6 steps (one thread)
+// GNOptimization :270-329
+__device__ void gn_step(SolveState* st, const double* tot, const SolveParams& sp) {
+  int rows = (int)tot[28];
+  st->gn_iters += 1;
+  if (rows < sp.gn_min_rows) return;
+  st->cost = tot[27];  // "not enough feature": pose untouched, loop goes on
+  double H[36], g[6], mg[6], X[6];
+  unpack_normal(tot, H, g);
+  for (int i = 0; i < 6; ++i) mg[i] = -g[i];
+  cpqr_solve<6, 6>(H, mg, X);
+  if (sp.iter == 0) {
+    double w[6], V[36], V2[36], Vi[36];
+    jacobi_eig<6>(H, w, V);
+    for (int i = 0; i < 36; ++i) V2[i] = V[i];
+    int deg = 0;
+    float thresh = 100;
+    for (int i = 5; i >= 0; --i) {  // literal: walks down from the LARGEST eigenvalue (:289-302)
+      if (w[i] < thresh) {
+        for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0.0;
+        deg = 1;
+      } else {
+        break;
+      }
+    }
+    invert6(V, Vi);
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) {
+        double s = 0;
+        for (int k = 0; k < 6; ++k) s += Vi[i * 6 + k] * V2[k * 6 + j];
+        st->gn_map[i * 6 + j] = s;
+      }
+    st->gn_degenerate = deg;
+  }
+  if (st->gn_degenerate) {
+    double Y[6];
+    for (int i = 0; i < 6; ++i) {
+      double s = 0;
+      for (int k = 0; k < 6; ++k) s += st->gn_map[i * 6 + k] * X[k];
+      Y[i] = s;
+    }
+    for (int i = 0; i < 6; ++i) X[i] = Y[i];
+  }
+  st->x[4] += X[3];
+  st->x[5] += X[4];
+  st->x[6] += X[5];
+  d3 dr = mk3(X[0], X[1], X[2]);
+  double dn = nrm3(dr);
+  d3 axis = dn > 0.0 ? mk3(dr.x / dn, dr.y / dn, dr.z / dn) : dr;
+  double ang = dn / 2;  // AngleAxisd(|d|/2, d^) :317
+  double sh = sin(0.5 * ang), ch = cos(0.5 * ang);
+  quat dq;
+  dq.x = sh * axis.x;
+  dq.y = sh * axis.y;
+  dq.z = sh * axis.z;
+  dq.w = ch;
+  quat q;
+  q.x = st->x[0];
+  q.y = st->x[1];
+  q.z = st->x[2];
+  q.w = st->x[3];
+  q = qmul(q, dq);
+  st->x[0] = q.x;
+  st->x[1] = q.y;
+  st->x[2] = q.z;
+  st->x[3] = q.w;
+  float deltaR = (float)(dn / 2);
+  float deltaT = (float)sqrt(pow(X[3] * 100, 2.0) + pow(X[4] * 100, 2.0) + pow(X[5] * 100, 2.0));
+  if (deltaR < 0.0009 && deltaT < 0.05) st->gn_done = 1;
+}
+
+__device__ __forceinline__ double grad_max(const double* g) {
+  double m = 0;
+  for (int j = 0; j < 6; ++j) m = fmax(m, fabs(g[j]));
+  return m;
+}
+
+// LevenbergMarquardtStrategy::ComputeStep + TrustRegionMinimizer::ComputeTrustRegionStep (Ceres 1.14
+// restated, see oracle): propose the next candidate, consuming iterations on invalid steps
+__device__ void lm_propose(SolveState* st, const SolveParams& sp) {
+  while (true) {
+    if (st->lm_iter >= sp.lm_max_iters) {
+      st->lm_active = 0;
+      return;
+    }
+    st->lm_iter += 1;
+    st->lm_steps_total += 1;
+    double Hs[36], gs[6], A[36], y[6], step[6];
+    for (int i = 0; i < 6; ++i) {
+      gs[i] = st->scale[i] * st->g[i];
+      for (int j = 0; j < 6; ++j) Hs[i * 6 + j] = st->scale[i] * st->H[i * 6 + j] * st->scale[j];
+    }
+    for (int i = 0; i < 36; ++i) A[i] = Hs[i];
+    for (int j = 0; j < 6; ++j) {
+      double dj = fmin(fmax(Hs[j * 6 + j], 1e-6), 1e32);
+      A[j * 6 + j] += dj / st->radius;
+    }
+    bool ok = spd_solve6(A, gs, y);
+    double mcc = 0.0;
+    if (ok) {
+      for (int j = 0; j < 6; ++j) {
+        step[j] = -y[j];
+        if (!isfinite(step[j])) ok = false;
+      }
+    }
+    if (ok) {
+      double sg = 0, sHs = 0;
+      for (int i = 0; i < 6; ++i) {
+        sg += step[i] * gs[i];
+        double row = 0;
+        for (int j = 0; j < 6; ++j) row += Hs[i * 6 + j] * step[j];
+        sHs += step[i] * row;
+      }
+      mcc = -(sg + 0.5 * sHs);
+    }
+    if (!ok || !(mcc > 0.0)) {
+      st->lm_invalid += 1;
+      if (st->lm_invalid >= 5) {
+        st->lm_active = 0;
+        return;
+      }
+      st->radius *= 0.5;
+      if (st->radius < 1e-32) {
+        st->lm_active = 0;
+        return;
+      }
+      continue;
+    }
+    st->lm_invalid = 0;
+    double delta[6];
+    for (int j = 0; j < 6; ++j) delta[j] = step[j] * st->scale[j];
+    se3_plus(st->x, delta, st->cand);
+    st->model_change = mcc;
+    return;
+  }
+}
+
+// TrustRegionMinimizer::IterationZero: state of a fresh ceres::Solve at x
+__device__ void lm_begin(SolveState* st, const double* tot, const SolveParams& sp) {
+  unpack_normal(tot, st->H, st->g);
+  st->cost = tot[27];
+  st->lm_iter = 0;
+  st->lm_invalid = 0;
+  st->radius = 1e4;
+  st->decrease = 2.0;
+  for (int j = 0; j < 6; ++j) st->scale[j] = 1.0 / (1.0 + sqrt(st->H[j * 6 + j]));
+  st->x_norm = norm7(st->x);
+  st->lm_active = 1;
+  if (tot[28] == 0.0 || grad_max(st->g) <= 1e-10) {
+    st->lm_active = 0;
+    return;
+  }
+  lm_propose(st, sp);
+}
+
+// the part of TrustRegionMinimizer::Minimize after the candidate has been evaluated
+__device__ void lm_update(SolveState* st, const double* tot, const SolveParams& sp) {
+  double cand_cost = tot[27];
+  double diff[7];
+  for (int i = 0; i < 7; ++i) diff[i] = st->x[i] - st->cand[i];
+  if (norm7(diff) <= 1e-8 * (st->x_norm + 1e-8)) {  // parameter tolerance: candidate not taken
+    st->lm_active = 0;
+    return;
+  }
+  double cc = st->cost - cand_cost;
+  if (fabs(cc) <= 1e-6 * st->cost) {  // function tolerance: candidate not taken
+    st->lm_active = 0;
+    return;
+  }
+  double rho = cc / st->model_change;
+  if (rho > 1e-3) {
+    for (int i = 0; i < 7; ++i) st->x[i] = st->cand[i];
+    st->x_norm = norm7(st->x);
+    unpack_normal(tot, st->H, st->g);
+    st->cost = cand_cost;
+    st->lm_steps_accepted += 1;
+    double f = 1.0 - pow(2.0 * rho - 1.0, 3.0);
+    st->radius = st->radius / fmax(1.0 / 3.0, f);
+    st->radius = fmin(1e16, st->radius);
+    st->decrease = 2.0;
+    if (grad_max(st->g) <= 1e-10) {
+      st->lm_active = 0;
+      return;
+    }
+  } else {
+    st->radius = st->radius / st->decrease;
+    st->decrease *= 2.0;
+  }
+  if (st->radius < 1e-32) {
+    st->lm_active = 0;
+    return;
+  }
+  lm_propose(st, sp);
+}
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(MATCH_BLOCK) k_match(const float4* __restrict__ feat, const int* __restrict__ counts,
+                                                       MapPair maps, int has_edge_map, int has_surf_map,
+                                                       SolveState* __restrict__ st, double* __restrict__ rec,
+                                                       uint8_t* __restrict__ okv, int rec_stride,
+                                                       double* __restrict__ partial, SolveParams sp) {
+  __shared__ double tot[LM_NSUM];
+  if (sp.solver == LMSF_SOLVER_GN && st->gn_done) return;
+  const int n_e = counts[0], n_s = counts[1];
+  const int i = blockIdx.x * MATCH_BLOCK + threadIdx.x;
+  quat q;
+  q.x = st->x[0];
+  q.y = st->x[1];
+  q.z = st->x[2];
+  q.w = st->x[3];
+  d3 t = mk3(st->x[4], st->x[5], st->x[6]);
+  Acc acc;
+  acc_zero(acc);
+  if (i < n_e + n_s) {
+    const bool is_edge = i < n_e;
+    float4 f = feat[i];
+    d3 pl = mk3((double)f.x, (double)f.y, (double)f.z);
+    d3 pw = add3(qrot(q, pl), t);
+    float px = (float)pw.x, py = (float)pw.y, pz = (float)pw.z;
+    bool ok = false;
+    Top5 nb;
+    if (is_edge) {
+      if (has_edge_map) {
+        knn5(maps.edge, px, py, pz, nb);
+        if (nb.full()) {
+          d3 n, a, b;
+          double r;
+          ok = fit_edge(maps.edge_cat, nb, px, py, pz, n, r, a, b);
+          if (ok) {
+            if (sp.solver == LMSF_SOLVER_GN) {
+              double R[9];
+              quat_to_mat(q, R);
+              gn_row(R, pl, n, r, acc);
+            } else {
+              rec[0 * rec_stride + i] = a.x;
+              rec[1 * rec_stride + i] = a.y;
+              rec[2 * rec_stride + i] = a.z;
+              rec[3 * rec_stride + i] = b.x;
+              rec[4 * rec_stride + i] = b.y;
+              rec[5 * rec_stride + i] = b.z;
+              edge_factor(q, t, pl, a, b, sp.huber, acc);
+            }
+          }
+        }
+      }
+    } else {
+      if (has_surf_map) {
+        knn5(maps.surf, px, py, pz, nb);
+        if (nb.full()) {
+          d3 n;
+          double D, r;
+          ok = fit_surf(maps.surf_cat, nb, px, py, pz, n, D, r);
+          if (ok) {
+            if (sp.solver == LMSF_SOLVER_GN) {
+              double R[9];
+              quat_to_mat(q, R);
+              gn_row(R, pl, n, r, acc);
+            } else {
+              rec[0 * rec_stride + i] = n.x;
+              rec[1 * rec_stride + i] = n.y;
+              rec[2 * rec_stride + i] = n.z;
+              rec[3 * rec_stride + i] = D;
+              surf_factor(q, t, pl, n, D, sp.huber, acc);
+            }
+          }
+        }
+      }
+    }
+    okv[i] = ok ? 1 : 0;
+    if (ok && is_edge) acc.v[29] += 1.0;
+  }
+  if (!reduce_grid(acc, partial, st, tot)) return;
+  if (threadIdx.x == 0) {
+    st->n_edge_ok = (int)tot[29];
+    st->n_surf_ok = (int)tot[28] - (int)tot[29];
+    double t2[LM_NSUM];
+    for (int k = 0; k < LM_NSUM; ++k) t2[k] = tot[k];
+    if (sp.solver == LMSF_SOLVER_GN)
+      gn_step(st, t2, sp);
+    else
+      lm_begin(st, t2, sp);
+  }
+}
+
+__global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(const float4* __restrict__ feat,
+                                                         const int* __restrict__ counts, SolveState* __restrict__ st,
+                                                         const double* __restrict__ rec,
+                                                         const uint8_t* __restrict__ okv, int rec_stride,
+                                                         double* __restrict__ partial, SolveParams sp) {
+  __shared__ double tot[LM_NSUM];
+  if (!st->lm_active) return;
+  const int n_e = counts[0], n_s = counts[1];
+  const int i = blockIdx.x * MATCH_BLOCK + threadIdx.x;
+  quat q;
+  q.x = st->cand[0];
+  q.y = st->cand[1];
+  q.z = st->cand[2];
+  q.w = st->cand[3];
+  d3 t = mk3(st->cand[4], st->cand[5], st->cand[6]);
+  Acc acc;
+  acc_zero(acc);
+  if (i < n_e + n_s && okv[i]) {
+    float4 f = feat[i];
+    d3 pl = mk3((double)f.x, (double)f.y, (double)f.z);
+    if (i < n_e) {
+      d3 a = mk3(rec[0 * rec_stride + i], rec[1 * rec_stride + i], rec[2 * rec_stride + i]);
+      d3 b = mk3(rec[3 * rec_stride + i], rec[4 * rec_stride + i], rec[5 * rec_stride + i]);
+      edge_factor(q, t, pl, a, b, sp.huber, acc);
+    } else {
+      d3 n = mk3(rec[0 * rec_stride + i], rec[1 * rec_stride + i], rec[2 * rec_stride + i]);
+      surf_factor(q, t, pl, n, rec[3 * rec_stride + i], sp.huber, acc);
+    }
+  }
+  if (!reduce_grid(acc, partial, st, tot)) return;
+  if (threadIdx.x == 0) {
+    double t2[LM_NSUM];
+    for (int k = 0; k < LM_NSUM; ++k) t2[k] = tot[k];
+    lm_update(st, t2, sp);
+  }
+}
+
+__global__ void k_state_init(SolveState* st, const double* __restrict__ pose) {
+  if (threadIdx.x != 0) return;
+  for (int i = 0; i < 7; ++i) st->x[i] = st->cand[i] = pose[i];
+  st->cost = 0;
+  st->n_edge_ok = st->n_surf_ok = 0;
+  st->gn_done = st->gn_degenerate = st->gn_iters = 0;
+  st->lm_active = 0;
+  st->lm_iter = st->lm_invalid = 0;
+  st->lm_steps_total = st->lm_steps_accepted = 0;
+  st->ticket = 0u;
+}
+
+// ------------------------------------------------------------------ test hooks
+__global__ void __launch_bounds__(128) k_knn_hook(MapView mv, const float* __restrict__ q, int nq,
+                                                  int* __restrict__ idx, float* __restrict__ d2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  Top5 nb;
+  knn5(mv, q[3 * i], q[3 * i + 1], q[3 * i + 2], nb);
+  for (int k = 0; k < 5; ++k) {
+    bool in = nb.id[k] >= 0;
+    idx[5 * i + k] = in ? nb.id[k] : -1;
+    d2[5 * i + k] = in ? nb.d[k] : __int_as_float(0x7f800000);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_match_hook(MapView mv, const float4* __restrict__ cat, int kind,
+                                                    const float* __restrict__ q, int nq, uint8_t* __restrict__ okv,
+                                                    double* __restrict__ out10) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
+  Top5 nb;
+  knn5(mv, px, py, pz, nb);
+  double o[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  bool ok = false;
+  if (nb.full()) {
+    if (kind == LMSF_KIND_EDGE) {
+      d3 n, a, b;
+      double r;
+      ok = fit_edge(cat, nb, px, py, pz, n, r, a, b);
+      if (ok) {
+        o[0] = n.x, o[1] = n.y, o[2] = n.z, o[3] = r;
+        o[4] = a.x, o[5] = a.y, o[6] = a.z, o[7] = b.x, o[8] = b.y, o[9] = b.z;
+      }
+    } else {
+      d3 n;
+      double D, r;
+      ok = fit_surf(cat, nb, px, py, pz, n, D, r);
+      if (ok) o[0] = n.x, o[1] = n.y, o[2] = n.z, o[3] = r, o[4] = D;
+    }
+  }
+  okv[i] = ok ? 1 : 0;
+  for (int k = 0; k < 10; ++k) out10[10 * i + k] = o[k];
+}
+
+// ------------------------------------------------------------------ host side
+static MapView view_of(const MapIndex& m) {
+  MapView v;
+  v.sorted = m.sorted;
+  v.table = m.table;
+  v.fine_start = m.fine_start;
+  v.dev = m.dev;
+  return v;
+}
+
+int solve_alloc(Ctx* c) {
+  size_t cap = (size_t)c->prm.max_points;
+  LM_CUDA(cudaMalloc(&c->d_rec, 6 * cap * sizeof(double)));
+  LM_CUDA(cudaMalloc(&c->d_ok, cap));
+  c->partial_blocks = div_up((int)cap, MATCH_BLOCK);
+  LM_CUDA(cudaMalloc(&c->d_partial, (size_t)c->partial_blocks * LM_NSUM * sizeof(double)));
+  LM_CUDA(cudaMalloc(&c->d_state, sizeof(SolveState)));
+  LM_CUDA(cudaMemset(c->d_state, 0, sizeof(SolveState)));
+  return LMSF_OK;
+}
+
+void solve_free(Ctx* c) {
+  cudaFree(c->d_rec);
+  cudaFree(c->d_ok);
+  cudaFree(c->d_partial);
+  cudaFree(c->d_state);
+}
+
+int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2) {
+  if (!c->map[kind].ready) return LMSF_ERR_STATE;
+  if (nq == 0) return LMSF_OK;
+  LM_LAUNCH(c, k_knn_hook, div_up(nq, 128), 128, 0, view_of(c->map[kind]), d_q, nq, d_idx, d_d2);
+  LM_CUDA(cudaGetLastError());
+  return LMSF_OK;
+}
+
+int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double* d_out10) {
+  if (!c->map[kind].ready) return LMSF_ERR_STATE;
+  if (nq == 0) return LMSF_OK;
+  LM_LAUNCH(c, k_match_hook, div_up(nq, 128), 128, 0, view_of(c->map[kind]), c->map[kind].cat, kind, d_q, nq, d_ok,
+            d_out10);
+  LM_CUDA(cudaGetLastError());
+  return LMSF_OK;
+}
+
+// Enqueue one whole solve on the stream, then read pose + statistics back (one sync).
+// upper = host-side upper bound of n_edge + n_surf (the device counts are authoritative).
+int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upper, int outer_count) {
+  if (upper < 0 || outer_count < 0) return LMSF_ERR_INVALID;
+  if (upper > c->prm.max_points) return LMSF_ERR_CAPACITY;
+  SolveParams sp;
+  sp.solver = solver;
+  sp.iter = 0;
+  sp.lm_max_iters = c->prm.lm_inner_iters;
+  sp.gn_min_rows = 10;
+  sp.huber = (double)c->prm.huber_delta;
+  MapPair maps;
+  maps.edge = view_of(c->map[0]);
+  maps.surf = view_of(c->map[1]);
+  maps.edge_cat = c->map[0].cat;
+  maps.surf_cat = c->map[1].cat;
+  const int he = c->map[0].ready ? 1 : 0, hs = c->map[1].ready ? 1 : 0;
+  const int grid = div_up(upper > 0 ? upper : 1, MATCH_BLOCK);
+  const int stride = c->prm.max_points;
+  for (int i = 0; i < 7; ++i) c->h_pose[i] = pose[i];
+  LM_CUDA(cudaMemcpyAsync(c->d_state->cand, c->h_pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  LM_LAUNCH(c, k_state_init, 1, 32, 0, c->d_state, c->d_state->cand);
+  const double alg_bytes = 16.0 * ((double)upper + (double)c->map[0].n_host + (double)c->map[1].n_host) + 216.0;
+  if (solver == LMSF_SOLVER_GN) {
+    for (int it = 0; it < outer_count; ++it) {
+      sp.iter = it;
+      StageScope scope(c, LMSF_STAGE_MATCH);
+      LM_LAUNCH(c, k_match, grid, MATCH_BLOCK, 0, c->d_feat, c->ex.counts, maps, he, hs, c->d_state, c->d_rec,
+                c->d_ok, stride, c->d_partial, sp);
+      c->match_bytes += alg_bytes;
+    }
+  } else {
+    for (int it = 0; it < outer_count; ++it) {
+      sp.iter = it;
+      {
+        StageScope scope(c, LMSF_STAGE_MATCH);
+        LM_LAUNCH(c, k_match, grid, MATCH_BLOCK, 0, c->d_feat, c->ex.counts, maps, he, hs, c->d_state, c->d_rec,
+                  c->d_ok, stride, c->d_partial, sp);
+        c->match_bytes += alg_bytes;
+      }
+      StageScope scope(c, LMSF_STAGE_SOLVE);
+      for (int k = 0; k < c->prm.lm_inner_iters; ++k)
+        LM_LAUNCH(c, k_lm_eval, grid, MATCH_BLOCK, 0, c->d_feat, c->ex.counts, c->d_state, c->d_rec, c->d_ok, stride,
+                  c->d_partial, sp);
+    }
+  }
+  LM_CUDA(cudaGetLastError());
+  LM_CUDA(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaMemcpyAsync(c->h_ints + 32, c->ex.counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  c->n_edge = c->h_ints[32];
+  c->n_surf = c->h_ints[33];
+  const SolveState& s = *c->h_state;
+  for (int i = 0; i < 7; ++i) pose[i] = s.x[i];
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    stats->n_edge_matched = s.n_edge_ok;
+    stats->n_surf_matched = s.n_surf_ok;
+    stats->final_cost = s.cost;
+    if (solver == LMSF_SOLVER_GN) {
+      stats->outer_iters = s.gn_iters;
+      stats->converged = s.gn_done;
+      stats->degenerate = s.gn_degenerate;
+    } else {
+      stats->outer_iters = outer_count;
+      stats->lm_steps_total = s.lm_steps_total;
+      stats->lm_steps_accepted = s.lm_steps_accepted;
+    }
+  }
+  return LMSF_OK;
+}
+
+}  // namespace lm

@@ -1,0 +1,410 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Bars (BASELINE.json north_star): feature labels and voxel membership bit-exact, kNN index
+sets identical (the oracle and the kernel share the (distance, index) tie order, so they are
+compared exactly), per-scan pose within 1e-4 m and 1e-5 rad."""
+import numpy as np
+import pytest
+
+from conftest import pose_err
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_M = 1e-4
+POSE_TOL_RAD = 1e-5
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def ctxs(gpu_lib, oracle_lib):
+    made = []
+
+    def make(**kw):
+        okw = dict(kw)
+        okw.setdefault("oracle_knn_mode", 0)
+        okw.setdefault("oracle_threads", 8)
+        g = gpu_lib.context(0, **kw)
+        o = oracle_lib.context(0, **okw)
+        made.extend([g, o])
+        return g, o
+
+    yield make
+    for c in made:
+        c.close()
+
+
+# ---------------------------------------------------------------- a1 feature extraction
+@pytest.mark.parametrize("name,ns", [("vlp16", 16), ("hdl64", 64)])
+@pytest.mark.parametrize("k", [0, 7])
+def test_extract_labels_bit_exact(ctxs, sweeps, name, ns, k):
+    g, o = ctxs(n_scans=ns)
+    sw = sweeps(name, k)
+    lg, eg, sg = g.extract_features(sw)
+    lo, eo, so = o.extract_features(sw)
+    assert np.array_equal(lg, lo)
+    assert eg.shape == eo.shape and sg.shape == so.shape
+    assert np.array_equal(bits(eg), bits(eo))
+    assert np.array_equal(bits(sg), bits(so))
+    assert (lg == 1).sum() == len(eg) and (lg == 2).sum() == len(sg)
+
+
+def test_extract_ragged_and_degenerate_inputs(ctxs, sweeps, synth):
+    g, o = ctxs(n_scans=16)
+    cases = {
+        "dropout": sweeps("vlp16", 3, dropout=0.3),
+        "noiseless": sweeps("vlp16", 1, noise=0.0),
+        "empty": np.zeros((0, 4), np.float32),
+        "one_point": np.array([[5, 0, 0, 0]], np.float32),
+        "short_rings": sweeps("vlp16", 2)[: 16 * 15],          # < 20 points per ring: all skipped
+        "ring_of_25": sweeps("vlp16", 2)[: 16 * 25],
+        "all_out_of_range": sweeps("vlp16", 2) * np.array([0.01, 0.01, 0.01, 1], np.float32),
+    }
+    nan_sw = sweeps("vlp16", 4).copy()
+    nan_sw[::97, 1] = np.nan
+    cases["nan_points"] = nan_sw
+    for name, sw in cases.items():
+        lg, eg, sg = g.extract_features(sw)
+        lo, eo, so = o.extract_features(sw)
+        assert np.array_equal(lg, lo), name
+        assert np.array_equal(bits(eg), bits(eo)) and np.array_equal(bits(sg), bits(so)), name
+
+
+def test_extract_without_bad_point_removal_and_other_thresholds(ctxs, sweeps):
+    sw = sweeps("hdl64", 5)
+    for kw in (dict(remove_bad_points=0), dict(edge_thresh=0.05), dict(min_range=5.0, max_range=25.0)):
+        g, o = ctxs(n_scans=64, **kw)
+        lg, eg, sg = g.extract_features(sw)
+        lo, eo, so = o.extract_features(sw)
+        assert np.array_equal(lg, lo), kw
+        assert np.array_equal(bits(eg), bits(eo)) and np.array_equal(bits(sg), bits(so)), kw
+
+
+def test_extract_single_long_ring(ctxs):
+    """All points on one ring (P = 40 000): sectors longer than the shared-memory sort (global path)."""
+    rng = np.random.default_rng(5)
+    n = 40000
+    az = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    r = 10 + 3 * np.sign(np.sin(9 * az)) + rng.normal(0, 0.01, n)
+    pts = np.stack([r * np.cos(az), r * np.sin(az), np.zeros(n), az], 1).astype(np.float32)
+    g, o = ctxs(n_scans=16)
+    lg, eg, sg = g.extract_features(pts)
+    lo, eo, so = o.extract_features(pts)
+    assert (lo == 1).sum() > 0
+    assert np.array_equal(lg, lo)
+    assert np.array_equal(bits(eg), bits(eo)) and np.array_equal(bits(sg), bits(so))
+
+
+# ---------------------------------------------------------------- a2 voxel grid
+@pytest.mark.parametrize("leaf", [0.1, 0.2, 0.4, 0.8])
+def test_voxel_membership_bit_exact(ctxs, sweeps, leaf):
+    g, o = ctxs(n_scans=64)
+    sw = sweeps("hdl64", 2)
+    vg, mg = g.voxel_downsample(sw, leaf)
+    vo, mo = o.voxel_downsample(sw, leaf)
+    assert np.array_equal(mg, mo)
+    assert np.array_equal(bits(vg), bits(vo))
+
+
+def test_voxel_edge_cases(ctxs, sweeps):
+    g, o = ctxs(n_scans=16)
+    sw = sweeps("vlp16", 0)
+    nan_sw = sw.copy()
+    nan_sw[::50, 0] = np.nan
+    nan_sw[7, 2] = np.inf
+    cases = {
+        "empty": (np.zeros((0, 4), np.float32), 0.2),
+        "single": (sw[:1], 0.2),
+        "all_same_voxel": (sw[:500] * np.float32(1e-4), 1.0),
+        "overflow_fallback": (sw, 1e-3),      # dx*dy*dz > INT32_MAX: output = input
+        "nan": (nan_sw, 0.3),
+        "all_nan": (np.full((10, 4), np.nan, np.float32), 0.3),
+        "negative_coords": (sw - np.float32(100.0), 0.25),
+    }
+    for name, (pts, leaf) in cases.items():
+        vg, mg = g.voxel_downsample(pts, leaf)
+        vo, mo = o.voxel_downsample(pts, leaf)
+        assert np.array_equal(mg, mo), name
+        assert vg.shape == vo.shape, name
+        assert np.array_equal(bits(vg), bits(vo)), name
+
+
+def test_voxel_properties_full_size(gpu_lib, synth):
+    """Size-independent properties on a 10-sweep HDL-64 window (1.3 M points, no oracle)."""
+    g = gpu_lib.context(0, n_scans=64)
+    sensor = synth.hdl64()
+    pts = np.concatenate([synth.make_sweep(sensor, k) for k in range(10)])
+    leaf = 0.4
+    v, m = g.voxel_downsample(pts, leaf)
+    assert m.min() == 0 and m.max() == len(v) - 1
+    cnt = np.bincount(m, minlength=len(v))
+    assert cnt.min() >= 1 and cnt.sum() == len(pts)
+    # every centroid is the mean of its members (checked in float64) and lies in its members' bbox
+    s = np.zeros((len(v), 4))
+    np.add.at(s, m, pts.astype(np.float64))
+    assert np.allclose(s / cnt[:, None], v, rtol=0, atol=2e-4)
+    # members of one voxel share floor(p / leaf)
+    key = np.floor(pts[:, :3] * np.float32(1.0 / leaf)).astype(np.int64)
+    first = np.zeros((len(v), 3), np.int64)
+    first[m] = key
+    assert np.array_equal(first[m], key)
+    # output ordered by voxel index: z-major, then y, then x
+    kv = first - first.min(0)
+    lin = (kv[:, 2] * (kv[:, 1].max() + 1) + kv[:, 1]) * (kv[:, 0].max() + 1) + kv[:, 0]
+    assert np.all(np.diff(lin) > 0)
+    g.close()
+
+
+# ---------------------------------------------------------------- a3 kNN
+def _map_and_queries(sweeps, synth, name, nq_step):
+    sensor = synth.sensor_by_name(name)
+    rel = []
+    for k in range(4):
+        sw = sweeps(name, k)
+        T = synth.qt_to_mat(synth.rel_gt_pose(k))
+        rel.append(np.concatenate([(sw[:, :3] @ T[:3, :3].T + T[:3, 3]).astype(np.float32), sw[:, 3:]], 1))
+    m = np.ascontiguousarray(np.concatenate(rel))
+    T = synth.qt_to_mat(synth.rel_gt_pose(5))
+    q = (sweeps(name, 5)[::nq_step, :3] @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+    return m, np.ascontiguousarray(q)
+
+
+@pytest.mark.parametrize("name,ns,step", [("vlp16", 16, 3), ("hdl64", 64, 9)])
+def test_knn5_identical_to_brute_force(ctxs, sweeps, synth, name, ns, step):
+    g, o = ctxs(n_scans=ns, oracle_knn_mode=1, max_map_points=600000)
+    m, q = _map_and_queries(sweeps, synth, name, step)
+    for kind in (0, 1):
+        g.map_set(kind, m)
+        o.map_set(kind, m)
+        ig, dg = g.knn5(kind, q)
+        io, do = o.knn5(kind, q)
+        assert np.array_equal(ig, io)
+        assert np.array_equal(bits(dg), bits(do))
+    assert (io[:, 4] >= 0).mean() > 0.5   # most queries have 5 neighbours within the radius
+
+
+def test_knn5_sparse_ties_and_outside_queries(ctxs):
+    g, o = ctxs(n_scans=16, oracle_knn_mode=1)
+    rng = np.random.default_rng(11)
+    # lattice map: many exact distance ties; duplicated points: ties at distance 0
+    ax = np.arange(-3, 3.01, 0.5, dtype=np.float32)
+    lat = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    lat = np.concatenate([lat, lat[:100]])
+    m = np.concatenate([lat, np.zeros((len(lat), 1), np.float32)], 1)
+    q = np.concatenate([
+        lat[::5] + np.float32(0.25),                     # cell corners / boundaries
+        lat[::7],                                        # on map points
+        rng.uniform(-4, 4, (500, 3)).astype(np.float32),
+        rng.uniform(50, 60, (20, 3)).astype(np.float32),  # far outside the grid
+        np.array([[-3.0, -3.0, -3.0], [3.0, 3.0, 3.0], [1e7, 0, 0]], np.float32),
+    ])
+    for kind in (0, 1):
+        g.map_set(kind, m)
+        o.map_set(kind, m)
+        ig, dg = g.knn5(kind, q)
+        io, do = o.knn5(kind, q)
+        assert np.array_equal(ig, io)
+        assert np.array_equal(bits(dg), bits(do))
+    # fewer than five points in the map: every query is rejected
+    g.map_set(0, m[:3])
+    o.map_set(0, m[:3])
+    ig, _ = g.knn5(0, q[:50])
+    io, _ = o.knn5(0, q[:50])
+    assert np.array_equal(ig, io) and (ig[:, 4] == -1).all()
+
+
+# ---------------------------------------------------------------- a4 matchers
+@pytest.mark.parametrize("name,ns,step", [("vlp16", 16, 2), ("hdl64", 64, 11)])
+def test_match_geometry(ctxs, sweeps, synth, name, ns, step):
+    g, o = ctxs(n_scans=ns, max_map_points=600000)
+    m, q = _map_and_queries(sweeps, synth, name, step)
+    # voxel-thin the map so that planes / lines are well conditioned and both outcomes occur
+    mv, _ = o.voxel_downsample(m, 0.3)
+    for kind in (0, 1):
+        g.map_set(kind, mv)
+        o.map_set(kind, mv)
+        okg, outg = g.match(kind, q)
+        oko, outo = o.match(kind, q)
+        assert np.array_equal(okg, oko)
+        assert 0 < oko.sum() < len(q) or kind == 1
+        # same IEEE operation sequence on both sides: expected bit-identical; the hard bar is 1e-12
+        assert np.allclose(outg, outo, rtol=0, atol=1e-12)
+        assert np.array_equal(outg, outo)
+
+
+# ---------------------------------------------------------------- a5 solvers
+def _scene(ctx_pair, sweeps, name, k_map, k_scan, leaf=(0.0, 0.0)):
+    g, o = ctx_pair
+    _, e0, s0 = o.extract_features(sweeps(name, k_map))
+    if leaf[0] > 0:
+        e0, _ = o.voxel_downsample(e0, leaf[0])
+    if leaf[1] > 0:
+        s0, _ = o.voxel_downsample(s0, leaf[1])
+    for c in (g, o):
+        c.map_set(0, e0)
+        c.map_set(1, s0)
+    _, e1, s1 = o.extract_features(sweeps(name, k_scan))
+    return e1, s1
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+@pytest.mark.parametrize("name,ns,leaf", [("vlp16", 16, (0.2, 0.4)), ("vlp16", 16, (0.0, 0.0)), ("hdl64", 64, (0.0, 0.0))])
+def test_register_pose_parity(ctxs, sweeps, name, ns, leaf, solver):
+    pair = ctxs(n_scans=ns)
+    e1, s1 = _scene(pair, sweeps, name, 0, 2, leaf)
+    g, o = pair
+    pg, sg = g.register(e1, s1, solver=solver)
+    po, so = o.register(e1, s1, solver=solver)
+    dt, dr = pose_err(pg, po)
+    assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (dt, dr, sg, so)
+    assert sg["n_edge_matched"] == so["n_edge_matched"] and sg["n_surf_matched"] == so["n_surf_matched"]
+    assert sg["outer_iters"] == so["outer_iters"]
+    assert sg["lm_steps_total"] == so["lm_steps_total"] and sg["lm_steps_accepted"] == so["lm_steps_accepted"]
+    assert sg["converged"] == so["converged"] and sg["degenerate"] == so["degenerate"]
+    assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-9 * max(1.0, abs(so["final_cost"]))
+
+
+def test_register_author_scenario(ctxs, sweeps, synth):
+    """The reference author's intended smoke test (src/test/registration/feature_registration_test.cpp:73-112):
+    map = scan moved by yaw 5 deg, t = (0.9, 0.4, 0.5), voxel 0.1 / 0.2, GN from identity."""
+    pair = ctxs(n_scans=16)
+    g, o = pair
+    _, e, s = o.extract_features(sweeps("vlp16", 0))
+    yaw = np.radians(5.0)
+    R = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
+    t = np.array([0.9, 0.4, 0.5])
+    mv = lambda c: np.concatenate([(c[:, :3] @ R.T + t).astype(np.float32), c[:, 3:]], 1)
+    em, _ = o.voxel_downsample(mv(e), 0.1)
+    sm, _ = o.voxel_downsample(mv(s), 0.2)
+    for c in pair:
+        c.map_set(0, em)
+        c.map_set(1, sm)
+    for solver in (0, 1):
+        for c in pair:
+            c.set_lm_outer(10)
+        pg, sg = g.register(e, s, solver=solver)
+        po, so = o.register(e, s, solver=solver)
+        dt, dr = pose_err(pg, po)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (solver, dt, dr)
+
+
+def test_register_degenerate_and_starved(ctxs, sweeps):
+    """Corridor-like starvation: too few matches (GN 'not enough feature' path) and the GN
+    degeneracy remap (floor-only map: three unobservable directions)."""
+    pair = ctxs(n_scans=16)
+    g, o = pair
+    _, e1, s1 = o.extract_features(sweeps("vlp16", 1))
+    # floor-only map
+    _, e0, s0 = o.extract_features(sweeps("vlp16", 0))
+    floor = s0[s0[:, 2] < -1.7]
+    floor, _ = o.voxel_downsample(floor, 0.3)
+    for c in pair:
+        c.map_set(0, floor[:10])
+        c.map_set(1, floor)
+    pg, sg = g.register(e1, s1, solver=0)
+    po, so = o.register(e1, s1, solver=0)
+    assert sg["degenerate"] == so["degenerate"]
+    dt, dr = pose_err(pg, po)
+    assert dt < 1e-3 and dr < 1e-4, (dt, dr)
+    # starved: 7 scan points only
+    pg, sg = g.register(e1[:3], s1[:4], solver=0)
+    po, so = o.register(e1[:3], s1[:4], solver=0)
+    assert sg["outer_iters"] == so["outer_iters"] == 10
+    assert np.array_equal(pg, po)
+    # no features at all
+    z = np.zeros((0, 4), np.float32)
+    for solver in (0, 1):
+        pg, _ = g.register(z, z, solver=solver)
+        po, _ = o.register(z, z, solver=solver)
+        assert np.array_equal(pg, po)
+
+
+# ---------------------------------------------------------------- a6 tracker
+@pytest.mark.parametrize("name,ns,kw,nsweeps", [
+    ("vlp16", 16, dict(map_leaf_edge=0.2, map_leaf_surf=0.4), 14),
+    ("vlp16", 16, dict(), 8),
+    ("vlp16", 16, dict(solver=0, window=3, map_leaf_edge=0.2, map_leaf_surf=0.4), 12),
+    ("vlp16", 16, dict(scan_leaf_edge=0.1, scan_leaf_surf=0.2, map_leaf_edge=0.2, map_leaf_surf=0.4), 6),
+    ("hdl64", 64, dict(), 5),
+])
+def test_tracker_sequence_parity(ctxs, sweeps, synth, name, ns, kw, nsweeps):
+    g, o = ctxs(n_scans=ns, **kw)
+    for k in range(nsweeps):
+        sw = sweeps(name, k)
+        pg, dg, sg = g.tracker_step(sw, 0.1 * k)
+        po, do, so = o.tracker_step(sw, 0.1 * k)
+        dt, dr = pose_err(pg, po)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (k, dt, dr)
+        dt, dr = pose_err(dg, do)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (k, "delta", dt, dr)
+        for key in ("n_edge", "n_surf", "keyframe", "map_edge", "map_surf", "first"):
+            assert sg[key] == so[key], (k, key, sg, so)
+        assert sg["reg"]["outer_iters"] == so["reg"]["outer_iters"]
+    # the local maps agree bit for bit (same keyframes, same fp64 -> fp32 transform)
+    for kind in (0, 1):
+        mg, mo = g.get_map(kind), o.get_map(kind)
+        assert mg.shape == mo.shape
+        assert np.allclose(mg, mo, rtol=0, atol=2e-4)
+
+
+def test_tracker_time_keyframe_prior_and_aux(ctxs, sweeps, synth):
+    g, o = ctxs(n_scans=16, map_leaf_edge=0.2, map_leaf_surf=0.4)
+    stamps = [0.0, 0.1, 11.0, 11.1]           # third sweep triggers the 10 s TIME update
+    for k, t in enumerate(stamps):
+        sw = sweeps("vlp16", 0)                # standing still
+        prior = (0, 0, 0, 1, 0, 0, 0) if k != 3 else (0, 0, 0.001, 0.9999995, 0.01, 0, 0)
+        pg, dg, sg = g.tracker_step(sw, t, prior)
+        po, do, so = o.tracker_step(sw, t, prior)
+        assert sg["keyframe"] == so["keyframe"], (k, sg, so)
+        assert sg["map_surf"] == so["map_surf"] and sg["map_edge"] == so["map_edge"]
+        dt, dr = pose_err(pg, po)
+        assert dt < POSE_TOL_M and dr < POSE_TOL_RAD
+    assert so["keyframe"] in (0, 1, 2)
+    # auxiliary LiDAR registered against the primary's map (ML_System.hpp:304)
+    yaw = np.radians(40.0)
+    Re = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
+    te = np.array([0.03, -0.54, -0.14])
+    aux = synth.make_sweep(synth.vlp16(), 0, extrinsic=(Re, te))
+    guess = synth.pose_to_qt(Re, te + 0.05)
+    pg, sg = g.tracker_register_aux(aux, guess)
+    po, so = o.tracker_register_aux(aux, guess)
+    dt, dr = pose_err(pg, po)
+    assert dt < POSE_TOL_M and dr < POSE_TOL_RAD
+    g.tracker_reset()
+    o.tracker_reset()
+    pg, _, sg = g.tracker_step(sweeps("vlp16", 1), 0.0)
+    assert sg["first"] == 1 and np.allclose(pg, [0, 0, 0, 1, 0, 0, 0])
+
+
+def test_round_trip_full_size(gpu_lib, synth):
+    """HDL-64 full size, no oracle: registering a sweep against the map made of itself from a
+    perturbed prior must come back to identity (encode -> perturb -> decode round trip)."""
+    g = gpu_lib.context(0, n_scans=64)
+    sw = synth.make_sweep(synth.hdl64(), 3)
+    _, e, s = g.extract_features(sw)
+    assert len(e) > 500 and len(s) > 100000
+    g.map_set(0, e)
+    g.map_set(1, s)
+    for solver in (0, 1):
+        g.set_lm_outer(10)
+        p, st = g.register(e, s, pose=(0, 0, 0.004, 0.999992, 0.05, -0.04, 0.02), solver=solver)
+        dt, dr = pose_err(p, (0, 0, 0, 1, 0, 0, 0))
+        assert dt < 2e-3 and dr < 2e-4, (solver, dt, dr, st)
+    g.close()
+
+
+def test_errors_and_capacity(gpu_lib):
+    g = gpu_lib.context(0, n_scans=16, max_points=1000, max_map_points=2000)
+    big = np.ones((1001, 4), np.float32)
+    with pytest.raises(RuntimeError):
+        g.extract_features(big)
+    with pytest.raises(RuntimeError):
+        g.knn5(0, np.zeros((1, 3), np.float32))      # no map yet
+    with pytest.raises(RuntimeError):
+        g.map_set(0, np.ones((2001, 4), np.float32))
+    with pytest.raises(RuntimeError):
+        gpu_lib.context(0, n_scans=17)
+    with pytest.raises(RuntimeError):
+        gpu_lib.context(99)                          # no such device: no CPU fallback
+    g.close()
