@@ -1121,6 +1121,12 @@ int lmsf_oracle_tracker_step(lmsf_oracle_ctx* c, const float* xyzi, int n, doubl
   return 0;
 }
 
+int lmsf_oracle_set_threads(lmsf_oracle_ctx* c, int threads) {
+  if (!c) return -1;
+  c->prm.threads = threads;
+  return 0;
+}
+
 int lmsf_oracle_tracker_reset(lmsf_oracle_ctx* c) {
   if (!c) return -1;
   c->init = false;

@@ -96,6 +96,8 @@ int lmsf_oracle_tracker_step_features(lmsf_oracle_ctx* c, const float* edge_xyzi
                                       double delta[7], double pose_out[7],
                                       lmsf_oracle_track_stats* st);
 int lmsf_oracle_tracker_reset(lmsf_oracle_ctx* c);
+/* oracle only: OpenMP threads used by the match loops from now on (bench.py cpu legs) */
+int lmsf_oracle_set_threads(lmsf_oracle_ctx* c, int threads);
 int lmsf_oracle_tracker_register_aux(lmsf_oracle_ctx* c, const float* xyzi, int n, double pose[7],
                                      lmsf_oracle_reg_stats* st);
 int lmsf_oracle_get_map(lmsf_oracle_ctx* c, int kind, float* xyzi, int cap, int* n);

