@@ -183,15 +183,17 @@ int lmsf_dev_upload(lmsf_ctx* c, void* d_dst, const void* h_src, int64_t bytes);
 
 /* ---- per-stage device timing (CUDA events on the context's stream) -- */
 #define LMSF_STAGE_EXTRACT 0
-#define LMSF_STAGE_MATCH 1    /* kNN + PCA/plane + residual (dominant kernel) */
-#define LMSF_STAGE_SOLVE 2    /* LM/GN evaluation + reduction + 6x6 step kernels */
+#define LMSF_STAGE_MATCH 1    /* k_knn: exact 5-NN over the local-map grid (dominant kernel) */
+#define LMSF_STAGE_SOLVE 2    /* k_lm_eval: LM candidate evaluation + reduction + 6x6 step */
 #define LMSF_STAGE_MAP 3      /* local-map update + index rebuild */
 #define LMSF_STAGE_VOXEL 4
-#define LMSF_N_STAGES 5
+#define LMSF_STAGE_ASSOC 5    /* k_assoc + query sort */
+#define LMSF_STAGE_FIT 6      /* k_fit: PCA/plane fit + residual/Jacobian + reduction + first 6x6 step */
+#define LMSF_N_STAGES 7
 /* enable = 1 records events around every stage (adds host syncs at query time only) */
 int lmsf_profile_enable(lmsf_ctx* c, int enable);
 /* accumulated milliseconds and launch counts per stage since the last reset;
- * bytes = algorithmic bytes of the match kernel launches (16*(F+M)+216 each) */
+ * bytes = algorithmic bytes of the k_knn launches (16*(F+M)+216 each) */
 int lmsf_profile_read(lmsf_ctx* c, double ms[LMSF_N_STAGES], int64_t launches[LMSF_N_STAGES],
                       double* match_alg_bytes, int reset);
 

@@ -2,7 +2,7 @@
 
 The binding is generic over (shared-library path, symbol prefix) because the CPU
 oracle under oracle/ deliberately exports the same entry points with the prefix
-``lmsf_oracle_`` (oracle/lmsf_oracle.h) so the parity tests can drive both through
+``lmsf_oracle_`` (see the header under oracle/) so the parity tests can drive both through
 one wrapper.  This package itself only ever loads the CUDA library
 (``csrc/liblmsf_b200.so``); pointing the binding at the oracle is done by
 tests/, bench.py's cpu_baseline leg and __graft_entry__.smoke() alone.
@@ -16,8 +16,8 @@ import numpy as np
 
 KIND_EDGE, KIND_SURF = 0, 1
 SOLVER_GN, SOLVER_HUBER_LM = 0, 1
-N_STAGES = 5
-STAGE_NAMES = ("extract", "match", "solve", "map", "voxel")
+N_STAGES = 7
+STAGE_NAMES = ("extract", "match", "solve", "map", "voxel", "assoc", "fit")
 
 
 class Params(C.Structure):

@@ -64,9 +64,9 @@ struct ExtractBufs {
 // probe is a single 32-byte sector.
 struct __align__(32) CellRec {
   unsigned long long key;   // packed relative cell coords, ~0 = empty slot
-  unsigned long long mask;  // occupancy of the 4x4x4 fine sub-cells (0.25 m)
+  unsigned long long mask;  // occupancy of the 4x4x4 L1 sub-cells (0.25 m)
   int start, end;           // range in the cell-sorted point array
-  int fine_base;            // first entry of this cell in fine_start[]
+  int fine_base;            // index of this cell's first occupied L1 cell (l1_mask / l1_first)
   int pad;
 };
 
@@ -92,7 +92,10 @@ struct MapIndex {
   unsigned long long* keys_alt = nullptr;  // [cap]
   int* vals = nullptr;                     // [cap]
   int* vals_alt = nullptr;                 // [cap]
-  int* fine_start = nullptr;               // [cap+1]
+  int* l2_start = nullptr;                 // [cap+1] start of every occupied L2 cell
+  int* l1_first = nullptr;                 // [cap+1] first L2 cell of every occupied L1 cell
+  unsigned long long* l1_mask = nullptr;   // [cap] L2 occupancy of every occupied L1 cell
+  int* d_cnt = nullptr;                    // [4] device counters: n2, n1
   uint8_t* flags = nullptr;                // [cap]
   CellRec* table = nullptr;                // [table_cap]
   unsigned table_cap = 0;
@@ -138,8 +141,15 @@ struct Ctx {
   MapIndex map[2];
 
   // per-feature match records (7 doubles SoA) + validity
-  double* d_rec = nullptr;     // [7][max_points]
-  uint8_t* d_ok = nullptr;     // [max_points]
+  double* d_rec = nullptr;     // [6][max_points] edge: a, b   surf: n, D  (by sorted query position)
+  float* d_recf = nullptr;     // [3][max_points] scan point, LiDAR frame
+  uint8_t* d_ok = nullptr;     // [max_points] 0 none, 1 edge, 2 surf
+  unsigned long long* q_keys = nullptr;      // [max_points] query sort keys (cell of the world point)
+  unsigned long long* q_keys_alt = nullptr;
+  int* q_vals = nullptr;                     // [max_points] feature index
+  int* q_vals_alt = nullptr;                 // sorted: position -> feature index
+  float4* d_pw = nullptr;      // [max_points] fp32 world point by feature index
+  int* d_nbr = nullptr;        // [5][max_points] neighbour indices by sorted query position
   double* d_partial = nullptr; // [grid][LM_NSUM]
   int partial_blocks = 0;
   SolveState* d_state = nullptr;
@@ -183,9 +193,10 @@ struct Ctx {
   };
   std::vector<Span> spans;
   std::vector<cudaEvent_t> ev_pool;
-  double prof_ms[LMSF_N_STAGES] = {0, 0, 0, 0, 0};
-  int64_t prof_launch[LMSF_N_STAGES] = {0, 0, 0, 0, 0};
+  double prof_ms[LMSF_N_STAGES] = {0, 0, 0, 0, 0, 0, 0};
+  int64_t prof_launch[LMSF_N_STAGES] = {0, 0, 0, 0, 0, 0, 0};
   double match_bytes = 0;
+  int64_t match_launches = 0;  // correspondence passes (k_assoc + sort + k_knn + k_fit)
 };
 
 struct StageScope {  // records CUDA events around a stage when profiling is on

@@ -1,15 +1,26 @@
-// knn.cuh — device-side exact 5-NN over the local-map hash grid.
+// knn.cuh — device-side exact 5-NN over the local-map grid (three nested cell levels).
 //
 // Replaces pcl::KdTreeFLANN::nearestKSearch(point, 5, ...) as called by
 // EdgeFeatureMatch::Match (registration/FeatureMatch/EdgeFeatureMatch.hpp:38) and
 // SurfFeatureMatch::Match (surfFeatureMatch.hpp:37).  Both callers reject the
 // query unless the 5th squared distance is < search_thresh_ = 1.0
-// (FeatureMatchBase.hpp:29), so a grid of 1 m cells swept over the 27 cells
-// around the query is exact for every query the matchers accept, and a query
-// it cannot fill is one they reject.  A first pass over the 27 fine cells
-// (0.25 m, a 4x4x4 occupancy mask per coarse cell) settles dense regions: it is
-// exact whenever the 5th distance found is < 0.25^2, because cell indices are
-// exact in fp32 for power-of-two cell sizes.
+// (FeatureMatchBase.hpp:29), so only neighbours with d2 < 1.0 are ever needed:
+// the 27 coarse (1 m) cells around the query hold all of them.
+//
+// Levels: L0 = 1 m cells in a hash table; every L0 cell has a 64-bit occupancy
+// mask of its 4x4x4 L1 cells (0.25 m); every occupied L1 cell has a 64-bit mask
+// of its 4x4x4 L2 cells (0.0625 m).  Points are sorted by (L0, L1, L2) so each
+// cell at each level is one contiguous range.  Search:
+//   A  the 27 L2 cells around the query (dense regions end here: exact as soon
+//      as the 5th distance is < 0.0625^2),
+//   B  the 27 L1 cells around the query, L2 cell by L2 cell, skipping what A saw
+//      and every L2 cell whose box is farther than the current 5th distance
+//      (exact as soon as the 5th distance is < 0.25^2),
+//   C  the 27 L0 cells, pruned the same way at L0, L1 and L2 granularity.
+// Cell sizes are powers of two, so cell indices and cell bounds are exact in
+// fp32 and the box distance — computed with the same rounding sequence as a
+// point distance — never exceeds the distance of a point inside the box:
+// pruning is exact, ties included.
 //
 // Distances are FLANN's L2_Simple: ((dx*dx)+dy*dy)+dz*dz in fp32.  Results are
 // ascending by (distance, original index): ties are resolved by index, which
@@ -20,9 +31,11 @@
 namespace lm {
 
 struct MapView {
-  const float4* sorted;    // cell-sorted points, .w = original index bits
-  const CellRec* table;    // hash table of coarse cells
-  const int* fine_start;   // start of every occupied fine cell in `sorted`, + sentinel
+  const float4* sorted;             // cell-sorted points, .w = original index bits
+  const CellRec* table;             // hash table of L0 cells
+  const unsigned long long* l1_mask;  // per occupied L1 cell: occupancy of its L2 cells
+  const int* l1_first;              // per occupied L1 cell: index of its first L2 cell in l2_start (+ sentinel)
+  const int* l2_start;              // start of every occupied L2 cell in `sorted` (+ sentinel)
   const MapDev* dev;
 };
 
@@ -71,14 +84,31 @@ __device__ __forceinline__ unsigned long long pack_cell(const MapDev& md, int cx
          (unsigned long long)(unsigned)cx;
 }
 
-__device__ __forceinline__ const CellRec* find_cell(const MapView& mv, unsigned tmask, unsigned long long key) {
-  unsigned h = hash_cell(key) & tmask;
+// one-entry cache in front of the hash probe: neighbouring cells mostly share their L0 cell
+struct CellCursor {
+  unsigned long long key;
+  const CellRec* rec;
+};
+
+__device__ __forceinline__ const CellRec* find_cell(const MapView& mv, const MapDev& md, CellCursor& cur, int cx,
+                                                    int cy, int cz) {
+  if (cx < 0 || cy < 0 || cz < 0 || cx >= md.dim[0] || cy >= md.dim[1] || cz >= md.dim[2]) return nullptr;
+  unsigned long long key = pack_cell(md, cx, cy, cz);
+  if (key == cur.key) return cur.rec;
+  unsigned h = hash_cell(key) & md.table_mask;
+  const CellRec* r = nullptr;
   while (true) {
     unsigned long long k = mv.table[h].key;
-    if (k == key) return &mv.table[h];
-    if (k == ~0ull) return nullptr;
-    h = (h + 1) & tmask;
+    if (k == key) {
+      r = &mv.table[h];
+      break;
+    }
+    if (k == ~0ull) break;
+    h = (h + 1) & md.table_mask;
   }
+  cur.key = key;
+  cur.rec = r;
+  return r;
 }
 
 __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz,
@@ -93,62 +123,123 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s
   }
 }
 
+// squared distance from q to the axis-aligned cell [c*s, (c+1)*s)^3, same rounding sequence as scan_range
+__device__ __forceinline__ float axis_gap(float q, int c, float s) {
+  float lo = (float)c * s;
+  float hi = lo + s;
+  return (q < lo) ? (lo - q) : ((q > hi) ? (q - hi) : 0.0f);
+}
+__device__ __forceinline__ float box_d2(float qx, float qy, float qz, int cx, int cy, int cz, float s) {
+  float dx = axis_gap(qx, cx, s), dy = axis_gap(qy, cy, s), dz = axis_gap(qz, cz, s);
+  float r = dx * dx;
+  r = r + dy * dy;
+  r = r + dz * dz;
+  return r;
+}
+
+// scan the L2 cells of one L1 cell (absolute L1 coords ax1..az1) that survive the box test and lie outside `skip`
+__device__ __forceinline__ void sweep_l1_cell(const MapView& mv, int l1, int ax1, int ay1, int az1, float qx, float qy,
+                                              float qz, int sx, int sy, int sz, Top5& nb) {
+  unsigned long long m2 = mv.l1_mask[l1];
+  int base = mv.l1_first[l1];
+  int rank = 0;
+  while (m2) {
+    int f2 = __ffsll((long long)m2) - 1;
+    m2 &= m2 - 1;
+    int ax2 = (ax1 << 2) | (f2 & 3), ay2 = (ay1 << 2) | ((f2 >> 2) & 3), az2 = (az1 << 2) | (f2 >> 4);
+    bool seen = (ax2 >= sx - 1 && ax2 <= sx + 1 && ay2 >= sy - 1 && ay2 <= sy + 1 && az2 >= sz - 1 && az2 <= sz + 1);
+    if (!seen && !(box_d2(qx, qy, qz, ax2, ay2, az2, 0.0625f) > nb.d[4])) {
+      int s = mv.l2_start[base + rank];
+      int e = mv.l2_start[base + rank + 1];
+      scan_range(mv.sorted, s, e, qx, qy, qz, nb);
+    }
+    ++rank;
+  }
+}
+
 // exact 5-NN within squared radius 1.0; nb.id[k] = -1 for unfilled slots
 __device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, float qz, Top5& nb) {
   nb.reset();
   const MapDev md = *mv.dev;
   if (md.n <= 0) return;
-  if (!(fabsf(qx) < 1.0e8f && fabsf(qy) < 1.0e8f && fabsf(qz) < 1.0e8f)) return;
-  // fine coordinates relative to the grid origin (x4 is exact in fp32)
-  const int gx = (int)floorf(qx * 4.0f) - 4 * md.min_c[0];
-  const int gy = (int)floorf(qy * 4.0f) - 4 * md.min_c[1];
-  const int gz = (int)floorf(qz * 4.0f) - 4 * md.min_c[2];
-  const unsigned tmask = md.table_mask;
-  // ---- pass 1: 3x3x3 fine cells; each (z,y) row is at most two runs of x sub-cells
+  if (!(fabsf(qx) < 2.0e5f && fabsf(qy) < 2.0e5f && fabsf(qz) < 2.0e5f)) return;
+  // absolute L2 cell coordinates of the query (x16 is exact in fp32), and the grid origin at each level
+  const int ax = (int)floorf(qx * 16.0f), ay = (int)floorf(qy * 16.0f), az = (int)floorf(qz * 16.0f);
+  const int ox = md.min_c[0], oy = md.min_c[1], oz = md.min_c[2];
+  CellCursor cur;
+  cur.key = ~0ull;
+  cur.rec = nullptr;
+  // ---- A: 3x3x3 L2 cells; each (z,y) row is at most two runs of x sub-cells inside one L1 cell each
   for (int dz = -1; dz <= 1; ++dz) {
-    int z = gz + dz, cz = z >> 2;
-    if (cz < 0 || cz >= md.dim[2]) continue;
+    int z = az + dz;
     for (int dy = -1; dy <= 1; ++dy) {
-      int y = gy + dy, cy = y >> 2;
-      if (cy < 0 || cy >= md.dim[1]) continue;
-      int row = ((z & 3) << 4) | ((y & 3) << 2);
-      int x0 = gx - 1, x1 = gx + 1;
-      int ca = x0 >> 2, cb = x1 >> 2;
-      for (int cx = ca; cx <= cb; ++cx) {
-        if (cx < 0 || cx >= md.dim[0]) continue;
-        int lo = (cx == ca) ? (x0 & 3) : 0;
-        int hi = (cx == cb) ? (x1 & 3) : 3;
-        const CellRec* rec = find_cell(mv, tmask, pack_cell(md, cx, cy, cz));
+      int y = ay + dy;
+      int row2 = ((z & 3) << 4) | ((y & 3) << 2);
+      int row1 = (((z >> 2) & 3) << 4) | (((y >> 2) & 3) << 2);
+      int x0 = ax - 1, x1 = ax + 1;
+      int la = x0 >> 2, lb = x1 >> 2;  // L1 x coords of the run's ends
+      for (int lx = la; lx <= lb; ++lx) {
+        const CellRec* rec = find_cell(mv, md, cur, (lx >> 2) - ox, (y >> 4) - oy, (z >> 4) - oz);
         if (!rec) continue;
-        unsigned long long mask = rec->mask;
-        int flo = row | lo, fhi = row | hi;
+        int f1 = row1 | (lx & 3);
+        unsigned long long m1 = rec->mask;
+        if (!((m1 >> f1) & 1ull)) continue;
+        int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
+        unsigned long long m2 = mv.l1_mask[l1];
+        int lo = (lx == la) ? (x0 & 3) : 0;
+        int hi = (lx == lb) ? (x1 & 3) : 3;
+        int flo = row2 | lo, fhi = row2 | hi;
         unsigned long long below = (1ull << flo) - 1ull;
-        unsigned long long upto = (2ull << fhi) - 1ull;
-        unsigned long long sub = mask & upto & ~below;
+        unsigned long long sub = m2 & ((2ull << fhi) - 1ull) & ~below;
         if (!sub) continue;
-        int base = rec->fine_base + __popcll(mask & below);
-        int s = mv.fine_start[base];
-        int e = mv.fine_start[base + __popcll(sub)];
-        scan_range(mv.sorted, s, e, qx, qy, qz, nb);
+        int b = mv.l1_first[l1] + __popcll(m2 & below);
+        scan_range(mv.sorted, mv.l2_start[b], mv.l2_start[b + __popcll(sub)], qx, qy, qz, nb);
+      }
+    }
+  }
+  if (nb.full() && nb.d[4] < 0.00390625f) return;
+  // ---- B: 3x3x3 L1 cells, L2 cell by L2 cell with box pruning, skipping what A scanned
+  const int bx = ax >> 2, by = ay >> 2, bz = az >> 2;
+  for (int dz = -1; dz <= 1; ++dz) {
+    int z = bz + dz;
+    for (int dy = -1; dy <= 1; ++dy) {
+      int y = by + dy;
+      for (int dx = -1; dx <= 1; ++dx) {
+        int x = bx + dx;
+        if (box_d2(qx, qy, qz, x, y, z, 0.25f) > nb.d[4]) continue;
+        const CellRec* rec = find_cell(mv, md, cur, (x >> 2) - ox, (y >> 2) - oy, (z >> 2) - oz);
+        if (!rec) continue;
+        int f1 = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
+        unsigned long long m1 = rec->mask;
+        if (!((m1 >> f1) & 1ull)) continue;
+        int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
+        sweep_l1_cell(mv, l1, x, y, z, qx, qy, qz, ax, ay, az, nb);
       }
     }
   }
   if (nb.full() && nb.d[4] < 0.0625f) return;
-  // ---- pass 2: 3x3x3 coarse cells (exact for every query the matchers accept)
-  nb.reset();
-  const int cx0 = gx >> 2, cy0 = gy >> 2, cz0 = gz >> 2;
+  // ---- C: 3x3x3 L0 cells, pruned at L0 / L1 / L2 granularity, skipping the L1 block B covered
+  const int cx0 = bx >> 2, cy0 = by >> 2, cz0 = bz >> 2;
   for (int dz = -1; dz <= 1; ++dz) {
-    int cz = cz0 + dz;
-    if (cz < 0 || cz >= md.dim[2]) continue;
+    int z = cz0 + dz;
     for (int dy = -1; dy <= 1; ++dy) {
-      int cy = cy0 + dy;
-      if (cy < 0 || cy >= md.dim[1]) continue;
+      int y = cy0 + dy;
       for (int dx = -1; dx <= 1; ++dx) {
-        int cx = cx0 + dx;
-        if (cx < 0 || cx >= md.dim[0]) continue;
-        const CellRec* rec = find_cell(mv, tmask, pack_cell(md, cx, cy, cz));
+        int x = cx0 + dx;
+        if (box_d2(qx, qy, qz, x, y, z, 1.0f) > nb.d[4]) continue;
+        const CellRec* rec = find_cell(mv, md, cur, x - ox, y - oy, z - oz);
         if (!rec) continue;
-        scan_range(mv.sorted, rec->start, rec->end, qx, qy, qz, nb);
+        unsigned long long m1 = rec->mask;
+        int l1 = rec->fine_base;
+        while (m1) {
+          int f1 = __ffsll((long long)m1) - 1;
+          m1 &= m1 - 1;
+          int x1 = (x << 2) | (f1 & 3), y1 = (y << 2) | ((f1 >> 2) & 3), z1 = (z << 2) | (f1 >> 4);
+          bool seen = (x1 >= bx - 1 && x1 <= bx + 1 && y1 >= by - 1 && y1 <= by + 1 && z1 >= bz - 1 && z1 <= bz + 1);
+          if (!seen && !(box_d2(qx, qy, qz, x1, y1, z1, 0.25f) > nb.d[4]))
+            sweep_l1_cell(mv, l1, x1, y1, z1, qx, qy, qz, ax, ay, az, nb);
+          ++l1;
+        }
       }
     }
   }

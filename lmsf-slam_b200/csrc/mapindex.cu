@@ -3,8 +3,8 @@
 // Replaces pcl::KdTreeFLANN::setInputCloud behind FeatureMatch::SetSearchTarget
 // (registration/FeatureMatch/FeatureMatchBase.hpp:40-44), which the tracker triggers
 // on every keyframe through SetInputSource (LidarTracker/LidarTrackerLocalMap.hpp:229).
-// Build = bbox -> 64-bit cell keys (coarse 1 m cell | 6-bit 0.25 m sub-cell) -> radix
-// sort -> gather -> fine-cell starts -> one hash-table record per coarse cell.
+// Build = bbox -> 64-bit cell keys (1 m cell | 6-bit 0.25 m sub-cell | 6-bit 0.0625 m sub-cell)
+// -> radix sort -> gather -> L2 cell starts -> L1 cell masks -> one hash-table record per 1 m cell.
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -27,11 +27,12 @@ __global__ void __launch_bounds__(256) k_map_keys(const float4* __restrict__ in,
   float4 p = in[i];
   unsigned long long key = ~0ull;
   if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-    int gx = (int)floorf(p.x * 4.0f) - 4 * md.min_c[0];
-    int gy = (int)floorf(p.y * 4.0f) - 4 * md.min_c[1];
-    int gz = (int)floorf(p.z * 4.0f) - 4 * md.min_c[2];
-    unsigned long long ck = pack_cell(md, gx >> 2, gy >> 2, gz >> 2);
-    key = (ck << 6) | (unsigned long long)(((gz & 3) << 4) | ((gy & 3) << 2) | (gx & 3));
+    // absolute L2 (0.0625 m) cell coordinates; x16 is exact in fp32
+    int ax = (int)floorf(p.x * 16.0f), ay = (int)floorf(p.y * 16.0f), az = (int)floorf(p.z * 16.0f);
+    unsigned long long ck = pack_cell(md, (ax >> 4) - md.min_c[0], (ay >> 4) - md.min_c[1], (az >> 4) - md.min_c[2]);
+    unsigned f1 = (((az >> 2) & 3) << 4) | (((ay >> 2) & 3) << 2) | ((ax >> 2) & 3);
+    unsigned f2 = ((az & 3) << 4) | ((ay & 3) << 2) | (ax & 3);
+    key = (ck << 12) | ((unsigned long long)f1 << 6) | (unsigned long long)f2;
   }
   keys[i] = key;
   vals[i] = i;
@@ -47,41 +48,69 @@ __global__ void __launch_bounds__(256) k_map_gather(const float4* __restrict__ i
   sorted[i] = p;
 }
 
-// one thread per occupied fine cell; the first fine cell of a coarse cell inserts the record
+// flags over the occupied L2 cells: 1 where a new L1 cell starts (0 beyond the n2 live entries)
+__global__ void __launch_bounds__(256) k_l1_flags(const unsigned long long* __restrict__ keys,
+                                                  const int* __restrict__ l2_start, const int* __restrict__ d_n2,
+                                                  int n, uint8_t* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int n2 = *d_n2;
+  uint8_t f = 0;
+  if (i < n2) f = (i == 0 || (keys[l2_start[i]] >> 6) != (keys[l2_start[i - 1]] >> 6)) ? 1 : 0;
+  flags[i] = f;
+}
+
+// one thread per occupied L1 cell: its L2 occupancy mask; the first L1 cell of an L0 cell also
+// assembles that cell's record and inserts it into the hash table
 __global__ void __launch_bounds__(256) k_cell_insert(const unsigned long long* __restrict__ keys,
-                                                     int* __restrict__ fine_start, const int* __restrict__ d_nfine,
-                                                     int n_pts, MapDev* __restrict__ dev, CellRec* __restrict__ table,
+                                                     int* __restrict__ l2_start, int* __restrict__ l1_first,
+                                                     unsigned long long* __restrict__ l1_mask,
+                                                     const int* __restrict__ d_cnt, int n_pts,
+                                                     MapDev* __restrict__ dev, CellRec* __restrict__ table,
                                                      unsigned tmask) {
-  const int nf = *d_nfine;
-  int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f == 0) {
-    fine_start[nf] = n_pts;
-    dev->n_fine = nf;
+  const int n2 = d_cnt[0], n1 = d_cnt[1];
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) {
+    dev->n_fine = n1;
   }
-  if (f >= nf) return;
-  int pos = fine_start[f];
-  unsigned long long ck = keys[pos] >> 6;
-  if (f > 0 && (keys[fine_start[f - 1]] >> 6) == ck) return;
-  unsigned long long mask = 0ull;
-  int last = f;
-  for (int g = f; g < nf; ++g) {
-    unsigned long long k = keys[fine_start[g]];
-    if ((k >> 6) != ck) break;
-    mask |= 1ull << (unsigned)(k & 63ull);
+  if (j >= n1) return;
+  const int a = l1_first[j];
+  const int b = (j + 1 < n1) ? l1_first[j + 1] : n2;
+  unsigned long long m2 = 0ull;
+  for (int i = a; i < b; ++i) m2 |= 1ull << (unsigned)(keys[l2_start[i]] & 63ull);
+  l1_mask[j] = m2;
+  const unsigned long long kj = keys[l2_start[a]];
+  const unsigned long long ck = kj >> 12;
+  if (j > 0 && (keys[l2_start[l1_first[j - 1]]] >> 12) == ck) return;
+  unsigned long long m1 = 0ull;
+  int last = j;
+  for (int g = j; g < n1; ++g) {
+    unsigned long long k = keys[l2_start[l1_first[g]]];
+    if ((k >> 12) != ck) break;
+    m1 |= 1ull << (unsigned)((k >> 6) & 63ull);
     last = g;
   }
-  int end = (last + 1 < nf) ? fine_start[last + 1] : n_pts;
+  int end = (last + 1 < n1) ? l2_start[l1_first[last + 1]] : n_pts;
   unsigned h = hash_cell(ck) & tmask;
   while (true) {
     unsigned long long prev = atomicCAS(&table[h].key, ~0ull, ck);
     if (prev == ~0ull) break;
     h = (h + 1) & tmask;
   }
-  table[h].mask = mask;
-  table[h].start = pos;
+  table[h].mask = m1;
+  table[h].start = l2_start[a];
   table[h].end = end;
-  table[h].fine_base = f;
+  table[h].fine_base = j;
   table[h].pad = 0;
+}
+
+// sentinels behind the live entries (written after every reader of the previous values is done)
+__global__ void k_sentinels(int* __restrict__ l2_start, int* __restrict__ l1_first, const int* __restrict__ d_cnt,
+                            int n_pts) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    l2_start[d_cnt[0]] = n_pts;
+    l1_first[d_cnt[1]] = d_cnt[0];
+  }
 }
 
 int map_alloc(Ctx* c, MapIndex& m, int cap) {
@@ -96,7 +125,10 @@ int map_alloc(Ctx* c, MapIndex& m, int cap) {
   LM_CUDA(cudaMalloc(&m.keys_alt, n * 8));
   LM_CUDA(cudaMalloc(&m.vals, n * 4));
   LM_CUDA(cudaMalloc(&m.vals_alt, n * 4));
-  LM_CUDA(cudaMalloc(&m.fine_start, (n + 1) * 4));
+  LM_CUDA(cudaMalloc(&m.l2_start, (n + 1) * 4));
+  LM_CUDA(cudaMalloc(&m.l1_first, (n + 1) * 4));
+  LM_CUDA(cudaMalloc(&m.l1_mask, n * 8));
+  LM_CUDA(cudaMalloc(&m.d_cnt, 4 * sizeof(int)));
   LM_CUDA(cudaMalloc(&m.flags, n));
   LM_CUDA(cudaMalloc(&m.dev, sizeof(MapDev)));
   LM_CUDA(cudaMemset(m.dev, 0, sizeof(MapDev)));
@@ -117,7 +149,10 @@ void map_free(MapIndex& m) {
   cudaFree(m.keys_alt);
   cudaFree(m.vals);
   cudaFree(m.vals_alt);
-  cudaFree(m.fine_start);
+  cudaFree(m.l2_start);
+  cudaFree(m.l1_first);
+  cudaFree(m.l1_mask);
+  cudaFree(m.d_cnt);
   cudaFree(m.flags);
   cudaFree(m.dev);
   cudaFree(m.table);
@@ -148,10 +183,10 @@ int map_build(Ctx* c, MapIndex& m, int n) {
   md.n = (int)hb[6];
   if (md.n == 0) return LMSF_OK;
   long long cells = 1;
-  int total_bits = 6;
+  int total_bits = 12;
   for (int a = 0; a < 3; ++a) {
     float mn = ord2f_host(hb[a]), mx = ord2f_host(hb[3 + a]);
-    if (!(fabsf(mn) < 1.0e8f && fabsf(mx) < 1.0e8f)) return LMSF_ERR_INVALID;  // coordinates beyond the grid's int range
+    if (!(fabsf(mn) < 1.0e5f && fabsf(mx) < 1.0e5f)) return LMSF_ERR_INVALID;  // beyond the exact-cell-bound range
     md.min_c[a] = (int)floorf(mn);
     md.dim[a] = (int)floorf(mx) - md.min_c[a] + 1;
     int b = 0;
@@ -185,12 +220,17 @@ int map_build(Ctx* c, MapIndex& m, int n) {
   LM_LAUNCH(c, k_map_gather, div_up(nf, 256), 256, 0, m.cat, m.vals_alt, nf, m.sorted);
   LM_LAUNCH(c, k_head_flags, div_up(nf, 256), 256, 0, m.keys_alt, nf, m.flags);
   tmp = c->cub_tmp_bytes;
-  int* d_nsel = (int*)c->d_bbox + 7;
-  LM_CUDA(cub::DeviceSelect::Flagged(c->cub_tmp, tmp, thrust::counting_iterator<int>(0), m.flags, m.fine_start, d_nsel,
-                                     nf, c->stream));
+  LM_CUDA(cub::DeviceSelect::Flagged(c->cub_tmp, tmp, thrust::counting_iterator<int>(0), m.flags, m.l2_start,
+                                     m.d_cnt + 0, nf, c->stream));
   c->launches++;
-  LM_LAUNCH(c, k_cell_insert, div_up(nf, 256), 256, 0, m.keys_alt, m.fine_start, d_nsel, nf, m.dev, m.table,
-            md.table_mask);
+  LM_LAUNCH(c, k_l1_flags, div_up(nf, 256), 256, 0, m.keys_alt, m.l2_start, m.d_cnt + 0, nf, m.flags);
+  tmp = c->cub_tmp_bytes;
+  LM_CUDA(cub::DeviceSelect::Flagged(c->cub_tmp, tmp, thrust::counting_iterator<int>(0), m.flags, m.l1_first,
+                                     m.d_cnt + 1, nf, c->stream));
+  c->launches++;
+  LM_LAUNCH(c, k_cell_insert, div_up(nf, 256), 256, 0, m.keys_alt, m.l2_start, m.l1_first, m.l1_mask, m.d_cnt, nf,
+            m.dev, m.table, md.table_mask);
+  LM_LAUNCH(c, k_sentinels, 1, 32, 0, m.l2_start, m.l1_first, m.d_cnt, nf);
   LM_CUDA(cudaGetLastError());
   m.ready = true;
   return LMSF_OK;

@@ -19,6 +19,8 @@
 // and every kernel of the pre-enqueued sequence exits at once when its phase is over.
 #include <float.h>
 
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 #include "knn.cuh"
 
@@ -466,80 +468,160 @@ __device__ void lm_update(SolveState* st, const double* tot, const SolveParams& 
 }
 
 // ------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(MATCH_BLOCK) k_match(const float4* __restrict__ feat, const int* __restrict__ counts,
-                                                       MapPair maps, int has_edge_map, int has_surf_map,
-                                                       SolveState* __restrict__ st, double* __restrict__ rec,
-                                                       uint8_t* __restrict__ okv, int rec_stride,
-                                                       double* __restrict__ partial, SolveParams sp) {
+struct QueryBufs {
+  unsigned long long* keys;  // [upper] sort keys (kind | L0 | L1 | L2 cell of the world point)
+  int* vals;                 // [upper] feature index
+  float4* pw;                // [upper] fp32 world point by feature index
+};
+
+// clamp-and-pack the cell of a query for sorting only (locality heuristic: any key is correct)
+__device__ __forceinline__ unsigned long long query_cell_key(const MapDev& md, float x, float y, float z) {
+  const float lim = 1.0e5f;
+  x = fminf(fmaxf(x, -lim), lim);
+  y = fminf(fmaxf(y, -lim), lim);
+  z = fminf(fmaxf(z, -lim), lim);
+  int ax = (int)floorf(x * 16.0f), ay = (int)floorf(y * 16.0f), az = (int)floorf(z * 16.0f);
+  int cx = min(max((ax >> 4) - md.min_c[0], 0), max(md.dim[0] - 1, 0));
+  int cy = min(max((ay >> 4) - md.min_c[1], 0), max(md.dim[1] - 1, 0));
+  int cz = min(max((az >> 4) - md.min_c[2], 0), max(md.dim[2] - 1, 0));
+  unsigned f1 = (((az >> 2) & 3) << 4) | (((ay >> 2) & 3) << 2) | ((ax >> 2) & 3);
+  unsigned f2 = ((az & 3) << 4) | ((ay & 3) << 2) | (ax & 3);
+  return (pack_cell(md, cx, cy, cz) << 12) | ((unsigned long long)f1 << 6) | (unsigned long long)f2;
+}
+
+// pointAssociateToMap (edgeSurfFeatureRegistration.hpp:342-350): world point in fp64, stored as fp32;
+// plus the sort key that groups the queries of one map cell into one warp
+__global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, const int* __restrict__ counts,
+                                               const SolveState* __restrict__ st, const MapDev* __restrict__ dev_e,
+                                               const MapDev* __restrict__ dev_s, int kind_bit, int upper,
+                                               int solver, QueryBufs qb) {
+  if (solver == LMSF_SOLVER_GN && st->gn_done) return;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= upper) return;
+  const int n_e = counts[0], n_s = counts[1];
+  unsigned long long key = 2ull << kind_bit;  // padding sorts behind every live query
+  if (i < n_e + n_s) {
+    quat q;
+    q.x = st->x[0];
+    q.y = st->x[1];
+    q.z = st->x[2];
+    q.w = st->x[3];
+    d3 t = mk3(st->x[4], st->x[5], st->x[6]);
+    float4 f = feat[i];
+    d3 pw = add3(qrot(q, mk3((double)f.x, (double)f.y, (double)f.z)), t);
+    float4 w = make_float4((float)pw.x, (float)pw.y, (float)pw.z, 0.f);
+    qb.pw[i] = w;
+    const bool is_edge = i < n_e;
+    key = query_cell_key(is_edge ? *dev_e : *dev_s, w.x, w.y, w.z) | (is_edge ? 0ull : (1ull << kind_bit));
+  }
+  qb.keys[i] = key;
+  qb.vals[i] = i;
+}
+
+// exact 5-NN of every query, in cell-sorted query order (t = sorted position)
+__global__ void __launch_bounds__(128) k_knn(const int* __restrict__ perm, const float4* __restrict__ pw,
+                                             const int* __restrict__ counts, const SolveState* __restrict__ st,
+                                             MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
+                                             int* __restrict__ nbr) {
+  if (solver == LMSF_SOLVER_GN && st->gn_done) return;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= upper) return;
+  const int n_e = counts[0], n_s = counts[1];
+  int f = perm[t];
+  if (f >= n_e + n_s) return;
+  const bool is_edge = f < n_e;
+  Top5 nb;
+  nb.reset();
+  if (is_edge ? has_edge_map : has_surf_map) {
+    float4 w = pw[f];
+    knn5(is_edge ? maps.edge : maps.surf, w.x, w.y, w.z, nb);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) nbr[k * upper + t] = nb.id[k];
+}
+
+struct RecBufs {
+  double* d;      // [6][stride] edge: a, b   surf: n, D
+  float* pl;      // [3][stride] scan point in the LiDAR frame
+  uint8_t* kind;  // [stride] 0 = no correspondence, 1 = edge, 2 = surf
+  int stride;
+};
+
+// fit + residual/Jacobian + reduction, grid-stride over the sorted queries; the last block runs the 6x6 step
+__global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ feat, const int* __restrict__ perm,
+                                                     const float4* __restrict__ pw, const int* __restrict__ nbr,
+                                                     const int* __restrict__ counts, MapPair maps, int upper,
+                                                     SolveState* __restrict__ st, RecBufs rb,
+                                                     double* __restrict__ partial, SolveParams sp) {
   __shared__ double tot[LM_NSUM];
   if (sp.solver == LMSF_SOLVER_GN && st->gn_done) return;
   const int n_e = counts[0], n_s = counts[1];
-  const int i = blockIdx.x * MATCH_BLOCK + threadIdx.x;
   quat q;
   q.x = st->x[0];
   q.y = st->x[1];
   q.z = st->x[2];
   q.w = st->x[3];
-  d3 t = mk3(st->x[4], st->x[5], st->x[6]);
+  d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
+  double R[9];
+  quat_to_mat(q, R);
   Acc acc;
   acc_zero(acc);
-  if (i < n_e + n_s) {
-    const bool is_edge = i < n_e;
-    float4 f = feat[i];
-    d3 pl = mk3((double)f.x, (double)f.y, (double)f.z);
-    d3 pw = add3(qrot(q, pl), t);
-    float px = (float)pw.x, py = (float)pw.y, pz = (float)pw.z;
-    bool ok = false;
+  for (int t = blockIdx.x * MATCH_BLOCK + threadIdx.x; t < upper; t += gridDim.x * MATCH_BLOCK) {
+    int f = perm[t];
+    if (f >= n_e + n_s) continue;  // padding
+    const bool is_edge = f < n_e;
     Top5 nb;
-    if (is_edge) {
-      if (has_edge_map) {
-        knn5(maps.edge, px, py, pz, nb);
-        if (nb.full()) {
-          d3 n, a, b;
-          double r;
-          ok = fit_edge(maps.edge_cat, nb, px, py, pz, n, r, a, b);
-          if (ok) {
-            if (sp.solver == LMSF_SOLVER_GN) {
-              double R[9];
-              quat_to_mat(q, R);
-              gn_row(R, pl, n, r, acc);
-            } else {
-              rec[0 * rec_stride + i] = a.x;
-              rec[1 * rec_stride + i] = a.y;
-              rec[2 * rec_stride + i] = a.z;
-              rec[3 * rec_stride + i] = b.x;
-              rec[4 * rec_stride + i] = b.y;
-              rec[5 * rec_stride + i] = b.z;
-              edge_factor(q, t, pl, a, b, sp.huber, acc);
-            }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      nb.id[k] = nbr[k * upper + t];
+      nb.d[k] = 0.f;
+    }
+    uint8_t kind = 0;
+    if (nb.full()) {
+      float4 fp = feat[f];
+      float4 w = pw[f];
+      d3 pl = mk3((double)fp.x, (double)fp.y, (double)fp.z);
+      if (is_edge) {
+        d3 n, a, b;
+        double r;
+        if (fit_edge(maps.edge_cat, nb, w.x, w.y, w.z, n, r, a, b)) {
+          kind = 1;
+          acc.v[29] += 1.0;
+          if (sp.solver == LMSF_SOLVER_GN) {
+            gn_row(R, pl, n, r, acc);
+          } else {
+            rb.d[0 * rb.stride + t] = a.x;
+            rb.d[1 * rb.stride + t] = a.y;
+            rb.d[2 * rb.stride + t] = a.z;
+            rb.d[3 * rb.stride + t] = b.x;
+            rb.d[4 * rb.stride + t] = b.y;
+            rb.d[5 * rb.stride + t] = b.z;
+            edge_factor(q, tr, pl, a, b, sp.huber, acc);
+          }
+        }
+      } else {
+        d3 n;
+        double D, r;
+        if (fit_surf(maps.surf_cat, nb, w.x, w.y, w.z, n, D, r)) {
+          kind = 2;
+          if (sp.solver == LMSF_SOLVER_GN) {
+            gn_row(R, pl, n, r, acc);
+          } else {
+            rb.d[0 * rb.stride + t] = n.x;
+            rb.d[1 * rb.stride + t] = n.y;
+            rb.d[2 * rb.stride + t] = n.z;
+            rb.d[3 * rb.stride + t] = D;
+            surf_factor(q, tr, pl, n, D, sp.huber, acc);
           }
         }
       }
-    } else {
-      if (has_surf_map) {
-        knn5(maps.surf, px, py, pz, nb);
-        if (nb.full()) {
-          d3 n;
-          double D, r;
-          ok = fit_surf(maps.surf_cat, nb, px, py, pz, n, D, r);
-          if (ok) {
-            if (sp.solver == LMSF_SOLVER_GN) {
-              double R[9];
-              quat_to_mat(q, R);
-              gn_row(R, pl, n, r, acc);
-            } else {
-              rec[0 * rec_stride + i] = n.x;
-              rec[1 * rec_stride + i] = n.y;
-              rec[2 * rec_stride + i] = n.z;
-              rec[3 * rec_stride + i] = D;
-              surf_factor(q, t, pl, n, D, sp.huber, acc);
-            }
-          }
-        }
+      if (kind && sp.solver != LMSF_SOLVER_GN) {
+        rb.pl[0 * rb.stride + t] = fp.x;
+        rb.pl[1 * rb.stride + t] = fp.y;
+        rb.pl[2 * rb.stride + t] = fp.z;
       }
     }
-    okv[i] = ok ? 1 : 0;
-    if (ok && is_edge) acc.v[29] += 1.0;
+    rb.kind[t] = kind;
   }
   if (!reduce_grid(acc, partial, st, tot)) return;
   if (threadIdx.x == 0) {
@@ -554,33 +636,30 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_match(const float4* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(const float4* __restrict__ feat,
-                                                         const int* __restrict__ counts, SolveState* __restrict__ st,
-                                                         const double* __restrict__ rec,
-                                                         const uint8_t* __restrict__ okv, int rec_stride,
+// re-evaluate the stored correspondences at the LM candidate; last block accepts / rejects / proposes
+__global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* __restrict__ st, RecBufs rb,
                                                          double* __restrict__ partial, SolveParams sp) {
   __shared__ double tot[LM_NSUM];
   if (!st->lm_active) return;
-  const int n_e = counts[0], n_s = counts[1];
-  const int i = blockIdx.x * MATCH_BLOCK + threadIdx.x;
   quat q;
   q.x = st->cand[0];
   q.y = st->cand[1];
   q.z = st->cand[2];
   q.w = st->cand[3];
-  d3 t = mk3(st->cand[4], st->cand[5], st->cand[6]);
+  d3 tr = mk3(st->cand[4], st->cand[5], st->cand[6]);
   Acc acc;
   acc_zero(acc);
-  if (i < n_e + n_s && okv[i]) {
-    float4 f = feat[i];
-    d3 pl = mk3((double)f.x, (double)f.y, (double)f.z);
-    if (i < n_e) {
-      d3 a = mk3(rec[0 * rec_stride + i], rec[1 * rec_stride + i], rec[2 * rec_stride + i]);
-      d3 b = mk3(rec[3 * rec_stride + i], rec[4 * rec_stride + i], rec[5 * rec_stride + i]);
-      edge_factor(q, t, pl, a, b, sp.huber, acc);
+  for (int t = blockIdx.x * MATCH_BLOCK + threadIdx.x; t < upper; t += gridDim.x * MATCH_BLOCK) {
+    uint8_t kind = rb.kind[t];
+    if (!kind) continue;
+    d3 pl = mk3((double)rb.pl[0 * rb.stride + t], (double)rb.pl[1 * rb.stride + t], (double)rb.pl[2 * rb.stride + t]);
+    double r0 = rb.d[0 * rb.stride + t], r1 = rb.d[1 * rb.stride + t], r2 = rb.d[2 * rb.stride + t];
+    double r3 = rb.d[3 * rb.stride + t];
+    if (kind == 1) {
+      d3 b = mk3(r3, rb.d[4 * rb.stride + t], rb.d[5 * rb.stride + t]);
+      edge_factor(q, tr, pl, mk3(r0, r1, r2), b, sp.huber, acc);
     } else {
-      d3 n = mk3(rec[0 * rec_stride + i], rec[1 * rec_stride + i], rec[2 * rec_stride + i]);
-      surf_factor(q, t, pl, n, rec[3 * rec_stride + i], sp.huber, acc);
+      surf_factor(q, tr, pl, mk3(r0, r1, r2), r3, sp.huber, acc);
     }
   }
   if (!reduce_grid(acc, partial, st, tot)) return;
@@ -652,7 +731,9 @@ static MapView view_of(const MapIndex& m) {
   MapView v;
   v.sorted = m.sorted;
   v.table = m.table;
-  v.fine_start = m.fine_start;
+  v.l1_mask = m.l1_mask;
+  v.l1_first = m.l1_first;
+  v.l2_start = m.l2_start;
   v.dev = m.dev;
   return v;
 }
@@ -660,7 +741,14 @@ static MapView view_of(const MapIndex& m) {
 int solve_alloc(Ctx* c) {
   size_t cap = (size_t)c->prm.max_points;
   LM_CUDA(cudaMalloc(&c->d_rec, 6 * cap * sizeof(double)));
+  LM_CUDA(cudaMalloc(&c->d_recf, 3 * cap * sizeof(float)));
   LM_CUDA(cudaMalloc(&c->d_ok, cap));
+  LM_CUDA(cudaMalloc(&c->q_keys, cap * 8));
+  LM_CUDA(cudaMalloc(&c->q_keys_alt, cap * 8));
+  LM_CUDA(cudaMalloc(&c->q_vals, cap * 4));
+  LM_CUDA(cudaMalloc(&c->q_vals_alt, cap * 4));
+  LM_CUDA(cudaMalloc(&c->d_pw, cap * sizeof(float4)));
+  LM_CUDA(cudaMalloc(&c->d_nbr, 5 * cap * sizeof(int)));
   c->partial_blocks = div_up((int)cap, MATCH_BLOCK);
   LM_CUDA(cudaMalloc(&c->d_partial, (size_t)c->partial_blocks * LM_NSUM * sizeof(double)));
   LM_CUDA(cudaMalloc(&c->d_state, sizeof(SolveState)));
@@ -670,7 +758,14 @@ int solve_alloc(Ctx* c) {
 
 void solve_free(Ctx* c) {
   cudaFree(c->d_rec);
+  cudaFree(c->d_recf);
   cudaFree(c->d_ok);
+  cudaFree(c->q_keys);
+  cudaFree(c->q_keys_alt);
+  cudaFree(c->q_vals);
+  cudaFree(c->q_vals_alt);
+  cudaFree(c->d_pw);
+  cudaFree(c->d_nbr);
   cudaFree(c->d_partial);
   cudaFree(c->d_state);
 }
@@ -709,33 +804,59 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
   maps.edge_cat = c->map[0].cat;
   maps.surf_cat = c->map[1].cat;
   const int he = c->map[0].ready ? 1 : 0, hs = c->map[1].ready ? 1 : 0;
-  const int grid = div_up(upper > 0 ? upper : 1, MATCH_BLOCK);
-  const int stride = c->prm.max_points;
+  const int up = upper > 0 ? upper : 1;
+  // persistent-style grids: a few CTAs per SM, grid-stride over the queries
+  int fit_grid = div_up(up, MATCH_BLOCK);
+  if (fit_grid > 148 * 4) fit_grid = 148 * 4;
+  int eval_grid = div_up(up, MATCH_BLOCK);
+  if (eval_grid > 148 * 2) eval_grid = 148 * 2;
+  RecBufs rb;
+  rb.d = c->d_rec;
+  rb.pl = c->d_recf;
+  rb.kind = c->d_ok;
+  rb.stride = c->prm.max_points;
+  QueryBufs qb;
+  qb.keys = c->q_keys;
+  qb.vals = c->q_vals;
+  qb.pw = c->d_pw;
+  // bits of a query sort key: 12 (L1, L2) + the wider of the two maps' packed L0 coordinates, + kind bit
+  int kb = 12;
+  for (int k = 0; k < 2; ++k) {
+    const MapDev& md = c->map[k].host;
+    int b = 12 + (c->map[k].ready ? md.bits[0] + md.bits[1] + md.bits[2] : 0);
+    if (b > kb) kb = b;
+  }
   for (int i = 0; i < 7; ++i) c->h_pose[i] = pose[i];
   LM_CUDA(cudaMemcpyAsync(c->d_state->cand, c->h_pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   LM_LAUNCH(c, k_state_init, 1, 32, 0, c->d_state, c->d_state->cand);
   const double alg_bytes = 16.0 * ((double)upper + (double)c->map[0].n_host + (double)c->map[1].n_host) + 216.0;
-  if (solver == LMSF_SOLVER_GN) {
-    for (int it = 0; it < outer_count; ++it) {
-      sp.iter = it;
-      StageScope scope(c, LMSF_STAGE_MATCH);
-      LM_LAUNCH(c, k_match, grid, MATCH_BLOCK, 0, c->d_feat, c->ex.counts, maps, he, hs, c->d_state, c->d_rec,
-                c->d_ok, stride, c->d_partial, sp);
-      c->match_bytes += alg_bytes;
+  for (int it = 0; it < outer_count; ++it) {
+    sp.iter = it;
+    {
+      StageScope scope(c, LMSF_STAGE_ASSOC);
+      LM_LAUNCH(c, k_assoc, div_up(up, 256), 256, 0, c->d_feat, c->ex.counts, c->d_state, c->map[0].dev, c->map[1].dev,
+                kb, up, solver, qb);
+      size_t tmp = c->cub_tmp_bytes;
+      LM_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->q_keys, c->q_keys_alt, c->q_vals, c->q_vals_alt, up,
+                                              0, kb + 2, c->stream));
+      c->launches++;
     }
-  } else {
-    for (int it = 0; it < outer_count; ++it) {
-      sp.iter = it;
-      {
-        StageScope scope(c, LMSF_STAGE_MATCH);
-        LM_LAUNCH(c, k_match, grid, MATCH_BLOCK, 0, c->d_feat, c->ex.counts, maps, he, hs, c->d_state, c->d_rec,
-                  c->d_ok, stride, c->d_partial, sp);
-        c->match_bytes += alg_bytes;
-      }
+    {
+      StageScope scope(c, LMSF_STAGE_MATCH);
+      LM_LAUNCH(c, k_knn, div_up(up, 128), 128, 0, c->q_vals_alt, c->d_pw, c->ex.counts, c->d_state, maps, he, hs, up,
+                solver, c->d_nbr);
+      c->match_bytes += alg_bytes;
+      c->match_launches += 1;
+    }
+    {
+      StageScope scope(c, LMSF_STAGE_FIT);
+      LM_LAUNCH(c, k_fit, fit_grid, MATCH_BLOCK, 0, c->d_feat, c->q_vals_alt, c->d_pw, c->d_nbr, c->ex.counts, maps,
+                up, c->d_state, rb, c->d_partial, sp);
+    }
+    if (solver == LMSF_SOLVER_HUBER_LM) {
       StageScope scope(c, LMSF_STAGE_SOLVE);
       for (int k = 0; k < c->prm.lm_inner_iters; ++k)
-        LM_LAUNCH(c, k_lm_eval, grid, MATCH_BLOCK, 0, c->d_feat, c->ex.counts, c->d_state, c->d_rec, c->d_ok, stride,
-                  c->d_partial, sp);
+        LM_LAUNCH(c, k_lm_eval, eval_grid, MATCH_BLOCK, 0, up, c->d_state, rb, c->d_partial, sp);
     }
   }
   LM_CUDA(cudaGetLastError());

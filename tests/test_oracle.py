@@ -1,0 +1,484 @@
+"""CPU tests of the oracle (no GPU): golden fixtures, numpy / scipy cross-checks of its algebra and of
+its Huber-LM loop, independent numpy restatements of feature extraction and the voxel grid, and the
+reference's own vendored nanoflann (oracle/_ref) as an exact-kNN cross-check."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+from conftest import pose_err
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+# ---------------------------------------------------------------- golden fixtures
+def test_golden_fixture_reproduced(oracle_lib):
+    g = np.load(os.path.join(GOLD, "vlp16_small.npz"))
+    o = oracle_lib.context(0, n_scans=16, oracle_knn_mode=1)
+    lab, e0, f0 = o.extract_features(g["sweep0"])
+    assert np.array_equal(lab, g["label0"])
+    assert len(e0) == int(g["n_edge0"]) and len(f0) == int(g["n_surf0"])
+    assert np.array_equal(bits(e0), bits(g["edge0"])) and np.array_equal(bits(f0[:64]), bits(g["surf0_head"]))
+    vox, mem = o.voxel_downsample(f0, 0.4)
+    assert np.array_equal(mem, g["mem"]) and np.array_equal(bits(vox), bits(g["vox"]))
+    o.map_set(0, e0)
+    o.map_set(1, vox)
+    _, e1, f1 = o.extract_features(g["sweep1"])
+    idx, d2 = o.knn5(1, g["q"])
+    assert np.array_equal(idx, g["knn_idx"]) and np.array_equal(bits(d2), bits(g["knn_d2"]))
+    ok, out = o.match(1, g["q"])
+    assert np.array_equal(ok, g["match_ok"]) and np.allclose(out, g["match_out"], rtol=0, atol=1e-13)
+    ok, out = o.match(0, np.ascontiguousarray(e1[:, :3]))
+    assert np.array_equal(ok, g["ematch_ok"]) and np.allclose(out, g["ematch_out"], rtol=0, atol=1e-13)
+    o.set_lm_outer(10)
+    p, st = o.register(e1, f1, solver=1)
+    assert np.allclose(p, g["pose_lm"], rtol=0, atol=1e-11)
+    assert [st["outer_iters"], st["n_edge_matched"], st["n_surf_matched"], st["lm_steps_total"],
+            st["lm_steps_accepted"]] == list(g["lm_stats"])
+    p, st = o.register(e1, f1, solver=0)
+    assert np.allclose(p, g["pose_gn"], rtol=0, atol=1e-11)
+    assert [st["outer_iters"], st["n_edge_matched"], st["n_surf_matched"], st["converged"],
+            st["degenerate"]] == list(g["gn_stats"])
+
+
+def test_golden_track_reproduced(oracle_lib, synth):
+    from make_golden import small_sweep
+    g = np.load(os.path.join(GOLD, "vlp16_small_track.npz"))
+    t = oracle_lib.context(0, n_scans=16, map_leaf_edge=0.2, map_leaf_surf=0.4)
+    for k in range(len(g["poses"])):
+        p, d, st = t.tracker_step(small_sweep(synth, k), 0.1 * k)
+        assert np.allclose(p, g["poses"][k], rtol=0, atol=1e-10), k
+        assert st["keyframe"] == g["keyframes"][k]
+
+
+# ---------------------------------------------------------------- small algebra vs numpy
+def _fn(lib, name, *argtypes):
+    f = lib.fn(name)
+    return f
+
+
+def test_symeig_vs_numpy(oracle_lib):
+    rng = np.random.default_rng(0)
+    for n, name in ((3, "symeig3"), (6, "symeig6")):
+        for trial in range(200):
+            a = rng.normal(size=(n, n)) * 10 ** rng.uniform(-3, 3)
+            a = a @ a.T if trial % 2 else (a + a.T)
+            if trial % 17 == 0:
+                a[:, 0] = a[0, :] = 0  # rank deficient
+            w = np.zeros(n)
+            v = np.zeros((n, n))
+            oracle_lib.fn(name)(a.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
+            wn, vn = np.linalg.eigh(a)
+            scale = max(1e-300, np.abs(wn).max())
+            assert np.allclose(w, wn, rtol=0, atol=1e-12 * scale)
+            assert np.all(np.diff(w) >= 0)
+            assert np.allclose(a @ v, v * w, rtol=0, atol=1e-11 * scale)
+            assert np.allclose(v.T @ v, np.eye(n), atol=1e-12)
+
+
+def test_lstsq_and_solve_vs_numpy(oracle_lib):
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        a = rng.normal(size=(5, 3)) * 10 + rng.normal(size=(1, 3)) * 30
+        b = -np.ones(5)
+        x = np.zeros(3)
+        oracle_lib.fn("lstsq53")(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p))
+        xn = np.linalg.lstsq(a, b, rcond=None)[0]
+        assert np.allclose(x, xn, rtol=1e-9, atol=1e-12)
+        j = rng.normal(size=(50, 6))
+        h = j.T @ j
+        g = rng.normal(size=6)
+        y = np.zeros(6)
+        oracle_lib.fn("solve6")(h.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p))
+        assert np.allclose(y, np.linalg.solve(h, g), rtol=1e-8, atol=1e-12)
+    # rank-deficient 5x3 (collinear neighbours through the origin direction): basic solution is finite
+    a = np.outer(np.arange(1, 6.0), [1.0, 2.0, 3.0])
+    x = np.zeros(3)
+    oracle_lib.fn("lstsq53")(a.ctypes.data_as(C.c_void_p), (-np.ones(5)).ctypes.data_as(C.c_void_p),
+                             x.ctypes.data_as(C.c_void_p))
+    assert np.all(np.isfinite(x))
+
+
+def test_se3_exp_vs_scipy(oracle_lib):
+    from scipy.linalg import expm
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(2)
+    for k in range(100):
+        d = rng.normal(size=6) * 10 ** rng.uniform(-6, 0)
+        q = np.zeros(4)
+        t = np.zeros(3)
+        oracle_lib.fn("se3_exp")(d.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p))
+        xi = np.zeros((4, 4))
+        xi[:3, :3] = [[0, -d[2], d[1]], [d[2], 0, -d[0]], [-d[1], d[0], 0]]
+        xi[:3, 3] = d[3:]
+        T = expm(xi)
+        assert np.allclose(Rotation.from_quat(q).as_matrix(), T[:3, :3], atol=1e-9)
+        assert np.allclose(t, T[:3, 3], atol=1e-9)
+
+
+# ---------------------------------------------------------------- independent restatement: feature extraction
+def _py_extract(sw, n_scans=16, min_d=2.0, max_d=80.0, thresh=1.0):
+    """Straight numpy/Python transcription of LOAMFeatureProcessor_base.hpp:59-343 (VLP-16 branch)."""
+    f32 = np.float32
+    rings = [[] for _ in range(n_scans)]
+    for i, p in enumerate(sw):
+        s = f32(p[0] * p[0]) + f32(p[1] * p[1])
+        dist = math.sqrt(float(f32(s)))
+        if dist > max_d or dist < min_d:
+            continue
+        ang = math.atan(float(p[2]) / dist) * 180 / math.pi
+        sid = int((ang + 15) / 2 + 0.5)
+        if sid > n_scans - 1 or sid < 0:
+            continue
+        rings[sid].append(i)
+    label = np.zeros(len(sw), np.uint8)
+    edge, surf = [], []
+    for ids in rings:
+        P = len(ids)
+        if P < 20 or P - 10 < 6:
+            continue
+        pc = sw[ids]
+        x, y, z = pc[:, 0], pc[:, 1], pc[:, 2]
+        dis = np.zeros(P, int)
+        is_edge = np.zeros(P, int)
+        j = 5
+        while j < P - 6:
+            a0 = math.atan2(float(x[j]), float(y[j]))
+            a1 = math.atan2(float(x[j + 1]), float(y[j + 1]))
+            da = abs(a0 - a1)
+            if da > math.pi:
+                da = math.pi * 2 - da
+            if da > 0.0175:
+                dis[j - 5:j + 6] = 1
+                j += 5
+                continue
+            d0 = math.sqrt(float(f32(f32(f32(x[j] * x[j]) + f32(y[j] * y[j])) + f32(z[j] * z[j]))))
+            d1 = math.sqrt(float(f32(f32(f32(x[j + 1] * x[j + 1]) + f32(y[j + 1] * y[j + 1])) + f32(z[j + 1] * z[j + 1]))))
+            ang = math.atan2(d0 * da, d1 - d0) if d0 < d1 else math.atan2(d1 * da, d0 - d1)
+            if ang <= 0.17:
+                if d0 < d1:
+                    dis[j + 1:j + 6] = 1
+                    j += 4
+                else:
+                    dis[j - 5:j + 1] = 1
+            j += 1
+        ln = (P - 10) // 6
+        for k in range(6):
+            s = 5 + ln * k
+            e = P - 6 if k == 5 else s + ln - 1
+            cur = []
+            for j in range(s, e + 1):
+                d = []
+                for c in (x, y, z):
+                    acc = f32(c[j - 5]) + f32(c[j - 4])
+                    for m in (-3, -2, -1):
+                        acc = f32(acc + c[j + m])
+                    acc = f32(acc - f32(f32(10) * c[j]))
+                    for m in (1, 2, 3, 4, 5):
+                        acc = f32(acc + c[j + m])
+                    d.append(float(acc))
+                cur.append((d[0] * d[0] + d[1] * d[1] + d[2] * d[2], j))
+            cur.sort()
+            picked = 0
+            for val, ind in reversed(cur):
+                if dis[ind] == 0:
+                    if val <= thresh:
+                        break
+                    picked += 1
+                    if picked <= 20:
+                        edge.append(ids[ind])
+                        is_edge[ind] = 1
+                    else:
+                        break
+                    for m in range(1, 6):
+                        dis[min(ind + m, P - 1)] = 1
+                        dis[max(ind - m, 0)] = 1
+            for val, ind in cur:
+                if not is_edge[ind]:
+                    surf.append(ids[ind])
+    label[edge] = 1
+    label[surf] = 2
+    return label, sw[edge], sw[surf]
+
+
+def test_extract_vs_python_restatement(oracle_lib, synth):
+    from make_golden import small_sweep
+    o = oracle_lib.context(0, n_scans=16)
+    for k, kw in ((0, {}), (5, {})):
+        sw = small_sweep(synth, k)
+        if k == 5:
+            sw = sw[np.random.default_rng(3).random(len(sw)) > 0.2]   # ragged rings
+        lab, e, s = o.extract_features(sw)
+        plab, pe, ps = _py_extract(sw)
+        assert np.array_equal(lab, plab)
+        assert np.array_equal(bits(e), bits(pe)) and np.array_equal(bits(s), bits(ps))
+        assert (lab == 1).sum() > 10
+
+
+def test_extract_edge_cases(oracle_lib, synth):
+    o = oracle_lib.context(0, n_scans=16)
+    lab, e, s = o.extract_features(np.zeros((0, 4), np.float32))
+    assert len(lab) == 0 and len(e) == 0 and len(s) == 0
+    sw = synth.make_sweep(synth.vlp16(), 0)[: 16 * 15]        # < 20 points per ring
+    lab, e, s = o.extract_features(sw)
+    assert lab.sum() == 0 and len(e) == 0 and len(s) == 0
+    sw = synth.make_sweep(synth.vlp16(), 0)
+    lab, e, s = o.extract_features(sw)
+    # per ring the first / last five points are never features; <= 20 edges per sector
+    assert len(e) <= 16 * 6 * 20 and len(e) + len(s) <= len(sw) - 16 * 10
+    o64 = oracle_lib.context(0, n_scans=64)
+    sw = synth.make_sweep(synth.hdl64(), 0)
+    lab, e, s = o64.extract_features(sw)
+    assert len(e) <= 64 * 6 * 20 and len(e) > 500 and len(s) > 100000
+
+
+# ---------------------------------------------------------------- independent restatement: voxel grid
+def _py_voxel(pts, leaf):
+    f32 = np.float32
+    fin = np.isfinite(pts[:, :3]).all(1)
+    p = pts[fin]
+    src = np.nonzero(fin)[0]
+    inv = f32(1.0) / f32(leaf)
+    mn, mx = p[:, :3].min(0), p[:, :3].max(0)
+    minb = np.floor(mn * inv).astype(np.int64)
+    maxb = np.floor(mx * inv).astype(np.int64)
+    div = maxb - minb + 1
+    ijk = (np.floor(p[:, :3] * inv) - minb.astype(f32)).astype(np.int64)
+    idx = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+    order = np.lexsort((src, idx))
+    out, mem = [], np.full(len(pts), -1, np.int32)
+    k = 0
+    while k < len(order):
+        e = k
+        acc = np.zeros(4, f32)
+        while e < len(order) and idx[order[e]] == idx[order[k]]:
+            acc = (acc + p[order[e]]).astype(f32)
+            mem[src[order[e]]] = len(out)
+            e += 1
+        out.append(acc / f32(e - k))
+        k = e
+    return np.array(out, f32), mem
+
+
+def test_voxel_vs_python_restatement(oracle_lib, synth):
+    from make_golden import small_sweep
+    o = oracle_lib.context(0, n_scans=16)
+    sw = small_sweep(synth, 2)
+    sw[::40, 1] = np.nan
+    for leaf in (0.2, 0.5, 1.3):
+        v, m = o.voxel_downsample(sw, leaf)
+        pv, pm = _py_voxel(sw, leaf)
+        assert np.array_equal(m, pm)
+        assert np.array_equal(bits(v), bits(pv))
+    # int32 overflow guard: output = input
+    v, m = o.voxel_downsample(sw[np.isfinite(sw).all(1)], 1e-3)
+    assert len(v) == np.isfinite(sw).all(1).sum() and np.array_equal(m, np.arange(len(v)))
+    v, m = o.voxel_downsample(np.zeros((0, 4), np.float32), 0.2)
+    assert len(v) == 0
+
+
+# ---------------------------------------------------------------- kNN cross-checks
+def _cloud(synth, n_sweeps=3):
+    sensor = synth.vlp16()
+    return np.ascontiguousarray(np.concatenate([synth.make_sweep(sensor, k) for k in range(n_sweeps)]))
+
+
+def test_kdtree_equals_brute_force(oracle_lib, synth):
+    m = _cloud(synth)
+    q = np.ascontiguousarray(synth.make_sweep(synth.vlp16(), 4)[::9, :3])
+    a = oracle_lib.context(0, oracle_knn_mode=0)
+    b = oracle_lib.context(0, oracle_knn_mode=1)
+    a.map_set(1, m)
+    b.map_set(1, m)
+    ia, da = a.knn5(1, q)
+    ib, db = b.knn5(1, q)
+    assert np.array_equal(ia, ib) and np.array_equal(bits(da), bits(db))
+
+
+def test_knn_vs_reference_nanoflann(oracle_lib, synth):
+    """The reference's own vendored nanoflann 1.3.2, compiled where it lies (oracle/Makefile -> oracle/_ref)."""
+    if not os.path.exists(entry.REF_NANOFLANN_LIB):
+        pytest.skip("oracle/_ref/libref_nanoflann.so not built (no /root/reference on this box)")
+    ref = C.CDLL(entry.REF_NANOFLANN_LIB)
+    m = _cloud(synth, 2)
+    q = np.ascontiguousarray(synth.make_sweep(synth.vlp16(), 3)[::15, :3])
+    idx = np.zeros((len(q), 5), np.int32)
+    d2 = np.zeros((len(q), 5), np.float32)
+    ref.ref_nanoflann_knn5(m.ctypes.data_as(C.c_void_p), len(m), q.ctypes.data_as(C.c_void_p), len(q),
+                           idx.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p))
+    o = oracle_lib.context(0, oracle_knn_mode=0)
+    o.map_set(0, m)
+    io, do = o.knn5(0, q)
+    inside = d2 < 1.0
+    # identical distances everywhere; identical indices except at exact distance ties
+    assert np.array_equal(bits(np.where(inside, d2, np.inf)), bits(do))
+    same = (np.where(inside, idx, -1) == io)
+    tie = np.zeros_like(same)
+    tie[:, 1:] |= (d2[:, 1:] == d2[:, :-1])
+    tie[:, :-1] |= (d2[:, :-1] == d2[:, 1:])
+    assert np.all(same | tie)
+    assert same.mean() > 0.999
+
+
+# ---------------------------------------------------------------- Huber-LM vs a numpy restatement of the Ceres loop
+def _np_lm(edge, surf, x, huber=0.1, max_iters=4):
+    from scipy.spatial.transform import Rotation
+
+    def rot(q, v):
+        u = q[:3]
+        uv = 2 * np.cross(u, v)
+        return v + q[3] * uv + np.cross(u, uv)
+
+    def qmul(a, b):
+        return np.array([a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1],
+                         a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2],
+                         a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0],
+                         a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2]])
+
+    def evaluate(x):
+        q, t = x[:4], x[4:]
+        J, r = [], []
+        for e in edge:
+            lp = rot(q, e[:3]) + t
+            a, b = e[3:6], e[6:9]
+            nu = np.cross(lp - a, lp - b)
+            de = a - b
+            res = np.linalg.norm(nu) / np.linalg.norm(de)
+            sk = lambda v: np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+            dp = np.hstack([-sk(lp), np.eye(3)])
+            J.append(-(nu / np.linalg.norm(nu)) @ sk(de) @ dp / np.linalg.norm(de))
+            r.append(res)
+        for s in surf:
+            lp = rot(q, s[:3]) + t
+            n = s[3:6]
+            sk = lambda v: np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+            J.append(n @ np.hstack([-sk(lp), np.eye(3)]))
+            r.append(n @ lp + s[6])
+        J, r = np.array(J), np.array(r)
+        s2 = r * r
+        out = s2 > huber ** 2
+        rho0 = np.where(out, 2 * huber * np.sqrt(s2) - huber ** 2, s2)
+        sc = np.where(out, np.sqrt(huber / np.sqrt(np.maximum(s2, 1e-300))), 1.0)
+        return 0.5 * rho0.sum(), J * sc[:, None], r * sc
+
+    def plus(x, d):
+        om, up = d[:3], d[3:]
+        th = np.linalg.norm(om)
+        dq = np.append(np.sin(th / 2) / th * om, np.cos(th / 2)) if th > 1e-10 else np.append(0.5 * om, 1.0)
+        O = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0]])
+        Jl = np.eye(3) + (1 - np.cos(th)) / th ** 2 * O + (th - np.sin(th)) / th ** 3 * O @ O if th > 1e-10 else np.eye(3)
+        return np.concatenate([qmul(dq, x[:4]), rot(dq, x[4:]) + Jl @ up])
+
+    x = np.array(x, float)
+    cost, J, r = evaluate(x)
+    scale = 1.0 / (1.0 + np.linalg.norm(J, axis=0))
+    radius, dec, steps, acc = 1e4, 2.0, 0, 0
+    for _ in range(max_iters):
+        steps += 1
+        Js = J * scale
+        diag = np.clip((Js * Js).sum(0), 1e-6, 1e32)
+        A = np.vstack([Js, np.diag(np.sqrt(diag / radius))])
+        step = -np.linalg.lstsq(A, np.concatenate([r, np.zeros(6)]), rcond=None)[0]
+        mr = Js @ step
+        mcc = -mr @ (r + mr / 2)
+        if not mcc > 0:
+            radius *= 0.5
+            continue
+        cand = plus(x, step * scale)
+        c2, J2, r2 = evaluate(cand)
+        if np.linalg.norm(x - cand) <= 1e-8 * (np.linalg.norm(x) + 1e-8):
+            break
+        if abs(cost - c2) <= 1e-6 * cost:
+            break
+        rho = (cost - c2) / mcc
+        if rho > 1e-3:
+            x, cost, J, r = cand, c2, J2, r2
+            acc += 1
+            radius = min(1e16, radius / max(1 / 3, 1 - (2 * rho - 1) ** 3))
+            dec = 2.0
+        else:
+            radius /= dec
+            dec *= 2
+    return x, steps, acc, cost
+
+
+def test_lm_solve_vs_numpy_ceres_restatement(oracle_lib):
+    rng = np.random.default_rng(4)
+    from scipy.spatial.transform import Rotation
+    for trial in range(6):
+        Rt = Rotation.from_rotvec(rng.normal(size=3) * 0.02)
+        tt = rng.normal(size=3) * 0.2
+        surf, edge = [], []
+        for _ in range(150):
+            n = rng.normal(size=3)
+            n /= np.linalg.norm(n)
+            pw = rng.uniform(-20, 20, 3)
+            pl = Rt.inv().apply(pw - tt)
+            noise = rng.normal() * 0.01 + (0.5 if rng.random() < 0.05 else 0.0)     # some Huber outliers
+            surf.append(np.concatenate([pl, n, [-(n @ pw) + noise]]))
+        for _ in range(40):
+            u = rng.normal(size=3)
+            u /= np.linalg.norm(u)
+            pw = rng.uniform(-20, 20, 3)
+            c = pw + rng.normal(size=3) * 0.01
+            pl = Rt.inv().apply(pw - tt)
+            edge.append(np.concatenate([pl, c + 0.1 * u, c - 0.1 * u]))
+        surf, edge = np.array(surf), np.array(edge)
+        x0 = np.array([0, 0, 0, 1.0, 0, 0, 0])
+        xn, sn, an, cn = _np_lm(edge, surf, x0, 0.1, 4)
+        x = x0.copy()
+        steps, acc, cost = C.c_int(0), C.c_int(0), C.c_double(0)
+        oracle_lib.fn("lm_solve")(edge.ctypes.data_as(C.c_void_p), len(edge), surf.ctypes.data_as(C.c_void_p), len(surf),
+                                  C.c_double(0.1), 4, x.ctypes.data_as(C.c_void_p), C.byref(steps), C.byref(acc),
+                                  C.byref(cost))
+        assert (steps.value, acc.value) == (sn, an)
+        assert np.allclose(x, xn, rtol=0, atol=1e-9)
+        assert abs(cost.value - cn) <= 1e-9 * max(1.0, cn)
+        # and it actually registers: close to the true transform after one solve from identity
+        dt, dr = pose_err(x, np.concatenate([Rt.as_quat(), tt]))
+        assert dt < 0.05 and dr < 0.01
+
+
+# ---------------------------------------------------------------- registration / tracker behaviour
+def test_registration_recovers_known_motion(oracle_lib, synth):
+    o = oracle_lib.context(0, n_scans=64, oracle_threads=8)
+    sensor = synth.hdl64()
+    _, e0, s0 = o.extract_features(synth.make_sweep(sensor, 0))
+    o.map_set(0, e0)
+    o.map_set(1, s0)
+    _, e1, s1 = o.extract_features(synth.make_sweep(sensor, 2))
+    gt = synth.rel_gt_pose(2)
+    for solver in (0, 1):
+        o.set_lm_outer(10)
+        p, st = o.register(e1, s1, solver=solver)
+        dt, dr = pose_err(p, gt)
+        assert dt < 0.02 and dr < 2e-3, (solver, dt, dr)
+
+
+def test_lm_outer_budget_is_stateful(oracle_lib, synth):
+    from make_golden import small_sweep
+    o = oracle_lib.context(0, n_scans=16)
+    _, e, s = o.extract_features(small_sweep(synth, 0))
+    o.map_set(0, e)
+    o.map_set(1, s)
+    outers = [o.register(e, s, solver=1)[1]["outer_iters"] for _ in range(10)]
+    assert outers == [9, 8, 7, 6, 5, 4, 3, 2, 2, 2]      # ceres_edgeSurfFeatureRegistration.hpp:100-101
+
+
+def test_tracker_keyframes_and_window(oracle_lib, synth):
+    from make_golden import small_sweep
+    o = oracle_lib.context(0, n_scans=16, window=2, map_leaf_edge=0.2, map_leaf_surf=0.4, oracle_threads=4)
+    sizes = []
+    for k in range(9):
+        p, d, st = o.tracker_step(small_sweep(synth, k), 0.1 * k)
+        sizes.append((st["keyframe"], st["map_surf"]))
+        assert st["first"] == (1 if k == 0 else 0)
+    assert sum(1 for kf, _ in sizes if kf == 1) >= 3
+    assert max(ms for _, ms in sizes) < 2 * 7200       # the window never holds more than two frames
