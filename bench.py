@@ -54,37 +54,54 @@ def make_sequence(n_sweeps: int, seq: int):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region, polled in-process through NVML (no fork:
+    spawning nvidia-smi from a process with CUDA loaded stalls the launching thread for tens of ms)."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index: int):
+    def __init__(self, index: int, period: float = 0.005):
         super().__init__(daemon=True)
         self.index = index
+        self.period = period
         self.samples = []
+        self.active = threading.Event()
         self.stop_flag = threading.Event()
+        self.err = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            self.err = repr(e)
 
     def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
         while not self.stop_flag.is_set():
+            # poll all the time (NVML's first calls take tens of ms and stall CUDA launches from other
+            # threads meanwhile: that must happen during warm-up), record only inside the timed region
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                if self.active.is_set():
+                    self.samples.append((sm, rs))
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+            self.stop_flag.wait(self.period)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable: " + str(self.err)]}
+        nv = self.nv
+        sm = sorted(s[0] for s in self.samples)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        reasons = [n for n, b in bits.items() if any(s[1] & b for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sm)}
 
 
 def peaks():
@@ -121,6 +138,9 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
     n_pts = [int(s.shape[0]) for s in sweeps]
 
+    sampler = ClockSampler(local)
+    sampler.start()
+
     def barrier():
         if use_dist:
             dist.barrier()
@@ -139,35 +159,43 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         per = []
         stats = []
+        flush_host = 0.0
+        sampler.active.set()
         t_wall0 = time.perf_counter()
         e0.record(stream)
         for k in range(W + 1, W + K + 1):
+            tf = time.perf_counter()
             with torch.cuda.stream(stream):
                 flush.zero_()                       # L2 flush between timed steps, inside the timed region
             t0 = time.perf_counter()
+            flush_host += t0 - tf
+            if os.environ.get('LMSF_BENCH_DEBUG'):
+                sys.stderr.write(f'flush {k} {(t0 - tf) * 1e3:.3f} ms\n')
             stats.append(step_fn(k, 0.1 * k))
             per.append((time.perf_counter() - t0) * 1e3)
         e1.record(stream)
         barrier()
+        sampler.active.clear()
         wall_ms = (time.perf_counter() - t_wall0) * 1e3
         dev_ms = e0.elapsed_time(e1)
         launches = ctx.launch_count() - l0
         prof = ctx.profile_read(reset=True) if profile else None
         ctx.profile_enable(False)
-        return dev_ms, wall_ms, per, launches, prof, stats
+        return dev_ms, wall_ms, per, launches, prof, stats, flush_host * 1e3 / K
 
     # ---- resident pass: sweeps already in HBM when the timed region starts
     d_ptrs = [ctx.dev_upload_new(s) for s in sweeps]
-    sampler = ClockSampler(local)
-    sampler.start()
-    dev_ms, wall_ms, per, launches, prof, stats = run_sequence(
-        lambda k, t: ctx.tracker_step_dev(d_ptrs[k], n_pts[k], t)[2], True)
+    dev_ms, wall_ms, per, launches, _, stats, fl1 = run_sequence(
+        lambda k, t: ctx.tracker_step_dev(d_ptrs[k], n_pts[k], t)[2], False)
     # ---- end-to-end pass: host buffers through lmsf_tracker_step (H2D of the sweep + D2H of the pose inside)
-    e_dev_ms, e_wall_ms, e_per, _, _, _ = run_sequence(lambda k, t: ctx.tracker_step(sweeps[k], t)[2], False)
+    e_dev_ms, e_wall_ms, e_per, _, _, _, fl2 = run_sequence(lambda k, t: ctx.tracker_step(sweeps[k], t)[2], False)
+    # ---- instrumented pass (not used for value): per-stage CUDA-event times on the context stream
+    p_dev_ms, _, _, _, prof, _, fl3 = run_sequence(
+        lambda k, t: ctx.tracker_step_dev(d_ptrs[k], n_pts[k], t)[2], True)
     sampler.stop_flag.set()
     sampler.join()
 
-    t_ms = torch.tensor([max(dev_ms, wall_ms if False else dev_ms), e_wall_ms], dtype=torch.float64, device=f"cuda:{local}")
+    t_ms = torch.tensor([dev_ms, e_wall_ms], dtype=torch.float64, device=f"cuda:{local}")
     if use_dist:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_ms_max = float(t_ms[0]), float(t_ms[1])
@@ -197,6 +225,8 @@ def run_ours(args):
                        "l2": "256 MiB memset between timed steps (L2 flush), inside the timed region",
                        "timing": "CUDA events on the context stream around the K steps, max over ranks",
                        "p50_ms_per_scan": float(np.median(per)), "p90_ms_per_scan": float(np.percentile(per, 90)),
+                       "max_ms_per_scan": float(np.max(per)), "wall_ms_per_step": wall_ms / K,
+                       "flush_host_ms_per_step": [fl1, fl2, fl3], "instrumented_pass_ms_per_step": p_dev_ms / K,
                        "keyframes_in_timed_region": kf,
                        "features_per_sweep": int(np.mean([s["n_edge"] + s["n_surf"] for s in stats])),
                        "map_points_end": int(stats[-1]["map_edge"] + stats[-1]["map_surf"]),
@@ -213,7 +243,7 @@ def run_ours(args):
                          "peak_source": peak_src, "traffic": traffic,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": match_ms,
                          "launches_per_step": ln["match"] / K,
-                         "share_of_step": ms["match"] / max(1e-9, dev_ms)},
+                         "share_of_step": ms["match"] / max(1e-9, p_dev_ms)},
         }
         if n_gpus == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(sweeps, W)

@@ -11,12 +11,15 @@
 // mask of its 4x4x4 L1 cells (0.25 m); every occupied L1 cell has a 64-bit mask
 // of its 4x4x4 L2 cells (0.0625 m).  Points are sorted by (L0, L1, L2) so each
 // cell at each level is one contiguous range.  Search:
-//   A  the 27 L2 cells around the query (dense regions end here: exact as soon
-//      as the 5th distance is < 0.0625^2),
-//   B  the 27 L1 cells around the query, L2 cell by L2 cell, skipping what A saw
-//      and every L2 cell whose box is farther than the current 5th distance
-//      (exact as soon as the 5th distance is < 0.25^2),
-//   C  the 27 L0 cells, pruned the same way at L0, L1 and L2 granularity.
+//   seed  (outer iterations after the first) the previous iteration's five neighbours give an
+//         upper bound of the 5th distance before anything is scanned,
+//   A     otherwise the 27 L2 cells around the query give it (dense regions end here: exact as
+//         soon as the 5th distance is < 0.0625^2),
+//   ball  with a bound < 0.25^2 the search restarts as a row sweep over exactly the L2 cells the
+//         ball of that radius touches, nearest rows first; insertions are rare because the bound
+//         is already tight,
+//   B, C  without one (sparse surroundings) the 27 L1 cells, then the 27 L0 cells, are swept
+//         cell by cell, skipping every cell whose box is farther than the current 5th distance.
 // Cell sizes are powers of two, so cell indices and cell bounds are exact in
 // fp32 and the box distance — computed with the same rounding sequence as a
 // point distance — never exceeds the distance of a point inside the box:
@@ -49,6 +52,14 @@ struct Top5 {
       id[k] = -1;
     }
   }
+  // five points are known to exist with d2 <= bound: accept d2 <= bound, ties included
+  __device__ __forceinline__ void reset_inclusive(float bound) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      d[k] = bound;
+      id[k] = 0x7fffffff;
+    }
+  }
   __device__ __forceinline__ void add(float dd, int ii) {
     if (dd < d[4] || (dd == d[4] && ii < id[4])) {
       d[4] = dd;
@@ -67,7 +78,7 @@ struct Top5 {
       }
     }
   }
-  __device__ __forceinline__ bool full() const { return id[4] >= 0; }
+  __device__ __forceinline__ bool full() const { return id[4] >= 0 && id[4] != 0x7fffffff; }
 };
 
 __device__ __forceinline__ unsigned hash_cell(unsigned long long k) {
@@ -84,6 +95,19 @@ __device__ __forceinline__ unsigned long long pack_cell(const MapDev& md, int cx
          (unsigned long long)(unsigned)cx;
 }
 
+struct KnnStats {  // debug counters (debug_stats.cu): per-query work and the pass the search ended in
+  int cand, boxes, lookups, level;
+};
+#ifdef LMSF_KNN_STATS
+#define KSTAT(x) x
+#define KS_DECL , KnnStats& ks
+#define KS_PASS , ks
+#else
+#define KSTAT(x)
+#define KS_DECL
+#define KS_PASS
+#endif
+
 // one-entry cache in front of the hash probe: neighbouring cells mostly share their L0 cell
 struct CellCursor {
   unsigned long long key;
@@ -91,7 +115,8 @@ struct CellCursor {
 };
 
 __device__ __forceinline__ const CellRec* find_cell(const MapView& mv, const MapDev& md, CellCursor& cur, int cx,
-                                                    int cy, int cz) {
+                                                    int cy, int cz KS_DECL) {
+  KSTAT(ks.lookups++;)
   if (cx < 0 || cy < 0 || cz < 0 || cx >= md.dim[0] || cy >= md.dim[1] || cz >= md.dim[2]) return nullptr;
   unsigned long long key = pack_cell(md, cx, cy, cz);
   if (key == cur.key) return cur.rec;
@@ -112,7 +137,8 @@ __device__ __forceinline__ const CellRec* find_cell(const MapView& mv, const Map
 }
 
 __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz,
-                                           Top5& nb) {
+                                           Top5& nb KS_DECL) {
+  KSTAT(ks.cand += e - s;)
   for (int p = s; p < e; ++p) {
     float4 m = __ldg(&pts[p]);
     float dx = m.x - qx, dy = m.y - qy, dz = m.z - qz;
@@ -137,9 +163,9 @@ __device__ __forceinline__ float box_d2(float qx, float qy, float qz, int cx, in
   return r;
 }
 
-// scan the L2 cells of one L1 cell (absolute L1 coords ax1..az1) that survive the box test and lie outside `skip`
+// scan the L2 cells of one L1 cell (absolute L1 coords ax1..az1) that survive the box test
 __device__ __forceinline__ void sweep_l1_cell(const MapView& mv, int l1, int ax1, int ay1, int az1, float qx, float qy,
-                                              float qz, int sx, int sy, int sz, Top5& nb) {
+                                              float qz, Top5& nb KS_DECL) {
   unsigned long long m2 = mv.l1_mask[l1];
   int base = mv.l1_first[l1];
   int rank = 0;
@@ -147,39 +173,46 @@ __device__ __forceinline__ void sweep_l1_cell(const MapView& mv, int l1, int ax1
     int f2 = __ffsll((long long)m2) - 1;
     m2 &= m2 - 1;
     int ax2 = (ax1 << 2) | (f2 & 3), ay2 = (ay1 << 2) | ((f2 >> 2) & 3), az2 = (az1 << 2) | (f2 >> 4);
-    bool seen = (ax2 >= sx - 1 && ax2 <= sx + 1 && ay2 >= sy - 1 && ay2 <= sy + 1 && az2 >= sz - 1 && az2 <= sz + 1);
-    if (!seen && !(box_d2(qx, qy, qz, ax2, ay2, az2, 0.0625f) > nb.d[4])) {
+    KSTAT(ks.boxes++;)
+    if (!(box_d2(qx, qy, qz, ax2, ay2, az2, 0.0625f) > nb.d[4])) {
       int s = mv.l2_start[base + rank];
       int e = mv.l2_start[base + rank + 1];
-      scan_range(mv.sorted, s, e, qx, qy, qz, nb);
+      scan_range(mv.sorted, s, e, qx, qy, qz, nb KS_PASS);
     }
     ++rank;
   }
 }
 
-// exact 5-NN within squared radius 1.0; nb.id[k] = -1 for unfilled slots
-__device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, float qz, Top5& nb) {
-  nb.reset();
-  const MapDev md = *mv.dev;
-  if (md.n <= 0) return;
-  if (!(fabsf(qx) < 2.0e5f && fabsf(qy) < 2.0e5f && fabsf(qz) < 2.0e5f)) return;
-  // absolute L2 cell coordinates of the query (x16 is exact in fp32), and the grid origin at each level
-  const int ax = (int)floorf(qx * 16.0f), ay = (int)floorf(qy * 16.0f), az = (int)floorf(qz * 16.0f);
+// Row sweep at L2 resolution over the cells that intersect the ball of squared radius nb.d[4] (the
+// running 5th distance, which only shrinks) around q, limited to +-R cells.  Each (z,y) row is a run
+// of x cells that crosses at most R/2+2 L1 cells; inside one L1 cell a run is one contiguous range.
+__device__ __forceinline__ void sweep_ball(const MapView& mv, const MapDev& md, CellCursor& cur, float qx, float qy,
+                                           float qz, int ax, int ay, int az, int R, Top5& nb KS_DECL) {
   const int ox = md.min_c[0], oy = md.min_c[1], oz = md.min_c[2];
-  CellCursor cur;
-  cur.key = ~0ull;
-  cur.rec = nullptr;
-  // ---- A: 3x3x3 L2 cells; each (z,y) row is at most two runs of x sub-cells inside one L1 cell each
-  for (int dz = -1; dz <= 1; ++dz) {
+  for (int kz = 0; kz <= 2 * R; ++kz) {
+    int dz = (kz + 1) >> 1;  // 0, +1, -1, +2, -2 ...: nearest layers first so the bound shrinks early
+    if (!(kz & 1)) dz = -dz;
     int z = az + dz;
-    for (int dy = -1; dy <= 1; ++dy) {
+    float gz = axis_gap(qz, z, 0.0625f);
+    float gz2 = gz * gz;
+    if (gz2 > nb.d[4]) continue;
+    for (int ky = 0; ky <= 2 * R; ++ky) {
+      int dy = (ky + 1) >> 1;
+      if (!(ky & 1)) dy = -dy;
       int y = ay + dy;
+      float gy = axis_gap(qy, y, 0.0625f);
+      float g2 = gy * gy + gz2;  // lower bound (same rounding order as a point distance's y,z terms added first)
+      KSTAT(ks.boxes++;)
+      if (g2 > nb.d[4]) continue;
+      // x extent of the ball in this row (slightly widened; a superset is always correct)
+      float rx = sqrtf(fmaxf(nb.d[4] - g2, 0.0f)) * 1.0001f + 1.0e-6f;
+      int x0 = max((int)floorf((qx - rx) * 16.0f), ax - R);
+      int x1 = min((int)floorf((qx + rx) * 16.0f), ax + R);
       int row2 = ((z & 3) << 4) | ((y & 3) << 2);
       int row1 = (((z >> 2) & 3) << 4) | (((y >> 2) & 3) << 2);
-      int x0 = ax - 1, x1 = ax + 1;
-      int la = x0 >> 2, lb = x1 >> 2;  // L1 x coords of the run's ends
+      int la = x0 >> 2, lb = x1 >> 2;
       for (int lx = la; lx <= lb; ++lx) {
-        const CellRec* rec = find_cell(mv, md, cur, (lx >> 2) - ox, (y >> 4) - oy, (z >> 4) - oz);
+        const CellRec* rec = find_cell(mv, md, cur, (lx >> 2) - ox, (y >> 4) - oy, (z >> 4) - oz KS_PASS);
         if (!rec) continue;
         int f1 = row1 | (lx & 3);
         unsigned long long m1 = rec->mask;
@@ -193,12 +226,63 @@ __device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, floa
         unsigned long long sub = m2 & ((2ull << fhi) - 1ull) & ~below;
         if (!sub) continue;
         int b = mv.l1_first[l1] + __popcll(m2 & below);
-        scan_range(mv.sorted, mv.l2_start[b], mv.l2_start[b + __popcll(sub)], qx, qy, qz, nb);
+        scan_range(mv.sorted, mv.l2_start[b], mv.l2_start[b + __popcll(sub)], qx, qy, qz, nb KS_PASS);
       }
     }
   }
-  if (nb.full() && nb.d[4] < 0.00390625f) return;
-  // ---- B: 3x3x3 L1 cells, L2 cell by L2 cell with box pruning, skipping what A scanned
+}
+
+// exact 5-NN within squared radius 1.0; nb.id[k] = -1 for unfilled slots.
+// seed (optional): five map indices believed to be close to q (the previous outer iteration's
+// neighbours); they only provide the initial search radius, never the result.
+__device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, float qz, Top5& nb,
+                                     const float4* __restrict__ cat, const int* seed KS_DECL) {
+  nb.reset();
+  const MapDev md = *mv.dev;
+  if (md.n <= 0) return;
+  if (!(fabsf(qx) < 2.0e5f && fabsf(qy) < 2.0e5f && fabsf(qz) < 2.0e5f)) return;
+  // absolute L2 cell coordinates of the query (x16 is exact in fp32)
+  const int ax = (int)floorf(qx * 16.0f), ay = (int)floorf(qy * 16.0f), az = (int)floorf(qz * 16.0f);
+  const int ox = md.min_c[0], oy = md.min_c[1], oz = md.min_c[2];
+  CellCursor cur;
+  cur.key = ~0ull;
+  cur.rec = nullptr;
+  float bound = 2.0f;  // > 1: no usable bound yet
+  if (seed != nullptr && seed[4] >= 0) {
+    bound = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      float4 m = __ldg(&cat[seed[k]]);
+      float dx = m.x - qx, dy = m.y - qy, dz = m.z - qz;
+      float r = dx * dx;
+      r = r + dy * dy;
+      r = r + dz * dz;
+      bound = fmaxf(bound, r);
+    }
+  }
+  if (!(bound < 1.0f)) {
+    // ---- A: the 27 L2 cells around the query, no prior bound
+    sweep_ball(mv, md, cur, qx, qy, qz, ax, ay, az, 1, nb KS_PASS);
+    KSTAT(ks.level = 1;)
+    if (nb.full()) {
+      if (nb.d[4] < 0.00390625f) return;  // 5th distance < one L2 cell: nothing outside the 27 cells can be closer
+      bound = nb.d[4];
+    }
+  }
+  if (bound < 0.0625f) {
+    // ---- ball of known radius < 0.25 m: five points are known to lie within `bound` (inclusive)
+    KSTAT(ks.level = 2;)
+    nb.reset_inclusive(bound);
+    int R = (int)ceilf(sqrtf(bound) * 16.0f * 1.0001f) + 1;
+    sweep_ball(mv, md, cur, qx, qy, qz, ax, ay, az, R > 5 ? 5 : R, nb KS_PASS);
+    return;
+  }
+  // ---- sparse neighbourhood: restart, 27 L1 cells (B) then 27 L0 cells (C) with box pruning
+  KSTAT(ks.level = 3;)
+  if (bound < 1.0f)
+    nb.reset_inclusive(bound);
+  else
+    nb.reset();
   const int bx = ax >> 2, by = ay >> 2, bz = az >> 2;
   for (int dz = -1; dz <= 1; ++dz) {
     int z = bz + dz;
@@ -206,19 +290,20 @@ __device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, floa
       int y = by + dy;
       for (int dx = -1; dx <= 1; ++dx) {
         int x = bx + dx;
+        KSTAT(ks.boxes++;)
         if (box_d2(qx, qy, qz, x, y, z, 0.25f) > nb.d[4]) continue;
-        const CellRec* rec = find_cell(mv, md, cur, (x >> 2) - ox, (y >> 2) - oy, (z >> 2) - oz);
+        const CellRec* rec = find_cell(mv, md, cur, (x >> 2) - ox, (y >> 2) - oy, (z >> 2) - oz KS_PASS);
         if (!rec) continue;
         int f1 = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
         unsigned long long m1 = rec->mask;
         if (!((m1 >> f1) & 1ull)) continue;
         int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
-        sweep_l1_cell(mv, l1, x, y, z, qx, qy, qz, ax, ay, az, nb);
+        sweep_l1_cell(mv, l1, x, y, z, qx, qy, qz, nb KS_PASS);
       }
     }
   }
   if (nb.full() && nb.d[4] < 0.0625f) return;
-  // ---- C: 3x3x3 L0 cells, pruned at L0 / L1 / L2 granularity, skipping the L1 block B covered
+  KSTAT(ks.level = 4;)
   const int cx0 = bx >> 2, cy0 = by >> 2, cz0 = bz >> 2;
   for (int dz = -1; dz <= 1; ++dz) {
     int z = cz0 + dz;
@@ -226,8 +311,9 @@ __device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, floa
       int y = cy0 + dy;
       for (int dx = -1; dx <= 1; ++dx) {
         int x = cx0 + dx;
+        KSTAT(ks.boxes++;)
         if (box_d2(qx, qy, qz, x, y, z, 1.0f) > nb.d[4]) continue;
-        const CellRec* rec = find_cell(mv, md, cur, x - ox, y - oy, z - oz);
+        const CellRec* rec = find_cell(mv, md, cur, x - ox, y - oy, z - oz KS_PASS);
         if (!rec) continue;
         unsigned long long m1 = rec->mask;
         int l1 = rec->fine_base;
@@ -236,8 +322,9 @@ __device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, floa
           m1 &= m1 - 1;
           int x1 = (x << 2) | (f1 & 3), y1 = (y << 2) | ((f1 >> 2) & 3), z1 = (z << 2) | (f1 >> 4);
           bool seen = (x1 >= bx - 1 && x1 <= bx + 1 && y1 >= by - 1 && y1 <= by + 1 && z1 >= bz - 1 && z1 <= bz + 1);
+          KSTAT(ks.boxes++;)
           if (!seen && !(box_d2(qx, qy, qz, x1, y1, z1, 0.25f) > nb.d[4]))
-            sweep_l1_cell(mv, l1, x1, y1, z1, qx, qy, qz, ax, ay, az, nb);
+            sweep_l1_cell(mv, l1, x1, y1, z1, qx, qy, qz, nb KS_PASS);
           ++l1;
         }
       }

@@ -494,7 +494,7 @@ __device__ __forceinline__ unsigned long long query_cell_key(const MapDev& md, f
 __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, const int* __restrict__ counts,
                                                const SolveState* __restrict__ st, const MapDev* __restrict__ dev_e,
                                                const MapDev* __restrict__ dev_s, int kind_bit, int upper,
-                                               int solver, QueryBufs qb) {
+                                               int solver, int with_keys, QueryBufs qb) {
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= upper) return;
@@ -514,15 +514,17 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
     const bool is_edge = i < n_e;
     key = query_cell_key(is_edge ? *dev_e : *dev_s, w.x, w.y, w.z) | (is_edge ? 0ull : (1ull << kind_bit));
   }
-  qb.keys[i] = key;
-  qb.vals[i] = i;
+  if (with_keys) {
+    qb.keys[i] = key;
+    qb.vals[i] = i;
+  }
 }
 
 // exact 5-NN of every query, in cell-sorted query order (t = sorted position)
 __global__ void __launch_bounds__(128) k_knn(const int* __restrict__ perm, const float4* __restrict__ pw,
                                              const int* __restrict__ counts, const SolveState* __restrict__ st,
                                              MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
-                                             int* __restrict__ nbr) {
+                                             int seeded, int* __restrict__ nbr) {
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= upper) return;
@@ -534,10 +536,14 @@ __global__ void __launch_bounds__(128) k_knn(const int* __restrict__ perm, const
   nb.reset();
   if (is_edge ? has_edge_map : has_surf_map) {
     float4 w = pw[f];
-    knn5(is_edge ? maps.edge : maps.surf, w.x, w.y, w.z, nb);
+    int seed[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) seed[k] = seeded ? nbr[k * upper + t] : -1;
+    knn5(is_edge ? maps.edge : maps.surf, w.x, w.y, w.z, nb, is_edge ? maps.edge_cat : maps.surf_cat,
+         seeded ? seed : nullptr);
   }
 #pragma unroll
-  for (int k = 0; k < 5; ++k) nbr[k * upper + t] = nb.id[k];
+  for (int k = 0; k < 5; ++k) nbr[k * upper + t] = nb.full() ? nb.id[k] : -1;
 }
 
 struct RecBufs {
@@ -568,12 +574,12 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
   acc_zero(acc);
   for (int t = blockIdx.x * MATCH_BLOCK + threadIdx.x; t < upper; t += gridDim.x * MATCH_BLOCK) {
     int f = perm[t];
-    if (f >= n_e + n_s) continue;  // padding
+    const bool live = f < n_e + n_s;  // padding sorts last; its kind must still be cleared for k_lm_eval
     const bool is_edge = f < n_e;
     Top5 nb;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-      nb.id[k] = nbr[k * upper + t];
+      nb.id[k] = live ? nbr[k * upper + t] : -1;
       nb.d[k] = 0.f;
     }
     uint8_t kind = 0;
@@ -688,9 +694,9 @@ __global__ void __launch_bounds__(128) k_knn_hook(MapView mv, const float* __res
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   Top5 nb;
-  knn5(mv, q[3 * i], q[3 * i + 1], q[3 * i + 2], nb);
+  knn5(mv, q[3 * i], q[3 * i + 1], q[3 * i + 2], nb, nullptr, nullptr);
   for (int k = 0; k < 5; ++k) {
-    bool in = nb.id[k] >= 0;
+    bool in = nb.id[k] >= 0 && nb.id[k] != 0x7fffffff;
     idx[5 * i + k] = in ? nb.id[k] : -1;
     d2[5 * i + k] = in ? nb.d[k] : __int_as_float(0x7f800000);
   }
@@ -703,7 +709,7 @@ __global__ void __launch_bounds__(128) k_match_hook(MapView mv, const float4* __
   if (i >= nq) return;
   float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
   Top5 nb;
-  knn5(mv, px, py, pz, nb);
+  knn5(mv, px, py, pz, nb, nullptr, nullptr);
   double o[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool ok = false;
   if (nb.full()) {
@@ -833,18 +839,23 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
   for (int it = 0; it < outer_count; ++it) {
     sp.iter = it;
     {
+      // the cell sort is a locality heuristic: done once per solve, its permutation is kept for the later
+      // outer iterations (the pose moves by millimetres between them), which also keeps the sorted position
+      // of a feature stable so that k_knn can seed its search with the previous iteration's neighbours
       StageScope scope(c, LMSF_STAGE_ASSOC);
       LM_LAUNCH(c, k_assoc, div_up(up, 256), 256, 0, c->d_feat, c->ex.counts, c->d_state, c->map[0].dev, c->map[1].dev,
-                kb, up, solver, qb);
-      size_t tmp = c->cub_tmp_bytes;
-      LM_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->q_keys, c->q_keys_alt, c->q_vals, c->q_vals_alt, up,
-                                              0, kb + 2, c->stream));
-      c->launches++;
+                kb, up, solver, it == 0 ? 1 : 0, qb);
+      if (it == 0) {
+        size_t tmp = c->cub_tmp_bytes;
+        LM_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->q_keys, c->q_keys_alt, c->q_vals, c->q_vals_alt,
+                                                up, 0, kb + 2, c->stream));
+        c->launches++;
+      }
     }
     {
       StageScope scope(c, LMSF_STAGE_MATCH);
       LM_LAUNCH(c, k_knn, div_up(up, 128), 128, 0, c->q_vals_alt, c->d_pw, c->ex.counts, c->d_state, maps, he, hs, up,
-                solver, c->d_nbr);
+                solver, it == 0 ? 0 : 1, c->d_nbr);
       c->match_bytes += alg_bytes;
       c->match_launches += 1;
     }
