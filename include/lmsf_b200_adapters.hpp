@@ -1,0 +1,248 @@
+// lmsf_b200_adapters.hpp — header-only C++ adapters that put the C ABI (lmsf_b200.h) behind the
+// reference's own three abstract interfaces, so its factories can instantiate the B200 path unchanged:
+//
+//   lmsf::CudaLoamFeatureProcessor<In,Out> : Algorithm::PointCloudProcessBase<In,Out>
+//        replaces  LOAMFeatureProcessorBase   (FeatureExtract/LOAMFeatureProcessor_base.hpp:26, built at
+//                                              factory/System/ML_SystemFactory.hpp:197)
+//   lmsf::CudaVoxelGridFilter<P>           : Algorithm::FilterBase<P>
+//        replaces  VoxelGridFilter            (Filter/voxel_grid.hpp:19, make_voxelGrid filter_factory.hpp:36-41)
+//   lmsf::CudaEdgeSurfRegistration<P>      : Algorithm::RegistrationBase<P>
+//        replaces  CeresEdgeSurfFeatureRegistration / EdgeSurfFeatureRegistration
+//                                             (registration/ceres_edgeSurfFeatureRegistration.hpp:26,
+//                                              edgeSurfFeatureRegistration.hpp:27, built at ML_SystemFactory.hpp:189-190)
+//
+// Error convention: the reference's seams return void and print on failure; the adapters print
+// lmsf_strerror to stderr and leave the output as the reference would (empty clouds / pose untouched).
+// In the reference tree: #define LMSF_WITH_REFERENCE before including this header and include the
+// reference's process_base.hpp / filter_base.hpp / registration_base.hpp first.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "lmsf_b200.h"
+#ifndef LMSF_WITH_REFERENCE
+#include "lmsf_compat/reference_stubs.hpp"
+#endif
+
+namespace lmsf {
+
+// shared, reference-counted context: one per LiDAR (the reference builds one processor + one tracker per LiDAR)
+class Context {
+ public:
+  explicit Context(int device = 0, const lmsf_params* params = nullptr) {
+    lmsf_params p;
+    if (params) p = *params; else lmsf_params_default(&p);
+    int rc = lmsf_ctx_create(device, &p, &ctx_);
+    if (rc != LMSF_OK) throw std::runtime_error(std::string("lmsf_ctx_create: ") + lmsf_strerror(rc));
+  }
+  ~Context() { lmsf_ctx_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  lmsf_ctx* get() const { return ctx_; }
+ private:
+  lmsf_ctx* ctx_ = nullptr;
+};
+using ContextPtr = std::shared_ptr<Context>;
+
+inline lmsf_params DefaultParams(int n_scans, float min_range, float max_range) {
+  lmsf_params p;
+  lmsf_params_default(&p);
+  p.n_scans = n_scans;
+  p.min_range = min_range;
+  p.max_range = max_range;
+  return p;
+}
+
+namespace detail {
+template <typename PointT>
+inline void pack(const pcl::PointCloud<PointT>& c, std::vector<float>& out) {
+  out.resize(c.points.size() * 4);
+  for (std::size_t i = 0; i < c.points.size(); ++i) {
+    out[4 * i + 0] = c.points[i].x;
+    out[4 * i + 1] = c.points[i].y;
+    out[4 * i + 2] = c.points[i].z;
+    out[4 * i + 3] = c.points[i].intensity;
+  }
+}
+template <typename PointT>
+inline typename pcl::PointCloud<PointT>::Ptr unpack(const float* xyzi, int n) {
+  typename pcl::PointCloud<PointT>::Ptr c(new pcl::PointCloud<PointT>());
+  c->points.resize(n);
+  for (int i = 0; i < n; ++i) {
+    PointT p{};
+    p.x = xyzi[4 * i + 0];
+    p.y = xyzi[4 * i + 1];
+    p.z = xyzi[4 * i + 2];
+    p.intensity = xyzi[4 * i + 3];
+    c->points[i] = p;
+  }
+  c->width = (std::uint32_t)n;
+  c->height = 1;
+  c->is_dense = true;
+  return c;
+}
+inline bool check(int rc, const char* what) {
+  if (rc == LMSF_OK) return true;
+  std::fprintf(stderr, "[lmsf_b200] %s failed: %s\n", what, lmsf_strerror(rc));
+  return false;
+}
+// Eigen::Quaterniond(T.rotation()) and q.toRotationMatrix(), as the reference does around Solve()
+template <typename Iso>
+inline void iso_to_pose(const Iso& T, double p[7]) {
+  double R[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) R[r * 3 + c] = T.linear()(r, c);
+  double tr = R[0] + R[4] + R[8];
+  if (tr > 0) {
+    double s = std::sqrt(tr + 1.0);
+    p[3] = 0.5 * s;
+    s = 0.5 / s;
+    p[0] = (R[7] - R[5]) * s;
+    p[1] = (R[2] - R[6]) * s;
+    p[2] = (R[3] - R[1]) * s;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i * 4]) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    double s = std::sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
+    double v[3];
+    v[i] = 0.5 * s;
+    s = 0.5 / s;
+    p[3] = (R[k * 3 + j] - R[j * 3 + k]) * s;
+    v[j] = (R[j * 3 + i] + R[i * 3 + j]) * s;
+    v[k] = (R[k * 3 + i] + R[i * 3 + k]) * s;
+    p[0] = v[0];
+    p[1] = v[1];
+    p[2] = v[2];
+  }
+  for (int i = 0; i < 3; ++i) p[4 + i] = T.translation()(i);
+}
+template <typename Iso>
+inline void pose_to_iso(const double p[7], Iso& T) {
+  const double x = p[0], y = p[1], z = p[2], w = p[3];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  T.linear()(0, 0) = 1 - (tyy + tzz);
+  T.linear()(0, 1) = txy - twz;
+  T.linear()(0, 2) = txz + twy;
+  T.linear()(1, 0) = txy + twz;
+  T.linear()(1, 1) = 1 - (txx + tzz);
+  T.linear()(1, 2) = tyz - twx;
+  T.linear()(2, 0) = txz - twy;
+  T.linear()(2, 1) = tyz + twx;
+  T.linear()(2, 2) = 1 - (txx + tyy);
+  for (int i = 0; i < 3; ++i) T.translation()(i) = p[4 + i];
+}
+}  // namespace detail
+
+// ---------------------------------------------------------------- seam 1
+template <typename _InputPointT, typename _OutputFeatureT>
+class CudaLoamFeatureProcessor : public Algorithm::PointCloudProcessBase<_InputPointT, _OutputFeatureT> {
+ public:
+  // same leading arguments as LOAMFeatureProcessorBase(N_SCANS_, min_distance, max_distance, edge_thresh, ...)
+  explicit CudaLoamFeatureProcessor(ContextPtr ctx) : ctx_(std::move(ctx)) {}
+  void Process(Slam3D::LidarData<_InputPointT> const& data_in, Slam3D::CloudContainer<_OutputFeatureT>& data_out) override {
+    detail::pack(data_in.point_cloud, in_);
+    const int n = (int)data_in.point_cloud.points.size();
+    edge_.resize((std::size_t)(n > 0 ? n : 1) * 4);
+    surf_.resize((std::size_t)(n > 0 ? n : 1) * 4);
+    int ne = 0, ns = 0;
+    if (!detail::check(lmsf_extract_features(ctx_->get(), in_.data(), n, nullptr, edge_.data(), &ne, surf_.data(), &ns),
+                       "lmsf_extract_features")) {
+      ne = ns = 0;
+    }
+    data_out.pointcloud_data_.insert(std::make_pair(std::string("loam_edge"), detail::unpack<_OutputFeatureT>(edge_.data(), ne)));
+    data_out.pointcloud_data_.insert(std::make_pair(std::string("loam_surf"), detail::unpack<_OutputFeatureT>(surf_.data(), ns)));
+  }
+ private:
+  ContextPtr ctx_;
+  std::vector<float> in_, edge_, surf_;
+};
+
+// ---------------------------------------------------------------- seam 2
+template <typename _PointType>
+class CudaVoxelGridFilter : public Algorithm::FilterBase<_PointType> {
+ public:
+  CudaVoxelGridFilter(ContextPtr ctx, float leaf) : ctx_(std::move(ctx)), leaf_(leaf) {}
+  // VoxelGridFilter::Reset("VoxelGrid", leaf) (Filter/voxel_grid.hpp:25-29)
+  void Reset(std::string const& name, float leaf) {
+    if (name == "VoxelGrid") leaf_ = leaf;
+  }
+  Algorithm::PointCloudPtr<_PointType> Filter(const Algorithm::PointCloudConstPtr<_PointType>& cloud_in) const override {
+    std::vector<float> in, out;
+    detail::pack(*cloud_in, in);
+    const int n = (int)cloud_in->points.size();
+    out.resize((std::size_t)(n > 0 ? n : 1) * 4);
+    int nv = 0;
+    if (!(leaf_ > 0.f) ||
+        !detail::check(lmsf_voxel_downsample(ctx_->get(), in.data(), n, leaf_, out.data(), &nv, nullptr), "lmsf_voxel_downsample")) {
+      return Algorithm::PointCloudPtr<_PointType>(new pcl::PointCloud<_PointType>(*cloud_in));  // filter_base.hpp:39-40
+    }
+    auto res = detail::unpack<_PointType>(out.data(), nv);
+    res->header = cloud_in->header;  // filter_base.hpp:43
+    return res;
+  }
+ private:
+  ContextPtr ctx_;
+  float leaf_;
+};
+
+// ---------------------------------------------------------------- seam 3
+template <typename _PointType>
+class CudaEdgeSurfRegistration : public Algorithm::RegistrationBase<_PointType> {
+  using Base = Algorithm::RegistrationBase<_PointType>;
+ public:
+  CudaEdgeSurfRegistration(ContextPtr ctx, std::string const& edge_name, std::string const& surf_name,
+                           int solver = LMSF_SOLVER_HUBER_LM)
+      : ctx_(std::move(ctx)), edge_name_(edge_name), surf_name_(surf_name), solver_(solver) {}
+
+  // "Source" is the local map, selected by name (ceres_edgeSurfFeatureRegistration.hpp:56-71)
+  void SetInputSource(typename Base::SourceInput const& source_input) override {
+    if (!source_input.second || source_input.second->empty()) return;
+    int kind = -1;
+    if (source_input.first == edge_name_) kind = LMSF_KIND_EDGE;
+    else if (source_input.first == surf_name_) kind = LMSF_KIND_SURF;
+    if (kind < 0) return;
+    std::vector<float> buf;
+    detail::pack(*source_input.second, buf);
+    detail::check(lmsf_map_set(ctx_->get(), kind, buf.data(), (int)source_input.second->points.size()), "lmsf_map_set");
+  }
+  // "Target" is the current scan's feature container (:73-84); the clouds are kept by shared_ptr
+  void SetInputTarget(Slam3D::FeaturePointCloudContainer<_PointType> const& target_input) override {
+    auto e = target_input.find(edge_name_);
+    if (e != target_input.end()) edge_in_ = e->second;
+    auto s = target_input.find(surf_name_);
+    if (s != target_input.end()) surf_in_ = s->second;
+  }
+  void SetMaxIteration(std::uint16_t const& n) { lmsf_set_lm_outer(ctx_->get(), (int)n); }
+  // predicted pose in, registered pose out (:96-130); on failure T is left as predicted
+  void Solve(Eigen::Isometry3d& T) override {
+    std::vector<float> e, s;
+    int ne = 0, ns = 0;
+    if (edge_in_) { detail::pack(*edge_in_, e); ne = (int)edge_in_->points.size(); }
+    if (surf_in_) { detail::pack(*surf_in_, s); ns = (int)surf_in_->points.size(); }
+    double pose[7];
+    detail::iso_to_pose(T, pose);
+    lmsf_reg_stats st;
+    if (detail::check(lmsf_register(ctx_->get(), e.data(), ne, s.data(), ns, solver_, pose, &st), "lmsf_register")) {
+      detail::pose_to_iso(pose, T);
+      last_ = st;
+    }
+  }
+  const lmsf_reg_stats& LastStats() const { return last_; }
+ private:
+  ContextPtr ctx_;
+  std::string edge_name_, surf_name_;
+  int solver_;
+  typename pcl::PointCloud<_PointType>::ConstPtr edge_in_, surf_in_;
+  lmsf_reg_stats last_{};
+};
+
+}  // namespace lmsf

@@ -123,7 +123,7 @@ struct SolveState {
   int lm_invalid;
   int lm_steps_total, lm_steps_accepted;
   unsigned ticket;    // last-block-done counter
-  int pad;
+  int knn_next;       // work-queue head of the running k_knn launch
 };
 
 struct Ctx {

@@ -33,6 +33,14 @@
 
 namespace lm {
 
+// the 27 neighbour offsets, nearest first (centre, 6 faces, 12 edges, 8 corners): the 5th-distance bound
+// tightens on the first cells and prunes most of the later ones
+__device__ static const signed char kNear27[27][3] = {
+    {0, 0, 0},   {-1, 0, 0},  {1, 0, 0},   {0, -1, 0},  {0, 1, 0},   {0, 0, -1},  {0, 0, 1},
+    {-1, -1, 0}, {1, -1, 0},  {-1, 1, 0},  {1, 1, 0},   {-1, 0, -1}, {1, 0, -1},  {-1, 0, 1},
+    {1, 0, 1},   {0, -1, -1}, {0, 1, -1},  {0, -1, 1},  {0, 1, 1},   {-1, -1, -1}, {1, -1, -1},
+    {-1, 1, -1}, {1, 1, -1},  {-1, -1, 1}, {1, -1, 1},  {-1, 1, 1},  {1, 1, 1}};
+
 struct MapView {
   const float4* sorted;             // cell-sorted points, .w = original index bits
   const CellRec* table;             // hash table of L0 cells
@@ -284,50 +292,38 @@ __device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, floa
   else
     nb.reset();
   const int bx = ax >> 2, by = ay >> 2, bz = az >> 2;
-  for (int dz = -1; dz <= 1; ++dz) {
-    int z = bz + dz;
-    for (int dy = -1; dy <= 1; ++dy) {
-      int y = by + dy;
-      for (int dx = -1; dx <= 1; ++dx) {
-        int x = bx + dx;
-        KSTAT(ks.boxes++;)
-        if (box_d2(qx, qy, qz, x, y, z, 0.25f) > nb.d[4]) continue;
-        const CellRec* rec = find_cell(mv, md, cur, (x >> 2) - ox, (y >> 2) - oy, (z >> 2) - oz KS_PASS);
-        if (!rec) continue;
-        int f1 = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
-        unsigned long long m1 = rec->mask;
-        if (!((m1 >> f1) & 1ull)) continue;
-        int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
-        sweep_l1_cell(mv, l1, x, y, z, qx, qy, qz, nb KS_PASS);
-      }
-    }
+  for (int k = 0; k < 27; ++k) {
+    int x = bx + kNear27[k][0], y = by + kNear27[k][1], z = bz + kNear27[k][2];
+    KSTAT(ks.boxes++;)
+    if (box_d2(qx, qy, qz, x, y, z, 0.25f) > nb.d[4]) continue;
+    const CellRec* rec = find_cell(mv, md, cur, (x >> 2) - ox, (y >> 2) - oy, (z >> 2) - oz KS_PASS);
+    if (!rec) continue;
+    int f1 = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
+    unsigned long long m1 = rec->mask;
+    if (!((m1 >> f1) & 1ull)) continue;
+    int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
+    sweep_l1_cell(mv, l1, x, y, z, qx, qy, qz, nb KS_PASS);
   }
   if (nb.full() && nb.d[4] < 0.0625f) return;
   KSTAT(ks.level = 4;)
   const int cx0 = bx >> 2, cy0 = by >> 2, cz0 = bz >> 2;
-  for (int dz = -1; dz <= 1; ++dz) {
-    int z = cz0 + dz;
-    for (int dy = -1; dy <= 1; ++dy) {
-      int y = cy0 + dy;
-      for (int dx = -1; dx <= 1; ++dx) {
-        int x = cx0 + dx;
-        KSTAT(ks.boxes++;)
-        if (box_d2(qx, qy, qz, x, y, z, 1.0f) > nb.d[4]) continue;
-        const CellRec* rec = find_cell(mv, md, cur, x - ox, y - oy, z - oz KS_PASS);
-        if (!rec) continue;
-        unsigned long long m1 = rec->mask;
-        int l1 = rec->fine_base;
-        while (m1) {
-          int f1 = __ffsll((long long)m1) - 1;
-          m1 &= m1 - 1;
-          int x1 = (x << 2) | (f1 & 3), y1 = (y << 2) | ((f1 >> 2) & 3), z1 = (z << 2) | (f1 >> 4);
-          bool seen = (x1 >= bx - 1 && x1 <= bx + 1 && y1 >= by - 1 && y1 <= by + 1 && z1 >= bz - 1 && z1 <= bz + 1);
-          KSTAT(ks.boxes++;)
-          if (!seen && !(box_d2(qx, qy, qz, x1, y1, z1, 0.25f) > nb.d[4]))
-            sweep_l1_cell(mv, l1, x1, y1, z1, qx, qy, qz, nb KS_PASS);
-          ++l1;
-        }
-      }
+  for (int k = 0; k < 27; ++k) {
+    int x = cx0 + kNear27[k][0], y = cy0 + kNear27[k][1], z = cz0 + kNear27[k][2];
+    KSTAT(ks.boxes++;)
+    if (box_d2(qx, qy, qz, x, y, z, 1.0f) > nb.d[4]) continue;
+    const CellRec* rec = find_cell(mv, md, cur, x - ox, y - oy, z - oz KS_PASS);
+    if (!rec) continue;
+    unsigned long long m1 = rec->mask;
+    int l1 = rec->fine_base;
+    while (m1) {
+      int f1 = __ffsll((long long)m1) - 1;
+      m1 &= m1 - 1;
+      int x1 = (x << 2) | (f1 & 3), y1 = (y << 2) | ((f1 >> 2) & 3), z1 = (z << 2) | (f1 >> 4);
+      bool seen = (x1 >= bx - 1 && x1 <= bx + 1 && y1 >= by - 1 && y1 <= by + 1 && z1 >= bz - 1 && z1 <= bz + 1);
+      KSTAT(ks.boxes++;)
+      if (!seen && !(box_d2(qx, qy, qz, x1, y1, z1, 0.25f) > nb.d[4]))
+        sweep_l1_cell(mv, l1, x1, y1, z1, qx, qy, qz, nb KS_PASS);
+      ++l1;
     }
   }
 }

@@ -205,12 +205,16 @@ __device__ __forceinline__ void gn_row(const double* R, d3 pl, d3 grad, double r
   acc_row(acc, J, rr, 0.5 * rr * rr);
 }
 
-// warp-shuffle + block tree; returns true in the last block to finish, with the grid total in `tot`
+// warp-shuffle + block tree; returns true in the last block to finish, with the grid total in `tot`.
+// Per-block partials are stored quantity-major (partial[k * gridDim.x + block]) so that the final sum,
+// one warp per quantity with lanes striding over the blocks, reads them coalesced.  Every order of
+// summation is fixed, so the result is reproducible bit for bit from run to run.
 __device__ __forceinline__ bool reduce_grid(const Acc& acc, double* __restrict__ partial, SolveState* __restrict__ st,
                                             double* tot /* shared [LM_NSUM] */) {
   __shared__ double wsum[MATCH_WARPS][LM_NSUM];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned nblk = gridDim.x;
 #pragma unroll
   for (int k = 0; k < LM_NSUM; ++k) {
     double x = acc.v[k];
@@ -223,36 +227,44 @@ __device__ __forceinline__ bool reduce_grid(const Acc& acc, double* __restrict__
     double x = 0.0;
 #pragma unroll
     for (int w = 0; w < MATCH_WARPS; ++w) x += wsum[w][threadIdx.x];
-    partial[(size_t)blockIdx.x * LM_NSUM + threadIdx.x] = x;
+    partial[(size_t)threadIdx.x * nblk + blockIdx.x] = x;
   }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned t = atomicAdd(&st->ticket, 1u);
-    last = (t == gridDim.x - 1);
+    last = (t == nblk - 1);
   }
   __syncthreads();
   if (!last) return false;
   __threadfence();
-  // fixed-order final sum: 4 strided sub-sums per quantity, combined in order
-  __shared__ double part[MATCH_WARPS][32];
-  {
-    int k = lane, p = warp;
+  for (int k = warp; k < LM_NSUM; k += MATCH_WARPS) {
+    const double* row = partial + (size_t)k * nblk;
     double x = 0.0;
-    if (k < LM_NSUM)
-      for (unsigned b = p; b < gridDim.x; b += MATCH_WARPS) x += __ldcg(&partial[(size_t)b * LM_NSUM + k]);
-    part[p][k] = x;
-  }
-  __syncthreads();
-  if (threadIdx.x < LM_NSUM) {
-    double x = 0.0;
+    for (unsigned b = lane; b < nblk; b += 32) x += __ldcg(&row[b]);
 #pragma unroll
-    for (int p = 0; p < MATCH_WARPS; ++p) x += part[p][threadIdx.x];
-    tot[threadIdx.x] = x;
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if (lane == 0) tot[k] = x;
   }
   __syncthreads();
   if (threadIdx.x == 0) st->ticket = 0u;
   return true;
+}
+
+// block-cooperative copy of the solver state between global and shared memory (8-byte words)
+static_assert(sizeof(SolveState) % 8 == 0, "SolveState is copied as 8-byte words");
+__device__ __forceinline__ void state_load(SolveState* sh, const SolveState* st) {
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(sh);
+  for (int i = threadIdx.x; i < (int)(sizeof(SolveState) / 8); i += blockDim.x) dst[i] = __ldcg(&src[i]);
+  __syncthreads();
+  if (threadIdx.x == 0) sh->ticket = 0u;  // reduce_grid has just re-armed it; never write a stale count back
+}
+__device__ __forceinline__ void state_store(SolveState* st, const SolveState* sh) {
+  __syncthreads();
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(sh);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(st);
+  for (int i = threadIdx.x; i < (int)(sizeof(SolveState) / 8); i += blockDim.x) dst[i] = src[i];
 }
 
 __device__ __forceinline__ void unpack_normal(const double* tot, double* H, double* g) {
@@ -339,7 +351,8 @@ __device__ void gn_step(SolveState* st, const double* tot, const SolveParams& sp
   st->x[2] = q.z;
   st->x[3] = q.w;
   float deltaR = (float)(dn / 2);
-  float deltaT = (float)sqrt(pow(X[3] * 100, 2.0) + pow(X[4] * 100, 2.0) + pow(X[5] * 100, 2.0));
+  double c3 = X[3] * 100, c4 = X[4] * 100, c5 = X[5] * 100;  // pow(., 2) == exact square
+  float deltaT = (float)sqrt(c3 * c3 + c4 * c4 + c5 * c5);
   if (deltaR < 0.0009 && deltaT < 0.05) st->gn_done = 1;
 }
 
@@ -448,7 +461,8 @@ __device__ void lm_update(SolveState* st, const double* tot, const SolveParams& 
     unpack_normal(tot, st->H, st->g);
     st->cost = cand_cost;
     st->lm_steps_accepted += 1;
-    double f = 1.0 - pow(2.0 * rho - 1.0, 3.0);
+    double u = 2.0 * rho - 1.0;
+    double f = 1.0 - u * u * u;
     st->radius = st->radius / fmax(1.0 / 3.0, f);
     st->radius = fmin(1e16, st->radius);
     st->decrease = 2.0;
@@ -469,7 +483,7 @@ __device__ void lm_update(SolveState* st, const double* tot, const SolveParams& 
 
 // ------------------------------------------------------------------ kernels
 struct QueryBufs {
-  unsigned long long* keys;  // [upper] sort keys (kind | L0 | L1 | L2 cell of the world point)
+  unsigned* keys;            // [upper] sort keys (kind | L0 | L1 | L2 cell of the world point, top 32 bits)
   int* vals;                 // [upper] feature index
   float4* pw;                // [upper] fp32 world point by feature index
 };
@@ -492,11 +506,12 @@ __device__ __forceinline__ unsigned long long query_cell_key(const MapDev& md, f
 // pointAssociateToMap (edgeSurfFeatureRegistration.hpp:342-350): world point in fp64, stored as fp32;
 // plus the sort key that groups the queries of one map cell into one warp
 __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, const int* __restrict__ counts,
-                                               const SolveState* __restrict__ st, const MapDev* __restrict__ dev_e,
-                                               const MapDev* __restrict__ dev_s, int kind_bit, int upper,
-                                               int solver, int with_keys, QueryBufs qb) {
+                                               SolveState* __restrict__ st, const MapDev* __restrict__ dev_e,
+                                               const MapDev* __restrict__ dev_s, int kind_bit, int key_shift,
+                                               int upper, int solver, int with_keys, QueryBufs qb) {
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) st->knn_next = 0;  // work queue of the k_knn launch that follows
   if (i >= upper) return;
   const int n_e = counts[0], n_s = counts[1];
   unsigned long long key = 2ull << kind_bit;  // padding sorts behind every live query
@@ -515,35 +530,48 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
     key = query_cell_key(is_edge ? *dev_e : *dev_s, w.x, w.y, w.z) | (is_edge ? 0ull : (1ull << kind_bit));
   }
   if (with_keys) {
-    qb.keys[i] = key;
+    // ordering heuristic only: when the packed cell key is wider than 32 bits its low (finest) bits are dropped
+    qb.keys[i] = (unsigned)(key >> key_shift);
     qb.vals[i] = i;
   }
 }
 
-// exact 5-NN of every query, in cell-sorted query order (t = sorted position)
+// exact 5-NN of every query, in cell-sorted query order (t = sorted position).  Persistent warps pull
+// chunks of 32 consecutive sorted queries from a device-side counter: queries of sparse regions cost several
+// times more than queries of dense ones and sort next to each other, so a static block->query map leaves a
+// long tail of heavy blocks.
 __global__ void __launch_bounds__(128) k_knn(const int* __restrict__ perm, const float4* __restrict__ pw,
-                                             const int* __restrict__ counts, const SolveState* __restrict__ st,
+                                             const int* __restrict__ counts, SolveState* __restrict__ st,
                                              MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
                                              int seeded, int* __restrict__ nbr) {
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= upper) return;
   const int n_e = counts[0], n_s = counts[1];
-  int f = perm[t];
-  if (f >= n_e + n_s) return;
-  const bool is_edge = f < n_e;
-  Top5 nb;
-  nb.reset();
-  if (is_edge ? has_edge_map : has_surf_map) {
-    float4 w = pw[f];
-    int seed[5];
+  const int lane = threadIdx.x & 31;
+  const int live = n_e + n_s;  // sorted positions >= live are padding
+  while (true) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&st->knn_next, 32);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= live) break;
+    int t = base + lane;
+    if (t >= upper) continue;
+    int f = perm[t];
+    if (f >= live) continue;
+    const bool is_edge = f < n_e;
+    Top5 nb;
+    nb.reset();
+    if (is_edge ? has_edge_map : has_surf_map) {
+      float4 w = pw[f];
+      int seed[5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) seed[k] = seeded ? nbr[k * upper + t] : -1;
-    knn5(is_edge ? maps.edge : maps.surf, w.x, w.y, w.z, nb, is_edge ? maps.edge_cat : maps.surf_cat,
-         seeded ? seed : nullptr);
+      for (int k = 0; k < 5; ++k) seed[k] = seeded ? nbr[k * upper + t] : -1;
+      knn5(is_edge ? maps.edge : maps.surf, w.x, w.y, w.z, nb, is_edge ? maps.edge_cat : maps.surf_cat,
+           seeded ? seed : nullptr);
+    }
+    const bool full = nb.full();
+#pragma unroll
+    for (int k = 0; k < 5; ++k) nbr[k * upper + t] = full ? nb.id[k] : -1;
   }
-#pragma unroll
-  for (int k = 0; k < 5; ++k) nbr[k * upper + t] = nb.full() ? nb.id[k] : -1;
 }
 
 struct RecBufs {
@@ -630,16 +658,19 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
     rb.kind[t] = kind;
   }
   if (!reduce_grid(acc, partial, st, tot)) return;
+  // the serial 6x6 step runs on a shared-memory copy of the state (one thread, latency bound:
+  // global-memory round trips on every st-> field would dominate it)
+  __shared__ SolveState sh;
+  state_load(&sh, st);
   if (threadIdx.x == 0) {
-    st->n_edge_ok = (int)tot[29];
-    st->n_surf_ok = (int)tot[28] - (int)tot[29];
-    double t2[LM_NSUM];
-    for (int k = 0; k < LM_NSUM; ++k) t2[k] = tot[k];
+    sh.n_edge_ok = (int)tot[29];
+    sh.n_surf_ok = (int)tot[28] - (int)tot[29];
     if (sp.solver == LMSF_SOLVER_GN)
-      gn_step(st, t2, sp);
+      gn_step(&sh, tot, sp);
     else
-      lm_begin(st, t2, sp);
+      lm_begin(&sh, tot, sp);
   }
+  state_store(st, &sh);
 }
 
 // re-evaluate the stored correspondences at the LM candidate; last block accepts / rejects / proposes
@@ -669,11 +700,10 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* 
     }
   }
   if (!reduce_grid(acc, partial, st, tot)) return;
-  if (threadIdx.x == 0) {
-    double t2[LM_NSUM];
-    for (int k = 0; k < LM_NSUM; ++k) t2[k] = tot[k];
-    lm_update(st, t2, sp);
-  }
+  __shared__ SolveState sh;
+  state_load(&sh, st);
+  if (threadIdx.x == 0) lm_update(&sh, tot, sp);
+  state_store(st, &sh);
 }
 
 __global__ void k_state_init(SolveState* st, const double* __restrict__ pose) {
@@ -686,6 +716,7 @@ __global__ void k_state_init(SolveState* st, const double* __restrict__ pose) {
   st->lm_iter = st->lm_invalid = 0;
   st->lm_steps_total = st->lm_steps_accepted = 0;
   st->ticket = 0u;
+  st->knn_next = 0;
 }
 
 // ------------------------------------------------------------------ test hooks
@@ -813,16 +844,16 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
   const int up = upper > 0 ? upper : 1;
   // persistent-style grids: a few CTAs per SM, grid-stride over the queries
   int fit_grid = div_up(up, MATCH_BLOCK);
-  if (fit_grid > 148 * 4) fit_grid = 148 * 4;
+  if (fit_grid > 148 * 2) fit_grid = 148 * 2;
   int eval_grid = div_up(up, MATCH_BLOCK);
-  if (eval_grid > 148 * 2) eval_grid = 148 * 2;
+  if (eval_grid > 148) eval_grid = 148;
   RecBufs rb;
   rb.d = c->d_rec;
   rb.pl = c->d_recf;
   rb.kind = c->d_ok;
   rb.stride = c->prm.max_points;
   QueryBufs qb;
-  qb.keys = c->q_keys;
+  qb.keys = (unsigned*)c->q_keys;
   qb.vals = c->q_vals;
   qb.pw = c->d_pw;
   // bits of a query sort key: 12 (L1, L2) + the wider of the two maps' packed L0 coordinates, + kind bit
@@ -843,18 +874,21 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
       // outer iterations (the pose moves by millimetres between them), which also keeps the sorted position
       // of a feature stable so that k_knn can seed its search with the previous iteration's neighbours
       StageScope scope(c, LMSF_STAGE_ASSOC);
+      const int key_shift = (kb + 2 > 32) ? (kb + 2 - 32) : 0;
       LM_LAUNCH(c, k_assoc, div_up(up, 256), 256, 0, c->d_feat, c->ex.counts, c->d_state, c->map[0].dev, c->map[1].dev,
-                kb, up, solver, it == 0 ? 1 : 0, qb);
+                kb, key_shift, up, solver, it == 0 ? 1 : 0, qb);
       if (it == 0) {
         size_t tmp = c->cub_tmp_bytes;
-        LM_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->q_keys, c->q_keys_alt, c->q_vals, c->q_vals_alt,
-                                                up, 0, kb + 2, c->stream));
+        LM_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, (unsigned*)c->q_keys, (unsigned*)c->q_keys_alt,
+                                                c->q_vals, c->q_vals_alt, up, 0, kb + 2 - key_shift, c->stream));
         c->launches++;
       }
     }
     {
       StageScope scope(c, LMSF_STAGE_MATCH);
-      LM_LAUNCH(c, k_knn, div_up(up, 128), 128, 0, c->q_vals_alt, c->d_pw, c->ex.counts, c->d_state, maps, he, hs, up,
+      int knn_grid = div_up(up, 128);
+      if (knn_grid > 148 * 6) knn_grid = 148 * 6;  // persistent: every resident warp pulls work
+      LM_LAUNCH(c, k_knn, knn_grid, 128, 0, c->q_vals_alt, c->d_pw, c->ex.counts, c->d_state, maps, he, hs, up,
                 solver, it == 0 ? 0 : 1, c->d_nbr);
       c->match_bytes += alg_bytes;
       c->match_launches += 1;

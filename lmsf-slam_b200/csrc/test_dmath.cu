@@ -1,0 +1,116 @@
+// test_dmath.cu — device-vs-host check of dmath.cuh: the same IEEE operation sequence must give the same
+// bits on the B200 as on the host (the library is built with -fmad=false for exactly this reason).
+// Built by the Makefile as csrc/test_dmath, run by tests/test_gpu_parity.py::test_device_algebra_bit_exact.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "dmath.cuh"
+
+using namespace lm;
+
+struct Case {
+  double H[36], g[6], A[15], S[9], se3[6], x7[7];
+};
+struct Out {
+  double qr6[6], qr53[3], w6[6], V6[36], w3[3], V3[9], inv[36], chol[6], plus[7];
+  int ok_inv, ok_chol;
+};
+
+HD void run_case(const Case& c, Out& o) {
+  cpqr_solve<6, 6>(c.H, c.g, o.qr6);
+  double b[5] = {-1, -1, -1, -1, -1};
+  cpqr_solve<5, 3>(c.A, b, o.qr53);
+  jacobi_eig<6>(c.H, o.w6, o.V6);
+  jacobi_eig<3>(c.S, o.w3, o.V3);
+  o.ok_inv = invert6(c.H, o.inv) ? 1 : 0;
+  o.ok_chol = spd_solve6(c.H, c.g, o.chol) ? 1 : 0;
+  se3_plus(c.x7, c.se3, o.plus);
+}
+
+__global__ void k_run(const Case* c, Out* o, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) run_case(c[i], o[i]);
+}
+
+static double rnd() { return rand() / (double)RAND_MAX - 0.5; }
+
+int main() {
+  const int n = 2000;
+  Case* hc = (Case*)malloc(n * sizeof(Case));
+  Out* ho = (Out*)malloc(n * sizeof(Out));
+  Out* hd = (Out*)malloc(n * sizeof(Out));
+  srand(7);
+  for (int t = 0; t < n; ++t) {
+    Case& c = hc[t];
+    double J[40][6];
+    int rows = (t % 9 == 0) ? 4 : 40;  // rank-deficient normal matrices too
+    memset(c.H, 0, sizeof c.H);
+    for (int i = 0; i < rows; ++i)
+      for (int j = 0; j < 6; ++j) J[i][j] = rnd() * (j < 3 ? 20 : 1);
+    for (int i = 0; i < 6; ++i) {
+      c.g[i] = rnd();
+      for (int j = 0; j < 6; ++j) {
+        double s = 0;
+        for (int k = 0; k < rows; ++k) s += J[k][i] * J[k][j];
+        c.H[i * 6 + j] = s;
+      }
+    }
+    for (int i = 0; i < 15; ++i) c.A[i] = rnd() * 30;
+    if (t % 11 == 0)
+      for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 3; ++j) c.A[i * 3 + j] = (i + 1) * (j + 1.5);  // collinear neighbours
+    double P[5][3], m[3] = {0, 0, 0};
+    for (int i = 0; i < 5; ++i)
+      for (int j = 0; j < 3; ++j) {
+        P[i][j] = rnd() * (j == 0 ? 2 : 0.05);
+        m[j] += P[i][j] / 5;
+      }
+    memset(c.S, 0, sizeof c.S);
+    for (int i = 0; i < 5; ++i)
+      for (int r = 0; r < 3; ++r)
+        for (int q = 0; q < 3; ++q) c.S[r * 3 + q] += (P[i][r] - m[r]) * (P[i][q] - m[q]);
+    for (int i = 0; i < 6; ++i) c.se3[i] = rnd() * (t % 5 == 0 ? 1e-12 : 0.05);
+    double qn = 0;
+    for (int i = 0; i < 4; ++i) {
+      c.x7[i] = rnd();
+      qn += c.x7[i] * c.x7[i];
+    }
+    for (int i = 0; i < 4; ++i) c.x7[i] /= sqrt(qn);
+    for (int i = 4; i < 7; ++i) c.x7[i] = rnd() * 10;
+  }
+  for (int t = 0; t < n; ++t) run_case(hc[t], ho[t]);
+  Case* dc;
+  Out* dout;
+  if (cudaMalloc(&dc, n * sizeof(Case)) != cudaSuccess) {
+    printf("no device\n");
+    return 2;
+  }
+  cudaMalloc(&dout, n * sizeof(Out));
+  cudaMemcpy(dc, hc, n * sizeof(Case), cudaMemcpyHostToDevice);
+  k_run<<<(n + 63) / 64, 64>>>(dc, dout, n);
+  if (cudaMemcpy(hd, dout, n * sizeof(Out), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    printf("kernel failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+    return 3;
+  }
+  // se3_plus uses sin/cos (libm differs by an ulp or two): compare it with a tolerance, the rest bit for bit
+  int bad = 0, bad_plus = 0;
+  for (int t = 0; t < n; ++t) {
+    if (memcmp(&ho[t], &hd[t], offsetof(Out, plus)) != 0 || ho[t].ok_inv != hd[t].ok_inv || ho[t].ok_chol != hd[t].ok_chol) {
+      if (bad < 5) {
+        const char* names[] = {"qr6", "qr53", "w6", "V6", "w3", "V3", "inv", "chol"};
+        size_t offs[] = {offsetof(Out, qr6), offsetof(Out, qr53), offsetof(Out, w6), offsetof(Out, V6), offsetof(Out, w3),
+                         offsetof(Out, V3), offsetof(Out, inv), offsetof(Out, chol), offsetof(Out, plus)};
+        for (int k = 0; k < 8; ++k)
+          if (memcmp((char*)&ho[t] + offs[k], (char*)&hd[t] + offs[k], offs[k + 1] - offs[k]) != 0)
+            printf("case %d: %s differs (host %.17g device %.17g)\n", t, names[k], *(double*)((char*)&ho[t] + offs[k]),
+                   *(double*)((char*)&hd[t] + offs[k]));
+      }
+      ++bad;
+    }
+    for (int i = 0; i < 7; ++i)
+      if (fabs(ho[t].plus[i] - hd[t].plus[i]) > 1e-14 * (1 + fabs(ho[t].plus[i]))) ++bad_plus;
+  }
+  printf("cases %d  bit mismatches %d  se3_plus out of tolerance %d\n", n, bad, bad_plus);
+  return (bad || bad_plus) ? 1 : 0;
+}

@@ -624,7 +624,8 @@ static void lm_solve(const std::vector<EdgeBlk>& eb, const std::vector<SurfBlk>&
       lm_evaluate(eb, sb, x, huber_a, true, N);
       cost = N.cost;
       ++accepted;
-      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3));
+      double u = 2.0 * rho - 1.0;  // Ceres: pow(2 rho - 1, 3); u*u*u differs from it by <= 1 ulp
+      radius = radius / std::max(1.0 / 3.0, 1.0 - u * u * u);
       radius = std::min(1e16, radius);
       decrease = 2.0;
       if (gmax() <= 1e-10) break;

@@ -1,0 +1,65 @@
+// adapter_smoke.cpp — drives the three reference seams through the C++ adapters exactly as the reference's
+// factories would (ML_SystemFactory.hpp:179-198): processor -> registration with "loam_edge"/"loam_surf".
+// Input: a binary file of float32 XYZI points (two sweeps back to back: n0, n1 given on the command line).
+// Prints the registered pose; tests/test_gpu_parity.py compares it with the ctypes path.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "lmsf_b200_adapters.hpp"
+
+using Pt = pcl::PointXYZI;
+
+static Slam3D::LidarData<Pt> load(const float* p, int n) {
+  Slam3D::LidarData<Pt> d;
+  d.point_cloud.points.resize(n);
+  for (int i = 0; i < n; ++i) {
+    Pt q{};
+    q.x = p[4 * i];
+    q.y = p[4 * i + 1];
+    q.z = p[4 * i + 2];
+    q.intensity = p[4 * i + 3];
+    d.point_cloud.points[i] = q;
+  }
+  return d;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 5) {
+    std::fprintf(stderr, "usage: adapter_smoke <file> <n0> <n1> <n_scans>\n");
+    return 2;
+  }
+  const int n0 = std::atoi(argv[2]), n1 = std::atoi(argv[3]), n_scans = std::atoi(argv[4]);
+  std::vector<float> buf((std::size_t)(n0 + n1) * 4);
+  FILE* f = std::fopen(argv[1], "rb");
+  if (!f || std::fread(buf.data(), sizeof(float), buf.size(), f) != buf.size()) return 3;
+  std::fclose(f);
+  lmsf_params prm = lmsf::DefaultParams(n_scans, 2.f, 80.f);
+  lmsf::ContextPtr ctx;
+  try {
+    ctx = std::make_shared<lmsf::Context>(0, &prm);
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "%s\n", e.what());
+    return 4;
+  }
+  std::unique_ptr<Algorithm::PointCloudProcessBase<Pt, Pt>> proc(new lmsf::CudaLoamFeatureProcessor<Pt, Pt>(ctx));
+  std::unique_ptr<Algorithm::FilterBase<Pt>> vox(new lmsf::CudaVoxelGridFilter<Pt>(ctx, 0.4f));
+  std::unique_ptr<Algorithm::RegistrationBase<Pt>> reg(new lmsf::CudaEdgeSurfRegistration<Pt>(ctx, "loam_edge", "loam_surf"));
+
+  Slam3D::CloudContainer<Pt> f0, f1;
+  proc->Process(load(buf.data(), n0), f0);
+  proc->Process(load(buf.data() + 4 * (std::size_t)n0, n1), f1);
+  auto surf_map = vox->Filter(f0.pointcloud_data_["loam_surf"]);
+  reg->SetInputSource({"loam_edge", f0.pointcloud_data_["loam_edge"]});
+  reg->SetInputSource({"loam_surf", surf_map});
+  reg->SetInputTarget(f1.pointcloud_data_);
+  Eigen::Isometry3d T = Eigen::Isometry3d::Identity();
+  reg->Solve(T);
+  double p[7];
+  lmsf::detail::iso_to_pose(T, p);
+  std::printf("features %zu %zu %zu %zu voxels %zu\n", f0.pointcloud_data_["loam_edge"]->size(),
+              f0.pointcloud_data_["loam_surf"]->size(), f1.pointcloud_data_["loam_edge"]->size(),
+              f1.pointcloud_data_["loam_surf"]->size(), surf_map->size());
+  std::printf("pose %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
+  return 0;
+}

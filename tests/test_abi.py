@@ -65,3 +65,15 @@ def test_strerror_and_null_handling(gpu_lib):
     assert gpu_lib.fn("params_default")(None) == -1
     assert gpu_lib.fn("ctx_create")(0, None, None) == -1
     gpu_lib.fn("ctx_destroy")(None)
+
+
+def test_cpp_adapter_binary_builds_and_fails_loudly_without_gpu():
+    import torch
+    exe = os.path.join(ROOT, "tests", "cpp", "adapter_smoke")
+    if not os.path.exists(exe):
+        entry.build()
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([exe, "/dev/null", "0", "0", "16"], capture_output=True, text=True)
+    assert r.returncode == 4 and "no CPU path" in r.stderr
