@@ -126,6 +126,7 @@ def run_ours(args):
     n_gpus = args.gpus
     use_dist = world > 1
     W, K = args.warmup, args.steps
+    # independent sequences are dealt round-robin to ranks (shard.assign): with one sequence per GPU rank r tracks sequence r
     sweeps = make_sequence(W + K + 1, seq=rank)     # before any CUDA call (fork-safe)
     torch.cuda.set_device(local)
     if use_dist:
@@ -195,10 +196,7 @@ def run_ours(args):
     sampler.stop_flag.set()
     sampler.join()
 
-    t_ms = torch.tensor([dev_ms, e_wall_ms], dtype=torch.float64, device=f"cuda:{local}")
-    if use_dist:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(t_ms[0]), float(t_ms[1])
+    dev_ms_max, e2e_ms_max = pkg.shard.max_over_ranks([dev_ms, e_wall_ms], device=f"cuda:{local}")
 
     if rank == 0:
         ms, ln, alg_bytes = prof
