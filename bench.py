@@ -31,7 +31,7 @@ import __graft_entry__ as entry  # noqa: E402
 METRIC = "scan-to-map registrations/sec (HDL-64 synthetic)"
 UNIT = "scans/s"
 SENSOR = "hdl64"
-STATE_D2H_BYTES = 872 + 8  # sizeof(SolveState) + the two feature counts, read back once per sweep
+STATE_D2H_BYTES = 880 + 8  # sizeof(SolveState) + the two feature counts, read back once per sweep
 
 
 def _gen(args):
@@ -147,7 +147,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_sequence(step_fn, profile):
+    def run_sequence(step_fn, profile, K=K):
         """W untimed + K timed steps; returns (device ms for K steps, per-step wall ms, launches, prof)."""
         ctx.tracker_reset()
         step_fn(0, 0.0)
@@ -186,6 +186,9 @@ def run_ours(args):
 
     # ---- resident pass: sweeps already in HBM when the timed region starts
     d_ptrs = [ctx.dev_upload_new(s) for s in sweeps]
+    # dress rehearsal (discarded): the very first timed loop of a process pays one-off lazy initialisation
+    # (CUDA event pools, NVML) of ~50-90 ms inside its first iteration
+    run_sequence(lambda k, t: ctx.tracker_step_dev(d_ptrs[k], n_pts[k], t)[2], False, K=2)
     dev_ms, wall_ms, per, launches, _, stats, fl1 = run_sequence(
         lambda k, t: ctx.tracker_step_dev(d_ptrs[k], n_pts[k], t)[2], False)
     # ---- end-to-end pass: host buffers through lmsf_tracker_step (H2D of the sweep + D2H of the pose inside)

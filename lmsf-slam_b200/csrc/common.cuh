@@ -123,7 +123,9 @@ struct SolveState {
   int lm_invalid;
   int lm_steps_total, lm_steps_accepted;
   unsigned ticket;    // last-block-done counter
-  int knn_next;       // work-queue head of the running k_knn launch
+  int knn_next;       // work-queue head of the running k_knn launch (light queries, chunks of 32)
+  int knn_next_heavy; // work-queue head for the heavy queries (chunks of 8)
+  int n_heavy;        // queries whose own map cell is (nearly) empty; they sort first
 };
 
 struct Ctx {

@@ -149,7 +149,7 @@ HD void rigid_to_pose(const rigid& a, double* p) {
 // Cyclic Jacobi eigen-decomposition of a symmetric NxN matrix (row-major).
 // w ascending; column j of V (V[i*N+j]) is the eigenvector of w[j].
 template <int N>
-HD void jacobi_eig(const double* Ain, double* w, double* V) {
+HD void jacobi_eig_generic(const double* Ain, double* w, double* V) {
   double a[N * N], d[N], b[N], z[N];
 #pragma unroll
   for (int i = 0; i < N * N; ++i) {
@@ -236,11 +236,144 @@ HD void jacobi_eig(const double* Ain, double* w, double* V) {
   for (int i = 0; i < N; ++i) w[i] = d[i];
 }
 
+// The 3x3 case written out on scalars: the same operations in the same order as jacobi_eig_generic<3>
+// (bit-identical results, checked by test_dmath), but every value lives in a register — the generic
+// version indexes small local arrays, which put ~40 us of dependent local-memory latency into every
+// thread that fits one edge (EdgeFeatureMatch.hpp:63).
+#define LM_JROT3(APQ, DP, DQ, ZP, ZQ, G1, H1, VP0, VQ0, VP1, VQ1, VP2, VQ2)                         \
+  {                                                                                                \
+    double apq = APQ;                                                                              \
+    double g = 100.0 * fabs(apq);                                                                  \
+    if (sweep > 4 && fabs(DP) + g == fabs(DP) && fabs(DQ) + g == fabs(DQ)) {                       \
+      APQ = 0.0;                                                                                   \
+    } else if (fabs(apq) > tresh) {                                                                \
+      double h = DQ - DP, t;                                                                       \
+      if (fabs(h) + g == fabs(h)) {                                                                \
+        t = apq / h;                                                                               \
+      } else {                                                                                     \
+        double theta = 0.5 * h / apq;                                                              \
+        t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));                                       \
+        if (theta < 0.0) t = -t;                                                                   \
+      }                                                                                            \
+      double c = 1.0 / sqrt(1.0 + t * t), s = t * c, tau = s / (1.0 + c);                          \
+      h = t * apq;                                                                                 \
+      ZP -= h;                                                                                     \
+      ZQ += h;                                                                                     \
+      DP -= h;                                                                                     \
+      DQ += h;                                                                                     \
+      APQ = 0.0;                                                                                   \
+      {                                                                                            \
+        double gg = G1, hh = H1;                                                                   \
+        G1 = gg - s * (hh + gg * tau);                                                             \
+        H1 = hh + s * (gg - hh * tau);                                                             \
+      }                                                                                            \
+      {                                                                                            \
+        double gg = VP0, hh = VQ0;                                                                 \
+        VP0 = gg - s * (hh + gg * tau);                                                            \
+        VQ0 = hh + s * (gg - hh * tau);                                                            \
+      }                                                                                            \
+      {                                                                                            \
+        double gg = VP1, hh = VQ1;                                                                 \
+        VP1 = gg - s * (hh + gg * tau);                                                            \
+        VQ1 = hh + s * (gg - hh * tau);                                                            \
+      }                                                                                            \
+      {                                                                                            \
+        double gg = VP2, hh = VQ2;                                                                 \
+        VP2 = gg - s * (hh + gg * tau);                                                            \
+        VQ2 = hh + s * (gg - hh * tau);                                                            \
+      }                                                                                            \
+    }                                                                                              \
+  }
+
+HD void jacobi_eig3(const double* Ain, double* w, double* V) {
+  double a01 = Ain[1], a02 = Ain[2], a12 = Ain[5];
+  double d0 = Ain[0], d1 = Ain[4], d2 = Ain[8];
+  double b0 = d0, b1 = d1, b2 = d2, z0 = 0.0, z1 = 0.0, z2 = 0.0;
+  double v00 = 1.0, v01 = 0.0, v02 = 0.0, v10 = 0.0, v11 = 1.0, v12 = 0.0, v20 = 0.0, v21 = 0.0, v22 = 1.0;
+  for (int sweep = 1; sweep <= 60; ++sweep) {
+    double sm = 0.0;
+    sm += fabs(a01);
+    sm += fabs(a02);
+    sm += fabs(a12);
+    if (sm == 0.0) break;
+    double tresh = (sweep < 4) ? 0.2 * sm / 9 : 0.0;
+    // (p,q) = (0,1): the j > q term touches a[0][2], a[1][2]
+    LM_JROT3(a01, d0, d1, z0, z1, a02, a12, v00, v01, v10, v11, v20, v21)
+    // (0,2): the p < j < q term touches a[0][1], a[1][2]
+    LM_JROT3(a02, d0, d2, z0, z2, a01, a12, v00, v02, v10, v12, v20, v22)
+    // (1,2): the j < p term touches a[0][1], a[0][2]
+    LM_JROT3(a12, d1, d2, z1, z2, a01, a02, v01, v02, v11, v12, v21, v22)
+    b0 += z0;
+    d0 = b0;
+    z0 = 0.0;
+    b1 += z1;
+    d1 = b1;
+    z1 = 0.0;
+    b2 += z2;
+    d2 = b2;
+    z2 = 0.0;
+  }
+  // ascending selection sort, columns follow (same comparisons as the generic version)
+#define LM_JSWAP(DA, DB, VA0, VB0, VA1, VB1, VA2, VB2) \
+  {                                                    \
+    double t_ = DA;                                    \
+    DA = DB;                                           \
+    DB = t_;                                           \
+    t_ = VA0;                                          \
+    VA0 = VB0;                                         \
+    VB0 = t_;                                          \
+    t_ = VA1;                                          \
+    VA1 = VB1;                                         \
+    VB1 = t_;                                          \
+    t_ = VA2;                                          \
+    VA2 = VB2;                                         \
+    VB2 = t_;                                          \
+  }
+  {
+    int k = 0;
+    double dk = d0;
+    if (d1 < dk) {
+      k = 1;
+      dk = d1;
+    }
+    if (d2 < dk) {
+      k = 2;
+      dk = d2;
+    }
+    if (k == 1) LM_JSWAP(d0, d1, v00, v01, v10, v11, v20, v21)
+    if (k == 2) LM_JSWAP(d0, d2, v00, v02, v10, v12, v20, v22)
+  }
+  if (d2 < d1) LM_JSWAP(d1, d2, v01, v02, v11, v12, v21, v22)
+#undef LM_JSWAP
+  w[0] = d0;
+  w[1] = d1;
+  w[2] = d2;
+  V[0] = v00;
+  V[1] = v01;
+  V[2] = v02;
+  V[3] = v10;
+  V[4] = v11;
+  V[5] = v12;
+  V[6] = v20;
+  V[7] = v21;
+  V[8] = v22;
+}
+#undef LM_JROT3
+
+template <int N>
+HD void jacobi_eig(const double* Ain, double* w, double* V) {
+  jacobi_eig_generic<N>(Ain, w, V);
+}
+template <>
+HD void jacobi_eig<3>(const double* Ain, double* w, double* V) {
+  jacobi_eig3(Ain, w, V);
+}
+
 // Least squares min |A x - b| for a row-major MxN A by Householder QR with
 // column pivoting (largest remaining column norm first); a column whose pivot
 // falls under eps*M*|first pivot| ends the factorisation, its x stays 0.
 template <int M, int N>
-HD void cpqr_solve(const double* Ain, const double* bin, double* x) {
+HD void cpqr_solve_generic(const double* Ain, const double* bin, double* x) {
   double A[M * N], b[M], v[M], y[N];
   int perm[N];
   for (int i = 0; i < M * N; ++i) A[i] = Ain[i];
@@ -301,6 +434,117 @@ HD void cpqr_solve(const double* Ain, const double* bin, double* x) {
     y[k] = s / A[k * N + k];
   }
   for (int j = 0; j < N; ++j) x[perm[j]] = y[j];
+}
+
+// Index-static form of the same factorisation (identical operations and order; pivoting moves data with
+// conditional swaps) so that, fully unrolled, the 5x3 plane fit of SurfFeatureMatch (surfFeatureMatch.hpp:52)
+// lives in registers.  Used for the 5x3 case only; test_dmath checks it bit for bit against the generic form.
+template <int M, int N>
+HD void cpqr_solve_static(const double* Ain, const double* bin, double* x) {
+  // every array index below is a compile-time constant once the loops are unrolled (M*N small), so the
+  // whole factorisation lives in registers; pivoting moves data with conditional swaps
+  double A[M * N], b[M], v[M], y[N];
+  int perm[N];
+#pragma unroll
+  for (int i = 0; i < M * N; ++i) A[i] = Ain[i];
+#pragma unroll
+  for (int i = 0; i < M; ++i) b[i] = bin[i];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    perm[j] = j;
+    y[j] = 0.0;
+  }
+  int rank = 0;
+  double first = 0.0;
+  constexpr int K = (M < N) ? M : N;
+  bool live = true;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    if (live) {
+      int piv = k;
+      double best = -1.0;
+#pragma unroll
+      for (int j = k; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = k; i < M; ++i) s += A[i * N + j] * A[i * N + j];
+        if (s > best) {
+          best = s;
+          piv = j;
+        }
+      }
+#pragma unroll
+      for (int j = k + 1; j < N; ++j) {
+        if (piv == j) {
+#pragma unroll
+          for (int i = 0; i < M; ++i) {
+            double t = A[i * N + k];
+            A[i * N + k] = A[i * N + j];
+            A[i * N + j] = t;
+          }
+          int t = perm[k];
+          perm[k] = perm[j];
+          perm[j] = t;
+        }
+      }
+      double nrm = sqrt(best);
+      if (k == 0) first = nrm;
+      if (!(nrm > 2.220446049250313e-16 * M * first) || nrm == 0.0) {
+        live = false;
+      } else {
+        rank = k + 1;
+        double alpha = (A[k * N + k] > 0.0) ? -nrm : nrm;
+        double v0 = A[k * N + k] - alpha;
+        v[k] = 1.0;
+#pragma unroll
+        for (int i = k + 1; i < M; ++i) v[i] = A[i * N + k] / v0;
+        double beta = -v0 / alpha;
+        A[k * N + k] = alpha;
+#pragma unroll
+        for (int i = k + 1; i < M; ++i) A[i * N + k] = 0.0;
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) {
+          double s = 0.0;
+#pragma unroll
+          for (int i = k; i < M; ++i) s += v[i] * A[i * N + j];
+          s *= beta;
+#pragma unroll
+          for (int i = k; i < M; ++i) A[i * N + j] -= s * v[i];
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int i = k; i < M; ++i) s += v[i] * b[i];
+        s *= beta;
+#pragma unroll
+        for (int i = k; i < M; ++i) b[i] -= s * v[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = K - 1; k >= 0; --k) {
+    if (k < rank) {
+      double s = b[k];
+#pragma unroll
+      for (int j = k + 1; j < K; ++j)
+        if (j < rank) s -= A[k * N + j] * y[j];
+      y[k] = s / A[k * N + k];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+#pragma unroll
+    for (int jj = 0; jj < N; ++jj)
+      if (perm[j] == jj) x[jj] = y[j];
+  }
+}
+
+template <int M, int N>
+HD void cpqr_solve(const double* Ain, const double* bin, double* x) {
+  cpqr_solve_generic<M, N>(Ain, bin, x);
+}
+template <>
+HD void cpqr_solve<5, 3>(const double* Ain, const double* bin, double* x) {
+  cpqr_solve_static<5, 3>(Ain, bin, x);
 }
 
 // 6x6 inverse, Gauss-Jordan with partial pivoting

@@ -481,6 +481,280 @@ __device__ void lm_update(SolveState* st, const double* tot, const SolveParams& 
   lm_propose(st, sp);
 }
 
+// ---- warp-cooperative versions of the LM 6x6 step -----------------------------------------------
+// The serial code above is the specification (it is what the oracle does, operation for operation);
+// the functions below give the same values — every sum keeps its serial order — but spread the 6x6
+// algebra over the lanes of warp 0 of the last block and keep the matrices in shared memory.  A single
+// thread walking ~2.5 k dependent fp64 instructions took ~45 us per k_fit launch (ncu: SMs idle for 65 %
+// of the kernel); the warp version's critical path is the 6-column Cholesky and the two substitutions.
+struct LmScratch {
+  double Hs[36], A[36], L[36], gs[6], y[6], x[6], step[6], row[6], trig[4];
+  int flag;
+};
+
+// se3_plus with the four trigonometric values supplied (cos(theta/2), sin(theta/2), cos(theta), sin(theta))
+__device__ __forceinline__ void se3_plus_pre(const double* x, const double* d, const double* trig, double* out) {
+  d3 om = mk3(d[0], d[1], d[2]), up = mk3(d[3], d[4], d[5]);
+  double theta = nrm3(om);
+  double re = trig[0], im;
+  if (theta < 1e-10) {
+    double t2 = theta * theta, t4 = t2 * t2;
+    im = 0.5 - 0.0208333 * t2 + 0.000260417 * t4;
+  } else {
+    im = trig[1] / theta;
+  }
+  quat dq;
+  dq.x = im * om.x;
+  dq.y = im * om.y;
+  dq.z = im * om.z;
+  dq.w = re;
+  double J[9];
+  if (theta < 1e-10) {
+    quat_to_mat(dq, J);
+  } else {
+    double O[9] = {0, -om.z, om.y, om.z, 0, -om.x, -om.y, om.x, 0};
+    double O2[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) O2[i * 3 + j] = O[i * 3 + 0] * O[0 * 3 + j] + O[i * 3 + 1] * O[1 * 3 + j] + O[i * 3 + 2] * O[2 * 3 + j];
+    double c1 = (1 - trig[2]) / (theta * theta);
+    double c2 = (theta - trig[3]) / (theta * theta * theta);
+    for (int i = 0; i < 9; ++i) J[i] = ((i % 4 == 0) ? 1.0 : 0.0) + c1 * O[i] + c2 * O2[i];
+  }
+  d3 dt = mk3(J[0] * up.x + J[1] * up.y + J[2] * up.z, J[3] * up.x + J[4] * up.y + J[5] * up.z,
+              J[6] * up.x + J[7] * up.y + J[8] * up.z);
+  quat q;
+  q.x = x[0];
+  q.y = x[1];
+  q.z = x[2];
+  q.w = x[3];
+  quat qp = qmul(dq, q);
+  d3 tp = add3(qrot(dq, mk3(x[4], x[5], x[6])), dt);
+  out[0] = qp.x;
+  out[1] = qp.y;
+  out[2] = qp.z;
+  out[3] = qp.w;
+  out[4] = tp.x;
+  out[5] = tp.y;
+  out[6] = tp.z;
+}
+
+// lm_propose, executed by all 32 lanes of one warp; st and w live in shared memory
+__device__ void lm_propose_warp(SolveState* st, LmScratch* w, const SolveParams& sp) {
+  const int lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  while (true) {
+    __syncwarp();
+    if (st->lm_iter >= sp.lm_max_iters) {
+      __syncwarp();
+      if (lane == 0) st->lm_active = 0;
+      __syncwarp();
+      return;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      st->lm_iter += 1;
+      st->lm_steps_total += 1;
+    }
+    for (int e = lane; e < 36; e += 32) {
+      int i = e / 6, j = e % 6;
+      double h = st->scale[i] * st->H[e] * st->scale[j];
+      w->Hs[e] = h;
+      w->A[e] = h;
+    }
+    if (lane < 6) w->gs[lane] = st->scale[lane] * st->g[lane];
+    __syncwarp();
+    if (lane < 6) {
+      double dj = fmin(fmax(w->Hs[lane * 7], 1e-6), 1e32);
+      w->A[lane * 7] += dj / st->radius;
+    }
+    __syncwarp();
+    // Cholesky, column by column; lane i owns row i
+    bool ok = true;
+    for (int j = 0; j < 6; ++j) {
+      double s = 0.0;
+      if (lane >= j && lane < 6) {
+        s = w->A[lane * 6 + j];
+        for (int k = 0; k < j; ++k) s -= w->L[lane * 6 + k] * w->L[j * 6 + k];
+      }
+      double sd = __shfl_sync(FULL, s, j);
+      if (!(sd > 0.0)) {
+        ok = false;
+        break;
+      }
+      double ljj = sqrt(sd);
+      if (lane == j)
+        w->L[j * 6 + j] = ljj;
+      else if (lane > j && lane < 6)
+        w->L[lane * 6 + j] = s / ljj;
+      __syncwarp();
+    }
+    double mcc = 0.0;
+    if (ok) {
+      // forward substitution, column oriented (row i subtracts L[i][k] y[k] for k ascending)
+      double acc = (lane < 6) ? w->gs[lane] : 0.0;
+      for (int i = 0; i < 6; ++i) {
+        double yi = __shfl_sync(FULL, acc, i) / w->L[i * 6 + i];
+        if (lane == i) w->y[i] = yi;
+        if (lane > i && lane < 6) acc -= w->L[lane * 6 + i] * yi;
+      }
+      __syncwarp();
+      // back substitution: x[i] = (y[i] - sum_{k>i, ascending} L[k][i] x[k]) / L[i][i]
+      if (lane == 0) {
+        for (int i = 5; i >= 0; --i) {
+          double s = w->y[i];
+          for (int k = i + 1; k < 6; ++k) s -= w->L[k * 6 + i] * w->x[k];
+          w->x[i] = s / w->L[i * 6 + i];
+        }
+      }
+      __syncwarp();
+      double stp = (lane < 6) ? -w->x[lane] : 0.0;
+      bool fin = isfinite(stp);
+      if (__any_sync(FULL, !fin)) ok = false;
+      if (lane < 6) w->step[lane] = stp;
+      __syncwarp();
+      if (ok) {
+        if (lane < 6) {
+          double row = 0;
+          for (int j = 0; j < 6; ++j) row += w->Hs[lane * 6 + j] * w->step[j];
+          w->row[lane] = row;
+        }
+        __syncwarp();
+        double sg = 0, sHs = 0;
+        for (int i = 0; i < 6; ++i) {
+          sg += w->step[i] * w->gs[i];
+          sHs += w->step[i] * w->row[i];
+        }
+        mcc = -(sg + 0.5 * sHs);
+      }
+    }
+    if (!ok || !(mcc > 0.0)) {  // uniform across the warp: every lane computed the same values
+      int give_up = 0;
+      __syncwarp();
+      if (lane == 0) {
+        st->lm_invalid += 1;
+        if (st->lm_invalid >= 5) {
+          st->lm_active = 0;
+          give_up = 1;
+        } else {
+          st->radius *= 0.5;
+          if (st->radius < 1e-32) {
+            st->lm_active = 0;
+            give_up = 1;
+          }
+        }
+      }
+      give_up = __shfl_sync(FULL, give_up, 0);
+      __syncwarp();
+      if (give_up) return;
+      continue;
+    }
+    // candidate = Plus(x, step * scale); the four trigonometric values come from four lanes
+    double delta[6];
+    for (int j = 0; j < 6; ++j) delta[j] = w->step[j] * st->scale[j];
+    double theta = nrm3(mk3(delta[0], delta[1], delta[2]));
+    double half = 0.5 * theta;
+    double tv = 0.0;
+    if (lane == 0) tv = cos(half);
+    if (lane == 1) tv = sin(half);
+    if (lane == 2) tv = cos(theta);
+    if (lane == 3) tv = sin(theta);
+    if (lane < 4) w->trig[lane] = tv;
+    __syncwarp();
+    if (lane == 0) {
+      st->lm_invalid = 0;
+      se3_plus_pre(st->x, delta, w->trig, st->cand);
+      st->model_change = mcc;
+    }
+    __syncwarp();
+    return;
+  }
+}
+
+__device__ void lm_begin_warp(SolveState* st, LmScratch* w, const double* tot, const SolveParams& sp) {
+  const int lane = threadIdx.x & 31;
+  for (int e = lane; e < 36; e += 32) {
+    int i = e / 6, j = e % 6;
+    int a = i < j ? i : j, b = i < j ? j : i;
+    st->H[e] = tot[a * 6 - a * (a - 1) / 2 + (b - a)];  // upper-triangle packing of acc_row
+  }
+  if (lane < 6) {
+    st->g[lane] = tot[21 + lane];
+    st->scale[lane] = 1.0 / (1.0 + sqrt(tot[lane * 6 - lane * (lane - 1) / 2]));
+  }
+  __syncwarp();
+  if (lane == 0) {
+    st->cost = tot[27];
+    st->lm_iter = 0;
+    st->lm_invalid = 0;
+    st->radius = 1e4;
+    st->decrease = 2.0;
+    st->x_norm = norm7(st->x);
+    st->lm_active = 1;
+    if (tot[28] == 0.0 || grad_max(st->g) <= 1e-10) st->lm_active = 0;
+  }
+  __syncwarp();
+  if (!st->lm_active) return;
+  lm_propose_warp(st, w, sp);
+}
+
+__device__ void lm_update_warp(SolveState* st, LmScratch* w, const double* tot, const SolveParams& sp) {
+  const int lane = threadIdx.x & 31;
+  int verdict = 0;  // 0 stop, 1 accepted, 2 rejected
+  if (lane == 0) {
+    double cand_cost = tot[27];
+    double diff[7];
+    for (int i = 0; i < 7; ++i) diff[i] = st->x[i] - st->cand[i];
+    double cc = st->cost - cand_cost;
+    if (norm7(diff) <= 1e-8 * (st->x_norm + 1e-8)) {
+      st->lm_active = 0;  // parameter tolerance: candidate not taken
+    } else if (fabs(cc) <= 1e-6 * st->cost) {
+      st->lm_active = 0;  // function tolerance: candidate not taken
+    } else {
+      double rho = cc / st->model_change;
+      if (rho > 1e-3) {
+        for (int i = 0; i < 7; ++i) st->x[i] = st->cand[i];
+        st->x_norm = norm7(st->x);
+        st->cost = cand_cost;
+        st->lm_steps_accepted += 1;
+        double u = 2.0 * rho - 1.0;
+        double f = 1.0 - u * u * u;
+        st->radius = st->radius / fmax(1.0 / 3.0, f);
+        st->radius = fmin(1e16, st->radius);
+        st->decrease = 2.0;
+        verdict = 1;
+      } else {
+        st->radius = st->radius / st->decrease;
+        st->decrease *= 2.0;
+        verdict = 2;
+      }
+    }
+  }
+  verdict = __shfl_sync(0xffffffffu, verdict, 0);
+  if (verdict == 0) return;
+  if (verdict == 1) {
+    for (int e = lane; e < 36; e += 32) {
+      int i = e / 6, j = e % 6;
+      int a = i < j ? i : j, b = i < j ? j : i;
+      st->H[e] = tot[a * 6 - a * (a - 1) / 2 + (b - a)];
+    }
+    if (lane < 6) st->g[lane] = tot[21 + lane];
+    __syncwarp();
+    int stop = 0;
+    if (lane == 0 && grad_max(st->g) <= 1e-10) {
+      st->lm_active = 0;
+      stop = 1;
+    }
+    if (__shfl_sync(0xffffffffu, stop, 0)) return;
+  }
+  int stop = 0;
+  if (lane == 0 && st->radius < 1e-32) {
+    st->lm_active = 0;
+    stop = 1;
+  }
+  if (__shfl_sync(0xffffffffu, stop, 0)) return;
+  lm_propose_warp(st, w, sp);
+}
+
 // ------------------------------------------------------------------ kernels
 struct QueryBufs {
   unsigned* keys;            // [upper] sort keys (kind | L0 | L1 | L2 cell of the world point, top 32 bits)
@@ -503,19 +777,46 @@ __device__ __forceinline__ unsigned long long query_cell_key(const MapDev& md, f
   return (pack_cell(md, cx, cy, cz) << 12) | ((unsigned long long)f1 << 6) | (unsigned long long)f2;
 }
 
+// number of map points in the L2 cell that holds (x,y,z): a cheap density probe (scheduling heuristic only)
+__device__ __forceinline__ int own_cell_population(const MapView& mv, float x, float y, float z) {
+  const MapDev md = *mv.dev;
+  if (md.n <= 0 || !(fabsf(x) < 2.0e5f && fabsf(y) < 2.0e5f && fabsf(z) < 2.0e5f)) return 0;
+  int ax = (int)floorf(x * 16.0f), ay = (int)floorf(y * 16.0f), az = (int)floorf(z * 16.0f);
+  CellCursor cur;
+  cur.key = ~0ull;
+  cur.rec = nullptr;
+  const CellRec* rec = find_cell(mv, md, cur, (ax >> 4) - md.min_c[0], (ay >> 4) - md.min_c[1], (az >> 4) - md.min_c[2]);
+  if (!rec) return 0;
+  int f1 = (((az >> 2) & 3) << 4) | (((ay >> 2) & 3) << 2) | ((ax >> 2) & 3);
+  unsigned long long m1 = rec->mask;
+  if (!((m1 >> f1) & 1ull)) return 0;
+  int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
+  int f2 = ((az & 3) << 4) | ((ay & 3) << 2) | (ax & 3);
+  unsigned long long m2 = mv.l1_mask[l1];
+  if (!((m2 >> f2) & 1ull)) return 0;
+  int b = mv.l1_first[l1] + __popcll(m2 & ((1ull << f2) - 1ull));
+  return mv.l2_start[b + 1] - mv.l2_start[b];
+}
+
 // pointAssociateToMap (edgeSurfFeatureRegistration.hpp:342-350): world point in fp64, stored as fp32;
-// plus the sort key that groups the queries of one map cell into one warp
+// plus the sort key that groups the queries of one map cell into one warp.  Queries whose own map cell is
+// (nearly) empty are the expensive ones (wider sweeps): their key sorts them first, so the persistent
+// k_knn warps start with them and the cheap dense-region queries fill the tail (longest job first).
 __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, const int* __restrict__ counts,
-                                               SolveState* __restrict__ st, const MapDev* __restrict__ dev_e,
-                                               const MapDev* __restrict__ dev_s, int kind_bit, int key_shift,
+                                               SolveState* __restrict__ st, MapPair maps, int has_edge_map,
+                                               int has_surf_map, int kind_bit, int key_shift,
                                                int upper, int solver, int with_keys, QueryBufs qb) {
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) st->knn_next = 0;  // work queue of the k_knn launch that follows
-  if (i >= upper) return;
+  if (i == 0) {  // work queues of the k_knn launch that follows
+    st->knn_next = 0;
+    st->knn_next_heavy = 0;
+  }
+  const bool in_range = i < upper;
   const int n_e = counts[0], n_s = counts[1];
-  unsigned long long key = 2ull << kind_bit;  // padding sorts behind every live query
-  if (i < n_e + n_s) {
+  unsigned long long key = 4ull << kind_bit;  // padding sorts behind every live query
+  bool heavy = false;
+  if (in_range && i < n_e + n_s) {
     quat q;
     q.x = st->x[0];
     q.y = st->x[1];
@@ -527,9 +828,22 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
     float4 w = make_float4((float)pw.x, (float)pw.y, (float)pw.z, 0.f);
     qb.pw[i] = w;
     const bool is_edge = i < n_e;
-    key = query_cell_key(is_edge ? *dev_e : *dev_s, w.x, w.y, w.z) | (is_edge ? 0ull : (1ull << kind_bit));
+    if (with_keys && (is_edge ? has_edge_map : has_surf_map)) {
+      const MapView& mv = is_edge ? maps.edge : maps.surf;
+      int pop = own_cell_population(mv, w.x, w.y, w.z);
+      heavy = pop < 5;
+      key = query_cell_key(*mv.dev, w.x, w.y, w.z) | (is_edge ? 0ull : (1ull << kind_bit)) |
+            (heavy ? 0ull : (2ull << kind_bit));
+    } else {
+      key = 0ull;
+      heavy = with_keys != 0;
+    }
   }
-  if (with_keys) {
+  if (with_keys) {  // warp-aggregated count of the heavy queries (they occupy sorted positions [0, n_heavy))
+    unsigned hb = __ballot_sync(0xffffffffu, heavy);
+    if ((threadIdx.x & 31) == 0 && hb) atomicAdd(&st->n_heavy, __popc(hb));
+  }
+  if (with_keys && in_range) {
     // ordering heuristic only: when the packed cell key is wider than 32 bits its low (finest) bits are dropped
     qb.keys[i] = (unsigned)(key >> key_shift);
     qb.vals[i] = i;
@@ -548,13 +862,29 @@ __global__ void __launch_bounds__(128) k_knn(const int* __restrict__ perm, const
   const int n_e = counts[0], n_s = counts[1];
   const int lane = threadIdx.x & 31;
   const int live = n_e + n_s;  // sorted positions >= live are padding
+  const int nh = min(st->n_heavy, live);
+  // (chunks of 8 for the heavy queries were measured: 30 % slower — with ~one 32-query chunk per resident warp
+  //  the kernel is bounded by instruction throughput of the heavy lanes, not by the latency of one chunk)
+  bool heavy_left = false && nh > 0;
   while (true) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&st->knn_next, 32);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= live) break;
+    // heavy queries (sorted first) go out eight at a time: a chunk's latency is the sum of its lanes'
+    // divergent searches, and these are the long ones; the rest go out a full warp at a time
+    int base = 0, width = 32;
+    if (heavy_left) {
+      if (lane == 0) base = atomicAdd(&st->knn_next_heavy, 8);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= nh) {
+        heavy_left = false;
+        continue;
+      }
+      width = min(8, nh - base);
+    } else {
+      if (lane == 0) base = atomicAdd(&st->knn_next, 32);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= live) break;
+    }
     int t = base + lane;
-    if (t >= upper) continue;
+    if (lane >= width || t >= upper) continue;
     int f = perm[t];
     if (f >= live) continue;
     const bool is_edge = f < n_e;
@@ -661,14 +991,16 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
   // the serial 6x6 step runs on a shared-memory copy of the state (one thread, latency bound:
   // global-memory round trips on every st-> field would dominate it)
   __shared__ SolveState sh;
+  __shared__ LmScratch scratch;
   state_load(&sh, st);
   if (threadIdx.x == 0) {
     sh.n_edge_ok = (int)tot[29];
     sh.n_surf_ok = (int)tot[28] - (int)tot[29];
-    if (sp.solver == LMSF_SOLVER_GN)
-      gn_step(&sh, tot, sp);
-    else
-      lm_begin(&sh, tot, sp);
+  }
+  if (sp.solver == LMSF_SOLVER_GN) {
+    if (threadIdx.x == 0) gn_step(&sh, tot, sp);
+  } else if (threadIdx.x < 32) {
+    lm_begin_warp(&sh, &scratch, tot, sp);
   }
   state_store(st, &sh);
 }
@@ -701,8 +1033,9 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* 
   }
   if (!reduce_grid(acc, partial, st, tot)) return;
   __shared__ SolveState sh;
+  __shared__ LmScratch scratch;
   state_load(&sh, st);
-  if (threadIdx.x == 0) lm_update(&sh, tot, sp);
+  if (threadIdx.x < 32) lm_update_warp(&sh, &scratch, tot, sp);
   state_store(st, &sh);
 }
 
@@ -717,6 +1050,8 @@ __global__ void k_state_init(SolveState* st, const double* __restrict__ pose) {
   st->lm_steps_total = st->lm_steps_accepted = 0;
   st->ticket = 0u;
   st->knn_next = 0;
+  st->knn_next_heavy = 0;
+  st->n_heavy = 0;
 }
 
 // ------------------------------------------------------------------ test hooks
@@ -874,20 +1209,20 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
       // outer iterations (the pose moves by millimetres between them), which also keeps the sorted position
       // of a feature stable so that k_knn can seed its search with the previous iteration's neighbours
       StageScope scope(c, LMSF_STAGE_ASSOC);
-      const int key_shift = (kb + 2 > 32) ? (kb + 2 - 32) : 0;
-      LM_LAUNCH(c, k_assoc, div_up(up, 256), 256, 0, c->d_feat, c->ex.counts, c->d_state, c->map[0].dev, c->map[1].dev,
-                kb, key_shift, up, solver, it == 0 ? 1 : 0, qb);
+      const int key_shift = (kb + 3 > 32) ? (kb + 3 - 32) : 0;
+      LM_LAUNCH(c, k_assoc, div_up(up, 256), 256, 0, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, kb, key_shift,
+                up, solver, it == 0 ? 1 : 0, qb);
       if (it == 0) {
         size_t tmp = c->cub_tmp_bytes;
         LM_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, (unsigned*)c->q_keys, (unsigned*)c->q_keys_alt,
-                                                c->q_vals, c->q_vals_alt, up, 0, kb + 2 - key_shift, c->stream));
+                                                c->q_vals, c->q_vals_alt, up, 0, kb + 3 - key_shift, c->stream));
         c->launches++;
       }
     }
     {
       StageScope scope(c, LMSF_STAGE_MATCH);
       int knn_grid = div_up(up, 128);
-      if (knn_grid > 148 * 6) knn_grid = 148 * 6;  // persistent: every resident warp pulls work
+      if (knn_grid > 148 * 7) knn_grid = 148 * 7;  // persistent: every resident warp pulls work
       LM_LAUNCH(c, k_knn, knn_grid, 128, 0, c->q_vals_alt, c->d_pw, c->ex.counts, c->d_state, maps, he, hs, up,
                 solver, it == 0 ? 0 : 1, c->d_nbr);
       c->match_bytes += alg_bytes;

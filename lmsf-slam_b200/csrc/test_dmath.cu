@@ -79,7 +79,12 @@ int main() {
     for (int i = 0; i < 4; ++i) c.x7[i] /= sqrt(qn);
     for (int i = 4; i < 7; ++i) c.x7[i] = rnd() * 10;
   }
-  for (int t = 0; t < n; ++t) run_case(hc[t], ho[t]);
+  for (int t = 0; t < n; ++t) {
+    run_case(hc[t], ho[t]);
+    jacobi_eig_generic<3>(hc[t].S, ho[t].w3, ho[t].V3);  // host reference of the scalar 3x3 version = the generic one
+    double bb[5] = {-1, -1, -1, -1, -1};
+    cpqr_solve_generic<5, 3>(hc[t].A, bb, ho[t].qr53);     // likewise for the index-static 5x3 QR
+  }
   Case* dc;
   Out* dout;
   if (cudaMalloc(&dc, n * sizeof(Case)) != cudaSuccess) {
