@@ -18,7 +18,7 @@ from .capi import (IDENTITY_POSE, KIND_EDGE, KIND_SURF, SOLVER_GN, SOLVER_HUBER_
                    LmsfError, Params, RegStats, TrackStats)
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "csrc", "liblmsf_b200.so")
+LIB_PATH = os.environ.get("LMSF_B200_LIB") or os.path.join(PKG_DIR, "csrc", "liblmsf_b200.so")  # env: tuning builds only
 
 _lib = None
 

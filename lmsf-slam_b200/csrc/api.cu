@@ -11,7 +11,7 @@
 namespace lm {
 
 // ------------------------------------------------------------------ profiling
-StageScope::StageScope(Ctx* c_, int s) : c(c_), stage(s), l0(c_->launches) {
+StageScope::StageScope(Ctx* c_, int s, cudaStream_t stream) : c(c_), stage(s), st(stream ? stream : c_->stream), l0(c_->launches) {
   if (!c->prof) return;
   auto take = [&]() {
     cudaEvent_t e = nullptr;
@@ -25,12 +25,12 @@ StageScope::StageScope(Ctx* c_, int s) : c(c_), stage(s), l0(c_->launches) {
   };
   a = take();
   b = take();
-  cudaEventRecord(a, c->stream);
+  cudaEventRecord(a, st);
 }
 StageScope::~StageScope() {
   c->prof_launch[stage] += c->launches - l0;
   if (!a) return;
-  cudaEventRecord(b, c->stream);
+  cudaEventRecord(b, st);
   c->spans.push_back(Ctx::Span{stage, a, b});
 }
 
@@ -73,59 +73,90 @@ static int fetch_counts(Ctx* c) {
 }
 
 // choose the cloud the index is built over (raw window or its voxel-filtered copy) and build
-static int index_window(Ctx* c, int kind) {
+static int index_window(Ctx* c, int kind, cudaStream_t st, bool fixed_grid) {
   MapIndex& m = c->map[kind];
   int total = 0;
   for (int f : m.frame_n) total += f;
   float leaf = kind ? c->prm.map_leaf_surf : c->prm.map_leaf_edge;
   int n = total;
   if (leaf > 0.f && total > 0) {
-    LM_TRY(voxel_run(c, m.win, total, leaf, m.vox, &n, nullptr));
+    LM_TRY(voxel_run(c, m.win, total, leaf, m.vox, &n, nullptr));  // main stream, synchronising
     m.cat = m.vox;
   } else {
     m.cat = m.win;
   }
   if (n == 0) return LMSF_OK;  // an empty source is ignored (ceres_edgeSurfFeatureRegistration.hpp:58)
-  return map_build(c, m, n);
+  return map_build(c, m, n, st, fixed_grid);
 }
 
 // updateLocalMap (LidarTrackerLocalMap.hpp:205-232) over the sliding-window local map (the reference's
 // PointCloudLocalMapBase is missing from its tree; contract inferred, SURVEY.md §8 a6'):
 // type 1 = AddFrameForMotion (append, evict the oldest beyond `window`), 2 = AddFrameForTime
-// (replace the newest frame).  c->n_edge / c->n_surf must be valid on the host.
+// (replace the newest frame).  c->n_edge / c->n_surf must be valid on the host and the main stream idle.
+//
+// When the features came from our own extraction (finite, range-gated) and no map voxel filter is set, the
+// whole update runs asynchronously on the map stream inside a grid frozen around the sensor: no host sync,
+// and the index rebuild overlaps the next sweep's upload and feature extraction.  ev_feat_free releases
+// d_feat to the next extraction, ev_map_done gates the next solve.
 static int update_map(Ctx* c, const rigid& T, int type) {
   Rigid12 T12;
   for (int i = 0; i < 9; ++i) T12.R[i] = T.R[i];
   for (int i = 0; i < 3; ++i) T12.t[i] = T.t[i];
+  const bool async = c->feat_from_extract && !(c->prm.map_leaf_edge > 0.f) && !(c->prm.map_leaf_surf > 0.f);
+  cudaStream_t st = async ? c->stream_map : c->stream;
+  const double reach = 1.2 * (double)c->prm.max_range + 2.0;
+  bool fixed_ok[2] = {false, false};
   for (int kind = 0; kind < 2; ++kind) {
     int nk = kind ? c->n_surf : c->n_edge;
     if (nk == 0) continue;
     MapIndex& m = c->map[kind];
-    {
-      StageScope scope(c, LMSF_STAGE_MAP);
-      int total = 0;
-      for (int f : m.frame_n) total += f;
-      int drop = 0;
-      if (type == 1) {
-        if ((int)m.frame_n.size() + 1 > c->prm.window) drop = m.frame_n.front();
-      } else if (!m.frame_n.empty()) {
-        total -= m.frame_n.back();
-        m.frame_n.pop_back();
-      }
-      int kept = total - drop;
-      if (kept + nk > m.cap) return LMSF_ERR_CAPACITY;
-      if (drop > 0) {
-        LM_CUDA(cudaMemcpyAsync(m.win_alt, m.win + drop, (size_t)kept * sizeof(float4), cudaMemcpyDeviceToDevice,
-                                c->stream));
-        float4* t = m.win;
-        m.win = m.win_alt;
-        m.win_alt = t;
-        m.frame_n.erase(m.frame_n.begin());
-      }
-      LM_LAUNCH(c, k_transform, div_up(nk, 256), 256, 0, c->d_feat, c->ex.counts, kind, T12, m.win + kept);
-      m.frame_n.push_back(nk);
+    StageScope scope(c, LMSF_STAGE_MAP, st);
+    int total = 0;
+    for (int f : m.frame_n) total += f;
+    int drop = 0;
+    if (type == 1) {
+      if ((int)m.frame_n.size() + 1 > c->prm.window) drop = m.frame_n.front();
+    } else if (!m.frame_n.empty()) {
+      total -= m.frame_n.back();
+      m.frame_n.pop_back();
+      m.frame_pos.pop_back();
     }
-    LM_TRY(index_window(c, kind));
+    int kept = total - drop;
+    if (kept + nk > m.cap) return LMSF_ERR_CAPACITY;
+    if (drop > 0) {
+      LM_CUDA(cudaMemcpyAsync(m.win_alt, m.win + drop, (size_t)kept * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+      float4* t = m.win;
+      m.win = m.win_alt;
+      m.win_alt = t;
+      m.frame_n.erase(m.frame_n.begin());
+      m.frame_pos.erase(m.frame_pos.begin());
+    }
+    LM_LAUNCH_ON(c, st, k_transform, div_up(nk, 256), 256, 0, c->d_feat, c->ex.counts, kind, T12, m.win + kept);
+    m.frame_n.push_back(nk);
+    m.frame_pos.push_back({T.t[0], T.t[1], T.t[2]});
+    if (async) {
+      // keep the frozen grid while every frame of the window fits it; otherwise re-centre it on this pose
+      bool ok = m.fixed;
+      for (const auto& fp : m.frame_pos) ok = ok && map_grid_covers(m, fp.data(), reach);
+      if (!ok) {
+        ok = map_freeze_grid(m, T.t);
+        for (const auto& fp : m.frame_pos) ok = ok && map_grid_covers(m, fp.data(), reach);
+      }
+      fixed_ok[kind] = ok;
+    }
+  }
+  if (async) {
+    LM_CUDA(cudaEventRecord(c->ev_feat_free, st));
+    c->feat_pending = true;
+  }
+  for (int kind = 0; kind < 2; ++kind) {
+    int nk = kind ? c->n_surf : c->n_edge;
+    if (nk == 0) continue;
+    LM_TRY(index_window(c, kind, st, async && fixed_ok[kind]));
+  }
+  if (async) {
+    LM_CUDA(cudaEventRecord(c->ev_map_done, st));
+    c->map_pending = true;
   }
   return LMSF_OK;
 }
@@ -191,6 +222,7 @@ static int tracker_core(Ctx* c, int upper, double stamp, double delta[7], double
     c->curr = ident ? rigid_mul(c->prev, c->motion) : rigid_mul(c->prev, rigid_from_pose(delta));
     double p[7];
     rigid_to_pose(c->curr, p);  // Quaterniond(T.rotation())
+    LM_TRY(wait_map(c));  // the previous keyframe's index rebuild (map stream) must be complete
     LM_TRY(run_solver(c, c->prm.solver, p, &s.reg, upper));  // leaves n_edge / n_surf on the host
     c->curr = rigid_from_pose(p);  // T.linear() = q.toRotationMatrix()
     c->motion = rigid_mul(rigid_inv(c->prev), c->curr);
@@ -216,6 +248,8 @@ static int tracker_core(Ctx* c, int upper, double stamp, double delta[7], double
 static int upload_features(Ctx* c, const float* edge, int n_e, const float* surf, int n_s) {
   if (n_e < 0 || n_s < 0 || (n_e > 0 && !edge) || (n_s > 0 && !surf)) return LMSF_ERR_INVALID;
   if (n_e + n_s > c->prm.max_points) return LMSF_ERR_CAPACITY;
+  LM_TRY(wait_feat(c));
+  c->feat_from_extract = false;  // caller-supplied features: arbitrary coordinates, the map update stays synchronous
   if (n_e) memcpy(c->h_pts, edge, (size_t)n_e * sizeof(float4));
   if (n_s) memcpy(c->h_pts + n_e, surf, (size_t)n_s * sizeof(float4));
   if (n_e + n_s)
@@ -237,6 +271,7 @@ static int upload_sweep(Ctx* c, const float* xyzi, int n) {
 static void destroy(Ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->stream_map) cudaStreamSynchronize(c->stream_map);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& sp : c->spans) {
     cudaEventDestroy(sp.a);
@@ -255,12 +290,18 @@ static void destroy(Ctx* c) {
   cudaFreeHost(c->h_pose);
   cudaFreeHost(c->h_ints);
   cudaFreeHost(c->h_state);
+  if (c->ev_feat_free) cudaEventDestroy(c->ev_feat_free);
+  if (c->ev_map_done) cudaEventDestroy(c->ev_map_done);
+  if (c->stream_map) cudaStreamDestroy(c->stream_map);
   if (c->stream) cudaStreamDestroy(c->stream);
 }
 
 static int create(Ctx* c) {
   size_t cap = (size_t)c->prm.max_points;
   LM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  LM_CUDA(cudaStreamCreateWithFlags(&c->stream_map, cudaStreamNonBlocking));
+  LM_CUDA(cudaEventCreateWithFlags(&c->ev_feat_free, cudaEventDisableTiming));
+  LM_CUDA(cudaEventCreateWithFlags(&c->ev_map_done, cudaEventDisableTiming));
   LM_CUDA(cudaMalloc(&c->d_sweep, cap * sizeof(float4)));
   LM_CUDA(cudaMalloc(&c->d_feat, cap * sizeof(float4)));
   LM_CUDA(cudaMalloc(&c->d_tmp, cap * sizeof(float4)));
@@ -367,7 +408,9 @@ int lmsf_extract_features(lmsf_ctx* c, const float* xyzi, int n, uint8_t* label_
                           float* surf_xyzi, int* n_surf) {
   ENTER(c);
   LM_TRY(upload_sweep(c, xyzi, n));
+  LM_TRY(wait_feat(c));
   LM_TRY(extract_run(c, c->d_sweep, n));
+  c->feat_from_extract = true;
   LM_TRY(fetch_counts(c));
   const int ne = c->n_edge, ns = c->n_surf;
   if (label_out && n) LM_CUDA(cudaMemcpyAsync(label_out, c->ex.label, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
@@ -385,6 +428,7 @@ int lmsf_extract_features(lmsf_ctx* c, const float* xyzi, int n, uint8_t* label_
 int lmsf_voxel_downsample(lmsf_ctx* c, const float* xyzi, int n, float leaf, float* out_xyzi, int* n_out,
                           int32_t* voxel_of_point) {
   ENTER(c);
+  LM_TRY(wait_map(c));
   if (n < 0 || !(leaf > 0.f) || !n_out || (n > 0 && !xyzi)) return LMSF_ERR_INVALID;
   if (n > c->vox_cap) return LMSF_ERR_CAPACITY;
   *n_out = 0;
@@ -414,6 +458,7 @@ int lmsf_map_set(lmsf_ctx* c, int kind, const float* xyzi, int n) {
   if (n == 0) return LMSF_OK;  // ceres_edgeSurfFeatureRegistration.hpp:58
   MapIndex& m = c->map[kind];
   if (n > m.cap) return LMSF_ERR_CAPACITY;
+  LM_TRY(wait_map(c));
   const int chunk = c->prm.max_points;
   for (int o = 0; o < n; o += chunk) {
     int k = (n - o < chunk) ? n - o : chunk;
@@ -422,12 +467,15 @@ int lmsf_map_set(lmsf_ctx* c, int kind, const float* xyzi, int n) {
     LM_CUDA(cudaStreamSynchronize(c->stream));
   }
   m.frame_n.assign(1, n);
+  m.frame_pos.assign(1, {0.0, 0.0, 0.0});
+  m.fixed = false;  // arbitrary cloud: bounding-box build
   m.cat = m.win;  // SetInputSource takes the cloud as given: no map voxel filter on this path
-  return map_build(c, m, n);
+  return map_build(c, m, n, c->stream, false);
 }
 
 int lmsf_knn5(lmsf_ctx* c, int kind, const float* q_xyz, int nq, int32_t* idx5, float* d2_5) {
   ENTER(c);
+  LM_TRY(wait_map(c));
   if (kind < 0 || kind > 1 || nq < 0 || (nq > 0 && (!q_xyz || !idx5 || !d2_5))) return LMSF_ERR_INVALID;
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
   float* d_q = nullptr;
@@ -460,6 +508,7 @@ int lmsf_knn5(lmsf_ctx* c, int kind, const float* q_xyz, int nq, int32_t* idx5, 
 
 int lmsf_match(lmsf_ctx* c, int kind, const float* q_xyz, int nq, uint8_t* ok, double* out10) {
   ENTER(c);
+  LM_TRY(wait_map(c));
   if (kind < 0 || kind > 1 || nq < 0 || (nq > 0 && (!q_xyz || !ok || !out10))) return LMSF_ERR_INVALID;
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
   if (nq == 0) return LMSF_OK;
@@ -493,6 +542,7 @@ int lmsf_match(lmsf_ctx* c, int kind, const float* q_xyz, int nq, uint8_t* ok, d
 int lmsf_register(lmsf_ctx* c, const float* edge_xyzi, int n_e, const float* surf_xyzi, int n_s, int solver,
                   double pose[7], lmsf_reg_stats* st) {
   ENTER(c);
+  LM_TRY(wait_map(c));
   if (!pose || (solver != LMSF_SOLVER_GN && solver != LMSF_SOLVER_HUBER_LM)) return LMSF_ERR_INVALID;
   LM_TRY(upload_features(c, edge_xyzi, n_e, surf_xyzi, n_s));
   return run_solver(c, solver, pose, st, n_e + n_s);
@@ -510,7 +560,9 @@ int lmsf_tracker_step(lmsf_ctx* c, const float* xyzi, int n, double stamp, doubl
   ENTER(c);
   if (!delta || !pose_out) return LMSF_ERR_INVALID;
   LM_TRY(upload_sweep(c, xyzi, n));
+  LM_TRY(wait_feat(c));
   LM_TRY(extract_run(c, c->d_sweep, n));
+  c->feat_from_extract = true;
   return tracker_core(c, n, stamp, delta, pose_out, st);
 }
 
@@ -518,7 +570,9 @@ int lmsf_tracker_step_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp,
                           lmsf_track_stats* st) {
   ENTER(c);
   if (!delta || !pose_out || n < 0 || (n > 0 && !d_xyzi)) return LMSF_ERR_INVALID;
+  LM_TRY(wait_feat(c));
   LM_TRY(extract_run(c, (const float4*)d_xyzi, n));
+  c->feat_from_extract = true;
   return tracker_core(c, n, stamp, delta, pose_out, st);
 }
 
@@ -532,10 +586,15 @@ int lmsf_tracker_step_features(lmsf_ctx* c, const float* edge_xyzi, int n_e, con
 
 int lmsf_tracker_reset(lmsf_ctx* c) {
   ENTER(c);
+  LM_CUDA(cudaStreamSynchronize(c->stream_map));
   LM_CUDA(cudaStreamSynchronize(c->stream));
+  c->map_pending = c->feat_pending = false;
   c->init = false;
   for (int k = 0; k < 2; ++k) {
     c->map[k].frame_n.clear();
+    c->map[k].frame_pos.clear();
+    c->map[k].fixed = false;
+    c->map[k].n_cells_seen = 0;
     c->map[k].ready = false;
     c->map[k].n_host = 0;
     c->map[k].cat = c->map[k].win;
@@ -549,11 +608,14 @@ int lmsf_tracker_register_aux(lmsf_ctx* c, const float* xyzi, int n, double pose
   ENTER(c);
   if (!pose) return LMSF_ERR_INVALID;
   LM_TRY(upload_sweep(c, xyzi, n));
+  LM_TRY(wait_feat(c));
   LM_TRY(extract_run(c, c->d_sweep, n));
+  c->feat_from_extract = true;
   LM_TRY(scan_filter(c));
   rigid T = rigid_from_pose(pose);  // Solve(Isometry3d&): quaternion <-> matrix round trip
   double p[7];
   rigid_to_pose(T, p);
+  LM_TRY(wait_map(c));
   LM_TRY(run_solver(c, c->prm.solver, p, st, n));
   T = rigid_from_pose(p);
   rigid_to_pose(T, pose);
@@ -562,6 +624,7 @@ int lmsf_tracker_register_aux(lmsf_ctx* c, const float* xyzi, int n, double pose
 
 int lmsf_get_map(lmsf_ctx* c, int kind, float* xyzi, int cap, int* n) {
   ENTER(c);
+  LM_TRY(wait_map(c));
   if (kind < 0 || kind > 1 || !n) return LMSF_ERR_INVALID;
   const MapIndex& m = c->map[kind];
   *n = m.n_host;
@@ -605,6 +668,7 @@ int lmsf_profile_enable(lmsf_ctx* c, int enable) {
 int lmsf_profile_read(lmsf_ctx* c, double ms[LMSF_N_STAGES], int64_t launches[LMSF_N_STAGES], double* match_alg_bytes,
                       int reset) {
   ENTER(c);
+  LM_CUDA(cudaStreamSynchronize(c->stream_map));
   LM_CUDA(cudaStreamSynchronize(c->stream));
   for (auto& sp : c->spans) {
     float t = 0.f;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <array>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,12 @@ namespace lm {
 #define LM_LAUNCH(c, kern, grid, block, smem, ...)                    \
   do {                                                                \
     kern<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__);      \
+    (c)->launches++;                                                  \
+  } while (0)
+// same, on an explicit stream (the local-map update runs on its own stream)
+#define LM_LAUNCH_ON(c, st, kern, grid, block, smem, ...)             \
+  do {                                                                \
+    kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);             \
     (c)->launches++;                                                  \
   } while (0)
 
@@ -95,13 +102,18 @@ struct MapIndex {
   int* l2_start = nullptr;                 // [cap+1] start of every occupied L2 cell
   int* l1_first = nullptr;                 // [cap+1] first L2 cell of every occupied L1 cell
   unsigned long long* l1_mask = nullptr;   // [cap] L2 occupancy of every occupied L1 cell
-  int* d_cnt = nullptr;                    // [4] device counters: n2, n1
+  int* d_cnt = nullptr;                    // [4] device counters: n2, n1, inserted L0 cells, insert-failed flag
+  unsigned* d_box = nullptr;               // [8] bbox scratch of this map (ordered-uint min/max, finite count)
+  int* h_cnt = nullptr;                    // [4] pinned mirror of d_cnt (read back with the next pose)
+  bool fixed = false;                      // grid origin / key width frozen (tracker maps): builds need no host sync
+  int n_cells_seen = 0;                    // occupied L0 cells of the last build that was read back
   uint8_t* flags = nullptr;                // [cap]
   CellRec* table = nullptr;                // [table_cap]
   unsigned table_cap = 0;
   MapDev* dev = nullptr;     // device copy
   MapDev host;               // host mirror (after build)
   std::vector<int> frame_n;  // sliding window frame sizes, oldest first
+  std::vector<std::array<double, 3>> frame_pos;  // sensor position of every window frame (frozen-grid cover test)
 };
 
 // ---------------------------------------------------------------- solver state (device resident)
@@ -173,6 +185,15 @@ struct Ctx {
 
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
+  void* cub_tmp_map = nullptr;  // CUB scratch of the map stream (builds overlap the next sweep's extraction)
+
+  // local-map update pipeline: its own stream, ordered against the main stream with two events
+  cudaStream_t stream_map = nullptr;
+  cudaEvent_t ev_feat_free = nullptr;  // map stream has consumed d_feat (transforms done)
+  cudaEvent_t ev_map_done = nullptr;   // map stream has finished the index builds
+  bool map_pending = false;            // main stream has not yet waited for ev_map_done
+  bool feat_pending = false;           // main stream has not yet waited for ev_feat_free
+  bool feat_from_extract = false;      // d_feat came from extract_run: finite and range-gated
 
   // pinned host staging
   float4* h_pts = nullptr;     // [max_points]
@@ -204,9 +225,10 @@ struct Ctx {
 struct StageScope {  // records CUDA events around a stage when profiling is on
   Ctx* c;
   int stage;
+  cudaStream_t st;
   cudaEvent_t a = nullptr, b = nullptr;
   int64_t l0;
-  StageScope(Ctx* c_, int s);
+  StageScope(Ctx* c_, int s, cudaStream_t stream = nullptr);
   ~StageScope();
 };
 
@@ -225,8 +247,17 @@ int voxel_run(Ctx* c, const float4* d_in, int n, float leaf, float4* d_out, int*
 // ---- implemented in mapindex.cu
 int map_alloc(Ctx* c, MapIndex& m, int cap);
 void map_free(MapIndex& m);
-// (re)build the hash-grid index over m.cat[0..n)
-int map_build(Ctx* c, MapIndex& m, int n);
+// (re)build the grid index over m.cat[0..n) on stream `st`.  fixed_grid = false: bounding box first (one host
+// sync; any input).  fixed_grid = true: the map's frozen origin / key width is reused, nothing is read back
+// (tracker maps whose points are known to lie inside the frozen grid).
+int map_build(Ctx* c, MapIndex& m, int n, cudaStream_t st, bool fixed_grid);
+// freeze the grid of a tracker map around a sensor position (1024 x 1024 x 256 m); false if p is unusable
+bool map_freeze_grid(MapIndex& m, const double p[3]);
+// true when a sweep taken at sensor position p (range-gated to `reach` metres) lies inside the frozen grid
+bool map_grid_covers(const MapIndex& m, const double p[3], double reach);
+// make the main stream wait for the pending local-map work (no-op when nothing is pending)
+int wait_map(Ctx* c);
+int wait_feat(Ctx* c);
 
 // ---- implemented in match.cu
 int solve_alloc(Ctx* c);

@@ -762,19 +762,22 @@ struct QueryBufs {
   float4* pw;                // [upper] fp32 world point by feature index
 };
 
-// clamp-and-pack the cell of a query for sorting only (locality heuristic: any key is correct)
-__device__ __forceinline__ unsigned long long query_cell_key(const MapDev& md, float x, float y, float z) {
+// 29-bit cell key of a query for sorting only (locality heuristic: any key is correct): 1 m cell relative to
+// a 256 x 256 x 128 m box around the sensor (8 + 8 + 7 bits, clamped) and the 0.25 m sub-cell (6 bits)
+struct QueryOrigin {
+  int x, y, z;
+};
+__device__ __forceinline__ unsigned query_cell_key(QueryOrigin o, float x, float y, float z) {
   const float lim = 1.0e5f;
   x = fminf(fmaxf(x, -lim), lim);
   y = fminf(fmaxf(y, -lim), lim);
   z = fminf(fmaxf(z, -lim), lim);
-  int ax = (int)floorf(x * 16.0f), ay = (int)floorf(y * 16.0f), az = (int)floorf(z * 16.0f);
-  int cx = min(max((ax >> 4) - md.min_c[0], 0), max(md.dim[0] - 1, 0));
-  int cy = min(max((ay >> 4) - md.min_c[1], 0), max(md.dim[1] - 1, 0));
-  int cz = min(max((az >> 4) - md.min_c[2], 0), max(md.dim[2] - 1, 0));
-  unsigned f1 = (((az >> 2) & 3) << 4) | (((ay >> 2) & 3) << 2) | ((ax >> 2) & 3);
-  unsigned f2 = ((az & 3) << 4) | ((ay & 3) << 2) | (ax & 3);
-  return (pack_cell(md, cx, cy, cz) << 12) | ((unsigned long long)f1 << 6) | (unsigned long long)f2;
+  int ax = (int)floorf(x * 4.0f), ay = (int)floorf(y * 4.0f), az = (int)floorf(z * 4.0f);
+  unsigned cx = (unsigned)min(max((ax >> 2) - o.x, 0), 255);
+  unsigned cy = (unsigned)min(max((ay >> 2) - o.y, 0), 255);
+  unsigned cz = (unsigned)min(max((az >> 2) - o.z, 0), 127);
+  unsigned f1 = ((az & 3) << 4) | ((ay & 3) << 2) | (ax & 3);
+  return (((((cz << 8) | cy) << 8) | cx) << 6) | f1;
 }
 
 // number of map points in the L2 cell that holds (x,y,z): a cheap density probe (scheduling heuristic only)
@@ -804,7 +807,7 @@ __device__ __forceinline__ int own_cell_population(const MapView& mv, float x, f
 // k_knn warps start with them and the cheap dense-region queries fill the tail (longest job first).
 __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, const int* __restrict__ counts,
                                                SolveState* __restrict__ st, MapPair maps, int has_edge_map,
-                                               int has_surf_map, int kind_bit, int key_shift,
+                                               int has_surf_map, QueryOrigin qorg,
                                                int upper, int solver, int with_keys, QueryBufs qb) {
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -814,7 +817,7 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
   }
   const bool in_range = i < upper;
   const int n_e = counts[0], n_s = counts[1];
-  unsigned long long key = 4ull << kind_bit;  // padding sorts behind every live query
+  unsigned key = 0x80000000u;  // padding sorts behind every live query
   bool heavy = false;
   if (in_range && i < n_e + n_s) {
     quat q;
@@ -832,10 +835,10 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
       const MapView& mv = is_edge ? maps.edge : maps.surf;
       int pop = own_cell_population(mv, w.x, w.y, w.z);
       heavy = pop < 5;
-      key = query_cell_key(*mv.dev, w.x, w.y, w.z) | (is_edge ? 0ull : (1ull << kind_bit)) |
-            (heavy ? 0ull : (2ull << kind_bit));
+      // [31] padding  [30] light (own cell populated)  [29] surf  [28..0] cell
+      key = query_cell_key(qorg, w.x, w.y, w.z) | (is_edge ? 0u : (1u << 29)) | (heavy ? 0u : (1u << 30));
     } else {
-      key = 0ull;
+      key = 0u;
       heavy = with_keys != 0;
     }
   }
@@ -844,8 +847,7 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
     if ((threadIdx.x & 31) == 0 && hb) atomicAdd(&st->n_heavy, __popc(hb));
   }
   if (with_keys && in_range) {
-    // ordering heuristic only: when the packed cell key is wider than 32 bits its low (finest) bits are dropped
-    qb.keys[i] = (unsigned)(key >> key_shift);
+    qb.keys[i] = key;
     qb.vals[i] = i;
   }
 }
@@ -854,7 +856,10 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
 // chunks of 32 consecutive sorted queries from a device-side counter: queries of sparse regions cost several
 // times more than queries of dense ones and sort next to each other, so a static block->query map leaves a
 // long tail of heavy blocks.
-__global__ void __launch_bounds__(128) k_knn(const int* __restrict__ perm, const float4* __restrict__ pw,
+#ifndef KNN_MINBLOCKS
+#define KNN_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, KNN_MINBLOCKS) k_knn(const int* __restrict__ perm, const float4* __restrict__ pw,
                                              const int* __restrict__ counts, SolveState* __restrict__ st,
                                              MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
                                              int seeded, int* __restrict__ nbr) {
@@ -1191,12 +1196,13 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
   qb.keys = (unsigned*)c->q_keys;
   qb.vals = c->q_vals;
   qb.pw = c->d_pw;
-  // bits of a query sort key: 12 (L1, L2) + the wider of the two maps' packed L0 coordinates, + kind bit
-  int kb = 12;
-  for (int k = 0; k < 2; ++k) {
-    const MapDev& md = c->map[k].host;
-    int b = 12 + (c->map[k].ready ? md.bits[0] + md.bits[1] + md.bits[2] : 0);
-    if (b > kb) kb = b;
+  // query sort keys are relative to a box around the sensor position of the prior pose
+  QueryOrigin qorg;
+  {
+    auto cell = [](double v) { return (int)floor(v < -1.0e5 ? -1.0e5 : (v > 1.0e5 ? 1.0e5 : v)); };
+    qorg.x = cell(pose[4]) - 128;
+    qorg.y = cell(pose[5]) - 128;
+    qorg.z = cell(pose[6]) - 64;
   }
   for (int i = 0; i < 7; ++i) c->h_pose[i] = pose[i];
   LM_CUDA(cudaMemcpyAsync(c->d_state->cand, c->h_pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1209,20 +1215,22 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
       // outer iterations (the pose moves by millimetres between them), which also keeps the sorted position
       // of a feature stable so that k_knn can seed its search with the previous iteration's neighbours
       StageScope scope(c, LMSF_STAGE_ASSOC);
-      const int key_shift = (kb + 3 > 32) ? (kb + 3 - 32) : 0;
-      LM_LAUNCH(c, k_assoc, div_up(up, 256), 256, 0, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, kb, key_shift,
-                up, solver, it == 0 ? 1 : 0, qb);
+      LM_LAUNCH(c, k_assoc, div_up(up, 256), 256, 0, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, qorg, up,
+                solver, it == 0 ? 1 : 0, qb);
       if (it == 0) {
         size_t tmp = c->cub_tmp_bytes;
         LM_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, (unsigned*)c->q_keys, (unsigned*)c->q_keys_alt,
-                                                c->q_vals, c->q_vals_alt, up, 0, kb + 3 - key_shift, c->stream));
+                                                c->q_vals, c->q_vals_alt, up, 0, 32, c->stream));
         c->launches++;
       }
     }
     {
       StageScope scope(c, LMSF_STAGE_MATCH);
       int knn_grid = div_up(up, 128);
-      if (knn_grid > 148 * 7) knn_grid = 148 * 7;  // persistent: every resident warp pulls work
+#ifndef KNN_GRID_PER_SM
+#define KNN_GRID_PER_SM 7
+#endif
+      if (knn_grid > 148 * KNN_GRID_PER_SM) knn_grid = 148 * KNN_GRID_PER_SM;  // persistent: every resident warp pulls work
       LM_LAUNCH(c, k_knn, knn_grid, 128, 0, c->q_vals_alt, c->d_pw, c->ex.counts, c->d_state, maps, he, hs, up,
                 solver, it == 0 ? 0 : 1, c->d_nbr);
       c->match_bytes += alg_bytes;
@@ -1245,6 +1253,16 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
   LM_CUDA(cudaStreamSynchronize(c->stream));
   c->n_edge = c->h_ints[32];
   c->n_surf = c->h_ints[33];
+  for (int k = 0; k < 2; ++k) {  // table occupancy of the last index build; a full table is an error, never silent
+    MapIndex& m = c->map[k];
+    if (!m.ready) continue;
+    m.n_cells_seen = m.h_cnt[2];
+    if (m.h_cnt[3]) {
+      c->last_error = "local-map hash table overflow";
+      m.ready = false;
+      return LMSF_ERR_CAPACITY;
+    }
+  }
   const SolveState& s = *c->h_state;
   for (int i = 0; i < 7; ++i) pose[i] = s.x[i];
   if (stats) {
