@@ -176,6 +176,59 @@ int lmsf_tracker_register_aux(lmsf_ctx* c, const float* xyzi, int n, double pose
 /* = LidarTrackerLocalMap::GetLocalMap (:184-192) */
 int lmsf_get_map(lmsf_ctx* c, int kind, float* xyzi, int cap, int* n);
 
+/* ---- loop-closure descriptors (ScanContext), device resident ------- */
+/* A descriptor is 20 x 60 fp32, row-major (ring, sector); a ring key is 20 fp32.  The database lives in the
+ * context's HBM (keys[n][20], descs[n][1200]); ids are insertion order, as polarcontexts_sc_ /
+ * polarcontext_ringkeys_vec_ (LoopDetection/SceneRecognitionScanContext.hpp:61-72). */
+#define LMSF_SC_RINGS 20
+#define LMSF_SC_SECTORS 60
+#define LMSF_SC_CELLS 1200
+#define LMSF_SC_CANDIDATES 10 /* NUM_CANDIDATES_FROM_TREE_ */
+/* one ring-key candidate of one query, as exchanged between database shards (24 bytes) */
+typedef struct {
+  double sc_dist;  /* DistanceBtnScanContext(query, candidate) */
+  float key_dist;  /* squared ring-key distance (nanoflann L2_Adaptor, fp32) */
+  int32_t id;      /* global keyframe id, -1 = empty slot */
+  int32_t shift;   /* column shift of the best alignment */
+  int32_t pad;
+} lmsf_sc_cand;
+/* = ScanContext::MakeScanContext + MakeRingkeyFromScanContext
+ * (Algorithm/PointClouds/processing/GlobalDescriptor/scanContext/Scancontext.hpp:59-104, :112-126) */
+int lmsf_sc_make(lmsf_ctx* c, const float* xyzi, int n, float* desc1200, float* key20);
+/* = ScanContext::DistanceBtnScanContext (Scancontext.hpp:133-172) for n_pairs explicit pairs
+ * (a = _sc1, the query; b = _sc2, the candidate that is shifted) */
+int lmsf_sc_distance(lmsf_ctx* c, const float* desc_a, const float* desc_b, int n_pairs, double* dist,
+                     int32_t* shift);
+int lmsf_scdb_reserve(lmsf_ctx* c, int capacity);
+int lmsf_scdb_clear(lmsf_ctx* c);
+int lmsf_scdb_size(lmsf_ctx* c, int* n);
+/* append n precomputed descriptors (SceneRecognitionScanContext::Load :165-231) */
+int lmsf_scdb_add(lmsf_ctx* c, const float* descs, const float* keys, int n);
+/* = the descriptor part of AddKeyFramePoints (:61-72): describe the cloud on the device and append it */
+int lmsf_scdb_add_cloud(lmsf_ctx* c, const float* xyzi, int n, int* id_out);
+int lmsf_scdb_get(lmsf_ctx* c, int id, float* desc1200, float* key20);
+/* test hook for the ring-key tree search of descFindSimilar (:267-279): exact 10-NN of every query among
+ * keys[0, limit), ascending by (distance, id); unfilled slots hold id -1 and +inf */
+int lmsf_scdb_knn(lmsf_ctx* c, const float* q_keys, int nq, int limit, int32_t* idx10, float* d10);
+/* = descFindSimilar (:260-333) for nq queries against ids [0, limit): loop id (-1 = "Not loop"), the
+ * smallest SC distance among the ten ring-key candidates and its column shift (yaw = shift * 6 deg).
+ * limit = size of polarcontext_ringkeys_to_search_ (see lmsf_sc_tree_limit). */
+int lmsf_scdb_search(lmsf_ctx* c, const float* q_keys, const float* q_descs, int nq, int limit, double thresh,
+                     int32_t* loop_id, double* loop_dist, int32_t* loop_shift);
+/* Sharded search (one database shard per GPU): ring-key top-10 and SC distances of nq DEVICE queries
+ * against local ids [0, limit_local); d_cand receives nq x 10 lmsf_sc_cand with id = local id + id_base.
+ * The caller all-gathers the candidate blocks of all ranks (NCCL) and calls lmsf_scdb_pick_dev on
+ * [n_ranks][nq][10] candidates: global ring-key top-10 by (key_dist, id), then the first strict minimum of
+ * sc_dist in that order, then the threshold — the selection of descFindSimilar :296-323.  Both calls only
+ * enqueue work on the context's stream. */
+int lmsf_scdb_search_shard_dev(lmsf_ctx* c, const float* d_q_keys, const float* d_q_descs, int nq,
+                               int limit_local, int id_base, void* d_cand);
+int lmsf_scdb_pick_dev(lmsf_ctx* c, const void* d_cand_all, int n_ranks, int nq, double thresh,
+                       int32_t* d_loop_id, double* d_loop_dist, int32_t* d_loop_shift);
+/* size of the searched prefix after n_keyframes AddKeyFramePoints calls: the tree is rebuilt over
+ * [0, size - 50) whenever (size - 1) % 10 == 0 and size > 50 (:74-92); 0 = no tree yet */
+int lmsf_sc_tree_limit(int n_keyframes);
+
 /* ---- device memory helpers for callers that keep sweeps resident ---- */
 int lmsf_dev_alloc(lmsf_ctx* c, int64_t bytes, void** d_ptr);
 int lmsf_dev_free(lmsf_ctx* c, void* d_ptr);

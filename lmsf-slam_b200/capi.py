@@ -15,6 +15,11 @@ import os
 import numpy as np
 
 KIND_EDGE, KIND_SURF = 0, 1
+SC_RINGS, SC_SECTORS, SC_CELLS, SC_CANDIDATES = 20, 60, 1200, 10
+SC_CAND_BYTES = 24       # sizeof(lmsf_sc_cand)
+SC_DIST_THRES = 0.2      # SC_DIST_THRES_ (LoopDetection/SceneRecognitionScanContext.hpp)
+SC_EXCLUDE_RECENT = 50   # NUM_EXCLUDE_RECENT_
+SC_TREE_PERIOD = 10      # TREE_MAKING_PERIOD_
 SOLVER_GN, SOLVER_HUBER_LM = 0, 1
 N_STAGES = 7
 STAGE_NAMES = ("extract", "match", "solve", "map", "voxel", "assoc", "fit")
@@ -124,6 +129,9 @@ class Library:
     DEVICE_ONLY = (
         "last_cuda_error", "launch_count", "stream", "tracker_step_dev", "dev_alloc", "dev_free",
         "dev_upload", "profile_enable", "profile_read",
+        # loop-closure descriptor path (scancontext.cu)
+        "sc_make", "sc_distance", "scdb_reserve", "scdb_clear", "scdb_size", "scdb_add", "scdb_add_cloud",
+        "scdb_get", "scdb_knn", "scdb_search", "scdb_search_shard_dev", "scdb_pick_dev", "sc_tree_limit",
     )
 
     def __init__(self, path: str, prefix: str = "lmsf_"):
@@ -152,6 +160,21 @@ class Library:
             f("last_cuda_error").argtypes = [C.c_void_p]
             f("profile_enable").argtypes = [C.c_void_p, C.c_int]
             f("profile_read").argtypes = [C.c_void_p, _f64p, C.POINTER(C.c_int64), _f64p, C.c_int]
+            f("sc_make").argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, _f32p]
+            f("sc_distance").argtypes = [C.c_void_p, _f32p, _f32p, C.c_int, _f64p, _i32p]
+            f("scdb_reserve").argtypes = [C.c_void_p, C.c_int]
+            f("scdb_clear").argtypes = [C.c_void_p]
+            f("scdb_size").argtypes = [C.c_void_p, _intp]
+            f("scdb_add").argtypes = [C.c_void_p, _f32p, _f32p, C.c_int]
+            f("scdb_add_cloud").argtypes = [C.c_void_p, _f32p, C.c_int, _intp]
+            f("scdb_get").argtypes = [C.c_void_p, C.c_int, _f32p, _f32p]
+            f("scdb_knn").argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, _i32p, _f32p]
+            f("scdb_search").argtypes = [C.c_void_p, _f32p, _f32p, C.c_int, C.c_int, C.c_double, _i32p, _f64p, _i32p]
+            f("scdb_search_shard_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                   C.c_void_p]
+            f("scdb_pick_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+            f("sc_tree_limit").argtypes = [C.c_int]
         f("ctx_create").argtypes = [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]
         f("ctx_destroy").argtypes = [C.c_void_p]
         f("extract_features").argtypes = [C.c_void_p, _f32p, C.c_int, _u8p, _f32p, _intp, _f32p, _intp]
@@ -347,6 +370,89 @@ class Context:
 
     def dev_free(self, ptr: int):
         self._chk(self.lib.fn("dev_free")(self._h, C.c_void_p(ptr)))
+
+    # -- loop-closure descriptors (ScanContext), device library only
+    def sc_make(self, xyzi):
+        """MakeScanContext + MakeRingkeyFromScanContext: (20, 60) descriptor and (20,) ring key."""
+        a = _xyzi(xyzi)
+        desc = np.empty((SC_RINGS, SC_SECTORS), np.float32)
+        key = np.empty(SC_RINGS, np.float32)
+        self._chk(self.lib.fn("sc_make")(self._h, _fp(a), a.shape[0], _fp(desc), _fp(key)))
+        return desc, key
+
+    def sc_distance(self, desc_a, desc_b):
+        """DistanceBtnScanContext for explicit pairs: (n,) distances and column shifts."""
+        a = np.ascontiguousarray(desc_a, dtype=np.float32).reshape(-1, SC_CELLS)
+        b = np.ascontiguousarray(desc_b, dtype=np.float32).reshape(-1, SC_CELLS)
+        if a.shape != b.shape:
+            raise ValueError("descriptor batches differ in shape")
+        n = a.shape[0]
+        dist = np.empty(max(n, 1), np.float64)
+        shift = np.empty(max(n, 1), np.int32)
+        self._chk(self.lib.fn("sc_distance")(self._h, _fp(a), _fp(b), n, dist.ctypes.data_as(_f64p),
+                                             shift.ctypes.data_as(_i32p)))
+        return dist[:n], shift[:n]
+
+    def scdb_reserve(self, capacity: int):
+        self._chk(self.lib.fn("scdb_reserve")(self._h, int(capacity)))
+
+    def scdb_clear(self):
+        self._chk(self.lib.fn("scdb_clear")(self._h))
+
+    def scdb_size(self) -> int:
+        n = C.c_int(0)
+        self._chk(self.lib.fn("scdb_size")(self._h, C.byref(n)))
+        return n.value
+
+    def scdb_add(self, descs, keys):
+        d = np.ascontiguousarray(descs, dtype=np.float32).reshape(-1, SC_CELLS)
+        k = np.ascontiguousarray(keys, dtype=np.float32).reshape(-1, SC_RINGS)
+        if d.shape[0] != k.shape[0]:
+            raise ValueError("descriptor / key counts differ")
+        self._chk(self.lib.fn("scdb_add")(self._h, _fp(d), _fp(k), d.shape[0]))
+
+    def scdb_add_cloud(self, xyzi) -> int:
+        a = _xyzi(xyzi)
+        i = C.c_int(-1)
+        self._chk(self.lib.fn("scdb_add_cloud")(self._h, _fp(a), a.shape[0], C.byref(i)))
+        return i.value
+
+    def scdb_get(self, idx: int):
+        desc = np.empty((SC_RINGS, SC_SECTORS), np.float32)
+        key = np.empty(SC_RINGS, np.float32)
+        self._chk(self.lib.fn("scdb_get")(self._h, int(idx), _fp(desc), _fp(key)))
+        return desc, key
+
+    def scdb_knn(self, q_keys, limit: int):
+        q = np.ascontiguousarray(q_keys, dtype=np.float32).reshape(-1, SC_RINGS)
+        nq = q.shape[0]
+        idx = np.empty((max(nq, 1), SC_CANDIDATES), np.int32)
+        d = np.empty((max(nq, 1), SC_CANDIDATES), np.float32)
+        self._chk(self.lib.fn("scdb_knn")(self._h, _fp(q), nq, int(limit), idx.ctypes.data_as(_i32p), _fp(d)))
+        return idx[:nq], d[:nq]
+
+    def scdb_search(self, q_keys, q_descs, limit: int, thresh: float = SC_DIST_THRES):
+        """descFindSimilar for a batch: loop ids (-1 = not a loop), SC distances, column shifts."""
+        k = np.ascontiguousarray(q_keys, dtype=np.float32).reshape(-1, SC_RINGS)
+        d = np.ascontiguousarray(q_descs, dtype=np.float32).reshape(-1, SC_CELLS)
+        nq = k.shape[0]
+        lid = np.empty(max(nq, 1), np.int32)
+        dist = np.empty(max(nq, 1), np.float64)
+        sh = np.empty(max(nq, 1), np.int32)
+        self._chk(self.lib.fn("scdb_search")(self._h, _fp(k), _fp(d), nq, int(limit), float(thresh),
+                                             lid.ctypes.data_as(_i32p), dist.ctypes.data_as(_f64p),
+                                             sh.ctypes.data_as(_i32p)))
+        return lid[:nq], dist[:nq], sh[:nq]
+
+    def scdb_search_shard_dev(self, d_q_keys: int, d_q_descs: int, nq: int, limit_local: int, id_base: int,
+                              d_cand: int):
+        self._chk(self.lib.fn("scdb_search_shard_dev")(self._h, C.c_void_p(d_q_keys), C.c_void_p(d_q_descs), nq,
+                                                       int(limit_local), int(id_base), C.c_void_p(d_cand)))
+
+    def scdb_pick_dev(self, d_cand_all: int, n_ranks: int, nq: int, thresh: float, d_id: int, d_dist: int,
+                      d_shift: int):
+        self._chk(self.lib.fn("scdb_pick_dev")(self._h, C.c_void_p(d_cand_all), n_ranks, nq, float(thresh),
+                                               C.c_void_p(d_id), C.c_void_p(d_dist), C.c_void_p(d_shift)))
 
     def profile_enable(self, on: bool = True):
         self._chk(self.lib.fn("profile_enable")(self._h, int(on)))

@@ -278,6 +278,7 @@ static void destroy(Ctx* c) {
     cudaEventDestroy(sp.b);
   }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
+  scdb_free(c);
   extract_free(c);
   voxel_free(c);
   solve_free(c);

@@ -220,6 +220,9 @@ struct Ctx {
   int64_t prof_launch[LMSF_N_STAGES] = {0, 0, 0, 0, 0, 0, 0};
   double match_bytes = 0;
   int64_t match_launches = 0;  // correspondence passes (k_assoc + sort + k_knn + k_fit)
+
+  // loop-closure descriptor database (scancontext.cu), allocated on first use
+  void* scdb = nullptr;
 };
 
 struct StageScope {  // records CUDA events around a stage when profiling is on
@@ -258,6 +261,9 @@ bool map_grid_covers(const MapIndex& m, const double p[3], double reach);
 // make the main stream wait for the pending local-map work (no-op when nothing is pending)
 int wait_map(Ctx* c);
 int wait_feat(Ctx* c);
+
+// ---- implemented in scancontext.cu
+void scdb_free(Ctx* c);
 
 // ---- implemented in match.cu
 int solve_alloc(Ctx* c);

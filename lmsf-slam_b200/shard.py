@@ -65,3 +65,61 @@ def merge_topk(local_dist: torch.Tensor, local_id: torch.Tensor, k: int):
     o2 = torch.argsort(d1, dim=1, stable=True)
     d2, i2 = torch.gather(d1, 1, o2), torch.gather(i1, 1, o2)
     return d2[:, :k].contiguous(), i2[:, :k].contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Loop-closure descriptor search over a sharded database (BASELINE config 5).
+# Rank r keeps keyframes [lo_r, hi_r) (shard_bounds) in its own HBM under local ids [0, hi_r - lo_r).
+# One exchange step: every rank computes, for every query, its local ring-key top-10 and their ScanContext
+# distances (lmsf_scdb_search_shard_dev), the 24-byte candidate records of all ranks are all-gathered, and
+# every rank runs the same selection (lmsf_scdb_pick_dev): global ring-key top-10 by (key distance, id), then
+# the first strict minimum of the SC distance in that order, then the 0.2 threshold — descFindSimilar
+# (LoopDetection/SceneRecognitionScanContext.hpp:260-333) on shards.
+
+def shard_limit(limit_global: int, lo: int, hi: int) -> int:
+    """How many of this shard's keyframes lie inside the searched prefix [0, limit_global)."""
+    return max(0, min(int(limit_global), hi) - lo)
+
+
+def gather_candidates(local_cand: torch.Tensor) -> torch.Tensor:
+    """all_gather of per-rank candidate blocks: (nq, 10, 24) uint8 -> (world, nq, 10, 24) uint8."""
+    if local_cand.dtype != torch.uint8 or local_cand.dim() != 3 or local_cand.shape[1:] != (10, 24):
+        raise ValueError("expected a (nq, 10, 24) uint8 block of lmsf_sc_cand records")
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    local_cand = local_cand.contiguous()
+    if world == 1:
+        return local_cand.unsqueeze(0)
+    nq = local_cand.shape[0]
+    out = torch.empty((world * nq, 10, 24), dtype=torch.uint8, device=local_cand.device)
+    dist.all_gather_into_tensor(out, local_cand)  # rank-major concatenation along dim 0
+    return out.view(world, nq, 10, 24)
+
+
+def loop_search_sharded(ctx, q_keys: torch.Tensor, q_descs: torch.Tensor, limit_global: int, lo: int, hi: int,
+                        thresh: float = 0.2):
+    """Sharded descFindSimilar for a batch of DEVICE queries (replicated on every rank).
+
+    ctx: the rank's lmsf context whose descriptor database holds keyframes [lo, hi).  q_keys (nq, 20) and
+    q_descs (nq, 1200) are float32 CUDA tensors on the context's device.  Returns CUDA tensors
+    (loop_id int32, loop_dist float64, loop_shift int32), identical on every rank.  All work is enqueued on
+    the context's stream; the caller synchronises.
+    """
+    if not (q_keys.is_cuda and q_descs.is_cuda):
+        raise ValueError("queries must be CUDA tensors (there is no CPU path)")
+    nq = int(q_keys.shape[0])
+    dev = q_keys.device
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    with torch.cuda.stream(stream):
+        cand = torch.empty((nq, 10, 24), dtype=torch.uint8, device=dev)
+        ctx.scdb_search_shard_dev(q_keys.data_ptr(), q_descs.data_ptr(), nq, shard_limit(limit_global, lo, hi), lo,
+                                  cand.data_ptr())
+        allc = gather_candidates(cand)
+        loop_id = torch.empty(nq, dtype=torch.int32, device=dev)
+        loop_dist = torch.empty(nq, dtype=torch.float64, device=dev)
+        loop_shift = torch.empty(nq, dtype=torch.int32, device=dev)
+        ctx.scdb_pick_dev(allc.data_ptr(), world, nq, thresh, loop_id.data_ptr(), loop_dist.data_ptr(),
+                          loop_shift.data_ptr())
+    for t in (q_keys, q_descs, cand, allc, loop_id, loop_dist, loop_shift):
+        t.record_stream(stream)
+    return loop_id, loop_dist, loop_shift

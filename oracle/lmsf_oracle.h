@@ -114,6 +114,14 @@ int lmsf_oracle_se3_exp(const double d[6], double q[4], double t[3]);
 int lmsf_oracle_lm_solve(const double* edge9, int n_e, const double* surf7, int n_s, double huber,
                          int max_iters, double x[7], int* steps, int* accepted, double* cost);
 
+/* ---- loop-closure descriptor path ("next" row f1): ScanContext 20 x 60 (row-major ring x sector, fp32),
+ * ring key (20 fp32), ring-key 10-NN by (distance, id), SC distance + column shift, descFindSimilar ---- */
+int lmsf_oracle_sc_make(const float* xyzi, int n, float* desc1200, float* key20);
+int lmsf_oracle_sc_distance(const float* desc_a, const float* desc_b, double* dist, int* shift);
+int lmsf_oracle_sc_knn(const float* keys, int limit, const float* q_keys, int nq, int32_t* idx10, float* d10);
+int lmsf_oracle_sc_search(const float* keys, const float* descs, int limit, const float* q_keys, const float* q_descs,
+                          int nq, double thresh, int32_t* loop_id, double* loop_dist, int32_t* loop_shift);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "nanoflann.hpp"
+#include "KDTreeVectorOfVectorsAdaptor.h"
 
 namespace {
 struct Cloud {
@@ -39,6 +40,30 @@ extern "C" int ref_nanoflann_knn5(const float* xyzi, int n, const float* q_xyz, 
     for (size_t k = 0; k < 5; ++k) {
       idx5[5 * i + k] = k < found ? (int32_t)idx[k] : -1;
       d2_5[5 * i + k] = k < found ? d2[k] : std::numeric_limits<float>::infinity();
+    }
+  }
+  return 0;
+}
+
+// The reference's own ring-key tree: KDTreeVectorOfVectorsAdaptor<vector<vector<float>>, float> with leaf 10 and
+// the default metric_L2 (SceneRecognitionScanContext.hpp:86-91), searched exactly like descFindSimilar (:272-279).
+extern "C" int ref_nanoflann_ringkey_knn10(const float* keys, int n, const float* q_keys, int nq, int32_t* idx10,
+                                           float* d10) {
+  typedef std::vector<std::vector<float> > KeyMat;
+  typedef KDTreeVectorOfVectorsAdaptor<KeyMat, float> KeyTree;
+  KeyMat mat((size_t)n, std::vector<float>(20));
+  for (int i = 0; i < n; ++i)
+    for (int d = 0; d < 20; ++d) mat[i][d] = keys[20 * (size_t)i + d];
+  KeyTree tree(20, mat, 10);
+  for (int q = 0; q < nq; ++q) {
+    std::vector<size_t> idx(10);
+    std::vector<float> dist(10);
+    nanoflann::KNNResultSet<float> rs(10);
+    rs.init(&idx[0], &dist[0]);
+    tree.index->findNeighbors(rs, q_keys + 20 * (size_t)q, nanoflann::SearchParams(10));
+    for (size_t k = 0; k < 10; ++k) {
+      idx10[10 * q + k] = k < rs.size() ? (int32_t)idx[k] : -1;
+      d10[10 * q + k] = k < rs.size() ? dist[k] : std::numeric_limits<float>::infinity();
     }
   }
   return 0;

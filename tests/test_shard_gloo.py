@@ -87,3 +87,82 @@ def test_single_process_paths():
     i = torch.tensor([[7, 9, 8]])
     md, mi = shard.merge_topk(d, i, 2)
     assert mi.tolist() == [[9, 8]]
+
+
+# ---------------------------------------------------------------- sharded loop-closure search (config 5)
+def _loop_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    entry.load_package()
+    from lmsf_slam_b200 import shard
+    import sc_helpers as sch
+
+    sco = sch.ScOracle()
+    n, nq, limit = 600, 24, 540
+    descs = sch.random_descs(n, seed=71)
+    keys = sch.keys_of_fast(descs)
+    rng = np.random.default_rng(72)
+    ids = rng.integers(0, n, size=nq)
+    qd = np.stack([np.roll(descs[i], int(s), axis=1) for i, s in zip(ids, rng.integers(0, 60, size=nq))])
+    qk = sch.keys_of_fast(qd)
+    lo, hi = shard.shard_bounds(n, world, rank)
+    lim_local = shard.shard_limit(limit, lo, hi)
+    # what lmsf_scdb_search_shard_dev produces on this rank, computed here by the CPU oracle
+    cand = np.zeros((nq, 10), sch.CAND_DTYPE)
+    cand["id"] = -1
+    cand["sc_dist"] = 10000000.0
+    cand["key_dist"] = np.inf
+    if lim_local > 0:
+        idx, kd = sco.knn(keys[lo:hi], lim_local, qk)
+        for qi in range(nq):
+            for j in range(10):
+                if idx[qi, j] < 0:
+                    continue
+                d, s = sco.distance(qd[qi], descs[lo + idx[qi, j]])
+                cand[qi, j] = (d[0], kd[qi, j], lo + idx[qi, j], s[0], 0)
+    block = torch.from_numpy(cand.view(np.uint8).reshape(nq, 10, 24).copy())
+    allc = shard.gather_candidates(block)
+    rec = allc.numpy().view(sch.CAND_DTYPE).reshape(world, nq, 10)
+    lid, dd, sh = sch.py_pick(rec)
+    q.put((rank, (lo, hi, lim_local, lid, dd, sh)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_loop_search_equals_unsharded_oracle():
+    import sc_helpers as sch
+
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_loop_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][:3] == (0, 300, 300) and res[1][:3] == (300, 600, 240)
+    sco = sch.ScOracle()
+    n, nq, limit = 600, 24, 540
+    descs = sch.random_descs(n, seed=71)
+    keys = sch.keys_of_fast(descs)
+    rng = np.random.default_rng(72)
+    ids = rng.integers(0, n, size=nq)
+    qd = np.stack([np.roll(descs[i], int(s), axis=1) for i, s in zip(ids, rng.integers(0, 60, size=nq))])
+    qk = sch.keys_of_fast(qd)
+    l_o, d_o, s_o = sco.search(keys, descs, limit, qk, qd)
+    for r in (0, 1):
+        _, _, _, lid, dd, sh = res[r]
+        assert np.array_equal(lid, l_o) and np.array_equal(dd, d_o) and np.array_equal(sh, s_o)
+    assert (l_o >= 0).sum() >= 15
+
+
+def test_shard_limit():
+    entry.load_package()
+    from lmsf_slam_b200 import shard
+    assert shard.shard_limit(540, 0, 300) == 300
+    assert shard.shard_limit(540, 300, 600) == 240
+    assert shard.shard_limit(100, 300, 600) == 0
