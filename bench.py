@@ -127,7 +127,7 @@ def run_ours(args):
     use_dist = world > 1
     W, K = args.warmup, args.steps
     # independent sequences are dealt round-robin to ranks (shard.assign): with one sequence per GPU rank r tracks sequence r
-    sweeps = make_sequence(W + K + 1, seq=rank)     # before any CUDA call (fork-safe)
+    sweeps = make_sequence(W + K + 2, seq=rank)     # before any CUDA call (fork-safe); +1: the last step prefetches
     torch.cuda.set_device(local)
     if use_dist:
         import torch.distributed as dist
@@ -188,14 +188,25 @@ def run_ours(args):
     d_ptrs = [ctx.dev_upload_new(s) for s in sweeps]
     # dress rehearsal (discarded): the very first timed loop of a process pays one-off lazy initialisation
     # (CUDA event pools, NVML) of ~50-90 ms inside its first iteration
-    run_sequence(lambda k, t: ctx.tracker_step_dev(d_ptrs[k], n_pts[k], t)[2], False, K=2)
-    dev_ms, wall_ms, per, launches, _, stats, fl1 = run_sequence(
-        lambda k, t: ctx.tracker_step_dev(d_ptrs[k], n_pts[k], t)[2], False)
-    # ---- end-to-end pass: host buffers through lmsf_tracker_step (H2D of the sweep + D2H of the pose inside)
-    e_dev_ms, e_wall_ms, e_per, _, _, _, fl2 = run_sequence(lambda k, t: ctx.tracker_step(sweeps[k], t)[2], False)
-    # ---- instrumented pass (not used for value): per-stage CUDA-event times on the context stream
-    p_dev_ms, _, _, _, prof, _, fl3 = run_sequence(
-        lambda k, t: ctx.tracker_step_dev(d_ptrs[k], n_pts[k], t)[2], True)
+    # Every step first hands the NEXT sweep to the front end (lmsf_tracker_prefetch*: upload + feature extraction
+    # on the context's front-end stream), then registers the current one — the reference's own two-thread pipeline
+    # (sensor thread: Process; estimate_thread_: Solve).  Each timed step therefore still contains exactly one
+    # upload (e2e pass), one feature extraction and one registration.
+    def step_dev(k, t):
+        ctx.tracker_prefetch_dev(d_ptrs[k + 1], n_pts[k + 1])
+        return ctx.tracker_step_dev(d_ptrs[k], n_pts[k], t)[2]
+
+    def step_host(k, t):
+        ctx.tracker_prefetch(sweeps[k + 1])
+        return ctx.tracker_step(sweeps[k], t)[2]
+
+    run_sequence(step_dev, False, K=2)
+    dev_ms, wall_ms, per, launches, _, stats, fl1 = run_sequence(step_dev, False)
+    # ---- end-to-end pass: host buffers through lmsf_tracker_prefetch + lmsf_tracker_step (H2D of a sweep + D2H of
+    # the pose inside every step)
+    e_dev_ms, e_wall_ms, e_per, _, _, _, fl2 = run_sequence(step_host, False)
+    # ---- instrumented pass (not used for value): per-stage CUDA-event times on the context's streams
+    p_dev_ms, _, _, _, prof, _, fl3 = run_sequence(step_dev, True)
     sampler.stop_flag.set()
     sampler.join()
 
@@ -225,6 +236,7 @@ def run_ours(args):
                        "points_per_sweep": int(np.mean(n_pts)), "sequences": n_gpus,
                        "l2": "256 MiB memset between timed steps (L2 flush), inside the timed region",
                        "timing": "CUDA events on the context stream around the K steps, max over ranks",
+                       "pipeline": "front end (extraction of sweep k+1) overlaps the registration of sweep k",
                        "p50_ms_per_scan": float(np.median(per)), "p90_ms_per_scan": float(np.percentile(per, 90)),
                        "max_ms_per_scan": float(np.max(per)), "wall_ms_per_step": wall_ms / K,
                        "flush_host_ms_per_step": [fl1, fl2, fl3], "instrumented_pass_ms_per_step": p_dev_ms / K,
@@ -236,7 +248,8 @@ def run_ours(args):
             "e2e": {"value": n_gpus * K / (e2e_ms_max * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(np.mean(n_pts)) * 16, "d2h_bytes_per_step": STATE_D2H_BYTES,
                     "p50_ms_per_scan": float(np.median(e_per)),
-                    "api": "lmsf_tracker_step (host sweep in, pose out), wall clock around K steps, max over ranks"},
+                    "api": "lmsf_tracker_prefetch(next host sweep) + lmsf_tracker_step(host sweep in, pose out), "
+                           "wall clock around K steps, max over ranks"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_knn (exact 5-NN of every scan feature over the local-map grid)",

@@ -162,6 +162,15 @@ int lmsf_tracker_step(lmsf_ctx* c, const float* xyzi, int n, double stamp, doubl
  * pointer on the context's device). */
 int lmsf_tracker_step_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp, double delta[7],
                           double pose_out[7], lmsf_track_stats* st);
+/* Front-end / back-end pipelining.  The reference runs LOAMFeatureProcessorBase::Process on the sensor
+ * thread and LidarTrackerLocalMap::Solve on estimate_thread_, connected by a queue
+ * (System/ML_System.hpp:137-141, :210-227): the features of sweep k+1 are extracted while sweep k is
+ * registered.  lmsf_tracker_prefetch(_dev) enqueues the upload and feature extraction of the NEXT sweep on
+ * the context's front-end stream and returns at once; the following lmsf_tracker_step(_dev) call with the
+ * same pointer and count consumes those features instead of extracting again (any other sweep: the
+ * prefetched one is dropped).  The caller must not modify a prefetched host buffer before that step. */
+int lmsf_tracker_prefetch(lmsf_ctx* c, const float* xyzi, int n);
+int lmsf_tracker_prefetch_dev(lmsf_ctx* c, const float* d_xyzi, int n);
 /* Same, fed with features instead of a raw sweep — the exact argument of
  * LidarTrackerLocalMap::Solve. */
 int lmsf_tracker_step_features(lmsf_ctx* c, const float* edge_xyzi, int n_e, const float* surf_xyzi,

@@ -127,7 +127,8 @@ class Library:
     )
     # symbols only the CUDA library exports
     DEVICE_ONLY = (
-        "last_cuda_error", "launch_count", "stream", "tracker_step_dev", "dev_alloc", "dev_free",
+        "last_cuda_error", "launch_count", "stream", "tracker_step_dev", "tracker_prefetch", "tracker_prefetch_dev",
+        "dev_alloc", "dev_free",
         "dev_upload", "profile_enable", "profile_read",
         # loop-closure descriptor path (scancontext.cu)
         "sc_make", "sc_distance", "scdb_reserve", "scdb_clear", "scdb_size", "scdb_add", "scdb_add_cloud",
@@ -152,6 +153,8 @@ class Library:
             f("stream").restype = C.c_void_p
             f("tracker_step_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, _f64p, _f64p,
                                               C.POINTER(TrackStats)]
+            f("tracker_prefetch").argtypes = [C.c_void_p, _f32p, C.c_int]
+            f("tracker_prefetch_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int]
             f("dev_alloc").argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
             f("dev_free").argtypes = [C.c_void_p, C.c_void_p]
             f("dev_upload").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
@@ -325,6 +328,18 @@ class Context:
         self._chk(self.lib.fn("tracker_step_dev")(self._h, C.c_void_p(d_ptr), n, float(stamp),
                                                   d.ctypes.data_as(_f64p), p.ctypes.data_as(_f64p), C.byref(st)))
         return p, d, st.as_dict()
+
+    def tracker_prefetch(self, xyzi):
+        """Enqueue upload + feature extraction of the NEXT sweep; pass the same array to the next tracker_step.
+        The array must already be a C-contiguous (n, 4) float32 array (it is matched by address)."""
+        a = xyzi
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous and a.ndim == 2
+                and a.shape[1] == 4):
+            raise ValueError("tracker_prefetch needs a C-contiguous (n, 4) float32 array")
+        self._chk(self.lib.fn("tracker_prefetch")(self._h, _fp(a), a.shape[0]))
+
+    def tracker_prefetch_dev(self, d_ptr: int, n: int):
+        self._chk(self.lib.fn("tracker_prefetch_dev")(self._h, C.c_void_p(d_ptr), n))
 
     def tracker_step_features(self, edge, surf, stamp: float, delta=IDENTITY_POSE):
         e, s = _xyzi(edge), _xyzi(surf)

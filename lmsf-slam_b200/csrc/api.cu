@@ -4,6 +4,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <chrono>
 #include <new>
 
 #include "common.cuh"
@@ -145,9 +146,10 @@ static int update_map(Ctx* c, const rigid& T, int type) {
       fixed_ok[kind] = ok;
     }
   }
-  if (async) {
-    LM_CUDA(cudaEventRecord(c->ev_feat_free, st));
-    c->feat_pending = true;
+  if (async) {  // the map stream has read this slot's features: the front end may refill it
+    Ctx::FeatSlot& sl = c->slot[c->slot_cur];
+    LM_CUDA(cudaEventRecord(sl.freed, st));
+    sl.freed_pending = true;
   }
   for (int kind = 0; kind < 2; ++kind) {
     int nk = kind ? c->n_surf : c->n_edge;
@@ -223,7 +225,10 @@ static int tracker_core(Ctx* c, int upper, double stamp, double delta[7], double
     double p[7];
     rigid_to_pose(c->curr, p);  // Quaterniond(T.rotation())
     LM_TRY(wait_map(c));  // the previous keyframe's index rebuild (map stream) must be complete
+    const auto h0 = std::chrono::steady_clock::now();
     LM_TRY(run_solver(c, c->prm.solver, p, &s.reg, upper));  // leaves n_edge / n_surf on the host
+    c->host_us[0] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count();
+    c->host_n[0] += 1;
     c->curr = rigid_from_pose(p);  // T.linear() = q.toRotationMatrix()
     c->motion = rigid_mul(rigid_inv(c->prev), c->curr);
     rigid_to_pose(c->motion, delta);
@@ -233,7 +238,10 @@ static int tracker_core(Ctx* c, int upper, double stamp, double delta[7], double
     if (ut) {
       c->last_kf = c->curr;
       c->last_kf_time = stamp;
+      const auto h0 = std::chrono::steady_clock::now();
       LM_TRY(update_map(c, c->curr, ut));
+      c->host_us[1] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count();
+      c->host_n[1] += 1;
     }
   }
   s.n_edge = c->n_edge;
@@ -245,9 +253,26 @@ static int tracker_core(Ctx* c, int upper, double stamp, double delta[7], double
   return LMSF_OK;
 }
 
+// make slot `si` the one the main stream works on (d_feat / ex.counts alias it)
+static void alias_slot(Ctx* c, int si) {
+  c->slot_cur = si;
+  c->d_feat = c->slot[si].feat;
+  c->ex.counts = c->slot[si].counts;
+}
+
+// a slot that holds no unconsumed prefetch (the current one preferred); when both do, the older prefetch is dropped
+static int writable_slot(Ctx* c) {
+  if (!c->slot[c->slot_cur].filled) return c->slot_cur;
+  if (!c->slot[c->slot_cur ^ 1].filled) return c->slot_cur ^ 1;
+  int si = c->slot[0].seq < c->slot[1].seq ? 0 : 1;
+  c->slot[si].filled = false;
+  return si;
+}
+
 static int upload_features(Ctx* c, const float* edge, int n_e, const float* surf, int n_s) {
   if (n_e < 0 || n_s < 0 || (n_e > 0 && !edge) || (n_s > 0 && !surf)) return LMSF_ERR_INVALID;
   if (n_e + n_s > c->prm.max_points) return LMSF_ERR_CAPACITY;
+  alias_slot(c, writable_slot(c));
   LM_TRY(wait_feat(c));
   c->feat_from_extract = false;  // caller-supplied features: arbitrary coordinates, the map update stays synchronous
   if (n_e) memcpy(c->h_pts, edge, (size_t)n_e * sizeof(float4));
@@ -258,19 +283,96 @@ static int upload_features(Ctx* c, const float* edge, int n_e, const float* surf
   return set_counts(c, n_e, n_s);
 }
 
+// host sweep -> d_sweep on the front-end stream, through one of two pinned staging buffers
 static int upload_sweep(Ctx* c, const float* xyzi, int n) {
   if (n < 0 || (n > 0 && !xyzi)) return LMSF_ERR_INVALID;
   if (n > c->prm.max_points) return LMSF_ERR_CAPACITY;
   if (n) {
-    memcpy(c->h_pts, xyzi, (size_t)n * sizeof(float4));
-    LM_CUDA(cudaMemcpyAsync(c->d_sweep, c->h_pts, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    const int b = c->stage_next;
+    c->stage_next ^= 1;
+    LM_CUDA(cudaEventSynchronize(c->ev_stage[b]));  // the copy that last read this staging buffer is done
+    memcpy(c->h_stage[b], xyzi, (size_t)n * sizeof(float4));
+    LM_CUDA(cudaMemcpyAsync(c->d_sweep, c->h_stage[b], (size_t)n * sizeof(float4), cudaMemcpyHostToDevice,
+                            c->stream_fe));
+    LM_CUDA(cudaEventRecord(c->ev_stage[b], c->stream_fe));
   }
   return LMSF_OK;
+}
+
+// Feature extraction of one sweep into slot `si` on the front-end stream (a1).  host != 0: xyzi is a host buffer,
+// staged and copied first; otherwise it is a device pointer.  Returns with the work enqueued.
+static int extract_into_slot(Ctx* c, int si, const float* xyzi, int n, bool host) {
+  if (n < 0 || (n > 0 && !xyzi)) return LMSF_ERR_INVALID;
+  if (n > c->prm.max_points) return LMSF_ERR_CAPACITY;
+  Ctx::FeatSlot& sl = c->slot[si];
+  if (sl.freed_pending) {  // a local-map update may still be reading this slot
+    LM_CUDA(cudaStreamWaitEvent(c->stream_fe, sl.freed, 0));
+    sl.freed_pending = false;
+  }
+  const float4* d_in = (const float4*)xyzi;
+  if (host) {
+    LM_TRY(upload_sweep(c, xyzi, n));
+    d_in = c->d_sweep;
+  }
+  LM_TRY(extract_run(c, d_in, n, c->stream_fe, sl.feat, sl.counts));
+  LM_CUDA(cudaEventRecord(sl.ready, c->stream_fe));
+  return LMSF_OK;
+}
+
+// adopt a slot whose extraction has been enqueued on the front-end stream
+static int adopt_slot(Ctx* c, int si) {
+  Ctx::FeatSlot& sl = c->slot[si];
+  alias_slot(c, si);
+  sl.filled = false;
+  sl.src = nullptr;
+  LM_CUDA(cudaStreamWaitEvent(c->stream, sl.ready, 0));
+  c->feat_from_extract = true;
+  return LMSF_OK;
+}
+
+// extraction for the synchronous entry points: main stream ordered behind it
+static int extract_current(Ctx* c, const float* xyzi, int n, bool host) {
+  const int si = writable_slot(c);
+  LM_TRY(extract_into_slot(c, si, xyzi, n, host));
+  return adopt_slot(c, si);
+}
+
+// lmsf_tracker_prefetch(_dev): extraction of a coming sweep into a slot that is not waiting to be consumed.
+// Called as prefetch(k+1); step(k): slot A holds k (prefetched earlier), slot B = the finished sweep k-1 -> k+1 goes to B.
+static int prefetch(Ctx* c, const float* xyzi, int n, bool host) {
+  int si = c->slot_cur ^ 1;
+  if (c->slot[si].filled) si = c->slot_cur;
+  if (c->slot[si].filled) return LMSF_ERR_STATE;  // two sweeps already waiting for their tracker step
+  LM_TRY(extract_into_slot(c, si, xyzi, n, host));
+  c->slot[si].filled = true;
+  c->slot[si].src = xyzi;
+  c->slot[si].n = n;
+  c->slot[si].seq = ++c->prefetch_seq;
+  c->slot[si].age = 0;
+  return LMSF_OK;
+}
+
+// tracker entry: consume the prefetched sweep when it is the one being stepped, else extract now
+static int take_sweep(Ctx* c, const float* xyzi, int n, bool host) {
+  int hit = -1;
+  for (int si = 0; si < 2; ++si) {
+    const Ctx::FeatSlot& sl = c->slot[si];
+    if (sl.filled && sl.src == (const void*)xyzi && sl.n == n && (hit < 0 || sl.seq < c->slot[hit].seq)) hit = si;
+  }
+  // a prefetched sweep is expected to be stepped within the next two tracker steps; older ones are dropped so that a
+  // recycled caller buffer can never match a stale slot
+  for (int si = 0; si < 2; ++si) {
+    Ctx::FeatSlot& sl = c->slot[si];
+    if (sl.filled && si != hit && ++sl.age >= 2) sl.filled = false;
+  }
+  if (hit >= 0) return adopt_slot(c, hit);
+  return extract_current(c, xyzi, n, host);
 }
 
 static void destroy(Ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->stream_fe) cudaStreamSynchronize(c->stream_fe);
   if (c->stream_map) cudaStreamSynchronize(c->stream_map);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& sp : c->spans) {
@@ -285,15 +387,22 @@ static void destroy(Ctx* c) {
   map_free(c->map[0]);
   map_free(c->map[1]);
   cudaFree(c->d_sweep);
-  cudaFree(c->d_feat);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(c->slot[i].feat);
+    cudaFree(c->slot[i].counts);
+    if (c->slot[i].ready) cudaEventDestroy(c->slot[i].ready);
+    if (c->slot[i].freed) cudaEventDestroy(c->slot[i].freed);
+    cudaFreeHost(c->h_stage[i]);
+    if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
+  }
   cudaFree(c->d_tmp);
   cudaFreeHost(c->h_pts);
   cudaFreeHost(c->h_pose);
   cudaFreeHost(c->h_ints);
   cudaFreeHost(c->h_state);
-  if (c->ev_feat_free) cudaEventDestroy(c->ev_feat_free);
   if (c->ev_map_done) cudaEventDestroy(c->ev_map_done);
   if (c->stream_map) cudaStreamDestroy(c->stream_map);
+  if (c->stream_fe) cudaStreamDestroy(c->stream_fe);
   if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -301,16 +410,27 @@ static int create(Ctx* c) {
   size_t cap = (size_t)c->prm.max_points;
   LM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   LM_CUDA(cudaStreamCreateWithFlags(&c->stream_map, cudaStreamNonBlocking));
-  LM_CUDA(cudaEventCreateWithFlags(&c->ev_feat_free, cudaEventDisableTiming));
+  LM_CUDA(cudaStreamCreateWithFlags(&c->stream_fe, cudaStreamNonBlocking));
   LM_CUDA(cudaEventCreateWithFlags(&c->ev_map_done, cudaEventDisableTiming));
   LM_CUDA(cudaMalloc(&c->d_sweep, cap * sizeof(float4)));
-  LM_CUDA(cudaMalloc(&c->d_feat, cap * sizeof(float4)));
+  for (int i = 0; i < 2; ++i) {
+    LM_CUDA(cudaMalloc(&c->slot[i].feat, cap * sizeof(float4)));
+    LM_CUDA(cudaMalloc(&c->slot[i].counts, 4 * sizeof(int)));
+    LM_CUDA(cudaMemset(c->slot[i].counts, 0, 4 * sizeof(int)));
+    LM_CUDA(cudaEventCreateWithFlags(&c->slot[i].ready, cudaEventDisableTiming));
+    LM_CUDA(cudaEventCreateWithFlags(&c->slot[i].freed, cudaEventDisableTiming));
+    LM_CUDA(cudaMallocHost(&c->h_stage[i], cap * sizeof(float4)));
+    LM_CUDA(cudaEventCreateWithFlags(&c->ev_stage[i], cudaEventDisableTiming));
+  }
+  c->slot_cur = 0;
+  c->d_feat = c->slot[0].feat;
   LM_CUDA(cudaMalloc(&c->d_tmp, cap * sizeof(float4)));
   LM_CUDA(cudaMallocHost(&c->h_pts, cap * sizeof(float4)));
   LM_CUDA(cudaMallocHost(&c->h_pose, 16 * sizeof(double)));
   LM_CUDA(cudaMallocHost(&c->h_ints, 64 * sizeof(int)));
   LM_CUDA(cudaMallocHost(&c->h_state, sizeof(SolveState)));
   LM_TRY(extract_alloc(c));
+  c->ex.counts = c->slot[0].counts;
   LM_TRY(voxel_alloc(c));
   LM_TRY(solve_alloc(c));
   LM_TRY(map_alloc(c, c->map[0], c->prm.max_map_points));
@@ -408,10 +528,7 @@ void* lmsf_stream(lmsf_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int lmsf_extract_features(lmsf_ctx* c, const float* xyzi, int n, uint8_t* label_out, float* edge_xyzi, int* n_edge,
                           float* surf_xyzi, int* n_surf) {
   ENTER(c);
-  LM_TRY(upload_sweep(c, xyzi, n));
-  LM_TRY(wait_feat(c));
-  LM_TRY(extract_run(c, c->d_sweep, n));
-  c->feat_from_extract = true;
+  LM_TRY(extract_current(c, xyzi, n, true));
   LM_TRY(fetch_counts(c));
   const int ne = c->n_edge, ns = c->n_surf;
   if (label_out && n) LM_CUDA(cudaMemcpyAsync(label_out, c->ex.label, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
@@ -560,10 +677,7 @@ int lmsf_tracker_step(lmsf_ctx* c, const float* xyzi, int n, double stamp, doubl
                       lmsf_track_stats* st) {
   ENTER(c);
   if (!delta || !pose_out) return LMSF_ERR_INVALID;
-  LM_TRY(upload_sweep(c, xyzi, n));
-  LM_TRY(wait_feat(c));
-  LM_TRY(extract_run(c, c->d_sweep, n));
-  c->feat_from_extract = true;
+  LM_TRY(take_sweep(c, xyzi, n, true));
   return tracker_core(c, n, stamp, delta, pose_out, st);
 }
 
@@ -571,10 +685,18 @@ int lmsf_tracker_step_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp,
                           lmsf_track_stats* st) {
   ENTER(c);
   if (!delta || !pose_out || n < 0 || (n > 0 && !d_xyzi)) return LMSF_ERR_INVALID;
-  LM_TRY(wait_feat(c));
-  LM_TRY(extract_run(c, (const float4*)d_xyzi, n));
-  c->feat_from_extract = true;
+  LM_TRY(take_sweep(c, d_xyzi, n, false));
   return tracker_core(c, n, stamp, delta, pose_out, st);
+}
+
+int lmsf_tracker_prefetch(lmsf_ctx* c, const float* xyzi, int n) {
+  ENTER(c);
+  return prefetch(c, xyzi, n, true);
+}
+
+int lmsf_tracker_prefetch_dev(lmsf_ctx* c, const float* d_xyzi, int n) {
+  ENTER(c);
+  return prefetch(c, d_xyzi, n, false);
 }
 
 int lmsf_tracker_step_features(lmsf_ctx* c, const float* edge_xyzi, int n_e, const float* surf_xyzi, int n_s,
@@ -587,9 +709,11 @@ int lmsf_tracker_step_features(lmsf_ctx* c, const float* edge_xyzi, int n_e, con
 
 int lmsf_tracker_reset(lmsf_ctx* c) {
   ENTER(c);
+  LM_CUDA(cudaStreamSynchronize(c->stream_fe));
   LM_CUDA(cudaStreamSynchronize(c->stream_map));
   LM_CUDA(cudaStreamSynchronize(c->stream));
-  c->map_pending = c->feat_pending = false;
+  c->map_pending = false;
+  for (int i = 0; i < 2; ++i) c->slot[i].freed_pending = c->slot[i].filled = false;
   c->init = false;
   for (int k = 0; k < 2; ++k) {
     c->map[k].frame_n.clear();
@@ -608,10 +732,7 @@ int lmsf_tracker_reset(lmsf_ctx* c) {
 int lmsf_tracker_register_aux(lmsf_ctx* c, const float* xyzi, int n, double pose[7], lmsf_reg_stats* st) {
   ENTER(c);
   if (!pose) return LMSF_ERR_INVALID;
-  LM_TRY(upload_sweep(c, xyzi, n));
-  LM_TRY(wait_feat(c));
-  LM_TRY(extract_run(c, c->d_sweep, n));
-  c->feat_from_extract = true;
+  LM_TRY(extract_current(c, xyzi, n, true));
   LM_TRY(scan_filter(c));
   rigid T = rigid_from_pose(pose);  // Solve(Isometry3d&): quaternion <-> matrix round trip
   double p[7];
@@ -660,6 +781,21 @@ int lmsf_dev_upload(lmsf_ctx* c, void* d_dst, const void* h_src, int64_t bytes) 
   return LMSF_OK;
 }
 
+/* tuning aid (not part of the documented ABI): host microseconds spent inside 0 = solve (enqueue + wait for the
+ * pose), 1 = local-map update enqueue, 2 = solve enqueue only; counts in n[] */
+int lmsf_debug_host_times(lmsf_ctx* c, double us[4], int64_t n[4], int reset) {
+  if (!c) return LMSF_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) {
+    us[i] = c->host_us[i];
+    n[i] = c->host_n[i];
+    if (reset) {
+      c->host_us[i] = 0;
+      c->host_n[i] = 0;
+    }
+  }
+  return LMSF_OK;
+}
+
 int lmsf_profile_enable(lmsf_ctx* c, int enable) {
   ENTER(c);
   c->prof = enable != 0;
@@ -669,6 +805,7 @@ int lmsf_profile_enable(lmsf_ctx* c, int enable) {
 int lmsf_profile_read(lmsf_ctx* c, double ms[LMSF_N_STAGES], int64_t launches[LMSF_N_STAGES], double* match_alg_bytes,
                       int reset) {
   ENTER(c);
+  LM_CUDA(cudaStreamSynchronize(c->stream_fe));
   LM_CUDA(cudaStreamSynchronize(c->stream_map));
   LM_CUDA(cudaStreamSynchronize(c->stream));
   for (auto& sp : c->spans) {

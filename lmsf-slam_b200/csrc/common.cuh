@@ -95,19 +95,17 @@ struct MapIndex {
   float4* vox = nullptr;     // [cap] voxel-filtered window (only when a map leaf size is set)
   float4* cat = nullptr;     // not owned: win or vox — the map cloud the index is built over
   float4* sorted = nullptr;  // [cap] cell-sorted copy, .w = bit pattern of the original index
-  unsigned long long* keys = nullptr;      // [cap]
-  unsigned long long* keys_alt = nullptr;  // [cap]
-  int* vals = nullptr;                     // [cap]
-  int* vals_alt = nullptr;                 // [cap]
-  int* l2_start = nullptr;                 // [cap+1] start of every occupied L2 cell
+  float4* grouped = nullptr;               // [cap] points grouped by L0 cell (build scratch), .w = original index
+  int2* slot_rank = nullptr;               // [cap] build scratch: hash slot of the point's L0 cell, rank inside it
+  int* cell_list = nullptr;                // [cap] build scratch: hash slots of the occupied L0 cells
+  int* l2_start = nullptr;                 // [2 cap+1] start of every occupied L2 cell; one sentinel per L0 cell
   int* l1_first = nullptr;                 // [cap+1] first L2 cell of every occupied L1 cell
   unsigned long long* l1_mask = nullptr;   // [cap] L2 occupancy of every occupied L1 cell
-  int* d_cnt = nullptr;                    // [4] device counters: n2, n1, inserted L0 cells, insert-failed flag
+  int* d_cnt = nullptr;                    // [8] device counters: L2 entries, L1 cells, L0 cells, insert-failed flag, point cursor
   unsigned* d_box = nullptr;               // [8] bbox scratch of this map (ordered-uint min/max, finite count)
   int* h_cnt = nullptr;                    // [4] pinned mirror of d_cnt (read back with the next pose)
   bool fixed = false;                      // grid origin / key width frozen (tracker maps): builds need no host sync
   int n_cells_seen = 0;                    // occupied L0 cells of the last build that was read back
-  uint8_t* flags = nullptr;                // [cap]
   CellRec* table = nullptr;                // [table_cap]
   unsigned table_cap = 0;
   MapDev* dev = nullptr;     // device copy
@@ -149,7 +147,7 @@ struct Ctx {
 
   // sweep + features
   float4* d_sweep = nullptr;   // [max_points]
-  float4* d_feat = nullptr;    // [max_points] edges first, then surfs
+  float4* d_feat = nullptr;    // alias of slot[slot_cur].feat: edges first, then surfs
   float4* d_tmp = nullptr;     // [max_points] scratch (transformed frame / voxel input)
   ExtractBufs ex;
   MapIndex map[2];
@@ -189,11 +187,31 @@ struct Ctx {
 
   // local-map update pipeline: its own stream, ordered against the main stream with two events
   cudaStream_t stream_map = nullptr;
-  cudaEvent_t ev_feat_free = nullptr;  // map stream has consumed d_feat (transforms done)
   cudaEvent_t ev_map_done = nullptr;   // map stream has finished the index builds
   bool map_pending = false;            // main stream has not yet waited for ev_map_done
-  bool feat_pending = false;           // main stream has not yet waited for ev_feat_free
   bool feat_from_extract = false;      // d_feat came from extract_run: finite and range-gated
+
+  // front end (feature extraction) pipeline: its own stream and two feature slots, so that the extraction of
+  // the next sweep overlaps the registration of the current one.  d_feat / ex.counts alias slot[slot_cur].
+  struct FeatSlot {
+    float4* feat = nullptr;         // [max_points] edges first, then surfs
+    int* counts = nullptr;          // [4] n_edge, n_surf (device)
+    cudaEvent_t ready = nullptr;    // front-end stream: extraction into this slot finished
+    cudaEvent_t freed = nullptr;    // map stream: the local-map update has consumed this slot
+    bool freed_pending = false;     // nobody has waited for `freed` yet
+    bool filled = false;            // holds a prefetched sweep that no step has consumed yet
+    const void* src = nullptr;      // the caller's pointer / count the prefetch was given
+    int n = 0;
+    int64_t seq = 0;                // order of the prefetches
+    int age = 0;                    // tracker steps that passed it over
+  };
+  FeatSlot slot[2];
+  int slot_cur = 0;
+  int64_t prefetch_seq = 0;
+  cudaStream_t stream_fe = nullptr;
+  float4* h_stage[2] = {nullptr, nullptr};  // pinned staging of host sweeps, alternating
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};  // H2D out of h_stage[i] finished
+  int stage_next = 0;
 
   // pinned host staging
   float4* h_pts = nullptr;     // [max_points]
@@ -221,6 +239,9 @@ struct Ctx {
   double match_bytes = 0;
   int64_t match_launches = 0;  // correspondence passes (k_assoc + sort + k_knn + k_fit)
 
+  double host_us[4] = {0, 0, 0, 0};  // tuning aid: host time per phase (lmsf_debug_host_times)
+  int64_t host_n[4] = {0, 0, 0, 0};
+
   // loop-closure descriptor database (scancontext.cu), allocated on first use
   void* scdb = nullptr;
 };
@@ -238,8 +259,9 @@ struct StageScope {  // records CUDA events around a stage when profiling is on
 // ---- implemented in extract.cu
 int extract_alloc(Ctx* c);
 void extract_free(Ctx* c);
-// sweep in c->d_sweep (n points) -> c->d_feat (edges, then surfs), counts in ex.counts, labels in ex.label
-int extract_run(Ctx* c, const float4* d_in, int n);
+// sweep d_in (n points, device) -> feat_out (edges, then surfs), counts_out[0..1], labels in ex.label; all launches
+// on stream `st`.  The scratch in ExtractBufs is shared: extractions must be ordered on one stream (the front end's).
+int extract_run(Ctx* c, const float4* d_in, int n, cudaStream_t st, float4* feat_out, int* counts_out);
 
 // ---- implemented in voxel.cu
 int voxel_alloc(Ctx* c);

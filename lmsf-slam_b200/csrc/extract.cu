@@ -458,8 +458,6 @@ int extract_alloc(Ctx* c) {
   LM_CUDA(cudaMalloc(&x.edge_ids, MAX_RINGS * 6 * 20 * sizeof(int)));
   LM_CUDA(cudaMalloc(&x.sec_cnt, MAX_RINGS * 6 * sizeof(int)));
   LM_CUDA(cudaMalloc(&x.label, cap));
-  LM_CUDA(cudaMalloc(&x.counts, 4 * sizeof(int)));
-  LM_CUDA(cudaMemset(x.counts, 0, 4 * sizeof(int)));
   return LMSF_OK;
 }
 
@@ -481,28 +479,27 @@ void extract_free(Ctx* c) {
   cudaFree(x.edge_ids);
   cudaFree(x.sec_cnt);
   cudaFree(x.label);
-  cudaFree(x.counts);
   x = ExtractBufs();
 }
 
-int extract_run(Ctx* c, const float4* d_in, int n) {
+int extract_run(Ctx* c, const float4* d_in, int n, cudaStream_t st, float4* feat_out, int* counts_out) {
   ExtractBufs& x = c->ex;
   if (n > x.cap) return LMSF_ERR_CAPACITY;
-  StageScope scope(c, LMSF_STAGE_EXTRACT);
+  StageScope scope(c, LMSF_STAGE_EXTRACT, st);
   ExtractParams prm{c->prm.n_scans, c->prm.min_range, c->prm.max_range, c->prm.edge_thresh, c->prm.remove_bad_points};
   const int R = c->prm.n_scans;
   int nblk = div_up(n > 0 ? n : 1, RING_BLOCK);
-  LM_CUDA(cudaMemsetAsync(x.label, 0, n > 0 ? n : 1, c->stream));
-  LM_LAUNCH(c, k_ring_classify, nblk, RING_BLOCK, 0, d_in, n, prm, nblk, x.ring_id, x.blk_cnt);
-  LM_LAUNCH(c, k_ring_scan, 1, 1024, 0, x.blk_cnt, nblk, x.ring_cnt, x.ring_off, x.counts);
-  LM_LAUNCH(c, k_ring_scatter, nblk, RING_BLOCK, 0, d_in, n, nblk, x.ring_id, x.blk_cnt, x.ring_off, x.ring_pts,
-            x.ring_src);
-  LM_LAUNCH(c, k_sector_sort, dim3(6, R), 256, 0, x.ring_pts, x.ring_cnt, x.ring_off, x.curv, x.sorted, x.sort_key,
-            x.sort_val);
-  LM_LAUNCH(c, k_ring_pick, R, 256, 0, x.ring_pts, x.ring_cnt, x.ring_off, x.curv, x.sorted, prm, x.flag, x.btype,
-            x.is_edge, x.edge_ids, x.sec_cnt);
-  LM_LAUNCH(c, k_feat_scatter, dim3(6, R), 256, 0, x.ring_pts, x.ring_src, x.ring_cnt, x.ring_off, x.sorted, x.is_edge,
-            x.edge_ids, x.sec_cnt, R, c->d_feat, x.label, x.counts);
+  LM_CUDA(cudaMemsetAsync(x.label, 0, n > 0 ? n : 1, st));
+  LM_LAUNCH_ON(c, st, k_ring_classify, nblk, RING_BLOCK, 0, d_in, n, prm, nblk, x.ring_id, x.blk_cnt);
+  LM_LAUNCH_ON(c, st, k_ring_scan, 1, 1024, 0, x.blk_cnt, nblk, x.ring_cnt, x.ring_off, counts_out);
+  LM_LAUNCH_ON(c, st, k_ring_scatter, nblk, RING_BLOCK, 0, d_in, n, nblk, x.ring_id, x.blk_cnt, x.ring_off, x.ring_pts,
+               x.ring_src);
+  LM_LAUNCH_ON(c, st, k_sector_sort, dim3(6, R), 256, 0, x.ring_pts, x.ring_cnt, x.ring_off, x.curv, x.sorted,
+               x.sort_key, x.sort_val);
+  LM_LAUNCH_ON(c, st, k_ring_pick, R, 256, 0, x.ring_pts, x.ring_cnt, x.ring_off, x.curv, x.sorted, prm, x.flag,
+               x.btype, x.is_edge, x.edge_ids, x.sec_cnt);
+  LM_LAUNCH_ON(c, st, k_feat_scatter, dim3(6, R), 256, 0, x.ring_pts, x.ring_src, x.ring_cnt, x.ring_off, x.sorted,
+               x.is_edge, x.edge_ids, x.sec_cnt, R, feat_out, x.label, counts_out);
   LM_CUDA(cudaGetLastError());
   return LMSF_OK;
 }

@@ -3,11 +3,9 @@
 // Replaces pcl::KdTreeFLANN::setInputCloud behind FeatureMatch::SetSearchTarget
 // (registration/FeatureMatch/FeatureMatchBase.hpp:40-44), which the tracker triggers
 // on every keyframe through SetInputSource (LidarTracker/LidarTrackerLocalMap.hpp:229).
-// Build = bbox -> 64-bit cell keys (1 m cell | 6-bit 0.25 m sub-cell | 6-bit 0.0625 m sub-cell)
-// -> radix sort -> gather -> L2 cell starts -> L1 cell masks -> one hash-table record per 1 m cell.
-#include <cub/cub.cuh>
-#include <thrust/iterator/counting_iterator.h>
-
+// Build = bbox (only for maps set through lmsf_map_set) -> three-level counting sort: points grouped by 1 m cell
+// through the hash table, every cell's segment sorted by its 6-bit 0.25 m | 6-bit 0.0625 m sub-cell in shared
+// memory, which also yields the L1 masks, the L2 cell starts and the hash-table record of the cell.
 #include "common.cuh"
 #include "knn.cuh"
 
@@ -16,107 +14,239 @@ namespace lm {
 // defined in voxel.cu
 __global__ void k_bbox_init(unsigned* bbox);
 __global__ void k_bbox(const float4* __restrict__ in, int n, unsigned* __restrict__ bbox);
-__global__ void k_head_flags(const unsigned long long* __restrict__ keys, int n, uint8_t* __restrict__ flags);
 
-__global__ void __launch_bounds__(256) k_map_keys(const float4* __restrict__ in, int n,
-                                                  const MapDev* __restrict__ dev,
-                                                  unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+// d_cnt layout: [0] occupied L2 cells (+ one sentinel per L0 cell)  [1] occupied L1 cells  [2] occupied L0 cells
+//               [3] hash-table overflow flag  [4] point cursor (segment allocation)
+enum { CNT_L2 = 0, CNT_L1 = 1, CNT_L0 = 2, CNT_FAIL = 3, CNT_PTS = 4, CNT_WORDS = 8 };
+
+// The index is built by a counting sort in three levels instead of a global radix sort: the order of the L0 cells
+// in memory is irrelevant (they are found through the hash table) and so is the order of the points inside one
+// L2 cell (every search result is ordered by (distance, original index)), so it is enough to (1) count the points
+// of every L0 cell while inserting the cells into the hash table, (2) give every L0 cell a contiguous segment,
+// (3) move the points into their segment, (4) counting-sort every segment by its 12-bit (L1, L2) sub-cell in
+// shared memory, emitting the L1 masks and L2 cell starts on the way.  Six launches, no library calls, no host
+// round trip.
+
+// (1) one thread per map point: find-or-insert its L0 cell, take a rank inside it.  The table arrives filled with
+// 0xff: key = ~0 (empty), end = -1 so that the first atomicAdd returns rank 0 (count = end + 1).
+__global__ void __launch_bounds__(256) k_cell_count(const float4* __restrict__ in, int n,
+                                                    const MapDev* __restrict__ dev, CellRec* __restrict__ table,
+                                                    unsigned tmask, int2* __restrict__ slot_rank,
+                                                    int* __restrict__ d_cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
   const MapDev md = *dev;
-  float4 p = in[i];
-  unsigned long long key = ~0ull;
-  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+  float4 p = (i < n) ? in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  int slot = -1, rank = 0;
+  if (i < n && isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
     // absolute L2 (0.0625 m) cell coordinates; x16 is exact in fp32
     int ax = (int)floorf(p.x * 16.0f), ay = (int)floorf(p.y * 16.0f), az = (int)floorf(p.z * 16.0f);
     unsigned long long ck = pack_cell(md, (ax >> 4) - md.min_c[0], (ay >> 4) - md.min_c[1], (az >> 4) - md.min_c[2]);
-    unsigned f1 = (((az >> 2) & 3) << 4) | (((ay >> 2) & 3) << 2) | ((ax >> 2) & 3);
-    unsigned f2 = ((az & 3) << 4) | ((ay & 3) << 2) | (ax & 3);
-    key = (ck << 12) | ((unsigned long long)f1 << 6) | (unsigned long long)f2;
-  }
-  keys[i] = key;
-  vals[i] = i;
-}
-
-__global__ void __launch_bounds__(256) k_map_gather(const float4* __restrict__ in, const int* __restrict__ vals, int n,
-                                                    float4* __restrict__ sorted) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int src = vals[i];
-  float4 p = in[src];
-  p.w = __int_as_float(src);
-  sorted[i] = p;
-}
-
-// flags over the occupied L2 cells: 1 where a new L1 cell starts (0 beyond the n2 live entries)
-__global__ void __launch_bounds__(256) k_l1_flags(const unsigned long long* __restrict__ keys,
-                                                  const int* __restrict__ l2_start, const int* __restrict__ d_n2,
-                                                  int n, uint8_t* __restrict__ flags) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int n2 = *d_n2;
-  uint8_t f = 0;
-  if (i < n2) f = (i == 0 || (keys[l2_start[i]] >> 6) != (keys[l2_start[i - 1]] >> 6)) ? 1 : 0;
-  flags[i] = f;
-}
-
-// one thread per occupied L1 cell: its L2 occupancy mask; the first L1 cell of an L0 cell also
-// assembles that cell's record and inserts it into the hash table
-__global__ void __launch_bounds__(256) k_cell_insert(const unsigned long long* __restrict__ keys,
-                                                     int* __restrict__ l2_start, int* __restrict__ l1_first,
-                                                     unsigned long long* __restrict__ l1_mask,
-                                                     int* __restrict__ d_cnt, int n_pts,
-                                                     MapDev* __restrict__ dev, CellRec* __restrict__ table,
-                                                     unsigned tmask) {
-  const int n2 = d_cnt[0], n1 = d_cnt[1];
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j == 0) {
-    dev->n_fine = n1;
-  }
-  if (j >= n1) return;
-  const int a = l1_first[j];
-  const int b = (j + 1 < n1) ? l1_first[j + 1] : n2;
-  unsigned long long m2 = 0ull;
-  for (int i = a; i < b; ++i) m2 |= 1ull << (unsigned)(keys[l2_start[i]] & 63ull);
-  l1_mask[j] = m2;
-  const unsigned long long kj = keys[l2_start[a]];
-  const unsigned long long ck = kj >> 12;
-  if (j > 0 && (keys[l2_start[l1_first[j - 1]]] >> 12) == ck) return;
-  unsigned long long m1 = 0ull;
-  int last = j;
-  for (int g = j; g < n1; ++g) {
-    unsigned long long k = keys[l2_start[l1_first[g]]];
-    if ((k >> 12) != ck) break;
-    m1 |= 1ull << (unsigned)((k >> 6) & 63ull);
-    last = g;
-  }
-  int end = (last + 1 < n1) ? l2_start[l1_first[last + 1]] : n_pts;
-  unsigned h = hash_cell(ck) & tmask;
-  unsigned probes = 0;
-  while (true) {
-    unsigned long long prev = atomicCAS(&table[h].key, ~0ull, ck);
-    if (prev == ~0ull) break;
-    h = (h + 1) & tmask;
-    if (++probes > tmask) {  // table full: flagged, reported as LMSF_ERR_CAPACITY with the next read-back
-      atomicExch(&d_cnt[3], 1);
-      return;
+    unsigned h = hash_cell(ck) & tmask;
+    unsigned probes = 0;
+    while (true) {
+      unsigned long long k = table[h].key;
+      if (k == ~0ull) k = atomicCAS(&table[h].key, ~0ull, ck);
+      if (k == ~0ull || k == ck) {
+        slot = (int)h;
+        break;
+      }
+      h = (h + 1) & tmask;
+      if (++probes > tmask) {  // table full: flagged, reported as LMSF_ERR_CAPACITY with the next read-back
+        atomicExch(&d_cnt[CNT_FAIL], 1);
+        break;
+      }
     }
   }
-  atomicAdd(&d_cnt[2], 1);
-  table[h].mask = m1;
-  table[h].start = l2_start[a];
-  table[h].end = end;
-  table[h].fine_base = j;
-  table[h].pad = 0;
+  {
+    // warp-aggregated count: the lanes that hit the same cell take consecutive ranks from one atomic
+    // (all 32 lanes take part in the match; the lanes without a cell form a group that does nothing)
+    const unsigned peers = __match_any_sync(0xffffffffu, slot);
+    const int leader = __ffs(peers) - 1;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (slot >= 0 && lane == leader) base = atomicAdd(&table[slot].end, __popc(peers)) + 1;
+    base = __shfl_sync(0xffffffffu, base, leader);
+    rank = base + __popc(peers & ((1u << lane) - 1u));
+  }
+  if (i < n) slot_rank[i] = make_int2(slot, rank);
 }
 
-// sentinels behind the live entries (written after every reader of the previous values is done)
-__global__ void k_sentinels(int* __restrict__ l2_start, int* __restrict__ l1_first, const int* __restrict__ d_cnt,
-                            int n_pts) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    l2_start[d_cnt[0]] = n_pts;
-    l1_first[d_cnt[1]] = d_cnt[0];
+// (2) one thread per table slot: occupied cells get their segment [start, end) and an entry in the cell list
+__global__ void __launch_bounds__(256) k_cell_alloc(CellRec* __restrict__ table, unsigned slots,
+                                                    int* __restrict__ cell_list, int* __restrict__ d_cnt) {
+  unsigned h = blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = h < slots && table[h].key != ~0ull;
+  int cnt = live ? table[h].end + 1 : 0;
+  // warp-aggregated allocation: one atomic per warp for the points, one for the list
+  int lane = threadIdx.x & 31;
+  int inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
   }
+  unsigned lv = __ballot_sync(0xffffffffu, live);
+  int tot = __shfl_sync(0xffffffffu, inc, 31);
+  int pbase = 0, cbase = 0;
+  if (lane == 0 && lv) {
+    pbase = atomicAdd(&d_cnt[CNT_PTS], tot);
+    cbase = atomicAdd(&d_cnt[CNT_L0], __popc(lv));
+  }
+  pbase = __shfl_sync(0xffffffffu, pbase, 0);
+  cbase = __shfl_sync(0xffffffffu, cbase, 0);
+  if (live) {
+    int start = pbase + inc - cnt;
+    table[h].start = start;
+    table[h].end = start + cnt;
+    cell_list[cbase + __popc(lv & ((1u << lane) - 1u))] = (int)h;
+  }
+}
+
+// (3) one thread per map point: into its cell's segment, .w = original index
+__global__ void __launch_bounds__(256) k_cell_scatter(const float4* __restrict__ in, int n,
+                                                      const int2* __restrict__ slot_rank,
+                                                      const CellRec* __restrict__ table,
+                                                      float4* __restrict__ grouped) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int2 sr = slot_rank[i];
+  if (sr.x < 0) return;
+  float4 p = in[i];
+  p.w = __int_as_float(i);
+  grouped[table[sr.x].start + sr.y] = p;
+}
+
+__device__ __forceinline__ unsigned sub_cell(float4 p) {
+  int ax = (int)floorf(p.x * 16.0f), ay = (int)floorf(p.y * 16.0f), az = (int)floorf(p.z * 16.0f);
+  unsigned f1 = (((az >> 2) & 3) << 4) | (((ay >> 2) & 3) << 2) | ((ax >> 2) & 3);
+  unsigned f2 = ((az & 3) << 4) | ((ay & 3) << 2) | (ax & 3);
+  return (f1 << 6) | f2;
+}
+
+// (4) one block per occupied L0 cell: counting sort of its segment by the 12-bit (L1, L2) sub-cell.  Thread t owns
+// the 16 bins [16 t, 16 t + 16) = a quarter of L1 cell t / 4; the L1 masks, the L2 cell starts (plus one sentinel
+// per L0 cell, so that "start of the next L2 cell" is always the end of the previous one) and the cell record are
+// written from the same histogram.
+constexpr int CS_THREADS = 256;
+__global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict__ cell_list,
+                                                          CellRec* __restrict__ table,
+                                                          const float4* __restrict__ grouped,
+                                                          float4* __restrict__ sorted,
+                                                          unsigned long long* __restrict__ l1_mask,
+                                                          int* __restrict__ l1_first, int* __restrict__ l2_start,
+                                                          int* __restrict__ d_cnt) {
+  __shared__ int hist[4096];
+  __shared__ int warp_pts[8], warp_n2[8], warp_n1[8];
+  __shared__ int s_base1, s_base2;
+  __shared__ unsigned long long s_m1[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n_cells = d_cnt[CNT_L0];  // final: written by k_cell_alloc, the previous launch on this stream
+  for (int ci = blockIdx.x; ci < n_cells; ci += gridDim.x) {
+  const int h = cell_list[ci];
+  const int s = table[h].start, e = table[h].end;
+  __syncthreads();  // the previous cell's scatter is done with the bins
+#pragma unroll
+  for (int k = 0; k < 16; ++k) hist[t + k * CS_THREADS] = 0;
+  __syncthreads();
+  for (int i = s + t; i < e; i += CS_THREADS) atomicAdd(&hist[sub_cell(grouped[i])], 1);
+  __syncthreads();
+  // thread-local: points, occupied L2 cells and their 16-bit mask
+  int cnt[16];
+  int pts = 0, n2 = 0;
+  unsigned m16 = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    cnt[k] = hist[t * 16 + k];
+    pts += cnt[k];
+    if (cnt[k]) {
+      ++n2;
+      m16 |= 1u << k;
+    }
+  }
+  // the four threads of one L1 cell are four consecutive lanes
+  unsigned long long m2 = (unsigned long long)m16 << (16 * (lane & 3));
+  m2 |= __shfl_xor_sync(0xffffffffu, m2, 1);
+  m2 |= __shfl_xor_sync(0xffffffffu, m2, 2);
+  const bool l1_head = (lane & 3) == 0 && m2 != 0ull;
+  int n1 = l1_head ? 1 : 0;
+  // block-wide exclusive scans of (pts, n2, n1)
+  int ip = pts, i2 = n2, i1 = n1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int a = __shfl_up_sync(0xffffffffu, ip, d), b = __shfl_up_sync(0xffffffffu, i2, d),
+        cc = __shfl_up_sync(0xffffffffu, i1, d);
+    if (lane >= d) {
+      ip += a;
+      i2 += b;
+      i1 += cc;
+    }
+  }
+  if (lane == 31) {
+    warp_pts[warp] = ip;
+    warp_n2[warp] = i2;
+    warp_n1[warp] = i1;
+  }
+  __syncthreads();
+  int wp = 0, w2 = 0, w1 = 0, tot2 = 0, tot1 = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (w < warp) {
+      wp += warp_pts[w];
+      w2 += warp_n2[w];
+      w1 += warp_n1[w];
+    }
+    tot2 += warp_n2[w];
+    tot1 += warp_n1[w];
+  }
+  const int ex_p = wp + ip - pts, ex_2 = w2 + i2 - n2, ex_1 = w1 + i1 - n1;
+  if (t == 0) {
+    s_base1 = atomicAdd(&d_cnt[CNT_L1], tot1);
+    s_base2 = atomicAdd(&d_cnt[CNT_L2], tot2 + 1);
+  }
+  __syncthreads();
+  const int base1 = s_base1, base2 = s_base2;
+  // L2 cell starts of this thread's occupied bins; the bins become running cursors for the scatter
+  {
+    int run = s + ex_p, r2 = base2 + ex_2;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      hist[t * 16 + k] = run;
+      if (cnt[k]) l2_start[r2++] = run;
+      run += cnt[k];
+    }
+  }
+  if (l1_head) {
+    l1_mask[base1 + ex_1] = m2;
+    l1_first[base1 + ex_1] = base2 + ex_2;
+  }
+  // occupancy of the 64 L1 cells: L1 cell j = lanes 4j..4j+3 of warp j / 8
+  unsigned heads = __ballot_sync(0xffffffffu, l1_head);
+  unsigned long long m1w = 0ull;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if ((heads >> (4 * j)) & 1u) m1w |= 1ull << (warp * 8 + j);
+  }
+  if (lane == 0) s_m1[warp] = m1w;
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long m1 = 0ull;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m1 |= s_m1[w];
+    l2_start[base2 + tot2] = e;  // sentinel of this L0 cell
+    table[h].mask = m1;
+    table[h].fine_base = base1;
+    table[h].pad = 0;
+  }
+  for (int i = s + t; i < e; i += CS_THREADS) {
+    float4 p = grouped[i];
+    sorted[atomicAdd(&hist[sub_cell(p)], 1)] = p;
+  }
+  }  // cells of this block
+}
+
+__global__ void k_map_finish(MapDev* __restrict__ dev, const int* __restrict__ d_cnt) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) dev->n_fine = d_cnt[CNT_L1];
 }
 
 int map_alloc(Ctx* c, MapIndex& m, int cap) {
@@ -127,20 +257,18 @@ int map_alloc(Ctx* c, MapIndex& m, int cap) {
   LM_CUDA(cudaMalloc(&m.vox, n * sizeof(float4)));
   m.cat = m.win;
   LM_CUDA(cudaMalloc(&m.sorted, n * sizeof(float4)));
-  LM_CUDA(cudaMalloc(&m.keys, n * 8));
-  LM_CUDA(cudaMalloc(&m.keys_alt, n * 8));
-  LM_CUDA(cudaMalloc(&m.vals, n * 4));
-  LM_CUDA(cudaMalloc(&m.vals_alt, n * 4));
-  LM_CUDA(cudaMalloc(&m.l2_start, (n + 1) * 4));
+  LM_CUDA(cudaMalloc(&m.grouped, n * sizeof(float4)));
+  LM_CUDA(cudaMalloc(&m.slot_rank, n * sizeof(int2)));
+  LM_CUDA(cudaMalloc(&m.cell_list, n * 4));
+  LM_CUDA(cudaMalloc(&m.l2_start, (2 * n + 1) * 4));  // one entry per occupied L2 cell + one sentinel per L0 cell
   LM_CUDA(cudaMalloc(&m.l1_first, (n + 1) * 4));
   LM_CUDA(cudaMalloc(&m.l1_mask, n * 8));
-  LM_CUDA(cudaMalloc(&m.d_cnt, 4 * sizeof(int)));
+  LM_CUDA(cudaMalloc(&m.d_cnt, CNT_WORDS * sizeof(int)));
   LM_CUDA(cudaMalloc(&m.d_box, 8 * sizeof(unsigned)));
   LM_CUDA(cudaMallocHost(&m.h_cnt, 64 * sizeof(int)));
   memset(m.h_cnt, 0, 64 * sizeof(int));
   m.fixed = false;
   m.n_cells_seen = 0;
-  LM_CUDA(cudaMalloc(&m.flags, n));
   LM_CUDA(cudaMalloc(&m.dev, sizeof(MapDev)));
   LM_CUDA(cudaMemset(m.dev, 0, sizeof(MapDev)));
   m.table_cap = 1u << 18;
@@ -156,17 +284,15 @@ void map_free(MapIndex& m) {
   cudaFree(m.win_alt);
   cudaFree(m.vox);
   cudaFree(m.sorted);
-  cudaFree(m.keys);
-  cudaFree(m.keys_alt);
-  cudaFree(m.vals);
-  cudaFree(m.vals_alt);
+  cudaFree(m.grouped);
+  cudaFree(m.slot_rank);
+  cudaFree(m.cell_list);
   cudaFree(m.l2_start);
   cudaFree(m.l1_first);
   cudaFree(m.l1_mask);
   cudaFree(m.d_cnt);
   cudaFree(m.d_box);
   cudaFreeHost(m.h_cnt);
-  cudaFree(m.flags);
   cudaFree(m.dev);
   cudaFree(m.table);
   m = MapIndex();
@@ -214,10 +340,12 @@ int wait_map(Ctx* c) {
   return LMSF_OK;
 }
 
+// main stream is about to overwrite the current feature slot: the map stream must have consumed it
 int wait_feat(Ctx* c) {
-  if (c->feat_pending) {
-    LM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_feat_free, 0));
-    c->feat_pending = false;
+  Ctx::FeatSlot& sl = c->slot[c->slot_cur];
+  if (sl.freed_pending) {
+    LM_CUDA(cudaStreamWaitEvent(c->stream, sl.freed, 0));
+    sl.freed_pending = false;
   }
   return LMSF_OK;
 }
@@ -229,7 +357,6 @@ int map_build(Ctx* c, MapIndex& m, int n, cudaStream_t st, bool fixed_grid) {
   m.ready = false;
   if (n == 0) return LMSF_OK;
   const int nb = div_up(n, 256);
-  void* tmp_buf = (st == c->stream) ? c->cub_tmp : c->cub_tmp_map;
   MapDev md;
   int total_bits = 12;
   unsigned slots = 64;
@@ -295,27 +422,14 @@ int map_build(Ctx* c, MapIndex& m, int n, cudaStream_t st, bool fixed_grid) {
   *hd = md;
   LM_CUDA(cudaMemcpyAsync(m.dev, hd, sizeof(MapDev), cudaMemcpyHostToDevice, st));
   LM_CUDA(cudaMemsetAsync(m.table, 0xff, (size_t)slots * sizeof(CellRec), st));
-  LM_CUDA(cudaMemsetAsync(m.d_cnt, 0, 4 * sizeof(int), st));
-  LM_LAUNCH_ON(c, st, k_map_keys, nb, 256, 0, m.cat, n, m.dev, m.keys, m.vals);
-  int end_bit = (md.n < n) ? 64 : total_bits;
-  size_t tmp = c->cub_tmp_bytes;
-  LM_CUDA(cub::DeviceRadixSort::SortPairs(tmp_buf, tmp, m.keys, m.keys_alt, m.vals, m.vals_alt, n, 0, end_bit, st));
-  c->launches++;
-  const int nf = md.n;
-  LM_LAUNCH_ON(c, st, k_map_gather, div_up(nf, 256), 256, 0, m.cat, m.vals_alt, nf, m.sorted);
-  LM_LAUNCH_ON(c, st, k_head_flags, div_up(nf, 256), 256, 0, m.keys_alt, nf, m.flags);
-  tmp = c->cub_tmp_bytes;
-  LM_CUDA(cub::DeviceSelect::Flagged(tmp_buf, tmp, thrust::counting_iterator<int>(0), m.flags, m.l2_start, m.d_cnt + 0,
-                                     nf, st));
-  c->launches++;
-  LM_LAUNCH_ON(c, st, k_l1_flags, div_up(nf, 256), 256, 0, m.keys_alt, m.l2_start, m.d_cnt + 0, nf, m.flags);
-  tmp = c->cub_tmp_bytes;
-  LM_CUDA(cub::DeviceSelect::Flagged(tmp_buf, tmp, thrust::counting_iterator<int>(0), m.flags, m.l1_first, m.d_cnt + 1,
-                                     nf, st));
-  c->launches++;
-  LM_LAUNCH_ON(c, st, k_cell_insert, div_up(nf, 256), 256, 0, m.keys_alt, m.l2_start, m.l1_first, m.l1_mask, m.d_cnt,
-               nf, m.dev, m.table, md.table_mask);
-  LM_LAUNCH_ON(c, st, k_sentinels, 1, 32, 0, m.l2_start, m.l1_first, m.d_cnt, nf);
+  LM_CUDA(cudaMemsetAsync(m.d_cnt, 0, CNT_WORDS * sizeof(int), st));
+  LM_LAUNCH_ON(c, st, k_cell_count, nb, 256, 0, m.cat, n, m.dev, m.table, md.table_mask, m.slot_rank, m.d_cnt);
+  LM_LAUNCH_ON(c, st, k_cell_alloc, div_up((int)slots, 256), 256, 0, m.table, slots, m.cell_list, m.d_cnt);
+  LM_LAUNCH_ON(c, st, k_cell_scatter, nb, 256, 0, m.cat, n, m.slot_rank, m.table, m.grouped);
+  // persistent blocks stride over the occupied L0 cells (their number is only known on the device)
+  LM_LAUNCH_ON(c, st, k_cell_sort, 148 * 6, CS_THREADS, 0, m.cell_list, m.table, m.grouped, m.sorted, m.l1_mask,
+               m.l1_first, m.l2_start, m.d_cnt);
+  LM_LAUNCH_ON(c, st, k_map_finish, 1, 32, 0, m.dev, m.d_cnt);
   // occupancy of the table (and the insert-failed flag) travel back with the next pose read-back
   LM_CUDA(cudaMemcpyAsync(m.h_cnt, m.d_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   LM_CUDA(cudaGetLastError());

@@ -19,6 +19,8 @@
 // and every kernel of the pre-enqueued sequence exits at once when its phase is over.
 #include <float.h>
 
+#include <chrono>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -1169,6 +1171,7 @@ int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double
 int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upper, int outer_count) {
   if (upper < 0 || outer_count < 0) return LMSF_ERR_INVALID;
   if (upper > c->prm.max_points) return LMSF_ERR_CAPACITY;
+  const auto h_enq0 = std::chrono::steady_clock::now();
   SolveParams sp;
   sp.solver = solver;
   sp.iter = 0;
@@ -1248,6 +1251,8 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
     }
   }
   LM_CUDA(cudaGetLastError());
+  c->host_us[2] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h_enq0).count();
+  c->host_n[2] += 1;
   LM_CUDA(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
   LM_CUDA(cudaMemcpyAsync(c->h_ints + 32, c->ex.counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   LM_CUDA(cudaStreamSynchronize(c->stream));

@@ -377,6 +377,40 @@ def test_tracker_time_keyframe_prior_and_aux(ctxs, sweeps, synth):
     assert sg["first"] == 1 and np.allclose(pg, [0, 0, 0, 1, 0, 0, 0])
 
 
+@pytest.mark.parametrize("name,ns,nsweeps", [("vlp16", 16, 10), ("hdl64", 64, 6)])
+def test_tracker_prefetch_pipeline_is_bit_identical(gpu_lib, sweeps, name, ns, nsweeps):
+    """Front-end pipelining (lmsf_tracker_prefetch*) only reorders work between streams: poses, statistics and
+    maps are bit-identical to the unpipelined sequence, a dropped prefetch included."""
+    seq = [np.ascontiguousarray(sweeps(name, k)) for k in range(nsweeps + 1)]
+    a = gpu_lib.context(0, n_scans=ns)
+    b = gpu_lib.context(0, n_scans=ns)
+    c = gpu_lib.context(0, n_scans=ns)
+    try:
+        d_ptrs = [c.dev_upload_new(s) for s in seq]
+        for k in range(nsweeps):
+            pa, da, sa = a.tracker_step(seq[k], 0.1 * k)
+            # b: host sweeps, prefetch(k+1) before step(k) as bench.py does; at k == 3 the prefetched sweep is the
+            # wrong one (never stepped) and at k == 2 nothing is prefetched: step 3 / 4 fall back to extracting now
+            if k == 3:
+                b.tracker_prefetch(seq[0])
+            elif k != 2:
+                b.tracker_prefetch(seq[k + 1])
+            pb, db, sb = b.tracker_step(seq[k], 0.1 * k)
+            c.tracker_prefetch_dev(d_ptrs[k + 1], len(seq[k + 1]))
+            pc, dc, sc = c.tracker_step_dev(d_ptrs[k], len(seq[k]), 0.1 * k)
+            assert np.array_equal(pa, pb) and np.array_equal(da, db) and sa == sb, k
+            assert np.array_equal(pa, pc) and np.array_equal(da, dc) and sa == sc, k
+        for kind in (0, 1):
+            ma = a.get_map(kind)
+            assert np.array_equal(bits(ma), bits(b.get_map(kind))) and np.array_equal(bits(ma), bits(c.get_map(kind)))
+        for p in d_ptrs:
+            c.dev_free(p)
+    finally:
+        a.close()
+        b.close()
+        c.close()
+
+
 def test_round_trip_full_size(gpu_lib, synth):
     """HDL-64 full size, no oracle: registering a sweep against the map made of itself from a
     perturbed prior must come back to identity (encode -> perturb -> decode round trip)."""
