@@ -73,7 +73,15 @@ struct __align__(32) CellRec {
   unsigned long long key;   // packed relative cell coords, ~0 = empty slot
   unsigned long long mask;  // occupancy of the 4x4x4 L1 sub-cells (0.25 m)
   int start, end;           // range in the cell-sorted point array
-  int fine_base;            // index of this cell's first occupied L1 cell (l1_mask / l1_first)
+  int fine_base;            // index of this cell's first occupied L1 cell (l1[])
+  int pad;
+};
+
+// One occupied L1 cell (0.25 m): occupancy of its 4x4x4 L2 cells and the index of its first L2 cell in l2_start.
+// 16 bytes: one load per visited cell.
+struct __align__(16) L1Rec {
+  unsigned long long mask;
+  int first;
   int pad;
 };
 
@@ -99,8 +107,7 @@ struct MapIndex {
   int2* slot_rank = nullptr;               // [cap] build scratch: hash slot of the point's L0 cell, rank inside it
   int* cell_list = nullptr;                // [cap] build scratch: hash slots of the occupied L0 cells
   int* l2_start = nullptr;                 // [2 cap+1] start of every occupied L2 cell; one sentinel per L0 cell
-  int* l1_first = nullptr;                 // [cap+1] first L2 cell of every occupied L1 cell
-  unsigned long long* l1_mask = nullptr;   // [cap] L2 occupancy of every occupied L1 cell
+  L1Rec* l1 = nullptr;                     // [cap] one record per occupied L1 cell
   int* d_cnt = nullptr;                    // [8] device counters: L2 entries, L1 cells, L0 cells, insert-failed flag, point cursor
   unsigned* d_box = nullptr;               // [8] bbox scratch of this map (ordered-uint min/max, finite count)
   int* h_cnt = nullptr;                    // [4] pinned mirror of d_cnt (read back with the next pose)

@@ -33,8 +33,7 @@ extern "C" int lmsf_debug_knn_stats(lmsf_ctx* c, int kind, const float* q_xyz, i
   MapView v;
   v.sorted = m.sorted;
   v.table = m.table;
-  v.l1_mask = m.l1_mask;
-  v.l1_first = m.l1_first;
+  v.l1 = m.l1;
   v.l2_start = m.l2_start;
   v.dev = m.dev;
   float* d_q = nullptr;

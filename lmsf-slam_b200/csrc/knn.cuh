@@ -9,7 +9,7 @@
 //
 // Levels: L0 = 1 m cells in a hash table; every L0 cell has a 64-bit occupancy
 // mask of its 4x4x4 L1 cells (0.25 m); every occupied L1 cell has a 64-bit mask
-// of its 4x4x4 L2 cells (0.0625 m).  Points are sorted by (L0, L1, L2) so each
+// of its 4x4x4 L2 cells (0.0625 m).  Points are grouped by (L0, L1, L2) so each
 // cell at each level is one contiguous range.  Search:
 //   seed  (outer iterations after the first) the previous iteration's five neighbours give an
 //         upper bound of the 5th distance before anything is scanned,
@@ -44,9 +44,8 @@ __device__ static const signed char kNear27[27][3] = {
 struct MapView {
   const float4* sorted;             // cell-sorted points, .w = original index bits
   const CellRec* table;             // hash table of L0 cells
-  const unsigned long long* l1_mask;  // per occupied L1 cell: occupancy of its L2 cells
-  const int* l1_first;              // per occupied L1 cell: index of its first L2 cell in l2_start (+ sentinel)
-  const int* l2_start;              // start of every occupied L2 cell in `sorted` (+ sentinel)
+  const L1Rec* l1;                  // per occupied L1 cell: occupancy of its L2 cells, index of its first L2 cell
+  const int* l2_start;              // start of every occupied L2 cell in `sorted` (+ one sentinel per L0 cell)
   const MapDev* dev;
 };
 
@@ -171,11 +170,22 @@ __device__ __forceinline__ float box_d2(float qx, float qy, float qz, int cx, in
   return r;
 }
 
+// one 16-byte load per visited L1 cell
+__device__ __forceinline__ L1Rec ldg_l1(const MapView& mv, int l1) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(mv.l1 + l1));
+  L1Rec r;
+  r.mask = ((unsigned long long)v.y << 32) | (unsigned long long)v.x;
+  r.first = (int)v.z;
+  r.pad = 0;
+  return r;
+}
+
 // scan the L2 cells of one L1 cell (absolute L1 coords ax1..az1) that survive the box test
 __device__ __forceinline__ void sweep_l1_cell(const MapView& mv, int l1, int ax1, int ay1, int az1, float qx, float qy,
                                               float qz, Top5& nb KS_DECL) {
-  unsigned long long m2 = mv.l1_mask[l1];
-  int base = mv.l1_first[l1];
+  const L1Rec lr = ldg_l1(mv, l1);
+  unsigned long long m2 = lr.mask;
+  int base = lr.first;
   int rank = 0;
   while (m2) {
     int f2 = __ffsll((long long)m2) - 1;
@@ -226,14 +236,15 @@ __device__ __forceinline__ void sweep_ball(const MapView& mv, const MapDev& md, 
         unsigned long long m1 = rec->mask;
         if (!((m1 >> f1) & 1ull)) continue;
         int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
-        unsigned long long m2 = mv.l1_mask[l1];
+        const L1Rec lr = ldg_l1(mv, l1);
+        unsigned long long m2 = lr.mask;
         int lo = (lx == la) ? (x0 & 3) : 0;
         int hi = (lx == lb) ? (x1 & 3) : 3;
         int flo = row2 | lo, fhi = row2 | hi;
         unsigned long long below = (1ull << flo) - 1ull;
         unsigned long long sub = m2 & ((2ull << fhi) - 1ull) & ~below;
         if (!sub) continue;
-        int b = mv.l1_first[l1] + __popcll(m2 & below);
+        int b = lr.first + __popcll(m2 & below);
         scan_range(mv.sorted, mv.l2_start[b], mv.l2_start[b + __popcll(sub)], qx, qy, qz, nb KS_PASS);
       }
     }

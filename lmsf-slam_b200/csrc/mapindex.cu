@@ -132,8 +132,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict_
                                                           CellRec* __restrict__ table,
                                                           const float4* __restrict__ grouped,
                                                           float4* __restrict__ sorted,
-                                                          unsigned long long* __restrict__ l1_mask,
-                                                          int* __restrict__ l1_first, int* __restrict__ l2_start,
+                                                          L1Rec* __restrict__ l1, int* __restrict__ l2_start,
                                                           int* __restrict__ d_cnt) {
   __shared__ int hist[4096];
   __shared__ int warp_pts[8], warp_n2[8], warp_n1[8];
@@ -216,8 +215,11 @@ __global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict_
     }
   }
   if (l1_head) {
-    l1_mask[base1 + ex_1] = m2;
-    l1_first[base1 + ex_1] = base2 + ex_2;
+    L1Rec r;
+    r.mask = m2;
+    r.first = base2 + ex_2;
+    r.pad = 0;
+    l1[base1 + ex_1] = r;
   }
   // occupancy of the 64 L1 cells: L1 cell j = lanes 4j..4j+3 of warp j / 8
   unsigned heads = __ballot_sync(0xffffffffu, l1_head);
@@ -261,8 +263,7 @@ int map_alloc(Ctx* c, MapIndex& m, int cap) {
   LM_CUDA(cudaMalloc(&m.slot_rank, n * sizeof(int2)));
   LM_CUDA(cudaMalloc(&m.cell_list, n * 4));
   LM_CUDA(cudaMalloc(&m.l2_start, (2 * n + 1) * 4));  // one entry per occupied L2 cell + one sentinel per L0 cell
-  LM_CUDA(cudaMalloc(&m.l1_first, (n + 1) * 4));
-  LM_CUDA(cudaMalloc(&m.l1_mask, n * 8));
+  LM_CUDA(cudaMalloc(&m.l1, n * sizeof(L1Rec)));
   LM_CUDA(cudaMalloc(&m.d_cnt, CNT_WORDS * sizeof(int)));
   LM_CUDA(cudaMalloc(&m.d_box, 8 * sizeof(unsigned)));
   LM_CUDA(cudaMallocHost(&m.h_cnt, 64 * sizeof(int)));
@@ -288,8 +289,7 @@ void map_free(MapIndex& m) {
   cudaFree(m.slot_rank);
   cudaFree(m.cell_list);
   cudaFree(m.l2_start);
-  cudaFree(m.l1_first);
-  cudaFree(m.l1_mask);
+  cudaFree(m.l1);
   cudaFree(m.d_cnt);
   cudaFree(m.d_box);
   cudaFreeHost(m.h_cnt);
@@ -427,8 +427,8 @@ int map_build(Ctx* c, MapIndex& m, int n, cudaStream_t st, bool fixed_grid) {
   LM_LAUNCH_ON(c, st, k_cell_alloc, div_up((int)slots, 256), 256, 0, m.table, slots, m.cell_list, m.d_cnt);
   LM_LAUNCH_ON(c, st, k_cell_scatter, nb, 256, 0, m.cat, n, m.slot_rank, m.table, m.grouped);
   // persistent blocks stride over the occupied L0 cells (their number is only known on the device)
-  LM_LAUNCH_ON(c, st, k_cell_sort, 148 * 6, CS_THREADS, 0, m.cell_list, m.table, m.grouped, m.sorted, m.l1_mask,
-               m.l1_first, m.l2_start, m.d_cnt);
+  LM_LAUNCH_ON(c, st, k_cell_sort, 148 * 6, CS_THREADS, 0, m.cell_list, m.table, m.grouped, m.sorted, m.l1,
+               m.l2_start, m.d_cnt);
   LM_LAUNCH_ON(c, st, k_map_finish, 1, 32, 0, m.dev, m.d_cnt);
   // occupancy of the table (and the insert-failed flag) travel back with the next pose read-back
   LM_CUDA(cudaMemcpyAsync(m.h_cnt, m.d_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -18,6 +18,7 @@
 // No host round trip happens inside a solve: iteration control lives in SolveState on the device,
 // and every kernel of the pre-enqueued sequence exits at once when its phase is over.
 #include <float.h>
+#include <stdlib.h>
 
 #include <chrono>
 
@@ -240,13 +241,30 @@ __device__ __forceinline__ bool reduce_grid(const Acc& acc, double* __restrict__
   __syncthreads();
   if (!last) return false;
   __threadfence();
-  for (int k = warp; k < LM_NSUM; k += MATCH_WARPS) {
-    const double* row = partial + (size_t)k * nblk;
-    double x = 0.0;
-    for (unsigned b = lane; b < nblk; b += 32) x += __ldcg(&row[b]);
+  // every warp owns ROWS of the LM_NSUM quantity rows; the loads of all its rows are issued together, so the sum
+  // costs about one L2 round trip per 32 blocks instead of one per row (the per-lane order of additions, and with it
+  // every bit of the result, is the same as summing row after row)
+  constexpr int ROWS = (LM_NSUM + MATCH_WARPS - 1) / MATCH_WARPS;
+  double x[ROWS];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-    if (lane == 0) tot[k] = x;
+  for (int j = 0; j < ROWS; ++j) x[j] = 0.0;
+  for (unsigned b = lane; b < nblk; b += 32) {
+    double v[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      const int k = warp + j * MATCH_WARPS;
+      v[j] = (k < LM_NSUM) ? __ldcg(&partial[(size_t)k * nblk + b]) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) x[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < ROWS; ++j) {
+    double y = x[j];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) y += __shfl_xor_sync(0xffffffffu, y, d);
+    const int k = warp + j * MATCH_WARPS;
+    if (lane == 0 && k < LM_NSUM) tot[k] = y;
   }
   __syncthreads();
   if (threadIdx.x == 0) st->ticket = 0u;
@@ -757,6 +775,23 @@ __device__ void lm_update_warp(SolveState* st, LmScratch* w, const double* tot, 
   lm_propose_warp(st, w, sp);
 }
 
+// ------------------------------------------------------------------ optional in-kernel timing (tuning builds)
+#ifdef LMSF_TIMING
+__device__ unsigned long long g_dbg[32];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TSTAMP(var) unsigned long long var = gtime()
+#define TACC(slot, a, b) atomicAdd(&g_dbg[slot], (b) - (a))
+#define TCOUNT(slot) atomicAdd(&g_dbg[slot], 1ull)
+#else
+#define TSTAMP(var)
+#define TACC(slot, a, b)
+#define TCOUNT(slot)
+#endif
+
 // ------------------------------------------------------------------ kernels
 struct QueryBufs {
   unsigned* keys;            // [upper] sort keys (kind | L0 | L1 | L2 cell of the world point, top 32 bits)
@@ -797,9 +832,10 @@ __device__ __forceinline__ int own_cell_population(const MapView& mv, float x, f
   if (!((m1 >> f1) & 1ull)) return 0;
   int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
   int f2 = ((az & 3) << 4) | ((ay & 3) << 2) | (ax & 3);
-  unsigned long long m2 = mv.l1_mask[l1];
+  const L1Rec lr = ldg_l1(mv, l1);
+  unsigned long long m2 = lr.mask;
   if (!((m2 >> f2) & 1ull)) return 0;
-  int b = mv.l1_first[l1] + __popcll(m2 & ((1ull << f2) - 1ull));
+  int b = lr.first + __popcll(m2 & ((1ull << f2) - 1ull));
   return mv.l2_start[b + 1] - mv.l2_start[b];
 }
 
@@ -926,6 +962,7 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
                                                      double* __restrict__ partial, SolveParams sp) {
   __shared__ double tot[LM_NSUM];
   if (sp.solver == LMSF_SOLVER_GN && st->gn_done) return;
+  TSTAMP(t_begin);
   const int n_e = counts[0], n_s = counts[1];
   quat q;
   q.x = st->x[0];
@@ -994,7 +1031,9 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
     }
     rb.kind[t] = kind;
   }
+  TSTAMP(t_loop);
   if (!reduce_grid(acc, partial, st, tot)) return;
+  TSTAMP(t_red);
   // the serial 6x6 step runs on a shared-memory copy of the state (one thread, latency bound:
   // global-memory round trips on every st-> field would dominate it)
   __shared__ SolveState sh;
@@ -1010,6 +1049,15 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
     lm_begin_warp(&sh, &scratch, tot, sp);
   }
   state_store(st, &sh);
+#ifdef LMSF_TIMING
+  if (threadIdx.x == 0) {
+    TSTAMP(t_end);
+    TACC(0, t_begin, t_loop);
+    TACC(1, t_loop, t_red);
+    TACC(2, t_red, t_end);
+    TCOUNT(3);
+  }
+#endif
 }
 
 // re-evaluate the stored correspondences at the LM candidate; last block accepts / rejects / proposes
@@ -1017,6 +1065,7 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* 
                                                          double* __restrict__ partial, SolveParams sp) {
   __shared__ double tot[LM_NSUM];
   if (!st->lm_active) return;
+  TSTAMP(t_begin);
   quat q;
   q.x = st->cand[0];
   q.y = st->cand[1];
@@ -1038,12 +1087,23 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* 
       surf_factor(q, tr, pl, mk3(r0, r1, r2), r3, sp.huber, acc);
     }
   }
+  TSTAMP(t_loop);
   if (!reduce_grid(acc, partial, st, tot)) return;
+  TSTAMP(t_red);
   __shared__ SolveState sh;
   __shared__ LmScratch scratch;
   state_load(&sh, st);
   if (threadIdx.x < 32) lm_update_warp(&sh, &scratch, tot, sp);
   state_store(st, &sh);
+#ifdef LMSF_TIMING
+  if (threadIdx.x == 0) {
+    TSTAMP(t_end);
+    TACC(4, t_begin, t_loop);
+    TACC(5, t_loop, t_red);
+    TACC(6, t_red, t_end);
+    TCOUNT(7);
+  }
+#endif
 }
 
 __global__ void k_state_init(SolveState* st, const double* __restrict__ pose) {
@@ -1106,12 +1166,20 @@ __global__ void __launch_bounds__(128) k_match_hook(MapView mv, const float4* __
 }
 
 // ------------------------------------------------------------------ host side
+#ifndef KNN_GRID_PER_SM
+#define KNN_GRID_PER_SM 7
+#endif
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  int x = v ? atoi(v) : 0;
+  return x > 0 ? x : dflt;
+}
+
 static MapView view_of(const MapIndex& m) {
   MapView v;
   v.sorted = m.sorted;
   v.table = m.table;
-  v.l1_mask = m.l1_mask;
-  v.l1_first = m.l1_first;
+  v.l1 = m.l1;
   v.l2_start = m.l2_start;
   v.dev = m.dev;
   return v;
@@ -1166,6 +1234,18 @@ int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double
   return LMSF_OK;
 }
 
+#ifdef LMSF_TIMING
+extern "C" int lmsf_debug_kernel_times(unsigned long long out[32], int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 32);
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_dbg, z, sizeof z);
+  }
+  return 0;
+}
+#endif
+
 // Enqueue one whole solve on the stream, then read pose + statistics back (one sync).
 // upper = host-side upper bound of n_edge + n_surf (the device counts are authoritative).
 int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upper, int outer_count) {
@@ -1185,11 +1265,14 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
   maps.surf_cat = c->map[1].cat;
   const int he = c->map[0].ready ? 1 : 0, hs = c->map[1].ready ? 1 : 0;
   const int up = upper > 0 ? upper : 1;
-  // persistent-style grids: a few CTAs per SM, grid-stride over the queries
+  // persistent-style grids: a few CTAs per SM, grid-stride over the queries (per-SM factors tunable through the
+  // environment for profiling sweeps only)
+  static const int fit_per_sm = env_int("LMSF_FIT_GRID", 2), eval_per_sm = env_int("LMSF_EVAL_GRID", 1),
+                   knn_per_sm = env_int("LMSF_KNN_GRID", KNN_GRID_PER_SM);
   int fit_grid = div_up(up, MATCH_BLOCK);
-  if (fit_grid > 148 * 2) fit_grid = 148 * 2;
+  if (fit_grid > 148 * fit_per_sm) fit_grid = 148 * fit_per_sm;
   int eval_grid = div_up(up, MATCH_BLOCK);
-  if (eval_grid > 148) eval_grid = 148;
+  if (eval_grid > 148 * eval_per_sm) eval_grid = 148 * eval_per_sm;
   RecBufs rb;
   rb.d = c->d_rec;
   rb.pl = c->d_recf;
@@ -1230,10 +1313,7 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
     {
       StageScope scope(c, LMSF_STAGE_MATCH);
       int knn_grid = div_up(up, 128);
-#ifndef KNN_GRID_PER_SM
-#define KNN_GRID_PER_SM 7
-#endif
-      if (knn_grid > 148 * KNN_GRID_PER_SM) knn_grid = 148 * KNN_GRID_PER_SM;  // persistent: every resident warp pulls work
+      if (knn_grid > 148 * knn_per_sm) knn_grid = 148 * knn_per_sm;  // persistent: every resident warp pulls work
       LM_LAUNCH(c, k_knn, knn_grid, 128, 0, c->q_vals_alt, c->d_pw, c->ex.counts, c->d_state, maps, he, hs, up,
                 solver, it == 0 ? 0 : 1, c->d_nbr);
       c->match_bytes += alg_bytes;
