@@ -190,6 +190,7 @@ static int scan_filter(Ctx* c) {
   const float le = c->prm.scan_leaf_edge, ls = c->prm.scan_leaf_surf;
   if (!(le > 0.f) && !(ls > 0.f)) return LMSF_OK;
   LM_TRY(fetch_counts(c));
+  c->perm_valid = false;  // the features are about to be replaced by voxel centroids
   const int ne = c->n_edge, ns = c->n_surf;
   if (ne + ns == 0) return LMSF_OK;
   LM_CUDA(cudaMemcpyAsync(c->d_tmp, c->d_feat, (size_t)(ne + ns) * sizeof(float4), cudaMemcpyDeviceToDevice,
@@ -258,6 +259,8 @@ static void alias_slot(Ctx* c, int si) {
   c->slot_cur = si;
   c->d_feat = c->slot[si].feat;
   c->ex.counts = c->slot[si].counts;
+  c->d_perm = c->slot[si].perm;
+  c->perm_valid = false;
 }
 
 // a slot that holds no unconsumed prefetch (the current one preferred); when both do, the older prefetch is dropped
@@ -314,7 +317,7 @@ static int extract_into_slot(Ctx* c, int si, const float* xyzi, int n, bool host
     LM_TRY(upload_sweep(c, xyzi, n));
     d_in = c->d_sweep;
   }
-  LM_TRY(extract_run(c, d_in, n, c->stream_fe, sl.feat, sl.counts));
+  LM_TRY(extract_run(c, d_in, n, c->stream_fe, sl.feat, sl.counts, sl.perm));
   LM_CUDA(cudaEventRecord(sl.ready, c->stream_fe));
   return LMSF_OK;
 }
@@ -327,6 +330,7 @@ static int adopt_slot(Ctx* c, int si) {
   sl.src = nullptr;
   LM_CUDA(cudaStreamWaitEvent(c->stream, sl.ready, 0));
   c->feat_from_extract = true;
+  c->perm_valid = true;
   return LMSF_OK;
 }
 
@@ -390,6 +394,7 @@ static void destroy(Ctx* c) {
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->slot[i].feat);
     cudaFree(c->slot[i].counts);
+    cudaFree(c->slot[i].perm);
     if (c->slot[i].ready) cudaEventDestroy(c->slot[i].ready);
     if (c->slot[i].freed) cudaEventDestroy(c->slot[i].freed);
     cudaFreeHost(c->h_stage[i]);
@@ -417,6 +422,7 @@ static int create(Ctx* c) {
     LM_CUDA(cudaMalloc(&c->slot[i].feat, cap * sizeof(float4)));
     LM_CUDA(cudaMalloc(&c->slot[i].counts, 4 * sizeof(int)));
     LM_CUDA(cudaMemset(c->slot[i].counts, 0, 4 * sizeof(int)));
+    LM_CUDA(cudaMalloc(&c->slot[i].perm, cap * sizeof(int)));
     LM_CUDA(cudaEventCreateWithFlags(&c->slot[i].ready, cudaEventDisableTiming));
     LM_CUDA(cudaEventCreateWithFlags(&c->slot[i].freed, cudaEventDisableTiming));
     LM_CUDA(cudaMallocHost(&c->h_stage[i], cap * sizeof(float4)));
@@ -424,6 +430,7 @@ static int create(Ctx* c) {
   }
   c->slot_cur = 0;
   c->d_feat = c->slot[0].feat;
+  c->d_perm = c->slot[0].perm;
   LM_CUDA(cudaMalloc(&c->d_tmp, cap * sizeof(float4)));
   LM_CUDA(cudaMallocHost(&c->h_pts, cap * sizeof(float4)));
   LM_CUDA(cudaMallocHost(&c->h_pose, 16 * sizeof(double)));

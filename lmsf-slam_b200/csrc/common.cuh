@@ -63,6 +63,7 @@ struct ExtractBufs {
   int* edge_ids = nullptr;     // [64*6*20] picked edges per sector in pick order
   int* sec_cnt = nullptr;      // [64*6] edges picked per sector
   uint8_t* label = nullptr;    // [cap] by original index
+  int* surf_rank = nullptr;    // [cap] scratch: feature index of the surf at a ring-order position
   int* counts = nullptr;       // [4] n_edge, n_surf, n_valid
 };
 
@@ -203,6 +204,7 @@ struct Ctx {
   struct FeatSlot {
     float4* feat = nullptr;         // [max_points] edges first, then surfs
     int* counts = nullptr;          // [4] n_edge, n_surf (device)
+    int* perm = nullptr;            // [max_points] processing order of the registration: position -> feature index
     cudaEvent_t ready = nullptr;    // front-end stream: extraction into this slot finished
     cudaEvent_t freed = nullptr;    // map stream: the local-map update has consumed this slot
     bool freed_pending = false;     // nobody has waited for `freed` yet
@@ -214,6 +216,8 @@ struct Ctx {
   };
   FeatSlot slot[2];
   int slot_cur = 0;
+  int* d_perm = nullptr;          // alias of slot[slot_cur].perm
+  bool perm_valid = false;        // d_perm describes d_feat (features from our own extraction, unfiltered)
   int64_t prefetch_seq = 0;
   cudaStream_t stream_fe = nullptr;
   float4* h_stage[2] = {nullptr, nullptr};  // pinned staging of host sweeps, alternating
@@ -268,7 +272,7 @@ int extract_alloc(Ctx* c);
 void extract_free(Ctx* c);
 // sweep d_in (n points, device) -> feat_out (edges, then surfs), counts_out[0..1], labels in ex.label; all launches
 // on stream `st`.  The scratch in ExtractBufs is shared: extractions must be ordered on one stream (the front end's).
-int extract_run(Ctx* c, const float4* d_in, int n, cudaStream_t st, float4* feat_out, int* counts_out);
+int extract_run(Ctx* c, const float4* d_in, int n, cudaStream_t st, float4* feat_out, int* counts_out, int* perm_out);
 
 // ---- implemented in voxel.cu
 int voxel_alloc(Ctx* c);

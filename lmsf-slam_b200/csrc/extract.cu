@@ -352,7 +352,8 @@ __global__ void __launch_bounds__(256) k_feat_scatter(const float4* __restrict__
                                                       const uint8_t* __restrict__ is_edge,
                                                       const int* __restrict__ edge_ids, const int* __restrict__ sec_cnt,
                                                       int n_scans, float4* __restrict__ feat,
-                                                      uint8_t* __restrict__ label, int* __restrict__ counts) {
+                                                      uint8_t* __restrict__ label, int* __restrict__ counts,
+                                                      int* __restrict__ surf_rank, int* __restrict__ perm) {
   __shared__ int red[4][8];
   __shared__ int tot[4];
   __shared__ int wsum[8];
@@ -404,6 +405,7 @@ __global__ void __launch_bounds__(256) k_feat_scatter(const float4* __restrict__
     int id = edge_ids[me * 20 + threadIdx.x];
     feat[e_before + threadIdx.x] = rp[id];
     label[src[id]] = 1;
+    perm[e_before + threadIdx.x] = e_before + threadIdx.x;  // edges keep their order in the processing permutation
   }
   // surfs: every id of the ascending order that is not an edge (:197-206)
   const int* ord = sorted + sc.off + (sc.s - 5);
@@ -430,7 +432,34 @@ __global__ void __launch_bounds__(256) k_feat_scatter(const float4* __restrict__
     if (f) {
       surf[run + wbase + inc - 1] = rp[id];
       label[src[id]] = 2;
+      surf_rank[sc.off + id] = e_total + s_before + run + wbase + inc - 1;
     }
+    run += all;
+    __syncthreads();
+  }
+  // Processing permutation of the registration (a locality order, any permutation is correct): the surfs of this
+  // sector in firing order instead of curvature order, so that the 32 queries of a warp are neighbours along the
+  // ring.  perm[position] = feature index; the sector owns the same position range as in the feature cloud.
+  run = 0;
+  for (int base = 0; base < sc.n; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int id = sc.s + i;
+    int f = (i < sc.n && is_edge[sc.off + id] == 0) ? 1 : 0;
+    int inc = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int wbase = 0, all = 0;
+    for (int w = 0; w < 8; ++w) {
+      int x = wsum[w];
+      if (w < warp) wbase += x;
+      all += x;
+    }
+    if (f) perm[e_total + s_before + run + wbase + inc - 1] = surf_rank[sc.off + id];
     run += all;
     __syncthreads();
   }
@@ -458,6 +487,7 @@ int extract_alloc(Ctx* c) {
   LM_CUDA(cudaMalloc(&x.edge_ids, MAX_RINGS * 6 * 20 * sizeof(int)));
   LM_CUDA(cudaMalloc(&x.sec_cnt, MAX_RINGS * 6 * sizeof(int)));
   LM_CUDA(cudaMalloc(&x.label, cap));
+  LM_CUDA(cudaMalloc(&x.surf_rank, cap * sizeof(int)));
   return LMSF_OK;
 }
 
@@ -479,10 +509,12 @@ void extract_free(Ctx* c) {
   cudaFree(x.edge_ids);
   cudaFree(x.sec_cnt);
   cudaFree(x.label);
+  cudaFree(x.surf_rank);
   x = ExtractBufs();
 }
 
-int extract_run(Ctx* c, const float4* d_in, int n, cudaStream_t st, float4* feat_out, int* counts_out) {
+int extract_run(Ctx* c, const float4* d_in, int n, cudaStream_t st, float4* feat_out, int* counts_out,
+                int* perm_out) {
   ExtractBufs& x = c->ex;
   if (n > x.cap) return LMSF_ERR_CAPACITY;
   StageScope scope(c, LMSF_STAGE_EXTRACT, st);
@@ -499,7 +531,7 @@ int extract_run(Ctx* c, const float4* d_in, int n, cudaStream_t st, float4* feat
   LM_LAUNCH_ON(c, st, k_ring_pick, R, 256, 0, x.ring_pts, x.ring_cnt, x.ring_off, x.curv, x.sorted, prm, x.flag,
                x.btype, x.is_edge, x.edge_ids, x.sec_cnt);
   LM_LAUNCH_ON(c, st, k_feat_scatter, dim3(6, R), 256, 0, x.ring_pts, x.ring_src, x.ring_cnt, x.ring_off, x.sorted,
-               x.is_edge, x.edge_ids, x.sec_cnt, R, feat_out, x.label, counts_out);
+               x.is_edge, x.edge_ids, x.sec_cnt, R, feat_out, x.label, counts_out, x.surf_rank, perm_out);
   LM_CUDA(cudaGetLastError());
   return LMSF_OK;
 }

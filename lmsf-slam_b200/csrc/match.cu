@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(128, KNN_MINBLOCKS) k_knn(const int* __restric
       if (base >= live) break;
     }
     int t = base + lane;
-    if (lane >= width || t >= upper) continue;
+    if (lane >= width || t >= upper || t >= live) continue;  // positions >= live: padding (sorted) or unset (ring order)
     int f = perm[t];
     if (f >= live) continue;
     const bool is_edge = f < n_e;
@@ -976,7 +976,7 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
   acc_zero(acc);
   for (int t = blockIdx.x * MATCH_BLOCK + threadIdx.x; t < upper; t += gridDim.x * MATCH_BLOCK) {
     int f = perm[t];
-    const bool live = f < n_e + n_s;  // padding sorts last; its kind must still be cleared for k_lm_eval
+    const bool live = t < n_e + n_s && f < n_e + n_s;  // positions behind the live ones: kind cleared for k_lm_eval
     const bool is_edge = f < n_e;
     Top5 nb;
 #pragma unroll
@@ -1278,6 +1278,12 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
   rb.pl = c->d_recf;
   rb.kind = c->d_ok;
   rb.stride = c->prm.max_points;
+  // Processing order of the queries (position -> feature index).  Features from our own extraction come with a
+  // permutation that walks the surfs along their rings (consecutive positions are neighbours in space): no sort.
+  // Caller-supplied or voxel-filtered features are sorted by map cell once per solve instead.
+  static const int force_qsort = env_int("LMSF_FORCE_QSORT", 0);  // tuning experiments
+  const bool ring_order = c->perm_valid && !force_qsort;
+  const int* perm = ring_order ? c->d_perm : c->q_vals_alt;
   QueryBufs qb;
   qb.keys = (unsigned*)c->q_keys;
   qb.vals = c->q_vals;
@@ -1302,8 +1308,8 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
       // of a feature stable so that k_knn can seed its search with the previous iteration's neighbours
       StageScope scope(c, LMSF_STAGE_ASSOC);
       LM_LAUNCH(c, k_assoc, div_up(up, 256), 256, 0, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, qorg, up,
-                solver, it == 0 ? 1 : 0, qb);
-      if (it == 0) {
+                solver, (it == 0 && !ring_order) ? 1 : 0, qb);
+      if (it == 0 && !ring_order) {
         size_t tmp = c->cub_tmp_bytes;
         LM_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, (unsigned*)c->q_keys, (unsigned*)c->q_keys_alt,
                                                 c->q_vals, c->q_vals_alt, up, 0, 32, c->stream));
@@ -1314,14 +1320,14 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
       StageScope scope(c, LMSF_STAGE_MATCH);
       int knn_grid = div_up(up, 128);
       if (knn_grid > 148 * knn_per_sm) knn_grid = 148 * knn_per_sm;  // persistent: every resident warp pulls work
-      LM_LAUNCH(c, k_knn, knn_grid, 128, 0, c->q_vals_alt, c->d_pw, c->ex.counts, c->d_state, maps, he, hs, up,
+      LM_LAUNCH(c, k_knn, knn_grid, 128, 0, perm, c->d_pw, c->ex.counts, c->d_state, maps, he, hs, up,
                 solver, it == 0 ? 0 : 1, c->d_nbr);
       c->match_bytes += alg_bytes;
       c->match_launches += 1;
     }
     {
       StageScope scope(c, LMSF_STAGE_FIT);
-      LM_LAUNCH(c, k_fit, fit_grid, MATCH_BLOCK, 0, c->d_feat, c->q_vals_alt, c->d_pw, c->d_nbr, c->ex.counts, maps,
+      LM_LAUNCH(c, k_fit, fit_grid, MATCH_BLOCK, 0, c->d_feat, perm, c->d_pw, c->d_nbr, c->ex.counts, maps,
                 up, c->d_state, rb, c->d_partial, sp);
     }
     if (solver == LMSF_SOLVER_HUBER_LM) {
