@@ -328,6 +328,173 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------
+# --workload loopdb: BASELINE.json configs[4] — loop-closure descriptor database search over 100 000 keyframes,
+# database sharded over the ranks, per-rank candidates merged with one NCCL all_gather (shard.loop_search_sharded).
+# Not the driver's default line; run explicitly:  python bench.py --workload loopdb [--gpus N]
+LOOP_METRIC = "loop-closure descriptor searches/sec (ScanContext, 100k-keyframe database)"
+LOOP_DB = 100_000
+LOOP_NQ = 1024
+
+
+def make_loop_data(rank_lo, rank_hi, seed=20260500):
+    """Seeded synthetic database shard [lo, hi) + the replicated query batch.  Descriptors are derived from real
+    ScanContext descriptors of 64 synthetic VLP-16 sweeps (made on the GPU) by scaling, noise and column shifts."""
+    pkg = entry.load_package()
+    rng = np.random.default_rng(seed)
+    base_desc = make_loop_data.base
+    nb = len(base_desc)
+    src = rng.integers(0, nb, size=LOOP_DB)
+    scale = rng.uniform(0.6, 1.4, size=LOOP_DB).astype(np.float32)
+    shift = rng.integers(0, 60, size=LOOP_DB)
+    q_ids = rng.integers(0, LOOP_DB - 50, size=LOOP_NQ)
+    q_shift = rng.integers(0, 60, size=LOOP_NQ)
+
+    def desc_of(ids):
+        out = np.empty((len(ids), 20, 60), np.float32)
+        for j, i in enumerate(ids):
+            r = np.random.default_rng(seed + 1 + int(i))
+            d = np.roll(base_desc[src[i]] * scale[i], int(shift[i]), axis=1)
+            out[j] = np.where(d > 0, d + r.normal(0, 0.15, size=d.shape), 0).astype(np.float32)
+        return out
+
+    def keys_of(d):
+        return (np.cumsum(d.astype(np.float64), axis=2)[:, :, -1] / 60).astype(np.float32)
+
+    shard_desc = desc_of(range(rank_lo, rank_hi))
+    qd = desc_of(q_ids)
+    qd = np.stack([np.roll(qd[j], int(q_shift[j]), axis=1) for j in range(LOOP_NQ)])
+    r = np.random.default_rng(seed + 7)
+    qd = np.where(qd > 0, qd + r.normal(0, 0.03, size=qd.shape), 0).astype(np.float32)
+    return shard_desc, keys_of(shard_desc), qd, keys_of(qd), q_ids, q_shift
+
+
+def run_loopdb(args):
+    import torch
+
+    rank, world, local = dist_env()
+    use_dist = world > 1
+    W, K = args.warmup, args.steps
+    torch.cuda.set_device(local)
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = entry.load_package()
+    ctx = pkg.context(local, n_scans=16, max_points=1 << 16, max_map_points=1 << 17)
+    sensor = pkg.synth.vlp16()
+    make_loop_data.base = np.stack([ctx.sc_make(pkg.synth.make_sweep(sensor, 3 * k))[0] for k in range(64)])
+    lo, hi = pkg.shard.shard_bounds(LOOP_DB, world, rank)
+    descs, keys, qd, qk, q_ids, q_shift = make_loop_data(lo, hi)
+    ctx.scdb_reserve(hi - lo)
+    for a in range(0, hi - lo, 8192):
+        ctx.scdb_add(descs[a:a + 8192], keys[a:a + 8192])
+    limit = pkg.library().fn("sc_tree_limit")(LOOP_DB)   # the searched prefix after LOOP_DB keyframes
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
+    h_qk = torch.from_numpy(qk).pin_memory()
+    h_qd = torch.from_numpy(qd.reshape(LOOP_NQ, 1200)).pin_memory()
+    d_qk, d_qd = h_qk.to(dev), h_qd.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = None
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return pkg.shard.loop_search_sharded(ctx, d_qk, d_qd, limit, lo, hi, 0.2)
+
+    def step_e2e():
+        with torch.cuda.stream(stream):
+            a = h_qk.to(dev, non_blocking=True)
+            b = h_qd.to(dev, non_blocking=True)
+        ids, dd, sh = pkg.shard.loop_search_sharded(ctx, a, b, limit, lo, hi, 0.2)
+        with torch.cuda.stream(stream):
+            out = (ids.cpu(), dd.cpu(), sh.cpu())
+        stream.synchronize()
+        return out
+
+    def timed(fn):
+        for _ in range(W):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active.set()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(K):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+            r = fn()
+        e1.record(stream)
+        barrier()
+        sampler.active.clear()
+        return e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3, r
+
+    l0 = ctx.launch_count()
+    dev_ms, _, res = timed(step_resident)
+    launches = ctx.launch_count() - l0
+    _, e_wall_ms, res_e = timed(step_e2e)
+    sampler.stop_flag.set()
+    sampler.join()
+    ids = res[0].cpu().numpy()
+    hit = float(np.mean(ids == q_ids))
+    assert np.array_equal(ids, res_e[0].numpy())
+    dev_ms_max, e2e_ms_max = pkg.shard.max_over_ranks([dev_ms, e_wall_ms], device=f"cuda:{local}")
+    if rank == 0:
+        peak, peak_src = peaks()
+        line = {
+            "metric": LOOP_METRIC, "value": LOOP_NQ * K / (dev_ms_max * 1e-3), "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ScanContext loop search: 100 000-keyframe database sharded over the ranks, "
+                                   f"{LOOP_NQ} replicated queries per step, exact ring-key top-10 + SC distance per shard, "
+                                   "one all_gather of 24-byte candidates, identical selection on every rank",
+                       "database": LOOP_DB, "searched_prefix": int(limit), "queries_per_step": LOOP_NQ,
+                       "shard": [int(lo), int(hi)], "recall_of_planted_revisits": hit,
+                       "l2": "256 MiB memset between timed steps (L2 flush), inside the timed region",
+                       "bound_note": "the ring-key scan is fp32-ALU bound (60 non-fused flops per key pair), not HBM bound"},
+            "e2e": {"value": LOOP_NQ * K / (e2e_ms_max * 1e-3), "unit": "queries/s",
+                    "h2d_bytes_per_step": LOOP_NQ * (80 + 4800), "d2h_bytes_per_step": LOOP_NQ * 16,
+                    "api": "pinned host queries -> lmsf_scdb_search_shard_dev + all_gather + lmsf_scdb_pick_dev -> host results"},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": "k_sc_scan (exact ring-key 10-NN scan of the shard)",
+                         "achieved": (80.0 * (hi - lo) + 84.0 * LOOP_NQ) / (dev_ms_max / K * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": (80.0 * (hi - lo) + 84.0 * LOOP_NQ) / (dev_ms_max / K * 1e-3) / 1e9 / peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "note": "whole step time used as the kernel time (upper bound); algorithmic bytes = keys once + queries"},
+        }
+        if args.gpus == 1 and not args.no_cpu:
+            import ctypes as C
+            lib = C.CDLL(entry.ORACLE_LIB)
+            nqs = 16
+            f32p, f64p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int32)
+            o_id = np.empty(nqs, np.int32)
+            o_d = np.empty(nqs, np.float64)
+            o_s = np.empty(nqs, np.int32)
+            kk = np.ascontiguousarray(keys)
+            dd = np.ascontiguousarray(descs.reshape(-1, 1200))
+            t0 = time.perf_counter()
+            lib.lmsf_oracle_sc_search(kk.ctypes.data_as(f32p), dd.ctypes.data_as(f32p), C.c_int(int(limit)),
+                                      qk[:nqs].ctypes.data_as(f32p), qd[:nqs].reshape(nqs, 1200).ctypes.data_as(f32p),
+                                      C.c_int(nqs), C.c_double(0.2), o_id.ctypes.data_as(i32p), o_d.ctypes.data_as(f64p),
+                                      o_s.ctypes.data_as(i32p))
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": nqs / dt, "unit": "queries/s", "cores": 1, "kind": "port",
+                                    "sample": f"{nqs} of the {LOOP_NQ} queries against the same database, oracle "
+                                              "brute-force ring-key scan + SC distance, 1 thread",
+                                    "agrees_with_gpu": bool(np.array_equal(o_id, ids[:nqs]))}
+        print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
+    del res, res_e, d_qk, d_qd, flush
+    ctx.close()
+    if use_dist:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -335,10 +502,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="registration", choices=["registration", "loopdb"],
+                    help="registration = the headline metric (default); loopdb = sharded loop-closure descriptor search")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "loopdb":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "loopdb workload: the CPU port is timed inside the "
+                                                               "line's cpu_baseline"}))
+            return
+        run_loopdb(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -102,7 +102,7 @@ def loop_search_sharded(ctx, q_keys: torch.Tensor, q_descs: torch.Tensor, limit_
     ctx: the rank's lmsf context whose descriptor database holds keyframes [lo, hi).  q_keys (nq, 20) and
     q_descs (nq, 1200) are float32 CUDA tensors on the context's device.  Returns CUDA tensors
     (loop_id int32, loop_dist float64, loop_shift int32), identical on every rank.  All work is enqueued on
-    the context's stream; the caller synchronises.
+    the context's stream; the caller synchronises (and keeps q_keys / q_descs alive until then).
     """
     if not (q_keys.is_cuda and q_descs.is_cuda):
         raise ValueError("queries must be CUDA tensors (there is no CPU path)")
@@ -120,6 +120,6 @@ def loop_search_sharded(ctx, q_keys: torch.Tensor, q_descs: torch.Tensor, limit_
         loop_shift = torch.empty(nq, dtype=torch.int32, device=dev)
         ctx.scdb_pick_dev(allc.data_ptr(), world, nq, thresh, loop_id.data_ptr(), loop_dist.data_ptr(),
                           loop_shift.data_ptr())
-    for t in (q_keys, q_descs, cand, allc, loop_id, loop_dist, loop_shift):
-        t.record_stream(stream)
+    # cand / allc / results were allocated on the context's stream (their allocation stream); the query tensors are
+    # the caller's: they must stay alive until the caller has synchronised with the context's stream.
     return loop_id, loop_dist, loop_shift
