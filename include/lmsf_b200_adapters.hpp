@@ -10,6 +10,8 @@
 //        replaces  CeresEdgeSurfFeatureRegistration / EdgeSurfFeatureRegistration
 //                                             (registration/ceres_edgeSurfFeatureRegistration.hpp:26,
 //                                              edgeSurfFeatureRegistration.hpp:27, built at ML_SystemFactory.hpp:189-190)
+//   lmsf::CudaSceneRecognitionScanContext<P>   (no abstract base in the reference: same public methods)
+//        replaces  Slam3D::SceneRecognitionScanContext   (LoopDetection/SceneRecognitionScanContext.hpp:21-345)
 //
 // Error convention: the reference's seams return void and print on failure; the adapters print
 // lmsf_strerror to stderr and leave the output as the reference would (empty clouds / pose untouched).
@@ -22,6 +24,8 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "lmsf_b200.h"
@@ -243,6 +247,94 @@ class CudaEdgeSurfRegistration : public Algorithm::RegistrationBase<_PointType> 
   int solver_;
   typename pcl::PointCloud<_PointType>::ConstPtr edge_in_, surf_in_;
   lmsf_reg_stats last_{};
+};
+
+// ---------------------------------------------------------------- loop-closure place recognition (row f1)
+// Same public surface as Slam3D::SceneRecognitionScanContext<_PointCloudT> (AddKeyFramePoints :61-94,
+// FindSimilarPointCloud :102-111, LoopDetect :119-134); descriptors, ring keys and the search live on the device.
+template <typename _PointCloudT>
+class CudaSceneRecognitionScanContext {
+ public:
+  using PointCloudContainer = std::unordered_map<std::string, typename pcl::PointCloud<_PointCloudT>::ConstPtr>;
+  explicit CudaSceneRecognitionScanContext(ContextPtr ctx, std::vector<std::string> target_names = {})
+      : ctx_(std::move(ctx)), target_names_(std::move(target_names)) {}
+
+  void AddKeyFramePoints(PointCloudContainer const& pcl_in) {
+    std::vector<float> buf;
+    const int n = select(pcl_in, buf);
+    int id = -1;
+    if (!detail::check(lmsf_scdb_add_cloud(ctx_->get(), buf.data(), n, &id), "lmsf_scdb_add_cloud")) return;
+    size_ = id + 1;
+    limit_ = lmsf_sc_tree_limit(size_);  // the tree is rebuilt every 10th keyframe over [0, size - 50) (:74-92)
+  }
+
+  std::pair<std::int64_t, Eigen::Isometry3d> FindSimilarPointCloud(PointCloudContainer const& scan_in) {
+    if (limit_ <= 0) return std::make_pair((std::int64_t)-1, Eigen::Isometry3d::Identity());  // no tree yet (:104)
+    std::vector<float> buf, desc(LMSF_SC_CELLS), key(LMSF_SC_RINGS);
+    const int n = select(scan_in, buf);
+    if (!detail::check(lmsf_sc_make(ctx_->get(), buf.data(), n, desc.data(), key.data()), "lmsf_sc_make"))
+      return std::make_pair((std::int64_t)-1, Eigen::Isometry3d::Identity());
+    return find(key.data(), desc.data());
+  }
+
+  std::pair<std::int64_t, Eigen::Isometry3d> LoopDetect(std::uint32_t const& id) {
+    if (size_ < 50 + 1 || limit_ <= 0) return std::make_pair((std::int64_t)-1, Eigen::Isometry3d::Identity());  // :129
+    std::vector<float> desc(LMSF_SC_CELLS), key(LMSF_SC_RINGS);
+    if (!detail::check(lmsf_scdb_get(ctx_->get(), (int)id, desc.data(), key.data()), "lmsf_scdb_get"))
+      return std::make_pair((std::int64_t)-1, Eigen::Isometry3d::Identity());
+    return find(key.data(), desc.data());
+  }
+
+  int Size() const { return size_; }
+  double LastDistance() const { return last_dist_; }
+  int LastShift() const { return last_shift_; }
+
+ private:
+  // extractInterestPointClouds (:236-252): every cloud of the container, or the named ones, concatenated
+  int select(PointCloudContainer const& in, std::vector<float>& out) const {
+    out.clear();
+    auto append = [&out](const pcl::PointCloud<_PointCloudT>& c) {
+      for (const auto& p : c.points) {
+        out.push_back(p.x);
+        out.push_back(p.y);
+        out.push_back(p.z);
+        out.push_back(p.intensity);
+      }
+    };
+    if (target_names_.empty()) {
+      for (auto it = in.begin(); it != in.end(); ++it)
+        if (it->second) append(*it->second);
+    } else {
+      for (const std::string& name : target_names_) {
+        auto it = in.find(name);
+        if (it != in.end() && it->second) append(*it->second);
+      }
+    }
+    return (int)(out.size() / 4);
+  }
+  // descFindSimilar (:260-333): ring-key top-10, best SC distance, threshold 0.2, yaw = shift * 6 deg about z
+  std::pair<std::int64_t, Eigen::Isometry3d> find(const float* key, const float* desc) {
+    std::int32_t id = -1, shift = 0;
+    double dist = 0;
+    Eigen::Isometry3d rel = Eigen::Isometry3d::Identity();
+    if (!detail::check(lmsf_scdb_search(ctx_->get(), key, desc, 1, limit_, 0.2, &id, &dist, &shift), "lmsf_scdb_search"))
+      return std::make_pair((std::int64_t)-1, rel);
+    last_dist_ = dist;
+    last_shift_ = shift;
+    if (id < 0) return std::make_pair((std::int64_t)-1, rel);
+    const float yaw = (float)((double)(shift * (360.0 / LMSF_SC_SECTORS)) * 3.14159265358979323846 / 180.0);  // deg2rad (:335)
+    const double c = std::cos((double)yaw), s = std::sin((double)yaw);
+    rel.linear()(0, 0) = c;
+    rel.linear()(0, 1) = -s;
+    rel.linear()(1, 0) = s;
+    rel.linear()(1, 1) = c;
+    return std::make_pair((std::int64_t)id, rel);
+  }
+  ContextPtr ctx_;
+  std::vector<std::string> target_names_;
+  int size_ = 0, limit_ = 0;
+  double last_dist_ = 0;
+  int last_shift_ = 0;
 };
 
 }  // namespace lmsf

@@ -61,5 +61,17 @@ int main(int argc, char** argv) {
               f0.pointcloud_data_["loam_surf"]->size(), f1.pointcloud_data_["loam_edge"]->size(),
               f1.pointcloud_data_["loam_surf"]->size(), surf_map->size());
   std::printf("pose %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
+
+  // place recognition as loopDetection.hpp drives SceneRecognitionScanContext: 60 keyframes (sweep 0, then sweep 1
+  // repeated), then the revisit query (sweep 0 again) and LoopDetect on a stored keyframe
+  lmsf::CudaSceneRecognitionScanContext<Pt> scene(ctx, {"loam_edge", "loam_surf"});
+  auto before = scene.FindSimilarPointCloud(f0.pointcloud_data_);
+  scene.AddKeyFramePoints(f0.pointcloud_data_);
+  for (int k = 1; k < 61; ++k) scene.AddKeyFramePoints(f1.pointcloud_data_);
+  auto hit = scene.FindSimilarPointCloud(f0.pointcloud_data_);
+  std::printf("loop %lld %lld %d %.17g %d\n", (long long)before.first, (long long)hit.first, scene.Size(),
+              scene.LastDistance(), scene.LastShift());
+  auto self = scene.LoopDetect(5);
+  std::printf("loopdetect %lld %.17g %d\n", (long long)self.first, scene.LastDistance(), scene.LastShift());
   return 0;
 }

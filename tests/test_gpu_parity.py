@@ -469,7 +469,13 @@ def test_cpp_adapters_match_ctypes_path(gpu_lib, sweeps, tmp_path):
     exe = os.path.join(entry.ROOT, "tests", "cpp", "adapter_smoke")
     r = subprocess.run([exe, str(f), str(len(s0)), str(len(s1)), "16"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    pose = np.array([float(x) for x in r.stdout.strip().splitlines()[-1].split()[1:]])
+    lines = {ln.split()[0]: ln.split()[1:] for ln in r.stdout.strip().splitlines()}
+    pose = np.array([float(x) for x in lines["pose"]])
+    # place recognition through the SceneRecognitionScanContext-shaped adapter: no tree before 51 keyframes, then the
+    # revisit of keyframe 0 is found with a zero column shift; LoopDetect(5) on a stored keyframe finds its twin
+    before, hit, size, dist, shift = lines["loop"]
+    assert int(before) == -1 and int(hit) == 0 and int(size) == 61 and float(dist) < 1e-12 and int(shift) == 0
+    assert int(lines["loopdetect"][0]) == 1 and float(lines["loopdetect"][1]) < 1e-12
     g = gpu_lib.context(0, n_scans=16)
     _, e0, f0 = g.extract_features(s0)
     v0, _ = g.voxel_downsample(f0, 0.4)
