@@ -143,8 +143,11 @@ __device__ __forceinline__ const CellRec* find_cell(const MapView& mv, const Map
   return r;
 }
 
+// `seeded`: the five slots were preloaded with real map points (the previous iteration's neighbours at their new
+// distances); those points are met again by the sweep and must not enter twice.  A candidate can only pass the
+// acceptance test of add() as a duplicate of slots 0..3 (slot 4 itself fails it), so four compares settle it.
 __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz,
-                                           Top5& nb KS_DECL) {
+                                           Top5& nb, bool seeded KS_DECL) {
   KSTAT(ks.cand += e - s;)
   for (int p = s; p < e; ++p) {
     float4 m = __ldg(&pts[p]);
@@ -152,7 +155,11 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s
     float r = dx * dx;
     r = r + dy * dy;
     r = r + dz * dz;
-    nb.add(r, __float_as_int(m.w));
+    const int ii = __float_as_int(m.w);
+    if (r < nb.d[4] || (r == nb.d[4] && ii < nb.id[4])) {
+      if (seeded && (ii == nb.id[0] || ii == nb.id[1] || ii == nb.id[2] || ii == nb.id[3])) continue;
+      nb.add(r, ii);
+    }
   }
 }
 
@@ -182,7 +189,7 @@ __device__ __forceinline__ L1Rec ldg_l1(const MapView& mv, int l1) {
 
 // scan the L2 cells of one L1 cell (absolute L1 coords ax1..az1) that survive the box test
 __device__ __forceinline__ void sweep_l1_cell(const MapView& mv, int l1, int ax1, int ay1, int az1, float qx, float qy,
-                                              float qz, Top5& nb KS_DECL) {
+                                              float qz, Top5& nb, bool seeded KS_DECL) {
   const L1Rec lr = ldg_l1(mv, l1);
   unsigned long long m2 = lr.mask;
   int base = lr.first;
@@ -195,7 +202,7 @@ __device__ __forceinline__ void sweep_l1_cell(const MapView& mv, int l1, int ax1
     if (!(box_d2(qx, qy, qz, ax2, ay2, az2, 0.0625f) > nb.d[4])) {
       int s = mv.l2_start[base + rank];
       int e = mv.l2_start[base + rank + 1];
-      scan_range(mv.sorted, s, e, qx, qy, qz, nb KS_PASS);
+      scan_range(mv.sorted, s, e, qx, qy, qz, nb, seeded KS_PASS);
     }
     ++rank;
   }
@@ -205,7 +212,7 @@ __device__ __forceinline__ void sweep_l1_cell(const MapView& mv, int l1, int ax1
 // running 5th distance, which only shrinks) around q, limited to +-R cells.  Each (z,y) row is a run
 // of x cells that crosses at most R/2+2 L1 cells; inside one L1 cell a run is one contiguous range.
 __device__ __forceinline__ void sweep_ball(const MapView& mv, const MapDev& md, CellCursor& cur, float qx, float qy,
-                                           float qz, int ax, int ay, int az, int R, Top5& nb KS_DECL) {
+                                           float qz, int ax, int ay, int az, int R, Top5& nb, bool seeded KS_DECL) {
   const int ox = md.min_c[0], oy = md.min_c[1], oz = md.min_c[2];
   for (int kz = 0; kz <= 2 * R; ++kz) {
     int dz = (kz + 1) >> 1;  // 0, +1, -1, +2, -2 ...: nearest layers first so the bound shrinks early
@@ -245,7 +252,7 @@ __device__ __forceinline__ void sweep_ball(const MapView& mv, const MapDev& md, 
         unsigned long long sub = m2 & ((2ull << fhi) - 1ull) & ~below;
         if (!sub) continue;
         int b = lr.first + __popcll(m2 & below);
-        scan_range(mv.sorted, mv.l2_start[b], mv.l2_start[b + __popcll(sub)], qx, qy, qz, nb KS_PASS);
+        scan_range(mv.sorted, mv.l2_start[b], mv.l2_start[b + __popcll(sub)], qx, qy, qz, nb, seeded KS_PASS);
       }
     }
   }
@@ -267,8 +274,12 @@ __device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, floa
   cur.key = ~0ull;
   cur.rec = nullptr;
   float bound = 2.0f;  // > 1: no usable bound yet
+  bool seeded = false;
   if (seed != nullptr && seed[4] >= 0) {
-    bound = 0.0f;
+    // preload the five slots with the seeds at their distances from this query: five real points, so the running
+    // 5th distance is a valid inclusive bound from the start and the sweep only inserts what beats them
+    // (all lanes of a seeded launch do this in step: no divergence)
+    float sd[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       float4 m = __ldg(&cat[seed[k]]);
@@ -276,12 +287,18 @@ __device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, floa
       float r = dx * dx;
       r = r + dy * dy;
       r = r + dz * dz;
-      bound = fmaxf(bound, r);
+      sd[k] = r;
     }
+    nb.reset_inclusive(__int_as_float(0x7f800000));
+#pragma unroll
+    for (int k = 0; k < 5; ++k) nb.add(sd[k], seed[k]);
+    bound = nb.d[4];
+    seeded = bound < 1.0f;  // a seed beyond the search radius cannot be a result: fall back to the unseeded search
+    if (!seeded) nb.reset();
   }
   if (!(bound < 1.0f)) {
     // ---- A: the 27 L2 cells around the query, no prior bound
-    sweep_ball(mv, md, cur, qx, qy, qz, ax, ay, az, 1, nb KS_PASS);
+    sweep_ball(mv, md, cur, qx, qy, qz, ax, ay, az, 1, nb, false KS_PASS);
     KSTAT(ks.level = 1;)
     if (nb.full()) {
       if (nb.d[4] < 0.00390625f) return;  // 5th distance < one L2 cell: nothing outside the 27 cells can be closer
@@ -291,17 +308,19 @@ __device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, floa
   if (bound < 0.0625f) {
     // ---- ball of known radius < 0.25 m: five points are known to lie within `bound` (inclusive)
     KSTAT(ks.level = 2;)
-    nb.reset_inclusive(bound);
+    if (!seeded) nb.reset_inclusive(bound);
     int R = (int)ceilf(sqrtf(bound) * 16.0f * 1.0001f) + 1;
-    sweep_ball(mv, md, cur, qx, qy, qz, ax, ay, az, R > 5 ? 5 : R, nb KS_PASS);
+    sweep_ball(mv, md, cur, qx, qy, qz, ax, ay, az, R > 5 ? 5 : R, nb, seeded KS_PASS);
     return;
   }
   // ---- sparse neighbourhood: restart, 27 L1 cells (B) then 27 L0 cells (C) with box pruning
   KSTAT(ks.level = 3;)
-  if (bound < 1.0f)
-    nb.reset_inclusive(bound);
-  else
-    nb.reset();
+  if (!seeded) {
+    if (bound < 1.0f)
+      nb.reset_inclusive(bound);
+    else
+      nb.reset();
+  }
   const int bx = ax >> 2, by = ay >> 2, bz = az >> 2;
   for (int k = 0; k < 27; ++k) {
     int x = bx + kNear27[k][0], y = by + kNear27[k][1], z = bz + kNear27[k][2];
@@ -313,7 +332,7 @@ __device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, floa
     unsigned long long m1 = rec->mask;
     if (!((m1 >> f1) & 1ull)) continue;
     int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
-    sweep_l1_cell(mv, l1, x, y, z, qx, qy, qz, nb KS_PASS);
+    sweep_l1_cell(mv, l1, x, y, z, qx, qy, qz, nb, seeded KS_PASS);
   }
   if (nb.full() && nb.d[4] < 0.0625f) return;
   KSTAT(ks.level = 4;)
@@ -333,7 +352,7 @@ __device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, floa
       bool seen = (x1 >= bx - 1 && x1 <= bx + 1 && y1 >= by - 1 && y1 <= by + 1 && z1 >= bz - 1 && z1 <= bz + 1);
       KSTAT(ks.boxes++;)
       if (!seen && !(box_d2(qx, qy, qz, x1, y1, z1, 0.25f) > nb.d[4]))
-        sweep_l1_cell(mv, l1, x1, y1, z1, qx, qy, qz, nb KS_PASS);
+        sweep_l1_cell(mv, l1, x1, y1, z1, qx, qy, qz, nb, seeded KS_PASS);
       ++l1;
     }
   }
