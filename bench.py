@@ -31,6 +31,7 @@ import __graft_entry__ as entry  # noqa: E402
 METRIC = "scan-to-map registrations/sec (HDL-64 synthetic)"
 UNIT = "scans/s"
 SENSOR = "hdl64"
+FLUSH_BYTES = 192 << 20   # written between timed steps: 1.5x the 126 MB L2
 STATE_D2H_BYTES = 880 + 8  # sizeof(SolveState) + the two feature counts, read back once per sweep
 
 
@@ -136,7 +137,7 @@ def run_ours(args):
     pkg = entry.load_package()
     ctx = pkg.context(local, n_scans=64, max_points=1 << 18)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
     n_pts = [int(s.shape[0]) for s in sweeps]
 
     sampler = ClockSampler(local)
@@ -192,13 +193,17 @@ def run_ours(args):
     # on the context's front-end stream), then registers the current one — the reference's own two-thread pipeline
     # (sensor thread: Process; estimate_thread_: Solve).  Each timed step therefore still contains exactly one
     # upload (e2e pass), one feature extraction and one registration.
+    # The step is issued in its two halves (lmsf_tracker_submit / lmsf_tracker_wait == lmsf_tracker_step) so that the
+    # host enqueues the next sweep's front end while the GPU registers the current one.
     def step_dev(k, t):
+        ctx.tracker_submit_dev(d_ptrs[k], n_pts[k], t)
         ctx.tracker_prefetch_dev(d_ptrs[k + 1], n_pts[k + 1])
-        return ctx.tracker_step_dev(d_ptrs[k], n_pts[k], t)[2]
+        return ctx.tracker_wait()[2]
 
     def step_host(k, t):
+        ctx.tracker_submit(sweeps[k], t)
         ctx.tracker_prefetch(sweeps[k + 1])
-        return ctx.tracker_step(sweeps[k], t)[2]
+        return ctx.tracker_wait()[2]
 
     run_sequence(step_dev, False, K=2)
     dev_ms, wall_ms, per, launches, _, stats, fl1 = run_sequence(step_dev, False)
@@ -234,7 +239,7 @@ def run_ours(args):
             "config": {"workload": "HDL-64 synthetic 64x2048 sweep (~131k pts) scan-to-map edge/surf registration, "
                                    "Huber-LM solver, raw 10-keyframe sliding-window map, one sequence per GPU",
                        "points_per_sweep": int(np.mean(n_pts)), "sequences": n_gpus,
-                       "l2": "256 MiB memset between timed steps (L2 flush), inside the timed region",
+                       "l2": f"{FLUSH_BYTES >> 20} MiB memset between timed steps (L2 flush: 1.5x the 126 MB L2), inside the timed region",
                        "timing": "CUDA events on the context stream around the K steps, max over ranks",
                        "pipeline": "front end (extraction of sweep k+1) overlaps the registration of sweep k",
                        "p50_ms_per_scan": float(np.median(per)), "p90_ms_per_scan": float(np.percentile(per, 90)),
@@ -248,7 +253,7 @@ def run_ours(args):
             "e2e": {"value": n_gpus * K / (e2e_ms_max * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(np.mean(n_pts)) * 16, "d2h_bytes_per_step": STATE_D2H_BYTES,
                     "p50_ms_per_scan": float(np.median(e_per)),
-                    "api": "lmsf_tracker_prefetch(next host sweep) + lmsf_tracker_step(host sweep in, pose out), "
+                    "api": "lmsf_tracker_submit(host sweep) + lmsf_tracker_prefetch(next host sweep) + lmsf_tracker_wait(pose out), "
                            "wall clock around K steps, max over ranks"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
@@ -394,7 +399,7 @@ def run_loopdb(args):
     h_qk = torch.from_numpy(qk).pin_memory()
     h_qd = torch.from_numpy(qd.reshape(LOOP_NQ, 1200)).pin_memory()
     d_qk, d_qd = h_qk.to(dev), h_qd.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local)
     sampler.start()
     l0 = None
@@ -455,7 +460,7 @@ def run_loopdb(args):
                                    "one all_gather of 24-byte candidates, identical selection on every rank",
                        "database": LOOP_DB, "searched_prefix": int(limit), "queries_per_step": LOOP_NQ,
                        "shard": [int(lo), int(hi)], "recall_of_planted_revisits": hit,
-                       "l2": "256 MiB memset between timed steps (L2 flush), inside the timed region",
+                       "l2": f"{FLUSH_BYTES >> 20} MiB memset between timed steps (L2 flush), inside the timed region",
                        "bound_note": "the ring-key scan is fp32-ALU bound (60 non-fused flops per key pair), not HBM bound"},
             "e2e": {"value": LOOP_NQ * K / (e2e_ms_max * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": LOOP_NQ * (80 + 4800), "d2h_bytes_per_step": LOOP_NQ * 16,

@@ -171,6 +171,14 @@ int lmsf_tracker_step_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp,
  * prefetched one is dropped).  The caller must not modify a prefetched host buffer before that step. */
 int lmsf_tracker_prefetch(lmsf_ctx* c, const float* xyzi, int n);
 int lmsf_tracker_prefetch_dev(lmsf_ctx* c, const float* d_xyzi, int n);
+/* lmsf_tracker_step in two halves, for callers that have host work to do while the GPU registers the sweep
+ * (typically: prefetch the next one).  submit = prediction + the whole registration enqueued, returns at once;
+ * wait = pose read-back, motion update, keyframe test, local-map update.  One sweep in flight per context:
+ * a second submit, or any call that rewrites the feature slot in use, returns LMSF_ERR_STATE until wait.
+ * lmsf_tracker_step(x) == lmsf_tracker_submit(x) + lmsf_tracker_wait(). */
+int lmsf_tracker_submit(lmsf_ctx* c, const float* xyzi, int n, double stamp, const double delta[7]);
+int lmsf_tracker_submit_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp, const double delta[7]);
+int lmsf_tracker_wait(lmsf_ctx* c, double delta_out[7], double pose_out[7], lmsf_track_stats* st);
 /* Same, fed with features instead of a raw sweep — the exact argument of
  * LidarTrackerLocalMap::Solve. */
 int lmsf_tracker_step_features(lmsf_ctx* c, const float* edge_xyzi, int n_e, const float* surf_xyzi,

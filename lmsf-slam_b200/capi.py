@@ -128,6 +128,7 @@ class Library:
     # symbols only the CUDA library exports
     DEVICE_ONLY = (
         "last_cuda_error", "launch_count", "stream", "tracker_step_dev", "tracker_prefetch", "tracker_prefetch_dev",
+        "tracker_submit", "tracker_submit_dev", "tracker_wait",
         "dev_alloc", "dev_free",
         "dev_upload", "profile_enable", "profile_read",
         # loop-closure descriptor path (scancontext.cu)
@@ -155,6 +156,9 @@ class Library:
                                               C.POINTER(TrackStats)]
             f("tracker_prefetch").argtypes = [C.c_void_p, _f32p, C.c_int]
             f("tracker_prefetch_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+            f("tracker_submit").argtypes = [C.c_void_p, _f32p, C.c_int, C.c_double, _f64p]
+            f("tracker_submit_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, _f64p]
+            f("tracker_wait").argtypes = [C.c_void_p, _f64p, _f64p, C.POINTER(TrackStats)]
             f("dev_alloc").argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
             f("dev_free").argtypes = [C.c_void_p, C.c_void_p]
             f("dev_upload").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
@@ -340,6 +344,28 @@ class Context:
 
     def tracker_prefetch_dev(self, d_ptr: int, n: int):
         self._chk(self.lib.fn("tracker_prefetch_dev")(self._h, C.c_void_p(d_ptr), n))
+
+    def tracker_submit(self, xyzi, stamp: float, delta=IDENTITY_POSE):
+        """First half of tracker_step: everything enqueued, nothing waited for (host array as for tracker_prefetch)."""
+        a = xyzi
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous and a.ndim == 2
+                and a.shape[1] == 4):
+            raise ValueError("tracker_submit needs a C-contiguous (n, 4) float32 array")
+        d = np.array(delta, dtype=np.float64)
+        self._chk(self.lib.fn("tracker_submit")(self._h, _fp(a), a.shape[0], float(stamp), d.ctypes.data_as(_f64p)))
+
+    def tracker_submit_dev(self, d_ptr: int, n: int, stamp: float, delta=IDENTITY_POSE):
+        d = np.array(delta, dtype=np.float64)
+        self._chk(self.lib.fn("tracker_submit_dev")(self._h, C.c_void_p(d_ptr), n, float(stamp),
+                                                    d.ctypes.data_as(_f64p)))
+
+    def tracker_wait(self):
+        """Second half of tracker_step: (pose, motion increment, statistics) of the submitted sweep."""
+        d = np.zeros(7, np.float64)
+        p = np.zeros(7, np.float64)
+        st = TrackStats()
+        self._chk(self.lib.fn("tracker_wait")(self._h, d.ctypes.data_as(_f64p), p.ctypes.data_as(_f64p), C.byref(st)))
+        return p, d, st.as_dict()
 
     def tracker_step_features(self, edge, surf, stamp: float, delta=IDENTITY_POSE):
         e, s = _xyzi(edge), _xyzi(surf)

@@ -206,12 +206,39 @@ static int scan_filter(Ctx* c) {
   return set_counts(c, ne2, ns2);
 }
 
-// LidarTrackerLocalMap::Solve (:107-160); features already in d_feat, counts on the device
-static int tracker_core(Ctx* c, int upper, double stamp, double delta[7], double pose_out[7], lmsf_track_stats* out) {
+// LidarTrackerLocalMap::Solve (:107-160) in two halves; features already in d_feat, counts on the device.
+// tracker_begin: prediction + the whole registration enqueued on the main stream, no host wait.
+static int tracker_begin(Ctx* c, int upper, double stamp, const double delta[7]) {
+  if (c->pending.active) return LMSF_ERR_STATE;  // one sweep in flight per tracker
+  LM_TRY(scan_filter(c));
+  c->pending = Ctx::Pending();
+  c->pending.stamp = stamp;
+  if (!c->init) {
+    c->pending.first = true;
+    c->pending.active = true;
+    return LMSF_OK;
+  }
+  bool ident = delta[0] == 0 && delta[1] == 0 && delta[2] == 0 && delta[3] == 1 && delta[4] == 0 && delta[5] == 0 &&
+               delta[6] == 0;
+  c->curr = ident ? rigid_mul(c->prev, c->motion) : rigid_mul(c->prev, rigid_from_pose(delta));
+  double p[7];
+  rigid_to_pose(c->curr, p);  // Quaterniond(T.rotation())
+  LM_TRY(wait_map(c));  // the previous keyframe's index rebuild (map stream) must be complete
+  c->pending.solver = c->prm.solver;
+  c->pending.outer = (c->prm.solver == LMSF_SOLVER_GN) ? c->prm.gn_max_iters : next_lm_outer(c);
+  LM_TRY(solve_enqueue(c, c->pending.solver, p, upper, c->pending.outer));
+  c->pending.active = true;
+  return LMSF_OK;
+}
+
+// tracker_end: wait for the pose, motion update, keyframe test (:239-262), local-map update (:205-232)
+static int tracker_end(Ctx* c, double delta[7], double pose_out[7], lmsf_track_stats* out) {
+  if (!c->pending.active) return LMSF_ERR_STATE;
+  c->pending.active = false;
+  const double stamp = c->pending.stamp;
   lmsf_track_stats s;
   memset(&s, 0, sizeof s);
-  LM_TRY(scan_filter(c));
-  if (!c->init) {
+  if (c->pending.first) {
     LM_TRY(fetch_counts(c));
     LM_TRY(update_map(c, rigid_identity(), 1));
     c->curr = c->prev = c->motion = c->last_kf = rigid_identity();
@@ -220,14 +247,9 @@ static int tracker_core(Ctx* c, int upper, double stamp, double delta[7], double
     s.first = 1;
     s.keyframe = 1;
   } else {
-    bool ident = delta[0] == 0 && delta[1] == 0 && delta[2] == 0 && delta[3] == 1 && delta[4] == 0 && delta[5] == 0 &&
-                 delta[6] == 0;
-    c->curr = ident ? rigid_mul(c->prev, c->motion) : rigid_mul(c->prev, rigid_from_pose(delta));
     double p[7];
-    rigid_to_pose(c->curr, p);  // Quaterniond(T.rotation())
-    LM_TRY(wait_map(c));  // the previous keyframe's index rebuild (map stream) must be complete
     const auto h0 = std::chrono::steady_clock::now();
-    LM_TRY(run_solver(c, c->prm.solver, p, &s.reg, upper));  // leaves n_edge / n_surf on the host
+    LM_TRY(solve_finish(c, c->pending.solver, p, &s.reg, c->pending.outer));  // leaves n_edge / n_surf on the host
     c->host_us[0] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count();
     c->host_n[0] += 1;
     c->curr = rigid_from_pose(p);  // T.linear() = q.toRotationMatrix()
@@ -239,9 +261,9 @@ static int tracker_core(Ctx* c, int upper, double stamp, double delta[7], double
     if (ut) {
       c->last_kf = c->curr;
       c->last_kf_time = stamp;
-      const auto h0 = std::chrono::steady_clock::now();
+      const auto h1 = std::chrono::steady_clock::now();
       LM_TRY(update_map(c, c->curr, ut));
-      c->host_us[1] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count();
+      c->host_us[1] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h1).count();
       c->host_n[1] += 1;
     }
   }
@@ -252,6 +274,11 @@ static int tracker_core(Ctx* c, int upper, double stamp, double delta[7], double
   rigid_to_pose(c->curr, pose_out);
   if (out) *out = s;
   return LMSF_OK;
+}
+
+static int tracker_core(Ctx* c, int upper, double stamp, double delta[7], double pose_out[7], lmsf_track_stats* out) {
+  LM_TRY(tracker_begin(c, upper, stamp, delta));
+  return tracker_end(c, delta, pose_out, out);
 }
 
 // make slot `si` the one the main stream works on (d_feat / ex.counts alias it)
@@ -275,6 +302,7 @@ static int writable_slot(Ctx* c) {
 static int upload_features(Ctx* c, const float* edge, int n_e, const float* surf, int n_s) {
   if (n_e < 0 || n_s < 0 || (n_e > 0 && !edge) || (n_s > 0 && !surf)) return LMSF_ERR_INVALID;
   if (n_e + n_s > c->prm.max_points) return LMSF_ERR_CAPACITY;
+  if (c->pending.active) return LMSF_ERR_STATE;
   alias_slot(c, writable_slot(c));
   LM_TRY(wait_feat(c));
   c->feat_from_extract = false;  // caller-supplied features: arbitrary coordinates, the map update stays synchronous
@@ -336,6 +364,7 @@ static int adopt_slot(Ctx* c, int si) {
 
 // extraction for the synchronous entry points: main stream ordered behind it
 static int extract_current(Ctx* c, const float* xyzi, int n, bool host) {
+  if (c->pending.active) return LMSF_ERR_STATE;  // a submitted sweep is still reading its feature slot
   const int si = writable_slot(c);
   LM_TRY(extract_into_slot(c, si, xyzi, n, host));
   return adopt_slot(c, si);
@@ -347,6 +376,7 @@ static int prefetch(Ctx* c, const float* xyzi, int n, bool host) {
   int si = c->slot_cur ^ 1;
   if (c->slot[si].filled) si = c->slot_cur;
   if (c->slot[si].filled) return LMSF_ERR_STATE;  // two sweeps already waiting for their tracker step
+  if (c->pending.active && si == c->slot_cur) return LMSF_ERR_STATE;  // that slot feeds the solve in flight
   LM_TRY(extract_into_slot(c, si, xyzi, n, host));
   c->slot[si].filled = true;
   c->slot[si].src = xyzi;
@@ -696,6 +726,30 @@ int lmsf_tracker_step_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp,
   return tracker_core(c, n, stamp, delta, pose_out, st);
 }
 
+int lmsf_tracker_submit(lmsf_ctx* c, const float* xyzi, int n, double stamp, const double delta[7]) {
+  ENTER(c);
+  if (!delta) return LMSF_ERR_INVALID;
+  if (c->pending.active) return LMSF_ERR_STATE;
+  LM_TRY(take_sweep(c, xyzi, n, true));
+  return tracker_begin(c, n, stamp, delta);
+}
+
+int lmsf_tracker_submit_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp, const double delta[7]) {
+  ENTER(c);
+  if (!delta || n < 0 || (n > 0 && !d_xyzi)) return LMSF_ERR_INVALID;
+  if (c->pending.active) return LMSF_ERR_STATE;
+  LM_TRY(take_sweep(c, d_xyzi, n, false));
+  return tracker_begin(c, n, stamp, delta);
+}
+
+int lmsf_tracker_wait(lmsf_ctx* c, double delta_out[7], double pose_out[7], lmsf_track_stats* st) {
+  ENTER(c);
+  if (!delta_out || !pose_out) return LMSF_ERR_INVALID;
+  const double ident[7] = {0, 0, 0, 1, 0, 0, 0};  // the initialising sweep has no motion increment
+  for (int i = 0; i < 7; ++i) delta_out[i] = ident[i];
+  return tracker_end(c, delta_out, pose_out, st);
+}
+
 int lmsf_tracker_prefetch(lmsf_ctx* c, const float* xyzi, int n) {
   ENTER(c);
   return prefetch(c, xyzi, n, true);
@@ -720,6 +774,7 @@ int lmsf_tracker_reset(lmsf_ctx* c) {
   LM_CUDA(cudaStreamSynchronize(c->stream_map));
   LM_CUDA(cudaStreamSynchronize(c->stream));
   c->map_pending = false;
+  c->pending = Ctx::Pending();
   for (int i = 0; i < 2; ++i) c->slot[i].freed_pending = c->slot[i].filled = false;
   c->init = false;
   for (int k = 0; k < 2; ++k) {

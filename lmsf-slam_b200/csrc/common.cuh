@@ -231,6 +231,12 @@ struct Ctx {
   SolveState* h_state = nullptr;
 
   // tracker (LidarTrackerLocalMap members)
+  struct Pending {            // a submitted sweep whose pose has not been waited for (lmsf_tracker_submit / _wait)
+    bool active = false;
+    bool first = false;       // the initialising sweep: nothing was enqueued
+    double stamp = 0;
+    int solver = 0, outer = 0;
+  } pending;
   bool init = false;
   rigid prev, curr, motion, last_kf;
   double last_kf_time = 0;
@@ -306,6 +312,9 @@ int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double
 // features in c->d_feat (counts in c->ex.counts on the device; `upper` bounds their sum on the
 // host); enqueues the whole solve, reads pose + statistics back (one stream sync)
 int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* st, int upper, int outer_count);
+// the two halves of solve_run: enqueue everything (no host wait) / wait for the pose and read the statistics
+int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer_count);
+int solve_finish(Ctx* c, int solver, double pose[7], lmsf_reg_stats* st, int outer_count);
 
 }  // namespace lm
 

@@ -1248,9 +1248,14 @@ extern "C" int lmsf_debug_kernel_times(unsigned long long out[32], int reset) {
 }
 #endif
 
-// Enqueue one whole solve on the stream, then read pose + statistics back (one sync).
-// upper = host-side upper bound of n_edge + n_surf (the device counts are authoritative).
+// Enqueue one whole solve on the stream (solve_enqueue), then read pose + statistics back with one sync
+// (solve_finish).  upper = host-side upper bound of n_edge + n_surf (the device counts are authoritative).
 int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upper, int outer_count) {
+  LM_TRY(solve_enqueue(c, solver, pose, upper, outer_count));
+  return solve_finish(c, solver, pose, stats, outer_count);
+}
+
+int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer_count) {
   if (upper < 0 || outer_count < 0) return LMSF_ERR_INVALID;
   if (upper > c->prm.max_points) return LMSF_ERR_CAPACITY;
   const auto h_enq0 = std::chrono::steady_clock::now();
@@ -1344,6 +1349,10 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
   c->host_n[2] += 1;
   LM_CUDA(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
   LM_CUDA(cudaMemcpyAsync(c->h_ints + 32, c->ex.counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  return LMSF_OK;
+}
+
+int solve_finish(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int outer_count) {
   LM_CUDA(cudaStreamSynchronize(c->stream));
   c->n_edge = c->h_ints[32];
   c->n_surf = c->h_ints[33];

@@ -27,9 +27,10 @@ kf = []
 t00 = time.perf_counter()
 for k in range(10, 10 + n):
     t0 = time.perf_counter()
+    ctx.tracker_submit_dev(d[k], len(sweeps[k]), 0.1 * k)
     ctx.tracker_prefetch_dev(d[k + 1], len(sweeps[k + 1]))
     t1 = time.perf_counter()
-    _, _, st = ctx.tracker_step_dev(d[k], len(sweeps[k]), 0.1 * k)
+    _, _, st = ctx.tracker_wait()
     t2 = time.perf_counter()
     per.append(((t1 - t0) * 1e6, (t2 - t1) * 1e6))
     kf.append(st["keyframe"])
@@ -38,7 +39,7 @@ ctx.lib.dll.lmsf_debug_host_times(ctx._h, us, cnt, 1)
 per = np.array(per)
 kf = np.array(kf) > 0
 print(f"steps {n}, keyframes {kf.sum()}, wall per step {tot:.0f} us")
-print(f"prefetch call: {per[:, 0].mean():.0f} us; step call: {per[:, 1].mean():.0f} us (KF steps {per[kf, 1].mean():.0f}, others {per[~kf, 1].mean():.0f})")
+print(f"submit + prefetch calls: {per[:, 0].mean():.0f} us; wait call: {per[:, 1].mean():.0f} us (KF steps {per[kf, 1].mean():.0f}, others {per[~kf, 1].mean():.0f})")
 print(f"step call following a KF step: {per[1:][kf[:-1], 1].mean():.0f} us, following a non-KF step: {per[1:][~kf[:-1], 1].mean():.0f} us")
 for i, name in enumerate(["solve (enqueue + wait)", "map update enqueue", "solve enqueue only"]):
     if cnt[i]:

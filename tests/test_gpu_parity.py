@@ -396,8 +396,13 @@ def test_tracker_prefetch_pipeline_is_bit_identical(gpu_lib, sweeps, name, ns, n
             elif k != 2:
                 b.tracker_prefetch(seq[k + 1])
             pb, db, sb = b.tracker_step(seq[k], 0.1 * k)
+            # c: resident sweeps, the step in its two halves with the next sweep's prefetch in between
+            c.tracker_submit_dev(d_ptrs[k], len(seq[k]), 0.1 * k)
             c.tracker_prefetch_dev(d_ptrs[k + 1], len(seq[k + 1]))
-            pc, dc, sc = c.tracker_step_dev(d_ptrs[k], len(seq[k]), 0.1 * k)
+            if k == 1:
+                with pytest.raises(Exception):      # one sweep in flight: a second submit is refused
+                    c.tracker_submit_dev(d_ptrs[k], len(seq[k]), 0.1 * k)
+            pc, dc, sc = c.tracker_wait()
             assert np.array_equal(pa, pb) and np.array_equal(da, db) and sa == sb, k
             assert np.array_equal(pa, pc) and np.array_equal(da, dc) and sa == sc, k
         for kind in (0, 1):
