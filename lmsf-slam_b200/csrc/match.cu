@@ -897,10 +897,13 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
 #ifndef KNN_MINBLOCKS
 #define KNN_MINBLOCKS 1
 #endif
-__global__ void __launch_bounds__(128, KNN_MINBLOCKS) k_knn(const int* __restrict__ perm, const float4* __restrict__ pw,
+// assoc != 0 (ring-order launches): the kernel also does k_assoc's work for its own query — pointAssociateToMap in
+// fp64, stored as fp32 in pw[] for k_fit — so no separate launch is needed.
+__global__ void __launch_bounds__(128, KNN_MINBLOCKS) k_knn(const int* __restrict__ perm, float4* __restrict__ pw,
+                                             const float4* __restrict__ feat,
                                              const int* __restrict__ counts, SolveState* __restrict__ st,
                                              MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
-                                             int seeded, int reverse, int* __restrict__ nbr) {
+                                             int seeded, int reverse, int assoc, int* __restrict__ nbr) {
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   const int n_e = counts[0], n_s = counts[1];
   const int lane = threadIdx.x & 31;
@@ -935,8 +938,22 @@ __global__ void __launch_bounds__(128, KNN_MINBLOCKS) k_knn(const int* __restric
     const bool is_edge = f < n_e;
     Top5 nb;
     nb.reset();
+    float4 w;
+    if (assoc) {
+      quat q;
+      q.x = st->x[0];
+      q.y = st->x[1];
+      q.z = st->x[2];
+      q.w = st->x[3];
+      d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
+      float4 fp = feat[f];
+      d3 pwd = add3(qrot(q, mk3((double)fp.x, (double)fp.y, (double)fp.z)), tr);
+      w = make_float4((float)pwd.x, (float)pwd.y, (float)pwd.z, 0.f);
+      pw[f] = w;
+    } else {
+      w = pw[f];
+    }
     if (is_edge ? has_edge_map : has_surf_map) {
-      float4 w = pw[f];
       int seed[5];
 #pragma unroll
       for (int k = 0; k < 5; ++k) seed[k] = seeded ? nbr[k * upper + t] : -1;
@@ -1044,6 +1061,8 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
   if (threadIdx.x == 0) {
     sh.n_edge_ok = (int)tot[29];
     sh.n_surf_ok = (int)tot[28] - (int)tot[29];
+    sh.knn_next = 0;  // work-queue heads of the next k_knn launch (k_assoc does it when it runs)
+    sh.knn_next_heavy = 0;
   }
   if (sp.solver == LMSF_SOLVER_GN) {
     if (threadIdx.x == 0) gn_step(&sh, tot, sp);
@@ -1315,8 +1334,9 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       // outer iterations (the pose moves by millimetres between them), which also keeps the sorted position
       // of a feature stable so that k_knn can seed its search with the previous iteration's neighbours
       StageScope scope(c, LMSF_STAGE_ASSOC);
-      LM_LAUNCH(c, k_assoc, div_up(up, 256), 256, 0, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, qorg, up,
-                solver, (it == 0 && !ring_order) ? 1 : 0, qb);
+      if (!ring_order)
+        LM_LAUNCH(c, k_assoc, div_up(up, 256), 256, 0, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, qorg, up,
+                  solver, it == 0 ? 1 : 0, qb);
       if (it == 0 && !ring_order) {
         size_t tmp = c->cub_tmp_bytes;
         LM_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, (unsigned*)c->q_keys, (unsigned*)c->q_keys_alt,
@@ -1328,8 +1348,8 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       StageScope scope(c, LMSF_STAGE_MATCH);
       int knn_grid = div_up(up, 128);
       if (knn_grid > 148 * knn_per_sm) knn_grid = 148 * knn_per_sm;  // persistent: every resident warp pulls work
-      LM_LAUNCH(c, k_knn, knn_grid, 128, 0, perm, c->d_pw, c->ex.counts, c->d_state, maps, he, hs, up,
-                solver, it == 0 ? 0 : 1, (ring_order && knn_reverse) ? 1 : 0, c->d_nbr);
+      LM_LAUNCH(c, k_knn, knn_grid, 128, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, up,
+                solver, it == 0 ? 0 : 1, (ring_order && knn_reverse) ? 1 : 0, ring_order ? 1 : 0, c->d_nbr);
       c->match_bytes += alg_bytes;
       c->match_launches += 1;
     }
