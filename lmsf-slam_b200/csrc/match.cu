@@ -929,6 +929,7 @@ __global__ void __launch_bounds__(128, KNN_MINBLOCKS) k_knn(const int* __restric
       base = __shfl_sync(0xffffffffu, base, 0);
       if (base >= live) break;
     }
+    TSTAMP(t_chunk0);
     // (handing the chunks out from the end — high rings first — was measured: 802 vs 753 us per sweep; kept as a
     //  tuning switch only)
     int t = (reverse ? ((live + 31) / 32) * 32 - 32 - base : base) + lane;
@@ -963,6 +964,16 @@ __global__ void __launch_bounds__(128, KNN_MINBLOCKS) k_knn(const int* __restric
     const bool full = nb.full();
 #pragma unroll
     for (int k = 0; k < 5; ++k) nbr[k * upper + t] = full ? nb.id[k] : -1;
+#ifdef LMSF_TIMING
+    {
+      unsigned long long t1 = gtime(), dt = t1 - t_chunk0;  // per lane: from chunk start to this lane's finish
+      atomicMax(&g_dbg[8], dt);
+      atomicAdd(&g_dbg[9], dt);
+      atomicAdd(&g_dbg[10], 1ull);
+      int bucket = dt < 20000 ? 0 : (dt < 40000 ? 1 : (dt < 80000 ? 2 : (dt < 160000 ? 3 : 4)));
+      atomicAdd(&g_dbg[11 + bucket], 1ull);
+    }
+#endif
   }
 }
 

@@ -26,3 +26,6 @@ for name, b in (("k_fit", 0), ("k_lm_eval (active)", 4)):
     c = max(1, o[b + 3])
     print(f"{name}: {o[b + 3]} launches; last block: loop {o[b] / c / 1e3:.1f} us, reduce+wait {o[b + 1] / c / 1e3:.1f} us, "
           f"tail {o[b + 2] / c / 1e3:.1f} us")
+c = max(1, o[10])
+print(f"k_knn lanes: {o[10]} queries; time from chunk start to the lane's finish: mean {o[9] / c / 1e3:.1f} us, max {o[8] / 1e3:.1f} us; "
+      f"histogram <20/<40/<80/<160/>=160 us: {[o[11 + i] for i in range(5)]}")
