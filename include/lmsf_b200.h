@@ -142,6 +142,15 @@ int lmsf_knn5(lmsf_ctx* c, int kind, const float* q_xyz, int nq, int32_t* idx5, 
  * (surfFeatureMatch.hpp:32-87) on world-frame fp32 points.  out10 per query:
  * kind 0: {nx,ny,nz, r, ax,ay,az, bx,by,bz}; kind 1: {nx,ny,nz, r, D, 0,0,0,0,0}. */
 int lmsf_match(lmsf_ctx* c, int kind, const float* q_xyz, int nq, uint8_t* ok, double* out10);
+/* = PointCloudAlignmentEvaluate::AlignmentScore (registration/alignEvaluate.hpp:55-87) against the map index
+ * `kind` (SetTargetPoints :42-46 = lmsf_map_set): the cloud is transformed by the row-major 4x4 fp32 relpose
+ * (pcl::transformPointCloud with a Matrix4f), every point looks up its nearest target point, points with
+ * squared distance <= inlier_thresh are inliers.  overlap = inliers / n; score = mean inlier squared distance
+ * when overlap > inlier_ratio_thresh, else DBL_MAX (also for an empty cloud).  inlier_thresh must be <= 1.0
+ * (the reference's callers use 0.1 and 1, loopDetection.hpp:177-178,411-412, backend_lifelong.hpp:319-320). */
+int lmsf_align_score(lmsf_ctx* c, int kind, const float* xyzi, int n, const float relpose16[16],
+                     double inlier_thresh, double inlier_ratio_thresh, double* score, double* overlap,
+                     int32_t* n_inlier);
 /* = SetInputTarget + Solve (registration_base.hpp:32-33): pose holds the
  * prediction on entry and the result on return.  solver: LMSF_SOLVER_*; the
  * Huber-LM outer-iteration budget is context state, as in the reference. */

@@ -10,6 +10,8 @@
 //        replaces  CeresEdgeSurfFeatureRegistration / EdgeSurfFeatureRegistration
 //                                             (registration/ceres_edgeSurfFeatureRegistration.hpp:26,
 //                                              edgeSurfFeatureRegistration.hpp:27, built at ML_SystemFactory.hpp:189-190)
+//   lmsf::CudaPointCloudAlignmentEvaluate<P>   (no abstract base in the reference: same public methods)
+//        replaces  Slam3D::PointCloudAlignmentEvaluate   (registration/alignEvaluate.hpp:23-98)
 //   lmsf::CudaSceneRecognitionScanContext<P>   (no abstract base in the reference: same public methods)
 //        replaces  Slam3D::SceneRecognitionScanContext   (LoopDetection/SceneRecognitionScanContext.hpp:21-345)
 //
@@ -247,6 +249,45 @@ class CudaEdgeSurfRegistration : public Algorithm::RegistrationBase<_PointType> 
   int solver_;
   typename pcl::PointCloud<_PointType>::ConstPtr edge_in_, surf_in_;
   lmsf_reg_stats last_{};
+};
+
+// ---------------------------------------------------------------- alignment score (row f2)
+// Same public surface as Slam3D::PointCloudAlignmentEvaluate<_PointT> (registration/alignEvaluate.hpp:23-98): the
+// target cloud becomes a device index (map slot `kind` of the context: use a context of its own, or a slot the
+// tracker does not need), the score is computed on the device.
+template <typename _PointT>
+class CudaPointCloudAlignmentEvaluate {
+ public:
+  explicit CudaPointCloudAlignmentEvaluate(ContextPtr ctx, std::string name = "processed", int kind = LMSF_KIND_SURF)
+      : ctx_(std::move(ctx)), name_(std::move(name)), kind_(kind) {}
+  std::string GetTargetName() const { return name_; }
+  void SetTargetPoints(typename pcl::PointCloud<_PointT>::ConstPtr const& cloud) {
+    std::vector<float> buf;
+    detail::pack(*cloud, buf);
+    set_target_ = detail::check(lmsf_map_set(ctx_->get(), kind_, buf.data(), (int)cloud->points.size()), "lmsf_map_set");
+  }
+  // (mean squared distance of the inliers, overlap ratio); (DBL_MAX, ratio) when the overlap is too small (:82-85)
+  std::pair<double, double> AlignmentScore(typename pcl::PointCloud<_PointT>::ConstPtr const& cloud,
+                                           Eigen::Matrix4f const& relpose, double const& inlier_thresh,
+                                           double const& inlier_ratio_thresh) {
+    const double none = 1.7976931348623157e308;
+    if (!set_target_ || cloud->empty()) return std::make_pair(none, 0.0);
+    std::vector<float> buf;
+    detail::pack(*cloud, buf);
+    float T[16];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) T[r * 4 + c] = relpose(r, c);
+    double score = none, overlap = 0;
+    if (!detail::check(lmsf_align_score(ctx_->get(), kind_, buf.data(), (int)cloud->points.size(), T, inlier_thresh,
+                                        inlier_ratio_thresh, &score, &overlap, nullptr), "lmsf_align_score"))
+      return std::make_pair(none, 0.0);
+    return std::make_pair(score, overlap);
+  }
+ private:
+  ContextPtr ctx_;
+  std::string name_;
+  int kind_;
+  bool set_target_ = false;
 };
 
 // ---------------------------------------------------------------- loop-closure place recognition (row f1)

@@ -58,6 +58,12 @@ struct Vector3dLite {
   double& operator[](int i) { return v[i]; }
   double operator[](int i) const { return v[i]; }
 };
+struct Matrix4f {  // row/column access only: what AlignmentScore's relpose argument needs
+  float m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  float& operator()(int r, int c) { return m[r * 4 + c]; }
+  float operator()(int r, int c) const { return m[r * 4 + c]; }
+  static Matrix4f Identity() { return Matrix4f(); }
+};
 class Isometry3d {
  public:
   static Isometry3d Identity() { return Isometry3d(); }

@@ -123,7 +123,7 @@ class Library:
     COMMON = (
         "params_default", "ctx_create", "ctx_destroy", "strerror", "extract_features",
         "voxel_downsample", "map_set", "knn5", "match", "register", "set_lm_outer",
-        "tracker_step", "tracker_step_features", "tracker_reset", "tracker_register_aux", "get_map",
+        "tracker_step", "tracker_step_features", "tracker_reset", "tracker_register_aux", "get_map", "align_score",
     )
     # symbols only the CUDA library exports
     DEVICE_ONLY = (
@@ -197,6 +197,8 @@ class Library:
         f("tracker_reset").argtypes = [C.c_void_p]
         f("tracker_register_aux").argtypes = [C.c_void_p, _f32p, C.c_int, _f64p, C.POINTER(RegStats)]
         f("get_map").argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int, _intp]
+        f("align_score").argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int, _f32p, C.c_double, C.c_double, _f64p, _f64p,
+                                     _i32p]
 
     def fn(self, name):
         return getattr(self.dll, self.prefix + name)
@@ -411,6 +413,16 @@ class Context:
 
     def dev_free(self, ptr: int):
         self._chk(self.lib.fn("dev_free")(self._h, C.c_void_p(ptr)))
+
+    def align_score(self, kind: int, xyzi, relpose4x4, inlier_thresh: float, inlier_ratio_thresh: float):
+        """AlignmentScore against the map index `kind`: (score, overlap ratio, inlier count)."""
+        a = _xyzi(xyzi)
+        T = np.ascontiguousarray(relpose4x4, dtype=np.float32).reshape(16)
+        sc, ov = C.c_double(0), C.c_double(0)
+        ni = C.c_int32(0)
+        self._chk(self.lib.fn("align_score")(self._h, kind, _fp(a), a.shape[0], _fp(T), float(inlier_thresh),
+                                             float(inlier_ratio_thresh), C.byref(sc), C.byref(ov), C.byref(ni)))
+        return sc.value, ov.value, ni.value
 
     # -- loop-closure descriptors (ScanContext), device library only
     def sc_make(self, xyzi):

@@ -694,6 +694,38 @@ int lmsf_match(lmsf_ctx* c, int kind, const float* q_xyz, int nq, uint8_t* ok, d
   return rc;
 }
 
+int lmsf_align_score(lmsf_ctx* c, int kind, const float* xyzi, int n, const float relpose16[16], double inlier_thresh,
+                     double inlier_ratio_thresh, double* score, double* overlap, int32_t* n_inlier) {
+  ENTER(c);
+  LM_TRY(wait_map(c));
+  if (kind < 0 || kind > 1 || n < 0 || (n > 0 && !xyzi) || !relpose16 || !score || !overlap) return LMSF_ERR_INVALID;
+  if (!(inlier_thresh >= 0.0 && inlier_thresh <= 1.0)) return LMSF_ERR_INVALID;  // the index answers d2 < 1
+  if (!c->map[kind].ready) return LMSF_ERR_STATE;
+  if (n_inlier) *n_inlier = 0;
+  if (n == 0) {  // alignEvaluate.hpp:61
+    *score = 1.7976931348623157e308;
+    *overlap = 0.0;
+    return LMSF_OK;
+  }
+  float4* d_pts = nullptr;
+  LM_CUDA(cudaMalloc(&d_pts, (size_t)n * sizeof(float4)));
+  int rc = LMSF_OK;
+  double sum = 0;
+  int cnt = 0;
+  if (cudaMemcpyAsync(d_pts, xyzi, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+    rc = LMSF_ERR_CUDA;
+  } else {
+    rc = align_hook(c, kind, d_pts, n, relpose16, (float)inlier_thresh, &sum, &cnt);
+  }
+  cudaFree(d_pts);
+  if (rc) return rc;
+  const double ratio = (double)cnt / (double)n;  // :80
+  *overlap = ratio;
+  *score = (ratio > inlier_ratio_thresh) ? sum / cnt : 1.7976931348623157e308;  // :82-85
+  if (n_inlier) *n_inlier = cnt;
+  return LMSF_OK;
+}
+
 int lmsf_register(lmsf_ctx* c, const float* edge_xyzi, int n_e, const float* surf_xyzi, int n_s, int solver,
                   double pose[7], lmsf_reg_stats* st) {
   ENTER(c);

@@ -309,6 +309,7 @@ int solve_alloc(Ctx* c);
 void solve_free(Ctx* c);
 int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2);
 int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double* d_out10);
+int align_hook(Ctx* c, int kind, const float4* d_pts, int n, const float T12[12], float thresh, double* sum, int* cnt);
 // features in c->d_feat (counts in c->ex.counts on the device; `upper` bounds their sum on the
 // host); enqueues the whole solve, reads pose + statistics back (one stream sync)
 int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* st, int upper, int outer_count);

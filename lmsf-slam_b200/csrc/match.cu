@@ -1197,6 +1197,82 @@ __global__ void __launch_bounds__(128) k_match_hook(MapView mv, const float4* __
   for (int k = 0; k < 10; ++k) out10[10 * i + k] = o[k];
 }
 
+// ------------------------------------------------------------------ alignment score (row f2)
+// PointCloudAlignmentEvaluate::AlignmentScore (registration/alignEvaluate.hpp:55-87): pcl::transformPointCloud with a
+// Matrix4f (fp32: ((m0 x + m1 y) + m2 z) + m3, no FMA), 1-NN in the target, inliers = squared distance <= thresh.
+struct Rigid12f {
+  float m[12];  // rows 0..2 of the 4x4, row-major
+};
+__global__ void __launch_bounds__(128) k_align_score(MapView mv, const float4* __restrict__ pts, int n, Rigid12f T,
+                                                     float thresh, double* __restrict__ part_sum,
+                                                     int* __restrict__ part_cnt) {
+  __shared__ double s_sum[4];
+  __shared__ int s_cnt[4];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  int in = 0;
+  Top5 nb;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (i < n) {
+    float4 p = pts[i];
+    qx = T.m[0] * p.x + T.m[1] * p.y + T.m[2] * p.z + T.m[3];
+    qy = T.m[4] * p.x + T.m[5] * p.y + T.m[6] * p.z + T.m[7];
+    qz = T.m[8] * p.x + T.m[9] * p.y + T.m[10] * p.z + T.m[11];
+  }
+  // every thread of the block calls knn5 (it owns shared-memory-free state only, but keeps the warps converged)
+  if (i < n) {
+    knn5(mv, qx, qy, qz, nb, nullptr, nullptr);
+    const bool found = nb.id[0] >= 0 && nb.id[0] != 0x7fffffff;
+    if (found && nb.d[0] <= thresh) {
+      v = (double)nb.d[0];
+      in = 1;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v += __shfl_xor_sync(0xffffffffu, v, d);
+    in += __shfl_xor_sync(0xffffffffu, in, d);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_sum[warp] = v;
+    s_cnt[warp] = in;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    part_sum[blockIdx.x] = ((s_sum[0] + s_sum[1]) + s_sum[2]) + s_sum[3];
+    part_cnt[blockIdx.x] = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+  }
+}
+
+// fixed-order final sum (reproducible bit for bit)
+__global__ void __launch_bounds__(256) k_align_finish(const double* __restrict__ part_sum,
+                                                      const int* __restrict__ part_cnt, int nblk,
+                                                      double* __restrict__ out_sum, int* __restrict__ out_cnt) {
+  __shared__ double s_sum[256];
+  __shared__ int s_cnt[256];
+  double v = 0.0;
+  int in = 0;
+  for (int b = threadIdx.x; b < nblk; b += 256) {
+    v += part_sum[b];
+    in += part_cnt[b];
+  }
+  s_sum[threadIdx.x] = v;
+  s_cnt[threadIdx.x] = in;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + d];
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + d];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *out_sum = s_sum[0];
+    *out_cnt = s_cnt[0];
+  }
+}
+
 // ------------------------------------------------------------------ host side
 #ifndef KNN_GRID_PER_SM
 #define KNN_GRID_PER_SM 7
@@ -1264,6 +1340,30 @@ int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double
             d_out10);
   LM_CUDA(cudaGetLastError());
   return LMSF_OK;
+}
+
+// device cloud -> (sum of inlier squared distances, inlier count) read back with one sync
+int align_hook(Ctx* c, int kind, const float4* d_pts, int n, const float T12[12], float thresh, double* sum, int* cnt) {
+  if (!c->map[kind].ready) return LMSF_ERR_STATE;
+  const int nblk = div_up(n, 128);
+  double* d_part = nullptr;
+  int* d_cnt = nullptr;
+  LM_CUDA(cudaMalloc(&d_part, (size_t)(nblk + 1) * sizeof(double)));
+  LM_CUDA(cudaMalloc(&d_cnt, (size_t)(nblk + 1) * sizeof(int)));
+  Rigid12f T;
+  for (int i = 0; i < 12; ++i) T.m[i] = T12[i];
+  LM_LAUNCH(c, k_align_score, nblk, 128, 0, view_of(c->map[kind]), d_pts, n, T, thresh, d_part, d_cnt);
+  LM_LAUNCH(c, k_align_finish, 1, 256, 0, d_part, d_cnt, nblk, d_part + nblk, d_cnt + nblk);
+  int rc = LMSF_OK;
+  if (cudaMemcpyAsync(sum, d_part + nblk, sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+      cudaMemcpyAsync(cnt, d_cnt + nblk, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+      cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    c->last_error = cudaGetErrorString(cudaGetLastError());
+    rc = LMSF_ERR_CUDA;
+  }
+  cudaFree(d_part);
+  cudaFree(d_cnt);
+  return rc;
 }
 
 #ifdef LMSF_TIMING

@@ -1060,6 +1060,42 @@ int lmsf_oracle_knn5(lmsf_oracle_ctx* c, int kind, const float* q, int nq, int32
   return 0;
 }
 
+// PointCloudAlignmentEvaluate::AlignmentScore (registration/alignEvaluate.hpp:55-87) against the map `kind`
+// (SetTargetPoints :42-46).  pcl::transformPointCloud with a Matrix4f: fp32, ((m0 x + m1 y) + m2 z) + m3
+// (PCL's non-SSE dense path); nearestKSearch(point, 1) without a radius; fitness accumulated in double in point
+// order.  Sequential on purpose: the accumulation order is the reference's.
+int lmsf_oracle_align_score(lmsf_oracle_ctx* c, int kind, const float* xyzi, int n, const float T[16],
+                            double inlier_thresh, double inlier_ratio_thresh, double* score, double* overlap,
+                            int32_t* n_inlier) {
+  if (!c || kind < 0 || kind > 1 || !c->map[kind].set || !score || !overlap) return -5;
+  if (n_inlier) *n_inlier = 0;
+  if (n == 0) {
+    *score = std::numeric_limits<double>::max();
+    *overlap = 0;
+    return 0;
+  }
+  const int mode = c->prm.knn_mode;
+  double fitness = 0.0;
+  int nr = 0;
+  for (int i = 0; i < n; ++i) {
+    const float x = xyzi[4 * i], y = xyzi[4 * i + 1], z = xyzi[4 * i + 2];
+    const float qx = T[0] * x + T[1] * y + T[2] * z + T[3];
+    const float qy = T[4] * x + T[5] * y + T[6] * z + T[7];
+    const float qz = T[8] * x + T[9] * y + T[10] * z + T[11];
+    Nb5 nb;
+    c->map[kind].knn(qx, qy, qz, mode, nb);  // the nearest of the five is the 1-NN
+    if (nb.n > 0 && (double)nb.d[0] <= inlier_thresh) {
+      fitness += (double)nb.d[0];
+      nr++;
+    }
+  }
+  const double ratio = (double)nr / (double)n;
+  *overlap = ratio;
+  *score = (ratio > inlier_ratio_thresh) ? fitness / nr : std::numeric_limits<double>::max();
+  if (n_inlier) *n_inlier = nr;
+  return 0;
+}
+
 int lmsf_oracle_match(lmsf_oracle_ctx* c, int kind, const float* q, int nq, uint8_t* ok, double* out10) {
   if (!c || kind < 0 || kind > 1 || !c->map[kind].set) return -5;
   const int mode = c->prm.knn_mode;

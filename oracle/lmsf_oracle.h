@@ -114,6 +114,11 @@ int lmsf_oracle_se3_exp(const double d[6], double q[4], double t[3]);
 int lmsf_oracle_lm_solve(const double* edge9, int n_e, const double* surf7, int n_s, double huber,
                          int max_iters, double x[7], int* steps, int* accepted, double* cost);
 
+/* = PointCloudAlignmentEvaluate::AlignmentScore (registration/alignEvaluate.hpp:55-87), row f2 */
+int lmsf_oracle_align_score(lmsf_oracle_ctx* c, int kind, const float* xyzi, int n, const float relpose16[16],
+                            double inlier_thresh, double inlier_ratio_thresh, double* score, double* overlap,
+                            int32_t* n_inlier);
+
 /* ---- loop-closure descriptor path ("next" row f1): ScanContext 20 x 60 (row-major ring x sector, fp32),
  * ring key (20 fp32), ring-key 10-NN by (distance, id), SC distance + column shift, descFindSimilar ---- */
 int lmsf_oracle_sc_make(const float* xyzi, int n, float* desc1200, float* key20);

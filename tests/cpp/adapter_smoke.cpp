@@ -62,6 +62,21 @@ int main(int argc, char** argv) {
               f1.pointcloud_data_["loam_surf"]->size(), surf_map->size());
   std::printf("pose %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
 
+  // alignment score as loopDetection.hpp:176-178 drives it (its own context: SetTargetPoints replaces a map index)
+  {
+    lmsf::ContextPtr ctx2 = std::make_shared<lmsf::Context>(0, &prm);
+    lmsf::CudaPointCloudAlignmentEvaluate<Pt> eval(ctx2, "loam_surf");
+    eval.SetTargetPoints(f0.pointcloud_data_["loam_surf"]);
+    Eigen::Matrix4f Tf = Eigen::Matrix4f::Identity();
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) Tf(r, c) = (float)T.linear()(r, c);
+      Tf(r, 3) = (float)T.translation()(r);
+    }
+    auto sc = eval.AlignmentScore(f1.pointcloud_data_["loam_surf"], Tf, 1.0, 0.3);
+    auto self = eval.AlignmentScore(f0.pointcloud_data_["loam_surf"], Eigen::Matrix4f::Identity(), 0.1, 0.6);
+    std::printf("align %.17g %.17g %.17g %.17g\n", sc.first, sc.second, self.first, self.second);
+  }
+
   // place recognition as loopDetection.hpp drives SceneRecognitionScanContext: 60 keyframes (sweep 0, then sweep 1
   // repeated), then the revisit query (sweep 0 again) and LoopDetect on a stored keyframe
   lmsf::CudaSceneRecognitionScanContext<Pt> scene(ctx, {"loam_edge", "loam_surf"});

@@ -481,6 +481,8 @@ def test_cpp_adapters_match_ctypes_path(gpu_lib, sweeps, tmp_path):
     before, hit, size, dist, shift = lines["loop"]
     assert int(before) == -1 and int(hit) == 0 and int(size) == 61 and float(dist) < 1e-12 and int(shift) == 0
     assert int(lines["loopdetect"][0]) == 1 and float(lines["loopdetect"][1]) < 1e-12
+    a_score, a_ov, self_score, self_ov = (float(x) for x in lines["align"])
+    assert self_score == 0.0 and self_ov == 1.0 and 0.3 < a_ov <= 1.0 and a_score < 1.0
     g = gpu_lib.context(0, n_scans=16)
     _, e0, f0 = g.extract_features(s0)
     v0, _ = g.voxel_downsample(f0, 0.4)
@@ -553,3 +555,30 @@ def test_multi_lidar_rig_config3(gpu_lib, oracle_lib, synth):
     finally:
         for c in g + o:
             c.close()
+
+
+@pytest.mark.parametrize("name,ns", [("vlp16", 16), ("hdl64", 64)])
+def test_align_score_parity(ctxs, sweeps, synth, name, ns):
+    """Row f2, PointCloudAlignmentEvaluate::AlignmentScore: inlier count and overlap identical to the oracle, the score
+    equal up to the order of the double sum (every term is identical)."""
+    g, o = ctxs(n_scans=ns)
+    _, _, f0 = g.extract_features(sweeps(name, 0))
+    _, _, f1 = g.extract_features(sweeps(name, 1))
+    for c in (g, o):
+        c.map_set(1, f0)
+    T_true = synth.qt_to_mat(synth.rel_gt_pose(1))
+    T_off = T_true.copy()
+    T_off[:3, 3] += [0.4, -0.3, 0.1]
+    T_far = np.eye(4)
+    T_far[:3, 3] = [500.0, 0, 0]
+    cloud = f1[::2]
+    for T, thr, rat in ((T_true, 0.1, 0.6), (T_true, 1.0, 0.6), (T_off, 0.1, 0.6), (T_off, 1.0, 0.3), (T_far, 0.1, 0.6)):
+        sg, og, ng = g.align_score(1, cloud, T, thr, rat)
+        so, oo, no = o.align_score(1, cloud, T, thr, rat)
+        assert ng == no and og == oo, (thr, rat)
+        assert sg == so or abs(sg - so) <= 1e-12 * abs(so), (sg, so)
+    sg, og, ng = g.align_score(1, cloud, T_true, 0.1, 0.6)
+    assert (sg < 0.05 and og > 0.6) if name == "hdl64" else og > 0.3
+    assert g.align_score(1, np.zeros((0, 4), np.float32), np.eye(4), 0.1, 0.6)[:2] == (np.finfo(np.float64).max, 0.0)
+    with pytest.raises(Exception):
+        g.align_score(1, cloud, T_true, 2.0, 0.6)            # beyond the index's reach: refused, never approximated

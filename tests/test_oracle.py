@@ -482,3 +482,51 @@ def test_tracker_keyframes_and_window(oracle_lib, synth):
         assert st["first"] == (1 if k == 0 else 0)
     assert sum(1 for kf, _ in sizes if kf == 1) >= 3
     assert max(ms for _, ms in sizes) < 2 * 7200       # the window never holds more than two frames
+
+
+# ---------------------------------------------------------------- f2 alignment score
+def py_align_score(target, cloud, T, thresh, ratio_thresh):
+    """alignEvaluate.hpp:55-87 restated independently: fp32 transform ((m0 x + m1 y) + m2 z) + m3, exact 1-NN with the
+    fp32 x->y->z squared distance (candidates from a double-precision cKDTree, re-ranked in fp32), double accumulation in
+    point order."""
+    from scipy.spatial import cKDTree
+    T = np.asarray(T, np.float32)
+    p = np.asarray(cloud, np.float32)[:, :3]
+    q = np.empty_like(p)
+    for r in range(3):
+        q[:, r] = ((T[r, 0] * p[:, 0] + T[r, 1] * p[:, 1]) + T[r, 2] * p[:, 2]) + T[r, 3]
+    tg = np.asarray(target, np.float32)[:, :3]
+    _, cand = cKDTree(tg.astype(np.float64)).query(q.astype(np.float64), k=min(4, len(tg)))
+    cand = cand.reshape(len(q), -1)
+    d = tg[cand] - q[:, None, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    nn = d2.min(axis=1)
+    fitness, nr = 0.0, 0
+    for v in nn:
+        if float(v) <= thresh:
+            fitness += float(v)
+            nr += 1
+    ov = nr / len(q)
+    return (fitness / nr if ov > ratio_thresh else np.finfo(np.float64).max), ov, nr
+
+
+def test_align_score_vs_python_restatement(oracle_lib, synth):
+    o = oracle_lib.context(0, n_scans=16, oracle_knn_mode=0)
+    s0, s1 = synth.make_sweep(synth.vlp16(), 0), synth.make_sweep(synth.vlp16(), 1)
+    _, _, f0 = o.extract_features(s0)
+    _, _, f1 = o.extract_features(s1)
+    o.map_set(1, f0)
+    T_true = synth.qt_to_mat(synth.rel_gt_pose(1))
+    T_off = T_true.copy()
+    T_off[:3, 3] += [0.4, -0.3, 0.0]
+    for T, thr, rat in ((T_true, 0.1, 0.6), (T_true, 1.0, 0.6), (T_off, 0.1, 0.6), (np.eye(4), 0.1, 0.5)):
+        sc, ov, ni = o.align_score(1, f1[::3], T, thr, rat)
+        sp, op, npy = py_align_score(f0, f1[::3], T, thr, rat)
+        assert ni == npy and ov == op
+        assert sc == sp or abs(sc - sp) <= 1e-15 * abs(sp)      # same values summed in the same order
+    good = o.align_score(1, f1[::3], T_true, 0.1, 0.6)
+    bad = o.align_score(1, f1[::3], T_off, 0.1, 0.6)
+    assert good[0] < 0.05 and good[1] > 0.6                      # the reference's acceptance test (loopDetection.hpp:181)
+    assert bad[1] < good[1]
+    assert o.align_score(1, np.zeros((0, 4), np.float32), np.eye(4), 0.1, 0.6)[:2] == (np.finfo(np.float64).max, 0.0)
+    o.close()
