@@ -49,6 +49,7 @@ struct ScDb {
   int* part_i = nullptr;
   float* top_d = nullptr;    // [q_cap][10]
   int* top_i = nullptr;      // [q_cap][10] local ids
+  float* tau = nullptr;      // [q_cap] per-query bound of the 10th ring-key distance (threshold pass)
   ScCand* cand = nullptr;    // [q_cap][10]
   int* out_id = nullptr;     // [q_cap]
   double* out_dist = nullptr;
@@ -74,6 +75,7 @@ void scdb_free(Ctx* c) {
   cudaFree(d->part_i);
   cudaFree(d->top_d);
   cudaFree(d->top_i);
+  cudaFree(d->tau);
   cudaFree(d->cand);
   cudaFree(d->out_id);
   cudaFree(d->out_dist);
@@ -167,6 +169,14 @@ struct Top10 {
       id[k] = 0x7fffffff;
     }
   }
+  // ten keys are known to exist with distance <= bound: accept distance <= bound, ties included
+  __device__ __forceinline__ void reset_inclusive(float bound) {
+#pragma unroll
+    for (int k = 0; k < SC_K; ++k) {
+      d[k] = bound;
+      id[k] = 0x7fffffff;
+    }
+  }
   __device__ __forceinline__ void add(float dd, int ii) {
     if (dd < d[SC_K - 1] || (dd == d[SC_K - 1] && ii < id[SC_K - 1])) {
       d[SC_K - 1] = dd;
@@ -209,8 +219,13 @@ __device__ __forceinline__ float key_dist(const float (&q)[SC_NR], const float* 
 
 // grid (query tiles, parts): block (tile, part) scans keys [part*per, min(limit, (part+1)*per)) for 32 queries and
 // writes their partial top-10 lists (ascending by (distance, id)).
+// tau (optional): per query an upper bound of its 10th smallest distance (the 10th of a sample of the same keys).
+// Every (warp, part) list is independent, and a list that starts empty inserts on most of its first few hundred
+// keys — with ~150 lists per query the sorted insert, not the distance, dominated the scan (83 % of the keys took
+// the insert path in some lane).  Starting every list at tau leaves only the ~0.2 % of keys that can still matter.
 __global__ void __launch_bounds__(KQ* KW) k_sc_scan(const float* __restrict__ keys, int limit, int per,
                                                      const float* __restrict__ q_keys, int nq,
+                                                     const float* __restrict__ tau,
                                                      float* __restrict__ part_d, int* __restrict__ part_i) {
   __shared__ __align__(16) float s_keys[KCHUNK * SC_NR];
   __shared__ float s_d[KW][SC_K][KQ];
@@ -222,7 +237,10 @@ __global__ void __launch_bounds__(KQ* KW) k_sc_scan(const float* __restrict__ ke
 #pragma unroll
   for (int d = 0; d < SC_NR; ++d) qk[d] = (q < nq) ? q_keys[(size_t)q * SC_NR + d] : 0.0f;
   Top10 top;
-  top.reset();
+  if (tau != nullptr && q < nq)
+    top.reset_inclusive(tau[q]);
+  else
+    top.reset();
   for (int base = lo; base < hi; base += KCHUNK) {
     const int cnt = min(KCHUNK, hi - base);
     __syncthreads();
@@ -253,24 +271,64 @@ __global__ void __launch_bounds__(KQ* KW) k_sc_scan(const float* __restrict__ ke
   }
 }
 
-// merge the per-part lists of every query: ascending (distance, id); empty slots -> id -1, distance +inf
+// merge the per-part lists of every query: ascending (distance, id); empty slots -> id -1, distance +inf.
+// One warp per query: every lane folds the entries lane, lane + 32, ... of the parts x 10 candidates into a sorted
+// list of its own, then ten rounds of a warp-wide lexicographic minimum over the list heads pop the result.
+// tau_out (optional): the 10th distance of the merged list (+inf when fewer than ten), for the threshold pass.
 __global__ void __launch_bounds__(128) k_sc_merge_parts(const float* __restrict__ part_d, const int* __restrict__ part_i,
                                                         int parts, int nq, float* __restrict__ top_d,
-                                                        int* __restrict__ top_i) {
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
+                                                        int* __restrict__ top_i, float* __restrict__ tau_out) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq) return;
   Top10 top;
   top.reset();
-  for (int p = 0; p < parts; ++p) {
-    size_t o = ((size_t)p * nq + q) * SC_K;
-#pragma unroll
-    for (int k = 0; k < SC_K; ++k) top.add(part_d[o + k], part_i[o + k]);
+  const int total = parts * SC_K;
+  for (int e = lane; e < total; e += 32) {
+    const int p = e / SC_K, k = e - p * SC_K;
+    const size_t o = ((size_t)p * nq + q) * SC_K + k;
+    const int id = part_i[o];
+    if (id != 0x7fffffff) top.add(part_d[o], id);
   }
+  float out_d = __int_as_float(0x7f800000);
+  int out_i = -1;
+  float tenth = __int_as_float(0x7f800000);
 #pragma unroll
-  for (int k = 0; k < SC_K; ++k) {
-    top_d[(size_t)q * SC_K + k] = top.d[k];
-    top_i[(size_t)q * SC_K + k] = top.id[k] == 0x7fffffff ? -1 : top.id[k];
+  for (int r = 0; r < SC_K; ++r) {
+    float d = top.d[0];
+    int id = top.id[0];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, d, s);
+      const int oi = __shfl_xor_sync(0xffffffffu, id, s);
+      if (od < d || (od == d && oi < id)) {
+        d = od;
+        id = oi;
+      }
+    }
+    // the lane that owns the minimum pops its head (ids are unique across lanes; placeholders never win over a real
+    // entry and, once only placeholders are left, every lane pops — harmless)
+    if (top.id[0] == id && top.d[0] == d) {
+#pragma unroll
+      for (int k = 0; k + 1 < SC_K; ++k) {
+        top.d[k] = top.d[k + 1];
+        top.id[k] = top.id[k + 1];
+      }
+      top.d[SC_K - 1] = __int_as_float(0x7f800000);
+      top.id[SC_K - 1] = 0x7fffffff;
+    }
+    const bool real = id != 0x7fffffff;
+    if (lane == r) {
+      out_d = real ? d : __int_as_float(0x7f800000);
+      out_i = real ? id : -1;
+    }
+    if (r == SC_K - 1 && real) tenth = d;
   }
+  if (lane < SC_K) {
+    top_d[(size_t)q * SC_K + lane] = out_d;
+    top_i[(size_t)q * SC_K + lane] = out_i;
+  }
+  if (tau_out != nullptr && lane == 0) tau_out[q] = tenth;
 }
 
 // ------------------------------------------------------------------ DistanceBtnScanContext
@@ -508,6 +566,7 @@ static int ensure_query(Ctx* c, ScDb* d, int nq, int parts) {
     cudaFree(d->part_i);
     cudaFree(d->top_d);
     cudaFree(d->top_i);
+    cudaFree(d->tau);
     cudaFree(d->cand);
     cudaFree(d->out_id);
     cudaFree(d->out_dist);
@@ -519,6 +578,7 @@ static int ensure_query(Ctx* c, ScDb* d, int nq, int parts) {
     LM_CUDA(cudaMalloc(&d->part_i, (size_t)pc * qc * SC_K * sizeof(int)));
     LM_CUDA(cudaMalloc(&d->top_d, (size_t)qc * SC_K * sizeof(float)));
     LM_CUDA(cudaMalloc(&d->top_i, (size_t)qc * SC_K * sizeof(int)));
+    LM_CUDA(cudaMalloc(&d->tau, (size_t)qc * sizeof(float)));
     LM_CUDA(cudaMalloc(&d->cand, (size_t)qc * SC_K * sizeof(ScCand)));
     LM_CUDA(cudaMalloc(&d->out_id, (size_t)qc * sizeof(int)));
     LM_CUDA(cudaMalloc(&d->out_dist, (size_t)qc * sizeof(double)));
@@ -556,22 +616,36 @@ static int stage_cloud(Ctx* c, ScDb* d, const float* xyzi, int n) {
   return LMSF_OK;
 }
 
-// ring-key 10-NN of nq device queries among keys[0, limit): results in d->top_d / d->top_i
-static int knn_dev(Ctx* c, ScDb* d, const float* d_q_keys, int nq, int limit) {
+// one exact scan of keys[0, limit) (optionally thresholded) + merge
+static int scan_once(Ctx* c, ScDb* d, const float* d_q_keys, int nq, int limit, const float* tau, float* tau_out) {
   int parts = scan_parts(nq, limit);
-  LM_TRY(ensure_query(c, d, nq, parts));
-  if (limit <= 0) {  // nothing of this shard is searchable: every slot empty
-    LM_LAUNCH(c, k_sc_merge_parts, div_up(nq, 128), 128, 0, d->part_d, d->part_i, 0, nq, d->top_d, d->top_i);
-    return LMSF_OK;
-  }
   int per = div_up(limit, parts);
   per = div_up(per, KCHUNK) * KCHUNK;
   parts = div_up(limit, per);
   if (parts < 1) parts = 1;
   dim3 grid(div_up(nq, KQ), parts);
-  LM_LAUNCH(c, k_sc_scan, grid, KQ * KW, 0, d->keys, limit, per, d_q_keys, nq, d->part_d, d->part_i);
-  LM_LAUNCH(c, k_sc_merge_parts, div_up(nq, 128), 128, 0, d->part_d, d->part_i, parts, nq, d->top_d, d->top_i);
+  LM_LAUNCH(c, k_sc_scan, grid, KQ * KW, 0, d->keys, limit, per, d_q_keys, nq, tau, d->part_d, d->part_i);
+  LM_LAUNCH(c, k_sc_merge_parts, div_up(nq, 4), 128, 0, d->part_d, d->part_i, parts, nq, d->top_d, d->top_i, tau_out);
   return LMSF_OK;
+}
+
+// ring-key 10-NN of nq device queries among keys[0, limit): results in d->top_d / d->top_i.  Large databases are
+// scanned twice: a 4096-key sample first, whose 10th distance bounds the 10th distance over the whole prefix, then
+// everything with every partial list starting at that bound.
+constexpr int SC_SAMPLE = 4096;
+static int knn_dev(Ctx* c, ScDb* d, const float* d_q_keys, int nq, int limit) {
+  LM_TRY(ensure_query(c, d, nq, scan_parts(nq, limit)));
+  if (limit <= 0) {  // nothing of this shard is searchable: every slot empty
+    LM_LAUNCH(c, k_sc_merge_parts, div_up(nq, 4), 128, 0, d->part_d, d->part_i, 0, nq, d->top_d, d->top_i,
+              (float*)nullptr);
+    return LMSF_OK;
+  }
+  const float* tau = nullptr;
+  if (limit >= 4 * SC_SAMPLE) {
+    LM_TRY(scan_once(c, d, d_q_keys, nq, SC_SAMPLE, nullptr, d->tau));
+    tau = d->tau;
+  }
+  return scan_once(c, d, d_q_keys, nq, limit, tau, nullptr);
 }
 
 // candidates of nq device queries against this shard -> d_cand[nq][10]

@@ -61,7 +61,8 @@ def test_scdb_add_cloud_and_get(gctx, sco, sweeps):
     assert gctx.scdb_size() == 0
 
 
-@pytest.mark.parametrize("n,limit", [(5000, 5000), (5000, 4999), (777, 300), (64, 4), (300, 256), (300, 257)])
+@pytest.mark.parametrize("n,limit", [(5000, 5000), (5000, 4999), (777, 300), (64, 4), (300, 256), (300, 257),
+                                     (20000, 20000), (20000, 16384), (20000, 16383)])   # >= 16384: thresholded two-pass scan
 def test_ringkey_knn_identical(gctx, sco, n, limit):
     rng = np.random.default_rng(n + limit)
     keys = rng.uniform(0, 5, size=(n, 20)).astype(np.float32)
