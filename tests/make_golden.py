@@ -24,6 +24,24 @@ def small_sweep(synth, k):
     return np.ascontiguousarray(sw[az % 4 == 0])
 
 
+def sc_golden_inputs(synth, sco):
+    """Seeded inputs of the loop-closure fixture: descriptors of six small sweeps, a 300-entry database derived from
+    them (scaled, column-shifted), six revisit queries (column-shifted database entries)."""
+    import sc_helpers as sch
+    made = [sco.make(small_sweep(synth, 2 * k)) for k in range(6)]
+    descs = np.stack([m[0] for m in made])
+    keys0 = np.stack([m[1] for m in made])
+    rng = np.random.default_rng(20260600)
+    src = rng.integers(0, 6, size=300)
+    scale = rng.uniform(0.7, 1.3, size=300)
+    shift = rng.integers(0, 60, size=300)
+    db = np.stack([np.roll(descs[i] * np.float32(s), int(sh), axis=1) for i, s, sh in zip(src, scale, shift)]).astype(np.float32)
+    dbk = sch.keys_of_fast(db)
+    qid = np.array([5, 40, 111, 170, 222, 249])
+    qd = np.stack([np.roll(db[i], 7 * j, axis=1) for j, i in enumerate(qid)]).astype(np.float32)
+    return descs, keys0, db, dbk, qid, qd, sch.keys_of_fast(qd)
+
+
 def main():
     pkg = entry.load_package()
     synth = pkg.synth
@@ -58,6 +76,17 @@ def main():
         poses.append(p)
         kfs.append(st["keyframe"])
     np.savez_compressed(os.path.join(OUT, "vlp16_small_track.npz"), poses=np.array(poses), keyframes=np.array(kfs))
+    # loop-closure descriptors + alignment score (rows f1 / f2)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import sc_helpers as sch
+    sco = sch.ScOracle()
+    descs, keys0, db, dbk, qid, qd, qk = sc_golden_inputs(synth, sco)
+    kidx, kd = sco.knn(dbk, 250, qk)
+    lid, ldist, lsh = sco.search(dbk, db, 250, qk, qd)
+    pd, ps = sco.distance(qd, db[qid])
+    a_sc, a_ov, a_n = o.align_score(1, f1[::4], np.eye(4), 1.0, 0.3)
+    np.savez_compressed(os.path.join(OUT, "sc_small.npz"), desc=descs, key=keys0, knn_idx=kidx, knn_d=kd, loop_id=lid,
+                        loop_dist=ldist, loop_shift=lsh, pair_dist=pd, pair_shift=ps, align=np.array([a_sc, a_ov, a_n]))
     print("wrote", os.listdir(OUT))
 
 

@@ -191,3 +191,27 @@ def test_round_trip_at_full_database_size(gpu_lib):
         assert not np.any(lid2 == 30_000 + ids)
     finally:
         c.close()
+
+
+def test_sc_golden_fixture_on_gpu(gctx, sco, synth):
+    """The CUDA path against the committed fixture (no oracle call in the comparison)."""
+    import os
+    from make_golden import sc_golden_inputs, small_sweep
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sc_small.npz"))
+    _, _, db, dbk, qid, qd, qk = sc_golden_inputs(synth, sco)
+    for k in range(6):
+        d, key = gctx.sc_make(small_sweep(synth, 2 * k))
+        assert np.array_equal(u32(d), u32(g["desc"][k])) and np.array_equal(u32(key), u32(g["key"][k]))
+    gctx.scdb_add(db, dbk)
+    kidx, kd = gctx.scdb_knn(qk, 250)
+    assert np.array_equal(kidx, g["knn_idx"]) and np.array_equal(kd.view(np.uint32), g["knn_d"].view(np.uint32))
+    lid, ldist, lsh = gctx.scdb_search(qk, qd, 250)
+    assert np.array_equal(lid, g["loop_id"]) and np.array_equal(ldist, g["loop_dist"]) and np.array_equal(lsh, g["loop_shift"])
+    pd, ps = gctx.sc_distance(qd, db[qid])
+    assert np.array_equal(pd, g["pair_dist"]) and np.array_equal(ps, g["pair_shift"])
+    _, e0, f0 = gctx.extract_features(small_sweep(synth, 0))
+    vox, _ = gctx.voxel_downsample(f0, 0.4)
+    gctx.map_set(1, vox)
+    _, _, f1 = gctx.extract_features(small_sweep(synth, 3))
+    sc, ov, ni = gctx.align_score(1, f1[::4], np.eye(4), 1.0, 0.3)
+    assert ov == g["align"][1] and ni == g["align"][2] and abs(sc - g["align"][0]) <= 1e-12 * g["align"][0]

@@ -131,3 +131,27 @@ def test_tree_limit_schedule(gpu_lib):
 def test_candidate_record_layout():
     assert sch.CAND_DTYPE.itemsize == 24
     assert [sch.CAND_DTYPE.fields[k][1] for k in ("sc_dist", "key_dist", "id", "shift")] == [0, 8, 12, 16]
+
+
+def test_sc_golden_fixture_reproduced(sco, oracle_lib, synth):
+    """tests/golden/sc_small.npz (tests/make_golden.py): descriptors, ring-key top-10, SC distances, loop decisions and
+    one alignment score — guards the oracle against drift between rounds."""
+    import os
+    from make_golden import sc_golden_inputs, small_sweep
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sc_small.npz"))
+    descs, keys0, db, dbk, qid, qd, qk = sc_golden_inputs(synth, sco)
+    assert np.array_equal(descs.view(np.uint32), g["desc"].view(np.uint32))
+    assert np.array_equal(keys0.view(np.uint32), g["key"].view(np.uint32))
+    kidx, kd = sco.knn(dbk, 250, qk)
+    assert np.array_equal(kidx, g["knn_idx"]) and np.array_equal(kd.view(np.uint32), g["knn_d"].view(np.uint32))
+    lid, ldist, lsh = sco.search(dbk, db, 250, qk, qd)
+    assert np.array_equal(lid, g["loop_id"]) and np.array_equal(ldist, g["loop_dist"]) and np.array_equal(lsh, g["loop_shift"])
+    pd, ps = sco.distance(qd, db[qid])
+    assert np.array_equal(pd, g["pair_dist"]) and np.array_equal(ps, g["pair_shift"])
+    o = oracle_lib.context(0, n_scans=16, oracle_knn_mode=1)
+    _, e0, f0 = o.extract_features(small_sweep(synth, 0))
+    vox, _ = o.voxel_downsample(f0, 0.4)
+    o.map_set(1, vox)
+    _, _, f1 = o.extract_features(small_sweep(synth, 3))
+    assert np.array_equal(np.array(o.align_score(1, f1[::4], np.eye(4), 1.0, 0.3)), g["align"])
+    o.close()
