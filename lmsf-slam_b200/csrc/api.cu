@@ -151,10 +151,21 @@ static int update_map(Ctx* c, const rigid& T, int type) {
     LM_CUDA(cudaEventRecord(sl.freed, st));
     sl.freed_pending = true;
   }
+  // the two index builds are independent: in the asynchronous case the (small) edge build runs on a second stream
+  // beside the surf build instead of in front of it
+  const bool fork = async && c->n_edge > 0 && c->n_surf > 0;
+  if (fork) {
+    LM_CUDA(cudaEventRecord(c->ev_map_fork, st));
+    LM_CUDA(cudaStreamWaitEvent(c->stream_map2, c->ev_map_fork, 0));
+  }
   for (int kind = 0; kind < 2; ++kind) {
     int nk = kind ? c->n_surf : c->n_edge;
     if (nk == 0) continue;
-    LM_TRY(index_window(c, kind, st, async && fixed_ok[kind]));
+    LM_TRY(index_window(c, kind, (fork && kind == 0) ? c->stream_map2 : st, async && fixed_ok[kind]));
+  }
+  if (fork) {
+    LM_CUDA(cudaEventRecord(c->ev_map_join, c->stream_map2));
+    LM_CUDA(cudaStreamWaitEvent(st, c->ev_map_join, 0));
   }
   if (async) {
     LM_CUDA(cudaEventRecord(c->ev_map_done, st));
@@ -407,6 +418,7 @@ static void destroy(Ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream_fe) cudaStreamSynchronize(c->stream_fe);
+  if (c->stream_map2) cudaStreamSynchronize(c->stream_map2);
   if (c->stream_map) cudaStreamSynchronize(c->stream_map);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& sp : c->spans) {
@@ -436,6 +448,9 @@ static void destroy(Ctx* c) {
   cudaFreeHost(c->h_ints);
   cudaFreeHost(c->h_state);
   if (c->ev_map_done) cudaEventDestroy(c->ev_map_done);
+  if (c->ev_map_fork) cudaEventDestroy(c->ev_map_fork);
+  if (c->ev_map_join) cudaEventDestroy(c->ev_map_join);
+  if (c->stream_map2) cudaStreamDestroy(c->stream_map2);
   if (c->stream_map) cudaStreamDestroy(c->stream_map);
   if (c->stream_fe) cudaStreamDestroy(c->stream_fe);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -445,6 +460,9 @@ static int create(Ctx* c) {
   size_t cap = (size_t)c->prm.max_points;
   LM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   LM_CUDA(cudaStreamCreateWithFlags(&c->stream_map, cudaStreamNonBlocking));
+  LM_CUDA(cudaStreamCreateWithFlags(&c->stream_map2, cudaStreamNonBlocking));
+  LM_CUDA(cudaEventCreateWithFlags(&c->ev_map_fork, cudaEventDisableTiming));
+  LM_CUDA(cudaEventCreateWithFlags(&c->ev_map_join, cudaEventDisableTiming));
   LM_CUDA(cudaStreamCreateWithFlags(&c->stream_fe, cudaStreamNonBlocking));
   LM_CUDA(cudaEventCreateWithFlags(&c->ev_map_done, cudaEventDisableTiming));
   LM_CUDA(cudaMalloc(&c->d_sweep, cap * sizeof(float4)));

@@ -195,6 +195,8 @@ struct Ctx {
 
   // local-map update pipeline: its own stream, ordered against the main stream with two events
   cudaStream_t stream_map = nullptr;
+  cudaStream_t stream_map2 = nullptr;   // the edge map's index build runs beside the surf map's
+  cudaEvent_t ev_map_fork = nullptr, ev_map_join = nullptr;
   cudaEvent_t ev_map_done = nullptr;   // map stream has finished the index builds
   bool map_pending = false;            // main stream has not yet waited for ev_map_done
   bool feat_from_extract = false;      // d_feat came from extract_run: finite and range-gated
