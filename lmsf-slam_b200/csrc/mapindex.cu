@@ -124,10 +124,17 @@ __device__ __forceinline__ unsigned sub_cell(float4 p) {
 }
 
 // (4) one block per occupied L0 cell: counting sort of its segment by the 12-bit (L1, L2) sub-cell.  Thread t owns
-// the 16 bins [16 t, 16 t + 16) = a quarter of L1 cell t / 4; the L1 masks, the L2 cell starts (plus one sentinel
+// the CS_BINS bins [CS_BINS t, CS_BINS (t + 1)) = 1 / CS_LPL of L1 cell t / CS_LPL; the L1 masks, the L2 cell starts (plus one sentinel
 // per L0 cell, so that "start of the next L2 cell" is always the end of the previous one) and the cell record are
 // written from the same histogram.
-constexpr int CS_THREADS = 256;
+#ifndef CS_THREADS_N
+#define CS_THREADS_N 512  // measured: 256 -> 726, 512 -> 713, 1024 -> 743 us per sweep (128: 754)
+#endif
+constexpr int CS_THREADS = CS_THREADS_N;
+constexpr int CS_BINS = 4096 / CS_THREADS;   // bins per thread
+constexpr int CS_LPL = 64 / CS_BINS;         // lanes per L1 cell
+constexpr int CS_WARPS = CS_THREADS / 32;
+constexpr int CS_L1W = 32 / CS_LPL;          // L1 cells per warp
 __global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict__ cell_list,
                                                           CellRec* __restrict__ table,
                                                           const float4* __restrict__ grouped,
@@ -135,9 +142,9 @@ __global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict_
                                                           L1Rec* __restrict__ l1, int* __restrict__ l2_start,
                                                           int* __restrict__ d_cnt) {
   __shared__ int hist[4096];
-  __shared__ int warp_pts[8], warp_n2[8], warp_n1[8];
+  __shared__ int warp_pts[CS_WARPS], warp_n2[CS_WARPS], warp_n1[CS_WARPS];
   __shared__ int s_base1, s_base2;
-  __shared__ unsigned long long s_m1[8];
+  __shared__ unsigned long long s_m1[CS_WARPS];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int n_cells = d_cnt[CNT_L0];  // final: written by k_cell_alloc, the previous launch on this stream
   for (int ci = blockIdx.x; ci < n_cells; ci += gridDim.x) {
@@ -145,28 +152,28 @@ __global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict_
   const int s = table[h].start, e = table[h].end;
   __syncthreads();  // the previous cell's scatter is done with the bins
 #pragma unroll
-  for (int k = 0; k < 16; ++k) hist[t + k * CS_THREADS] = 0;
+  for (int k = 0; k < CS_BINS; ++k) hist[t + k * CS_THREADS] = 0;
   __syncthreads();
   for (int i = s + t; i < e; i += CS_THREADS) atomicAdd(&hist[sub_cell(grouped[i])], 1);
   __syncthreads();
-  // thread-local: points, occupied L2 cells and their 16-bit mask
-  int cnt[16];
+  // thread-local: points, occupied L2 cells and their mask
+  int cnt[CS_BINS];
   int pts = 0, n2 = 0;
-  unsigned m16 = 0;
+  unsigned mloc = 0;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    cnt[k] = hist[t * 16 + k];
+  for (int k = 0; k < CS_BINS; ++k) {
+    cnt[k] = hist[t * CS_BINS + k];
     pts += cnt[k];
     if (cnt[k]) {
       ++n2;
-      m16 |= 1u << k;
+      mloc |= 1u << k;
     }
   }
-  // the four threads of one L1 cell are four consecutive lanes
-  unsigned long long m2 = (unsigned long long)m16 << (16 * (lane & 3));
-  m2 |= __shfl_xor_sync(0xffffffffu, m2, 1);
-  m2 |= __shfl_xor_sync(0xffffffffu, m2, 2);
-  const bool l1_head = (lane & 3) == 0 && m2 != 0ull;
+  // the CS_LPL threads of one L1 cell are consecutive lanes
+  unsigned long long m2 = (unsigned long long)mloc << (CS_BINS * (lane & (CS_LPL - 1)));
+#pragma unroll
+  for (int d = 1; d < CS_LPL; d <<= 1) m2 |= __shfl_xor_sync(0xffffffffu, m2, d);
+  const bool l1_head = (lane & (CS_LPL - 1)) == 0 && m2 != 0ull;
   int n1 = l1_head ? 1 : 0;
   // block-wide exclusive scans of (pts, n2, n1)
   int ip = pts, i2 = n2, i1 = n1;
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict_
   __syncthreads();
   int wp = 0, w2 = 0, w1 = 0, tot2 = 0, tot1 = 0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
+  for (int w = 0; w < CS_WARPS; ++w) {
     if (w < warp) {
       wp += warp_pts[w];
       w2 += warp_n2[w];
@@ -208,8 +215,8 @@ __global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict_
   {
     int run = s + ex_p, r2 = base2 + ex_2;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      hist[t * 16 + k] = run;
+    for (int k = 0; k < CS_BINS; ++k) {
+      hist[t * CS_BINS + k] = run;
       if (cnt[k]) l2_start[r2++] = run;
       run += cnt[k];
     }
@@ -221,20 +228,20 @@ __global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict_
     r.pad = 0;
     l1[base1 + ex_1] = r;
   }
-  // occupancy of the 64 L1 cells: L1 cell j = lanes 4j..4j+3 of warp j / 8
+  // occupancy of the 64 L1 cells: L1 cell j = lanes j CS_LPL .. of warp j / CS_L1W
   unsigned heads = __ballot_sync(0xffffffffu, l1_head);
   unsigned long long m1w = 0ull;
   if (lane == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if ((heads >> (4 * j)) & 1u) m1w |= 1ull << (warp * 8 + j);
+    for (int j = 0; j < CS_L1W; ++j)
+      if ((heads >> (CS_LPL * j)) & 1u) m1w |= 1ull << (warp * CS_L1W + j);
   }
   if (lane == 0) s_m1[warp] = m1w;
   __syncthreads();
   if (t == 0) {
     unsigned long long m1 = 0ull;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) m1 |= s_m1[w];
+    for (int w = 0; w < CS_WARPS; ++w) m1 |= s_m1[w];
     l2_start[base2 + tot2] = e;  // sentinel of this L0 cell
     table[h].mask = m1;
     table[h].fine_base = base1;
@@ -427,7 +434,7 @@ int map_build(Ctx* c, MapIndex& m, int n, cudaStream_t st, bool fixed_grid) {
   LM_LAUNCH_ON(c, st, k_cell_alloc, div_up((int)slots, 256), 256, 0, m.table, slots, m.cell_list, m.d_cnt);
   LM_LAUNCH_ON(c, st, k_cell_scatter, nb, 256, 0, m.cat, n, m.slot_rank, m.table, m.grouped);
   // persistent blocks stride over the occupied L0 cells (their number is only known on the device)
-  LM_LAUNCH_ON(c, st, k_cell_sort, 148 * 6, CS_THREADS, 0, m.cell_list, m.table, m.grouped, m.sorted, m.l1,
+  LM_LAUNCH_ON(c, st, k_cell_sort, 148 * (CS_THREADS >= 512 ? 4 : 6), CS_THREADS, 0, m.cell_list, m.table, m.grouped, m.sorted, m.l1,
                m.l2_start, m.d_cnt);
   LM_LAUNCH_ON(c, st, k_map_finish, 1, 32, 0, m.dev, m.d_cnt);
   // occupancy of the table (and the insert-failed flag) travel back with the next pose read-back
