@@ -128,7 +128,8 @@ def run_ours(args):
     use_dist = world > 1
     W, K = args.warmup, args.steps
     # independent sequences are dealt round-robin to ranks (shard.assign): with one sequence per GPU rank r tracks sequence r
-    sweeps = make_sequence(W + K + 2, seq=rank)     # before any CUDA call (fork-safe); +1: the last step prefetches
+    seq_id = rank + int(os.environ.get("LMSF_BENCH_SEQ", "0"))   # env: single-GPU experiments on another sequence
+    sweeps = make_sequence(W + K + 2, seq=seq_id)     # before any CUDA call (fork-safe); +1: the last step prefetches
     torch.cuda.set_device(local)
     if use_dist:
         import torch.distributed as dist
@@ -216,6 +217,12 @@ def run_ours(args):
     sampler.join()
 
     dev_ms_max, e2e_ms_max = pkg.shard.max_over_ranks([dev_ms, e_wall_ms], device=f"cuda:{local}")
+    per_rank = [dev_ms / K]
+    if use_dist:   # every rank's own device time per step (evidence for the weak-scaling figure; rank r = sequence r)
+        t = torch.tensor([dev_ms / K, float(sum(1 for s in stats if s["keyframe"]))], dtype=torch.float64, device=f"cuda:{local}")
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [[round(float(x[0]), 4), int(x[1])] for x in allt]
 
     if rank == 0:
         ms, ln, alg_bytes = prof
@@ -245,7 +252,7 @@ def run_ours(args):
                        "p50_ms_per_scan": float(np.median(per)), "p90_ms_per_scan": float(np.percentile(per, 90)),
                        "max_ms_per_scan": float(np.max(per)), "wall_ms_per_step": wall_ms / K,
                        "flush_host_ms_per_step": [fl1, fl2, fl3], "instrumented_pass_ms_per_step": p_dev_ms / K,
-                       "keyframes_in_timed_region": kf,
+                       "keyframes_in_timed_region": kf, "per_rank_ms_per_step_and_keyframes": per_rank,
                        "features_per_sweep": int(np.mean([s["n_edge"] + s["n_surf"] for s in stats])),
                        "map_points_end": int(stats[-1]["map_edge"] + stats[-1]["map_surf"]),
                        "stage_ms_per_step": {k: v / K for k, v in ms.items()},

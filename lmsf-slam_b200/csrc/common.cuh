@@ -191,7 +191,6 @@ struct Ctx {
 
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
-  void* cub_tmp_map = nullptr;  // CUB scratch of the map stream (builds overlap the next sweep's extraction)
 
   // local-map update pipeline: its own stream, ordered against the main stream with two events
   cudaStream_t stream_map = nullptr;

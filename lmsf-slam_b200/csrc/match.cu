@@ -1,9 +1,11 @@
 // match.cu — correspondence search, residuals/Jacobians, normal-equation reduction and the
 // device-resident Gauss-Newton / Huber-LM loops.
 //
-//   k_match     one thread per scan feature: pointAssociateToMap (fp64 -> fp32,
-//               edgeSurfFeatureRegistration.hpp:342-350), exact 5-NN (knn.cuh),
-//               EdgeFeatureMatch::Match (FeatureMatch/EdgeFeatureMatch.hpp:33-87: 3x3 scatter,
+//   k_knn       one thread per scan feature, in ring order (permutation from the feature extraction):
+//               pointAssociateToMap (fp64 -> fp32, edgeSurfFeatureRegistration.hpp:342-350) and the exact
+//               5-NN over the local-map grid (knn.cuh), seeded with the previous outer iteration's neighbours.
+//               (k_assoc + a cell sort of the queries replace the ring order for caller-supplied features.)
+//   k_fit       EdgeFeatureMatch::Match (FeatureMatch/EdgeFeatureMatch.hpp:33-87: 3x3 scatter,
 //               symmetric eigen, line test, point-to-line residual and gradient) or
 //               SurfFeatureMatch::Match (surfFeatureMatch.hpp:32-87: 5x3 least squares plane,
 //               0.2 m validity, signed distance truncated to float), then the 1x6 Jacobian row of

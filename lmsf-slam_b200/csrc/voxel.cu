@@ -194,7 +194,6 @@ int voxel_alloc(Ctx* c) {
                              (int*)nullptr, cap, c->stream);
   c->cub_tmp_bytes = (b1 > b2 ? b1 : b2) + 256;
   LM_CUDA(cudaMalloc(&c->cub_tmp, c->cub_tmp_bytes));
-  LM_CUDA(cudaMalloc(&c->cub_tmp_map, c->cub_tmp_bytes));
   return LMSF_OK;
 }
 
@@ -211,7 +210,6 @@ void voxel_free(Ctx* c) {
   cudaFree(c->v_params);
   cudaFree(c->d_bbox);
   cudaFree(c->cub_tmp);
-  cudaFree(c->cub_tmp_map);
 }
 
 int voxel_run(Ctx* c, const float4* d_in, int n, float leaf, float4* d_out, int* n_out, int* d_member) {
