@@ -31,6 +31,11 @@ import __graft_entry__ as entry  # noqa: E402
 METRIC = "scan-to-map registrations/sec (HDL-64 synthetic)"
 UNIT = "scans/s"
 SENSOR = "hdl64"
+# Untimed initialisation sweeps in front of every pass (ours and the reference arm alike): a tracker that has just been
+# reset is not the workload — its sliding window fills over the first ten keyframes (~20 sweeps at 1.5 m/s) and the
+# Huber-LM outer-iteration budget decays 9, 8, ..., 2 over the first eight solves (ceres_edgeSurfFeatureRegistration.hpp:
+# 100-101).  After SETTLE sweeps the window is full and the budget sits at its floor, whatever --warmup is.
+SETTLE = 24
 FLUSH_BYTES = 192 << 20   # written between timed steps: 1.5x the 126 MB L2
 STATE_D2H_BYTES = 880 + 8  # sizeof(SolveState) + the two feature counts, read back once per sweep
 
@@ -129,7 +134,7 @@ def run_ours(args):
     W, K = args.warmup, args.steps
     # independent sequences are dealt round-robin to ranks (shard.assign): with one sequence per GPU rank r tracks sequence r
     seq_id = rank + int(os.environ.get("LMSF_BENCH_SEQ", "0"))   # env: single-GPU experiments on another sequence
-    sweeps = make_sequence(W + K + 2, seq=seq_id)     # before any CUDA call (fork-safe); +1: the last step prefetches
+    sweeps = make_sequence(SETTLE + W + K + 2, seq=seq_id)     # before any CUDA call (fork-safe); +1: the last step prefetches
     torch.cuda.set_device(local)
     if use_dist:
         import torch.distributed as dist
@@ -152,8 +157,9 @@ def run_ours(args):
     def run_sequence(step_fn, profile, K=K):
         """W untimed + K timed steps; returns (device ms for K steps, per-step wall ms, launches, prof)."""
         ctx.tracker_reset()
-        step_fn(0, 0.0)
-        for k in range(1, W + 1):
+        for k in range(0, SETTLE + 1):          # initialisation (see SETTLE), then the W warm-up steps
+            step_fn(k, 0.1 * k)
+        for k in range(SETTLE + 1, SETTLE + W + 1):
             step_fn(k, 0.1 * k)
         barrier()
         ctx.profile_enable(profile)
@@ -166,7 +172,7 @@ def run_ours(args):
         sampler.active.set()
         t_wall0 = time.perf_counter()
         e0.record(stream)
-        for k in range(W + 1, W + K + 1):
+        for k in range(SETTLE + W + 1, SETTLE + W + K + 1):
             tf = time.perf_counter()
             with torch.cuda.stream(stream):
                 flush.zero_()                       # L2 flush between timed steps, inside the timed region
@@ -248,6 +254,7 @@ def run_ours(args):
                        "points_per_sweep": int(np.mean(n_pts)), "sequences": n_gpus,
                        "l2": f"{FLUSH_BYTES >> 20} MiB memset between timed steps (L2 flush: 1.5x the 126 MB L2), inside the timed region",
                        "timing": "CUDA events on the context stream around the K steps, max over ranks",
+                       "initialisation": f"{SETTLE} untimed sweeps before the warm-up: full 10-keyframe window, LM budget at its floor",
                        "pipeline": "front end (extraction of sweep k+1) overlaps the registration of sweep k",
                        "p50_ms_per_scan": float(np.median(per)), "p90_ms_per_scan": float(np.percentile(per, 90)),
                        "max_ms_per_scan": float(np.max(per)), "wall_ms_per_step": wall_ms / K,
@@ -288,7 +295,7 @@ def cpu_baseline(sweeps, W, sample=4):
     lib = entry.load_oracle()
     threads = os.cpu_count() or 1
     o = lib.context(0, n_scans=64, oracle_knn_mode=0, oracle_threads=threads)
-    warm = min(W, len(sweeps) - sample - 1)
+    warm = min(SETTLE + W, len(sweeps) - sample - 1)
     for k in range(0, warm + 1):
         o.tracker_step(sweeps[k], 0.1 * k)
     lib.fn("set_threads")(o._h, 1)
@@ -311,15 +318,15 @@ def run_reference(args):
     if rank != 0:
         return
     W, K = args.warmup, args.steps
-    sweeps = make_sequence(W + K + 1, seq=0)
+    sweeps = make_sequence(SETTLE + W + K + 1, seq=0)
     lib = entry.load_oracle()
     threads = os.cpu_count() or 1
     o = lib.context(0, n_scans=64, oracle_knn_mode=0, oracle_threads=threads)
-    for k in range(0, W + 1):
+    for k in range(0, SETTLE + W + 1):
         o.tracker_step(sweeps[k], 0.1 * k)
     per = []
     t0 = time.perf_counter()
-    for k in range(W + 1, W + K + 1):
+    for k in range(SETTLE + W + 1, SETTLE + W + K + 1):
         t1 = time.perf_counter()
         o.tracker_step(sweeps[k], 0.1 * k)
         per.append((time.perf_counter() - t1) * 1e3)
@@ -334,7 +341,8 @@ def run_reference(args):
                                "Huber-LM solver, raw 10-keyframe sliding-window map, one sequence",
                    "p50_ms_per_scan": float(np.median(per))},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{K} consecutive sweeps after {W} warm-up sweeps, oracle tracker, {threads} threads"},
+                         "sample": f"{K} consecutive sweeps after {SETTLE} initialisation + {W} warm-up sweeps, oracle tracker, "
+                                   f"{threads} threads"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)

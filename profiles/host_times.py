@@ -13,10 +13,11 @@ pkg = entry.load_package()
 synth = pkg.synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 sensor = synth.hdl64()
-sweeps = [synth.make_sweep(sensor, k) for k in range(n + 12)]
+WARM = 34  # bench.py's SETTLE + default warm-up: full keyframe window, LM budget at its floor
+sweeps = [synth.make_sweep(sensor, k) for k in range(n + WARM + 2)]
 ctx = pkg.context(0, n_scans=64, max_points=1 << 18)
 d = [ctx.dev_upload_new(s) for s in sweeps]
-for k in range(10):
+for k in range(WARM):
     ctx.tracker_prefetch_dev(d[k + 1], len(sweeps[k + 1]))
     ctx.tracker_step_dev(d[k], len(sweeps[k]), 0.1 * k)
 us = (C.c_double * 4)()
@@ -25,7 +26,7 @@ ctx.lib.dll.lmsf_debug_host_times(ctx._h, us, cnt, 1)
 per = []
 kf = []
 t00 = time.perf_counter()
-for k in range(10, 10 + n):
+for k in range(WARM, WARM + n):
     t0 = time.perf_counter()
     ctx.tracker_submit_dev(d[k], len(sweeps[k]), 0.1 * k)
     ctx.tracker_prefetch_dev(d[k + 1], len(sweeps[k + 1]))
