@@ -255,6 +255,22 @@ int lmsf_scdb_pick_dev(lmsf_ctx* c, const void* d_cand_all, int n_ranks, int nq,
  * [0, size - 50) whenever (size - 1) % 10 == 0 and size > 50 (:74-92); 0 = no tree yet */
 int lmsf_sc_tree_limit(int n_keyframes);
 
+/* ---- multi-LiDAR extrinsic initialisation (hand-eye), host side ------ */
+/* = Algorithm::HandEyeCalibrationBase (Algorithm/calibration/handeye_calibration_base.hpp:36-246) as driven by
+ * MultiLidarSystem::process() in calibration status 0 (System/ML_System.hpp:243-283).  Poses are per-sweep motion
+ * increments {qx,qy,qz,qw,tx,ty,tz} of the primary and the auxiliary tracker (lmsf_tracker_step's delta output).
+ * add_pose = AddPose (:73-108, with checkScrewMotion :208-243); *enough = 1 once three pairs are stored.
+ * calibrate = CalibExRotation (:115-153) + CalibExTranslation (:155-190) + GetCalibResult (:193-202): *ok = 1 and
+ * extrinsic = pose of the auxiliary LiDAR in the primary's frame when the second smallest singular value exceeds
+ * 0.25; singular_values (optional) are returned in descending order.  Status 1, the per-sweep refinement of the
+ * extrinsic against the primary's local map (:286-323), is lmsf_tracker_register_aux.  Pure host arithmetic. */
+typedef struct lmsf_handeye lmsf_handeye;
+int lmsf_handeye_create(lmsf_handeye** out);
+void lmsf_handeye_destroy(lmsf_handeye* h);
+int lmsf_handeye_add_pose(lmsf_handeye* h, const double delta_primary[7], const double delta_sub[7], int* enough);
+int lmsf_handeye_calibrate(lmsf_handeye* h, double extrinsic[7], double singular_values[4], int* ok);
+int lmsf_handeye_size(lmsf_handeye* h, int* n);
+
 /* ---- device memory helpers for callers that keep sweeps resident ---- */
 int lmsf_dev_alloc(lmsf_ctx* c, int64_t bytes, void** d_ptr);
 int lmsf_dev_free(lmsf_ctx* c, void* d_ptr);

@@ -10,6 +10,8 @@
 //        replaces  CeresEdgeSurfFeatureRegistration / EdgeSurfFeatureRegistration
 //                                             (registration/ceres_edgeSurfFeatureRegistration.hpp:26,
 //                                              edgeSurfFeatureRegistration.hpp:27, built at ML_SystemFactory.hpp:189-190)
+//   lmsf::CudaMultiLidarExtrinsics             the calibration branch of MultiLidarSystem::process()
+//                                             (System/ML_System.hpp:239-323) + HandEyeCalibrationBase
 //   lmsf::CudaPointCloudAlignmentEvaluate<P>   (no abstract base in the reference: same public methods)
 //        replaces  Slam3D::PointCloudAlignmentEvaluate   (registration/alignEvaluate.hpp:23-98)
 //   lmsf::CudaSceneRecognitionScanContext<P>   (no abstract base in the reference: same public methods)
@@ -288,6 +290,88 @@ class CudaPointCloudAlignmentEvaluate {
   std::string name_;
   int kind_;
   bool set_target_ = false;
+};
+
+// ---------------------------------------------------------------- multi-LiDAR extrinsic calibration loop (row f3)
+// The calibration branch of MultiLidarSystem::process() (System/ML_System.hpp:239-323) for a primary and one
+// auxiliary LiDAR, on two device contexts: status 0 = both trackers + hand-eye initialisation
+// (HandEyeCalibrationBase, Algorithm/calibration/handeye_calibration_base.hpp), status 1 = primary tracker +
+// registration of the auxiliary sweep against the primary's local map.  Poses are {qx,qy,qz,qw,tx,ty,tz}.
+class CudaMultiLidarExtrinsics {
+ public:
+  CudaMultiLidarExtrinsics(ContextPtr primary, ContextPtr auxiliary) : ctx_{std::move(primary), std::move(auxiliary)} {
+    if (lmsf_handeye_create(&he_) != LMSF_OK) throw std::runtime_error("lmsf_handeye_create");
+  }
+  ~CudaMultiLidarExtrinsics() { lmsf_handeye_destroy(he_); }
+  CudaMultiLidarExtrinsics(const CudaMultiLidarExtrinsics&) = delete;
+  CudaMultiLidarExtrinsics& operator=(const CudaMultiLidarExtrinsics&) = delete;
+
+  int Status() const { return status_; }                 // EXTRINSIC_CALIB_STATUS_: 0 initialising, 1 refining
+  const double* Extrinsic() const { return ext_; }       // lidar_lidar_estrinsic_: auxiliary LiDAR in the primary's frame
+  const double* PrimaryPose() const { return pose0_; }
+
+  // one synchronised pair of sweeps (float32 XYZI, n0 / n1 points)
+  bool Process(const float* sweep0, int n0, const float* sweep1, int n1, double stamp) {
+    double d0[7] = {0, 0, 0, 1, 0, 0, 0}, d1[7] = {0, 0, 0, 1, 0, 0, 0}, p1[7];
+    lmsf_track_stats st0, st1;
+    if (status_ == 0) {
+      // (the reference runs the two trackers under `omp parallel for`; the contexts are independent, so may the caller)
+      if (!detail::check(lmsf_tracker_step(ctx_[0]->get(), sweep0, n0, stamp, d0, pose0_, &st0), "lmsf_tracker_step") ||
+          !detail::check(lmsf_tracker_step(ctx_[1]->get(), sweep1, n1, stamp, d1, p1, &st1), "lmsf_tracker_step"))
+        return false;
+      if (st0.first) return true;
+      int enough = 0, ok = 0;
+      lmsf_handeye_add_pose(he_, d0, d1, &enough);
+      if (enough) {
+        double e[7];
+        lmsf_handeye_calibrate(he_, e, nullptr, &ok);
+        if (ok) {
+          std::memcpy(ext_, e, sizeof e);
+          status_ = 1;
+        }
+      }
+      return true;
+    }
+    if (!detail::check(lmsf_tracker_step(ctx_[0]->get(), sweep0, n0, stamp, d0, pose0_, &st0), "lmsf_tracker_step"))
+      return false;
+    double sub[7];
+    mul(pose0_, ext_, sub);  // sub_lidar_pose = primary_lidar_pose * lidar_lidar_estrinsic_ (:301)
+    lmsf_reg_stats rs;
+    if (!detail::check(lmsf_tracker_register_aux(ctx_[0]->get(), sweep1, n1, sub, &rs), "lmsf_tracker_register_aux"))
+      return false;
+    double inv0[7];
+    inv(pose0_, inv0);
+    mul(inv0, sub, ext_);    // lidar_lidar_estrinsic_ = primary_lidar_pose.inverse() * sub_lidar_pose (:306)
+    return true;
+  }
+
+ private:
+  static void rotv(const double* q, const double* v, double* o) {
+    const double ux = q[0], uy = q[1], uz = q[2], w = q[3];
+    double cx = 2 * (uy * v[2] - uz * v[1]), cy = 2 * (uz * v[0] - ux * v[2]), cz = 2 * (ux * v[1] - uy * v[0]);
+    o[0] = v[0] + w * cx + (uy * cz - uz * cy);
+    o[1] = v[1] + w * cy + (uz * cx - ux * cz);
+    o[2] = v[2] + w * cz + (ux * cy - uy * cx);
+  }
+  static void mul(const double* a, const double* b, double* o) {
+    double q[4] = {a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1], a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2],
+                   a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0], a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2]};
+    double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), t[3];
+    rotv(a, b + 4, t);
+    for (int i = 0; i < 4; ++i) o[i] = q[i] / n;
+    for (int i = 0; i < 3; ++i) o[4 + i] = t[i] + a[4 + i];
+  }
+  static void inv(const double* a, double* o) {
+    double qi[4] = {-a[0], -a[1], -a[2], a[3]}, t[3];
+    rotv(qi, a + 4, t);
+    for (int i = 0; i < 4; ++i) o[i] = qi[i];
+    for (int i = 0; i < 3; ++i) o[4 + i] = -t[i];
+  }
+  ContextPtr ctx_[2];
+  lmsf_handeye* he_ = nullptr;
+  int status_ = 0;
+  double ext_[7] = {0, 0, 0, 1, 0, 0, 0};
+  double pose0_[7] = {0, 0, 0, 1, 0, 0, 0};
 };
 
 // ---------------------------------------------------------------- loop-closure place recognition (row f1)

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import os
 
-from . import capi, shard, synth  # noqa: F401
+from . import capi, rig, shard, synth  # noqa: F401
 from .capi import (IDENTITY_POSE, KIND_EDGE, KIND_SURF, SOLVER_GN, SOLVER_HUBER_LM, Context, Library,  # noqa: F401
                    LmsfError, Params, RegStats, TrackStats)
 

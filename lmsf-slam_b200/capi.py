@@ -134,6 +134,8 @@ class Library:
         # loop-closure descriptor path (scancontext.cu)
         "sc_make", "sc_distance", "scdb_reserve", "scdb_clear", "scdb_size", "scdb_add", "scdb_add_cloud",
         "scdb_get", "scdb_knn", "scdb_search", "scdb_search_shard_dev", "scdb_pick_dev", "sc_tree_limit",
+        # multi-LiDAR extrinsic initialisation (calib.cu, host arithmetic)
+        "handeye_create", "handeye_destroy", "handeye_add_pose", "handeye_calibrate", "handeye_size",
     )
 
     def __init__(self, path: str, prefix: str = "lmsf_"):
@@ -182,6 +184,12 @@ class Library:
             f("scdb_pick_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
             f("sc_tree_limit").argtypes = [C.c_int]
+            f("handeye_create").argtypes = [C.POINTER(C.c_void_p)]
+            f("handeye_destroy").argtypes = [C.c_void_p]
+            f("handeye_destroy").restype = None
+            f("handeye_add_pose").argtypes = [C.c_void_p, _f64p, _f64p, _intp]
+            f("handeye_calibrate").argtypes = [C.c_void_p, _f64p, _f64p, _intp]
+            f("handeye_size").argtypes = [C.c_void_p, _intp]
         f("ctx_create").argtypes = [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]
         f("ctx_destroy").argtypes = [C.c_void_p]
         f("extract_features").argtypes = [C.c_void_p, _f32p, C.c_int, _u8p, _f32p, _intp, _f32p, _intp]
@@ -219,6 +227,52 @@ class Library:
 
     def context(self, device: int = 0, **overrides) -> "Context":
         return Context(self, device, **overrides)
+
+
+class HandEye:
+    """HandEyeCalibrationBase (handeye_calibration_base.hpp): extrinsic initialisation from paired motion increments."""
+
+    def __init__(self, lib: "Library"):
+        self.lib = lib
+        self._h = C.c_void_p()
+        rc = lib.fn("handeye_create")(C.byref(self._h))
+        if rc:
+            raise LmsfError(rc, "handeye_create")
+
+    def close(self):
+        if self._h:
+            self.lib.fn("handeye_destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_pose(self, delta_primary, delta_sub) -> bool:
+        a = np.array(delta_primary, dtype=np.float64)
+        b = np.array(delta_sub, dtype=np.float64)
+        ok = C.c_int(0)
+        rc = self.lib.fn("handeye_add_pose")(self._h, a.ctypes.data_as(_f64p), b.ctypes.data_as(_f64p), C.byref(ok))
+        if rc:
+            raise LmsfError(rc, "handeye_add_pose")
+        return bool(ok.value)
+
+    def calibrate(self):
+        """(ok, extrinsic {qx,qy,qz,qw,tx,ty,tz}, singular values descending)"""
+        e = np.zeros(7, np.float64)
+        sv = np.zeros(4, np.float64)
+        ok = C.c_int(0)
+        rc = self.lib.fn("handeye_calibrate")(self._h, e.ctypes.data_as(_f64p), sv.ctypes.data_as(_f64p), C.byref(ok))
+        if rc:
+            raise LmsfError(rc, "handeye_calibrate")
+        return bool(ok.value), e, sv
+
+    def size(self) -> int:
+        n = C.c_int(0)
+        self.lib.fn("handeye_size")(self._h, C.byref(n))
+        return n.value
 
 
 class Context:

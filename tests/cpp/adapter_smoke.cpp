@@ -77,6 +77,16 @@ int main(int argc, char** argv) {
     std::printf("align %.17g %.17g %.17g %.17g\n", sc.first, sc.second, self.first, self.second);
   }
 
+  // multi-LiDAR extrinsics: compile-and-run check of the calibration loop class (two contexts, same sweeps: the
+  // increments are identical, so the pairs are accepted; identical LiDARs cannot excite the rotation -> status stays 0)
+  {
+    lmsf::ContextPtr ca = std::make_shared<lmsf::Context>(0, &prm), cb = std::make_shared<lmsf::Context>(0, &prm);
+    lmsf::CudaMultiLidarExtrinsics rig(ca, cb);
+    bool ok0 = rig.Process(buf.data(), n0, buf.data(), n0, 0.0);
+    bool ok1 = rig.Process(buf.data() + 4 * (std::size_t)n0, n1, buf.data() + 4 * (std::size_t)n0, n1, 0.1);
+    std::printf("rig %d %d %d\n", (int)ok0, (int)ok1, rig.Status());
+  }
+
   // place recognition as loopDetection.hpp drives SceneRecognitionScanContext: 60 keyframes (sweep 0, then sweep 1
   // repeated), then the revisit query (sweep 0 again) and LoopDetect on a stored keyframe
   lmsf::CudaSceneRecognitionScanContext<Pt> scene(ctx, {"loam_edge", "loam_surf"});

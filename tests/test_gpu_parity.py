@@ -481,6 +481,7 @@ def test_cpp_adapters_match_ctypes_path(gpu_lib, sweeps, tmp_path):
     before, hit, size, dist, shift = lines["loop"]
     assert int(before) == -1 and int(hit) == 0 and int(size) == 61 and float(dist) < 1e-12 and int(shift) == 0
     assert int(lines["loopdetect"][0]) == 1 and float(lines["loopdetect"][1]) < 1e-12
+    assert lines["rig"] == ["1", "1", "0"]
     a_score, a_ov, self_score, self_ov = (float(x) for x in lines["align"])
     assert self_score == 0.0 and self_ov == 1.0 and 0.3 < a_ov <= 1.0 and a_score < 1.0
     g = gpu_lib.context(0, n_scans=16)
