@@ -127,6 +127,14 @@ int lmsf_extract_features(lmsf_ctx* c, const float* xyzi, int n, uint8_t* label_
 int lmsf_voxel_downsample(lmsf_ctx* c, const float* xyzi, int n, float leaf, float* out_xyzi,
                           int* n_out, int32_t* voxel_of_point);
 
+/* = PointCloudCommonProcess::Process (Algorithm/PointClouds/processing/common_processing.hpp:87-111), the front
+ * end of the direct-method branch: (1) pcl::removeNaNFromPointCloud when remove_nan != 0, (2) the VoxelGrid
+ * down-sampling when leaf > 0, (3) — outlier removal is not offered (out of scope; the reference's default is
+ * none) — (4) DistanceFilter (Filter/distance_filter.hpp:24-44): keep near < |p| < far, skipped when both are 0.
+ * Order preserving.  out_xyzi needs room for n points. */
+int lmsf_common_process(lmsf_ctx* c, const float* xyzi, int n, int remove_nan, float leaf, float dist_near,
+                        float dist_far, float* out_xyzi, int* n_out);
+
 /* ---- seam 3: registration ------------------------------------------- */
 /* = RegistrationBase::SetInputSource (registration/registration_base.hpp:31): upload a
  * local map and build its kNN index (replaces pcl::KdTreeFLANN::setInputCloud,

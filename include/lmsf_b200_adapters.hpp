@@ -10,6 +10,8 @@
 //        replaces  CeresEdgeSurfFeatureRegistration / EdgeSurfFeatureRegistration
 //                                             (registration/ceres_edgeSurfFeatureRegistration.hpp:26,
 //                                              edgeSurfFeatureRegistration.hpp:27, built at ML_SystemFactory.hpp:189-190)
+//   lmsf::CudaPointCloudCommonProcess<P>   : Algorithm::PointCloudProcessBase<P,P>
+//        replaces  PointCloudCommonProcess    (processing/common_processing.hpp:28, removeNaN + VoxelGrid + DistanceFilter)
 //   lmsf::CudaMultiLidarExtrinsics             the calibration branch of MultiLidarSystem::process()
 //                                             (System/ML_System.hpp:239-323) + HandEyeCalibrationBase
 //   lmsf::CudaPointCloudAlignmentEvaluate<P>   (no abstract base in the reference: same public methods)
@@ -172,6 +174,39 @@ class CudaLoamFeatureProcessor : public Algorithm::PointCloudProcessBase<_InputP
  private:
   ContextPtr ctx_;
   std::vector<float> in_, edge_, surf_;
+};
+
+// ---------------------------------------------------------------- direct-method front end (row f4)
+// Same surface as Algorithm::PointCloudCommonProcess<P> (processing/common_processing.hpp:28-121): removeNaN,
+// VoxelGrid, DistanceFilter; the result is inserted under output_name.  SetOutlierRemoval is not offered.
+template <typename _PointType>
+class CudaPointCloudCommonProcess : public Algorithm::PointCloudProcessBase<_PointType, _PointType> {
+ public:
+  CudaPointCloudCommonProcess(ContextPtr ctx, std::string output_name, bool removal_nan = true)
+      : ctx_(std::move(ctx)), output_name_(std::move(output_name)), removal_nan_(removal_nan) {}
+  void SetVoxelGrid(std::string const& name, float leaf) {
+    if (name == "VoxelGrid") leaf_ = leaf;
+  }
+  void SetDistanceFilter(float const& distance_near_thresh, float const& distance_far_thresh) {
+    near_ = distance_near_thresh;
+    far_ = distance_far_thresh;
+  }
+  void Process(Slam3D::LidarData<_PointType> const& data_in, Slam3D::CloudContainer<_PointType>& data_out) override {
+    detail::pack(data_in.point_cloud, in_);
+    const int n = (int)data_in.point_cloud.points.size();
+    out_.resize((std::size_t)(n > 0 ? n : 1) * 4);
+    int m = 0;
+    if (!detail::check(lmsf_common_process(ctx_->get(), in_.data(), n, removal_nan_ ? 1 : 0, leaf_, near_, far_, out_.data(), &m),
+                       "lmsf_common_process"))
+      m = 0;
+    data_out.pointcloud_data_.insert(std::make_pair(output_name_, detail::unpack<_PointType>(out_.data(), m)));
+  }
+ private:
+  ContextPtr ctx_;
+  std::string output_name_;
+  bool removal_nan_;
+  float leaf_ = 0.f, near_ = 0.f, far_ = 0.f;
+  std::vector<float> in_, out_;
 };
 
 // ---------------------------------------------------------------- seam 2

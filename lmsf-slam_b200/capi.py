@@ -123,7 +123,7 @@ class Library:
     COMMON = (
         "params_default", "ctx_create", "ctx_destroy", "strerror", "extract_features",
         "voxel_downsample", "map_set", "knn5", "match", "register", "set_lm_outer",
-        "tracker_step", "tracker_step_features", "tracker_reset", "tracker_register_aux", "get_map", "align_score",
+        "tracker_step", "tracker_step_features", "tracker_reset", "tracker_register_aux", "get_map", "align_score", "common_process",
     )
     # symbols only the CUDA library exports
     DEVICE_ONLY = (
@@ -207,6 +207,7 @@ class Library:
         f("get_map").argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int, _intp]
         f("align_score").argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int, _f32p, C.c_double, C.c_double, _f64p, _f64p,
                                      _i32p]
+        f("common_process").argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _f32p, _intp]
 
     def fn(self, name):
         return getattr(self.dll, self.prefix + name)
@@ -336,6 +337,17 @@ class Context:
         self._chk(self.lib.fn("voxel_downsample")(self._h, _fp(a), n, float(leaf), _fp(out), C.byref(no),
                                                   mem.ctypes.data_as(_i32p) if mem is not None else None))
         return out[: no.value].copy(), (mem[:n].copy() if mem is not None else None)
+
+    def common_process(self, xyzi, remove_nan: bool = True, leaf: float = 0.0, dist_near: float = 0.0,
+                       dist_far: float = 0.0):
+        """PointCloudCommonProcess::Process: removeNaN -> VoxelGrid(leaf) -> DistanceFilter(near, far)."""
+        a = _xyzi(xyzi)
+        n = a.shape[0]
+        out = np.empty((max(n, 1), 4), np.float32)
+        no = C.c_int(0)
+        self._chk(self.lib.fn("common_process")(self._h, _fp(a), n, int(bool(remove_nan)), float(leaf), float(dist_near),
+                                                float(dist_far), _fp(out), C.byref(no)))
+        return out[: no.value].copy()
 
     # -- seam 3
     def map_set(self, kind: int, xyzi):

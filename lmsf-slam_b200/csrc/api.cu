@@ -6,6 +6,7 @@
 
 #include <chrono>
 #include <new>
+#include <utility>
 
 #include "common.cuh"
 
@@ -622,6 +623,48 @@ int lmsf_voxel_downsample(lmsf_ctx* c, const float* xyzi, int n, float leaf, flo
     LM_CUDA(cudaMemcpyAsync(voxel_of_point, c->v_member, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   LM_CUDA(cudaStreamSynchronize(c->stream));
   *n_out = nv;
+  return LMSF_OK;
+}
+
+int lmsf_common_process(lmsf_ctx* c, const float* xyzi, int n, int remove_nan, float leaf, float dist_near,
+                        float dist_far, float* out_xyzi, int* n_out) {
+  ENTER(c);
+  LM_TRY(wait_map(c));
+  if (n < 0 || !n_out || (n > 0 && (!xyzi || !out_xyzi)) || leaf < 0.f) return LMSF_ERR_INVALID;
+  if (n > c->vox_cap) return LMSF_ERR_CAPACITY;
+  *n_out = 0;
+  if (n == 0) return LMSF_OK;
+  const int chunk = c->prm.max_points;
+  for (int o = 0; o < n; o += chunk) {
+    int m = (n - o < chunk) ? n - o : chunk;
+    memcpy(c->h_pts, xyzi + 4 * (size_t)o, (size_t)m * sizeof(float4));
+    LM_CUDA(cudaMemcpyAsync(c->v_in + o, c->h_pts, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    LM_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  float4 *cur = c->v_in, *other = c->v_out;
+  int m = n;
+  if (remove_nan) {  // common_processing.hpp:93-97
+    int k = 0;
+    LM_TRY(filter_run(c, cur, m, 0, 0.f, 0.f, other, &k));
+    std::swap(cur, other);
+    m = k;
+  }
+  if (leaf > 0.f && m > 0) {  // :103 (a VoxelGridFilter without a leaf returns its input)
+    int k = 0;
+    LM_TRY(voxel_run(c, cur, m, leaf, other, &k, nullptr));
+    std::swap(cur, other);
+    m = k;
+  }
+  // :105 outlier removal: not offered here (out of scope) — the reference's default is "none"
+  if (!(dist_near == 0.f && dist_far == 0.f) && m > 0) {  // :107-108, distance_filter.hpp:27-31
+    int k = 0;
+    LM_TRY(filter_run(c, cur, m, 1, dist_near, dist_far, other, &k));
+    std::swap(cur, other);
+    m = k;
+  }
+  if (m > 0) LM_CUDA(cudaMemcpyAsync(out_xyzi, cur, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  *n_out = m;
   return LMSF_OK;
 }
 

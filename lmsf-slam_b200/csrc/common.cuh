@@ -287,6 +287,9 @@ void voxel_free(Ctx* c);
 // device in -> device out; *n_out read back (synchronises the stream)
 int voxel_run(Ctx* c, const float4* d_in, int n, float leaf, float4* d_out, int* n_out, int* d_member);
 
+// order-preserving point filter on the main stream: mode 0 = finite x/y/z, mode 1 = near < |p| < far (fp32 norm)
+int filter_run(Ctx* c, const float4* d_in, int n, int mode, float near_t, float far_t, float4* d_out, int* n_out);
+
 // ---- implemented in mapindex.cu
 int map_alloc(Ctx* c, MapIndex& m, int cap);
 void map_free(MapIndex& m);

@@ -172,6 +172,54 @@ __global__ void __launch_bounds__(256) k_fill_member(int* __restrict__ member, i
   if (i < n) member[i] = mode ? i : -1;
 }
 
+// ---- PointCloudCommonProcess's order-preserving point filters (row f4) ---------------------------------------
+// mode 0: pcl::removeNaNFromPointCloud — keep points whose x, y and z are finite
+// mode 1: DistanceFilter::Filter (Filter/distance_filter.hpp:24-44) — d = Vector3f norm (fp32 (x x + y y) + z z,
+//         fp32 sqrt) widened to double, keep near < d < far against the float thresholds widened to double
+__global__ void __launch_bounds__(256) k_keep_flags(const float4* __restrict__ in, int n, int mode, float near_t,
+                                                    float far_t, uint8_t* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = in[i];
+  bool keep;
+  if (mode == 0) {
+    keep = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+  } else {
+    float s = p.x * p.x + p.y * p.y;
+    s = s + p.z * p.z;
+    double d = (double)sqrtf(s);
+    keep = d > (double)near_t && d < (double)far_t;
+  }
+  flags[i] = keep ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_gather_points(const float4* __restrict__ in, const int* __restrict__ sel,
+                                                       int n, float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[sel[i]];
+}
+
+// stable compaction of d_in[0..n) by the predicate `mode` into d_out; *n_out read back (one sync)
+int filter_run(Ctx* c, const float4* d_in, int n, int mode, float near_t, float far_t, float4* d_out, int* n_out) {
+  if (n > c->vox_cap) return LMSF_ERR_CAPACITY;
+  *n_out = 0;
+  if (n == 0) return LMSF_OK;
+  const int nb = div_up(n, 256);
+  LM_LAUNCH(c, k_keep_flags, nb, 256, 0, d_in, n, mode, near_t, far_t, c->v_flags);
+  size_t tmp = c->cub_tmp_bytes;
+  int* d_nsel = (int*)c->d_bbox + 7;
+  LM_CUDA(cub::DeviceSelect::Flagged(c->cub_tmp, tmp, thrust::counting_iterator<int>(0), c->v_flags, c->v_heads, d_nsel,
+                                     n, c->stream));
+  c->launches++;
+  LM_CUDA(cudaMemcpyAsync(c->h_ints, d_nsel, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  const int m = c->h_ints[0];
+  if (m > 0) LM_LAUNCH(c, k_gather_points, div_up(m, 256), 256, 0, d_in, c->v_heads, m, d_out);
+  LM_CUDA(cudaGetLastError());
+  *n_out = m;
+  return LMSF_OK;
+}
+
 int voxel_alloc(Ctx* c) {
   int cap = c->prm.max_points > c->prm.max_map_points ? c->prm.max_points : c->prm.max_map_points;
   c->vox_cap = cap;

@@ -1036,6 +1036,39 @@ int lmsf_oracle_voxel_downsample(lmsf_oracle_ctx* c, const float* xyzi, int n, f
   return 0;
 }
 
+// PointCloudCommonProcess::Process (processing/common_processing.hpp:87-111): removeNaN, VoxelGrid, (no outlier
+// removal), DistanceFilter (Filter/distance_filter.hpp:24-44: fp32 Vector3f norm widened to double, open interval)
+int lmsf_oracle_common_process(lmsf_oracle_ctx* c, const float* xyzi, int n, int remove_nan, float leaf, float dist_near,
+                               float dist_far, float* out_xyzi, int* n_out) {
+  if (!c || n < 0 || !n_out || leaf < 0.f) return -1;
+  const P4* in = reinterpret_cast<const P4*>(xyzi);
+  std::vector<P4> cur(in, in + n), nxt;
+  if (remove_nan) {
+    nxt.clear();
+    for (const P4& p : cur)
+      if (std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z)) nxt.push_back(p);
+    cur.swap(nxt);
+  }
+  if (leaf > 0.f && !cur.empty()) {
+    nxt.clear();
+    voxel(cur.data(), (int)cur.size(), leaf, nxt, nullptr);
+    cur.swap(nxt);
+  }
+  if (!(dist_near == 0.f && dist_far == 0.f)) {
+    nxt.clear();
+    for (const P4& p : cur) {
+      float s = p.x * p.x + p.y * p.y;
+      s = s + p.z * p.z;
+      double d = (double)std::sqrt(s);
+      if (d > (double)dist_near && d < (double)dist_far) nxt.push_back(p);
+    }
+    cur.swap(nxt);
+  }
+  if (out_xyzi && !cur.empty()) std::memcpy(out_xyzi, cur.data(), cur.size() * sizeof(P4));
+  *n_out = (int)cur.size();
+  return 0;
+}
+
 int lmsf_oracle_map_set(lmsf_oracle_ctx* c, int kind, const float* xyzi, int n) {
   if (!c || kind < 0 || kind > 1 || n < 0) return -1;
   if (n == 0) return 0;

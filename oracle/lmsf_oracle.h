@@ -114,6 +114,10 @@ int lmsf_oracle_se3_exp(const double d[6], double q[4], double t[3]);
 int lmsf_oracle_lm_solve(const double* edge9, int n_e, const double* surf7, int n_s, double huber,
                          int max_iters, double x[7], int* steps, int* accepted, double* cost);
 
+/* = PointCloudCommonProcess::Process (processing/common_processing.hpp:87-111), row f4 */
+int lmsf_oracle_common_process(lmsf_oracle_ctx* c, const float* xyzi, int n, int remove_nan, float leaf, float dist_near,
+                               float dist_far, float* out_xyzi, int* n_out);
+
 /* = PointCloudAlignmentEvaluate::AlignmentScore (registration/alignEvaluate.hpp:55-87), row f2 */
 int lmsf_oracle_align_score(lmsf_oracle_ctx* c, int kind, const float* xyzi, int n, const float relpose16[16],
                             double inlier_thresh, double inlier_ratio_thresh, double* score, double* overlap,

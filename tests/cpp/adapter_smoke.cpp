@@ -77,6 +77,18 @@ int main(int argc, char** argv) {
     std::printf("align %.17g %.17g %.17g %.17g\n", sc.first, sc.second, self.first, self.second);
   }
 
+  // direct-method front end: removeNaN + VoxelGrid + DistanceFilter behind PointCloudProcessBase
+  {
+    std::unique_ptr<Algorithm::PointCloudProcessBase<Pt, Pt>> pre;
+    auto* cp = new lmsf::CudaPointCloudCommonProcess<Pt>(ctx, "processed", true);
+    cp->SetVoxelGrid("VoxelGrid", 0.5f);
+    cp->SetDistanceFilter(3.0f, 40.0f);
+    pre.reset(cp);
+    Slam3D::CloudContainer<Pt> pc;
+    pre->Process(load(buf.data(), n0), pc);
+    std::printf("common %zu\n", pc.pointcloud_data_["processed"]->size());
+  }
+
   // multi-LiDAR extrinsics: compile-and-run check of the calibration loop class (two contexts, same sweeps: the
   // increments are identical, so the pairs are accepted; identical LiDARs cannot excite the rotation -> status stays 0)
   {

@@ -482,6 +482,9 @@ def test_cpp_adapters_match_ctypes_path(gpu_lib, sweeps, tmp_path):
     assert int(before) == -1 and int(hit) == 0 and int(size) == 61 and float(dist) < 1e-12 and int(shift) == 0
     assert int(lines["loopdetect"][0]) == 1 and float(lines["loopdetect"][1]) < 1e-12
     assert lines["rig"] == ["1", "1", "0"]
+    gc = gpu_lib.context(0, n_scans=16)
+    assert int(lines["common"][0]) == len(gc.common_process(s0, True, 0.5, 3.0, 40.0))
+    gc.close()
     a_score, a_ov, self_score, self_ov = (float(x) for x in lines["align"])
     assert self_score == 0.0 and self_ov == 1.0 and 0.3 < a_ov <= 1.0 and a_score < 1.0
     g = gpu_lib.context(0, n_scans=16)
@@ -583,3 +586,17 @@ def test_align_score_parity(ctxs, sweeps, synth, name, ns):
     assert g.align_score(1, np.zeros((0, 4), np.float32), np.eye(4), 0.1, 0.6)[:2] == (np.finfo(np.float64).max, 0.0)
     with pytest.raises(Exception):
         g.align_score(1, cloud, T_true, 2.0, 0.6)            # beyond the index's reach: refused, never approximated
+
+
+def test_common_process_bit_exact(ctxs, sweeps):
+    """Row f4, PointCloudCommonProcess::Process: the filtered cloud is bit-identical to the oracle's, order included."""
+    g, o = ctxs(n_scans=64)
+    sw = sweeps("hdl64", 4).copy()
+    sw[::53, 1] = np.nan
+    sw[11, 0] = -np.inf
+    for args in ((True, 0.0, 0.0, 0.0), (True, 0.0, 2.5, 40.0), (True, 0.4, 0.0, 0.0), (True, 0.8, 3.0, 30.0),
+                 (False, 0.3, 1.0, 60.0), (True, 0.0, 100.0, 200.0)):
+        a = g.common_process(sw, *args)
+        b = o.common_process(sw, *args)
+        assert a.shape == b.shape and np.array_equal(bits(a), bits(b)), args
+    assert len(g.common_process(np.zeros((0, 4), np.float32))) == 0

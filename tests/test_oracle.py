@@ -530,3 +530,28 @@ def test_align_score_vs_python_restatement(oracle_lib, synth):
     assert bad[1] < good[1]
     assert o.align_score(1, np.zeros((0, 4), np.float32), np.eye(4), 0.1, 0.6)[:2] == (np.finfo(np.float64).max, 0.0)
     o.close()
+
+
+# ---------------------------------------------------------------- f4 common pre-processing
+def test_common_process_vs_numpy(oracle_lib, synth):
+    """PointCloudCommonProcess::Process (common_processing.hpp:87-111): removeNaN -> VoxelGrid -> DistanceFilter."""
+    o = oracle_lib.context(0, n_scans=16)
+    sw = synth.make_sweep(synth.vlp16(), 2).copy()
+    sw[::31, 0] = np.nan
+    sw[5, 2] = np.inf
+    fin = sw[np.isfinite(sw[:, :3]).all(axis=1)]
+    out = o.common_process(sw, True, 0.0, 0.0, 0.0)
+    assert np.array_equal(out.view(np.uint32), fin.view(np.uint32))                      # order kept, only NaN/inf dropped
+    s = fin[:, 0] * fin[:, 0] + fin[:, 1] * fin[:, 1]
+    d = np.sqrt((s + fin[:, 2] * fin[:, 2]).astype(np.float32)).astype(np.float64)
+    near, far = np.float32(3.0), np.float32(25.5)
+    keep = (d > float(near)) & (d < float(far))
+    out = o.common_process(sw, True, 0.0, near, far)
+    assert np.array_equal(out.view(np.uint32), fin[keep].view(np.uint32))
+    vox, _ = o.voxel_downsample(fin, 0.5)
+    sv = vox[:, 0] * vox[:, 0] + vox[:, 1] * vox[:, 1]
+    dv = np.sqrt((sv + vox[:, 2] * vox[:, 2]).astype(np.float32)).astype(np.float64)
+    out = o.common_process(sw, True, 0.5, near, far)
+    assert np.array_equal(out.view(np.uint32), vox[(dv > float(near)) & (dv < float(far))].view(np.uint32))
+    assert len(o.common_process(np.zeros((0, 4), np.float32))) == 0
+    o.close()
