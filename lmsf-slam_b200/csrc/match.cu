@@ -1140,9 +1140,13 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* 
 #endif
 }
 
-__global__ void k_state_init(SolveState* st, const double* __restrict__ pose) {
+struct Pose7 {
+  double v[7];
+};
+// the prior pose travels as a kernel argument: no host-to-device copy in front of the solve
+__global__ void k_state_init(SolveState* st, Pose7 pose) {
   if (threadIdx.x != 0) return;
-  for (int i = 0; i < 7; ++i) st->x[i] = st->cand[i] = pose[i];
+  for (int i = 0; i < 7; ++i) st->x[i] = st->cand[i] = pose.v[i];
   st->cost = 0;
   st->n_edge_ok = st->n_surf_ok = 0;
   st->gn_done = st->gn_degenerate = st->gn_iters = 0;
@@ -1436,9 +1440,9 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
     qorg.y = cell(pose[5]) - 128;
     qorg.z = cell(pose[6]) - 64;
   }
-  for (int i = 0; i < 7; ++i) c->h_pose[i] = pose[i];
-  LM_CUDA(cudaMemcpyAsync(c->d_state->cand, c->h_pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  LM_LAUNCH(c, k_state_init, 1, 32, 0, c->d_state, c->d_state->cand);
+  Pose7 prior;
+  for (int i = 0; i < 7; ++i) prior.v[i] = pose[i];
+  LM_LAUNCH(c, k_state_init, 1, 32, 0, c->d_state, prior);
   const double alg_bytes = 16.0 * ((double)upper + (double)c->map[0].n_host + (double)c->map[1].n_host) + 216.0;
   for (int it = 0; it < outer_count; ++it) {
     sp.iter = it;
