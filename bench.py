@@ -28,9 +28,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
-METRIC = "scan-to-map registrations/sec (HDL-64 synthetic)"
+METRIC = "scan-to-map registrations/sec (HDL-64 synthetic)"   # renamed for --sensor vlp16 in main()
 UNIT = "scans/s"
-SENSOR = "hdl64"
+SENSOR = "hdl64"   # --sensor vlp16 switches to BASELINE.json configs[0] (not the headline line)
+SENSORS = {"hdl64": (64, "HDL-64 synthetic 64x2048 sweep (~131k pts)"), "vlp16": (16, "VLP-16 synthetic 16x1800 sweep (~29k pts)")}
 # Untimed initialisation sweeps in front of every pass (ours and the reference arm alike): a tracker that has just been
 # reset is not the workload — its sliding window fills over the first ten keyframes (~20 sweeps at 1.5 m/s) and the
 # Huber-LM outer-iteration budget decays 9, 8, ..., 2 over the first eight solves (ceres_edgeSurfFeatureRegistration.hpp:
@@ -141,7 +142,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     pkg = entry.load_package()
-    ctx = pkg.context(local, n_scans=64, max_points=1 << 18)
+    ctx = pkg.context(local, n_scans=SENSORS[SENSOR][0], max_points=1 << 18)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
     n_pts = [int(s.shape[0]) for s in sweeps]
@@ -249,7 +250,7 @@ def run_ours(args):
             "metric": METRIC, "value": n_gpus * K / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
             "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "HDL-64 synthetic 64x2048 sweep (~131k pts) scan-to-map edge/surf registration, "
+            "config": {"workload": SENSORS[SENSOR][1] + " scan-to-map edge/surf registration, "
                                    "Huber-LM solver, raw 10-keyframe sliding-window map, one sequence per GPU",
                        "points_per_sweep": int(np.mean(n_pts)), "sequences": n_gpus,
                        "l2": f"{FLUSH_BYTES >> 20} MiB memset between timed steps (L2 flush: 1.5x the 126 MB L2), inside the timed region",
@@ -294,7 +295,7 @@ def cpu_baseline(sweeps, W, sample=4):
     timed with ONE thread — the reference runs one thread per LiDAR (System/ML_System.hpp:137,248)."""
     lib = entry.load_oracle()
     threads = os.cpu_count() or 1
-    o = lib.context(0, n_scans=64, oracle_knn_mode=0, oracle_threads=threads)
+    o = lib.context(0, n_scans=SENSORS[SENSOR][0], oracle_knn_mode=0, oracle_threads=threads)
     warm = min(SETTLE + W, len(sweeps) - sample - 1)
     for k in range(0, warm + 1):
         o.tracker_step(sweeps[k], 0.1 * k)
@@ -305,7 +306,7 @@ def cpu_baseline(sweeps, W, sample=4):
     dt = time.perf_counter() - t0
     o.close()
     return {"value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{sample} consecutive HDL-64 sweeps after a {warm}-sweep warm-up of the same sequence, "
+            "sample": f"{sample} consecutive {SENSOR} sweeps after a {warm}-sweep warm-up of the same sequence, "
                       f"oracle tracker (kd-tree kNN), 1 thread; host has {threads} cores",
             "seconds": dt}
 
@@ -321,7 +322,7 @@ def run_reference(args):
     sweeps = make_sequence(SETTLE + W + K + 1, seq=0)
     lib = entry.load_oracle()
     threads = os.cpu_count() or 1
-    o = lib.context(0, n_scans=64, oracle_knn_mode=0, oracle_threads=threads)
+    o = lib.context(0, n_scans=SENSORS[SENSOR][0], oracle_knn_mode=0, oracle_threads=threads)
     for k in range(0, SETTLE + W + 1):
         o.tracker_step(sweeps[k], 0.1 * k)
     per = []
@@ -337,7 +338,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "HDL-64 synthetic 64x2048 sweep (~131k pts) scan-to-map edge/surf registration, "
+        "config": {"workload": SENSORS[SENSOR][1] + " scan-to-map edge/surf registration, "
                                "Huber-LM solver, raw 10-keyframe sliding-window map, one sequence",
                    "p50_ms_per_scan": float(np.median(per))},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
@@ -528,11 +529,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sensor", default="hdl64", choices=sorted(SENSORS), help="hdl64 = the headline configuration")
     ap.add_argument("--workload", default="registration", choices=["registration", "loopdb"],
                     help="registration = the headline metric (default); loopdb = sharded loop-closure descriptor search")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    global SENSOR, METRIC
+    SENSOR = args.sensor
+    if SENSOR != "hdl64":
+        METRIC = METRIC.replace("HDL-64", "VLP-16")
     if args.workload == "loopdb":
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "loopdb workload: the CPU port is timed inside the "
