@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(128, KNN_MINBLOCKS) k_knn(const int* __restric
                                              const float4* __restrict__ feat,
                                              const int* __restrict__ counts, SolveState* __restrict__ st,
                                              MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
-                                             int seeded, int reverse, int assoc, int* __restrict__ nbr) {
+                                             int seeded, int reverse, int assoc, int chunk, int* __restrict__ nbr) {
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   const int n_e = counts[0], n_s = counts[1];
   const int lane = threadIdx.x & 31;
@@ -927,14 +927,18 @@ __global__ void __launch_bounds__(128, KNN_MINBLOCKS) k_knn(const int* __restric
       }
       width = min(8, nh - base);
     } else {
-      if (lane == 0) base = atomicAdd(&st->knn_next, 32);
+      // `chunk` queries per warp (32, 16 or 8: the host picks it so that a small sweep still spreads over every
+      // resident warp — a chunk is a serial, divergent piece of work and its latency, not the SM's throughput,
+      // bounds a launch that has fewer chunks than warp slots)
+      if (lane == 0) base = atomicAdd(&st->knn_next, chunk);
       base = __shfl_sync(0xffffffffu, base, 0);
       if (base >= live) break;
+      width = chunk;
     }
     TSTAMP(t_chunk0);
     // (handing the chunks out from the end — high rings first — was measured: 802 vs 753 us per sweep; kept as a
     //  tuning switch only)
-    int t = (reverse ? ((live + 31) / 32) * 32 - 32 - base : base) + lane;
+    int t = (reverse ? ((live + chunk - 1) / chunk) * chunk - chunk - base : base) + lane;
     if (lane >= width || t >= upper || t >= live) continue;  // positions >= live: padding (sorted) or unset (ring order)
     int f = perm[t];
     if (f >= live) continue;
@@ -1463,10 +1467,14 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
     }
     {
       StageScope scope(c, LMSF_STAGE_MATCH);
-      int knn_grid = div_up(up, 128);
+      static const int knn_width = env_int("LMSF_KNN_WIDTH", 0);  // tuning experiments
+      int chunk = 32;  // queries per warp: halve it while the sweep has fewer chunks than ~1.5x the resident warps
+      while (chunk > 8 && up / chunk < 148 * 24 * 3 / 2) chunk >>= 1;
+      if (knn_width == 8 || knn_width == 16 || knn_width == 32) chunk = knn_width;
+      int knn_grid = div_up(up, 4 * chunk);
       if (knn_grid > 148 * knn_per_sm) knn_grid = 148 * knn_per_sm;  // persistent: every resident warp pulls work
       LM_LAUNCH(c, k_knn, knn_grid, 128, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, up,
-                solver, it == 0 ? 0 : 1, (ring_order && knn_reverse) ? 1 : 0, ring_order ? 1 : 0, c->d_nbr);
+                solver, it == 0 ? 0 : 1, (ring_order && knn_reverse) ? 1 : 0, ring_order ? 1 : 0, chunk, c->d_nbr);
       c->match_bytes += alg_bytes;
       c->match_launches += 1;
     }
