@@ -149,8 +149,11 @@ __device__ __forceinline__ const CellRec* find_cell(const MapView& mv, const Map
 __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz,
                                            Top5& nb, bool seeded KS_DECL) {
   KSTAT(ks.cand += e - s;)
+  if (s >= e) return;
+  float4 nxt = __ldg(&pts[s]);  // the next candidate is in flight while the current one is judged
   for (int p = s; p < e; ++p) {
-    float4 m = __ldg(&pts[p]);
+    const float4 m = nxt;
+    if (p + 1 < e) nxt = __ldg(&pts[p + 1]);
     float dx = m.x - qx, dy = m.y - qy, dz = m.z - qz;
     float r = dx * dx;
     r = r + dy * dy;
