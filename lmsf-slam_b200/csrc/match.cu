@@ -905,40 +905,23 @@ __global__ void __launch_bounds__(128, KNN_MINBLOCKS) k_knn(const int* __restric
                                              const float4* __restrict__ feat,
                                              const int* __restrict__ counts, SolveState* __restrict__ st,
                                              MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
-                                             int seeded, int reverse, int assoc, int chunk, int* __restrict__ nbr) {
+                                             int seeded, int assoc, int chunk, int* __restrict__ nbr) {
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   const int n_e = counts[0], n_s = counts[1];
   const int lane = threadIdx.x & 31;
   const int live = n_e + n_s;  // sorted positions >= live are padding
-  const int nh = min(st->n_heavy, live);
-  // (chunks of 8 for the heavy queries were measured: 30 % slower — with ~one 32-query chunk per resident warp
-  //  the kernel is bounded by instruction throughput of the heavy lanes, not by the latency of one chunk)
-  bool heavy_left = false && nh > 0;
   while (true) {
-    // heavy queries (sorted first) go out eight at a time: a chunk's latency is the sum of its lanes'
-    // divergent searches, and these are the long ones; the rest go out a full warp at a time
-    int base = 0, width = 32;
-    if (heavy_left) {
-      if (lane == 0) base = atomicAdd(&st->knn_next_heavy, 8);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (base >= nh) {
-        heavy_left = false;
-        continue;
-      }
-      width = min(8, nh - base);
-    } else {
-      // `chunk` queries per warp (32, 16 or 8: the host picks it so that a small sweep still spreads over every
-      // resident warp — a chunk is a serial, divergent piece of work and its latency, not the SM's throughput,
-      // bounds a launch that has fewer chunks than warp slots)
-      if (lane == 0) base = atomicAdd(&st->knn_next, chunk);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (base >= live) break;
-      width = chunk;
-    }
+    // `chunk` queries per warp (32, 16 or 8: the host picks it so that a small sweep still spreads over every
+    // resident warp — a chunk is a serial, divergent piece of work and its latency, not the SM's throughput,
+    // bounds a launch that has fewer chunks than warp slots).  (Measured and dropped: handing the expensive
+    // queries out eight at a time, +30 %; handing the chunks out from the end, 802 vs 753 us per sweep.)
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&st->knn_next, chunk);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= live) break;
+    const int width = chunk;
     TSTAMP(t_chunk0);
-    // (handing the chunks out from the end — high rings first — was measured: 802 vs 753 us per sweep; kept as a
-    //  tuning switch only)
-    int t = (reverse ? ((live + chunk - 1) / chunk) * chunk - chunk - base : base) + lane;
+    int t = base + lane;
     if (lane >= width || t >= upper || t >= live) continue;  // positions >= live: padding (sorted) or unset (ring order)
     int f = perm[t];
     if (f >= live) continue;
@@ -1429,7 +1412,6 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
   // permutation that walks the surfs along their rings (consecutive positions are neighbours in space): no sort.
   // Caller-supplied or voxel-filtered features are sorted by map cell once per solve instead.
   static const int force_qsort = env_int("LMSF_FORCE_QSORT", 0);  // tuning experiments
-  static const int knn_reverse = env_int("LMSF_KNN_REVERSE", 0);
   const bool ring_order = c->perm_valid && !force_qsort;
   const int* perm = ring_order ? c->d_perm : c->q_vals_alt;
   QueryBufs qb;
@@ -1474,7 +1456,7 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       int knn_grid = div_up(up, 4 * chunk);
       if (knn_grid > 148 * knn_per_sm) knn_grid = 148 * knn_per_sm;  // persistent: every resident warp pulls work
       LM_LAUNCH(c, k_knn, knn_grid, 128, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, up,
-                solver, it == 0 ? 0 : 1, (ring_order && knn_reverse) ? 1 : 0, ring_order ? 1 : 0, chunk, c->d_nbr);
+                solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_nbr);
       c->match_bytes += alg_bytes;
       c->match_launches += 1;
     }
