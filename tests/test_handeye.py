@@ -148,3 +148,17 @@ def test_rig_calibrates_then_refines(gpu_lib, synth):
         assert np.linalg.norm(r.extrinsic[4:] - te) < 0.03
     finally:
         r.close()
+
+
+def test_rig_pose_algebra(synth):
+    """rig.pose_mul / pose_inv (host side of the calibration loop) against 4x4 matrices."""
+    from lmsf_slam_b200 import rig
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        A, B = np.eye(4), np.eye(4)
+        A[:3, :3], A[:3, 3] = rot(rng.normal(size=3), rng.uniform(0, 3.0)), rng.normal(size=3)
+        B[:3, :3], B[:3, 3] = rot(rng.normal(size=3), rng.uniform(0, 3.0)), rng.normal(size=3)
+        pa, pb = to_pose(A[:3, :3], A[:3, 3], synth), to_pose(B[:3, :3], B[:3, 3], synth)
+        assert np.allclose(synth.qt_to_mat(rig.pose_mul(pa, pb)), A @ B, atol=1e-12)
+        assert np.allclose(synth.qt_to_mat(rig.pose_inv(pa)), np.linalg.inv(A), atol=1e-12)
+        assert np.allclose(synth.qt_to_mat(rig.pose_mul(rig.pose_inv(pa), pa)), np.eye(4), atol=1e-12)
