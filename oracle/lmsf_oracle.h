@@ -16,7 +16,9 @@
  * cited per function in lmsf_oracle.cpp, (ii) numpy / scipy cross-checks of its
  * linear algebra and of its Huber-LM solve (tests/), (iii) the reference's
  * vendored nanoflann 1.3.2 (compiled from /root/reference into oracle/_ref) as
- * an independent exact-kNN check.
+ * an independent exact-kNN check — for the 3-D map search and, through the
+ * reference's own KDTreeVectorOfVectorsAdaptor, for the 20-D ring-key search of
+ * the loop-closure path, which is thereby the one piece pinned bit for bit.
  *
  * The entry points mirror include/lmsf_b200.h one to one (prefix lmsf_oracle_)
  * so that the parity tests drive both through the same ctypes wrapper; the

@@ -1,6 +1,8 @@
 // lmsf_oracle_sc.cpp — CPU ORACLE of the loop-closure descriptor path ("next" row f1, BASELINE config 5).
 //
-// TEST INFRASTRUCTURE ONLY (see lmsf_oracle.h; parity unpinned: the reference has no fixtures for it either).
+// TEST INFRASTRUCTURE ONLY (see lmsf_oracle.h).  Parity unpinned for the descriptor and the SC distance (the reference has
+// no fixtures for them, Eigen / PCL are absent); the ring-key search IS pinned: tests/test_oracle_sc.py compares it bit for
+// bit with the reference's own KDTreeVectorOfVectorsAdaptor over its vendored nanoflann, compiled into oracle/_ref.
 // Restates, with file:line under src/MultiSensorFusionEstimator3D/include/:
 //   ScanContext::MakeScanContext / MakeRingkeyFromScanContext / DistanceBtnScanContext / distDirectSC /
 //   fastAlignUsingVkey / circshift / xy2theta
