@@ -13,6 +13,7 @@
 // sequential semantics: `disable_point` is shared by the six sectors of a ring
 // (:75-78), so one block walks a ring's sectors in order.
 #include "common.cuh"
+#include "fmath.cuh"
 
 namespace lm {
 
@@ -31,7 +32,9 @@ struct ExtractParams {
 __device__ __forceinline__ int ring_of(float4 p, const ExtractParams& prm) {
   if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) return -1;
   float s = p.x * p.x + p.y * p.y;
-  double distance = sqrt((double)s);
+  // sqrt(float) is std::sqrt(float) in the reference's translation unit (`using namespace std;`, utility.hpp:51):
+  // a correctly rounded float square root, widened
+  double distance = (double)__fsqrt_rn(s);
   if (distance > (double)prm.max_range || distance < (double)prm.min_range) return -1;
   double angle = atan((double)p.z / distance) * 180 / 3.14159265358979323846;
   int id;
@@ -217,15 +220,16 @@ __global__ void __launch_bounds__(256) k_sector_sort(const float4* __restrict__ 
 // point second (disable j-5..j).
 __device__ __forceinline__ int bad_class(const float4* __restrict__ p, int j) {
   float4 a = p[j], b = p[j + 1];
-  double a0 = atan2((double)a.x, (double)a.y);
-  double a1 = atan2((double)b.x, (double)b.y);
+  // atan2 of two floats = std::atan2(float, float) = the C library's atan2f (:223-224); fmath.cuh returns its bits
+  double a0 = (double)atan2f_fdlibm(a.x, a.y);
+  double a1 = (double)atan2f_fdlibm(b.x, b.y);
   double da = fabs(a0 - a1);
   const double PI = 3.14159265358979323846;
   if (da > PI) da = PI * 2 - da;
   if (da > 0.0175) return 1;
   float s0 = a.x * a.x + a.y * a.y + a.z * a.z;
   float s1 = b.x * b.x + b.y * b.y + b.z * b.z;
-  double d0 = sqrt((double)s0), d1 = sqrt((double)s1);
+  double d0 = (double)__fsqrt_rn(s0), d1 = (double)__fsqrt_rn(s1);  // std::sqrt(float) (:247-252)
   double ang = (d0 < d1) ? atan2(d0 * da, d1 - d0) : atan2(d1 * da, d0 - d1);
   if (ang <= 0.17) return (d0 < d1) ? 2 : 3;
   return 0;

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "dmath.cuh"
+#include "fmath.cuh"
 
 using namespace lm;
 
@@ -31,6 +32,42 @@ HD void run_case(const Case& c, Out& o) {
 __global__ void k_run(const Case* c, Out* o, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) run_case(c[i], o[i]);
+}
+
+// fmath.cuh on the device against the host C library's atan2f / sqrtf (the std::atan2(float, float) / std::sqrt(float)
+// the reference's bad-point test calls): bit for bit
+__global__ void k_fm(const float2* in, float2* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float2(atan2f_fdlibm(in[i].x, in[i].y), __fsqrt_rn(fabsf(in[i].x)));
+}
+
+static int check_fmath() {
+  const int n = 1 << 22;
+  float2* h = (float2*)malloc(n * sizeof(float2));
+  float2* r = (float2*)malloc(n * sizeof(float2));
+  for (int i = 0; i < n; ++i) {
+    float sc = (i & 1) ? 100.f : 4.f;
+    h[i] = make_float2((rand() / (float)RAND_MAX - 0.5f) * 2 * sc, (rand() / (float)RAND_MAX - 0.5f) * 2 * sc);
+  }
+  float2 *d_in, *d_out;
+  cudaMalloc(&d_in, n * sizeof(float2));
+  cudaMalloc(&d_out, n * sizeof(float2));
+  cudaMemcpy(d_in, h, n * sizeof(float2), cudaMemcpyHostToDevice);
+  k_fm<<<(n + 255) / 256, 256>>>(d_in, d_out, n);
+  if (cudaMemcpy(r, d_out, n * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  int bad = 0;
+  for (int i = 0; i < n; ++i) {
+    float a = atan2f(h[i].x, h[i].y), s = sqrtf(fabsf(h[i].x));
+    if (memcmp(&a, &r[i].x, 4) != 0 || memcmp(&s, &r[i].y, 4) != 0) {
+      if (bad < 5) printf("atan2f(%a, %a): host %a device %a; sqrtf host %a device %a\n", h[i].x, h[i].y, a, r[i].x, s, r[i].y);
+      ++bad;
+    }
+  }
+  cudaFree(d_in);
+  cudaFree(d_out);
+  free(h);
+  free(r);
+  return bad;
 }
 
 static double rnd() { return rand() / (double)RAND_MAX - 0.5; }
@@ -116,6 +153,8 @@ int main() {
     for (int i = 0; i < 7; ++i)
       if (fabs(ho[t].plus[i] - hd[t].plus[i]) > 1e-14 * (1 + fabs(ho[t].plus[i]))) ++bad_plus;
   }
-  printf("cases %d  bit mismatches %d  se3_plus out of tolerance %d\n", n, bad, bad_plus);
-  return (bad || bad_plus) ? 1 : 0;
+  int bad_fm = check_fmath();
+  printf("cases %d  bit mismatches %d  se3_plus out of tolerance %d  atan2f/sqrtf mismatches (4M arguments) %d\n", n, bad, bad_plus,
+         bad_fm);
+  return (bad || bad_plus || bad_fm) ? 1 : 0;
 }

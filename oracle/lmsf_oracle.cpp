@@ -239,7 +239,10 @@ struct Features {
 // splitScan (FeatureExtract/LOAMFeatureProcessor_base.hpp:290-343).  ring id or -1.
 static int ring_of(const P4& p, int n_scans, float min_d, float max_d) {
   float s = p.x * p.x + p.y * p.y;  // float products and sum (:300-301)
-  double distance = std::sqrt((double)s);
+  // `sqrt(float)` resolves to std::sqrt(float): `using namespace std;` (src/apps/include/utility.hpp:51, reached through
+  // ros_utils.hpp) precedes this header in the node's translation unit (MultiLidarSLAM_node.cpp:10-17) — confirmed by
+  // compiling the reference's own header (oracle/ref_loam.cpp), which this function must match bit for bit
+  double distance = (double)std::sqrt(s);
   if (distance > max_d || distance < min_d) return -1;
   double angle = std::atan(p.z / distance) * 180 / M_PI;
   int id = 0;
@@ -266,8 +269,8 @@ static int ring_of(const P4& p, int n_scans, float min_d, float max_d) {
 static void check_bad(const std::vector<P4>& pc, std::vector<int>& disable) {
   int P = (int)pc.size();
   for (int j = 5; j < P - 6; j++) {
-    double a0 = std::atan2((double)pc[j].x, (double)pc[j].y);
-    double a1 = std::atan2((double)pc[j + 1].x, (double)pc[j + 1].y);
+    double a0 = (double)std::atan2(pc[j].x, pc[j].y);  // two float arguments: std::atan2(float, float) (:223-224)
+    double a1 = (double)std::atan2(pc[j + 1].x, pc[j + 1].y);
     double da = std::fabs(a0 - a1);
     if (da > M_PI) da = M_PI * 2 - da;
     if (da > 0.0175) {
@@ -277,7 +280,7 @@ static void check_bad(const std::vector<P4>& pc, std::vector<int>& disable) {
     }
     float s0 = pc[j].x * pc[j].x + pc[j].y * pc[j].y + pc[j].z * pc[j].z;
     float s1 = pc[j + 1].x * pc[j + 1].x + pc[j + 1].y * pc[j + 1].y + pc[j + 1].z * pc[j + 1].z;
-    double d0 = std::sqrt((double)s0), d1 = std::sqrt((double)s1);
+    double d0 = (double)std::sqrt(s0), d1 = (double)std::sqrt(s1);  // std::sqrt(float) (:247-252)
     double ang;
     if (d0 < d1)
       ang = std::atan2(d0 * da, d1 - d0);

@@ -452,7 +452,8 @@ def test_errors_and_capacity(gpu_lib):
 
 # ---------------------------------------------------------------- native checks
 def test_device_algebra_bit_exact():
-    """dmath.cuh on the B200 vs the same code on the host: QR, Jacobi, inverse, Cholesky bit for bit."""
+    """dmath.cuh on the B200 vs the same code on the host: QR, Jacobi, inverse, Cholesky bit for bit; fmath.cuh's
+    atan2f and the device's sqrtf against the host C library on 4 M arguments, bit for bit."""
     import os
     import subprocess
     import __graft_entry__ as entry
@@ -460,6 +461,7 @@ def test_device_algebra_bit_exact():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "bit mismatches 0" in r.stdout
+    assert "atan2f/sqrtf mismatches (4M arguments) 0" in r.stdout, r.stdout
 
 
 def test_cpp_adapters_match_ctypes_path(gpu_lib, sweeps, tmp_path):

@@ -1,6 +1,7 @@
 """CPU tests of the oracle (no GPU): golden fixtures, numpy / scipy cross-checks of its algebra and of
-its Huber-LM loop, independent numpy restatements of feature extraction and the voxel grid, and the
-reference's own vendored nanoflann (oracle/_ref) as an exact-kNN cross-check."""
+its Huber-LM loop, independent numpy restatements of feature extraction and the voxel grid, and two pieces of the
+reference's OWN code compiled into oracle/_ref: its LOAM feature extractor / common point-cloud process (bit-exact
+pin of rows a1 and f4) and its vendored nanoflann (exact-kNN cross-check)."""
 import ctypes as C
 import math
 import os
@@ -124,13 +125,21 @@ def test_se3_exp_vs_scipy(oracle_lib):
 
 
 # ---------------------------------------------------------------- independent restatement: feature extraction
+_libm = C.CDLL("libm.so.6")
+_libm.atan2f.restype = C.c_float
+_libm.atan2f.argtypes = [C.c_float, C.c_float]
+_libm.sqrtf.restype = C.c_float
+_libm.sqrtf.argtypes = [C.c_float]
+
+
 def _py_extract(sw, n_scans=16, min_d=2.0, max_d=80.0, thresh=1.0):
-    """Straight numpy/Python transcription of LOAMFeatureProcessor_base.hpp:59-343 (VLP-16 branch)."""
+    """Straight numpy/Python transcription of LOAMFeatureProcessor_base.hpp:59-343 (VLP-16 branch).  `sqrt` / `atan2`
+    of float arguments are the C library's sqrtf / atan2f (std:: overloads, `using namespace std;` utility.hpp:51)."""
     f32 = np.float32
     rings = [[] for _ in range(n_scans)]
     for i, p in enumerate(sw):
         s = f32(p[0] * p[0]) + f32(p[1] * p[1])
-        dist = math.sqrt(float(f32(s)))
+        dist = float(_libm.sqrtf(float(f32(s))))
         if dist > max_d or dist < min_d:
             continue
         ang = math.atan(float(p[2]) / dist) * 180 / math.pi
@@ -150,8 +159,8 @@ def _py_extract(sw, n_scans=16, min_d=2.0, max_d=80.0, thresh=1.0):
         is_edge = np.zeros(P, int)
         j = 5
         while j < P - 6:
-            a0 = math.atan2(float(x[j]), float(y[j]))
-            a1 = math.atan2(float(x[j + 1]), float(y[j + 1]))
+            a0 = float(_libm.atan2f(float(x[j]), float(y[j])))
+            a1 = float(_libm.atan2f(float(x[j + 1]), float(y[j + 1])))
             da = abs(a0 - a1)
             if da > math.pi:
                 da = math.pi * 2 - da
@@ -159,8 +168,8 @@ def _py_extract(sw, n_scans=16, min_d=2.0, max_d=80.0, thresh=1.0):
                 dis[j - 5:j + 6] = 1
                 j += 5
                 continue
-            d0 = math.sqrt(float(f32(f32(f32(x[j] * x[j]) + f32(y[j] * y[j])) + f32(z[j] * z[j]))))
-            d1 = math.sqrt(float(f32(f32(f32(x[j + 1] * x[j + 1]) + f32(y[j + 1] * y[j + 1])) + f32(z[j + 1] * z[j + 1]))))
+            d0 = float(_libm.sqrtf(float(f32(f32(f32(x[j] * x[j]) + f32(y[j] * y[j])) + f32(z[j] * z[j])))))
+            d1 = float(_libm.sqrtf(float(f32(f32(f32(x[j + 1] * x[j + 1]) + f32(y[j + 1] * y[j + 1])) + f32(z[j + 1] * z[j + 1])))))
             ang = math.atan2(d0 * da, d1 - d0) if d0 < d1 else math.atan2(d1 * da, d0 - d1)
             if ang <= 0.17:
                 if d0 < d1:
@@ -237,6 +246,95 @@ def test_extract_edge_cases(oracle_lib, synth):
     sw = synth.make_sweep(synth.hdl64(), 0)
     lab, e, s = o64.extract_features(sw)
     assert len(e) <= 64 * 6 * 20 and len(e) > 500 and len(s) > 100000
+
+
+# ---------------------------------------------------------------- the reference's OWN extraction code (oracle/_ref)
+class _RefLoam:
+    """oracle/_ref/libref_loam.so: LOAMFeatureProcessorBase / PointCloudCommonProcess compiled from the reference's
+    unmodified headers where they lie (oracle/Makefile, oracle/ref_loam.cpp, PCL as a container: oracle/shim/)."""
+
+    def __init__(self):
+        path = os.path.join(os.path.dirname(entry.ORACLE_LIB), "_ref", "libref_loam.so")
+        if not os.path.exists(path):
+            pytest.skip("oracle/_ref/libref_loam.so is not built (needs /root/reference)")
+        self.dll = C.CDLL(path)
+
+    def extract(self, sw, n_scans, min_r=2.0, max_r=80.0, thresh=1.0, bad=True):
+        sw = np.ascontiguousarray(sw, np.float32)
+        n = len(sw)
+        fp = C.POINTER(C.c_float)
+        e, s = np.zeros((max(n, 1), 4), np.float32), np.zeros((max(n, 1), 4), np.float32)
+        ne, ns = C.c_int(0), C.c_int(0)
+        rc = self.dll.ref_loam_extract(sw.ctypes.data_as(fp), n, n_scans, C.c_float(min_r), C.c_float(max_r),
+                                       C.c_float(thresh), int(bad), n, e.ctypes.data_as(fp), C.byref(ne),
+                                       s.ctypes.data_as(fp), C.byref(ns))
+        assert rc == 0
+        return e[:ne.value], s[:ns.value]
+
+    def common_process(self, sw, remove_nan, near, far):
+        sw = np.ascontiguousarray(sw, np.float32)
+        n = len(sw)
+        fp = C.POINTER(C.c_float)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        m = C.c_int(0)
+        rc = self.dll.ref_common_process(sw.ctypes.data_as(fp), n, int(remove_nan), C.c_float(near), C.c_float(far), n,
+                                         out.ctypes.data_as(fp), C.byref(m))
+        assert rc == 0
+        return out[:m.value]
+
+
+@pytest.fixture(scope="module")
+def ref_loam():
+    return _RefLoam()
+
+
+def test_extract_vs_reference_code(oracle_lib, synth, ref_loam):
+    """Rows a1.1-a1.4 PINNED: the oracle against the reference's own LOAMFeatureProcessorBase::Process, compiled from
+    its unmodified source.  Edge and surf clouds are identical bit for bit, order included, on full-size VLP-16 and
+    HDL-64 sweeps, ragged rings, the 32-line branch, other thresholds and the degenerate inputs."""
+    rng = np.random.default_rng(11)
+    cases = []
+    for k in (0, 1, 7, 50, 120):
+        cases.append((16, synth.make_sweep(synth.vlp16(), k), {}))
+    for k in (0, 1, 7, 50):
+        cases.append((64, synth.make_sweep(synth.hdl64(), k), {}))
+    sw = synth.make_sweep(synth.vlp16(), 3)
+    cases.append((16, sw[rng.random(len(sw)) > 0.3], {}))                       # ragged rings
+    cases.append((16, sw, dict(thresh=0.2)))
+    cases.append((16, sw, dict(bad=False)))
+    cases.append((16, sw, dict(min_r=5.0, max_r=30.0)))
+    cases.append((32, sw, {}))                                                  # 32-line ring formula on the same rays
+    h = synth.make_sweep(synth.hdl64(), 9)
+    cases.append((64, h[rng.random(len(h)) > 0.5], dict(thresh=0.5)))
+    cases.append((64, h[: 64 * 15], {}))                                        # < 20 points per ring
+    cases.append((16, sw[: 16 * 40], {}))                                       # short rings: 30 candidates, sectors of 5
+    cases.append((16, np.zeros((0, 4), np.float32), {}))
+    n_feat = 0
+    for n_scans, cloud, kw in cases:
+        o = oracle_lib.context(0, n_scans=n_scans, min_range=kw.get("min_r", 2.0), max_range=kw.get("max_r", 80.0),
+                               edge_thresh=kw.get("thresh", 1.0), remove_bad_points=int(kw.get("bad", True)))
+        _, oe, os_ = o.extract_features(cloud)
+        re_, rs_ = ref_loam.extract(cloud, n_scans, **kw)
+        assert (len(oe), len(os_)) == (len(re_), len(rs_)), (n_scans, len(cloud), kw)
+        assert np.array_equal(bits(oe), bits(re_)) and np.array_equal(bits(os_), bits(rs_)), (n_scans, len(cloud), kw)
+        n_feat += len(oe) + len(os_)
+        o.close()
+    assert n_feat > 800000
+
+
+def test_common_process_vs_reference_code(oracle_lib, synth, ref_loam):
+    """Row f4 PINNED (removeNaN + DistanceFilter; the VoxelGrid stage is PCL arithmetic, not available): the oracle
+    against the reference's own PointCloudCommonProcess::Process (common_processing.hpp:87-111)."""
+    o = oracle_lib.context(0, n_scans=16)
+    sw = synth.make_sweep(synth.vlp16(), 2).copy()
+    sw[::31, 0] = np.nan
+    sw[5, 2] = np.inf
+    sw[77, 1] = -np.inf
+    for near, far in ((0.0, 0.0), (3.0, 25.5), (0.0, 10.0), (7.25, 7.5)):
+        ref = ref_loam.common_process(sw, True, near, far)
+        out = o.common_process(sw, True, 0.0, near, far)
+        assert np.array_equal(bits(out), bits(ref)), (near, far)
+    o.close()
 
 
 # ---------------------------------------------------------------- independent restatement: voxel grid
