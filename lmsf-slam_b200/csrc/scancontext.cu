@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "fmath.cuh"
 
 namespace lm {
 
@@ -100,13 +101,15 @@ __device__ __forceinline__ int ceil_to_int(double v) {
   return (int)c;
 }
 
-// xy2theta (Scancontext.hpp:304-318): double atan of the float quotient, returned as float
+// xy2theta (Scancontext.hpp:304-318): atan of the float quotient is std::atan(float) = the C library's atanf in the
+// reference's translation unit (`using namespace std;`, utility.hpp:51; fmath.cuh returns its bits), widened for the
+// product with 180 / M_PI, returned as float
 __device__ __forceinline__ float xy2theta(float x, float y) {
   const double k = 180 / M_PI;
-  if (x >= 0 && y >= 0) return (float)(k * atan((double)(y / x)));
-  if (x < 0 && y >= 0) return (float)(180 - (k * atan((double)(y / (-x)))));
-  if (x < 0 && y < 0) return (float)(180 + (k * atan((double)(y / x))));
-  if (x >= 0 && y < 0) return (float)(360 - (k * atan((double)((-y) / x))));
+  if (x >= 0 && y >= 0) return (float)(k * (double)atanf_fdlibm(y / x));
+  if (x < 0 && y >= 0) return (float)(180 - (k * (double)atanf_fdlibm(y / (-x))));
+  if (x < 0 && y < 0) return (float)(180 + (k * (double)atanf_fdlibm(y / x)));
+  if (x >= 0 && y < 0) return (float)(360 - (k * (double)atanf_fdlibm((-y) / x)));
   return __int_as_float(0x7fc00000);
 }
 
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(256) k_sc_bin(const float4* __restrict__ pts, 
     float x = p.x, y = p.y;
     float z = (float)((double)p.z + 2.0);
     float xx = x * x, yy = y * y;
-    float rng = (float)sqrt((double)(xx + yy));
+    float rng = (float)sqrt((double)(xx + yy));  // == std::sqrt(float) (:78): rounding a double sqrt to float is exact
     float ang = xy2theta(x, y);
     if ((double)rng > 80.0) continue;
     int ring = max(min(SC_NR, ceil_to_int(((double)rng / 80.0) * SC_NR)), 1);

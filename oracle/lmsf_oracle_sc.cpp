@@ -23,12 +23,14 @@ namespace {
 const int NR = 20, NS = 60;
 const double MAX_RADIUS = 80.0, LIDAR_HEIGHT = 2.0;
 
-// xy2theta (Scancontext.hpp:304-314); atan on the float quotient, result returned as float
+// xy2theta (Scancontext.hpp:304-314); atan on the float quotient is std::atan(float) — `using namespace std;`
+// (src/apps/include/utility.hpp:51) precedes this header in the node's translation unit, as for the feature extractor
+// (see ring_of in lmsf_oracle.cpp) — its float result widened for the product with 180 / M_PI, returned as float
 float xy2theta(float x, float y) {
-  if (x >= 0 && y >= 0) return (float)((180 / M_PI) * std::atan((double)(y / x)));
-  if (x < 0 && y >= 0) return (float)(180 - ((180 / M_PI) * std::atan((double)(y / (-x)))));
-  if (x < 0 && y < 0) return (float)(180 + ((180 / M_PI) * std::atan((double)(y / x))));
-  if (x >= 0 && y < 0) return (float)(360 - ((180 / M_PI) * std::atan((double)((-y) / x))));
+  if (x >= 0 && y >= 0) return (float)((180 / M_PI) * std::atan(y / x));
+  if (x < 0 && y >= 0) return (float)(180 - ((180 / M_PI) * std::atan(y / (-x))));
+  if (x < 0 && y < 0) return (float)(180 + ((180 / M_PI) * std::atan(y / x)));
+  if (x >= 0 && y < 0) return (float)(360 - ((180 / M_PI) * std::atan((-y) / x)));
   return std::numeric_limits<float>::quiet_NaN();
 }
 
@@ -46,7 +48,7 @@ void make_sc(const float* xyzi, int n, float* desc) {
   for (int i = 0; i < n; ++i) {
     float x = xyzi[4 * i], y = xyzi[4 * i + 1];
     float z = (float)((double)xyzi[4 * i + 2] + LIDAR_HEIGHT);
-    float azim_range = (float)std::sqrt((double)(x * x + y * y));
+    float azim_range = std::sqrt(x * x + y * y);  // std::sqrt(float) (:78)
     float azim_angle = xy2theta(x, y);
     if (azim_range > MAX_RADIUS) continue;
     int ring = std::max(std::min(NR, ceil_to_int(((double)azim_range / MAX_RADIUS) * NR)), 1);

@@ -85,6 +85,16 @@ def ref_ringkey_knn10(keys, q_keys):
 
 
 # ---------------------------------------------------------------- independent numpy transcription
+_libm = C.CDLL("libm.so.6")
+_libm.atanf.restype = C.c_float
+_libm.atanf.argtypes = [C.c_float]
+
+
+def _atanf(q):
+    """std::atan(float) of the reference's translation unit = the C library's atanf, element by element, as float64."""
+    return np.array([_libm.atanf(float(v)) for v in np.asarray(q, np.float32)], np.float64)
+
+
 def py_make_sc(xyzi):
     """Scancontext.hpp:59-104 + :112-126, written independently of the C++ oracle (vectorised numpy)."""
     p = np.asarray(xyzi, np.float32).reshape(-1, 4)
@@ -98,10 +108,10 @@ def py_make_sc(xyzi):
         q2 = (x < 0) & (y >= 0)
         q3 = (x < 0) & (y < 0)
         q4 = (x >= 0) & (y < 0)
-        ang[q1] = k * np.arctan((y[q1] / x[q1]).astype(np.float64))
-        ang[q2] = 180 - k * np.arctan((y[q2] / (-x[q2])).astype(np.float64))
-        ang[q3] = 180 + k * np.arctan((y[q3] / x[q3]).astype(np.float64))
-        ang[q4] = 360 - k * np.arctan(((-y[q4]) / x[q4]).astype(np.float64))
+        ang[q1] = k * _atanf(y[q1] / x[q1])
+        ang[q2] = 180 - k * _atanf(y[q2] / (-x[q2]))
+        ang[q3] = 180 + k * _atanf(y[q3] / x[q3])
+        ang[q4] = 360 - k * _atanf((-y[q4]) / x[q4])
     ang = ang.astype(np.float32)
     keep = ~(rng.astype(np.float64) > 80.0)
 
