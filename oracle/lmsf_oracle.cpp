@@ -1,9 +1,12 @@
 // lmsf_oracle.cpp — CPU ORACLE of the LMSF-SLAM scan-to-map registration hot path.
 //
-// TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (see lmsf_oracle.h): the reference
-// has no golden vectors and cannot be built here, so this file restates its
-// source text; every function cites the reference file:line it follows
-// (paths relative to src/MultiSensorFusionEstimator3D/include/).
+// TEST INFRASTRUCTURE ONLY.  PARITY PINNED IN PART (see lmsf_oracle.h): feature
+// extraction (rows a1.*), the common point-cloud process (f4) and the exact kNN
+// (a3.2) are checked bit for bit against the reference's own code compiled into
+// oracle/_ref; voxel grid, matchers, solvers and tracker (a2, a4-a6) rest on
+// absent third-party arithmetic and are PARITY UNPINNED restatements of the
+// source text.  Every function cites the reference file:line it follows (paths
+// relative to src/MultiSensorFusionEstimator3D/include/).
 //
 // Floating-point contract: build with -ffp-contract=off (the reference builds
 // -O3 without -march, i.e. no FMA; CMakeLists.txt:10-12).  float expressions in

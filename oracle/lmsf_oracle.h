@@ -7,18 +7,33 @@
  * cpu_baseline / --impl reference legs.  Nothing under lmsf-slam_b200/ may
  * include, link or call it.
  *
- * PARITY UNPINNED: the reference holds no golden vectors, known-answer tests or
- * fixtures for this path (its two test main()s assert nothing and their PCD
- * inputs are not in the tree), the tree does not compile as shipped (Map/ is
- * git-ignored) and its third-party arithmetic (PCL, FLANN, Eigen, Ceres) is
- * neither vendored nor version-pinned, so the oracle cannot be checked against
- * reference outputs.  It is anchored instead on (i) the reference source text,
- * cited per function in lmsf_oracle.cpp, (ii) numpy / scipy cross-checks of its
- * linear algebra and of its Huber-LM solve (tests/), (iii) the reference's
- * vendored nanoflann 1.3.2 (compiled from /root/reference into oracle/_ref) as
- * an independent exact-kNN check — for the 3-D map search and, through the
- * reference's own KDTreeVectorOfVectorsAdaptor, for the 20-D ring-key search of
- * the loop-closure path, which is thereby the one piece pinned bit for bit.
+ * PARITY PINNED IN PART.  The reference holds no golden vectors, known-answer
+ * tests or fixtures for this path (its two test main()s assert nothing and
+ * their PCD inputs are not in the tree), its tree does not build as shipped
+ * (Map/ is git-ignored) and its third-party arithmetic (PCL, FLANN, Eigen,
+ * Ceres) is neither vendored nor version-pinned.  What CAN be run here is the
+ * reference's own header-only code wherever it is plain C++ over containers;
+ * oracle/Makefile compiles it where it lies under /root/reference into
+ * oracle/_ref/ (PCL / Eigen as container-only stand-ins, oracle/shim/) and
+ * tests/ demand bit-identical outputs:
+ *   PINNED   rows a1.1-a1.4  LOAMFeatureProcessorBase::Process (edge and surf
+ *            clouds, order included; libref_loam.so), row f4's removeNaN +
+ *            DistanceFilter flow (libref_loam.so), row f1's ScanContext
+ *            descriptor, ring key, SC distance and shift (libref_sc.so; Eigen's
+ *            mean / norm / dot taken as sequential sums) and ring-key k-d tree
+ *            search (libref_nanoflann.so), row a3.2's exact 5-NN against the
+ *            reference's vendored nanoflann 1.3.2 (libref_nanoflann.so).
+ *   UNPINNED rows a2 (PCL VoxelGrid), a4 (Eigen eigen solver / QR inside the
+ *            matchers), a5 (Gauss-Newton, Ceres Huber-LM), a6 (tracker, missing
+ *            local-map class): third-party arithmetic that is absent; anchored
+ *            on the reference source text (cited per function), numpy / scipy /
+ *            LAPACK restatements of the same algorithms (tests/test_oracle.py)
+ *            and behaviour (known-motion recovery).
+ * The first pin already paid for itself: it showed that sqrt / atan2 / atan of
+ * float arguments resolve to the std:: FLOAT overloads in the reference's
+ * translation unit (`using namespace std;` src/apps/include/utility.hpp:51
+ * precedes every header), which moves ring membership on the boundary rings of
+ * the 64-line sensor and ScanContext sectors on bin boundaries.
  *
  * The entry points mirror include/lmsf_b200.h one to one (prefix lmsf_oracle_)
  * so that the parity tests drive both through the same ctypes wrapper; the

@@ -1,8 +1,10 @@
 // lmsf_oracle_sc.cpp — CPU ORACLE of the loop-closure descriptor path ("next" row f1, BASELINE config 5).
 //
-// TEST INFRASTRUCTURE ONLY (see lmsf_oracle.h).  Parity unpinned for the descriptor and the SC distance (the reference has
-// no fixtures for them, Eigen / PCL are absent); the ring-key search IS pinned: tests/test_oracle_sc.py compares it bit for
-// bit with the reference's own KDTreeVectorOfVectorsAdaptor over its vendored nanoflann, compiled into oracle/_ref.
+// TEST INFRASTRUCTURE ONLY (see lmsf_oracle.h).  PINNED against the reference's own code compiled into oracle/_ref
+// (tests/test_oracle_sc.py, bit for bit): descriptor, ring key, SC distance and shift against its ScanContext class
+// (libref_sc.so; Eigen's mean / norm / dot taken as sequential sums on both sides — the one documented divergence, <= 1 ulp
+// of a double), the ring-key search against its KDTreeVectorOfVectorsAdaptor over its vendored nanoflann.  The selection
+// of descFindSimilar and the tree-rebuild schedule are restatements (parity unpinned).
 // Restates, with file:line under src/MultiSensorFusionEstimator3D/include/:
 //   ScanContext::MakeScanContext / MakeRingkeyFromScanContext / DistanceBtnScanContext / distDirectSC /
 //   fastAlignUsingVkey / circshift / xy2theta

@@ -77,3 +77,15 @@ def test_cpp_adapter_binary_builds_and_fails_loudly_without_gpu():
         pytest.skip("a CUDA device is present")
     r = subprocess.run([exe, "/dev/null", "0", "0", "16"], capture_output=True, text=True)
     assert r.returncode == 4 and "no CPU path" in r.stderr
+
+
+def test_fmath_atan2f_has_the_c_librarys_bits(tmp_path):
+    """csrc/fmath.cuh (the atan2f / atanf the extraction and ScanContext kernels use) compiled for the host against
+    the C library's atan2f — std::atan2(float, float) of the reference's translation unit: 9 M arguments, every bit.
+    (The device side of the same check is csrc/test_dmath, run by the GPU tests.)"""
+    src = os.path.join(entry.CSRC, "test_fmath.cpp")
+    exe = str(tmp_path / "test_fmath")
+    subprocess.run(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-I", entry.CSRC, "-o", exe, src], check=True)
+    r = subprocess.run([exe, "3000000"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bit mismatches 0" in r.stdout
