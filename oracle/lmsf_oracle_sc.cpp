@@ -3,8 +3,8 @@
 // TEST INFRASTRUCTURE ONLY (see lmsf_oracle.h).  PINNED against the reference's own code compiled into oracle/_ref
 // (tests/test_oracle_sc.py, bit for bit): descriptor, ring key, SC distance and shift against its ScanContext class
 // (libref_sc.so; Eigen's mean / norm / dot taken as sequential sums on both sides — the one documented divergence, <= 1 ulp
-// of a double), the ring-key search against its KDTreeVectorOfVectorsAdaptor over its vendored nanoflann.  The selection
-// of descFindSimilar and the tree-rebuild schedule are restatements (parity unpinned).
+// of a double), the ring-key search against its KDTreeVectorOfVectorsAdaptor over its vendored nanoflann, and the search
+// end to end (tree-rebuild schedule, top-10, selection, threshold, yaw) against its SceneRecognitionScanContext class.
 // Restates, with file:line under src/MultiSensorFusionEstimator3D/include/:
 //   ScanContext::MakeScanContext / MakeRingkeyFromScanContext / DistanceBtnScanContext / distDirectSC /
 //   fastAlignUsingVkey / circshift / xy2theta

@@ -3,7 +3,9 @@
 // /root/reference (oracle/Makefile, target `ref`) against oracle/shim/ (PCL as a container; Eigen's dynamic matrix as a
 // container whose three reductions — mean, norm, dot — are sequential sums, see shim/Eigen/Dense).  Used by
 // tests/test_oracle_sc.py to pin the oracle's restatement of row f1 against the reference's real control flow:
-// polar binning, ring key, sector-key alignment, shift refinement, argmin.  Never linked into the product.
+// polar binning, ring key, sector-key alignment, shift refinement, argmin — and, through the reference's own
+// SceneRecognitionScanContext (LoopDetection/SceneRecognitionScanContext.hpp), the keyframe database: tree-rebuild
+// schedule, ring-key top-10, selection and threshold of descFindSimilar.  Never linked into the product.
 #include <algorithm>
 #include <cmath>
 #include <iostream>
@@ -11,9 +13,22 @@
 #include <utility>
 #include <vector>
 
+#include <deque>
+#include <fstream>
+#include <memory>
+#include <unordered_map>
+
 using namespace std;  // as in the node's translation unit (src/apps/include/utility.hpp:51 precedes every header)
 
+// names SceneRecognitionScanContext.hpp expects from headers included before it in the node (Save / Load only)
+namespace boost { namespace filesystem {
+inline bool is_directory(const std::string&) { return true; }
+inline bool create_directory(const std::string&) { return true; }
+} }
+namespace common { const std::string GREEN, RESET; }
+
 #include "Algorithm/PointClouds/processing/GlobalDescriptor/scanContext/Scancontext.hpp"
+#include "LoopDetection/SceneRecognitionScanContext.hpp"
 
 namespace {
 
@@ -66,6 +81,38 @@ int ref_sc_distance(const float* desc_a, const float* desc_b, double* dist, int*
   std::pair<double, int> r = sc.DistanceBtnScanContext(to_mat(desc_a), to_mat(desc_b));
   *dist = r.first;
   *shift = r.second;
+  return 0;
+}
+
+// SceneRecognitionScanContext (LoopDetection/SceneRecognitionScanContext.hpp:61-94, 112-124, 260-333): the keyframe
+// database with its ring-key tree rebuilt every tenth keyframe over [0, size - 50).
+void* ref_scdb_create() { return new Slam3D::SceneRecognitionScanContext<Point>(); }
+void ref_scdb_destroy(void* h) { delete static_cast<Slam3D::SceneRecognitionScanContext<Point>*>(h); }
+
+// AddKeyFramePoints of one cloud (container with a single entry: every entry is selected, :176-181)
+int ref_scdb_add(void* h, const float* xyzi, int n) {
+  Quiet q;
+  auto pc = std::make_shared<pcl::PointCloud<Point>>();
+  pc->points.resize(n);
+  for (int i = 0; i < n; ++i) {
+    pc->points[i].x = xyzi[4 * i];
+    pc->points[i].y = xyzi[4 * i + 1];
+    pc->points[i].z = xyzi[4 * i + 2];
+    pc->points[i].intensity = xyzi[4 * i + 3];
+  }
+  std::unordered_map<std::string, pcl::PointCloud<Point>::ConstPtr> in;
+  in["cloud"] = pc;
+  static_cast<Slam3D::SceneRecognitionScanContext<Point>*>(h)->AddKeyFramePoints(in);
+  return 0;
+}
+
+// LoopDetect(id): loop id or -1, and the yaw the reference puts into the relative pose (float deg2rad(shift * 6))
+int ref_scdb_loop_detect(void* h, unsigned id, long long* loop_id, double* yaw_rad) {
+  Quiet q;
+  uint32_t i = id;
+  auto r = static_cast<Slam3D::SceneRecognitionScanContext<Point>*>(h)->LoopDetect(i);
+  *loop_id = r.first;
+  *yaw_rad = r.second.linear().yaw;
   return 0;
 }
 

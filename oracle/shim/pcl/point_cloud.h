@@ -47,6 +47,12 @@ class PointCloud {
   PointT& operator[](std::size_t i) { return points[i]; }
   const PointT& operator[](std::size_t i) const { return points[i]; }
   Ptr makeShared() const { return Ptr(new PointCloud<PointT>(*this)); }
+  PointCloud& operator+=(const PointCloud& o) {  // concatenation, as pcl::PointCloud::operator+=
+    points.insert(points.end(), o.points.begin(), o.points.end());
+    width = static_cast<std::uint32_t>(points.size());
+    height = 1;
+    return *this;
+  }
 };
 
 }  // namespace pcl

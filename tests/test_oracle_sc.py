@@ -125,6 +125,51 @@ def test_sc_distance_vs_reference_code(sco, sweeps, ref_sc):
     assert n > 150
 
 
+def test_loop_search_vs_reference_code(sco, synth, ref_sc, gpu_lib):
+    """Row f1 PINNED end to end: the reference's own SceneRecognitionScanContext (AddKeyFramePoints + LoopDetect,
+    SceneRecognitionScanContext.hpp:61-124, 260-333) fed 140 keyframe clouds — 70 places, then the same 70 revisited
+    under random yaw with fresh noise — against the oracle's search over the prefix the product's lmsf_sc_tree_limit
+    names: identical loop id (or -1) and identical yaw (= column shift) for every keyframe from the 51st on."""
+    import math
+    dll = ref_sc.dll
+    dll.ref_scdb_create.restype = C.c_void_p
+    h = C.c_void_p(dll.ref_scdb_create())
+    tree_limit = gpu_lib.fn("sc_tree_limit")
+    tree_limit.restype = C.c_int
+    rng = np.random.default_rng(8)
+    sensor = synth.vlp16()
+
+    def yawed(cloud, deg):
+        c, s_ = math.cos(math.radians(deg)), math.sin(math.radians(deg))
+        out = cloud.copy()
+        out[:, 0] = c * cloud[:, 0] - s_ * cloud[:, 1]
+        out[:, 1] = s_ * cloud[:, 0] + c * cloud[:, 1]
+        return out.astype(np.float32)
+
+    places = [synth.make_sweep(sensor, 3 * i)[::4] for i in range(70)]
+    clouds = places + [yawed(p + rng.normal(0, 0.01, p.shape).astype(np.float32), float(rng.uniform(0, 360)))
+                       for p in places]
+    keys, descs, n_loop = [], [], 0
+    fp = C.POINTER(C.c_float)
+    for i, cl in enumerate(clouds):
+        cl = np.ascontiguousarray(cl, np.float32)
+        assert dll.ref_scdb_add(h, cl.ctypes.data_as(fp), len(cl)) == 0
+        d, k = sco.make(cl)
+        descs.append(d.reshape(-1))
+        keys.append(k)
+        if i + 1 < 51:
+            continue                                   # LoopDetect returns -1 below NUM_EXCLUDE_RECENT_ + 1 keyframes
+        lid, yaw = C.c_longlong(0), C.c_double(0)
+        assert dll.ref_scdb_loop_detect(h, i, C.byref(lid), C.byref(yaw)) == 0
+        o_id, _, o_sh = sco.search(np.array(keys), np.array(descs), tree_limit(i + 1), keys[i], descs[i])
+        # float deg2rad(float degrees) { return degrees * M_PI / 180.0; } on nn_align * PC_UNIT_SECTORANGLE_ (:325, :344)
+        o_yaw = float(np.float32(float(np.float32(o_sh[0] * 6.0)) * math.pi / 180.0)) if o_id[0] >= 0 else 0.0
+        assert (lid.value, yaw.value) == (int(o_id[0]), o_yaw), (i, lid.value, yaw.value, o_id[0], o_sh[0])
+        n_loop += lid.value >= 0
+    dll.ref_scdb_destroy(h)
+    assert n_loop > 60                                 # the revisits are found, not merely "both say -1"
+
+
 def test_ringkey_knn_vs_reference_kdtree(sco):
     """Oracle brute force == the reference's own KDTreeVectorOfVectorsAdaptor<.., float> (leaf 10, metric_L2)."""
     rng = np.random.default_rng(11)
