@@ -22,7 +22,9 @@
  *            descriptor, ring key, SC distance and shift (libref_sc.so; Eigen's
  *            mean / norm / dot taken as sequential sums), ring-key k-d tree
  *            search (libref_nanoflann.so) and keyframe-database search end to
- *            end (SceneRecognitionScanContext, libref_sc.so), row a3.2's exact 5-NN against the
+ *            end (SceneRecognitionScanContext, libref_sc.so), row f2's
+ *            AlignmentScore control flow (libref_align.so; 1-NN by the vendored
+ *            nanoflann, pcl::transformPointCloud restated), row a3.2's exact 5-NN against the
  *            reference's vendored nanoflann 1.3.2 (libref_nanoflann.so).
  *   UNPINNED rows a2 (PCL VoxelGrid), a4 (Eigen eigen solver / QR inside the
  *            matchers), a5 (Gauss-Newton, Ceres Huber-LM), a6 (tracker, missing

@@ -5,8 +5,10 @@
 namespace Eigen {
 // Sensor/lidar_data_type.h:74 names Eigen::Matrix4f::Identity() in a struct the extraction path never instantiates
 struct Matrix4f {
-  float m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  float m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};  // row-major here; only (i, j) access is offered
   static Matrix4f Identity() { return Matrix4f(); }
+  float& operator()(int i, int j) { return m[4 * i + j]; }
+  const float& operator()(int i, int j) const { return m[4 * i + j]; }
 };
 }  // namespace Eigen
 

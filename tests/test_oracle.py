@@ -630,6 +630,46 @@ def test_align_score_vs_python_restatement(oracle_lib, synth):
     o.close()
 
 
+def test_align_score_vs_reference_code(oracle_lib, synth):
+    """Row f2 PINNED (control flow): the oracle against the reference's own PointCloudAlignmentEvaluate::AlignmentScore
+    (alignEvaluate.hpp:55-87) compiled from its unmodified header into oracle/_ref/libref_align.so — 1-NN by the
+    reference's vendored nanoflann (exact, fp32 L2_Simple), pcl::transformPointCloud restated in the shim.  Score and
+    overlap ratio are bit-identical: same inliers, same values summed in the same order, same return branch."""
+    path = os.path.join(os.path.dirname(entry.ORACLE_LIB), "_ref", "libref_align.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_align.so is not built (needs /root/reference)")
+    dll = C.CDLL(path)
+    fp = C.POINTER(C.c_float)
+
+    def ref(target, cloud, T, thr, rat):
+        t = np.ascontiguousarray(target, np.float32)
+        c = np.ascontiguousarray(cloud, np.float32)
+        M = np.ascontiguousarray(T, np.float32)
+        sc, ov = C.c_double(0), C.c_double(0)
+        assert dll.ref_align_score(t.ctypes.data_as(fp), len(t), c.ctypes.data_as(fp), len(c), M.ctypes.data_as(fp),
+                                   C.c_double(thr), C.c_double(rat), C.byref(sc), C.byref(ov)) == 0
+        return sc.value, ov.value
+
+    o = oracle_lib.context(0, n_scans=16, oracle_knn_mode=0)
+    s0, s1 = synth.make_sweep(synth.vlp16(), 0), synth.make_sweep(synth.vlp16(), 1)
+    _, _, f0 = o.extract_features(s0)
+    _, _, f1 = o.extract_features(s1)
+    o.map_set(1, f0)
+    T_true = synth.qt_to_mat(synth.rel_gt_pose(1))
+    T_off = T_true.copy()
+    T_off[:3, 3] += [0.4, -0.3, 0.0]
+    n_finite = 0
+    for T, thr, rat in ((T_true, 0.1, 0.6), (T_true, 1.0, 0.6), (T_true, 0.01, 0.2), (T_off, 0.1, 0.6),
+                        (T_off, 0.5, 0.3), (np.eye(4), 0.1, 0.5), (np.eye(4), 0.05, 0.99)):
+        for q in (f1[::3], f1[5::17], f1[:1]):
+            sc, ov, _ = o.align_score(1, q, T, thr, rat)
+            rs, ro = ref(f0, q, T, thr, rat)
+            assert (sc, ov) == (rs, ro), (thr, rat, len(q), sc, rs, ov, ro)
+            n_finite += sc < 1e300
+    assert n_finite >= 6                       # both return branches are exercised
+    o.close()
+
+
 # ---------------------------------------------------------------- f4 common pre-processing
 def test_common_process_vs_numpy(oracle_lib, synth):
     """PointCloudCommonProcess::Process (common_processing.hpp:87-111): removeNaN -> VoxelGrid -> DistanceFilter."""
