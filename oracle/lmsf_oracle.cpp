@@ -2,10 +2,11 @@
 //
 // TEST INFRASTRUCTURE ONLY.  PARITY PINNED IN PART (see lmsf_oracle.h): feature
 // extraction (rows a1.*), the common point-cloud process (f4) and the exact kNN
-// (a3.2) are checked bit for bit against the reference's own code compiled into
-// oracle/_ref; voxel grid, matchers, solvers and tracker (a2, a4-a6) rest on
-// absent third-party arithmetic and are PARITY UNPINNED restatements of the
-// source text.  Every function cites the reference file:line it follows (paths
+// (a3.2), the alignment score (f2) and the matchers' control flow (a4) are checked
+// bit for bit against the reference's own code compiled into oracle/_ref; voxel
+// grid, Eigen's solver arithmetic, the GN / LM solves and the tracker (a2, a5, a6)
+// rest on absent third-party arithmetic and are PARITY UNPINNED restatements of
+// the source text.  Every function cites the reference file:line it follows (paths
 // relative to src/MultiSensorFusionEstimator3D/include/).
 //
 // Floating-point contract: build with -ffp-contract=off (the reference builds

@@ -26,8 +26,11 @@
  *            AlignmentScore control flow (libref_align.so; 1-NN by the vendored
  *            nanoflann, pcl::transformPointCloud restated), row a3.2's exact 5-NN against the
  *            reference's vendored nanoflann 1.3.2 (libref_nanoflann.so).
- *   UNPINNED rows a2 (PCL VoxelGrid), a4 (Eigen eigen solver / QR inside the
- *            matchers), a5 (Gauss-Newton, Ceres Huber-LM), a6 (tracker, missing
+ *            Rows a4.1 / a4.2: control flow, types and expression order of the
+ *            two matchers (libref_match.so; Eigen's solvers answered by
+ *            oracle_math.h, so their arithmetic is not part of the pin).
+ *   UNPINNED rows a2 (PCL VoxelGrid), a4's solver arithmetic (Eigen eigen
+ *            solver / QR), a5 (Gauss-Newton, Ceres Huber-LM), a6 (tracker, missing
  *            local-map class): third-party arithmetic that is absent; anchored
  *            on the reference source text (cited per function), numpy / scipy /
  *            LAPACK restatements of the same algorithms (tests/test_oracle.py)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cmath>
 
+#ifndef LMSF_SHIM_EIGEN_MATRIX4F
 namespace Eigen {
 // Sensor/lidar_data_type.h:74 names Eigen::Matrix4f::Identity() in a struct the extraction path never instantiates
 struct Matrix4f {
@@ -11,6 +12,7 @@ struct Matrix4f {
   const float& operator()(int i, int j) const { return m[4 * i + j]; }
 };
 }  // namespace Eigen
+#endif
 
 namespace pcl {
 

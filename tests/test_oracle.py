@@ -791,6 +791,44 @@ def test_match_vs_numpy_restatement(oracle_lib, synth):
     assert n_acc > 200
 
 
+def test_match_vs_reference_code(oracle_lib, synth):
+    """Rows a4.1 / a4.2 PINNED (control flow, types, expression order): the oracle against the reference's own
+    EdgeFeatureMatch::Match / SurfFeatureMatch::Match compiled from their unmodified headers into
+    oracle/_ref/libref_match.so.  kNN by the reference's vendored nanoflann; Eigen's fixed-size expressions evaluated
+    coefficient by coefficient; its eigen solver and pivoted QR answered by the oracle's restatements (oracle_math.h) —
+    so every output is bit-identical, and what is NOT pinned is Eigen's solver arithmetic (numpy / LAPACK above)."""
+    path = os.path.join(os.path.dirname(entry.ORACLE_LIB), "_ref", "libref_match.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_match.so is not built (needs /root/reference)")
+    dll = C.CDLL(path)
+    fp = C.POINTER(C.c_float)
+
+    def ref(kind, cloud, q):
+        cloud, q = np.ascontiguousarray(cloud, np.float32), np.ascontiguousarray(q, np.float32)
+        ok, out = np.zeros(len(q), np.uint8), np.zeros((len(q), 10), np.float64)
+        assert dll.ref_match(kind, cloud.ctypes.data_as(fp), len(cloud), q.ctypes.data_as(fp), len(q),
+                             ok.ctypes.data_as(C.POINTER(C.c_ubyte)), out.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        return ok, out
+
+    n_acc = 0
+    for sensor, n_scans, step in ((synth.vlp16(), 16, 7), (synth.hdl64(), 64, 29)):
+        o = oracle_lib.context(0, n_scans=n_scans, oracle_knn_mode=0)
+        _, me, ms = o.extract_features(synth.make_sweep(sensor, 0))
+        o.map_set(0, me)
+        o.map_set(1, ms)
+        _, e, s = o.extract_features(synth.make_sweep(sensor, 2))
+        far = np.array([[500.0, 0, 0], [0, 0, 40.0]], np.float32)          # no neighbour within the search threshold
+        for kind, cloud, q in ((0, me, np.vstack([e[:, :3], far])), (1, ms, np.vstack([s[::step, :3], far]))):
+            ok_o, out_o = o.match(kind, np.ascontiguousarray(q))
+            ok_r, out_r = ref(kind, cloud, q)
+            assert np.array_equal(ok_o.astype(bool), ok_r.astype(bool))
+            assert np.array_equal(out_o.view(np.uint64), out_r.view(np.uint64))
+            assert not ok_o[-1] and not ok_o[-2]
+            n_acc += int(ok_o.sum())
+        o.close()
+    assert n_acc > 5000
+
+
 def _np_gn(me, ms, edge, surf, pose, max_iters=10):
     """EdgeSurfFeatureRegistration::Solve + GNOptimization (registration/edgeSurfFeatureRegistration.hpp:113-330):
     re-match every iteration, J = grad^T [-R skew(p) | I], float residual, QR solve of JTJ, first-iteration degeneracy
