@@ -1,0 +1,148 @@
+"""Shared harness of the "pinned against the reference's own code" tests: ctypes wrappers of oracle/_ref/libref_*.so
+(the reference's unmodified headers compiled where they lie, oracle/Makefile) and the comparison loops, written once
+and run twice — on the CPU with the oracle (tests/test_oracle*.py) and on the B200 with the CUDA library
+(tests/test_zz_gpu_reference_pin.py).  `oracle/_ref` travels to the GPU box prebuilt; without it the tests skip."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+
+NR, NS = 20, 60
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _ref_path(name):
+    path = os.path.join(os.path.dirname(entry.ORACLE_LIB), "_ref", name)
+    if not os.path.exists(path):
+        pytest.skip(f"oracle/_ref/{name} is not built (needs /root/reference at build time)")
+    return path
+
+
+class RefLoam:
+    """oracle/_ref/libref_loam.so: LOAMFeatureProcessorBase / PointCloudCommonProcess compiled from the reference's
+    unmodified headers where they lie (oracle/Makefile, oracle/ref_loam.cpp, PCL as a container: oracle/shim/)."""
+
+    def __init__(self):
+        self.dll = C.CDLL(_ref_path("libref_loam.so"))
+
+    def extract(self, sw, n_scans, min_r=2.0, max_r=80.0, thresh=1.0, bad=True):
+        sw = np.ascontiguousarray(sw, np.float32)
+        n = len(sw)
+        fp = C.POINTER(C.c_float)
+        e, s = np.zeros((max(n, 1), 4), np.float32), np.zeros((max(n, 1), 4), np.float32)
+        ne, ns = C.c_int(0), C.c_int(0)
+        rc = self.dll.ref_loam_extract(sw.ctypes.data_as(fp), n, n_scans, C.c_float(min_r), C.c_float(max_r),
+                                       C.c_float(thresh), int(bad), n, e.ctypes.data_as(fp), C.byref(ne),
+                                       s.ctypes.data_as(fp), C.byref(ns))
+        assert rc == 0
+        return e[:ne.value], s[:ns.value]
+
+    def common_process(self, sw, remove_nan, near, far):
+        sw = np.ascontiguousarray(sw, np.float32)
+        n = len(sw)
+        fp = C.POINTER(C.c_float)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        m = C.c_int(0)
+        rc = self.dll.ref_common_process(sw.ctypes.data_as(fp), n, int(remove_nan), C.c_float(near), C.c_float(far), n,
+                                         out.ctypes.data_as(fp), C.byref(m))
+        assert rc == 0
+        return out[:m.value]
+
+
+class RefSc:
+    """oracle/_ref/libref_sc.so: the reference's own ScanContext class compiled from its unmodified header where it
+    lies (oracle/Makefile, oracle/ref_sc.cpp; PCL / Eigen as containers: oracle/shim/)."""
+
+    def __init__(self):
+        self.dll = C.CDLL(_ref_path("libref_sc.so"))
+
+    def make(self, xyzi):
+        a = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+        fp = C.POINTER(C.c_float)
+        desc, key = np.zeros((NR, NS), np.float32), np.zeros(NR, np.float32)
+        assert self.dll.ref_sc_make(a.ctypes.data_as(fp), len(a), desc.ctypes.data_as(fp), key.ctypes.data_as(fp)) == 0
+        return desc, key
+
+    def distance(self, a, b):
+        a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+        fp = C.POINTER(C.c_float)
+        d, s = C.c_double(0), C.c_int(0)
+        assert self.dll.ref_sc_distance(a.ctypes.data_as(fp), b.ctypes.data_as(fp), C.byref(d), C.byref(s)) == 0
+        return d.value, s.value
+
+
+def check_extract_against_reference(make_ctx, synth, ref_loam, include_32_line=True):
+    """make_ctx(**params) -> a context with extract_features (oracle or CUDA library).  Edge and surf clouds must equal
+    the reference's LOAMFeatureProcessorBase::Process bit for bit, order included.  Returns the features compared."""
+    rng = np.random.default_rng(11)
+    cases = []
+    for k in (0, 1, 7, 50, 120):
+        cases.append((16, synth.make_sweep(synth.vlp16(), k), {}))
+    for k in (0, 1, 7, 50):
+        cases.append((64, synth.make_sweep(synth.hdl64(), k), {}))
+    sw = synth.make_sweep(synth.vlp16(), 3)
+    cases.append((16, sw[rng.random(len(sw)) > 0.3], {}))                       # ragged rings
+    cases.append((16, sw, dict(thresh=0.2)))
+    cases.append((16, sw, dict(bad=False)))
+    cases.append((16, sw, dict(min_r=5.0, max_r=30.0)))
+    if include_32_line:
+        cases.append((32, sw, {}))                                              # 32-line ring formula on the same rays
+    h = synth.make_sweep(synth.hdl64(), 9)
+    cases.append((64, h[rng.random(len(h)) > 0.5], dict(thresh=0.5)))
+    cases.append((64, h[: 64 * 15], {}))                                        # < 20 points per ring
+    cases.append((16, sw[: 16 * 40], {}))                                       # short rings: 30 candidates, sectors of 5
+    cases.append((16, np.zeros((0, 4), np.float32), {}))
+    n_feat = 0
+    for n_scans, cloud, kw in cases:
+        o = make_ctx(n_scans=n_scans, min_range=kw.get("min_r", 2.0), max_range=kw.get("max_r", 80.0),
+                     edge_thresh=kw.get("thresh", 1.0), remove_bad_points=int(kw.get("bad", True)))
+        _, oe, os_ = o.extract_features(cloud)
+        re_, rs_ = ref_loam.extract(cloud, n_scans, **kw)
+        assert (len(oe), len(os_)) == (len(re_), len(rs_)), (n_scans, len(cloud), kw)
+        assert np.array_equal(bits(oe), bits(re_)) and np.array_equal(bits(os_), bits(rs_)), (n_scans, len(cloud), kw)
+        n_feat += len(oe) + len(os_)
+        o.close()
+    return n_feat
+
+
+def check_common_process_against_reference(ctx, synth, ref_loam):
+    """removeNaN + DistanceFilter of PointCloudCommonProcess::Process (no VoxelGrid: PCL arithmetic is not available)."""
+    sw = synth.make_sweep(synth.vlp16(), 2).copy()
+    sw[::31, 0] = np.nan
+    sw[5, 2] = np.inf
+    sw[77, 1] = -np.inf
+    for near, far in ((0.0, 0.0), (3.0, 25.5), (0.0, 10.0), (7.25, 7.5)):
+        ref = ref_loam.common_process(sw, True, near, far)
+        out = ctx.common_process(sw, True, 0.0, near, far)
+        assert np.array_equal(bits(out), bits(ref)), (near, far)
+
+
+def check_sc_make_against_reference(make, sweeps, ref_sc):
+    """make(xyzi) -> (descriptor, ring key) (oracle or CUDA library) against the reference's MakeScanContext /
+    MakeRingkeyFromScanContext, bit for bit (NaN x / y is undefined behaviour in the reference's xy2theta: left out)."""
+    for name, k in (("vlp16", 0), ("vlp16", 5), ("vlp16", 77), ("hdl64", 3), ("hdl64", 41)):
+        sw = sweeps(name, k)
+        d_o, k_o = make(sw)
+        d_r, k_r = ref_sc.make(sw)
+        assert np.array_equal(bits(d_o), bits(d_r)), (name, k)
+        assert np.array_equal(bits(k_o), bits(k_r)), (name, k)
+    rng = np.random.default_rng(4)
+    cloud = np.zeros((20000, 4), np.float32)
+    cloud[:, :2] = rng.uniform(-95, 95, size=(20000, 2))      # all quadrants, some beyond the 80 m radius
+    cloud[:, 2] = rng.uniform(-3, 6, size=20000)              # heights below the sensor too
+    cloud[::7, 0] = 0.0                                       # on the y axis: atan(+-inf)
+    cloud[::11, 1] = 0.0                                      # on the x axis
+    cloud[::77, :2] = 0.0                                     # x = y = 0: atan(NaN)
+    edge = np.array([[1.0, 0.0, 0.5, 0], [0.0, 0.0, 9.0, 0], [79.9, 0.0, 1.0, 0], [80.5, 0.0, 5.0, 0],
+                     [-3.0, -3.0, -1.5, 0], [2.0, 2.0, np.nan, 0], [5.0, -5.0, -1003.0, 0]], np.float32)
+    for pts in (cloud, edge, np.zeros((0, 4), np.float32)):
+        d_o, k_o = make(pts)
+        d_r, k_r = ref_sc.make(pts)
+        assert np.array_equal(bits(d_o), bits(d_r))
+        assert np.array_equal(bits(k_o), bits(k_r))

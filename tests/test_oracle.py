@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import __graft_entry__ as entry
+import ref_pin
 from conftest import pose_err
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -249,76 +250,16 @@ def test_extract_edge_cases(oracle_lib, synth):
 
 
 # ---------------------------------------------------------------- the reference's OWN extraction code (oracle/_ref)
-class _RefLoam:
-    """oracle/_ref/libref_loam.so: LOAMFeatureProcessorBase / PointCloudCommonProcess compiled from the reference's
-    unmodified headers where they lie (oracle/Makefile, oracle/ref_loam.cpp, PCL as a container: oracle/shim/)."""
-
-    def __init__(self):
-        path = os.path.join(os.path.dirname(entry.ORACLE_LIB), "_ref", "libref_loam.so")
-        if not os.path.exists(path):
-            pytest.skip("oracle/_ref/libref_loam.so is not built (needs /root/reference)")
-        self.dll = C.CDLL(path)
-
-    def extract(self, sw, n_scans, min_r=2.0, max_r=80.0, thresh=1.0, bad=True):
-        sw = np.ascontiguousarray(sw, np.float32)
-        n = len(sw)
-        fp = C.POINTER(C.c_float)
-        e, s = np.zeros((max(n, 1), 4), np.float32), np.zeros((max(n, 1), 4), np.float32)
-        ne, ns = C.c_int(0), C.c_int(0)
-        rc = self.dll.ref_loam_extract(sw.ctypes.data_as(fp), n, n_scans, C.c_float(min_r), C.c_float(max_r),
-                                       C.c_float(thresh), int(bad), n, e.ctypes.data_as(fp), C.byref(ne),
-                                       s.ctypes.data_as(fp), C.byref(ns))
-        assert rc == 0
-        return e[:ne.value], s[:ns.value]
-
-    def common_process(self, sw, remove_nan, near, far):
-        sw = np.ascontiguousarray(sw, np.float32)
-        n = len(sw)
-        fp = C.POINTER(C.c_float)
-        out = np.zeros((max(n, 1), 4), np.float32)
-        m = C.c_int(0)
-        rc = self.dll.ref_common_process(sw.ctypes.data_as(fp), n, int(remove_nan), C.c_float(near), C.c_float(far), n,
-                                         out.ctypes.data_as(fp), C.byref(m))
-        assert rc == 0
-        return out[:m.value]
-
-
 @pytest.fixture(scope="module")
 def ref_loam():
-    return _RefLoam()
+    return ref_pin.RefLoam()
 
 
 def test_extract_vs_reference_code(oracle_lib, synth, ref_loam):
     """Rows a1.1-a1.4 PINNED: the oracle against the reference's own LOAMFeatureProcessorBase::Process, compiled from
     its unmodified source.  Edge and surf clouds are identical bit for bit, order included, on full-size VLP-16 and
-    HDL-64 sweeps, ragged rings, the 32-line branch, other thresholds and the degenerate inputs."""
-    rng = np.random.default_rng(11)
-    cases = []
-    for k in (0, 1, 7, 50, 120):
-        cases.append((16, synth.make_sweep(synth.vlp16(), k), {}))
-    for k in (0, 1, 7, 50):
-        cases.append((64, synth.make_sweep(synth.hdl64(), k), {}))
-    sw = synth.make_sweep(synth.vlp16(), 3)
-    cases.append((16, sw[rng.random(len(sw)) > 0.3], {}))                       # ragged rings
-    cases.append((16, sw, dict(thresh=0.2)))
-    cases.append((16, sw, dict(bad=False)))
-    cases.append((16, sw, dict(min_r=5.0, max_r=30.0)))
-    cases.append((32, sw, {}))                                                  # 32-line ring formula on the same rays
-    h = synth.make_sweep(synth.hdl64(), 9)
-    cases.append((64, h[rng.random(len(h)) > 0.5], dict(thresh=0.5)))
-    cases.append((64, h[: 64 * 15], {}))                                        # < 20 points per ring
-    cases.append((16, sw[: 16 * 40], {}))                                       # short rings: 30 candidates, sectors of 5
-    cases.append((16, np.zeros((0, 4), np.float32), {}))
-    n_feat = 0
-    for n_scans, cloud, kw in cases:
-        o = oracle_lib.context(0, n_scans=n_scans, min_range=kw.get("min_r", 2.0), max_range=kw.get("max_r", 80.0),
-                               edge_thresh=kw.get("thresh", 1.0), remove_bad_points=int(kw.get("bad", True)))
-        _, oe, os_ = o.extract_features(cloud)
-        re_, rs_ = ref_loam.extract(cloud, n_scans, **kw)
-        assert (len(oe), len(os_)) == (len(re_), len(rs_)), (n_scans, len(cloud), kw)
-        assert np.array_equal(bits(oe), bits(re_)) and np.array_equal(bits(os_), bits(rs_)), (n_scans, len(cloud), kw)
-        n_feat += len(oe) + len(os_)
-        o.close()
+    HDL-64 sweeps, ragged rings, the 32-line branch, other thresholds and the degenerate inputs (tests/ref_pin.py)."""
+    n_feat = ref_pin.check_extract_against_reference(lambda **kw: oracle_lib.context(0, **kw), synth, ref_loam)
     assert n_feat > 800000
 
 
@@ -326,14 +267,7 @@ def test_common_process_vs_reference_code(oracle_lib, synth, ref_loam):
     """Row f4 PINNED (removeNaN + DistanceFilter; the VoxelGrid stage is PCL arithmetic, not available): the oracle
     against the reference's own PointCloudCommonProcess::Process (common_processing.hpp:87-111)."""
     o = oracle_lib.context(0, n_scans=16)
-    sw = synth.make_sweep(synth.vlp16(), 2).copy()
-    sw[::31, 0] = np.nan
-    sw[5, 2] = np.inf
-    sw[77, 1] = -np.inf
-    for near, far in ((0.0, 0.0), (3.0, 25.5), (0.0, 10.0), (7.25, 7.5)):
-        ref = ref_loam.common_process(sw, True, near, far)
-        out = o.common_process(sw, True, 0.0, near, far)
-        assert np.array_equal(bits(out), bits(ref)), (near, far)
+    ref_pin.check_common_process_against_reference(o, synth, ref_loam)
     o.close()
 
 

@@ -7,6 +7,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
+import ref_pin
 import sc_helpers as sch
 
 
@@ -46,61 +47,16 @@ def test_sc_make_edge_cases(sco):
     assert np.count_nonzero(d) == 3
 
 
-class _RefSc:
-    """oracle/_ref/libref_sc.so: the reference's own ScanContext class compiled from its unmodified header where it
-    lies (oracle/Makefile, oracle/ref_sc.cpp; PCL / Eigen as containers: oracle/shim/)."""
-
-    def __init__(self):
-        import os
-        path = os.path.join(os.path.dirname(sch.entry.ORACLE_LIB), "_ref", "libref_sc.so")
-        if not os.path.exists(path):
-            pytest.skip("oracle/_ref/libref_sc.so is not built (needs /root/reference)")
-        self.dll = C.CDLL(path)
-
-    def make(self, xyzi):
-        a = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
-        fp = C.POINTER(C.c_float)
-        desc, key = np.zeros((sch.NR, sch.NS), np.float32), np.zeros(sch.NR, np.float32)
-        assert self.dll.ref_sc_make(a.ctypes.data_as(fp), len(a), desc.ctypes.data_as(fp), key.ctypes.data_as(fp)) == 0
-        return desc, key
-
-    def distance(self, a, b):
-        a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
-        fp = C.POINTER(C.c_float)
-        d, s = C.c_double(0), C.c_int(0)
-        assert self.dll.ref_sc_distance(a.ctypes.data_as(fp), b.ctypes.data_as(fp), C.byref(d), C.byref(s)) == 0
-        return d.value, s.value
-
-
 @pytest.fixture(scope="module")
 def ref_sc():
-    return _RefSc()
+    return ref_pin.RefSc()
 
 
 def test_sc_make_vs_reference_code(sco, sweeps, ref_sc):
     """Row f1 PINNED (descriptor + ring key): the oracle against the reference's own MakeScanContext /
     MakeRingkeyFromScanContext (Scancontext.hpp:59-126), bit for bit, on full sweeps of both sensors and on the
-    defined edge cases (NaN x / y is undefined behaviour in the reference's xy2theta and is left out)."""
-    for name, k in (("vlp16", 0), ("vlp16", 5), ("vlp16", 77), ("hdl64", 3), ("hdl64", 41)):
-        sw = sweeps(name, k)
-        d_o, k_o = sco.make(sw)
-        d_r, k_r = ref_sc.make(sw)
-        assert np.array_equal(d_o.view(np.uint32), d_r.view(np.uint32)), (name, k)
-        assert np.array_equal(k_o.view(np.uint32), k_r.view(np.uint32)), (name, k)
-    rng = np.random.default_rng(4)
-    cloud = np.zeros((20000, 4), np.float32)
-    cloud[:, :2] = rng.uniform(-95, 95, size=(20000, 2))      # all quadrants, some beyond the 80 m radius
-    cloud[:, 2] = rng.uniform(-3, 6, size=20000)              # heights below the sensor too
-    cloud[::7, 0] = 0.0                                       # on the y axis: atan(+-inf)
-    cloud[::11, 1] = 0.0                                      # on the x axis
-    cloud[::77, :2] = 0.0                                     # x = y = 0: atan(NaN)
-    edge = np.array([[1.0, 0.0, 0.5, 0], [0.0, 0.0, 9.0, 0], [79.9, 0.0, 1.0, 0], [80.5, 0.0, 5.0, 0],
-                     [-3.0, -3.0, -1.5, 0], [2.0, 2.0, np.nan, 0], [5.0, -5.0, -1003.0, 0]], np.float32)
-    for pts in (cloud, edge, np.zeros((0, 4), np.float32)):
-        d_o, k_o = sco.make(pts)
-        d_r, k_r = ref_sc.make(pts)
-        assert np.array_equal(d_o.view(np.uint32), d_r.view(np.uint32))
-        assert np.array_equal(k_o.view(np.uint32), k_r.view(np.uint32))
+    defined edge cases (tests/ref_pin.py)."""
+    ref_pin.check_sc_make_against_reference(sco.make, sweeps, ref_sc)
 
 
 def test_sc_distance_vs_reference_code(sco, sweeps, ref_sc):
