@@ -487,44 +487,53 @@ static inline void accum(Normal& N, const double J[6], double r, double huber_a)
 // se3PointEdgeFactor::Evaluate (ceres_factor/edge_factor.hpp:33-61),
 // se3PointSurfFactor::Evaluate (ceres_factor/surf_factor.hpp:32-56);
 // local Jacobian = first 6 columns (PoseSE3Parameterization.hpp:54-60).
+static inline void edge_factor(const Quat& q, const V3& t, const EdgeBlk& e, bool want_jac, double& r, double J[6]) {
+  V3 lp = qrot(q, e.pl) + t;
+  V3 nu = cross(lp - e.a, lp - e.b);
+  V3 de = e.a - e.b;
+  double den = norm(de), nun = norm(nu);
+  r = nun / den;
+  for (int i = 0; i < 6; ++i) J[i] = 0;
+  if (want_jac) {
+    V3 u{nu.x / nun, nu.y / nun, nu.z / nun};
+    V3 g = cross(de, u);   // -(u^T skew(de))
+    V3 jr = cross(lp, g);  //  g^T (-skew(lp))
+    J[0] = jr.x / den;
+    J[1] = jr.y / den;
+    J[2] = jr.z / den;
+    J[3] = g.x / den;
+    J[4] = g.y / den;
+    J[5] = g.z / den;
+  }
+}
+
+static inline void surf_factor(const Quat& q, const V3& t, const SurfBlk& s, bool want_jac, double& r, double J[6]) {
+  V3 lp = qrot(q, s.pl) + t;
+  r = dot(s.n, lp) + s.D;
+  for (int i = 0; i < 6; ++i) J[i] = 0;
+  if (want_jac) {
+    V3 jr = cross(lp, s.n);
+    J[0] = jr.x;
+    J[1] = jr.y;
+    J[2] = jr.z;
+    J[3] = s.n.x;
+    J[4] = s.n.y;
+    J[5] = s.n.z;
+  }
+}
+
 static void lm_evaluate(const std::vector<EdgeBlk>& eb, const std::vector<SurfBlk>& sb, const double x[7],
                         double huber_a, bool want_jac, Normal& N) {
   std::memset(&N, 0, sizeof N);
   Quat q{x[0], x[1], x[2], x[3]};
   V3 t{x[4], x[5], x[6]};
+  double r, J[6];
   for (const EdgeBlk& e : eb) {
-    V3 lp = qrot(q, e.pl) + t;
-    V3 nu = cross(lp - e.a, lp - e.b);
-    V3 de = e.a - e.b;
-    double den = norm(de), nun = norm(nu);
-    double r = nun / den;
-    double J[6] = {0, 0, 0, 0, 0, 0};
-    if (want_jac) {
-      V3 u{nu.x / nun, nu.y / nun, nu.z / nun};
-      V3 g = cross(de, u);  // -(u^T skew(de))
-      V3 jr = cross(lp, g); //  g^T (-skew(lp))
-      J[0] = jr.x / den;
-      J[1] = jr.y / den;
-      J[2] = jr.z / den;
-      J[3] = g.x / den;
-      J[4] = g.y / den;
-      J[5] = g.z / den;
-    }
+    edge_factor(q, t, e, want_jac, r, J);
     accum(N, J, r, huber_a);
   }
   for (const SurfBlk& s : sb) {
-    V3 lp = qrot(q, s.pl) + t;
-    double r = dot(s.n, lp) + s.D;
-    double J[6] = {0, 0, 0, 0, 0, 0};
-    if (want_jac) {
-      V3 jr = cross(lp, s.n);
-      J[0] = jr.x;
-      J[1] = jr.y;
-      J[2] = jr.z;
-      J[3] = s.n.x;
-      J[4] = s.n.y;
-      J[5] = s.n.z;
-    }
+    surf_factor(q, t, s, want_jac, r, J);
     accum(N, J, r, huber_a);
   }
 }
@@ -1257,6 +1266,22 @@ int lmsf_oracle_lstsq53(const double a[15], const double b[5], double x[3]) {
 }
 int lmsf_oracle_solve6(const double a[36], const double b[6], double x[6]) {
   qr_solve<6, 6>(a, b, x);
+  return 0;
+}
+// test hooks: one cost-function evaluation (kind 0: geom = a, b; kind 1: geom = n, D) and the SE3 plus
+int lmsf_oracle_factor_eval(int kind, const double x[7], const double p[3], const double geom[7], double* r,
+                            double J6[6]) {
+  Quat q{x[0], x[1], x[2], x[3]};
+  V3 t{x[4], x[5], x[6]};
+  V3 pl{p[0], p[1], p[2]};
+  if (kind == 0)
+    edge_factor(q, t, EdgeBlk{pl, V3{geom[0], geom[1], geom[2]}, V3{geom[3], geom[4], geom[5]}}, true, *r, J6);
+  else
+    surf_factor(q, t, SurfBlk{pl, V3{geom[0], geom[1], geom[2]}, geom[3]}, true, *r, J6);
+  return 0;
+}
+int lmsf_oracle_se3_plus(const double x[7], const double d[6], double out[7]) {
+  se3_plus(x, d, out);
   return 0;
 }
 int lmsf_oracle_se3_exp(const double d[6], double q[4], double t[3]) {

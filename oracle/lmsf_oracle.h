@@ -29,8 +29,10 @@
  *            Rows a4.1 / a4.2: control flow, types and expression order of the
  *            two matchers (libref_match.so; Eigen's solvers answered by
  *            oracle_math.h, so their arithmetic is not part of the pin).
+ *            Row a5.4: the Ceres cost functions' residuals / Jacobians and the
+ *            SE3 parameterization's Plus (libref_factor.so).
  *   UNPINNED rows a2 (PCL VoxelGrid), a4's solver arithmetic (Eigen eigen
- *            solver / QR), a5 (Gauss-Newton, Ceres Huber-LM), a6 (tracker, missing
+ *            solver / QR), a5.1-a5.3 (Gauss-Newton loop, Ceres trust-region loop), a6 (tracker, missing
  *            local-map class): third-party arithmetic that is absent; anchored
  *            on the reference source text (cited per function), numpy / scipy /
  *            LAPACK restatements of the same algorithms (tests/test_oracle.py)
@@ -130,6 +132,9 @@ int lmsf_oracle_symeig3(const double a[9], double w[3], double v[9]);
 int lmsf_oracle_symeig6(const double a[36], double w[6], double v[36]);
 int lmsf_oracle_lstsq53(const double a[15], const double b[5], double x[3]);
 int lmsf_oracle_solve6(const double a[36], const double b[6], double x[6]);
+int lmsf_oracle_factor_eval(int kind, const double x[7], const double p[3], const double geom[7], double* r,
+                            double J6[6]);
+int lmsf_oracle_se3_plus(const double x[7], const double d[6], double out[7]);
 int lmsf_oracle_se3_exp(const double d[6], double q[4], double t[3]);
 /* one Ceres-style Huber-LM solve on explicit residual blocks (tests compare it
  * with a numpy restatement): edge blocks {pl(3), a(3), b(3)}, surf blocks

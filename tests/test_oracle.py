@@ -763,6 +763,51 @@ def test_match_vs_reference_code(oracle_lib, synth):
     assert n_acc > 5000
 
 
+def test_factors_vs_reference_code(oracle_lib):
+    """Row a5.4 PINNED: the oracle's residuals, Jacobians and SE3 plus against the reference's own
+    se3PointEdgeFactor::Evaluate, se3PointSurfFactor::Evaluate, PoseSE3Parameterization::{Plus, ComputeJacobian} and
+    Math::GetTransformFromSe3, compiled from their unmodified headers into oracle/_ref/libref_factor.so (Eigen's
+    fixed-size expressions coefficient by coefficient, quaternion product / rotation answered by oracle_math.h).
+    Conventions (left perturbation, a / b order, signs, the Taylor branch of the exponential) and expression order are
+    what is pinned: every number is bit-identical over 2 000 random poses."""
+    path = os.path.join(os.path.dirname(entry.ORACLE_LIB), "_ref", "libref_factor.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_factor.so is not built (needs /root/reference)")
+    ref, orc = C.CDLL(path), C.CDLL(entry.ORACLE_LIB)
+    dp = C.POINTER(C.c_double)
+
+    def ev(lib, name, kind, x, p, g):
+        r, J = C.c_double(0), np.zeros(6)
+        assert getattr(lib, name)(kind, x.ctypes.data_as(dp), p.ctypes.data_as(dp), g.ctypes.data_as(dp), C.byref(r),
+                                  J.ctypes.data_as(dp)) == 0
+        return np.concatenate([[r.value], J])
+
+    def plus(lib, name, x, d):
+        out = np.zeros(7)
+        assert getattr(lib, name)(x.ctypes.data_as(dp), d.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+        return out
+
+    rng = np.random.default_rng(1)
+    u64 = lambda v: np.ascontiguousarray(v, np.float64).view(np.uint64)
+    jac_norm = 0.0
+    for it in range(2000):
+        q = rng.normal(size=4)
+        x = np.concatenate([q / np.linalg.norm(q), rng.normal(size=3) * 5])
+        p = rng.normal(size=3) * 20
+        a = rng.normal(size=3) * 20
+        b = a + rng.normal(size=3) * 0.2                      # the matcher's a, b: 0.2 m apart
+        n = rng.normal(size=3)
+        for kind, g in ((0, np.concatenate([a, b, [0.0]])),
+                        (1, np.concatenate([n / np.linalg.norm(n), [rng.normal() * 5, 0.0, 0.0, 0.0]]))):
+            vr = ev(ref, "ref_factor_eval", kind, x, p, g)
+            vo = ev(orc, "lmsf_oracle_factor_eval", kind, x, p, g)
+            assert np.array_equal(u64(vr), u64(vo)), (it, kind, vr, vo)
+            jac_norm += np.abs(vr[1:]).sum()
+        d = rng.normal(size=6) * (1e-12 if it % 7 == 0 else 0.05)          # both branches of GetTransformFromSe3
+        assert np.array_equal(u64(plus(ref, "ref_se3_plus", x, d)), u64(plus(orc, "lmsf_oracle_se3_plus", x, d))), it
+    assert jac_norm > 1000.0
+
+
 def _np_gn(me, ms, edge, surf, pose, max_iters=10):
     """EdgeSurfFeatureRegistration::Solve + GNOptimization (registration/edgeSurfFeatureRegistration.hpp:113-330):
     re-match every iteration, J = grad^T [-R skew(p) | I], float residual, QR solve of JTJ, first-iteration degeneracy
