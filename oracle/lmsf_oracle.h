@@ -30,9 +30,10 @@
  *            two matchers (libref_match.so; Eigen's solvers answered by
  *            oracle_math.h, so their arithmetic is not part of the pin).
  *            Row a5.4: the Ceres cost functions' residuals / Jacobians and the
- *            SE3 parameterization's Plus (libref_factor.so).
+ *            SE3 parameterization's Plus (libref_factor.so).  Rows a4.3 / a5.1 /
+ *            a5.2: the whole Gauss-Newton registration loop (libref_gn.so).
  *   UNPINNED rows a2 (PCL VoxelGrid), a4's solver arithmetic (Eigen eigen
- *            solver / QR), a5.1-a5.3 (Gauss-Newton loop, Ceres trust-region loop), a6 (tracker, missing
+ *            solver / QR / inverse), a5.3 (Ceres trust-region loop), a6 (tracker, missing
  *            local-map class): third-party arithmetic that is absent; anchored
  *            on the reference source text (cited per function), numpy / scipy /
  *            LAPACK restatements of the same algorithms (tests/test_oracle.py)

@@ -808,6 +808,72 @@ def test_factors_vs_reference_code(oracle_lib):
     assert jac_norm > 1000.0
 
 
+def test_gn_register_vs_reference_code(oracle_lib, synth):
+    """Rows a4.3 / a5.1 / a5.2 PINNED: the oracle's Gauss-Newton registration against the reference's own
+    EdgeSurfFeatureRegistration::Solve (with its own matchers) compiled from the unmodified headers into
+    oracle/_ref/libref_gn.so — Eigen coefficient by coefficient, its small solvers and quaternion algebra answered by
+    oracle_math.h, kNN by the vendored nanoflann.  The loop, the row order, the float truncations, the degeneracy
+    quirk, the half-angle update and the float convergence test are what is pinned: the translation is bit-identical
+    and the rotation equal to the last bit after 1, 2 and 10 iterations, from three priors, and in the converged,
+    starved (< 10 matches) and fully degenerate cases."""
+    from scipy.spatial.transform import Rotation
+    path = os.path.join(os.path.dirname(entry.ORACLE_LIB), "_ref", "libref_gn.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_gn.so is not built (needs /root/reference)")
+    dll = C.CDLL(path)
+    fp, dp = C.POINTER(C.c_float), C.POINTER(C.c_double)
+
+    def ref_gn(me, ms, e, s, iters, R, t):
+        me, ms, e, s = [np.ascontiguousarray(a, np.float32).reshape(-1, 4) for a in (me, ms, e, s)]
+        R, t, q = np.array(R, np.float64).reshape(9).copy(), np.array(t, np.float64).copy(), np.zeros(4)
+        assert dll.ref_gn_solve(me.ctypes.data_as(fp), len(me), ms.ctypes.data_as(fp), len(ms), e.ctypes.data_as(fp), len(e),
+                                s.ctypes.data_as(fp), len(s), iters, R.ctypes.data_as(dp), t.ctypes.data_as(dp),
+                                q.ctypes.data_as(dp)) == 0
+        return R.reshape(3, 3), t, q
+
+    sensor = synth.vlp16()
+    sw0, sw1 = synth.make_sweep(sensor, 0), synth.make_sweep(sensor, 1)
+    yaw = Rotation.from_euler("z", 0.4, degrees=True).as_matrix()
+    seen = set()
+    for iters in (1, 2, 10):
+        o = oracle_lib.context(0, n_scans=16, oracle_knn_mode=0, gn_max_iters=iters, oracle_threads=os.cpu_count() or 1)
+        _, me, ms = o.extract_features(sw0)
+        o.map_set(0, me)
+        o.map_set(1, ms)
+        _, e, s_all = o.extract_features(sw1)
+        s = s_all[::5]
+        cases = [(e, s, np.eye(3), np.zeros(3)),
+                 (e, s, np.eye(3), np.array([0.05, -0.03, 0.01])),
+                 (e, s, yaw, np.array([0.02, 0.0, 0.0])),
+                 (e[:4], s[:3], np.eye(3), np.zeros(3))]                       # starved: fewer than ten matches
+        if iters == 10:
+            cases.append((e, s_all, np.eye(3), np.zeros(3)))                   # every feature: converges in < 10 steps
+        for ce, cs, R0, t0 in cases:
+            R, t, q0 = ref_gn(me, ms, ce, cs, iters, R0, t0)
+            po, st = o.register(ce, cs, pose=np.concatenate([q0, t0]), solver=0)
+            assert np.array_equal(t.view(np.uint64), po[4:].view(np.uint64)), (iters, len(ce), len(cs), t, po[4:])
+            assert np.abs(R - Rotation.from_quat(po[:4]).as_matrix()).max() < 1e-15
+            seen.add(("converged", bool(st["converged"])))
+            seen.add(("degenerate", bool(st["degenerate"])))
+            seen.add(("starved", st["n_edge_matched"] + st["n_surf_matched"] < 10))
+        if iters == 10:
+            # degenerate: the scene shrunk five times and twelve surf points only -> the LARGEST eigenvalue of JTJ is
+            # below 100, the reference's loop (:289-302) zeroes all six rows, the step vanishes, "converged" at once
+            sc = np.array([0.2, 0.2, 0.2, 1.0], np.float32)
+            ok, _ = o.match(1, np.ascontiguousarray(s_all[:, :3]))
+            cand = s_all[ok.astype(bool)]
+            near = cand[np.argsort(np.linalg.norm(cand[:, :3], axis=1))[:12]] * sc
+            o.map_set(0, me * sc)
+            o.map_set(1, ms * sc)
+            R, t, q0 = ref_gn(me * sc, ms * sc, e[:0], near, iters, np.eye(3), np.array([0.001, 0.0, 0.0]))
+            po, st = o.register(e[:0], near, pose=np.concatenate([q0, [0.001, 0.0, 0.0]]), solver=0)
+            assert np.array_equal(t.view(np.uint64), po[4:].view(np.uint64)) and np.array_equal(R, np.eye(3))
+            assert st["degenerate"] and st["converged"] and st["outer_iters"] == 1 and st["n_surf_matched"] >= 10
+            seen.add(("degenerate", True))
+        o.close()
+    assert {("converged", True), ("converged", False), ("degenerate", True), ("starved", True)} <= seen
+
+
 def _np_gn(me, ms, edge, surf, pose, max_iters=10):
     """EdgeSurfFeatureRegistration::Solve + GNOptimization (registration/edgeSurfFeatureRegistration.hpp:113-330):
     re-match every iteration, J = grad^T [-R skew(p) | I], float residual, QR solve of JTJ, first-iteration degeneracy
