@@ -67,7 +67,8 @@ typedef struct {
   int32_t gn_max_iters;      /* 10   (edgeSurfFeatureRegistration.hpp:65) */
   int32_t lm_outer_start;    /* 10, decremented before every solve, floor 2 (ceres_...:46,100-101) */
   int32_t lm_inner_iters;    /* 4    (ceres_...:118) */
-  float huber_delta;         /* 0.1  (ceres_...:107) */
+  float huber_delta;         /* 0.1  (ceres_...:107); read as the decimal it was written as ("%.6g" -> double),
+                                because the reference's literal is the double 0.1, not (double)0.1f */
   double kf_trans;           /* 0.3 m   (LidarTrackerLocalMap.hpp:65) */
   double kf_rot;             /* 0.1 rad */
   double kf_time;            /* 10 s */

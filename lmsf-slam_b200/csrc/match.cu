@@ -20,6 +20,7 @@
 // No host round trip happens inside a solve: iteration control lives in SolveState on the device,
 // and every kernel of the pre-enqueued sequence exits at once when its phase is over.
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <chrono>
@@ -1378,6 +1379,15 @@ int solve_run(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int upp
   return solve_finish(c, solver, pose, stats, outer_count);
 }
 
+// lmsf_params.huber_delta is a float; the reference writes the double literal HuberLoss(0.1)
+// (ceres_edgeSurfFeatureRegistration.hpp:107) and (double)0.1f = 0.10000000149 moves the pose by 1e-9 m.  The parameter
+// is read as the decimal constant it was written as (shortest 6-digit decimal -> double); host code, same as the oracle.
+static double decimal_of_float(float f) {
+  char buf[48];
+  snprintf(buf, sizeof buf, "%.6g", (double)f);
+  return strtod(buf, nullptr);
+}
+
 int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer_count) {
   if (upper < 0 || outer_count < 0) return LMSF_ERR_INVALID;
   if (upper > c->prm.max_points) return LMSF_ERR_CAPACITY;
@@ -1387,7 +1397,7 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
   sp.iter = 0;
   sp.lm_max_iters = c->prm.lm_inner_iters;
   sp.gn_min_rows = 10;
-  sp.huber = (double)c->prm.huber_delta;
+  sp.huber = decimal_of_float(c->prm.huber_delta);
   MapPair maps;
   maps.edge = view_of(c->map[0]);
   maps.surf = view_of(c->map[1]);

@@ -561,20 +561,33 @@ static double norm7(const double* x) {
   return std::sqrt(s);
 }
 
+// The Huber width travels through the ABI as a float, the reference writes the double literal `HuberLoss(0.1)`
+// (ceres_edgeSurfFeatureRegistration.hpp:107): (double)0.1f = 0.10000000149 moves the pose by 1e-9 m against the
+// reference's own code (oracle/ref_lm.cpp found it).  A float parameter is therefore read as the decimal constant it was
+// written as: its shortest 6-significant-digit decimal, converted to double.
+static double decimal_of_float(float f) {
+  char buf[48];
+  std::snprintf(buf, sizeof buf, "%.6g", (double)f);
+  return std::strtod(buf, nullptr);
+}
+
 // ceres::Solve with DENSE_QR, Levenberg-Marquardt trust region, Jacobi scaling,
 // max_num_iterations (ceres_edgeSurfFeatureRegistration.hpp:116-123).  Ceres is
 // absent and unpinned: TrustRegionMinimizer / LevenbergMarquardtStrategy of
 // Ceres 1.14 restated.  The regularised least-squares step
 // is solved through its normal equations (Cholesky) instead of QR of [J; D].
-static void lm_solve(const std::vector<EdgeBlk>& eb, const std::vector<SurfBlk>& sb, double huber_a, int max_iters,
-                     double x[7], int& steps, int& accepted, double& cost_out) {
+// `evaluate(x, want_jac, Normal&)` and `plus(x, delta, out)` are the problem: the library's own blocks (lm_solve
+// below) or a caller's residual callbacks (lmsf_oracle_lm_solve_cb, used to run the reference's own cost functions).
+template <class Eval, class Plus>
+static void lm_solve_t(Eval&& evaluate, Plus&& plus, bool empty, int max_iters, double x[7], int& steps, int& accepted,
+                       double& cost_out) {
   Normal N;
-  lm_evaluate(eb, sb, x, huber_a, true, N);
+  evaluate(x, true, N);
   double cost = N.cost;
   cost_out = cost;
   steps = 0;
   accepted = 0;
-  if (eb.empty() && sb.empty()) return;
+  if (empty) return;
   double scale[6];
   for (int j = 0; j < 6; ++j) scale[j] = 1.0 / (1.0 + std::sqrt(N.H[j * 6 + j]));
   double radius = 1e4, decrease = 2.0;
@@ -625,9 +638,9 @@ static void lm_solve(const std::vector<EdgeBlk>& eb, const std::vector<SurfBlk>&
     invalid = 0;
     double delta[6], cand[7];
     for (int j = 0; j < 6; ++j) delta[j] = step[j] * scale[j];
-    se3_plus(x, delta, cand);
+    plus(x, delta, cand);
     Normal Nc;
-    lm_evaluate(eb, sb, cand, huber_a, false, Nc);
+    evaluate(cand, false, Nc);
     double diff[7];
     for (int i = 0; i < 7; ++i) diff[i] = x[i] - cand[i];
     if (norm7(diff) <= 1e-8 * (x_norm + 1e-8)) break;   // parameter tolerance: candidate NOT taken
@@ -637,7 +650,7 @@ static void lm_solve(const std::vector<EdgeBlk>& eb, const std::vector<SurfBlk>&
     if (rho > 1e-3) {
       std::memcpy(x, cand, sizeof(double) * 7);
       x_norm = norm7(x);
-      lm_evaluate(eb, sb, x, huber_a, true, N);
+      evaluate(x, true, N);
       cost = N.cost;
       ++accepted;
       double u = 2.0 * rho - 1.0;  // Ceres: pow(2 rho - 1, 3); u*u*u differs from it by <= 1 ulp
@@ -652,6 +665,13 @@ static void lm_solve(const std::vector<EdgeBlk>& eb, const std::vector<SurfBlk>&
     if (radius < 1e-32) break;
   }
   cost_out = cost;
+}
+
+static void lm_solve(const std::vector<EdgeBlk>& eb, const std::vector<SurfBlk>& sb, double huber_a, int max_iters,
+                     double x[7], int& steps, int& accepted, double& cost_out) {
+  lm_solve_t([&](const double* xx, bool jac, Normal& N) { lm_evaluate(eb, sb, xx, huber_a, jac, N); },
+             [&](const double* xx, const double* d, double* out) { se3_plus(xx, d, out); }, eb.empty() && sb.empty(),
+             max_iters, x, steps, accepted, cost_out);
 }
 
 }  // namespace
@@ -849,7 +869,7 @@ static void solve_lm(lmsf_oracle_ctx* c, const P4* edge, int ne, const P4* surf,
     for (int i = 0; i < ns; ++i)
       if (ok_s[i]) sb.push_back(SurfBlk{V3{(double)surf[i].x, (double)surf[i].y, (double)surf[i].z}, si[i].n, si[i].D});
     int s = 0, a = 0;
-    lm_solve(eb, sb, c->prm.huber_delta, c->prm.lm_inner_iters, x, s, a, cost);
+    lm_solve(eb, sb, decimal_of_float(c->prm.huber_delta), c->prm.lm_inner_iters, x, s, a, cost);
     total += s;
     acc += a;
   }
@@ -1278,6 +1298,30 @@ int lmsf_oracle_factor_eval(int kind, const double x[7], const double p[3], cons
     edge_factor(q, t, EdgeBlk{pl, V3{geom[0], geom[1], geom[2]}, V3{geom[3], geom[4], geom[5]}}, true, *r, J6);
   else
     surf_factor(q, t, SurfBlk{pl, V3{geom[0], geom[1], geom[2]}, geom[3]}, true, *r, J6);
+  return 0;
+}
+// test hook: the same trust-region loop over a caller's problem — n_res residual blocks, each giving (r, 1x6 local
+// Jacobian) at x through `residual`, the manifold plus through `plus`; Huber loss + corrector and the accumulation of the
+// normal equations in block order are the oracle's (accum).  Used to run the reference's own cost functions and
+// parameterization inside the restated ceres::Solve (oracle/shim_fixed/ceres/ceres.h).
+int lmsf_oracle_lm_solve_cb(int n_res, lmsf_oracle_residual_cb residual, lmsf_oracle_plus_cb plus, void* user,
+                            double huber_a, int max_iters, double x[7], int* steps, int* accepted, double* cost) {
+  int st = 0, ac = 0;
+  double c = 0;
+  lm_solve_t(
+      [&](const double* xx, bool jac, Normal& N) {
+        std::memset(&N, 0, sizeof N);
+        double r, J[6];
+        for (int i = 0; i < n_res; ++i) {
+          for (int k = 0; k < 6; ++k) J[k] = 0;
+          residual(user, i, xx, jac ? 1 : 0, &r, J);
+          accum(N, J, r, huber_a);
+        }
+      },
+      [&](const double* xx, const double* d, double* out) { plus(user, xx, d, out); }, n_res == 0, max_iters, x, st, ac, c);
+  if (steps) *steps = st;
+  if (accepted) *accepted = ac;
+  if (cost) *cost = c;
   return 0;
 }
 int lmsf_oracle_se3_plus(const double x[7], const double d[6], double out[7]) {

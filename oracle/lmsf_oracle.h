@@ -31,9 +31,11 @@
  *            oracle_math.h, so their arithmetic is not part of the pin).
  *            Row a5.4: the Ceres cost functions' residuals / Jacobians and the
  *            SE3 parameterization's Plus (libref_factor.so).  Rows a4.3 / a5.1 /
- *            a5.2: the whole Gauss-Newton registration loop (libref_gn.so).
+ *            a5.2: the whole Gauss-Newton registration loop (libref_gn.so).  Row
+ *            a5.3: the factory-default Ceres registration around ceres::Solve —
+ *            outer budget, problem construction, re-matching (libref_lm.so).
  *   UNPINNED rows a2 (PCL VoxelGrid), a4's solver arithmetic (Eigen eigen
- *            solver / QR / inverse), a5.3 (Ceres trust-region loop), a6 (tracker, missing
+ *            solver / QR / inverse), Ceres' own trust-region loop (a5.3), a6 (tracker, missing
  *            local-map class): third-party arithmetic that is absent; anchored
  *            on the reference source text (cited per function), numpy / scipy /
  *            LAPACK restatements of the same algorithms (tests/test_oracle.py)
@@ -135,6 +137,10 @@ int lmsf_oracle_lstsq53(const double a[15], const double b[5], double x[3]);
 int lmsf_oracle_solve6(const double a[36], const double b[6], double x[6]);
 int lmsf_oracle_factor_eval(int kind, const double x[7], const double p[3], const double geom[7], double* r,
                             double J6[6]);
+typedef void (*lmsf_oracle_residual_cb)(void* user, int i, const double x[7], int want_jac, double* r, double J6[6]);
+typedef void (*lmsf_oracle_plus_cb)(void* user, const double x[7], const double d[6], double out[7]);
+int lmsf_oracle_lm_solve_cb(int n_res, lmsf_oracle_residual_cb residual, lmsf_oracle_plus_cb plus, void* user,
+                            double huber_a, int max_iters, double x[7], int* steps, int* accepted, double* cost);
 int lmsf_oracle_se3_plus(const double x[7], const double d[6], double out[7]);
 int lmsf_oracle_se3_exp(const double d[6], double q[4], double t[3]);
 /* one Ceres-style Huber-LM solve on explicit residual blocks (tests compare it
