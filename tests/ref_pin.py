@@ -146,3 +146,47 @@ def check_sc_make_against_reference(make, sweeps, ref_sc):
         d_r, k_r = ref_sc.make(pts)
         assert np.array_equal(bits(d_o), bits(d_r))
         assert np.array_equal(bits(k_o), bits(k_r))
+
+
+def check_lm_register_against_reference(ctx, synth, exact):
+    """ctx: a context (oracle or CUDA library) with extract_features / map_set / set_lm_outer / register.  Twelve
+    consecutive factory-default (Huber-LM) solves on ONE solver object against the reference's own
+    CeresEdgeSurfFeatureRegistration (oracle/_ref/libref_lm.so; ceres::Solve answered by the oracle's restated loop).
+    exact: translation bit-identical and rotation to the last bit (oracle); otherwise BASELINE.json's parity bar,
+    1e-4 m and 1e-5 rad (CUDA library: its fp64 reduction order over the rows differs).  Returns the outer budgets."""
+    from scipy.spatial.transform import Rotation
+    C.CDLL(entry.ORACLE_LIB, mode=C.RTLD_GLOBAL)
+    dll = C.CDLL(_ref_path("libref_lm.so"))
+    dll.ref_lm_create.restype = C.c_void_p
+    fp, dp = C.POINTER(C.c_float), C.POINTER(C.c_double)
+    sensor = synth.vlp16()
+    _, me, ms = ctx.extract_features(synth.make_sweep(sensor, 0))
+    ctx.map_set(0, me)
+    ctx.map_set(1, ms)
+    h = C.c_void_p(dll.ref_lm_create())
+    for kind, m in ((0, me), (1, ms)):
+        m = np.ascontiguousarray(m, np.float32)
+        assert dll.ref_lm_set_map(h, kind, m.ctypes.data_as(fp), len(m)) == 0
+    ctx.set_lm_outer(10)
+    yaw = Rotation.from_euler("z", 0.4, degrees=True).as_matrix()
+    priors = [(np.eye(3), np.zeros(3)), (np.eye(3), np.array([0.05, -0.03, 0.01])), (yaw, np.array([0.02, 0.0, 0.0]))]
+    outers = []
+    for k in range(12):
+        R0, t0 = priors[k % 3]
+        _, e, s = ctx.extract_features(synth.make_sweep(sensor, 1 + k % 3))
+        e, s = np.ascontiguousarray(e), np.ascontiguousarray(s[::3])
+        R, t, q0 = np.array(R0, np.float64).reshape(9).copy(), np.array(t0, np.float64).copy(), np.zeros(4)
+        assert dll.ref_lm_solve(h, e.ctypes.data_as(fp), len(e), s.ctypes.data_as(fp), len(s), R.ctypes.data_as(dp),
+                                t.ctypes.data_as(dp), q0.ctypes.data_as(dp)) == 0
+        po, st = ctx.register(e, s, pose=np.concatenate([q0, t0]), solver=1)
+        Ro = Rotation.from_quat(po[:4]).as_matrix()
+        if exact:
+            assert np.array_equal(t.view(np.uint64), po[4:].view(np.uint64)), (k, t, po[4:])
+            assert np.abs(R.reshape(3, 3) - Ro).max() < 1e-15
+        else:
+            assert np.linalg.norm(t - po[4:]) < 1e-4, (k, t, po[4:])
+            assert Rotation.from_matrix(R.reshape(3, 3) @ Ro.T).magnitude() < 1e-5, k
+        assert np.linalg.norm(t - t0) > 1e-3                     # the solve moved the pose: the comparison is not vacuous
+        outers.append(st["outer_iters"])
+    dll.ref_lm_destroy(h)
+    return outers

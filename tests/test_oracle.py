@@ -881,41 +881,10 @@ def test_lm_register_vs_reference_code(oracle_lib, synth):
     10 -> 9, 8, ..., 2, 2 — compiled from the unmodified headers into oracle/_ref/libref_lm.so.  ceres::Solve is answered
     by the oracle's restated trust-region loop running over the reference's residual blocks (shim_fixed/ceres/ceres.h), so
     the loop itself is not part of the pin.  Twelve consecutive solves on one solver object: translation bit-identical,
-    rotation equal to the last bit.  (This pin found that the Huber width, a float in the ABI, has to be read as the
-    decimal 0.1 and not as (double)0.1f.)"""
-    from scipy.spatial.transform import Rotation
-    path = os.path.join(os.path.dirname(entry.ORACLE_LIB), "_ref", "libref_lm.so")
-    if not os.path.exists(path):
-        pytest.skip("oracle/_ref/libref_lm.so is not built (needs /root/reference)")
-    dll = C.CDLL(path)
-    dll.ref_lm_create.restype = C.c_void_p
-    fp, dp = C.POINTER(C.c_float), C.POINTER(C.c_double)
-    sensor = synth.vlp16()
+    rotation equal to the last bit (tests/ref_pin.py).  (This pin found that the Huber width, a float in the ABI, has to
+    be read as the decimal 0.1 and not as (double)0.1f.)"""
     o = oracle_lib.context(0, n_scans=16, oracle_knn_mode=0, oracle_threads=os.cpu_count() or 1)
-    _, me, ms = o.extract_features(synth.make_sweep(sensor, 0))
-    o.map_set(0, me)
-    o.map_set(1, ms)
-    h = C.c_void_p(dll.ref_lm_create())
-    for kind, m in ((0, me), (1, ms)):
-        m = np.ascontiguousarray(m, np.float32)
-        assert dll.ref_lm_set_map(h, kind, m.ctypes.data_as(fp), len(m)) == 0
-    o.set_lm_outer(10)
-    yaw = Rotation.from_euler("z", 0.4, degrees=True).as_matrix()
-    priors = [(np.eye(3), np.zeros(3)), (np.eye(3), np.array([0.05, -0.03, 0.01])), (yaw, np.array([0.02, 0.0, 0.0]))]
-    outers = []
-    for k in range(12):
-        R0, t0 = priors[k % 3]
-        _, e, s = o.extract_features(synth.make_sweep(sensor, 1 + k % 3))
-        e, s = np.ascontiguousarray(e), np.ascontiguousarray(s[::3])
-        R, t, q0 = np.array(R0, np.float64).reshape(9).copy(), np.array(t0, np.float64).copy(), np.zeros(4)
-        assert dll.ref_lm_solve(h, e.ctypes.data_as(fp), len(e), s.ctypes.data_as(fp), len(s), R.ctypes.data_as(dp),
-                                t.ctypes.data_as(dp), q0.ctypes.data_as(dp)) == 0
-        po, st = o.register(e, s, pose=np.concatenate([q0, t0]), solver=1)
-        assert np.array_equal(t.view(np.uint64), po[4:].view(np.uint64)), (k, t, po[4:])
-        assert np.abs(R.reshape(3, 3) - Rotation.from_quat(po[:4]).as_matrix()).max() < 1e-15
-        assert np.linalg.norm(t - t0) > 1e-3                     # the solve moved the pose: the comparison is not vacuous
-        outers.append(st["outer_iters"])
-    dll.ref_lm_destroy(h)
+    outers = ref_pin.check_lm_register_against_reference(o, synth, exact=True)
     o.close()
     assert outers == [9, 8, 7, 6, 5, 4, 3, 2, 2, 2, 2, 2]
 

@@ -33,3 +33,14 @@ def test_cuda_sc_make_vs_reference_code(gpu_lib, sweeps):
     g = gpu_lib.context(0, n_scans=16, max_points=1 << 15, max_map_points=1 << 16)
     ref_pin.check_sc_make_against_reference(g.sc_make, sweeps, ref)
     g.close()
+
+
+def test_cuda_lm_register_vs_reference_code(gpu_lib, synth):
+    """Rows a3-a5, the headline parity bar against the reference's own code: twelve consecutive lmsf_register calls
+    (factory-default Huber-LM, stateful outer budget) against CeresEdgeSurfFeatureRegistration::Solve
+    (ceres_edgeSurfFeatureRegistration.hpp:96-130; ceres::Solve answered by the oracle's restated loop) — every pose
+    within 1e-4 m and 1e-5 rad, the budget 9, 8, ..., 2, 2 in step."""
+    g = gpu_lib.context(0, n_scans=16)
+    outers = ref_pin.check_lm_register_against_reference(g, synth, exact=False)
+    g.close()
+    assert outers == [9, 8, 7, 6, 5, 4, 3, 2, 2, 2, 2, 2]
