@@ -39,6 +39,8 @@ SENSORS = {"hdl64": (64, "HDL-64 synthetic 64x2048 sweep (~131k pts)"), "vlp16":
 SETTLE = 24
 FLUSH_BYTES = 192 << 20   # written between timed steps: 1.5x the 126 MB L2
 STATE_D2H_BYTES = 880 + 8  # sizeof(SolveState) + the two feature counts, read back once per sweep
+MAP_LEAF = {}              # --map-leaf E,S: voxel-filtered local map (lmsf_params.map_leaf_edge / map_leaf_surf)
+MAP_DESC = "raw 10-keyframe sliding-window map"
 
 
 def _gen(args):
@@ -142,7 +144,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     pkg = entry.load_package()
-    ctx = pkg.context(local, n_scans=SENSORS[SENSOR][0], max_points=1 << 18)
+    ctx = pkg.context(local, n_scans=SENSORS[SENSOR][0], max_points=1 << 18, **MAP_LEAF)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
     n_pts = [int(s.shape[0]) for s in sweeps]
@@ -155,13 +157,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_sequence(step_fn, profile, K=K):
-        """W untimed + K timed steps; returns (device ms for K steps, per-step wall ms, launches, prof)."""
+    poses = {}
+
+    def run_sequence(step_fn, first_fn, profile, K=K, flush_l2=True):
+        """W untimed + K timed steps; returns (device ms for K steps, per-step wall ms, launches, prof, ...).
+        first_fn(k) prefetches sweep k (the ticket the first step consumes); every step consumes the ticket of its
+        sweep and prefetches the next one."""
         ctx.tracker_reset()
+        state = {"ticket": first_fn(0)}
         for k in range(0, SETTLE + 1):          # initialisation (see SETTLE), then the W warm-up steps
-            step_fn(k, 0.1 * k)
+            poses[k] = step_fn(k, 0.1 * k, state)[0]
         for k in range(SETTLE + 1, SETTLE + W + 1):
-            step_fn(k, 0.1 * k)
+            poses[k] = step_fn(k, 0.1 * k, state)[0]
         barrier()
         ctx.profile_enable(profile)
         ctx.profile_read(reset=True)
@@ -170,28 +177,34 @@ def run_ours(args):
         per = []
         stats = []
         flush_host = 0.0
+        marks = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         sampler.active.set()
         t_wall0 = time.perf_counter()
         e0.record(stream)
-        for k in range(SETTLE + W + 1, SETTLE + W + K + 1):
+        for i, k in enumerate(range(SETTLE + W + 1, SETTLE + W + K + 1)):
             tf = time.perf_counter()
-            with torch.cuda.stream(stream):
-                flush.zero_()                       # L2 flush between timed steps, inside the timed region
+            if flush_l2:
+                with torch.cuda.stream(stream):
+                    flush.zero_()                   # L2 flush between timed steps, inside the timed region
             t0 = time.perf_counter()
             flush_host += t0 - tf
-            if os.environ.get('LMSF_BENCH_DEBUG'):
-                sys.stderr.write(f'flush {k} {(t0 - tf) * 1e3:.3f} ms\n')
-            stats.append(step_fn(k, 0.1 * k))
+            marks[i][0].record(stream)              # behind the flush: the step's own work starts here
+            pose, st = step_fn(k, 0.1 * k, state)
+            marks[i][1].record(stream)
+            poses[k] = pose
+            stats.append(st)
             per.append((time.perf_counter() - t0) * 1e3)
         e1.record(stream)
         barrier()
         sampler.active.clear()
         wall_ms = (time.perf_counter() - t_wall0) * 1e3
         dev_ms = e0.elapsed_time(e1)
+        step_ms = sum(a.elapsed_time(b) for a, b in marks)   # the same K steps without the K memsets
         launches = ctx.launch_count() - l0
         prof = ctx.profile_read(reset=True) if profile else None
         ctx.profile_enable(False)
-        return dev_ms, wall_ms, per, launches, prof, stats, flush_host * 1e3 / K
+        ctx.tracker_prefetch_cancel(state["ticket"])
+        return dev_ms, wall_ms, per, launches, prof, stats, flush_host * 1e3 / K, step_ms
 
     # ---- resident pass: sweeps already in HBM when the timed region starts
     d_ptrs = [ctx.dev_upload_new(s) for s in sweeps]
@@ -203,23 +216,34 @@ def run_ours(args):
     # upload (e2e pass), one feature extraction and one registration.
     # The step is issued in its two halves (lmsf_tracker_submit / lmsf_tracker_wait == lmsf_tracker_step) so that the
     # host enqueues the next sweep's front end while the GPU registers the current one.
-    def step_dev(k, t):
-        ctx.tracker_submit_dev(d_ptrs[k], n_pts[k], t)
-        ctx.tracker_prefetch_dev(d_ptrs[k + 1], n_pts[k + 1])
-        return ctx.tracker_wait()[2]
+    def first_dev(k):
+        return ctx.tracker_prefetch_dev(d_ptrs[k], n_pts[k])
 
-    def step_host(k, t):
-        ctx.tracker_submit(sweeps[k], t)
-        ctx.tracker_prefetch(sweeps[k + 1])
-        return ctx.tracker_wait()[2]
+    def first_host(k):
+        return ctx.tracker_prefetch(sweeps[k])
 
-    run_sequence(step_dev, False, K=2)
-    dev_ms, wall_ms, per, launches, _, stats, fl1 = run_sequence(step_dev, False)
-    # ---- end-to-end pass: host buffers through lmsf_tracker_prefetch + lmsf_tracker_step (H2D of a sweep + D2H of
-    # the pose inside every step)
-    e_dev_ms, e_wall_ms, e_per, _, _, _, fl2 = run_sequence(step_host, False)
+    def step_dev(k, t, state):
+        ctx.tracker_submit_ticket(state["ticket"], t)
+        state["ticket"] = ctx.tracker_prefetch_dev(d_ptrs[k + 1], n_pts[k + 1])
+        r = ctx.tracker_wait()
+        return r[0], r[2]
+
+    def step_host(k, t, state):
+        ctx.tracker_submit_ticket(state["ticket"], t)
+        state["ticket"] = ctx.tracker_prefetch(sweeps[k + 1])     # H2D of the next sweep, inside the step
+        r = ctx.tracker_wait()                                       # D2H of this sweep's pose
+        return r[0], r[2]
+
+    run_sequence(step_dev, first_dev, False, K=2)
+    dev_ms, wall_ms, per, launches, _, stats, fl1, step_ms = run_sequence(step_dev, first_dev, False)
+    gpu_poses = dict(poses)
+    # ---- end-to-end pass: host buffers through lmsf_tracker_prefetch + lmsf_tracker_submit_ticket + lmsf_tracker_wait
+    # (H2D of a sweep + D2H of the pose inside every step)
+    e_dev_ms, e_wall_ms, e_per, _, _, _, fl2, _ = run_sequence(step_host, first_host, False)
+    # ---- the same resident pass without the L2 flush (reported beside the flushed figure, never as `value`)
+    nf_dev_ms, _, _, _, _, _, _, _ = run_sequence(step_dev, first_dev, False, flush_l2=False)
     # ---- instrumented pass (not used for value): per-stage CUDA-event times on the context's streams
-    p_dev_ms, _, _, _, prof, _, fl3 = run_sequence(step_dev, True)
+    p_dev_ms, _, _, _, prof, _, fl3, _ = run_sequence(step_dev, first_dev, True)
     sampler.stop_flag.set()
     sampler.join()
 
@@ -238,11 +262,13 @@ def run_ours(args):
         match_ms = ms["match"] / match_launches
         bytes_per_launch = alg_bytes / match_launches
         achieved = bytes_per_launch / (match_ms * 1e-3) / 1e9 if match_ms > 0 else 0.0
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "match_traffic_bytes.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = tj.get("source", "ncu --set full capture (profiles/), not measured in this run")
             except Exception:
                 traffic = None
         kf = sum(1 for s in stats if s["keyframe"])
@@ -251,7 +277,7 @@ def run_ours(args):
             "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": SENSORS[SENSOR][1] + " scan-to-map edge/surf registration, "
-                                   "Huber-LM solver, raw 10-keyframe sliding-window map, one sequence per GPU",
+                                   "Huber-LM solver, " + MAP_DESC + ", one sequence per GPU",
                        "points_per_sweep": int(np.mean(n_pts)), "sequences": n_gpus,
                        "l2": f"{FLUSH_BYTES >> 20} MiB memset between timed steps (L2 flush: 1.5x the 126 MB L2), inside the timed region",
                        "timing": "CUDA events on the context stream around the K steps, max over ranks",
@@ -260,6 +286,8 @@ def run_ours(args):
                        "p50_ms_per_scan": float(np.median(per)), "p90_ms_per_scan": float(np.percentile(per, 90)),
                        "max_ms_per_scan": float(np.max(per)), "wall_ms_per_step": wall_ms / K,
                        "flush_host_ms_per_step": [fl1, fl2, fl3], "instrumented_pass_ms_per_step": p_dev_ms / K,
+                       "ms_per_step_between_flushes": step_ms / K,
+                       "ms_per_step_no_flush_pass": nf_dev_ms / K,
                        "keyframes_in_timed_region": kf, "per_rank_ms_per_step_and_keyframes": per_rank,
                        "features_per_sweep": int(np.mean([s["n_edge"] + s["n_surf"] for s in stats])),
                        "map_points_end": int(stats[-1]["map_edge"] + stats[-1]["map_surf"]),
@@ -268,19 +296,19 @@ def run_ours(args):
             "e2e": {"value": n_gpus * K / (e2e_ms_max * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(np.mean(n_pts)) * 16, "d2h_bytes_per_step": STATE_D2H_BYTES,
                     "p50_ms_per_scan": float(np.median(e_per)),
-                    "api": "lmsf_tracker_submit(host sweep) + lmsf_tracker_prefetch(next host sweep) + lmsf_tracker_wait(pose out), "
-                           "wall clock around K steps, max over ranks"},
+                    "api": "lmsf_tracker_submit_ticket(sweep k) + lmsf_tracker_prefetch(host sweep k+1: H2D + extraction) + "
+                           "lmsf_tracker_wait(pose out), wall clock around K steps, max over ranks"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_knn (exact 5-NN of every scan feature over the local-map grid)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": traffic,
+                         "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": match_ms,
                          "launches_per_step": ln["match"] / K,
                          "share_of_step": ms["match"] / max(1e-9, p_dev_ms)},
         }
         if n_gpus == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(sweeps, W)
+            line["cpu_baseline"], line["parity"] = cpu_baseline(sweeps, W, gpu_poses)
         print(json.dumps(line), flush=True)
     for p in d_ptrs:
         ctx.dev_free(p)
@@ -289,61 +317,111 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(sweeps, W, sample=4):
+def _pose_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    dt = float(np.linalg.norm(a[4:] - b[4:]))
+    qa, qb = a[:4] / np.linalg.norm(a[:4]), b[:4] / np.linalg.norm(b[:4])
+    return dt, 2.0 * float(np.arccos(min(1.0, abs(float(np.dot(qa, qb))))))
+
+
+def cpu_baseline(sweeps, W, gpu_poses, sample=4):
     """The oracle port of the reference's CPU path on a bounded sample of the same workload: the
     tracker is brought to the steady state with all host threads (untimed), then `sample` sweeps are
-    timed with ONE thread — the reference runs one thread per LiDAR (System/ML_System.hpp:137,248)."""
+    timed with ONE thread — the reference runs one thread per LiDAR (System/ML_System.hpp:137,248).
+    Every pose the oracle produces on the way (initialisation, warm-up and the timed sample) is compared with the
+    pose the CUDA path gave for the same sweep in the resident pass -> the line's `parity` object."""
     lib = entry.load_oracle()
     threads = os.cpu_count() or 1
-    o = lib.context(0, n_scans=SENSORS[SENSOR][0], oracle_knn_mode=0, oracle_threads=threads)
+    o = lib.context(0, n_scans=SENSORS[SENSOR][0], oracle_knn_mode=0, oracle_threads=threads, **MAP_LEAF)
     warm = min(SETTLE + W, len(sweeps) - sample - 1)
+    max_dt = max_dr = 0.0
+    kf_equal = True
+    n_cmp = 0
+
+    def compare(k, r):
+        nonlocal max_dt, max_dr, n_cmp
+        if k in gpu_poses:
+            dt, dr = _pose_err(gpu_poses[k], r[0])
+            max_dt, max_dr, n_cmp = max(max_dt, dt), max(max_dr, dr), n_cmp + 1
+
     for k in range(0, warm + 1):
-        o.tracker_step(sweeps[k], 0.1 * k)
+        compare(k, o.tracker_step(sweeps[k], 0.1 * k))
     lib.fn("set_threads")(o._h, 1)
     t0 = time.perf_counter()
+    res = []
     for k in range(warm + 1, warm + 1 + sample):
-        o.tracker_step(sweeps[k], 0.1 * k)
+        res.append((k, o.tracker_step(sweeps[k], 0.1 * k)))
     dt = time.perf_counter() - t0
+    for k, r in res:
+        compare(k, r)
     o.close()
-    return {"value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
+    base = {"value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{sample} consecutive {SENSOR} sweeps after a {warm}-sweep warm-up of the same sequence, "
                       f"oracle tracker (kd-tree kNN), 1 thread; host has {threads} cores",
             "seconds": dt}
+    parity = {"max_dt_m": max_dt, "max_dr_rad": max_dr, "sweeps_compared": n_cmp, "tol_m": 1e-4, "tol_rad": 1e-5,
+              "ok": bool(n_cmp > 0 and max_dt < 1e-4 and max_dr < 1e-5),
+              "what": "CUDA tracker poses (resident pass) vs oracle tracker poses on the same sweeps: sweeps 0.."
+                      f"{warm + sample} of the bench sequence, including {sample} sweeps of the timed region"}
+    return base, parity
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be
     built here (no PCL/Eigen/Ceres; its tree lacks Map/), so this times the oracle port with all the host
-    threads it can use (OpenMP over features, as the reference's unbuilt LIO-SAM copy does)."""
+    threads it can use.  --gpus N: N independent sequences (seeds 0..N-1, the workload of the N-GPU arm), tracked
+    concurrently by N oracle trackers that share the host cores (cores // N OpenMP threads each — BASELINE.md: "one
+    sequence per core" for the batched configuration); value = N*K sweeps / wall time of the slowest tracker."""
     rank, world, local = dist_env()
     if rank != 0:
         return
     W, K = args.warmup, args.steps
-    sweeps = make_sequence(SETTLE + W + K + 1, seq=0)
+    n_seq = max(1, args.gpus)
+    seqs = [make_sequence(SETTLE + W + K + 1, seq=s) for s in range(n_seq)]
     lib = entry.load_oracle()
-    threads = os.cpu_count() or 1
-    o = lib.context(0, n_scans=SENSORS[SENSOR][0], oracle_knn_mode=0, oracle_threads=threads)
-    for k in range(0, SETTLE + W + 1):
-        o.tracker_step(sweeps[k], 0.1 * k)
-    per = []
+    cores = os.cpu_count() or 1
+    threads = max(1, cores // n_seq)
+    ctxs = [lib.context(0, n_scans=SENSORS[SENSOR][0], oracle_knn_mode=0, oracle_threads=threads, **MAP_LEAF)
+            for _ in range(n_seq)]
+    per = [[] for _ in range(n_seq)]
+    go = threading.Barrier(n_seq + 1)
+    done = threading.Barrier(n_seq + 1)
+
+    def track(i):
+        o, sweeps = ctxs[i], seqs[i]
+        for k in range(0, SETTLE + W + 1):
+            o.tracker_step(sweeps[k], 0.1 * k)
+        go.wait()
+        for k in range(SETTLE + W + 1, SETTLE + W + K + 1):
+            t1 = time.perf_counter()
+            o.tracker_step(sweeps[k], 0.1 * k)
+            per[i].append((time.perf_counter() - t1) * 1e3)
+        done.wait()
+
+    ths = [threading.Thread(target=track, args=(i,), daemon=True) for i in range(n_seq)]
+    for t in ths:
+        t.start()
+    go.wait()                      # every tracker has finished its untimed sweeps
     t0 = time.perf_counter()
-    for k in range(SETTLE + W + 1, SETTLE + W + K + 1):
-        t1 = time.perf_counter()
-        o.tracker_step(sweeps[k], 0.1 * k)
-        per.append((time.perf_counter() - t1) * 1e3)
+    done.wait()                    # the slowest tracker has finished its K timed sweeps
     dt = time.perf_counter() - t0
-    o.close()
-    v = K / dt
+    for t in ths:
+        t.join()
+    for o in ctxs:
+        o.close()
+    v = n_seq * K / dt
+    allper = [x for p in per for x in p]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": SENSORS[SENSOR][1] + " scan-to-map edge/surf registration, "
-                               "Huber-LM solver, raw 10-keyframe sliding-window map, one sequence",
-                   "p50_ms_per_scan": float(np.median(per))},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{K} consecutive sweeps after {SETTLE} initialisation + {W} warm-up sweeps, oracle tracker, "
-                                   f"{threads} threads"},
+                               "Huber-LM solver, " + MAP_DESC + ", one sequence per GPU",
+                   "sequences": n_seq, "p50_ms_per_scan": float(np.median(allper))},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads * n_seq, "kind": "port",
+                         "sample": f"{K} consecutive sweeps of each of {n_seq} sequence(s) after {SETTLE} initialisation + "
+                                   f"{W} warm-up sweeps, oracle tracker, {n_seq} tracker(s) x {threads} OpenMP threads "
+                                   f"on {cores} host cores"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -388,6 +466,58 @@ def make_loop_data(rank_lo, rank_hi, seed=20260500):
     r = np.random.default_rng(seed + 7)
     qd = np.where(qd > 0, qd + r.normal(0, 0.03, size=qd.shape), 0).astype(np.float32)
     return shard_desc, keys_of(shard_desc), qd, keys_of(qd), q_ids, q_shift
+
+
+def loopdb_cpu_baseline(keys, descs, qk, qd, limit, gpu_ids, nqs=64):
+    """descFindSimilar on the host cores for a bounded sample of the query batch: the ring-key stage is the
+    REFERENCE'S OWN vendored nanoflann k-d tree (oracle/_ref/libref_nanoflann.so: KDTreeVectorOfVectorsAdaptor, leaf 10,
+    SceneRecognitionScanContext.hpp:86-91, 272-279; built outside the timed region as the reference rebuilds it only
+    every tenth keyframe), the ScanContext distance of the ten candidates and the selection are the oracle port."""
+    import ctypes as C
+
+    lib = C.CDLL(entry.ORACLE_LIB)
+    f32p, f64p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    kk = np.ascontiguousarray(keys[:limit])
+    dd = np.ascontiguousarray(descs.reshape(-1, 1200))
+    q_k = np.ascontiguousarray(qk[:nqs])
+    q_d = np.ascontiguousarray(qd[:nqs].reshape(nqs, 1200))
+    o_id = np.full(nqs, -1, np.int32)
+    if os.path.exists(entry.REF_NANOFLANN_LIB):
+        ref = C.CDLL(entry.REF_NANOFLANN_LIB)
+        ref.ref_ringkey_tree_create.restype = C.c_void_p
+        ref.ref_ringkey_tree_create.argtypes = [f32p, C.c_int]
+        ref.ref_ringkey_tree_knn10.argtypes = [C.c_void_p, f32p, C.c_int, i32p, f32p]
+        ref.ref_ringkey_tree_destroy.argtypes = [C.c_void_p]
+        tree = ref.ref_ringkey_tree_create(kk.ctypes.data_as(f32p), C.c_int(limit))
+        idx = np.empty((nqs, 10), np.int32)
+        d10 = np.empty((nqs, 10), np.float32)
+        dist, shift = C.c_double(0), C.c_int(0)
+        t0 = time.perf_counter()
+        ref.ref_ringkey_tree_knn10(tree, q_k.ctypes.data_as(f32p), nqs, idx.ctypes.data_as(i32p), d10.ctypes.data_as(f32p))
+        for q in range(nqs):
+            best, best_id = 1e300, -1
+            for c in idx[q]:
+                if c < 0:
+                    continue
+                lib.lmsf_oracle_sc_distance(q_d[q].ctypes.data_as(f32p), dd[c].ctypes.data_as(f32p), C.byref(dist),
+                                            C.byref(shift))
+                if dist.value < best:
+                    best, best_id = dist.value, int(c)
+            o_id[q] = best_id if best < 0.2 else -1
+        dt = time.perf_counter() - t0
+        ref.ref_ringkey_tree_destroy(tree)
+        how = "ring-key 10-NN by the reference's own nanoflann k-d tree (kind 'reference' for that stage), SC distance + selection by the oracle port"
+    else:
+        o_d, o_s = np.empty(nqs, np.float64), np.empty(nqs, np.int32)
+        t0 = time.perf_counter()
+        lib.lmsf_oracle_sc_search(kk.ctypes.data_as(f32p), dd.ctypes.data_as(f32p), C.c_int(limit), q_k.ctypes.data_as(f32p),
+                                  q_d.ctypes.data_as(f32p), C.c_int(nqs), C.c_double(0.2), o_id.ctypes.data_as(i32p),
+                                  o_d.ctypes.data_as(f64p), o_s.ctypes.data_as(i32p))
+        dt = time.perf_counter() - t0
+        how = "oracle brute-force ring-key scan + SC distance (oracle/_ref/libref_nanoflann.so absent)"
+    return {"value": nqs / dt, "unit": "queries/s", "cores": 1, "kind": "port",
+            "sample": f"{nqs} of the {LOOP_NQ} queries against the same database, {how}, 1 thread",
+            "agrees_with_gpu": bool(np.array_equal(o_id, gpu_ids[:nqs]))}
 
 
 def run_loopdb(args):
@@ -490,25 +620,7 @@ def run_loopdb(args):
                          "note": "whole step time used as the kernel time (upper bound); algorithmic bytes = keys once + queries"},
         }
         if args.gpus == 1 and not args.no_cpu:
-            import ctypes as C
-            lib = C.CDLL(entry.ORACLE_LIB)
-            nqs = 16
-            f32p, f64p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int32)
-            o_id = np.empty(nqs, np.int32)
-            o_d = np.empty(nqs, np.float64)
-            o_s = np.empty(nqs, np.int32)
-            kk = np.ascontiguousarray(keys)
-            dd = np.ascontiguousarray(descs.reshape(-1, 1200))
-            t0 = time.perf_counter()
-            lib.lmsf_oracle_sc_search(kk.ctypes.data_as(f32p), dd.ctypes.data_as(f32p), C.c_int(int(limit)),
-                                      qk[:nqs].ctypes.data_as(f32p), qd[:nqs].reshape(nqs, 1200).ctypes.data_as(f32p),
-                                      C.c_int(nqs), C.c_double(0.2), o_id.ctypes.data_as(i32p), o_d.ctypes.data_as(f64p),
-                                      o_s.ctypes.data_as(i32p))
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": nqs / dt, "unit": "queries/s", "cores": 1, "kind": "port",
-                                    "sample": f"{nqs} of the {LOOP_NQ} queries against the same database, oracle "
-                                              "brute-force ring-key scan + SC distance, 1 thread",
-                                    "agrees_with_gpu": bool(np.array_equal(o_id, ids[:nqs]))}
+            line["cpu_baseline"] = loopdb_cpu_baseline(keys, descs, qk, qd, int(limit), ids)
         print(json.dumps(line), flush=True)
     # Everything torch allocated or copied on the context's (external) stream must be released while that stream
     # still exists: freeing a pinned block records an event on the streams it was used with.
@@ -530,13 +642,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--sensor", default="hdl64", choices=sorted(SENSORS), help="hdl64 = the headline configuration")
+    ap.add_argument("--map-leaf", default="", help="E,S: voxel-filter the local map at these leaf sizes (LIO-SAM-style "
+                    "0.2,0.4); default: the shipped tracker's raw window")
     ap.add_argument("--workload", default="registration", choices=["registration", "loopdb"],
                     help="registration = the headline metric (default); loopdb = sharded loop-closure descriptor search")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    global SENSOR, METRIC
+    global SENSOR, METRIC, MAP_LEAF, MAP_DESC
     SENSOR = args.sensor
+    if args.map_leaf:
+        le, ls = (float(x) for x in args.map_leaf.split(","))
+        MAP_LEAF = {"map_leaf_edge": le, "map_leaf_surf": ls}
+        MAP_DESC = f"10-keyframe sliding-window map voxel-filtered at {le} m (edge) / {ls} m (surf)"
     if SENSOR != "hdl64":
         METRIC = METRIC.replace("HDL-64", "VLP-16")
     if args.workload == "loopdb":

@@ -73,9 +73,7 @@ typedef struct {
   double kf_rot;             /* 0.1 rad */
   double kf_time;            /* 10 s */
   int32_t max_map_points;    /* capacity of one local map; default window * max_points */
-  int32_t oracle_knn_mode;   /* ignored by the CUDA library (oracle: 0 kd-tree, 1 brute force) */
-  int32_t oracle_threads;    /* ignored by the CUDA library */
-  int32_t reserved[9];
+  int32_t reserved[11];      /* must be zero */
 } lmsf_params;
 
 typedef struct {
@@ -183,19 +181,26 @@ int lmsf_tracker_step_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp,
 /* Front-end / back-end pipelining.  The reference runs LOAMFeatureProcessorBase::Process on the sensor
  * thread and LidarTrackerLocalMap::Solve on estimate_thread_, connected by a queue
  * (System/ML_System.hpp:137-141, :210-227): the features of sweep k+1 are extracted while sweep k is
- * registered.  lmsf_tracker_prefetch(_dev) enqueues the upload and feature extraction of the NEXT sweep on
- * the context's front-end stream and returns at once; the following lmsf_tracker_step(_dev) call with the
- * same pointer and count consumes those features instead of extracting again (any other sweep: the
- * prefetched one is dropped).  The caller must not modify a prefetched host buffer before that step. */
-int lmsf_tracker_prefetch(lmsf_ctx* c, const float* xyzi, int n);
-int lmsf_tracker_prefetch_dev(lmsf_ctx* c, const float* d_xyzi, int n);
+ * registered.  lmsf_tracker_prefetch(_dev) enqueues the upload and feature extraction of a COMING sweep on
+ * the context's front-end stream, hands back a ticket (> 0) and returns at once; lmsf_tracker_step_ticket /
+ * lmsf_tracker_submit_ticket consume exactly that sweep.  A prefetched sweep is identified by its ticket only
+ * (never by the caller's pointer), a host sweep is copied at prefetch time, at most two sweeps wait at a time
+ * (a third prefetch returns LMSF_ERR_STATE), lmsf_tracker_prefetch_cancel gives a waiting one up, and a
+ * ticket that was consumed, cancelled or displaced is refused with LMSF_ERR_STATE.  lmsf_tracker_step /
+ * _submit with a sweep pointer always extract that sweep now. */
+int lmsf_tracker_prefetch(lmsf_ctx* c, const float* xyzi, int n, int64_t* ticket);
+int lmsf_tracker_prefetch_dev(lmsf_ctx* c, const float* d_xyzi, int n, int64_t* ticket);
+int lmsf_tracker_prefetch_cancel(lmsf_ctx* c, int64_t ticket);
+int lmsf_tracker_step_ticket(lmsf_ctx* c, int64_t ticket, double stamp, double delta[7], double pose_out[7],
+                             lmsf_track_stats* st);
 /* lmsf_tracker_step in two halves, for callers that have host work to do while the GPU registers the sweep
  * (typically: prefetch the next one).  submit = prediction + the whole registration enqueued, returns at once;
  * wait = pose read-back, motion update, keyframe test, local-map update.  One sweep in flight per context:
- * a second submit, or any call that rewrites the feature slot in use, returns LMSF_ERR_STATE until wait.
+ * a second submit, a step, or any call that rewrites the feature slot in use, returns LMSF_ERR_STATE until wait.
  * lmsf_tracker_step(x) == lmsf_tracker_submit(x) + lmsf_tracker_wait(). */
 int lmsf_tracker_submit(lmsf_ctx* c, const float* xyzi, int n, double stamp, const double delta[7]);
 int lmsf_tracker_submit_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp, const double delta[7]);
+int lmsf_tracker_submit_ticket(lmsf_ctx* c, int64_t ticket, double stamp, const double delta[7]);
 int lmsf_tracker_wait(lmsf_ctx* c, double delta_out[7], double pose_out[7], lmsf_track_stats* st);
 /* Same, fed with features instead of a raw sweep — the exact argument of
  * LidarTrackerLocalMap::Solve. */

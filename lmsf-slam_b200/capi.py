@@ -26,7 +26,7 @@ STAGE_NAMES = ("extract", "match", "solve", "map", "voxel", "assoc", "fit")
 
 
 class Params(C.Structure):
-    """lmsf_params (include/lmsf_b200.h) — same layout as lmsf_oracle_params."""
+    """lmsf_params (include/lmsf_b200.h)."""
 
     _fields_ = [
         ("n_scans", C.c_int32),
@@ -49,9 +49,7 @@ class Params(C.Structure):
         ("kf_rot", C.c_double),
         ("kf_time", C.c_double),
         ("max_map_points", C.c_int32),
-        ("oracle_knn_mode", C.c_int32),
-        ("oracle_threads", C.c_int32),
-        ("reserved", C.c_int32 * 9),
+        ("reserved", C.c_int32 * 11),
     ]
 
 
@@ -128,7 +126,8 @@ class Library:
     # symbols only the CUDA library exports
     DEVICE_ONLY = (
         "last_cuda_error", "launch_count", "stream", "tracker_step_dev", "tracker_prefetch", "tracker_prefetch_dev",
-        "tracker_submit", "tracker_submit_dev", "tracker_wait",
+        "tracker_submit", "tracker_submit_dev", "tracker_wait", "tracker_prefetch_cancel", "tracker_step_ticket",
+        "tracker_submit_ticket",
         "dev_alloc", "dev_free",
         "dev_upload", "profile_enable", "profile_read",
         # loop-closure descriptor path (scancontext.cu)
@@ -138,7 +137,8 @@ class Library:
         "handeye_create", "handeye_destroy", "handeye_add_pose", "handeye_calibrate", "handeye_size",
     )
 
-    def __init__(self, path: str, prefix: str = "lmsf_"):
+    def __init__(self, path: str, prefix: str = "lmsf_", params_cls=Params):
+        self.params_cls = params_cls   # a same-layout struct that names implementation-specific reserved words
         if not os.path.exists(path):
             raise FileNotFoundError(
                 f"{path} is missing: build it first (python -c 'import __graft_entry__ as g; g.build()'). "
@@ -156,8 +156,11 @@ class Library:
             f("stream").restype = C.c_void_p
             f("tracker_step_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, _f64p, _f64p,
                                               C.POINTER(TrackStats)]
-            f("tracker_prefetch").argtypes = [C.c_void_p, _f32p, C.c_int]
-            f("tracker_prefetch_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+            f("tracker_prefetch").argtypes = [C.c_void_p, _f32p, C.c_int, C.POINTER(C.c_int64)]
+            f("tracker_prefetch_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+            f("tracker_prefetch_cancel").argtypes = [C.c_void_p, C.c_int64]
+            f("tracker_step_ticket").argtypes = [C.c_void_p, C.c_int64, C.c_double, _f64p, _f64p, C.POINTER(TrackStats)]
+            f("tracker_submit_ticket").argtypes = [C.c_void_p, C.c_int64, C.c_double, _f64p]
             f("tracker_submit").argtypes = [C.c_void_p, _f32p, C.c_int, C.c_double, _f64p]
             f("tracker_submit_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, _f64p]
             f("tracker_wait").argtypes = [C.c_void_p, _f64p, _f64p, C.POINTER(TrackStats)]
@@ -190,7 +193,7 @@ class Library:
             f("handeye_add_pose").argtypes = [C.c_void_p, _f64p, _f64p, _intp]
             f("handeye_calibrate").argtypes = [C.c_void_p, _f64p, _f64p, _intp]
             f("handeye_size").argtypes = [C.c_void_p, _intp]
-        f("ctx_create").argtypes = [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]
+        f("ctx_create").argtypes = [C.c_int, C.POINTER(params_cls), C.POINTER(C.c_void_p)]
         f("ctx_destroy").argtypes = [C.c_void_p]
         f("extract_features").argtypes = [C.c_void_p, _f32p, C.c_int, _u8p, _f32p, _intp, _f32p, _intp]
         f("voxel_downsample").argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, _f32p, _intp, _i32p]
@@ -220,7 +223,7 @@ class Library:
             return False
 
     def default_params(self) -> Params:
-        p = Params()
+        p = self.params_cls()
         rc = self.fn("params_default")(C.byref(p))
         if rc:
             raise LmsfError(rc, "params_default")
@@ -401,24 +404,37 @@ class Context:
                                                   d.ctypes.data_as(_f64p), p.ctypes.data_as(_f64p), C.byref(st)))
         return p, d, st.as_dict()
 
-    def tracker_prefetch(self, xyzi):
-        """Enqueue upload + feature extraction of the NEXT sweep; pass the same array to the next tracker_step.
-        The array must already be a C-contiguous (n, 4) float32 array (it is matched by address)."""
-        a = xyzi
-        if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous and a.ndim == 2
-                and a.shape[1] == 4):
-            raise ValueError("tracker_prefetch needs a C-contiguous (n, 4) float32 array")
-        self._chk(self.lib.fn("tracker_prefetch")(self._h, _fp(a), a.shape[0]))
+    def tracker_prefetch(self, xyzi) -> int:
+        """Enqueue upload + feature extraction of a COMING sweep (copied now); returns the ticket that
+        tracker_step_ticket / tracker_submit_ticket consume."""
+        a = _xyzi(xyzi)
+        t = C.c_int64(0)
+        self._chk(self.lib.fn("tracker_prefetch")(self._h, _fp(a), a.shape[0], C.byref(t)))
+        return t.value
 
-    def tracker_prefetch_dev(self, d_ptr: int, n: int):
-        self._chk(self.lib.fn("tracker_prefetch_dev")(self._h, C.c_void_p(d_ptr), n))
+    def tracker_prefetch_dev(self, d_ptr: int, n: int) -> int:
+        t = C.c_int64(0)
+        self._chk(self.lib.fn("tracker_prefetch_dev")(self._h, C.c_void_p(d_ptr), n, C.byref(t)))
+        return t.value
+
+    def tracker_prefetch_cancel(self, ticket: int):
+        self._chk(self.lib.fn("tracker_prefetch_cancel")(self._h, int(ticket)))
+
+    def tracker_step_ticket(self, ticket: int, stamp: float, delta=IDENTITY_POSE):
+        d = np.array(delta, dtype=np.float64)
+        p = np.zeros(7, np.float64)
+        st = TrackStats()
+        self._chk(self.lib.fn("tracker_step_ticket")(self._h, int(ticket), float(stamp), d.ctypes.data_as(_f64p),
+                                                     p.ctypes.data_as(_f64p), C.byref(st)))
+        return p, d, st.as_dict()
+
+    def tracker_submit_ticket(self, ticket: int, stamp: float, delta=IDENTITY_POSE):
+        d = np.array(delta, dtype=np.float64)
+        self._chk(self.lib.fn("tracker_submit_ticket")(self._h, int(ticket), float(stamp), d.ctypes.data_as(_f64p)))
 
     def tracker_submit(self, xyzi, stamp: float, delta=IDENTITY_POSE):
-        """First half of tracker_step: everything enqueued, nothing waited for (host array as for tracker_prefetch)."""
-        a = xyzi
-        if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags.c_contiguous and a.ndim == 2
-                and a.shape[1] == 4):
-            raise ValueError("tracker_submit needs a C-contiguous (n, 4) float32 array")
+        """First half of tracker_step: everything enqueued, nothing waited for."""
+        a = _xyzi(xyzi)
         d = np.array(delta, dtype=np.float64)
         self._chk(self.lib.fn("tracker_submit")(self._h, _fp(a), a.shape[0], float(stamp), d.ctypes.data_as(_f64p)))
 

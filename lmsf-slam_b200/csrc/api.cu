@@ -108,6 +108,19 @@ static int update_map(Ctx* c, const rigid& T, int type) {
   cudaStream_t st = async ? c->stream_map : c->stream;
   const double reach = 1.2 * (double)c->prm.max_range + 2.0;
   bool fixed_ok[2] = {false, false};
+  for (int kind = 0; kind < 2; ++kind) {  // capacity of both maps first: a refused update leaves both windows untouched
+    int nk = kind ? c->n_surf : c->n_edge;
+    if (nk == 0) continue;
+    const MapIndex& m = c->map[kind];
+    int total = 0;
+    for (int f : m.frame_n) total += f;
+    if (type == 1) {
+      if ((int)m.frame_n.size() + 1 > c->prm.window) total -= m.frame_n.front();
+    } else if (!m.frame_n.empty()) {
+      total -= m.frame_n.back();
+    }
+    if (total + nk > m.cap) return LMSF_ERR_CAPACITY;
+  }
   for (int kind = 0; kind < 2; ++kind) {
     int nk = kind ? c->n_surf : c->n_edge;
     if (nk == 0) continue;
@@ -367,7 +380,6 @@ static int adopt_slot(Ctx* c, int si) {
   Ctx::FeatSlot& sl = c->slot[si];
   alias_slot(c, si);
   sl.filled = false;
-  sl.src = nullptr;
   LM_CUDA(cudaStreamWaitEvent(c->stream, sl.ready, 0));
   c->feat_from_extract = true;
   c->perm_valid = true;
@@ -383,37 +395,39 @@ static int extract_current(Ctx* c, const float* xyzi, int n, bool host) {
 }
 
 // lmsf_tracker_prefetch(_dev): extraction of a coming sweep into a slot that is not waiting to be consumed.
-// Called as prefetch(k+1); step(k): slot A holds k (prefetched earlier), slot B = the finished sweep k-1 -> k+1 goes to B.
-static int prefetch(Ctx* c, const float* xyzi, int n, bool host) {
+// Called as prefetch(k+1) after submit(k): slot A feeds the solve in flight, k+1 goes to slot B.  The prefetched
+// sweep is identified by the ticket handed back here and by nothing else — a caller buffer recycled at the same
+// address can never be mistaken for it.
+static int prefetch(Ctx* c, const float* xyzi, int n, bool host, int64_t* ticket) {
+  if (!ticket) return LMSF_ERR_INVALID;
+  *ticket = 0;
   int si = c->slot_cur ^ 1;
   if (c->slot[si].filled) si = c->slot_cur;
   if (c->slot[si].filled) return LMSF_ERR_STATE;  // two sweeps already waiting for their tracker step
   if (c->pending.active && si == c->slot_cur) return LMSF_ERR_STATE;  // that slot feeds the solve in flight
   LM_TRY(extract_into_slot(c, si, xyzi, n, host));
   c->slot[si].filled = true;
-  c->slot[si].src = xyzi;
   c->slot[si].n = n;
   c->slot[si].seq = ++c->prefetch_seq;
-  c->slot[si].age = 0;
+  *ticket = c->slot[si].seq;
   return LMSF_OK;
 }
 
-// tracker entry: consume the prefetched sweep when it is the one being stepped, else extract now
-static int take_sweep(Ctx* c, const float* xyzi, int n, bool host) {
-  int hit = -1;
+// tracker entry by ticket: the prefetched sweep becomes the current one; *n_out = its point count
+static int take_ticket(Ctx* c, int64_t ticket, int* n_out) {
+  if (ticket <= 0) return LMSF_ERR_INVALID;
   for (int si = 0; si < 2; ++si) {
     const Ctx::FeatSlot& sl = c->slot[si];
-    if (sl.filled && sl.src == (const void*)xyzi && sl.n == n && (hit < 0 || sl.seq < c->slot[hit].seq)) hit = si;
+    if (sl.filled && sl.seq == ticket) {
+      *n_out = sl.n;
+      return adopt_slot(c, si);
+    }
   }
-  // a prefetched sweep is expected to be stepped within the next two tracker steps; older ones are dropped so that a
-  // recycled caller buffer can never match a stale slot
-  for (int si = 0; si < 2; ++si) {
-    Ctx::FeatSlot& sl = c->slot[si];
-    if (sl.filled && si != hit && ++sl.age >= 2) sl.filled = false;
-  }
-  if (hit >= 0) return adopt_slot(c, hit);
-  return extract_current(c, xyzi, n, host);
+  return LMSF_ERR_STATE;  // unknown, cancelled, displaced or already consumed
 }
+
+// tracker entry with a sweep: always extracted now (a waiting prefetch is only displaced when both slots hold one)
+static int take_sweep(Ctx* c, const float* xyzi, int n, bool host) { return extract_current(c, xyzi, n, host); }
 
 static void destroy(Ctx* c) {
   if (!c) return;
@@ -525,8 +539,6 @@ int lmsf_params_default(lmsf_params* p) {
   p->kf_rot = 0.1;
   p->kf_time = 10.0;
   p->max_map_points = 0;
-  p->oracle_knn_mode = 0;
-  p->oracle_threads = 1;
   return LMSF_OK;
 }
 
@@ -694,32 +706,18 @@ int lmsf_knn5(lmsf_ctx* c, int kind, const float* q_xyz, int nq, int32_t* idx5, 
   LM_TRY(wait_map(c));
   if (kind < 0 || kind > 1 || nq < 0 || (nq > 0 && (!q_xyz || !idx5 || !d2_5))) return LMSF_ERR_INVALID;
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
-  float* d_q = nullptr;
-  int* d_i = nullptr;
-  float* d_d = nullptr;
   if (nq == 0) return LMSF_OK;
-  LM_CUDA(cudaMalloc(&d_q, (size_t)nq * 12));
-  LM_CUDA(cudaMalloc(&d_i, (size_t)nq * 20));
-  LM_CUDA(cudaMalloc(&d_d, (size_t)nq * 20));
-  int rc = LMSF_OK;
-  do {
-    if (cudaMemcpyAsync(d_q, q_xyz, (size_t)nq * 12, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
-      rc = LMSF_ERR_CUDA;
-      break;
-    }
-    rc = knn_hook(c, kind, d_q, nq, d_i, d_d);
-    if (rc) break;
-    cudaMemcpyAsync(idx5, d_i, (size_t)nq * 20, cudaMemcpyDeviceToHost, c->stream);
-    cudaMemcpyAsync(d2_5, d_d, (size_t)nq * 20, cudaMemcpyDeviceToHost, c->stream);
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
-      c->last_error = cudaGetErrorString(cudaGetLastError());
-      rc = LMSF_ERR_CUDA;
-    }
-  } while (0);
-  cudaFree(d_q);
-  cudaFree(d_i);
-  cudaFree(d_d);
-  return rc;
+  char* buf = nullptr;
+  LM_TRY(hook_scratch(c, (size_t)nq * 52, (void**)&buf));
+  float* d_q = (float*)buf;
+  int* d_i = (int*)(buf + (size_t)nq * 12);
+  float* d_d = (float*)(buf + (size_t)nq * 32);
+  LM_CUDA(cudaMemcpyAsync(d_q, q_xyz, (size_t)nq * 12, cudaMemcpyHostToDevice, c->stream));
+  LM_TRY(knn_hook(c, kind, d_q, nq, d_i, d_d));
+  LM_CUDA(cudaMemcpyAsync(idx5, d_i, (size_t)nq * 20, cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaMemcpyAsync(d2_5, d_d, (size_t)nq * 20, cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  return LMSF_OK;
 }
 
 int lmsf_match(lmsf_ctx* c, int kind, const float* q_xyz, int nq, uint8_t* ok, double* out10) {
@@ -728,31 +726,17 @@ int lmsf_match(lmsf_ctx* c, int kind, const float* q_xyz, int nq, uint8_t* ok, d
   if (kind < 0 || kind > 1 || nq < 0 || (nq > 0 && (!q_xyz || !ok || !out10))) return LMSF_ERR_INVALID;
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
   if (nq == 0) return LMSF_OK;
-  float* d_q = nullptr;
-  uint8_t* d_ok = nullptr;
-  double* d_o = nullptr;
-  LM_CUDA(cudaMalloc(&d_q, (size_t)nq * 12));
-  LM_CUDA(cudaMalloc(&d_ok, (size_t)nq));
-  LM_CUDA(cudaMalloc(&d_o, (size_t)nq * 80));
-  int rc = LMSF_OK;
-  do {
-    if (cudaMemcpyAsync(d_q, q_xyz, (size_t)nq * 12, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
-      rc = LMSF_ERR_CUDA;
-      break;
-    }
-    rc = match_hook(c, kind, d_q, nq, d_ok, d_o);
-    if (rc) break;
-    cudaMemcpyAsync(ok, d_ok, (size_t)nq, cudaMemcpyDeviceToHost, c->stream);
-    cudaMemcpyAsync(out10, d_o, (size_t)nq * 80, cudaMemcpyDeviceToHost, c->stream);
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
-      c->last_error = cudaGetErrorString(cudaGetLastError());
-      rc = LMSF_ERR_CUDA;
-    }
-  } while (0);
-  cudaFree(d_q);
-  cudaFree(d_ok);
-  cudaFree(d_o);
-  return rc;
+  char* buf = nullptr;
+  LM_TRY(hook_scratch(c, (size_t)nq * 96 + 64, (void**)&buf));
+  double* d_o = (double*)buf;                       // 80 B per query, 8-byte aligned first
+  float* d_q = (float*)(buf + (size_t)nq * 80);
+  uint8_t* d_ok = (uint8_t*)(buf + (size_t)nq * 92);
+  LM_CUDA(cudaMemcpyAsync(d_q, q_xyz, (size_t)nq * 12, cudaMemcpyHostToDevice, c->stream));
+  LM_TRY(match_hook(c, kind, d_q, nq, d_ok, d_o));
+  LM_CUDA(cudaMemcpyAsync(ok, d_ok, (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaMemcpyAsync(out10, d_o, (size_t)nq * 80, cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  return LMSF_OK;
 }
 
 int lmsf_align_score(lmsf_ctx* c, int kind, const float* xyzi, int n, const float relpose16[16], double inlier_thresh,
@@ -769,17 +753,12 @@ int lmsf_align_score(lmsf_ctx* c, int kind, const float* xyzi, int n, const floa
     return LMSF_OK;
   }
   float4* d_pts = nullptr;
-  LM_CUDA(cudaMalloc(&d_pts, (size_t)n * sizeof(float4)));
-  int rc = LMSF_OK;
+  const size_t nblk = (size_t)(n + 127) / 128;
+  LM_TRY(hook_scratch(c, (size_t)n * sizeof(float4) + (nblk + 1) * (sizeof(double) + sizeof(int)) + 64, (void**)&d_pts));
   double sum = 0;
   int cnt = 0;
-  if (cudaMemcpyAsync(d_pts, xyzi, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
-    rc = LMSF_ERR_CUDA;
-  } else {
-    rc = align_hook(c, kind, d_pts, n, relpose16, (float)inlier_thresh, &sum, &cnt);
-  }
-  cudaFree(d_pts);
-  if (rc) return rc;
+  LM_CUDA(cudaMemcpyAsync(d_pts, xyzi, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  LM_TRY(align_hook(c, kind, d_pts, n, relpose16, (float)inlier_thresh, &sum, &cnt));
   const double ratio = (double)cnt / (double)n;  // :80
   *overlap = ratio;
   *score = (ratio > inlier_ratio_thresh) ? sum / cnt : 1.7976931348623157e308;  // :82-85
@@ -807,6 +786,7 @@ int lmsf_tracker_step(lmsf_ctx* c, const float* xyzi, int n, double stamp, doubl
                       lmsf_track_stats* st) {
   ENTER(c);
   if (!delta || !pose_out) return LMSF_ERR_INVALID;
+  if (c->pending.active) return LMSF_ERR_STATE;  // before any slot state is touched
   LM_TRY(take_sweep(c, xyzi, n, true));
   return tracker_core(c, n, stamp, delta, pose_out, st);
 }
@@ -815,8 +795,40 @@ int lmsf_tracker_step_dev(lmsf_ctx* c, const float* d_xyzi, int n, double stamp,
                           lmsf_track_stats* st) {
   ENTER(c);
   if (!delta || !pose_out || n < 0 || (n > 0 && !d_xyzi)) return LMSF_ERR_INVALID;
+  if (c->pending.active) return LMSF_ERR_STATE;
   LM_TRY(take_sweep(c, d_xyzi, n, false));
   return tracker_core(c, n, stamp, delta, pose_out, st);
+}
+
+int lmsf_tracker_step_ticket(lmsf_ctx* c, int64_t ticket, double stamp, double delta[7], double pose_out[7],
+                             lmsf_track_stats* st) {
+  ENTER(c);
+  if (!delta || !pose_out) return LMSF_ERR_INVALID;
+  if (c->pending.active) return LMSF_ERR_STATE;
+  int n = 0;
+  LM_TRY(take_ticket(c, ticket, &n));
+  return tracker_core(c, n, stamp, delta, pose_out, st);
+}
+
+int lmsf_tracker_submit_ticket(lmsf_ctx* c, int64_t ticket, double stamp, const double delta[7]) {
+  ENTER(c);
+  if (!delta) return LMSF_ERR_INVALID;
+  if (c->pending.active) return LMSF_ERR_STATE;
+  int n = 0;
+  LM_TRY(take_ticket(c, ticket, &n));
+  return tracker_begin(c, n, stamp, delta);
+}
+
+int lmsf_tracker_prefetch_cancel(lmsf_ctx* c, int64_t ticket) {
+  ENTER(c);
+  for (int si = 0; si < 2; ++si) {
+    Ctx::FeatSlot& sl = c->slot[si];
+    if (sl.filled && sl.seq == ticket) {
+      sl.filled = false;  // the extraction already enqueued runs to completion; its slot is simply reusable
+      return LMSF_OK;
+    }
+  }
+  return LMSF_ERR_STATE;
 }
 
 int lmsf_tracker_submit(lmsf_ctx* c, const float* xyzi, int n, double stamp, const double delta[7]) {
@@ -843,20 +855,21 @@ int lmsf_tracker_wait(lmsf_ctx* c, double delta_out[7], double pose_out[7], lmsf
   return tracker_end(c, delta_out, pose_out, st);
 }
 
-int lmsf_tracker_prefetch(lmsf_ctx* c, const float* xyzi, int n) {
+int lmsf_tracker_prefetch(lmsf_ctx* c, const float* xyzi, int n, int64_t* ticket) {
   ENTER(c);
-  return prefetch(c, xyzi, n, true);
+  return prefetch(c, xyzi, n, true, ticket);
 }
 
-int lmsf_tracker_prefetch_dev(lmsf_ctx* c, const float* d_xyzi, int n) {
+int lmsf_tracker_prefetch_dev(lmsf_ctx* c, const float* d_xyzi, int n, int64_t* ticket) {
   ENTER(c);
-  return prefetch(c, d_xyzi, n, false);
+  return prefetch(c, d_xyzi, n, false, ticket);
 }
 
 int lmsf_tracker_step_features(lmsf_ctx* c, const float* edge_xyzi, int n_e, const float* surf_xyzi, int n_s,
                                double stamp, double delta[7], double pose_out[7], lmsf_track_stats* st) {
   ENTER(c);
   if (!delta || !pose_out) return LMSF_ERR_INVALID;
+  if (c->pending.active) return LMSF_ERR_STATE;
   LM_TRY(upload_features(c, edge_xyzi, n_e, surf_xyzi, n_s));
   return tracker_core(c, n_e + n_s, stamp, delta, pose_out, st);
 }

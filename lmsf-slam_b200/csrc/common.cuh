@@ -191,6 +191,8 @@ struct Ctx {
 
   void* cub_tmp = nullptr;
   size_t cub_tmp_bytes = 0;
+  void* hook_buf = nullptr;    // grow-only scratch of the test / loop-closure hooks (lmsf_knn5, lmsf_match, lmsf_align_score)
+  size_t hook_bytes = 0;
 
   // local-map update pipeline: its own stream, ordered against the main stream with two events
   cudaStream_t stream_map = nullptr;
@@ -210,10 +212,8 @@ struct Ctx {
     cudaEvent_t freed = nullptr;    // map stream: the local-map update has consumed this slot
     bool freed_pending = false;     // nobody has waited for `freed` yet
     bool filled = false;            // holds a prefetched sweep that no step has consumed yet
-    const void* src = nullptr;      // the caller's pointer / count the prefetch was given
-    int n = 0;
-    int64_t seq = 0;                // order of the prefetches
-    int age = 0;                    // tracker steps that passed it over
+    int n = 0;                      // its point count
+    int64_t seq = 0;                // the ticket lmsf_tracker_prefetch* handed out for it (order of the prefetches)
   };
   FeatSlot slot[2];
   int slot_cur = 0;
@@ -311,6 +311,9 @@ void scdb_free(Ctx* c);
 // ---- implemented in match.cu
 int solve_alloc(Ctx* c);
 void solve_free(Ctx* c);
+// grow-only scratch arena of the hooks: `bytes` of device memory, valid until the next hook call (a regrow
+// synchronises the device, steady-state calls do not allocate)
+int hook_scratch(Ctx* c, size_t bytes, void** out);
 int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2);
 int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double* d_out10);
 int align_hook(Ctx* c, int kind, const float4* d_pts, int n, const float T12[12], float thresh, double* sum, int* cnt);

@@ -129,7 +129,7 @@ __device__ __forceinline__ const CellRec* find_cell(const MapView& mv, const Map
   if (key == cur.key) return cur.rec;
   unsigned h = hash_cell(key) & md.table_mask;
   const CellRec* r = nullptr;
-  while (true) {
+  for (unsigned probes = 0; probes <= md.table_mask; ++probes) {  // bounded: a full table must not hang the search
     unsigned long long k = mv.table[h].key;
     if (k == key) {
       r = &mv.table[h];

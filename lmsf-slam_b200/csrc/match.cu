@@ -1317,6 +1317,20 @@ void solve_free(Ctx* c) {
   cudaFree(c->d_nbr);
   cudaFree(c->d_partial);
   cudaFree(c->d_state);
+  cudaFree(c->hook_buf);
+}
+
+int hook_scratch(Ctx* c, size_t bytes, void** out) {
+  if (bytes > c->hook_bytes) {
+    size_t want = bytes + bytes / 4 + 4096;
+    if (c->hook_buf) LM_CUDA(cudaFree(c->hook_buf));
+    c->hook_buf = nullptr;
+    c->hook_bytes = 0;
+    LM_CUDA(cudaMalloc(&c->hook_buf, want));
+    c->hook_bytes = want;
+  }
+  *out = c->hook_buf;
+  return LMSF_OK;
 }
 
 int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2) {
@@ -1340,10 +1354,9 @@ int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double
 int align_hook(Ctx* c, int kind, const float4* d_pts, int n, const float T12[12], float thresh, double* sum, int* cnt) {
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
   const int nblk = div_up(n, 128);
-  double* d_part = nullptr;
-  int* d_cnt = nullptr;
-  LM_CUDA(cudaMalloc(&d_part, (size_t)(nblk + 1) * sizeof(double)));
-  LM_CUDA(cudaMalloc(&d_cnt, (size_t)(nblk + 1) * sizeof(int)));
+  // partial sums live behind the caller's points in the hook arena (d_pts is its first n float4)
+  double* d_part = (double*)(d_pts + n);
+  int* d_cnt = (int*)(d_part + nblk + 1);
   Rigid12f T;
   for (int i = 0; i < 12; ++i) T.m[i] = T12[i];
   LM_LAUNCH(c, k_align_score, nblk, 128, 0, view_of(c->map[kind]), d_pts, n, T, thresh, d_part, d_cnt);
@@ -1355,8 +1368,6 @@ int align_hook(Ctx* c, int kind, const float4* d_pts, int n, const float T12[12]
     c->last_error = cudaGetErrorString(cudaGetLastError());
     rc = LMSF_ERR_CUDA;
   }
-  cudaFree(d_part);
-  cudaFree(d_cnt);
   return rc;
 }
 

@@ -15,6 +15,32 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_device_count() -> int:
+    """CUDA devices visible to this process, asked of the driver library (present exactly where a GPU is)."""
+    import ctypes
+
+    try:
+        drv = ctypes.CDLL("libcuda.so.1")
+    except OSError:
+        return 0
+    n = ctypes.c_int(0)
+    if drv.cuInit(0) != 0 or drv.cuDeviceGetCount(ctypes.byref(n)) != 0:
+        return 0
+    return n.value
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a device: skipped (not errored) on a box without one."""
+    if not any("gpu" in it.keywords for it in items):
+        return
+    if _cuda_device_count() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device: gpu tests run on the B200 box")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 def _ensure_built():
     if not os.path.exists(entry.ORACLE_LIB) or not os.path.exists(pkg.LIB_PATH):
         entry.build()

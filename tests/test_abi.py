@@ -30,8 +30,11 @@ def test_oracle_mirrors_the_abi(gpu_lib, oracle_lib):
     for name in pkg.capi.Library.COMMON:
         assert oracle_lib.has(name), name
     a, b = gpu_lib.default_params(), oracle_lib.default_params()
-    assert C.sizeof(a) == 136
-    assert bytes(a) == bytes(b)
+    assert C.sizeof(a) == 136 and C.sizeof(b) == 136
+    common = type(a).reserved.offset        # the oracle names two of the public struct's reserved words (knn mode, threads)
+    assert bytes(a)[:common] == bytes(b)[:common]
+    assert not any(bytes(a)[common:]), "lmsf_params.reserved must default to zero"
+    assert not hasattr(a, "oracle_knn_mode") and not hasattr(a, "oracle_threads")   # test infrastructure stays out of the ABI
     assert (a.n_scans, a.min_range, a.max_range, a.edge_thresh, a.window) == (16, 2.0, 80.0, 1.0, 10)
     assert (a.gn_max_iters, a.lm_outer_start, a.lm_inner_iters) == (10, 10, 4)
     assert abs(a.huber_delta - 0.1) < 1e-7 and (a.kf_trans, a.kf_rot, a.kf_time) == (0.3, 0.1, 10.0)

@@ -29,6 +29,14 @@ def test_reference_arm_line_contract():
     assert "VLP-16" in d["metric"] and "workload" in d["config"]
 
 
+def test_reference_arm_tracks_one_sequence_per_gpu():
+    """--impl reference --gpus N tracks N sequences on the host cores (the N-GPU arm's workload), rank 0 only."""
+    d = _run("--impl", "reference", "--sensor", "vlp16", "--steps", "2", "--warmup", "3", "--gpus", "2")
+    assert d["n_gpus"] == 2 and d["config"]["sequences"] == 2
+    assert abs(d["ms_per_step"] * d["value"] - 2000.0) < 1e-6 * 2000.0
+    assert "2 tracker(s)" in d["cpu_baseline"]["sample"]
+
+
 def test_reference_arm_of_the_loop_search_is_declared_unavailable():
     d = _run("--impl", "reference", "--workload", "loopdb")
     assert d["impl"] == "reference" and "unavailable" in d

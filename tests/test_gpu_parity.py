@@ -25,7 +25,7 @@ def ctxs(gpu_lib, oracle_lib):
         okw = dict(kw)
         okw.setdefault("oracle_knn_mode", 0)
         okw.setdefault("oracle_threads", 8)
-        g = gpu_lib.context(0, **kw)
+        g = gpu_lib.context(0, **{k: v for k, v in kw.items() if not k.startswith("oracle_")})
         o = oracle_lib.context(0, **okw)
         made.extend([g, o])
         return g, o
@@ -36,7 +36,7 @@ def ctxs(gpu_lib, oracle_lib):
 
 
 # ---------------------------------------------------------------- a1 feature extraction
-@pytest.mark.parametrize("name,ns", [("vlp16", 16), ("hdl64", 64)])
+@pytest.mark.parametrize("name,ns", [("vlp16", 16), ("hdl64", 64), ("vlp16", 32), ("hdl64", 32)])   # 32: the :319 ring formula
 @pytest.mark.parametrize("k", [0, 7])
 def test_extract_labels_bit_exact(ctxs, sweeps, name, ns, k):
     g, o = ctxs(n_scans=ns)
@@ -385,23 +385,39 @@ def test_tracker_prefetch_pipeline_is_bit_identical(gpu_lib, sweeps, name, ns, n
     a = gpu_lib.context(0, n_scans=ns)
     b = gpu_lib.context(0, n_scans=ns)
     c = gpu_lib.context(0, n_scans=ns)
+    tb = tc = 0
     try:
         d_ptrs = [c.dev_upload_new(s) for s in seq]
         for k in range(nsweeps):
             pa, da, sa = a.tracker_step(seq[k], 0.1 * k)
-            # b: host sweeps, prefetch(k+1) before step(k) as bench.py does; at k == 3 the prefetched sweep is the
-            # wrong one (never stepped) and at k == 2 nothing is prefetched: step 3 / 4 fall back to extracting now
+            # b: host sweeps through tickets.  The sweep for step k + 1 is prefetched before step k runs; at k == 2
+            # nothing is prefetched and at k == 3 a wrong sweep is prefetched and cancelled, so steps 3 and 4 extract
+            # on the spot; a consumed or cancelled ticket is refused.
+            if k == 0:
+                tb = b.tracker_prefetch(seq[0])
+            pb, db, sb = b.tracker_step_ticket(tb, 0.1 * k) if tb else b.tracker_step(seq[k], 0.1 * k)
+            if tb:
+                with pytest.raises(Exception):
+                    b.tracker_step_ticket(tb, 0.1 * k)   # consumed
+            tb = 0
             if k == 3:
-                b.tracker_prefetch(seq[0])
+                wrong = b.tracker_prefetch(seq[0])
+                b.tracker_prefetch_cancel(wrong)
+                with pytest.raises(Exception):
+                    b.tracker_step_ticket(wrong, 0.0)     # cancelled
             elif k != 2:
-                b.tracker_prefetch(seq[k + 1])
-            pb, db, sb = b.tracker_step(seq[k], 0.1 * k)
+                tb = b.tracker_prefetch(seq[k + 1])
             # c: resident sweeps, the step in its two halves with the next sweep's prefetch in between
-            c.tracker_submit_dev(d_ptrs[k], len(seq[k]), 0.1 * k)
-            c.tracker_prefetch_dev(d_ptrs[k + 1], len(seq[k + 1]))
+            if k == 0:
+                c.tracker_submit_dev(d_ptrs[0], len(seq[0]), 0.0)
+            else:
+                c.tracker_submit_ticket(tc, 0.1 * k)
+            tc = c.tracker_prefetch_dev(d_ptrs[k + 1], len(seq[k + 1]))
             if k == 1:
-                with pytest.raises(Exception):      # one sweep in flight: a second submit is refused
+                with pytest.raises(Exception):      # one sweep in flight: a second submit / a step is refused
                     c.tracker_submit_dev(d_ptrs[k], len(seq[k]), 0.1 * k)
+                with pytest.raises(Exception):
+                    c.tracker_step_dev(d_ptrs[k], len(seq[k]), 0.1 * k)
             pc, dc, sc = c.tracker_wait()
             assert np.array_equal(pa, pb) and np.array_equal(da, db) and sa == sb, k
             assert np.array_equal(pa, pc) and np.array_equal(da, dc) and sa == sc, k
@@ -414,6 +430,65 @@ def test_tracker_prefetch_pipeline_is_bit_identical(gpu_lib, sweeps, name, ns, n
         a.close()
         b.close()
         c.close()
+
+
+def test_headline_hdl64_full_window_parity(gpu_lib, oracle_lib, synth):
+    """The bench's own configuration, on its own inputs: HDL-64 sequence 0 driven through lmsf_tracker_submit_ticket /
+    _prefetch / _wait (the calls bench.py times) until the 10-keyframe window is full (1.28 M map points) and the
+    Huber-LM budget sits at its floor, against the oracle tracker sweep by sweep (LidarTrackerLocalMap.hpp:107-160,
+    ceres_edgeSurfFeatureRegistration.hpp:96-130): every pose within 1e-4 m / 1e-5 rad, identical keyframe decisions,
+    feature and match counts and trust-region step counts, equal final maps; then lmsf_knn5 on that steady-state index
+    (the tracker's own frozen-grid build) against brute force."""
+    import os
+
+    n_sw = 44
+    sensor = synth.hdl64()
+    seq = [synth.make_sweep(sensor, k, seq=0) for k in range(n_sw + 1)]
+    g = gpu_lib.context(0, n_scans=64, max_points=1 << 18)
+    o = oracle_lib.context(0, n_scans=64, max_points=1 << 18, oracle_knn_mode=0, oracle_threads=os.cpu_count() or 1)
+    b = oracle_lib.context(0, n_scans=64, max_points=1 << 18, oracle_knn_mode=1, oracle_threads=os.cpu_count() or 1)
+    try:
+        ticket = g.tracker_prefetch(seq[0])
+        worst = [0.0, 0.0]
+        for k in range(n_sw):
+            g.tracker_submit_ticket(ticket, 0.1 * k)
+            ticket = g.tracker_prefetch(seq[k + 1])
+            pg, dg, sg = g.tracker_wait()
+            po, do, so = o.tracker_step(seq[k], 0.1 * k)
+            dt, dr = pose_err(pg, po)
+            worst = [max(worst[0], dt), max(worst[1], dr)]
+            assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (k, dt, dr)
+            dt, dr = pose_err(dg, do)
+            assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (k, "delta", dt, dr)
+            for key in ("n_edge", "n_surf", "keyframe", "map_edge", "map_surf", "first"):
+                assert sg[key] == so[key], (k, key, sg, so)
+            for key in ("outer_iters", "n_edge_matched", "n_surf_matched", "lm_steps_total", "lm_steps_accepted"):
+                assert sg["reg"][key] == so["reg"][key], (k, key, sg, so)
+        g.tracker_prefetch_cancel(ticket)
+        # the state the bench times: full window, budget at its floor
+        assert sg["map_surf"] > 1_100_000 and sg["reg"]["outer_iters"] == 2, sg
+        maps = []
+        for kind in (0, 1):
+            mg, mo = g.get_map(kind), o.get_map(kind)
+            assert mg.shape == mo.shape
+            assert np.allclose(mg, mo, rtol=0, atol=2e-4)
+            maps.append(mg)
+        # exact 5-NN on the steady-state index: world points of the next sweep's features at the last pose
+        _, e, f = g.extract_features(seq[n_sw])
+        T = synth.qt_to_mat(pg)
+        for kind, feat, step in ((0, e, 1), (1, f, 29)):
+            q = np.ascontiguousarray((feat[::step, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32))
+            ig, dg2 = g.knn5(kind, q)                   # the tracker's own index (frozen grid, incremental history)
+            b.map_set(kind, maps[kind])
+            ib, db = b.knn5(kind, q)                    # brute force over the same cloud
+            assert np.array_equal(ig, ib), kind
+            assert np.array_equal(bits(dg2), bits(db)), kind
+            assert (ib[:, 4] >= 0).mean() > 0.8
+        print(f"headline parity: worst pose error over {n_sw} sweeps {worst[0]:.2e} m {worst[1]:.2e} rad")
+    finally:
+        g.close()
+        o.close()
+        b.close()
 
 
 def test_round_trip_full_size(gpu_lib, synth):

@@ -11,11 +11,11 @@ pytestmark = pytest.mark.gpu
 
 def test_cuda_extract_vs_reference_code(gpu_lib, synth):
     """Rows a1.1-a1.4: lmsf_extract_features == LOAMFeatureProcessorBase::Process (LOAMFeatureProcessor_base.hpp:59-343),
-    edge and surf clouds bit for bit, order included: VLP-16, HDL-64, ragged / short / empty inputs, other thresholds.
-    (The 32-line ring formula is pinned on the CPU only: no 32-line case has run on a GPU yet — DESIGN.md section 8.)"""
+    edge and surf clouds bit for bit, order included: VLP-16, HDL-64, the 32-line ring formula (:319), ragged / short /
+    empty inputs, other thresholds."""
     ref = ref_pin.RefLoam()
     n_feat = ref_pin.check_extract_against_reference(lambda **kw: gpu_lib.context(0, **kw), synth, ref,
-                                                     include_32_line=False)
+                                                     include_32_line=True)
     assert n_feat > 800000
 
 
