@@ -753,7 +753,7 @@ int lmsf_align_score(lmsf_ctx* c, int kind, const float* xyzi, int n, const floa
     return LMSF_OK;
   }
   float4* d_pts = nullptr;
-  const size_t nblk = (size_t)(n + 127) / 128;
+  const size_t nblk = (size_t)(n + 15) / 16;  // k_align_score: one partial per block of 16 points
   LM_TRY(hook_scratch(c, (size_t)n * sizeof(float4) + (nblk + 1) * (sizeof(double) + sizeof(int)) + 64, (void**)&d_pts));
   double sum = 0;
   int cnt = 0;

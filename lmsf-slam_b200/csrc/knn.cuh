@@ -1,25 +1,36 @@
-// knn.cuh — device-side exact 5-NN over the local-map grid (three nested cell levels).
+// knn.cuh — exact 5-NN over the local-map grid, searched COOPERATIVELY by a group of lanes per query.
 //
 // Replaces pcl::KdTreeFLANN::nearestKSearch(point, 5, ...) as called by
 // EdgeFeatureMatch::Match (registration/FeatureMatch/EdgeFeatureMatch.hpp:38) and
 // SurfFeatureMatch::Match (surfFeatureMatch.hpp:37).  Both callers reject the
 // query unless the 5th squared distance is < search_thresh_ = 1.0
-// (FeatureMatchBase.hpp:29), so only neighbours with d2 < 1.0 are ever needed:
-// the 27 coarse (1 m) cells around the query hold all of them.
+// (FeatureMatchBase.hpp:29), so only neighbours with d2 < 1.0 are ever needed.
 //
-// Levels: L0 = 1 m cells in a hash table; every L0 cell has a 64-bit occupancy
+// Index (mapindex.cu): L0 = 1 m cells in a hash table; every L0 cell has a 64-bit occupancy
 // mask of its 4x4x4 L1 cells (0.25 m); every occupied L1 cell has a 64-bit mask
-// of its 4x4x4 L2 cells (0.0625 m).  Points are grouped by (L0, L1, L2) so each
-// cell at each level is one contiguous range.  Search:
-//   seed  (outer iterations after the first) the previous iteration's five neighbours give an
-//         upper bound of the 5th distance before anything is scanned,
-//   A     otherwise the 27 L2 cells around the query give it (dense regions end here: exact as
-//         soon as the 5th distance is < 0.0625^2),
-//   ball  with a bound < 0.25^2 the search restarts as a row sweep over exactly the L2 cells the
-//         ball of that radius touches, nearest rows first; insertions are rare because the bound
-//         is already tight,
-//   B, C  without one (sparse surroundings) the 27 L1 cells, then the 27 L0 cells, are swept
-//         cell by cell, skipping every cell whose box is farther than the current 5th distance.
+// of its 4x4x4 L2 cells (0.0625 m).  Points are grouped by (L0, L1, L2), x fastest, so an x-run of
+// L2 cells inside one L1 cell — and a whole L1 cell — is one contiguous range of `sorted`.
+//
+// Search (round 2; round 1 walked the grid with one thread per query: 5-6 of 32 lanes active, 19-31 % of the
+// issue slots in a per-thread sorted insert).  A query is owned by a GROUP of G = 8 lanes, four queries per warp:
+//   tasks       the cells of a box around the query are cut into tasks — (z,y) rows of L2 cells per L1 cell
+//               ("rows" mode, boxes up to 11 cells wide) or whole L1 cells ("cells" mode, larger boxes) — dealt
+//               round-robin to the lanes; a task ends in one contiguous segment [s, e) of `sorted` (three dependent
+//               loads: hash probe, L1 record, two L2 starts).  With a bound on the 5th distance, rows outside the
+//               ball are skipped and the x-run is clipped to the ball.  Non-empty segments are compacted into a
+//               per-group list in shared memory.
+//   candidates  the segments are flattened (prefix sums) and the group strides over the candidates with coalesced
+//               16-byte loads: every lane computes one distance per step, whatever the cell occupancy is.
+//   accept      a candidate whose key (distance bits, index) is <= the bound key is appended to the group's
+//               accepted list (ballot + popc: no sorted insert, no divergence); when the list fills up it is
+//               compressed to its five smallest keys and the bound tightens.
+//   select      the five smallest keys of the list, ascending: rank counting for lists of up to G keys, five rounds
+//               of group-min extraction otherwise.
+// A query runs through a small state machine: with seeds (the previous outer iteration's neighbours) one bounded
+// sweep is enough; without, the 27 L2 cells around the query give the bound (or the answer when the 5th distance
+// is below one cell), then one bounded sweep; sparse surroundings escalate to the 27 L1 cells and to everything
+// within 1 m.  All groups of a warp step through the machine in lockstep.
+//
 // Cell sizes are powers of two, so cell indices and cell bounds are exact in
 // fp32 and the box distance — computed with the same rounding sequence as a
 // point distance — never exceeds the distance of a point inside the box:
@@ -28,18 +39,26 @@
 // Distances are FLANN's L2_Simple: ((dx*dx)+dy*dy)+dz*dz in fp32.  Results are
 // ascending by (distance, original index): ties are resolved by index, which
 // FLANN resolves by traversal order ("identical except at exact ties").
+//
+// The search is written once, as templates over an executor X (lane id inside the group, ballot / shuffle /
+// any): WarpGroup8 on the device, HostGroup1 (one lane) in csrc/test_knn_model.cu, which runs the same source on the
+// CPU against brute force.
 #pragma once
+#include <string.h>
+
 #include "common.cuh"
 
 namespace lm {
 
-// the 27 neighbour offsets, nearest first (centre, 6 faces, 12 edges, 8 corners): the 5th-distance bound
-// tightens on the first cells and prunes most of the later ones
-__device__ static const signed char kNear27[27][3] = {
-    {0, 0, 0},   {-1, 0, 0},  {1, 0, 0},   {0, -1, 0},  {0, 1, 0},   {0, 0, -1},  {0, 0, 1},
-    {-1, -1, 0}, {1, -1, 0},  {-1, 1, 0},  {1, 1, 0},   {-1, 0, -1}, {1, 0, -1},  {-1, 0, 1},
-    {1, 0, 1},   {0, -1, -1}, {0, 1, -1},  {0, -1, 1},  {0, 1, 1},   {-1, -1, -1}, {1, -1, -1},
-    {-1, 1, -1}, {1, 1, -1},  {-1, -1, 1}, {1, -1, 1},  {-1, 1, 1},  {1, 1, 1}};
+#if defined(__CUDA_ARCH__)
+#define KG_POPC64(x) __popcll(x)
+#define KG_POPC32(x) __popc(x)
+#define KG_LD(p) __ldg(p)
+#else
+#define KG_POPC64(x) __builtin_popcountll(x)
+#define KG_POPC32(x) __builtin_popcount(x)
+#define KG_LD(p) (*(p))
+#endif
 
 struct MapView {
   const float4* sorted;             // cell-sorted points, .w = original index bits
@@ -49,46 +68,7 @@ struct MapView {
   const MapDev* dev;
 };
 
-struct Top5 {
-  float d[5];
-  int id[5];
-  __device__ __forceinline__ void reset() {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      d[k] = 1.0f;  // search_thresh_: only neighbours with d2 < 1.0 can enter
-      id[k] = -1;
-    }
-  }
-  // five points are known to exist with d2 <= bound: accept d2 <= bound, ties included
-  __device__ __forceinline__ void reset_inclusive(float bound) {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      d[k] = bound;
-      id[k] = 0x7fffffff;
-    }
-  }
-  __device__ __forceinline__ void add(float dd, int ii) {
-    if (dd < d[4] || (dd == d[4] && ii < id[4])) {
-      d[4] = dd;
-      id[4] = ii;
-#pragma unroll
-      for (int k = 4; k > 0; --k) {
-        bool sw = d[k] < d[k - 1] || (d[k] == d[k - 1] && id[k] < id[k - 1]);
-        if (sw) {
-          float td = d[k];
-          d[k] = d[k - 1];
-          d[k - 1] = td;
-          int ti = id[k];
-          id[k] = id[k - 1];
-          id[k - 1] = ti;
-        }
-      }
-    }
-  }
-  __device__ __forceinline__ bool full() const { return id[4] >= 0 && id[4] != 0x7fffffff; }
-};
-
-__device__ __forceinline__ unsigned hash_cell(unsigned long long k) {
+HD unsigned hash_cell(unsigned long long k) {
   k ^= k >> 33;
   k *= 0xff51afd7ed558ccdULL;
   k ^= k >> 33;
@@ -97,82 +77,33 @@ __device__ __forceinline__ unsigned hash_cell(unsigned long long k) {
   return (unsigned)k;
 }
 
-__device__ __forceinline__ unsigned long long pack_cell(const MapDev& md, int cx, int cy, int cz) {
+HD unsigned long long pack_cell(const MapDev& md, int cx, int cy, int cz) {
   return ((((unsigned long long)(unsigned)cz << md.bits[1]) | (unsigned long long)(unsigned)cy) << md.bits[0]) |
          (unsigned long long)(unsigned)cx;
 }
 
-struct KnnStats {  // debug counters (debug_stats.cu): per-query work and the pass the search ended in
-  int cand, boxes, lookups, level;
-};
-#ifdef LMSF_KNN_STATS
-#define KSTAT(x) x
-#define KS_DECL , KnnStats& ks
-#define KS_PASS , ks
-#else
-#define KSTAT(x)
-#define KS_DECL
-#define KS_PASS
-#endif
-
-// one-entry cache in front of the hash probe: neighbouring cells mostly share their L0 cell
-struct CellCursor {
-  unsigned long long key;
-  const CellRec* rec;
-};
-
-__device__ __forceinline__ const CellRec* find_cell(const MapView& mv, const MapDev& md, CellCursor& cur, int cx,
-                                                    int cy, int cz KS_DECL) {
-  KSTAT(ks.lookups++;)
+// L0 cell at coordinates relative to the grid origin; nullptr when outside the grid or unoccupied.  The probe
+// sequence is bounded: a completely full table must not hang the search.
+HD const CellRec* find_cell(const MapView& mv, const MapDev& md, int cx, int cy, int cz) {
   if (cx < 0 || cy < 0 || cz < 0 || cx >= md.dim[0] || cy >= md.dim[1] || cz >= md.dim[2]) return nullptr;
-  unsigned long long key = pack_cell(md, cx, cy, cz);
-  if (key == cur.key) return cur.rec;
+  const unsigned long long key = pack_cell(md, cx, cy, cz);
   unsigned h = hash_cell(key) & md.table_mask;
-  const CellRec* r = nullptr;
-  for (unsigned probes = 0; probes <= md.table_mask; ++probes) {  // bounded: a full table must not hang the search
-    unsigned long long k = mv.table[h].key;
-    if (k == key) {
-      r = &mv.table[h];
-      break;
-    }
-    if (k == ~0ull) break;
+  for (unsigned probes = 0; probes <= md.table_mask; ++probes) {
+    const unsigned long long k = KG_LD(&mv.table[h].key);
+    if (k == key) return &mv.table[h];
+    if (k == ~0ull) return nullptr;
     h = (h + 1) & md.table_mask;
   }
-  cur.key = key;
-  cur.rec = r;
-  return r;
+  return nullptr;
 }
 
-// `seeded`: the five slots were preloaded with real map points (the previous iteration's neighbours at their new
-// distances); those points are met again by the sweep and must not enter twice.  A candidate can only pass the
-// acceptance test of add() as a duplicate of slots 0..3 (slot 4 itself fails it), so four compares settle it.
-__device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz,
-                                           Top5& nb, bool seeded KS_DECL) {
-  KSTAT(ks.cand += e - s;)
-  if (s >= e) return;
-  float4 nxt = __ldg(&pts[s]);  // the next candidate is in flight while the current one is judged
-  for (int p = s; p < e; ++p) {
-    const float4 m = nxt;
-    if (p + 1 < e) nxt = __ldg(&pts[p + 1]);
-    float dx = m.x - qx, dy = m.y - qy, dz = m.z - qz;
-    float r = dx * dx;
-    r = r + dy * dy;
-    r = r + dz * dz;
-    const int ii = __float_as_int(m.w);
-    if (r < nb.d[4] || (r == nb.d[4] && ii < nb.id[4])) {
-      if (seeded && (ii == nb.id[0] || ii == nb.id[1] || ii == nb.id[2] || ii == nb.id[3])) continue;
-      nb.add(r, ii);
-    }
-  }
-}
-
-// squared distance from q to the axis-aligned cell [c*s, (c+1)*s)^3, same rounding sequence as scan_range
-__device__ __forceinline__ float axis_gap(float q, int c, float s) {
+// squared distance from q to the axis-aligned cell [c*s, (c+1)*s)^3, same rounding sequence as a point distance
+HD float axis_gap(float q, int c, float s) {
   float lo = (float)c * s;
   float hi = lo + s;
   return (q < lo) ? (lo - q) : ((q > hi) ? (q - hi) : 0.0f);
 }
-__device__ __forceinline__ float box_d2(float qx, float qy, float qz, int cx, int cy, int cz, float s) {
+HD float box_d2(float qx, float qy, float qz, int cx, int cy, int cz, float s) {
   float dx = axis_gap(qx, cx, s), dy = axis_gap(qy, cy, s), dz = axis_gap(qz, cz, s);
   float r = dx * dx;
   r = r + dy * dy;
@@ -181,8 +112,8 @@ __device__ __forceinline__ float box_d2(float qx, float qy, float qz, int cx, in
 }
 
 // one 16-byte load per visited L1 cell
-__device__ __forceinline__ L1Rec ldg_l1(const MapView& mv, int l1) {
-  const uint4 v = __ldg(reinterpret_cast<const uint4*>(mv.l1 + l1));
+HD L1Rec ld_l1(const MapView& mv, int l1) {
+  const uint4 v = KG_LD(reinterpret_cast<const uint4*>(mv.l1 + l1));
   L1Rec r;
   r.mask = ((unsigned long long)v.y << 32) | (unsigned long long)v.x;
   r.first = (int)v.z;
@@ -190,175 +121,489 @@ __device__ __forceinline__ L1Rec ldg_l1(const MapView& mv, int l1) {
   return r;
 }
 
-// scan the L2 cells of one L1 cell (absolute L1 coords ax1..az1) that survive the box test
-__device__ __forceinline__ void sweep_l1_cell(const MapView& mv, int l1, int ax1, int ay1, int az1, float qx, float qy,
-                                              float qz, Top5& nb, bool seeded KS_DECL) {
-  const L1Rec lr = ldg_l1(mv, l1);
-  unsigned long long m2 = lr.mask;
-  int base = lr.first;
+HD unsigned f2u(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  unsigned u;
+  memcpy(&u, &f, 4);
+  return u;
+#endif
+}
+HD float u2f(unsigned u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+// a / b for 0 <= a < 4096 and the reciprocal of 1 <= b <= 128 computed once: (a + 0.5) / b is at least 0.5 / b away
+// from an integer, far more than the rounding of the two float operations
+HD int div_small(int a, float inv_b) { return (int)(((float)a + 0.5f) * inv_b); }
+
+// (distance, index) as one ordered key: squared distances are >= +0, so their bit patterns order like the values
+HD unsigned long long kg_key(float d2, int id) { return ((unsigned long long)f2u(d2) << 32) | (unsigned)id; }
+HD float kg_key_d2(unsigned long long k) { return u2f((unsigned)(k >> 32)); }
+HD int kg_key_id(unsigned long long k) { return (int)(unsigned)(k & 0xffffffffull); }
+
+constexpr int KG_SEG_CAP = 64;   // segments a group collects before it scans them
+constexpr int KG_ACC_CAP = 64;   // accepted keys a group collects before it compresses them to five
+constexpr unsigned long long KG_KEY_LT_1 = (0x3f800000ull << 32) - 1ull;  // accepts exactly the keys with d2 < 1.0f
+
+struct KnnScratch {  // per group (shared memory on the device)
+  unsigned long long acc[KG_ACC_CAP];  // accepted keys; after a search: the result, ascending
+  int seg_s[KG_SEG_CAP];               // first point of every collected segment
+  int seg_pre[KG_SEG_CAP + 8];         // collected: lengths; flattened: [i] = offset of segment i, [nseg] = total
+};
+
+enum { KG_START = 0, KG_BALL = 1, KG_SPARSE1 = 2, KG_SPARSE2 = 3, KG_DONE = 4 };
+
+#ifdef LMSF_KNN_STATS  // tuning builds: work counters (global atomics), see kg_stat
+__device__ unsigned long long g_knn_stat[16];
+HD void kg_stat_add(int slot, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+  if (v) atomicAdd(&g_knn_stat[slot], v);
+#endif
+}
+#define KG_STAT(slot, v) kg_stat_add(slot, (unsigned long long)(v))
+#else
+#define KG_STAT(slot, v)
+#endif
+
+// ---- executors -------------------------------------------------------------------------------------------------
+// eight lanes per query, four queries per warp; every warp-wide primitive is executed by all 32 lanes
+struct WarpGroup8 {
+  static constexpr int G = 8;
+  int l;            // lane inside the group
+  unsigned gshift;  // bit position of the group inside a warp ballot
+#if defined(__CUDA_ARCH__)
+  HD WarpGroup8() {
+    const int lane = threadIdx.x & 31;
+    l = lane & 7;
+    gshift = lane & 24;
+  }
+  HD unsigned ballot(bool p) const { return (__ballot_sync(0xffffffffu, p) >> gshift) & 0xffu; }
+  HD bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }  // warp-wide: loop control
+  HD int shfl(int v, int src) const { return __shfl_sync(0xffffffffu, v, src, 8); }
+  HD int shfl_up(int v, int d) const { return __shfl_up_sync(0xffffffffu, v, d, 8); }
+  HD unsigned long long shfl_xor64(unsigned long long v, int d) const { return __shfl_xor_sync(0xffffffffu, v, d, 8); }
+  HD void sync() const { __syncwarp(); }
+#else  // host pass of nvcc: never executed
+  HD WarpGroup8() : l(0), gshift(0) {}
+  HD unsigned ballot(bool) const { return 0u; }
+  HD bool any(bool) const { return false; }
+  HD int shfl(int v, int) const { return v; }
+  HD int shfl_up(int v, int) const { return v; }
+  HD unsigned long long shfl_xor64(unsigned long long v, int) const { return v; }
+  HD void sync() const {}
+#endif
+};
+struct HostGroup1 {  // the same source with one lane per query (CPU model, csrc/test_knn_model.cu)
+  static constexpr int G = 1;
+  int l = 0;
+  HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
+  HD bool any(bool p) const { return p; }
+  HD int shfl(int v, int) const { return v; }
+  HD int shfl_up(int v, int) const { return v; }
+  HD unsigned long long shfl_xor64(unsigned long long v, int) const { return v; }
+  HD void sync() const {}
+};
+
+// ---- select: the five smallest keys of acc[0, n), ascending, to acc[0, min(n, 5)); n <- min(n, 5) ---------------------
+template <class X>
+HD void kg_select5(const X& x, KnnScratch* s, int& n) {
+  constexpr int G = X::G;
+  const bool small = n <= G;
+  // lists of up to G keys: one key per lane, rank = number of smaller keys (keys are unique: indices are)
+  unsigned long long mine = ~0ull;
   int rank = 0;
-  while (m2) {
-    int f2 = __ffsll((long long)m2) - 1;
-    m2 &= m2 - 1;
-    int ax2 = (ax1 << 2) | (f2 & 3), ay2 = (ay1 << 2) | ((f2 >> 2) & 3), az2 = (az1 << 2) | (f2 >> 4);
-    KSTAT(ks.boxes++;)
-    if (!(box_d2(qx, qy, qz, ax2, ay2, az2, 0.0625f) > nb.d[4])) {
-      int s = mv.l2_start[base + rank];
-      int e = mv.l2_start[base + rank + 1];
-      scan_range(mv.sorted, s, e, qx, qy, qz, nb, seeded KS_PASS);
-    }
-    ++rank;
-  }
-}
-
-// Row sweep at L2 resolution over the cells that intersect the ball of squared radius nb.d[4] (the
-// running 5th distance, which only shrinks) around q, limited to +-R cells.  Each (z,y) row is a run
-// of x cells that crosses at most R/2+2 L1 cells; inside one L1 cell a run is one contiguous range.
-__device__ __forceinline__ void sweep_ball(const MapView& mv, const MapDev& md, CellCursor& cur, float qx, float qy,
-                                           float qz, int ax, int ay, int az, int R, Top5& nb, bool seeded KS_DECL) {
-  const int ox = md.min_c[0], oy = md.min_c[1], oz = md.min_c[2];
-  for (int kz = 0; kz <= 2 * R; ++kz) {
-    int dz = (kz + 1) >> 1;  // 0, +1, -1, +2, -2 ...: nearest layers first so the bound shrinks early
-    if (!(kz & 1)) dz = -dz;
-    int z = az + dz;
-    float gz = axis_gap(qz, z, 0.0625f);
-    float gz2 = gz * gz;
-    if (gz2 > nb.d[4]) continue;
-    for (int ky = 0; ky <= 2 * R; ++ky) {
-      int dy = (ky + 1) >> 1;
-      if (!(ky & 1)) dy = -dy;
-      int y = ay + dy;
-      float gy = axis_gap(qy, y, 0.0625f);
-      float g2 = gy * gy + gz2;  // lower bound (same rounding order as a point distance's y,z terms added first)
-      KSTAT(ks.boxes++;)
-      if (g2 > nb.d[4]) continue;
-      // x extent of the ball in this row (slightly widened; a superset is always correct)
-      float rx = sqrtf(fmaxf(nb.d[4] - g2, 0.0f)) * 1.0001f + 1.0e-6f;
-      int x0 = max((int)floorf((qx - rx) * 16.0f), ax - R);
-      int x1 = min((int)floorf((qx + rx) * 16.0f), ax + R);
-      int row2 = ((z & 3) << 4) | ((y & 3) << 2);
-      int row1 = (((z >> 2) & 3) << 4) | (((y >> 2) & 3) << 2);
-      int la = x0 >> 2, lb = x1 >> 2;
-      for (int lx = la; lx <= lb; ++lx) {
-        const CellRec* rec = find_cell(mv, md, cur, (lx >> 2) - ox, (y >> 4) - oy, (z >> 4) - oz KS_PASS);
-        if (!rec) continue;
-        int f1 = row1 | (lx & 3);
-        unsigned long long m1 = rec->mask;
-        if (!((m1 >> f1) & 1ull)) continue;
-        int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
-        const L1Rec lr = ldg_l1(mv, l1);
-        unsigned long long m2 = lr.mask;
-        int lo = (lx == la) ? (x0 & 3) : 0;
-        int hi = (lx == lb) ? (x1 & 3) : 3;
-        int flo = row2 | lo, fhi = row2 | hi;
-        unsigned long long below = (1ull << flo) - 1ull;
-        unsigned long long sub = m2 & ((2ull << fhi) - 1ull) & ~below;
-        if (!sub) continue;
-        int b = lr.first + __popcll(m2 & below);
-        scan_range(mv.sorted, mv.l2_start[b], mv.l2_start[b + __popcll(sub)], qx, qy, qz, nb, seeded KS_PASS);
-      }
+  if (x.any(small && n > 0)) {
+    if (small && x.l < n) mine = s->acc[x.l];
+    for (int j = 0; x.any(small && j < n); ++j) {
+      if (small && j < n) rank += (s->acc[j] < mine) ? 1 : 0;
     }
   }
-}
-
-// exact 5-NN within squared radius 1.0; nb.id[k] = -1 for unfilled slots.
-// seed (optional): five map indices believed to be close to q (the previous outer iteration's
-// neighbours); they only provide the initial search radius, never the result.
-__device__ __forceinline__ void knn5(const MapView& mv, float qx, float qy, float qz, Top5& nb,
-                                     const float4* __restrict__ cat, const int* seed KS_DECL) {
-  nb.reset();
-  const MapDev md = *mv.dev;
-  if (md.n <= 0) return;
-  if (!(fabsf(qx) < 2.0e5f && fabsf(qy) < 2.0e5f && fabsf(qz) < 2.0e5f)) return;
-  // absolute L2 cell coordinates of the query (x16 is exact in fp32)
-  const int ax = (int)floorf(qx * 16.0f), ay = (int)floorf(qy * 16.0f), az = (int)floorf(qz * 16.0f);
-  const int ox = md.min_c[0], oy = md.min_c[1], oz = md.min_c[2];
-  CellCursor cur;
-  cur.key = ~0ull;
-  cur.rec = nullptr;
-  float bound = 2.0f;  // > 1: no usable bound yet
-  bool seeded = false;
-  if (seed != nullptr && seed[4] >= 0) {
-    // preload the five slots with the seeds at their distances from this query: five real points, so the running
-    // 5th distance is a valid inclusive bound from the start and the sweep only inserts what beats them
-    // (all lanes of a seeded launch do this in step: no divergence)
-    float sd[5];
+  // longer lists: five rounds of "smallest key above the last one taken"
+  unsigned long long res[5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      float4 m = __ldg(&cat[seed[k]]);
-      float dx = m.x - qx, dy = m.y - qy, dz = m.z - qz;
+  for (int r = 0; r < 5; ++r) res[r] = ~0ull;
+  if (x.any(!small)) {
+    unsigned long long last = 0ull;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      unsigned long long m = ~0ull;
+      for (int e0 = 0; x.any(!small && e0 < n); e0 += G) {
+        const int e = e0 + x.l;
+        if (!small && e < n) {
+          const unsigned long long k = s->acc[e];
+          if ((r == 0 || k > last) && k < m) m = k;
+        }
+      }
+#pragma unroll
+      for (int d = G >> 1; d > 0; d >>= 1) {
+        const unsigned long long o = x.shfl_xor64(m, d);
+        m = o < m ? o : m;
+      }
+      res[r] = m;
+      last = m;
+    }
+  }
+  x.sync();  // every lane has read what it needs of acc[]
+  if (small) {
+    if (x.l < n && rank < 5) s->acc[rank] = mine;
+  } else if (x.l == 0) {
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+      if (r < n) s->acc[r] = res[r];
+  }
+  x.sync();
+  if (n > 5) n = 5;
+}
+
+// ---- sweep ---------------------------------------------------------------------------------------------------------
+// Per-group search state (every lane of a group holds the same values).
+struct KgState {
+  float qx, qy, qz;
+  int lo[3], hi[3];              // box of absolute L2 cells to visit (inclusive)
+  bool active;                   // this group takes part in the sweep
+  bool rows;                     // tasks are (z,y) rows of L2 cells (else whole L1 cells)
+  bool ball;                     // bound_d is valid: skip cells farther than it
+  float bound_d;                 // squared radius for pruning (the distance part of bound_key, or 1.0)
+  unsigned long long bound_key;  // accept keys <= bound_key
+  int nacc;                      // keys in acc[]
+};
+
+// scan the collected segments of every group: flatten, stride over the candidates, accept, compress when full
+template <class X>
+HD void kg_scan_segments(const X& x, const MapView& mv, KnnScratch* s, KgState& st, int& nseg) {
+  constexpr int G = X::G;
+  // exclusive prefix of the segment lengths, in place
+  int run = 0;
+  for (int i0 = 0; x.any(i0 < nseg); i0 += G) {
+    const int i = i0 + x.l;
+    const int len = (i < nseg) ? s->seg_pre[i] : 0;
+    int inc = len;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+      const int t = x.shfl_up(inc, d);
+      if (x.l >= d) inc += t;
+    }
+    if (i < nseg) s->seg_pre[i] = run + inc - len;
+    run += x.shfl(inc, G - 1);
+  }
+  if (x.l == 0) s->seg_pre[nseg] = run;
+  x.sync();
+  const int total = run;
+  KG_STAT(2, (x.l == 0) ? total : 0);
+  int j = 0;
+  for (int c0 = 0; x.any(c0 < total); c0 += G) {
+    const int c = c0 + x.l;
+    bool pass = false;
+    unsigned long long key = 0ull;
+    if (c < total) {
+      while (c >= s->seg_pre[j + 1]) ++j;
+      const float4 m = KG_LD(&mv.sorted[s->seg_s[j] + (c - s->seg_pre[j])]);
+      const float dx = m.x - st.qx, dy = m.y - st.qy, dz = m.z - st.qz;
       float r = dx * dx;
       r = r + dy * dy;
       r = r + dz * dz;
-      sd[k] = r;
+      key = kg_key(r, (int)f2u(m.w));
+      pass = key <= st.bound_key;
     }
-    nb.reset_inclusive(__int_as_float(0x7f800000));
+    const unsigned gb = x.ballot(pass);
+    if (pass) s->acc[st.nacc + KG_POPC32(gb & ((1u << x.l) - 1u))] = key;
+    st.nacc += KG_POPC32(gb);
+    if (x.any(st.nacc > KG_ACC_CAP - G)) {
+      // a list about to overflow is cut to its five smallest keys; their largest is the new bound
+      x.sync();
+      const bool cut = st.nacc > KG_ACC_CAP - G;
+      int n = cut ? st.nacc : 0;
+      kg_select5(x, s, n);
+      if (cut) {
+        st.nacc = n;
+        st.bound_key = s->acc[4];
+        st.bound_d = kg_key_d2(st.bound_key);
+        st.ball = true;
+      }
+      KG_STAT(5, (x.l == 0 && cut) ? 1 : 0);
+    }
+  }
+  x.sync();
+  nseg = 0;
+}
+
+// one sweep over the box of every active group
+template <class X>
+HD void kg_sweep(const X& x, const MapView& mv, const MapDev& md, KnnScratch* s, KgState& st) {
+  constexpr int G = X::G;
+  // L0 cells the box touches (at most 3 per axis)
+  int c0[3], n0[3];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) nb.add(sd[k], seed[k]);
-    bound = nb.d[4];
-    seeded = bound < 1.0f;  // a seed beyond the search radius cannot be a result: fall back to the unseeded search
-    if (!seeded) nb.reset();
+  for (int a = 0; a < 3; ++a) {
+    c0[a] = st.lo[a] >> 4;
+    n0[a] = (st.hi[a] >> 4) - c0[a] + 1;
   }
-  if (!(bound < 1.0f)) {
-    // ---- A: the 27 L2 cells around the query, no prior bound
-    sweep_ball(mv, md, cur, qx, qy, qz, ax, ay, az, 1, nb, false KS_PASS);
-    KSTAT(ks.level = 1;)
-    if (nb.full()) {
-      if (nb.d[4] < 0.00390625f) return;  // 5th distance < one L2 cell: nothing outside the 27 cells can be closer
-      bound = nb.d[4];
+  const int n0_all = st.active ? n0[0] * n0[1] * n0[2] : 0;
+  const float inv_n0xy = 1.0f / (float)(n0[0] * n0[1] > 0 ? n0[0] * n0[1] : 1);
+  const float inv_n0x = 1.0f / (float)(n0[0] > 0 ? n0[0] : 1);
+  int nseg = 0;
+  int i0 = -1;             // current L0 cell of the box
+  int ntasks = 0, t0 = 0;  // tasks of the current L0 cell, next task round
+  // state of the current L0 cell
+  unsigned long long m1 = 0ull;
+  int fine_base = 0;
+  int slo[3] = {0, 0, 0}, shi[3] = {0, 0, 0};
+  int na = 1, nb = 1;                // rows: L1 parts per row, rows per layer; cells: L1 cells per row, per layer
+  float inv_na = 1.0f, inv_nb = 1.0f, inv_nab = 1.0f;
+  bool tasks_done = false;
+  while (true) {
+    if (!tasks_done) {
+      if (!x.any(t0 < ntasks)) {
+        // every group has dealt out the tasks of its current L0 cell: on to the next one
+        ++i0;
+        if (!x.any(i0 < n0_all)) {
+          tasks_done = true;
+        } else {
+          ntasks = 0;
+          t0 = 0;
+          if (i0 < n0_all) {
+            const int iz = div_small(i0, inv_n0xy);
+            const int rem = i0 - iz * (n0[0] * n0[1]);
+            const int iy = div_small(rem, inv_n0x);
+            const int cx = c0[0] + (rem - iy * n0[0]), cy = c0[1] + iy, cz = c0[2] + iz;
+            bool ok = true;
+            if (st.ball) ok = !(box_d2(st.qx, st.qy, st.qz, cx, cy, cz, 1.0f) > st.bound_d);
+            const CellRec* rec = ok ? find_cell(mv, md, cx - md.min_c[0], cy - md.min_c[1], cz - md.min_c[2]) : nullptr;
+            KG_STAT(0, (x.l == 0) ? 1 : 0);
+            if (rec) {
+              m1 = KG_LD(&rec->mask);
+              fine_base = KG_LD(&rec->fine_base);
+              const int cc[3] = {cx, cy, cz};
+#pragma unroll
+              for (int a = 0; a < 3; ++a) {
+                slo[a] = st.lo[a] > (cc[a] << 4) ? st.lo[a] : (cc[a] << 4);
+                shi[a] = st.hi[a] < (cc[a] << 4) + 15 ? st.hi[a] : (cc[a] << 4) + 15;
+              }
+              if (st.rows) {
+                na = (shi[0] >> 2) - (slo[0] >> 2) + 1;  // L1 cells the x-run crosses
+                nb = shi[1] - slo[1] + 1;                // rows per z layer
+                ntasks = na * nb * (shi[2] - slo[2] + 1);
+              } else {
+                na = (shi[0] >> 2) - (slo[0] >> 2) + 1;
+                nb = (shi[1] >> 2) - (slo[1] >> 2) + 1;
+                ntasks = na * nb * ((shi[2] >> 2) - (slo[2] >> 2) + 1);
+              }
+              inv_na = 1.0f / (float)na;
+              inv_nb = 1.0f / (float)nb;
+              inv_nab = 1.0f / (float)(na * nb);
+            }
+          }
+        }
+      } else {
+        // one round of tasks: lane l takes task t0 + l of its group
+        const int t = t0 + x.l;
+        t0 += G;
+        int seg_s = 0, seg_n = 0;
+        if (t < ntasks) {
+          KG_STAT(1, 1);
+          if (st.rows) {
+            const int r = div_small(t, inv_na), p = t - r * na;
+            const int zz = div_small(r, inv_nb);
+            const int y = slo[1] + (r - zz * nb), z = slo[2] + zz;
+            int xa = slo[0], xb = shi[0];
+            bool ok = true;
+            if (st.ball) {
+              const float gz = axis_gap(st.qz, z, 0.0625f), gy = axis_gap(st.qy, y, 0.0625f);
+              const float g2 = gy * gy + gz * gz;  // lower bound: the y and z terms of a point distance
+              ok = !(g2 > st.bound_d);
+              if (ok) {
+                // x extent of the ball in this row (slightly widened; a superset is always correct)
+                const float rem = st.bound_d - g2;
+                const float rx = sqrtf(rem > 0.0f ? rem : 0.0f) * 1.0001f + 1.0e-6f;
+                const int bx0 = (int)floorf((st.qx - rx) * 16.0f), bx1 = (int)floorf((st.qx + rx) * 16.0f);
+                xa = bx0 > xa ? bx0 : xa;
+                xb = bx1 < xb ? bx1 : xb;
+              }
+            }
+            const int lx = (slo[0] >> 2) + p;  // absolute L1 x of this part of the row
+            const int xlo = xa > (lx << 2) ? xa : (lx << 2);
+            const int xhi = xb < (lx << 2) + 3 ? xb : (lx << 2) + 3;
+            ok = ok && xlo <= xhi;
+            const int f1 = (((z >> 2) & 3) << 4) | (((y >> 2) & 3) << 2) | (lx & 3);
+            ok = ok && ((m1 >> f1) & 1ull);
+            if (ok) {
+              const L1Rec lr = ld_l1(mv, fine_base + KG_POPC64(m1 & ((1ull << f1) - 1ull)));
+              const int row2 = ((z & 3) << 4) | ((y & 3) << 2);
+              const int flo = row2 | (xlo & 3), fhi = row2 | (xhi & 3);
+              const unsigned long long below = (1ull << flo) - 1ull;
+              const unsigned long long sub = lr.mask & ((2ull << fhi) - 1ull) & ~below;
+              if (sub) {
+                const int b = lr.first + KG_POPC64(lr.mask & below);
+                seg_s = KG_LD(&mv.l2_start[b]);
+                seg_n = KG_LD(&mv.l2_start[b + KG_POPC64(sub)]) - seg_s;
+              }
+            }
+          } else {
+            const int iz = div_small(t, inv_nab);
+            const int rem = t - iz * (na * nb);
+            const int iy = div_small(rem, inv_na);
+            const int lx = (slo[0] >> 2) + (rem - iy * na), ly = (slo[1] >> 2) + iy, lz = (slo[2] >> 2) + iz;
+            const int f1 = ((lz & 3) << 4) | ((ly & 3) << 2) | (lx & 3);
+            bool ok = (m1 >> f1) & 1ull;
+            if (ok && st.ball) ok = !(box_d2(st.qx, st.qy, st.qz, lx, ly, lz, 0.25f) > st.bound_d);
+            if (ok) {
+              const L1Rec lr = ld_l1(mv, fine_base + KG_POPC64(m1 & ((1ull << f1) - 1ull)));
+              seg_s = KG_LD(&mv.l2_start[lr.first]);
+              seg_n = KG_LD(&mv.l2_start[lr.first + KG_POPC64(lr.mask)]) - seg_s;
+            }
+          }
+        }
+        const bool has = seg_n > 0;
+        const unsigned gb = x.ballot(has);
+        if (has) {
+          const int at = nseg + KG_POPC32(gb & ((1u << x.l) - 1u));
+          s->seg_s[at] = seg_s;
+          s->seg_pre[at] = seg_n;
+        }
+        nseg += KG_POPC32(gb);
+      }
     }
-  }
-  if (bound < 0.0625f) {
-    // ---- ball of known radius < 0.25 m: five points are known to lie within `bound` (inclusive)
-    KSTAT(ks.level = 2;)
-    if (!seeded) nb.reset_inclusive(bound);
-    int R = (int)ceilf(sqrtf(bound) * 16.0f * 1.0001f) + 1;
-    sweep_ball(mv, md, cur, qx, qy, qz, ax, ay, az, R > 5 ? 5 : R, nb, seeded KS_PASS);
-    return;
-  }
-  // ---- sparse neighbourhood: restart, 27 L1 cells (B) then 27 L0 cells (C) with box pruning
-  KSTAT(ks.level = 3;)
-  if (!seeded) {
-    if (bound < 1.0f)
-      nb.reset_inclusive(bound);
-    else
-      nb.reset();
-  }
-  const int bx = ax >> 2, by = ay >> 2, bz = az >> 2;
-  for (int k = 0; k < 27; ++k) {
-    int x = bx + kNear27[k][0], y = by + kNear27[k][1], z = bz + kNear27[k][2];
-    KSTAT(ks.boxes++;)
-    if (box_d2(qx, qy, qz, x, y, z, 0.25f) > nb.d[4]) continue;
-    const CellRec* rec = find_cell(mv, md, cur, (x >> 2) - ox, (y >> 2) - oy, (z >> 2) - oz KS_PASS);
-    if (!rec) continue;
-    int f1 = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
-    unsigned long long m1 = rec->mask;
-    if (!((m1 >> f1) & 1ull)) continue;
-    int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
-    sweep_l1_cell(mv, l1, x, y, z, qx, qy, qz, nb, seeded KS_PASS);
-  }
-  if (nb.full() && nb.d[4] < 0.0625f) return;
-  KSTAT(ks.level = 4;)
-  const int cx0 = bx >> 2, cy0 = by >> 2, cz0 = bz >> 2;
-  for (int k = 0; k < 27; ++k) {
-    int x = cx0 + kNear27[k][0], y = cy0 + kNear27[k][1], z = cz0 + kNear27[k][2];
-    KSTAT(ks.boxes++;)
-    if (box_d2(qx, qy, qz, x, y, z, 1.0f) > nb.d[4]) continue;
-    const CellRec* rec = find_cell(mv, md, cur, x - ox, y - oy, z - oz KS_PASS);
-    if (!rec) continue;
-    unsigned long long m1 = rec->mask;
-    int l1 = rec->fine_base;
-    while (m1) {
-      int f1 = __ffsll((long long)m1) - 1;
-      m1 &= m1 - 1;
-      int x1 = (x << 2) | (f1 & 3), y1 = (y << 2) | ((f1 >> 2) & 3), z1 = (z << 2) | (f1 >> 4);
-      bool seen = (x1 >= bx - 1 && x1 <= bx + 1 && y1 >= by - 1 && y1 <= by + 1 && z1 >= bz - 1 && z1 <= bz + 1);
-      KSTAT(ks.boxes++;)
-      if (!seen && !(box_d2(qx, qy, qz, x1, y1, z1, 0.25f) > nb.d[4]))
-        sweep_l1_cell(mv, l1, x1, y1, z1, qx, qy, qz, nb, seeded KS_PASS);
-      ++l1;
+    if (tasks_done || x.any(nseg > KG_SEG_CAP - G)) {
+      x.sync();
+      kg_scan_segments(x, mv, s, st, nseg);
+      if (tasks_done) break;
     }
   }
 }
+
+// ---- the search ----------------------------------------------------------------------------------------------------
+// Exact 5-NN within squared radius 1.0 of one query per group.  seed_key = 0: no prior knowledge; otherwise an
+// inclusive upper bound of the 5th key (five map points are known to have keys <= seed_key).  On return acc[0, n)
+// holds the n <= 5 nearest keys, ascending; n < 5: fewer than five points within the radius (callers reject).
+template <class X>
+HD int kg_knn5(const X& x, const MapView& mv, KnnScratch* s, float qx, float qy, float qz, bool active,
+               unsigned long long seed_key) {
+  const MapDev md = *mv.dev;
+  KgState st;
+  st.qx = qx;
+  st.qy = qy;
+  st.qz = qz;
+  st.nacc = 0;
+  if (!(md.n > 0) || !(fabsf(qx) < 2.0e5f && fabsf(qy) < 2.0e5f && fabsf(qz) < 2.0e5f)) active = false;
+  // absolute L2 cell coordinates of the query (x16 is exact in fp32)
+  const int a[3] = {active ? (int)floorf(qx * 16.0f) : 0, active ? (int)floorf(qy * 16.0f) : 0,
+                    active ? (int)floorf(qz * 16.0f) : 0};
+  const float q[3] = {qx, qy, qz};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) st.lo[k] = st.hi[k] = 0;
+  int state = active ? KG_START : KG_DONE;
+  st.bound_key = KG_KEY_LT_1;
+  st.bound_d = 1.0f;
+  if (active && seed_key != 0ull && seed_key <= KG_KEY_LT_1) {  // a seed beyond the search radius is no bound
+    state = KG_BALL;
+    st.bound_key = seed_key;
+    st.bound_d = kg_key_d2(seed_key);
+  }
+  int n_res = 0;
+  while (x.any(state != KG_DONE)) {
+    st.active = state != KG_DONE;
+    st.nacc = 0;
+    if (state == KG_START) {
+      // the 27 L2 cells around the query, no prior bound
+      st.rows = true;
+      st.ball = false;
+      st.bound_key = KG_KEY_LT_1;
+      st.bound_d = 1.0f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        st.lo[k] = a[k] - 1;
+        st.hi[k] = a[k] + 1;
+      }
+    } else if (state == KG_BALL) {
+      // five points are known within bound_key (inclusive): the cells the ball touches, rows while it is small
+      st.ball = true;
+      const float rad = sqrtf(st.bound_d) * 1.0001f + 1.0e-6f;
+      int w = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        st.lo[k] = (int)floorf((q[k] - rad) * 16.0f);
+        st.hi[k] = (int)floorf((q[k] + rad) * 16.0f);
+        w = st.hi[k] - st.lo[k] > w ? st.hi[k] - st.lo[k] : w;
+      }
+      st.rows = w <= 10;
+    } else if (state == KG_SPARSE1) {
+      // fewer than five points in the 27 L2 cells: the 27 L1 cells, whole cells
+      st.rows = false;
+      st.ball = false;
+      st.bound_key = KG_KEY_LT_1;
+      st.bound_d = 1.0f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        st.lo[k] = ((a[k] >> 2) - 1) << 2;
+        st.hi[k] = (((a[k] >> 2) + 1) << 2) + 3;
+      }
+    } else if (state == KG_SPARSE2) {
+      // everything within the search radius
+      st.rows = false;
+      st.ball = true;
+      st.bound_key = KG_KEY_LT_1;
+      st.bound_d = 1.0f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        st.lo[k] = (int)floorf((q[k] - 1.0f) * 16.0f);
+        st.hi[k] = (int)floorf((q[k] + 1.0f) * 16.0f);
+      }
+    }
+    KG_STAT(8 + (state < 4 ? state : 0), (x.l == 0 && state != KG_DONE) ? 1 : 0);
+    kg_sweep(x, mv, md, s, st);
+    int n = st.active ? st.nacc : 0;
+    kg_select5(x, s, n);
+    if (st.active) {
+      const bool full = n == 5;
+      const unsigned long long k5 = full ? s->acc[4] : 0ull;
+      const float d5 = kg_key_d2(k5);
+      n_res = n;
+      if (state == KG_START) {
+        if (!full) {
+          state = KG_SPARSE1;
+        } else if (d5 < 0.00390625f) {
+          state = KG_DONE;  // 5th distance < one L2 cell: nothing outside the 27 cells can be closer
+        } else {
+          state = KG_BALL;
+          st.bound_key = k5;
+          st.bound_d = d5;
+        }
+      } else if (state == KG_SPARSE1) {
+        if (!full) {
+          state = KG_SPARSE2;
+        } else if (d5 < 0.0625f) {
+          state = KG_DONE;  // 5th distance < one L1 cell: the 27 L1 cells hold every closer point
+        } else {
+          state = KG_BALL;
+          st.bound_key = k5;
+          st.bound_d = d5;
+        }
+      } else {
+        state = KG_DONE;  // KG_BALL and KG_SPARSE2 are exhaustive
+      }
+    }
+    x.sync();
+  }
+  return n_res;
+}
+
+// five neighbours of one query as the fits read them (match.cu): ascending by (distance, index)
+struct Top5 {
+  float d[5];
+  int id[5];
+  HD bool full() const { return id[4] >= 0; }
+};
+
+// kernels that search: blocks of KG_BLOCK threads = KG_QPB queries in flight, one KnnScratch per group
+constexpr int KG_BLOCK = 128;
+constexpr int KG_QPB = KG_BLOCK / WarpGroup8::G;
 
 }  // namespace lm

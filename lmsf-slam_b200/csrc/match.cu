@@ -825,17 +825,14 @@ __device__ __forceinline__ int own_cell_population(const MapView& mv, float x, f
   const MapDev md = *mv.dev;
   if (md.n <= 0 || !(fabsf(x) < 2.0e5f && fabsf(y) < 2.0e5f && fabsf(z) < 2.0e5f)) return 0;
   int ax = (int)floorf(x * 16.0f), ay = (int)floorf(y * 16.0f), az = (int)floorf(z * 16.0f);
-  CellCursor cur;
-  cur.key = ~0ull;
-  cur.rec = nullptr;
-  const CellRec* rec = find_cell(mv, md, cur, (ax >> 4) - md.min_c[0], (ay >> 4) - md.min_c[1], (az >> 4) - md.min_c[2]);
+  const CellRec* rec = find_cell(mv, md, (ax >> 4) - md.min_c[0], (ay >> 4) - md.min_c[1], (az >> 4) - md.min_c[2]);
   if (!rec) return 0;
   int f1 = (((az >> 2) & 3) << 4) | (((ay >> 2) & 3) << 2) | ((ax >> 2) & 3);
   unsigned long long m1 = rec->mask;
   if (!((m1 >> f1) & 1ull)) return 0;
   int l1 = rec->fine_base + __popcll(m1 & ((1ull << f1) - 1ull));
   int f2 = ((az & 3) << 4) | ((ay & 3) << 2) | (ax & 3);
-  const L1Rec lr = ldg_l1(mv, l1);
+  const L1Rec lr = ld_l1(mv, l1);
   unsigned long long m2 = lr.mask;
   if (!((m2 >> f2) & 1ull)) return 0;
   int b = lr.first + __popcll(m2 & ((1ull << f2) - 1ull));
@@ -893,77 +890,96 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
   }
 }
 
-// exact 5-NN of every query, in cell-sorted query order (t = sorted position).  Persistent warps pull
-// chunks of 32 consecutive sorted queries from a device-side counter: queries of sparse regions cost several
-// times more than queries of dense ones and sort next to each other, so a static block->query map leaves a
-// long tail of heavy blocks.
+// one query per group of eight lanes, called by all 32 lanes of a warp: seed bound from the previous iteration's
+// neighbours (seeded launches), the search, the five indices to nbr[k * upper + t] (-1 x 5 unless five neighbours lie
+// within the search radius: both callers reject such a query)
+__device__ __forceinline__ void knn_one(const WarpGroup8& x, KnnScratch* s, const MapPair& maps, bool is_edge,
+                                        bool has_map, bool active, float wx, float wy, float wz, int seeded, int upper,
+                                        int t, int* __restrict__ nbr) {
+  unsigned long long seed_key = 0ull;
+  if (seeded) {
+    const float4* __restrict__ cat = is_edge ? maps.edge_cat : maps.surf_cat;
+    const int sid = (active && has_map && x.l < 5) ? nbr[x.l * upper + t] : -1;
+    unsigned long long k = 0ull;
+    if (sid >= 0) {
+      const float4 m = __ldg(&cat[sid]);
+      const float dx = m.x - wx, dy = m.y - wy, dz = m.z - wz;
+      float r = dx * dx;
+      r = r + dy * dy;
+      r = r + dz * dz;
+      k = kg_key(r, sid);
+    }
+    const unsigned okb = x.ballot(sid >= 0);
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1) {
+      const unsigned long long o = x.shfl_xor64(k, d);
+      k = o > k ? o : k;
+    }
+    if ((okb & 31u) == 31u) seed_key = k;
+  }
+  const int n = kg_knn5(x, is_edge ? maps.edge : maps.surf, s, wx, wy, wz, active && has_map, seed_key);
+  if (active && x.l < 5) nbr[x.l * upper + t] = (n == 5) ? kg_key_id(s->acc[x.l]) : -1;
+  x.sync();  // acc[] is read before the next search writes it
+}
+
+// exact 5-NN of every query, in processing order (t = position).  A query is searched by a group of eight lanes
+// (knn.cuh), four queries per warp.  Persistent warps pull chunks of consecutive positions from a device-side counter:
+// queries of sparse regions cost several times more than queries of dense ones and lie next to each other, so a
+// static block->query map leaves a long tail of heavy blocks.
 #ifndef KNN_MINBLOCKS
-#define KNN_MINBLOCKS 1
+#define KNN_MINBLOCKS 4
 #endif
 // assoc != 0 (ring-order launches): the kernel also does k_assoc's work for its own query — pointAssociateToMap in
 // fp64, stored as fp32 in pw[] for k_fit — so no separate launch is needed.
-__global__ void __launch_bounds__(128, KNN_MINBLOCKS) k_knn(const int* __restrict__ perm, float4* __restrict__ pw,
+// seeded != 0 (outer iterations after the first): nbr[] holds the previous iteration's neighbours of the same position;
+// the largest of their keys at the query's new place bounds the 5th key from the start.
+__global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __restrict__ perm, float4* __restrict__ pw,
                                              const float4* __restrict__ feat,
                                              const int* __restrict__ counts, SolveState* __restrict__ st,
                                              MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
                                              int seeded, int assoc, int chunk, int* __restrict__ nbr) {
+  __shared__ KnnScratch scratch[KG_QPB];
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   const int n_e = counts[0], n_s = counts[1];
   const int lane = threadIdx.x & 31;
-  const int live = n_e + n_s;  // sorted positions >= live are padding
+  const WarpGroup8 x;
+  KnnScratch* s = &scratch[threadIdx.x >> 3];
+  const int live = n_e + n_s;  // positions >= live are padding (sorted) or unset (ring order)
   while (true) {
-    // `chunk` queries per warp (32, 16 or 8: the host picks it so that a small sweep still spreads over every
-    // resident warp — a chunk is a serial, divergent piece of work and its latency, not the SM's throughput,
-    // bounds a launch that has fewer chunks than warp slots).  (Measured and dropped: handing the expensive
-    // queries out eight at a time, +30 %; handing the chunks out from the end, 802 vs 753 us per sweep.)
     int base = 0;
     if (lane == 0) base = atomicAdd(&st->knn_next, chunk);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= live) break;
-    const int width = chunk;
-    TSTAMP(t_chunk0);
-    int t = base + lane;
-    if (lane >= width || t >= upper || t >= live) continue;  // positions >= live: padding (sorted) or unset (ring order)
-    int f = perm[t];
-    if (f >= live) continue;
-    const bool is_edge = f < n_e;
-    Top5 nb;
-    nb.reset();
-    float4 w;
-    if (assoc) {
-      quat q;
-      q.x = st->x[0];
-      q.y = st->x[1];
-      q.z = st->x[2];
-      q.w = st->x[3];
-      d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
-      float4 fp = feat[f];
-      d3 pwd = add3(qrot(q, mk3((double)fp.x, (double)fp.y, (double)fp.z)), tr);
-      w = make_float4((float)pwd.x, (float)pwd.y, (float)pwd.z, 0.f);
-      pw[f] = w;
-    } else {
-      w = pw[f];
+    for (int r = 0; r < chunk && base + r < live; r += 4) {  // four queries per round, one per group
+      const int t = base + r + (lane >> 3);
+      bool active = t < upper && t < live;
+      int f = active ? perm[t] : 0;
+      if (f >= live) active = false;
+      const bool is_edge = f < n_e;
+      float wx = 0.f, wy = 0.f, wz = 0.f;
+      if (assoc) {
+        if (active && x.l == 0) {  // one lane per query; the group receives the point by shuffle
+          quat q;
+          q.x = st->x[0];
+          q.y = st->x[1];
+          q.z = st->x[2];
+          q.w = st->x[3];
+          const d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
+          const float4 fp = feat[f];
+          const d3 pwd = add3(qrot(q, mk3((double)fp.x, (double)fp.y, (double)fp.z)), tr);
+          wx = (float)pwd.x, wy = (float)pwd.y, wz = (float)pwd.z;
+          pw[f] = make_float4(wx, wy, wz, 0.f);
+        }
+        wx = __shfl_sync(0xffffffffu, wx, 0, 8);
+        wy = __shfl_sync(0xffffffffu, wy, 0, 8);
+        wz = __shfl_sync(0xffffffffu, wz, 0, 8);
+      } else if (active) {
+        const float4 w = pw[f];
+        wx = w.x, wy = w.y, wz = w.z;
+      }
+      knn_one(x, s, maps, is_edge, is_edge ? has_edge_map != 0 : has_surf_map != 0, active, wx, wy, wz, seeded, upper, t,
+              nbr);
     }
-    if (is_edge ? has_edge_map : has_surf_map) {
-      int seed[5];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) seed[k] = seeded ? nbr[k * upper + t] : -1;
-      knn5(is_edge ? maps.edge : maps.surf, w.x, w.y, w.z, nb, is_edge ? maps.edge_cat : maps.surf_cat,
-           seeded ? seed : nullptr);
-    }
-    const bool full = nb.full();
-#pragma unroll
-    for (int k = 0; k < 5; ++k) nbr[k * upper + t] = full ? nb.id[k] : -1;
-#ifdef LMSF_TIMING
-    {
-      unsigned long long t1 = gtime(), dt = t1 - t_chunk0;  // per lane: from chunk start to this lane's finish
-      atomicMax(&g_dbg[8], dt);
-      atomicAdd(&g_dbg[9], dt);
-      atomicAdd(&g_dbg[10], 1ull);
-      int bucket = dt < 20000 ? 0 : (dt < 40000 ? 1 : (dt < 80000 ? 2 : (dt < 160000 ? 3 : 4)));
-      atomicAdd(&g_dbg[11 + bucket], 1ull);
-    }
-#endif
   }
 }
 
@@ -1148,43 +1164,56 @@ __global__ void k_state_init(SolveState* st, Pose7 pose) {
 }
 
 // ------------------------------------------------------------------ test hooks
-__global__ void __launch_bounds__(128) k_knn_hook(MapView mv, const float* __restrict__ q, int nq,
-                                                  int* __restrict__ idx, float* __restrict__ d2) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
-  Top5 nb;
-  knn5(mv, q[3 * i], q[3 * i + 1], q[3 * i + 2], nb, nullptr, nullptr);
-  for (int k = 0; k < 5; ++k) {
-    bool in = nb.id[k] >= 0 && nb.id[k] != 0x7fffffff;
-    idx[5 * i + k] = in ? nb.id[k] : -1;
-    d2[5 * i + k] = in ? nb.d[k] : __int_as_float(0x7f800000);
+// one query per group of eight lanes: blocks of KG_BLOCK threads search KG_QPB queries
+__global__ void __launch_bounds__(KG_BLOCK) k_knn_hook(MapView mv, const float* __restrict__ q, int nq,
+                                                       int* __restrict__ idx, float* __restrict__ d2) {
+  __shared__ KnnScratch scratch[KG_QPB];
+  const WarpGroup8 x;
+  KnnScratch* s = &scratch[threadIdx.x >> 3];
+  const int i = blockIdx.x * KG_QPB + (threadIdx.x >> 3);
+  const bool active = i < nq;
+  const float qx = active ? q[3 * i] : 0.f, qy = active ? q[3 * i + 1] : 0.f, qz = active ? q[3 * i + 2] : 0.f;
+  const int n = kg_knn5(x, mv, s, qx, qy, qz, active, 0ull);
+  if (active && x.l < 5) {
+    const bool in = x.l < n;
+    idx[5 * i + x.l] = in ? kg_key_id(s->acc[x.l]) : -1;
+    d2[5 * i + x.l] = in ? kg_key_d2(s->acc[x.l]) : __int_as_float(0x7f800000);
   }
 }
 
-__global__ void __launch_bounds__(128) k_match_hook(MapView mv, const float4* __restrict__ cat, int kind,
-                                                    const float* __restrict__ q, int nq, uint8_t* __restrict__ okv,
-                                                    double* __restrict__ out10) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
-  float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
-  Top5 nb;
-  knn5(mv, px, py, pz, nb, nullptr, nullptr);
+__global__ void __launch_bounds__(KG_BLOCK) k_match_hook(MapView mv, const float4* __restrict__ cat, int kind,
+                                                         const float* __restrict__ q, int nq,
+                                                         uint8_t* __restrict__ okv, double* __restrict__ out10) {
+  __shared__ KnnScratch scratch[KG_QPB];
+  const WarpGroup8 x;
+  KnnScratch* s = &scratch[threadIdx.x >> 3];
+  const int i = blockIdx.x * KG_QPB + (threadIdx.x >> 3);
+  const bool active = i < nq;
+  const float px = active ? q[3 * i] : 0.f, py = active ? q[3 * i + 1] : 0.f, pz = active ? q[3 * i + 2] : 0.f;
+  const int n = kg_knn5(x, mv, s, px, py, pz, active, 0ull);
+  if (!active || x.l != 0) return;
   double o[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool ok = false;
-  if (nb.full()) {
+  if (n == 5) {
+    Top5 nb;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      nb.id[k] = kg_key_id(s->acc[k]);
+      nb.d[k] = kg_key_d2(s->acc[k]);
+    }
     if (kind == LMSF_KIND_EDGE) {
-      d3 n, a, b;
+      d3 nn, a, b;
       double r;
-      ok = fit_edge(cat, nb, px, py, pz, n, r, a, b);
+      ok = fit_edge(cat, nb, px, py, pz, nn, r, a, b);
       if (ok) {
-        o[0] = n.x, o[1] = n.y, o[2] = n.z, o[3] = r;
+        o[0] = nn.x, o[1] = nn.y, o[2] = nn.z, o[3] = r;
         o[4] = a.x, o[5] = a.y, o[6] = a.z, o[7] = b.x, o[8] = b.y, o[9] = b.z;
       }
     } else {
-      d3 n;
+      d3 nn;
       double D, r;
-      ok = fit_surf(cat, nb, px, py, pz, n, D, r);
-      if (ok) o[0] = n.x, o[1] = n.y, o[2] = n.z, o[3] = r, o[4] = D;
+      ok = fit_surf(cat, nb, px, py, pz, nn, D, r);
+      if (ok) o[0] = nn.x, o[1] = nn.y, o[2] = nn.z, o[3] = r, o[4] = D;
     }
   }
   okv[i] = ok ? 1 : 0;
@@ -1197,15 +1226,17 @@ __global__ void __launch_bounds__(128) k_match_hook(MapView mv, const float4* __
 struct Rigid12f {
   float m[12];  // rows 0..2 of the 4x4, row-major
 };
-__global__ void __launch_bounds__(128) k_align_score(MapView mv, const float4* __restrict__ pts, int n, Rigid12f T,
-                                                     float thresh, double* __restrict__ part_sum,
-                                                     int* __restrict__ part_cnt) {
+__global__ void __launch_bounds__(KG_BLOCK) k_align_score(MapView mv, const float4* __restrict__ pts, int n, Rigid12f T,
+                                                          float thresh, double* __restrict__ part_sum,
+                                                          int* __restrict__ part_cnt) {
+  __shared__ KnnScratch scratch[KG_QPB];
   __shared__ double s_sum[4];
   __shared__ int s_cnt[4];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const WarpGroup8 x;
+  KnnScratch* s = &scratch[threadIdx.x >> 3];
+  const int i = blockIdx.x * KG_QPB + (threadIdx.x >> 3);  // one source point per group of eight lanes
   double v = 0.0;
   int in = 0;
-  Top5 nb;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   if (i < n) {
     float4 p = pts[i];
@@ -1213,12 +1244,11 @@ __global__ void __launch_bounds__(128) k_align_score(MapView mv, const float4* _
     qy = T.m[4] * p.x + T.m[5] * p.y + T.m[6] * p.z + T.m[7];
     qz = T.m[8] * p.x + T.m[9] * p.y + T.m[10] * p.z + T.m[11];
   }
-  // every thread of the block calls knn5 (it owns shared-memory-free state only, but keeps the warps converged)
-  if (i < n) {
-    knn5(mv, qx, qy, qz, nb, nullptr, nullptr);
-    const bool found = nb.id[0] >= 0 && nb.id[0] != 0x7fffffff;
-    if (found && nb.d[0] <= thresh) {
-      v = (double)nb.d[0];
+  const int found = kg_knn5(x, mv, s, qx, qy, qz, i < n, 0ull);
+  if (i < n && x.l == 0 && found > 0) {
+    const float d0 = kg_key_d2(s->acc[0]);
+    if (d0 <= thresh) {
+      v = (double)d0;
       in = 1;
     }
   }
@@ -1336,7 +1366,7 @@ int hook_scratch(Ctx* c, size_t bytes, void** out) {
 int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2) {
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
   if (nq == 0) return LMSF_OK;
-  LM_LAUNCH(c, k_knn_hook, div_up(nq, 128), 128, 0, view_of(c->map[kind]), d_q, nq, d_idx, d_d2);
+  LM_LAUNCH(c, k_knn_hook, div_up(nq, KG_QPB), KG_BLOCK, 0, view_of(c->map[kind]), d_q, nq, d_idx, d_d2);
   LM_CUDA(cudaGetLastError());
   return LMSF_OK;
 }
@@ -1344,7 +1374,7 @@ int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2
 int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double* d_out10) {
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
   if (nq == 0) return LMSF_OK;
-  LM_LAUNCH(c, k_match_hook, div_up(nq, 128), 128, 0, view_of(c->map[kind]), c->map[kind].cat, kind, d_q, nq, d_ok,
+  LM_LAUNCH(c, k_match_hook, div_up(nq, KG_QPB), KG_BLOCK, 0, view_of(c->map[kind]), c->map[kind].cat, kind, d_q, nq, d_ok,
             d_out10);
   LM_CUDA(cudaGetLastError());
   return LMSF_OK;
@@ -1353,13 +1383,13 @@ int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double
 // device cloud -> (sum of inlier squared distances, inlier count) read back with one sync
 int align_hook(Ctx* c, int kind, const float4* d_pts, int n, const float T12[12], float thresh, double* sum, int* cnt) {
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
-  const int nblk = div_up(n, 128);
+  const int nblk = div_up(n, KG_QPB);
   // partial sums live behind the caller's points in the hook arena (d_pts is its first n float4)
   double* d_part = (double*)(d_pts + n);
   int* d_cnt = (int*)(d_part + nblk + 1);
   Rigid12f T;
   for (int i = 0; i < 12; ++i) T.m[i] = T12[i];
-  LM_LAUNCH(c, k_align_score, nblk, 128, 0, view_of(c->map[kind]), d_pts, n, T, thresh, d_part, d_cnt);
+  LM_LAUNCH(c, k_align_score, nblk, KG_BLOCK, 0, view_of(c->map[kind]), d_pts, n, T, thresh, d_part, d_cnt);
   LM_LAUNCH(c, k_align_finish, 1, 256, 0, d_part, d_cnt, nblk, d_part + nblk, d_cnt + nblk);
   int rc = LMSF_OK;
   if (cudaMemcpyAsync(sum, d_part + nblk, sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
@@ -1476,7 +1506,7 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       if (knn_width == 8 || knn_width == 16 || knn_width == 32) chunk = knn_width;
       int knn_grid = div_up(up, 4 * chunk);
       if (knn_grid > 148 * knn_per_sm) knn_grid = 148 * knn_per_sm;  // persistent: every resident warp pulls work
-      LM_LAUNCH(c, k_knn, knn_grid, 128, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, up,
+      LM_LAUNCH(c, k_knn, knn_grid, KG_BLOCK, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, up,
                 solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_nbr);
       c->match_bytes += alg_bytes;
       c->match_launches += 1;

@@ -35,6 +35,13 @@ for line in out:
                      int(r[ix["Thread Instructions Executed"]])))
     except ValueError:
         pass
+agg = {}
+for r in rows:   # the same line of every captured launch (and every inlined copy) is one entry
+    a = agg.setdefault((r[0], r[1]), [r[0], r[1], r[2], 0, 0, 0])
+    a[3] += r[3]
+    a[4] += r[4]
+    a[5] += r[5]
+rows = [tuple(a) for a in agg.values()]
 ts = sum(r[3] for r in rows) or 1
 ti = sum(r[4] for r in rows) or 1
 tt = sum(r[5] for r in rows)
