@@ -708,12 +708,12 @@ int lmsf_knn5(lmsf_ctx* c, int kind, const float* q_xyz, int nq, int32_t* idx5, 
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
   if (nq == 0) return LMSF_OK;
   char* buf = nullptr;
-  LM_TRY(hook_scratch(c, (size_t)nq * 52, (void**)&buf));
+  LM_TRY(hook_scratch(c, (size_t)nq * 56 + 8, (void**)&buf));
   float* d_q = (float*)buf;
   int* d_i = (int*)(buf + (size_t)nq * 12);
   float* d_d = (float*)(buf + (size_t)nq * 32);
   LM_CUDA(cudaMemcpyAsync(d_q, q_xyz, (size_t)nq * 12, cudaMemcpyHostToDevice, c->stream));
-  LM_TRY(knn_hook(c, kind, d_q, nq, d_i, d_d));
+  LM_TRY(knn_hook(c, kind, d_q, nq, d_i, d_d, (int*)(buf + (size_t)nq * 52)));
   LM_CUDA(cudaMemcpyAsync(idx5, d_i, (size_t)nq * 20, cudaMemcpyDeviceToHost, c->stream));
   LM_CUDA(cudaMemcpyAsync(d2_5, d_d, (size_t)nq * 20, cudaMemcpyDeviceToHost, c->stream));
   LM_CUDA(cudaStreamSynchronize(c->stream));
@@ -753,7 +753,7 @@ int lmsf_align_score(lmsf_ctx* c, int kind, const float* xyzi, int n, const floa
     return LMSF_OK;
   }
   float4* d_pts = nullptr;
-  const size_t nblk = (size_t)(n + 15) / 16;  // k_align_score: one partial per block of 16 points
+  const size_t nblk = (size_t)(n + 127) / 128;
   LM_TRY(hook_scratch(c, (size_t)n * sizeof(float4) + (nblk + 1) * (sizeof(double) + sizeof(int)) + 64, (void**)&d_pts));
   double sum = 0;
   int cnt = 0;

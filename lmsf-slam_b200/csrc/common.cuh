@@ -142,7 +142,8 @@ struct SolveState {
   int lm_steps_total, lm_steps_accepted;
   unsigned ticket;    // last-block-done counter
   int knn_next;       // work-queue head of the running k_knn launch (light queries, chunks of 32)
-  int knn_next_heavy; // work-queue head for the heavy queries (chunks of 8)
+  int defer_next;     // work-queue head of the k_knn_sparse launch that follows (one deferred query per warp)
+  int n_defer;        // queries the running k_knn launch handed to k_knn_sparse (positions in Ctx::d_defer)
   int n_heavy;        // queries whose own map cell is (nearly) empty; they sort first
 };
 
@@ -170,6 +171,7 @@ struct Ctx {
   int* q_vals_alt = nullptr;                 // sorted: position -> feature index
   float4* d_pw = nullptr;      // [max_points] fp32 world point by feature index
   int* d_nbr = nullptr;        // [5][max_points] neighbour indices by sorted query position
+  int* d_defer = nullptr;      // [max_points] positions of the queries k_knn left to k_knn_sparse
   double* d_partial = nullptr; // [grid][LM_NSUM]
   int partial_blocks = 0;
   SolveState* d_state = nullptr;
@@ -314,7 +316,8 @@ void solve_free(Ctx* c);
 // grow-only scratch arena of the hooks: `bytes` of device memory, valid until the next hook call (a regrow
 // synchronises the device, steady-state calls do not allocate)
 int hook_scratch(Ctx* c, size_t bytes, void** out);
-int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2);
+// d_work: nq + 2 ints of scratch (deferral counters and list)
+int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2, int* d_work);
 int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double* d_out10);
 int align_hook(Ctx* c, int kind, const float4* d_pts, int n, const float T12[12], float thresh, double* sum, int* cnt);
 // features in c->d_feat (counts in c->ex.counts on the device; `upper` bounds their sum on the

@@ -1,7 +1,7 @@
-// debug_stats.cu — instrumented copy of the cooperative kNN search (compiled with LMSF_KNN_STATS) used to tune it:
+// debug_stats.cu — instrumented copy of the kNN search (compiled with LMSF_KNN_STATS) used to tune it:
 // work counters summed over a batch of queries.  Not part of the documented ABI; exported as lmsf_debug_knn_stats for
 // scripts under profiles/.
-//   out[0] L0 cell lookups   out[1] tasks dealt   out[2] candidates scanned   out[5] list compressions
+//   out[0] L0 cell lookups   out[1] L1 cells visited   out[2] candidates scanned   out[3] segments
 //   out[8..11] sweeps started in state START / BALL / SPARSE1 / SPARSE2       out[16] queries, out[17] with 5 neighbours
 #define LMSF_KNN_STATS 1
 #include "common.cuh"
@@ -10,17 +10,13 @@
 namespace lm {
 __global__ void __launch_bounds__(KG_BLOCK) k_knn_stats(MapView mv, const float* __restrict__ q, int nq,
                                                         unsigned long long* __restrict__ out) {
-  __shared__ KnnScratch scratch[KG_QPB];
-  const WarpGroup8 x;
-  KnnScratch* s = &scratch[threadIdx.x >> 3];
-  const int i = blockIdx.x * KG_QPB + (threadIdx.x >> 3);
-  const bool active = i < nq;
-  const float qx = active ? q[3 * i] : 0.f, qy = active ? q[3 * i + 1] : 0.f, qz = active ? q[3 * i + 2] : 0.f;
-  const int n = kg_knn5(x, mv, s, qx, qy, qz, active, 0ull);
-  if (active && x.l == 0) {
-    atomicAdd(&out[16], 1ull);
-    if (n == 5) atomicAdd(&out[17], 1ull);
-  }
+  __shared__ int s_seg[KQ_SMEM_INTS];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  KqTop top;
+  const int n = kq_knn5<false>(mv, kq_list(s_seg), q[3 * i], q[3 * i + 1], q[3 * i + 2], nullptr, top);
+  atomicAdd(&out[16], 1ull);
+  if (n == 5) atomicAdd(&out[17], 1ull);
 }
 __global__ void k_knn_stats_collect(unsigned long long* __restrict__ out, int reset) {
   const int i = threadIdx.x;
@@ -52,7 +48,7 @@ extern "C" int lmsf_debug_knn_stats(lmsf_ctx* c, int kind, const float* q_xyz, i
   LM_CUDA(cudaMemsetAsync(d_o, 0, 28 * 8, c->stream));
   LM_CUDA(cudaMemcpyAsync(d_q, q_xyz, (size_t)nq * 12, cudaMemcpyHostToDevice, c->stream));
   k_knn_stats_collect<<<1, 32, 0, c->stream>>>(d_o, 1);
-  k_knn_stats<<<div_up(nq, KG_QPB), KG_BLOCK, 0, c->stream>>>(v, d_q, nq, d_o);
+  k_knn_stats<<<div_up(nq, KG_BLOCK), KG_BLOCK, 0, c->stream>>>(v, d_q, nq, d_o);
   k_knn_stats_collect<<<1, 32, 0, c->stream>>>(d_o, 0);
   LM_CUDA(cudaMemcpyAsync(out, d_o, 28 * 8, cudaMemcpyDeviceToHost, c->stream));
   LM_CUDA(cudaStreamSynchronize(c->stream));

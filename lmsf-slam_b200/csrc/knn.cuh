@@ -1,4 +1,4 @@
-// knn.cuh — exact 5-NN over the local-map grid, searched COOPERATIVELY by a group of lanes per query.
+// knn.cuh — exact 5-NN over the local-map grid: one thread per query, in two phases per sweep.
 //
 // Replaces pcl::KdTreeFLANN::nearestKSearch(point, 5, ...) as called by
 // EdgeFeatureMatch::Match (registration/FeatureMatch/EdgeFeatureMatch.hpp:38) and
@@ -8,41 +8,30 @@
 //
 // Index (mapindex.cu): L0 = 1 m cells in a hash table; every L0 cell has a 64-bit occupancy
 // mask of its 4x4x4 L1 cells (0.25 m); every occupied L1 cell has a 64-bit mask
-// of its 4x4x4 L2 cells (0.0625 m).  Points are grouped by (L0, L1, L2), x fastest, so an x-run of
-// L2 cells inside one L1 cell — and a whole L1 cell — is one contiguous range of `sorted`.
+// of its 4x4x4 L2 cells (0.0625 m).  Points are grouped by (L0, L1, L2), x fastest, so any set of L2 cells that are
+// consecutive among the OCCUPIED cells of one L1 cell is one contiguous range of `sorted`.
 //
-// Search (round 2; round 1 walked the grid with one thread per query: 5-6 of 32 lanes active, 19-31 % of the
-// issue slots in a per-thread sorted insert).  A query is owned by a GROUP of G = 8 lanes, four queries per warp:
-//   tasks       the cells of a box around the query are cut into tasks — (z,y) rows of L2 cells per L1 cell
-//               ("rows" mode, boxes up to 11 cells wide) or whole L1 cells ("cells" mode, larger boxes) — dealt
-//               round-robin to the lanes; a task ends in one contiguous segment [s, e) of `sorted` (three dependent
-//               loads: hash probe, L1 record, two L2 starts).  With a bound on the 5th distance, rows outside the
-//               ball are skipped and the x-run is clipped to the ball.  Non-empty segments are compacted into a
-//               per-group list in shared memory.
-//   candidates  the segments are flattened (prefix sums) and the group strides over the candidates with coalesced
-//               16-byte loads: every lane computes one distance per step, whatever the cell occupancy is.
-//   accept      a candidate whose key (distance bits, index) is <= the bound key is appended to the group's
-//               accepted list (ballot + popc: no sorted insert, no divergence); when the list fills up it is
-//               compressed to its five smallest keys and the bound tightens.
-//   select      the five smallest keys of the list, ascending: rank counting for lists of up to G keys, five rounds
-//               of group-min extraction otherwise.
-// A query runs through a small state machine: with seeds (the previous outer iteration's neighbours) one bounded
-// sweep is enough; without, the 27 L2 cells around the query give the bound (or the answer when the 5th distance
-// is below one cell), then one bounded sweep; sparse surroundings escalate to the 27 L1 cells and to everything
-// within 1 m.  All groups of a warp step through the machine in lockstep.
+// Search (round 2).  Round 1 walked the grid row by row with nested loops per thread: 5-6 of 32 lanes active and a
+// chain of ~75 dependent loads per query.  A first round-2 attempt (8 lanes per query, shared-memory task lists) reached
+// 25 lanes per instruction but executed 20x the thread instructions.  This version keeps one thread per query and
+// removes the divergence where it was made:
+//   sweep    = all points in a box of L2 cells [lo, hi] minus an already searched box, in two phases:
+//   phase A  cells -> segments.  The box is intersected with the occupancy masks (two ANDs with a box mask built by
+//            bit arithmetic: no row or cell loops), the selected cells are cut into runs of consecutive occupied
+//            cells, and every run becomes one (start, end) pair in a small per-lane list in shared memory.
+//   phase B  segments -> neighbours.  ONE flat loop over the candidates of all the segments, the next point in flight
+//            while the current one is judged; a candidate enters the sorted five (64-bit keys = distance bits | index)
+//            only if it beats the current fifth.  The lanes of a warp differ in the trip count of this one loop only.
+// With seeds (the previous outer iteration's neighbours) one sweep of the ball's bounding box is enough; without,
+// the search adapts to the density around the query (own cell, 27 cells, then a counted growth: see kq_knn5).
 //
 // Cell sizes are powers of two, so cell indices and cell bounds are exact in
-// fp32 and the box distance — computed with the same rounding sequence as a
-// point distance — never exceeds the distance of a point inside the box:
-// pruning is exact, ties included.
-//
+// fp32 and a box is a superset of the ball it covers (edges computed exactly, in fp64).
 // Distances are FLANN's L2_Simple: ((dx*dx)+dy*dy)+dz*dz in fp32.  Results are
 // ascending by (distance, original index): ties are resolved by index, which
 // FLANN resolves by traversal order ("identical except at exact ties").
 //
-// The search is written once, as templates over an executor X (lane id inside the group, ballot / shuffle /
-// any): WarpGroup8 on the device, HostGroup1 (one lane) in csrc/test_knn_model.cu, which runs the same source on the
-// CPU against brute force.
+// The search is plain per-thread code (HD): csrc/test_knn_model.cu runs the same source on the CPU against brute force.
 #pragma once
 #include <string.h>
 
@@ -53,10 +42,12 @@ namespace lm {
 #if defined(__CUDA_ARCH__)
 #define KG_POPC64(x) __popcll(x)
 #define KG_POPC32(x) __popc(x)
+#define KG_FFS32(x) (__ffs((int)(x)) - 1)
 #define KG_LD(p) __ldg(p)
 #else
 #define KG_POPC64(x) __builtin_popcountll(x)
 #define KG_POPC32(x) __builtin_popcount(x)
+#define KG_FFS32(x) __builtin_ctz(x)
 #define KG_LD(p) (*(p))
 #endif
 
@@ -149,23 +140,24 @@ HD unsigned long long kg_key(float d2, int id) { return ((unsigned long long)f2u
 HD float kg_key_d2(unsigned long long k) { return u2f((unsigned)(k >> 32)); }
 HD int kg_key_id(unsigned long long k) { return (int)(unsigned)(k & 0xffffffffull); }
 
-constexpr int KG_SEG_CAP = 64;   // segments a group collects before it scans them
-constexpr int KG_ACC_CAP = 64;   // accepted keys a group collects before it compresses them to five
-constexpr unsigned long long KG_KEY_LT_1 = (0x3f800000ull << 32) - 1ull;  // accepts exactly the keys with d2 < 1.0f
+constexpr int KQ_SEG_CAP = 16;  // segments a lane collects before it scans them
+constexpr unsigned long long KG_KEY_LT_1 = (0x3f800000ull << 32) - 1ull;  // largest key with d2 < 1.0f
 
-struct KnnScratch {  // per group (shared memory on the device)
-  unsigned long long acc[KG_ACC_CAP];  // accepted keys; after a search: the result, ascending
-  int seg_s[KG_SEG_CAP];               // first point of every collected segment
-  int seg_pre[KG_SEG_CAP + 8];         // collected: lengths; flattened: [i] = offset of segment i, [nseg] = total
+// where a lane keeps its segment list: seg[(2 k) * stride], seg[(2 k + 1) * stride] = start, end of segment k
+// (device: shared memory, stride 32, so that the lanes of a warp never share a bank)
+struct KqList {
+  int* seg;
+  int stride;
 };
 
-enum { KG_START = 0, KG_BALL = 1, KG_SPARSE1 = 2, KG_SPARSE2 = 3, KG_DONE = 4 };
-
-#ifdef LMSF_KNN_STATS  // tuning builds: work counters (global atomics), see kg_stat
-__device__ unsigned long long g_knn_stat[16];
+#ifdef LMSF_KNN_STATS  // tuning builds: work counters (global atomics)
+static __device__ unsigned long long g_knn_stat[16];
+static unsigned long long g_knn_stat_host[16];  // the CPU model's copy
 HD void kg_stat_add(int slot, unsigned long long v) {
 #if defined(__CUDA_ARCH__)
   if (v) atomicAdd(&g_knn_stat[slot], v);
+#else
+  g_knn_stat_host[slot] += v;
 #endif
 }
 #define KG_STAT(slot, v) kg_stat_add(slot, (unsigned long long)(v))
@@ -173,426 +165,621 @@ HD void kg_stat_add(int slot, unsigned long long v) {
 #define KG_STAT(slot, v)
 #endif
 
-// ---- executors -------------------------------------------------------------------------------------------------
-// eight lanes per query, four queries per warp; every warp-wide primitive is executed by all 32 lanes
-struct WarpGroup8 {
-  static constexpr int G = 8;
-  int l;            // lane inside the group
-  unsigned gshift;  // bit position of the group inside a warp ballot
+#ifdef LMSF_KNN_CHECK  // debugging builds: index checks that record the first violation instead of faulting
+static __device__ int g_knn_check[8];
+HD bool kq_check_fail(int code, int a, int b, int c) {
 #if defined(__CUDA_ARCH__)
-  HD WarpGroup8() {
-    const int lane = threadIdx.x & 31;
-    l = lane & 7;
-    gshift = lane & 24;
+  if (atomicCAS(&g_knn_check[0], 0, code) == 0) {
+    g_knn_check[1] = a;
+    g_knn_check[2] = b;
+    g_knn_check[3] = c;
+    g_knn_check[4] = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   }
-  HD unsigned ballot(bool p) const { return (__ballot_sync(0xffffffffu, p) >> gshift) & 0xffu; }
-  HD bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }  // warp-wide: loop control
-  HD int shfl(int v, int src) const { return __shfl_sync(0xffffffffu, v, src, 8); }
-  HD int shfl_up(int v, int d) const { return __shfl_up_sync(0xffffffffu, v, d, 8); }
-  HD unsigned long long shfl_xor64(unsigned long long v, int d) const { return __shfl_xor_sync(0xffffffffu, v, d, 8); }
-  HD void sync() const { __syncwarp(); }
-#else  // host pass of nvcc: never executed
-  HD WarpGroup8() : l(0), gshift(0) {}
-  HD unsigned ballot(bool) const { return 0u; }
-  HD bool any(bool) const { return false; }
-  HD int shfl(int v, int) const { return v; }
-  HD int shfl_up(int v, int) const { return v; }
-  HD unsigned long long shfl_xor64(unsigned long long v, int) const { return v; }
-  HD void sync() const {}
 #endif
-};
-struct HostGroup1 {  // the same source with one lane per query (CPU model, csrc/test_knn_model.cu)
-  static constexpr int G = 1;
-  int l = 0;
-  HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
-  HD bool any(bool p) const { return p; }
-  HD int shfl(int v, int) const { return v; }
-  HD int shfl_up(int v, int) const { return v; }
-  HD unsigned long long shfl_xor64(unsigned long long v, int) const { return v; }
-  HD void sync() const {}
-};
+  return true;
+}
+#define KQ_CHECK(ok, code, a, b, c) \
+  if (!(ok) && kq_check_fail(code, a, b, c)) return
+#else
+#define KQ_CHECK(ok, code, a, b, c)
+#endif
 
-// ---- select: the five smallest keys of acc[0, n), ascending, to acc[0, min(n, 5)); n <- min(n, 5) ---------------------
-template <class X>
-HD void kg_select5(const X& x, KnnScratch* s, int& n) {
-  constexpr int G = X::G;
-  const bool small = n <= G;
-  // lists of up to G keys: one key per lane, rank = number of smaller keys (keys are unique: indices are)
-  unsigned long long mine = ~0ull;
-  int rank = 0;
-  if (x.any(small && n > 0)) {
-    if (small && x.l < n) mine = s->acc[x.l];
-    for (int j = 0; x.any(small && j < n); ++j) {
-      if (small && j < n) rank += (s->acc[j] < mine) ? 1 : 0;
+HD int kq_ffs64(unsigned long long v) {  // index of the lowest set bit; v != 0
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)v) - 1;
+#else
+  return __builtin_ctzll(v);
+#endif
+}
+HD unsigned long long kq_below(int b) { return (1ull << b) - 1ull; }  // bits [0, b), b < 64
+
+// the five best keys so far, ascending; slots that hold no point yet hold the (exclusive) bound
+struct KqTop {
+  unsigned long long k[5];
+  float d4;  // distance part of k[4]: a candidate farther than this cannot enter
+  int n;     // points among them
+};
+HD void kq_top_reset(KqTop& t, unsigned long long exclusive_bound) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) t.k[i] = exclusive_bound;
+  t.d4 = kg_key_d2(exclusive_bound);
+  t.n = 0;
+}
+// key < t.k[4].  dedup: the sweep may meet points that are in the list already (sparse path only)
+HD void kq_insert(KqTop& t, unsigned long long key, bool dedup) {
+  if (dedup && (key == t.k[0] || key == t.k[1] || key == t.k[2] || key == t.k[3])) return;
+  t.n = t.n < 5 ? t.n + 1 : 5;
+  // the new key takes the place of the 5th and sinks; most keys stop after a step or two
+  if (key < t.k[3]) {
+    t.k[4] = t.k[3];
+    if (key < t.k[2]) {
+      t.k[3] = t.k[2];
+      if (key < t.k[1]) {
+        t.k[2] = t.k[1];
+        if (key < t.k[0]) {
+          t.k[1] = t.k[0];
+          t.k[0] = key;
+        } else {
+          t.k[1] = key;
+        }
+      } else {
+        t.k[2] = key;
+      }
+    } else {
+      t.k[3] = key;
+    }
+  } else {
+    t.k[4] = key;
+  }
+  t.d4 = kg_key_d2(t.k[4]);
+}
+
+// bits (x + 4 y + 16 z) of a 4x4x4 block whose coordinates lie in [xl, xh] x [yl, yh] x [zl, zh]; the ranges are
+// clamped to the block, an empty range gives 0
+HD unsigned long long kq_box_mask(int xl, int xh, int yl, int yh, int zl, int zh) {
+  xl = xl < 0 ? 0 : xl, yl = yl < 0 ? 0 : yl, zl = zl < 0 ? 0 : zl;
+  xh = xh > 3 ? 3 : xh, yh = yh > 3 ? 3 : yh, zh = zh > 3 ? 3 : zh;
+  if (xl > xh || yl > yh || zl > zh) return 0ull;
+  const unsigned xb = ((2u << xh) - 1u) & ~((1u << xl) - 1u);                 // x range, 4 bits
+  const unsigned yb = ((2u << (4 * yh + 3)) - 1u) & ~((1u << (4 * yl)) - 1u);  // rows yl..yh of one layer, 16 bits
+  const unsigned w = (xb * 0x11111111u) & (yb * 0x00010001u);                  // two layers
+  // layers zl..zh: two per 32-bit half
+  const unsigned zb = ((2u << zh) - 1u) & ~((1u << zl) - 1u);  // 4 bits
+  const unsigned lo = w & ((zb & 1u ? 0x0000ffffu : 0u) | (zb & 2u ? 0xffff0000u : 0u));
+  const unsigned hi = w & ((zb & 4u ? 0x0000ffffu : 0u) | (zb & 8u ? 0xffff0000u : 0u));
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+// phase B: one flat loop over the `total` candidates of segments [first, ...) of the list, two loads ahead of the
+// judgement
+HD void kq_scan(const MapView& mv, const KqList& li, int first, int total, float qx, float qy, float qz, KqTop& top,
+                bool dedup) {
+  if (total <= 0) return;
+  int at = (2 * first) * li.stride;  // the fetch cursor: list position of the current segment, next point, its end
+  int p = li.seg[at], e = li.seg[at + li.stride];
+  int fetched = 0;
+  float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0;
+#define KQ_FETCH(dst)                                               \
+  if (fetched < total) {                                            \
+    if (p == e) {                                                   \
+      at += 2 * li.stride;                                          \
+      p = li.seg[at];                                               \
+      e = li.seg[at + li.stride];                                   \
+    }                                                               \
+    KQ_CHECK(p >= 0 && p < e && e <= mv.dev->n, 2, p, e, fetched);  \
+    dst = KG_LD(&mv.sorted[p]);                                     \
+    ++p;                                                            \
+    ++fetched;                                                      \
+  }
+  KQ_FETCH(n0);
+  KQ_FETCH(n1);
+  for (int i = 0; i < total; ++i) {
+    const float4 m = n0;
+    n0 = n1;
+    KQ_FETCH(n1);
+    const float dx = m.x - qx, dy = m.y - qy, dz = m.z - qz;
+    float r = dx * dx;
+    r = r + dy * dy;
+    r = r + dz * dz;
+    KG_STAT(2, 1);
+    if (r <= top.d4) {  // cheap rejection first; ties and order are settled on the full key
+      const unsigned long long key = kg_key(r, (int)f2u(m.w));
+      if (key < top.k[4]) kq_insert(top, key, dedup);
     }
   }
-  // longer lists: five rounds of "smallest key above the last one taken"
-  unsigned long long res[5];
-#pragma unroll
-  for (int r = 0; r < 5; ++r) res[r] = ~0ull;
-  if (x.any(!small)) {
-    unsigned long long last = 0ull;
-#pragma unroll
-    for (int r = 0; r < 5; ++r) {
-      unsigned long long m = ~0ull;
-      for (int e0 = 0; x.any(!small && e0 < n); e0 += G) {
-        const int e = e0 + x.l;
-        if (!small && e < n) {
-          const unsigned long long k = s->acc[e];
-          if ((r == 0 || k > last) && k < m) m = k;
+#undef KQ_FETCH
+}
+
+// what one sweep does with the cells of its box
+enum { KQ_SCAN = 0, KQ_COUNT = 1, KQ_NEAREST_L1 = 2 };
+
+struct KqSweep {
+  int lo[3], hi[3];    // box of L2 cells (inclusive)
+  int xlo[3], xhi[3];  // cells searched before: left out (none when xlo[0] > xhi[0])
+  float bound_d;       // L1 cells farther than this (squared) are skipped
+  int mode;
+  bool own_first;      // KQ_SCAN: the cell own[] goes to list position 0 and is counted in n_own
+  int own[3];
+  // KQ_NEAREST_L1: the occupied L1 cell of the box nearest to the query among those behind (after_d, after_id)
+  float after_d;
+  int after_id;
+  // results
+  int count;           // points in the swept cells
+  int n_own;
+  float best_d;        // KQ_NEAREST_L1: squared distance, id and L2 origin of the cell found (best_id < 0: none)
+  int best_id, best_o[3];
+};
+
+// Phase A of one sweep (see the header).  KQ_SCAN: segments to the list; when own_first, scanning is left to the
+// caller (kq_scan over the list: position 0 = the own cell, possibly empty, then `nseg - 1` others) as long as the
+// list does not overflow.  Returns the number of list entries that are waiting to be scanned.
+HD int kq_collect(const MapView& mv, const MapDev& md, const KqList& li, float qx, float qy, float qz, KqSweep& sw,
+                  KqTop& top, bool dedup, int& pending) {
+  int nseg = 0;
+  pending = 0;
+  sw.count = 0;
+  sw.n_own = 0;
+  sw.best_id = -1;
+  sw.best_d = 3.0e38f;
+  const bool excl = sw.xlo[0] <= sw.xhi[0];
+  if (sw.mode == KQ_SCAN && sw.own_first) {  // position 0 is the own cell's (empty until found)
+    li.seg[0] = 0;
+    li.seg[li.stride] = 0;
+    nseg = 1;
+  }
+  for (int cz = sw.lo[2] >> 4; cz <= (sw.hi[2] >> 4); ++cz)
+    for (int cy = sw.lo[1] >> 4; cy <= (sw.hi[1] >> 4); ++cy)
+      for (int cx = sw.lo[0] >> 4; cx <= (sw.hi[0] >> 4); ++cx) {
+        KG_STAT(0, 1);
+        const CellRec* rec = find_cell(mv, md, cx - md.min_c[0], cy - md.min_c[1], cz - md.min_c[2]);
+        if (!rec) continue;
+        const unsigned long long m1 = KG_LD(&rec->mask);
+        const int fine_base = KG_LD(&rec->fine_base);
+        // L1 cells of this L0 cell that the box touches, without those that lie inside the excluded box
+        unsigned long long sel1 = m1 & kq_box_mask((sw.lo[0] >> 2) - (cx << 2), (sw.hi[0] >> 2) - (cx << 2),
+                                                   (sw.lo[1] >> 2) - (cy << 2), (sw.hi[1] >> 2) - (cy << 2),
+                                                   (sw.lo[2] >> 2) - (cz << 2), (sw.hi[2] >> 2) - (cz << 2));
+        if (excl)
+          sel1 &= ~kq_box_mask(((sw.xlo[0] + 3) >> 2) - (cx << 2), ((sw.xhi[0] + 1) >> 2) - 1 - (cx << 2),
+                               ((sw.xlo[1] + 3) >> 2) - (cy << 2), ((sw.xhi[1] + 1) >> 2) - 1 - (cy << 2),
+                               ((sw.xlo[2] + 3) >> 2) - (cz << 2), ((sw.xhi[2] + 1) >> 2) - 1 - (cz << 2));
+        while (sel1) {
+          const int f1 = kq_ffs64(sel1);
+          sel1 &= sel1 - 1ull;
+          // origin of the L1 cell in L2 coordinates
+          const int ox = ((cx << 2) | (f1 & 3)) << 2, oy = ((cy << 2) | ((f1 >> 2) & 3)) << 2,
+                    oz = ((cz << 2) | (f1 >> 4)) << 2;
+          const float cd = box_d2(qx, qy, qz, ox >> 2, oy >> 2, oz >> 2, 0.25f);
+          if (cd > sw.bound_d) continue;
+          if (sw.mode == KQ_NEAREST_L1) {
+            // (distance, id) orders the cells; id = position in a 16^3 block of L1 cells around the box corner
+            const int id = ((((oz >> 2) - (sw.lo[2] >> 2)) & 15) << 8) | ((((oy >> 2) - (sw.lo[1] >> 2)) & 15) << 4) |
+                           (((ox >> 2) - (sw.lo[0] >> 2)) & 15);
+            const bool behind = cd > sw.after_d || (cd == sw.after_d && id > sw.after_id);
+            const bool better = cd < sw.best_d || (cd == sw.best_d && id < sw.best_id);
+            if (behind && better) {
+              sw.best_d = cd;
+              sw.best_id = id;
+              sw.best_o[0] = ox, sw.best_o[1] = oy, sw.best_o[2] = oz;
+            }
+            continue;
+          }
+          KG_STAT(1, 1);
+          KQ_CHECK(fine_base >= 0 && fine_base <= md.n, 3, fine_base, f1, md.n) 0;
+          const L1Rec lr = ld_l1(mv, fine_base + KG_POPC64(m1 & kq_below(f1)));
+          unsigned long long sel2 = lr.mask & kq_box_mask(sw.lo[0] - ox, sw.hi[0] - ox, sw.lo[1] - oy, sw.hi[1] - oy,
+                                                          sw.lo[2] - oz, sw.hi[2] - oz);
+          if (excl)
+            sel2 &= ~kq_box_mask(sw.xlo[0] - ox, sw.xhi[0] - ox, sw.xlo[1] - oy, sw.xhi[1] - oy, sw.xlo[2] - oz,
+                                 sw.xhi[2] - oz);
+          if (sw.mode == KQ_SCAN && sw.own_first) {
+            // the own cell, if it lies in this L1 cell and is occupied, is taken out of the runs: position 0
+            const int rx = sw.own[0] - ox, ry = sw.own[1] - oy, rz = sw.own[2] - oz;
+            if ((unsigned)rx < 4u && (unsigned)ry < 4u && (unsigned)rz < 4u) {
+              const int f2 = (rz << 4) | (ry << 2) | rx;
+              if ((sel2 >> f2) & 1ull) {
+                sel2 &= ~(1ull << f2);
+                const int b = lr.first + KG_POPC64(lr.mask & kq_below(f2));
+                const int s = KG_LD(&mv.l2_start[b]);
+                const int e = KG_LD(&mv.l2_start[b + 1]);
+                li.seg[0] = s;
+                li.seg[li.stride] = e;
+                sw.n_own = e - s;
+                sw.count += e - s;
+                pending += e - s;
+              }
+            }
+          }
+          while (sel2) {
+            // a run: selected cells with no occupied unselected cell between them are contiguous in `sorted`
+            const int lb = kq_ffs64(sel2);
+            const unsigned long long gap = lr.mask & ~sel2 & ~kq_below(lb);
+            const unsigned long long run = gap ? (sel2 & kq_below(kq_ffs64(gap))) : sel2;
+            sel2 &= ~run;
+            const int b0 = lr.first + KG_POPC64(lr.mask & kq_below(lb));
+            KQ_CHECK(b0 >= 0 && b0 + KG_POPC64(run) <= 2 * md.n, 4, b0, lr.first, (int)KG_POPC64(run)) 0;
+            const int s = KG_LD(&mv.l2_start[b0]);
+            const int e = KG_LD(&mv.l2_start[b0 + KG_POPC64(run)]);
+            KQ_CHECK(s >= 0 && s < e && e <= md.n, 5, s, e, b0) 0;
+            sw.count += e - s;
+            KG_STAT(3, 1);
+            if (sw.mode == KQ_SCAN) {
+              if (nseg == KQ_SEG_CAP) {  // rare: a long list is scanned in pieces (the own-cell choice is off then)
+                kq_scan(mv, li, (sw.own_first && sw.n_own == 0) ? 1 : 0, pending, qx, qy, qz, top, dedup);
+                sw.own_first = false;
+                nseg = 0;
+                pending = 0;
+              }
+              li.seg[(2 * nseg) * li.stride] = s;
+              li.seg[(2 * nseg + 1) * li.stride] = e;
+              ++nseg;
+              pending += e - s;
+            }
+          }
         }
       }
-#pragma unroll
-      for (int d = G >> 1; d > 0; d >>= 1) {
-        const unsigned long long o = x.shfl_xor64(m, d);
-        m = o < m ? o : m;
-      }
-      res[r] = m;
-      last = m;
-    }
-  }
-  x.sync();  // every lane has read what it needs of acc[]
-  if (small) {
-    if (x.l < n && rank < 5) s->acc[rank] = mine;
-  } else if (x.l == 0) {
-#pragma unroll
-    for (int r = 0; r < 5; ++r)
-      if (r < n) s->acc[r] = res[r];
-  }
-  x.sync();
-  if (n > 5) n = 5;
+  return nseg;
 }
 
-// ---- sweep ---------------------------------------------------------------------------------------------------------
-// Per-group search state (every lane of a group holds the same values).
-struct KgState {
-  float qx, qy, qz;
-  int lo[3], hi[3];              // box of absolute L2 cells to visit (inclusive)
-  bool active;                   // this group takes part in the sweep
-  bool rows;                     // tasks are (z,y) rows of L2 cells (else whole L1 cells)
-  bool ball;                     // bound_d is valid: skip cells farther than it
-  float bound_d;                 // squared radius for pruning (the distance part of bound_key, or 1.0)
-  unsigned long long bound_key;  // accept keys <= bound_key
-  int nacc;                      // keys in acc[]
+// L2 cells of the bounding box of the ball of squared radius d2 around q: exact edges (fp64), radius slightly widened
+HD void kq_ball_box(float qx, float qy, float qz, float d2, int lo[3], int hi[3]) {
+  const double rad = (double)(sqrtf(d2) * 1.0001f + 1.0e-6f) * 16.0;
+  const double c[3] = {(double)qx * 16.0, (double)qy * 16.0, (double)qz * 16.0};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    lo[k] = (int)floor(c[k] - rad);
+    hi[k] = (int)floor(c[k] + rad);
+  }
+}
+
+// everything outside the box [lo, hi] of L2 cells is at least sqrt(result) away from q (differences rounded like a
+// point's coordinate differences: a comparison with a point's distance is safe under monotonic rounding)
+HD float kq_gap2(const float q[3], const int lo[3], const int hi[3]) {
+  float gap = 3.0e38f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float g0 = q[k] - (float)lo[k] * 0.0625f, g1 = (float)(hi[k] + 1) * 0.0625f - q[k];
+    gap = fminf(gap, fminf(g0, g1));
+  }
+  return gap > 0.0f ? gap * gap : 0.0f;
+}
+
+enum {
+  KQ_ST_START = 0,   // the 27 L2 cells around the query, the own cell first
+  KQ_ST_BALL = 1,    // the ball of the known bound, minus what was searched
+  KQ_ST_GROW = 2,    // sparse: count a larger box
+  KQ_ST_SHELL = 3,   // sparse: scan the box that holds five points (few points)
+  KQ_ST_FIND = 4,    // sparse: the box holds many points — find the nearest L1 cell not scanned yet
+  KQ_ST_CELL = 5,    // sparse: scan that L1 cell
+  KQ_ST_LAST = 6,    // sparse: the ball of the bound, everything (duplicates filtered)
+  KQ_ST_DONE = 7
 };
+constexpr int KQ_SHELL_MAX = 96;  // a grown box with more points than this is searched cell by cell, nearest first
 
-// scan the collected segments of every group: flatten, stride over the candidates, accept, compress when full
-template <class X>
-HD void kg_scan_segments(const X& x, const MapView& mv, KnnScratch* s, KgState& st, int& nseg) {
-  constexpr int G = X::G;
-  // exclusive prefix of the segment lengths, in place
-  int run = 0;
-  for (int i0 = 0; x.any(i0 < nseg); i0 += G) {
-    const int i = i0 + x.l;
-    const int len = (i < nseg) ? s->seg_pre[i] : 0;
-    int inc = len;
+// Exact 5-NN within squared radius 1.0 of one query.  seed = nullptr: no prior knowledge; otherwise the keys of five
+// distinct map points (any order) believed to be near the query.  Returns n <= 5 and the n nearest keys,
+// ascending, in top.k[0, n); n < 5: fewer than five points within the radius (the callers reject such a query).
+//
+// Every step is one sweep (phase A + phase B) at ONE call site, so that the lanes of a warp stay together whatever
+// state their queries are in.  Without a seed the search adapts to the density around the query:
+//   START  the 27 L2 cells around the query are collected; if the query's own cell holds five points only that cell is
+//          scanned, else all 27.  Five points in hand and nothing unsearched nearer than the 5th: done.
+//   BALL   else what the ball of the 5th distance holds beyond the searched box settles the answer.
+//   sparse (fewer than five points in the 27 cells): the box grows — points are only COUNTED — until it holds five.
+//          Few points: they are scanned (SHELL) and BALL finishes.  Many (a dense surface has entered the box, which a
+//          box does with a whole face): the L1 cells of the box are scanned nearest first (FIND, CELL) until five
+//          points are known, and the ball of that bound is swept once more with duplicates filtered (LAST).
+//
+// DEFER (the registration kernel): the sparse cases that cost a single thread a long chain of dependent loads —
+// no five points within 4 cells, or a dense surface inside the grown box — are not searched here: the function returns
+// -1 and the caller hands the query to the warp-cooperative search (kw_knn5).
+template <bool DEFER>
+HD int kq_knn5(const MapView& mv, const KqList& li, float qx, float qy, float qz, const unsigned long long* seed,
+               KqTop& top) {
+  const MapDev md = *mv.dev;
+  kq_top_reset(top, KG_KEY_LT_1 + 1ull);
+  if (!(md.n > 0) || !(fabsf(qx) < 2.0e5f && fabsf(qy) < 2.0e5f && fabsf(qz) < 2.0e5f)) return 0;
+  // absolute L2 cell coordinates of the query (x16 is exact in fp32)
+  const int a[3] = {(int)floorf(qx * 16.0f), (int)floorf(qy * 16.0f), (int)floorf(qz * 16.0f)};
+  const float q[3] = {qx, qy, qz};
+  KqSweep sw;
+  sw.xlo[0] = 1, sw.xhi[0] = 0;  // nothing searched yet
+  sw.xlo[1] = sw.xlo[2] = sw.xhi[1] = sw.xhi[2] = 0;
+  sw.bound_d = 1.0f;
+  sw.mode = KQ_SCAN;
+  sw.own_first = false;
+  sw.after_d = -1.0f;
+  sw.after_id = -1;
 #pragma unroll
-    for (int d = 1; d < G; d <<= 1) {
-      const int t = x.shfl_up(inc, d);
-      if (x.l >= d) inc += t;
-    }
-    if (i < nseg) s->seg_pre[i] = run + inc - len;
-    run += x.shfl(inc, G - 1);
+  for (int k = 0; k < 3; ++k) sw.own[k] = a[k];
+  int state;
+  bool dedup = false;
+  int total = 0;  // points in the boxes swept so far
+  int grow = 0;   // sparse: next box width to try
+  int glo[3] = {0, 0, 0}, ghi[3] = {0, 0, 0};  // sparse: the box that holds five points
+  bool seeded = false;
+  if (seed != nullptr) {
+    // the five seeds ARE the list to beat: the sweep of their ball only inserts what is nearer than one of them (between
+    // two outer iterations the pose moves by millimetres and hardly anything is); the sweep meets the seeds again
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (seed[k] < top.k[4]) kq_insert(top, seed[k], false);
+    seeded = top.n == 5;  // a seed beyond the search radius is no bound
+    if (!seeded) kq_top_reset(top, KG_KEY_LT_1 + 1ull);
   }
-  if (x.l == 0) s->seg_pre[nseg] = run;
-  x.sync();
-  const int total = run;
-  KG_STAT(2, (x.l == 0) ? total : 0);
-  int j = 0;
-  for (int c0 = 0; x.any(c0 < total); c0 += G) {
-    const int c = c0 + x.l;
-    bool pass = false;
-    unsigned long long key = 0ull;
-    if (c < total) {
-      while (c >= s->seg_pre[j + 1]) ++j;
-      const float4 m = KG_LD(&mv.sorted[s->seg_s[j] + (c - s->seg_pre[j])]);
-      const float dx = m.x - st.qx, dy = m.y - st.qy, dz = m.z - st.qz;
-      float r = dx * dx;
-      r = r + dy * dy;
-      r = r + dz * dz;
-      key = kg_key(r, (int)f2u(m.w));
-      pass = key <= st.bound_key;
-    }
-    const unsigned gb = x.ballot(pass);
-    if (pass) s->acc[st.nacc + KG_POPC32(gb & ((1u << x.l) - 1u))] = key;
-    st.nacc += KG_POPC32(gb);
-    if (x.any(st.nacc > KG_ACC_CAP - G)) {
-      // a list about to overflow is cut to its five smallest keys; their largest is the new bound
-      x.sync();
-      const bool cut = st.nacc > KG_ACC_CAP - G;
-      int n = cut ? st.nacc : 0;
-      kg_select5(x, s, n);
-      if (cut) {
-        st.nacc = n;
-        st.bound_key = s->acc[4];
-        st.bound_d = kg_key_d2(st.bound_key);
-        st.ball = true;
+  if (seeded) {
+    state = KQ_ST_BALL;
+    dedup = true;
+    sw.bound_d = top.d4;
+    kq_ball_box(qx, qy, qz, sw.bound_d, sw.lo, sw.hi);
+  } else {
+    state = KQ_ST_START;
+    sw.own_first = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sw.lo[k] = a[k] - 1, sw.hi[k] = a[k] + 1;
+  }
+  while (state != KQ_ST_DONE) {
+    KG_STAT(8 + state, 1);
+    int pending = 0;
+    const int nseg = kq_collect(mv, md, li, qx, qy, qz, sw, top, dedup, pending);
+    if (sw.mode == KQ_SCAN) {
+      int first = 0;
+      bool own_only = false;
+      if (sw.own_first) {  // START, list intact: the own cell alone if it holds five points
+        own_only = sw.n_own >= 5;
+        first = sw.n_own > 0 ? 0 : 1;
+        if (own_only) pending = sw.n_own;
       }
-      KG_STAT(5, (x.l == 0 && cut) ? 1 : 0);
+      if (nseg > first) kq_scan(mv, li, first, pending, qx, qy, qz, top, dedup);
+      if (state == KQ_ST_START) {
+        // searched: the own cell or the 27 cells
+        const int w = own_only ? 0 : 1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sw.xlo[k] = a[k] - w, sw.xhi[k] = a[k] + w;
+        total = own_only ? sw.n_own : sw.count;
+        sw.own_first = false;
+      }
+    }
+    // ---- transitions
+    if (state == KQ_ST_BALL || state == KQ_ST_LAST) {
+      state = KQ_ST_DONE;  // exhaustive
+    } else if (state == KQ_ST_START || state == KQ_ST_SHELL) {
+      if (state == KQ_ST_SHELL) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sw.xlo[k] = sw.lo[k], sw.xhi[k] = sw.hi[k];
+      }
+      if (top.n == 5) {
+        if (top.d4 < kq_gap2(q, sw.xlo, sw.xhi)) {
+          state = KQ_ST_DONE;  // nothing outside the searched box can be nearer than the 5th
+        } else {
+          state = KQ_ST_BALL;
+          sw.mode = KQ_SCAN;
+          sw.bound_d = top.d4;
+          kq_ball_box(qx, qy, qz, top.d4, sw.lo, sw.hi);
+        }
+      } else if (state == KQ_ST_START) {
+        state = KQ_ST_GROW;
+        sw.mode = KQ_COUNT;
+        grow = 2;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sw.lo[k] = a[k] - grow, sw.hi[k] = a[k] + grow;
+      } else {
+        // the shell was scanned and still fewer than five points are within the radius 1.0: cannot happen while the
+        // counted points lie within it; a box that reaches beyond the radius can hold points that do not count
+        state = KQ_ST_LAST;
+        dedup = true;
+        sw.mode = KQ_SCAN;
+        sw.xlo[0] = 1, sw.xhi[0] = 0;
+        sw.bound_d = 1.0f;
+        kq_ball_box(qx, qy, qz, 1.0f, sw.lo, sw.hi);
+      }
+    } else if (state == KQ_ST_GROW) {
+      total += sw.count;
+      if (DEFER && ((total < 5 && grow >= 4) || total - top.n > KQ_SHELL_MAX)) return -1;
+      if (total >= 5 || grow >= 16) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) glo[k] = sw.lo[k], ghi[k] = sw.hi[k];
+        // the counted box becomes the searched one after the next step; what START searched stays left out
+        if (total - top.n <= KQ_SHELL_MAX) {
+          state = KQ_ST_SHELL;
+          sw.mode = KQ_SCAN;  // box = the counted box, minus START's
+        } else {
+          state = KQ_ST_FIND;
+          sw.mode = KQ_NEAREST_L1;
+          sw.xlo[0] = 1, sw.xhi[0] = 0;  // whole L1 cells from here on, duplicates filtered
+          dedup = true;
+          sw.after_d = -1.0f;
+          sw.after_id = -1;
+          if (DEFER) return -1;  // not reached (deferred above): lets the compiler drop the cell-by-cell states
+        }
+      } else {
+        // next width: 2, 3, 4, 6, 8, 12, 16; the box counted so far is left out of the next count
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sw.xlo[k] = sw.lo[k], sw.xhi[k] = sw.hi[k];
+        grow = grow < 4 ? grow + 1 : (grow == 4 ? 6 : (grow == 6 ? 8 : (grow == 8 ? 12 : 16)));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sw.lo[k] = a[k] - grow, sw.hi[k] = a[k] + grow;
+      }
+      if (state == KQ_ST_SHELL) {
+        // leave out what START searched (the 27 cells), not the boxes that were only counted
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sw.xlo[k] = a[k] - 1, sw.xhi[k] = a[k] + 1;
+      }
+    } else if (DEFER) {
+      return -1;  // not reached
+    } else if (state == KQ_ST_FIND) {
+      if (sw.best_id < 0) {
+        // no cell left in the box: sweep the search radius
+        state = KQ_ST_LAST;
+        sw.mode = KQ_SCAN;
+        sw.bound_d = top.n == 5 ? top.d4 : 1.0f;
+        kq_ball_box(qx, qy, qz, sw.bound_d, sw.lo, sw.hi);
+      } else {
+        state = KQ_ST_CELL;
+        sw.mode = KQ_SCAN;
+        sw.after_d = sw.best_d;
+        sw.after_id = sw.best_id;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sw.lo[k] = sw.best_o[k], sw.hi[k] = sw.best_o[k] + 3;
+      }
+    } else {  // KQ_ST_CELL
+      if (top.n == 5) {
+        state = KQ_ST_LAST;
+        sw.mode = KQ_SCAN;
+        sw.bound_d = top.d4;
+        kq_ball_box(qx, qy, qz, top.d4, sw.lo, sw.hi);
+      } else {
+        state = KQ_ST_FIND;
+        sw.mode = KQ_NEAREST_L1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sw.lo[k] = glo[k], sw.hi[k] = ghi[k];
+      }
     }
   }
-  x.sync();
-  nseg = 0;
+  return top.n;
 }
+// ---- the sparse cases, searched by a whole warp -------------------------------------------------------------------
+// One query per warp: best-first over the occupied L1 cells within the search radius.  Every load a single thread
+// would chain (27 hash probes, one L1 record and two cell starts per L1 cell) is issued by its own lane.
+//   1  lanes 0..26 probe the 27 L0 cells the ball of radius 1 can touch;
+//   2  the occupied L1 cells of those cells become items in shared memory (prefix sum over the lanes);
+//   3  every lane takes items: distance of the cell's box to the query, and — if that is inside the radius — the
+//      cell's point range (L1 record, first and last L2 start);
+//   4  until no unscanned item is nearer than the 5th neighbour so far: the nearest item (warp minimum) is scanned,
+//      32 points per step; candidates that beat the 5th key are inserted by all lanes alike (every lane holds the same
+//      five keys).
+// Exact: a cell's box distance never exceeds the distance of a point inside it (knn.cuh header).
+constexpr int KW_ITEM_CAP = 512;
+struct KwScratch {  // per warp
+  float cd[KW_ITEM_CAP];  // squared box distance of the item's L1 cell; KW_NONE: scanned or outside the radius
+  int a[KW_ITEM_CAP];     // step 2: L1 record index; step 3 on: first point
+  int b[KW_ITEM_CAP];     // step 2: packed cell coordinates; step 3 on: number of points
+};
+constexpr float KW_NONE = 3.0e38f;
 
-// one sweep over the box of every active group
-template <class X>
-HD void kg_sweep(const X& x, const MapView& mv, const MapDev& md, KnnScratch* s, KgState& st) {
-  constexpr int G = X::G;
-  // L0 cells the box touches (at most 3 per axis)
-  int c0[3], n0[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    c0[a] = st.lo[a] >> 4;
-    n0[a] = (st.hi[a] >> 4) - c0[a] + 1;
+#if defined(__CUDACC__)
+struct Warp32 {  // executor of the device
+  int lane;
+  __device__ Warp32() : lane(threadIdx.x & 31) {}
+  __device__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+  __device__ int shfl(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ int shfl_up(int v, int d) const { return __shfl_up_sync(0xffffffffu, v, d); }
+  __device__ unsigned long long shfl64(unsigned long long v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ unsigned long long shfl_xor64(unsigned long long v, int d) const {
+    return __shfl_xor_sync(0xffffffffu, v, d);
   }
-  const int n0_all = st.active ? n0[0] * n0[1] * n0[2] : 0;
-  const float inv_n0xy = 1.0f / (float)(n0[0] * n0[1] > 0 ? n0[0] * n0[1] : 1);
-  const float inv_n0x = 1.0f / (float)(n0[0] > 0 ? n0[0] : 1);
-  int nseg = 0;
-  int i0 = -1;             // current L0 cell of the box
-  int ntasks = 0, t0 = 0;  // tasks of the current L0 cell, next task round
-  // state of the current L0 cell
+  __device__ void sync() const { __syncwarp(); }
+};
+#endif
+
+// all 32 lanes call with the same arguments; on return every lane holds the same `top`.  Returns top.n, or -1 when the
+// surroundings hold more occupied L1 cells than the item list (the caller falls back to the per-thread search).
+template <class X>
+HD int kw_knn5(const X& x, const MapView& mv, KwScratch* s, float qx, float qy, float qz, KqTop& top) {
+  const MapDev md = *mv.dev;
+  kq_top_reset(top, KG_KEY_LT_1 + 1ull);
+  if (!(md.n > 0) || !(fabsf(qx) < 2.0e5f && fabsf(qy) < 2.0e5f && fabsf(qz) < 2.0e5f)) return 0;
+  const int c0[3] = {(int)floorf(qx), (int)floorf(qy), (int)floorf(qz)};
+  // 1: one L0 cell per lane
   unsigned long long m1 = 0ull;
   int fine_base = 0;
-  int slo[3] = {0, 0, 0}, shi[3] = {0, 0, 0};
-  int na = 1, nb = 1;                // rows: L1 parts per row, rows per layer; cells: L1 cells per row, per layer
-  float inv_na = 1.0f, inv_nb = 1.0f, inv_nab = 1.0f;
-  bool tasks_done = false;
+  const int dx = x.lane % 3 - 1, dy = (x.lane / 3) % 3 - 1, dz = x.lane / 9 - 1;
+  if (x.lane < 27) {
+    const CellRec* rec =
+        find_cell(mv, md, c0[0] + dx - md.min_c[0], c0[1] + dy - md.min_c[1], c0[2] + dz - md.min_c[2]);
+    if (rec) {
+      m1 = KG_LD(&rec->mask);
+      fine_base = KG_LD(&rec->fine_base);
+    }
+  }
+  // 2: items
+  const int cnt = KG_POPC64(m1);
+  int inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = x.shfl_up(inc, d);
+    if (x.lane >= d) inc += t;
+  }
+  const int total = x.shfl(inc, 31);
+  if (total > KW_ITEM_CAP) return -1;
+  {
+    int at = inc - cnt, r = 0;
+    unsigned long long m = m1;
+    while (m) {
+      const int f1 = kq_ffs64(m);
+      m &= m - 1ull;
+      s->a[at] = fine_base + r;
+      // L1 coordinates relative to the corner of the 3x3x3 block of L0 cells: 0..11 per axis
+      s->b[at] = ((((dz + 1) << 2) | (f1 >> 4)) << 8) | ((((dy + 1) << 2) | ((f1 >> 2) & 3)) << 4) |
+                 (((dx + 1) << 2) | (f1 & 3));
+      ++at;
+      ++r;
+    }
+  }
+  x.sync();
+  // 3: distance and point range of every item
+  for (int k = x.lane; k < total; k += 32) {
+    const int pk = s->b[k];
+    const int lx = ((c0[0] - 1) << 2) + (pk & 15), ly = ((c0[1] - 1) << 2) + ((pk >> 4) & 15),
+              lz = ((c0[2] - 1) << 2) + (pk >> 8);
+    float cd = box_d2(qx, qy, qz, lx, ly, lz, 0.25f);
+    int ps = 0, np = 0;
+    if (cd < 1.0f) {
+      const L1Rec lr = ld_l1(mv, s->a[k]);
+      ps = KG_LD(&mv.l2_start[lr.first]);
+      np = KG_LD(&mv.l2_start[lr.first + KG_POPC64(lr.mask)]) - ps;
+    } else {
+      cd = KW_NONE;
+    }
+    s->cd[k] = cd;
+    s->a[k] = ps;
+    s->b[k] = np;
+  }
+  x.sync();
+  // 4: best first
   while (true) {
-    if (!tasks_done) {
-      if (!x.any(t0 < ntasks)) {
-        // every group has dealt out the tasks of its current L0 cell: on to the next one
-        ++i0;
-        if (!x.any(i0 < n0_all)) {
-          tasks_done = true;
-        } else {
-          ntasks = 0;
-          t0 = 0;
-          if (i0 < n0_all) {
-            const int iz = div_small(i0, inv_n0xy);
-            const int rem = i0 - iz * (n0[0] * n0[1]);
-            const int iy = div_small(rem, inv_n0x);
-            const int cx = c0[0] + (rem - iy * n0[0]), cy = c0[1] + iy, cz = c0[2] + iz;
-            bool ok = true;
-            if (st.ball) ok = !(box_d2(st.qx, st.qy, st.qz, cx, cy, cz, 1.0f) > st.bound_d);
-            const CellRec* rec = ok ? find_cell(mv, md, cx - md.min_c[0], cy - md.min_c[1], cz - md.min_c[2]) : nullptr;
-            KG_STAT(0, (x.l == 0) ? 1 : 0);
-            if (rec) {
-              m1 = KG_LD(&rec->mask);
-              fine_base = KG_LD(&rec->fine_base);
-              const int cc[3] = {cx, cy, cz};
-#pragma unroll
-              for (int a = 0; a < 3; ++a) {
-                slo[a] = st.lo[a] > (cc[a] << 4) ? st.lo[a] : (cc[a] << 4);
-                shi[a] = st.hi[a] < (cc[a] << 4) + 15 ? st.hi[a] : (cc[a] << 4) + 15;
-              }
-              if (st.rows) {
-                na = (shi[0] >> 2) - (slo[0] >> 2) + 1;  // L1 cells the x-run crosses
-                nb = shi[1] - slo[1] + 1;                // rows per z layer
-                ntasks = na * nb * (shi[2] - slo[2] + 1);
-              } else {
-                na = (shi[0] >> 2) - (slo[0] >> 2) + 1;
-                nb = (shi[1] >> 2) - (slo[1] >> 2) + 1;
-                ntasks = na * nb * ((shi[2] >> 2) - (slo[2] >> 2) + 1);
-              }
-              inv_na = 1.0f / (float)na;
-              inv_nb = 1.0f / (float)nb;
-              inv_nab = 1.0f / (float)(na * nb);
-            }
-          }
-        }
-      } else {
-        // one round of tasks: lane l takes task t0 + l of its group
-        const int t = t0 + x.l;
-        t0 += G;
-        int seg_s = 0, seg_n = 0;
-        if (t < ntasks) {
-          KG_STAT(1, 1);
-          if (st.rows) {
-            const int r = div_small(t, inv_na), p = t - r * na;
-            const int zz = div_small(r, inv_nb);
-            const int y = slo[1] + (r - zz * nb), z = slo[2] + zz;
-            int xa = slo[0], xb = shi[0];
-            bool ok = true;
-            if (st.ball) {
-              const float gz = axis_gap(st.qz, z, 0.0625f), gy = axis_gap(st.qy, y, 0.0625f);
-              const float g2 = gy * gy + gz * gz;  // lower bound: the y and z terms of a point distance
-              ok = !(g2 > st.bound_d);
-              if (ok) {
-                // x extent of the ball in this row (slightly widened; a superset is always correct)
-                const float rem = st.bound_d - g2;
-                const float rx = sqrtf(rem > 0.0f ? rem : 0.0f) * 1.0001f + 1.0e-6f;
-                const int bx0 = (int)floorf((st.qx - rx) * 16.0f), bx1 = (int)floorf((st.qx + rx) * 16.0f);
-                xa = bx0 > xa ? bx0 : xa;
-                xb = bx1 < xb ? bx1 : xb;
-              }
-            }
-            const int lx = (slo[0] >> 2) + p;  // absolute L1 x of this part of the row
-            const int xlo = xa > (lx << 2) ? xa : (lx << 2);
-            const int xhi = xb < (lx << 2) + 3 ? xb : (lx << 2) + 3;
-            ok = ok && xlo <= xhi;
-            const int f1 = (((z >> 2) & 3) << 4) | (((y >> 2) & 3) << 2) | (lx & 3);
-            ok = ok && ((m1 >> f1) & 1ull);
-            if (ok) {
-              const L1Rec lr = ld_l1(mv, fine_base + KG_POPC64(m1 & ((1ull << f1) - 1ull)));
-              const int row2 = ((z & 3) << 4) | ((y & 3) << 2);
-              const int flo = row2 | (xlo & 3), fhi = row2 | (xhi & 3);
-              const unsigned long long below = (1ull << flo) - 1ull;
-              const unsigned long long sub = lr.mask & ((2ull << fhi) - 1ull) & ~below;
-              if (sub) {
-                const int b = lr.first + KG_POPC64(lr.mask & below);
-                seg_s = KG_LD(&mv.l2_start[b]);
-                seg_n = KG_LD(&mv.l2_start[b + KG_POPC64(sub)]) - seg_s;
-              }
-            }
-          } else {
-            const int iz = div_small(t, inv_nab);
-            const int rem = t - iz * (na * nb);
-            const int iy = div_small(rem, inv_na);
-            const int lx = (slo[0] >> 2) + (rem - iy * na), ly = (slo[1] >> 2) + iy, lz = (slo[2] >> 2) + iz;
-            const int f1 = ((lz & 3) << 4) | ((ly & 3) << 2) | (lx & 3);
-            bool ok = (m1 >> f1) & 1ull;
-            if (ok && st.ball) ok = !(box_d2(st.qx, st.qy, st.qz, lx, ly, lz, 0.25f) > st.bound_d);
-            if (ok) {
-              const L1Rec lr = ld_l1(mv, fine_base + KG_POPC64(m1 & ((1ull << f1) - 1ull)));
-              seg_s = KG_LD(&mv.l2_start[lr.first]);
-              seg_n = KG_LD(&mv.l2_start[lr.first + KG_POPC64(lr.mask)]) - seg_s;
-            }
-          }
-        }
-        const bool has = seg_n > 0;
-        const unsigned gb = x.ballot(has);
-        if (has) {
-          const int at = nseg + KG_POPC32(gb & ((1u << x.l) - 1u));
-          s->seg_s[at] = seg_s;
-          s->seg_pre[at] = seg_n;
-        }
-        nseg += KG_POPC32(gb);
+    unsigned long long best = ~0ull;  // (distance bits, item): box distances are >= 0
+    for (int k = x.lane; k < total; k += 32) {
+      const float cd = s->cd[k];
+      if (cd != KW_NONE) {
+        const unsigned long long key = kg_key(cd, k);
+        best = key < best ? key : best;
       }
     }
-    if (tasks_done || x.any(nseg > KG_SEG_CAP - G)) {
-      x.sync();
-      kg_scan_segments(x, mv, s, st, nseg);
-      if (tasks_done) break;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long o = x.shfl_xor64(best, d);
+      best = o < best ? o : best;
     }
-  }
-}
-
-// ---- the search ----------------------------------------------------------------------------------------------------
-// Exact 5-NN within squared radius 1.0 of one query per group.  seed_key = 0: no prior knowledge; otherwise an
-// inclusive upper bound of the 5th key (five map points are known to have keys <= seed_key).  On return acc[0, n)
-// holds the n <= 5 nearest keys, ascending; n < 5: fewer than five points within the radius (callers reject).
-template <class X>
-HD int kg_knn5(const X& x, const MapView& mv, KnnScratch* s, float qx, float qy, float qz, bool active,
-               unsigned long long seed_key) {
-  const MapDev md = *mv.dev;
-  KgState st;
-  st.qx = qx;
-  st.qy = qy;
-  st.qz = qz;
-  st.nacc = 0;
-  if (!(md.n > 0) || !(fabsf(qx) < 2.0e5f && fabsf(qy) < 2.0e5f && fabsf(qz) < 2.0e5f)) active = false;
-  // absolute L2 cell coordinates of the query (x16 is exact in fp32)
-  const int a[3] = {active ? (int)floorf(qx * 16.0f) : 0, active ? (int)floorf(qy * 16.0f) : 0,
-                    active ? (int)floorf(qz * 16.0f) : 0};
-  const float q[3] = {qx, qy, qz};
-#pragma unroll
-  for (int k = 0; k < 3; ++k) st.lo[k] = st.hi[k] = 0;
-  int state = active ? KG_START : KG_DONE;
-  st.bound_key = KG_KEY_LT_1;
-  st.bound_d = 1.0f;
-  if (active && seed_key != 0ull && seed_key <= KG_KEY_LT_1) {  // a seed beyond the search radius is no bound
-    state = KG_BALL;
-    st.bound_key = seed_key;
-    st.bound_d = kg_key_d2(seed_key);
-  }
-  int n_res = 0;
-  while (x.any(state != KG_DONE)) {
-    st.active = state != KG_DONE;
-    st.nacc = 0;
-    if (state == KG_START) {
-      // the 27 L2 cells around the query, no prior bound
-      st.rows = true;
-      st.ball = false;
-      st.bound_key = KG_KEY_LT_1;
-      st.bound_d = 1.0f;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        st.lo[k] = a[k] - 1;
-        st.hi[k] = a[k] + 1;
+    if (best == ~0ull) break;
+    const float cd = kg_key_d2(best);
+    if (top.n == 5 && cd > top.d4) break;  // no unscanned cell can hold a point that beats the 5th
+    const int k = kg_key_id(best);
+    const int ps = s->a[k], np = s->b[k];
+    x.sync();  // every lane has read the item
+    if (x.lane == 0) s->cd[k] = KW_NONE;
+    for (int p0 = 0; p0 < np; p0 += 32) {
+      const int p = p0 + x.lane;
+      unsigned long long key = ~0ull;
+      if (p < np) {
+        const float4 m = KG_LD(&mv.sorted[ps + p]);
+        const float ex = m.x - qx, ey = m.y - qy, ez = m.z - qz;
+        float r = ex * ex;
+        r = r + ey * ey;
+        r = r + ez * ez;
+        key = kg_key(r, (int)f2u(m.w));
       }
-    } else if (state == KG_BALL) {
-      // five points are known within bound_key (inclusive): the cells the ball touches, rows while it is small
-      st.ball = true;
-      const float rad = sqrtf(st.bound_d) * 1.0001f + 1.0e-6f;
-      int w = 0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        st.lo[k] = (int)floorf((q[k] - rad) * 16.0f);
-        st.hi[k] = (int)floorf((q[k] + rad) * 16.0f);
-        w = st.hi[k] - st.lo[k] > w ? st.hi[k] - st.lo[k] : w;
-      }
-      st.rows = w <= 10;
-    } else if (state == KG_SPARSE1) {
-      // fewer than five points in the 27 L2 cells: the 27 L1 cells, whole cells
-      st.rows = false;
-      st.ball = false;
-      st.bound_key = KG_KEY_LT_1;
-      st.bound_d = 1.0f;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        st.lo[k] = ((a[k] >> 2) - 1) << 2;
-        st.hi[k] = (((a[k] >> 2) + 1) << 2) + 3;
-      }
-    } else if (state == KG_SPARSE2) {
-      // everything within the search radius
-      st.rows = false;
-      st.ball = true;
-      st.bound_key = KG_KEY_LT_1;
-      st.bound_d = 1.0f;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        st.lo[k] = (int)floorf((q[k] - 1.0f) * 16.0f);
-        st.hi[k] = (int)floorf((q[k] + 1.0f) * 16.0f);
-      }
-    }
-    KG_STAT(8 + (state < 4 ? state : 0), (x.l == 0 && state != KG_DONE) ? 1 : 0);
-    kg_sweep(x, mv, md, s, st);
-    int n = st.active ? st.nacc : 0;
-    kg_select5(x, s, n);
-    if (st.active) {
-      const bool full = n == 5;
-      const unsigned long long k5 = full ? s->acc[4] : 0ull;
-      const float d5 = kg_key_d2(k5);
-      n_res = n;
-      if (state == KG_START) {
-        if (!full) {
-          state = KG_SPARSE1;
-        } else if (d5 < 0.00390625f) {
-          state = KG_DONE;  // 5th distance < one L2 cell: nothing outside the 27 cells can be closer
-        } else {
-          state = KG_BALL;
-          st.bound_key = k5;
-          st.bound_d = d5;
-        }
-      } else if (state == KG_SPARSE1) {
-        if (!full) {
-          state = KG_SPARSE2;
-        } else if (d5 < 0.0625f) {
-          state = KG_DONE;  // 5th distance < one L1 cell: the 27 L1 cells hold every closer point
-        } else {
-          state = KG_BALL;
-          st.bound_key = k5;
-          st.bound_d = d5;
-        }
-      } else {
-        state = KG_DONE;  // KG_BALL and KG_SPARSE2 are exhaustive
+      unsigned pass = x.ballot(key < top.k[4]);
+      while (pass) {  // the same sequence of inserts in every lane
+        const int src = KG_FFS32(pass);
+        pass &= pass - 1u;
+        const unsigned long long kk = x.shfl64(key, src);
+        if (kk < top.k[4]) kq_insert(top, kk, false);
       }
     }
     x.sync();
   }
-  return n_res;
+  return top.n;
 }
 
 // five neighbours of one query as the fits read them (match.cu): ascending by (distance, index)
@@ -602,8 +789,17 @@ struct Top5 {
   HD bool full() const { return id[4] >= 0; }
 };
 
-// kernels that search: blocks of KG_BLOCK threads = KG_QPB queries in flight, one KnnScratch per group
+// kernels that search: blocks of KG_BLOCK threads, one query per thread, one segment list per lane in shared memory
 constexpr int KG_BLOCK = 128;
-constexpr int KG_QPB = KG_BLOCK / WarpGroup8::G;
+constexpr int KQ_SMEM_INTS = KG_BLOCK * 2 * KQ_SEG_CAP;  // per block
+#if defined(__CUDACC__)
+// the calling lane's list inside the block's array s_seg[KQ_SMEM_INTS]
+__device__ __forceinline__ KqList kq_list(int* s_seg) {
+  KqList li;
+  li.seg = s_seg + (threadIdx.x >> 5) * (32 * 2 * KQ_SEG_CAP) + (threadIdx.x & 31);
+  li.stride = 32;
+  return li;
+}
+#endif
 
 }  // namespace lm

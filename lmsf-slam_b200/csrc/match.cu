@@ -851,7 +851,8 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {  // work queues of the k_knn launch that follows
     st->knn_next = 0;
-    st->knn_next_heavy = 0;
+    st->defer_next = 0;
+    st->n_defer = 0;
   }
   const bool in_range = i < upper;
   const int n_e = counts[0], n_s = counts[1];
@@ -890,42 +891,10 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
   }
 }
 
-// one query per group of eight lanes, called by all 32 lanes of a warp: seed bound from the previous iteration's
-// neighbours (seeded launches), the search, the five indices to nbr[k * upper + t] (-1 x 5 unless five neighbours lie
-// within the search radius: both callers reject such a query)
-__device__ __forceinline__ void knn_one(const WarpGroup8& x, KnnScratch* s, const MapPair& maps, bool is_edge,
-                                        bool has_map, bool active, float wx, float wy, float wz, int seeded, int upper,
-                                        int t, int* __restrict__ nbr) {
-  unsigned long long seed_key = 0ull;
-  if (seeded) {
-    const float4* __restrict__ cat = is_edge ? maps.edge_cat : maps.surf_cat;
-    const int sid = (active && has_map && x.l < 5) ? nbr[x.l * upper + t] : -1;
-    unsigned long long k = 0ull;
-    if (sid >= 0) {
-      const float4 m = __ldg(&cat[sid]);
-      const float dx = m.x - wx, dy = m.y - wy, dz = m.z - wz;
-      float r = dx * dx;
-      r = r + dy * dy;
-      r = r + dz * dz;
-      k = kg_key(r, sid);
-    }
-    const unsigned okb = x.ballot(sid >= 0);
-#pragma unroll
-    for (int d = 4; d > 0; d >>= 1) {
-      const unsigned long long o = x.shfl_xor64(k, d);
-      k = o > k ? o : k;
-    }
-    if ((okb & 31u) == 31u) seed_key = k;
-  }
-  const int n = kg_knn5(x, is_edge ? maps.edge : maps.surf, s, wx, wy, wz, active && has_map, seed_key);
-  if (active && x.l < 5) nbr[x.l * upper + t] = (n == 5) ? kg_key_id(s->acc[x.l]) : -1;
-  x.sync();  // acc[] is read before the next search writes it
-}
-
-// exact 5-NN of every query, in processing order (t = position).  A query is searched by a group of eight lanes
-// (knn.cuh), four queries per warp.  Persistent warps pull chunks of consecutive positions from a device-side counter:
-// queries of sparse regions cost several times more than queries of dense ones and lie next to each other, so a
-// static block->query map leaves a long tail of heavy blocks.
+// exact 5-NN of every query, in processing order (t = position), one thread per query (knn.cuh).  Persistent warps pull
+// chunks of 32 consecutive positions from a device-side counter: queries of sparse regions cost several times more
+// than queries of dense ones and lie next to each other, so a static block->query map leaves a long tail of heavy
+// blocks.
 #ifndef KNN_MINBLOCKS
 #define KNN_MINBLOCKS 4
 #endif
@@ -937,49 +906,116 @@ __global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __re
                                              const float4* __restrict__ feat,
                                              const int* __restrict__ counts, SolveState* __restrict__ st,
                                              MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
-                                             int seeded, int assoc, int chunk, int* __restrict__ nbr) {
-  __shared__ KnnScratch scratch[KG_QPB];
+                                             int seeded, int assoc, int chunk, int* __restrict__ defer,
+                                             int* __restrict__ nbr) {
+  __shared__ int s_seg[KQ_SMEM_INTS];
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   const int n_e = counts[0], n_s = counts[1];
   const int lane = threadIdx.x & 31;
-  const WarpGroup8 x;
-  KnnScratch* s = &scratch[threadIdx.x >> 3];
+  const KqList li = kq_list(s_seg);
   const int live = n_e + n_s;  // positions >= live are padding (sorted) or unset (ring order)
   while (true) {
     int base = 0;
     if (lane == 0) base = atomicAdd(&st->knn_next, chunk);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= live) break;
-    for (int r = 0; r < chunk && base + r < live; r += 4) {  // four queries per round, one per group
-      const int t = base + r + (lane >> 3);
-      bool active = t < upper && t < live;
-      int f = active ? perm[t] : 0;
-      if (f >= live) active = false;
-      const bool is_edge = f < n_e;
-      float wx = 0.f, wy = 0.f, wz = 0.f;
-      if (assoc) {
-        if (active && x.l == 0) {  // one lane per query; the group receives the point by shuffle
-          quat q;
-          q.x = st->x[0];
-          q.y = st->x[1];
-          q.z = st->x[2];
-          q.w = st->x[3];
-          const d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
-          const float4 fp = feat[f];
-          const d3 pwd = add3(qrot(q, mk3((double)fp.x, (double)fp.y, (double)fp.z)), tr);
-          wx = (float)pwd.x, wy = (float)pwd.y, wz = (float)pwd.z;
-          pw[f] = make_float4(wx, wy, wz, 0.f);
-        }
-        wx = __shfl_sync(0xffffffffu, wx, 0, 8);
-        wy = __shfl_sync(0xffffffffu, wy, 0, 8);
-        wz = __shfl_sync(0xffffffffu, wz, 0, 8);
-      } else if (active) {
-        const float4 w = pw[f];
-        wx = w.x, wy = w.y, wz = w.z;
-      }
-      knn_one(x, s, maps, is_edge, is_edge ? has_edge_map != 0 : has_surf_map != 0, active, wx, wy, wz, seeded, upper, t,
-              nbr);
+    const int t = base + lane;
+    if (lane >= chunk || t >= upper || t >= live) continue;
+    const int f = perm[t];
+    if (f >= live) continue;
+    const bool is_edge = f < n_e;
+    float4 w;
+    if (assoc) {
+      quat q;
+      q.x = st->x[0];
+      q.y = st->x[1];
+      q.z = st->x[2];
+      q.w = st->x[3];
+      const d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
+      const float4 fp = feat[f];
+      const d3 pwd = add3(qrot(q, mk3((double)fp.x, (double)fp.y, (double)fp.z)), tr);
+      w = make_float4((float)pwd.x, (float)pwd.y, (float)pwd.z, 0.f);
+      pw[f] = w;
+    } else {
+      w = pw[f];
     }
+    int n = 0;
+    KqTop top;
+    if (is_edge ? has_edge_map : has_surf_map) {
+      unsigned long long seed[5];
+      bool have_seed = false;
+      if (seeded) {
+        const float4* __restrict__ cat = is_edge ? maps.edge_cat : maps.surf_cat;
+        int sid[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) sid[k] = nbr[k * upper + t];
+        if (sid[4] >= 0) {  // five or none
+          have_seed = true;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const float4 m = __ldg(&cat[sid[k]]);
+            const float dx = m.x - w.x, dy = m.y - w.y, dz = m.z - w.z;
+            float r = dx * dx;
+            r = r + dy * dy;
+            r = r + dz * dz;
+            seed[k] = kg_key(r, sid[k]);
+          }
+        }
+      }
+      n = kq_knn5<true>(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, have_seed ? seed : nullptr, top);
+    }
+    if (n < 0) {  // a sparse case: left to k_knn_sparse (one warp per query)
+      defer[atomicAdd(&st->n_defer, 1)] = t;
+      continue;
+    }
+    // -1 x 5 unless five neighbours lie within the search radius: both callers reject such a query
+#pragma unroll
+    for (int k = 0; k < 5; ++k) nbr[k * upper + t] = (n == 5) ? kg_key_id(top.k[k]) : -1;
+  }
+}
+
+// the queries k_knn deferred, one per warp (kw_knn5): the launch is enqueued behind every k_knn, its size is only
+// known on the device.  pw[] holds the world point already.
+__global__ void __launch_bounds__(KG_BLOCK) k_knn_sparse(const int* __restrict__ perm, const float4* __restrict__ pw,
+                                                         const int* __restrict__ counts, SolveState* __restrict__ st,
+                                                         MapPair maps, int upper, int solver,
+                                                         const int* __restrict__ defer, int* __restrict__ nbr) {
+  __shared__ KwScratch scratch[KG_BLOCK / 32];
+  if (solver == LMSF_SOLVER_GN && st->gn_done) return;
+  const int n_def = st->n_defer;
+  if (n_def == 0) return;
+  const int n_e = counts[0];
+  const Warp32 x;
+  KwScratch* s = &scratch[threadIdx.x >> 5];
+  while (true) {
+    int i = 0;
+    if (x.lane == 0) i = atomicAdd(&st->defer_next, 1);
+    i = x.shfl(i, 0);
+    if (i >= n_def) break;
+    const int t = defer[i];
+    const int f = perm[t];
+    const bool is_edge = f < n_e;
+    const float4 w = pw[f];
+    KqTop top;
+    int n = kw_knn5(x, is_edge ? maps.edge : maps.surf, s, w.x, w.y, w.z, top);
+    if (n < 0) {
+      // more occupied cells around the query than the item list holds: the complete per-thread search, by lane 0
+      // (its segment list lives in the same shared memory)
+      if (x.lane == 0) {
+        KqList li;
+        li.seg = reinterpret_cast<int*>(s);
+        li.stride = 1;
+        n = kq_knn5<false>(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, nullptr, top);
+      }
+      n = x.shfl(n, 0);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) top.k[k] = x.shfl64(top.k[k], 0);
+    }
+    if (x.lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) nbr[k * upper + t] = (n == 5) ? kg_key_id(top.k[k]) : -1;
+    }
+    x.sync();
   }
 }
 
@@ -1078,8 +1114,9 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
   if (threadIdx.x == 0) {
     sh.n_edge_ok = (int)tot[29];
     sh.n_surf_ok = (int)tot[28] - (int)tot[29];
-    sh.knn_next = 0;  // work-queue heads of the next k_knn launch (k_assoc does it when it runs)
-    sh.knn_next_heavy = 0;
+    sh.knn_next = 0;  // work-queue heads of the next k_knn / k_knn_sparse launches (k_assoc does it when it runs)
+    sh.defer_next = 0;
+    sh.n_defer = 0;
   }
   if (sp.solver == LMSF_SOLVER_GN) {
     if (threadIdx.x == 0) gn_step(&sh, tot, sp);
@@ -1159,47 +1196,87 @@ __global__ void k_state_init(SolveState* st, Pose7 pose) {
   st->lm_steps_total = st->lm_steps_accepted = 0;
   st->ticket = 0u;
   st->knn_next = 0;
-  st->knn_next_heavy = 0;
+  st->defer_next = 0;
+  st->n_defer = 0;
   st->n_heavy = 0;
 }
 
 // ------------------------------------------------------------------ test hooks
-// one query per group of eight lanes: blocks of KG_BLOCK threads search KG_QPB queries
+// lmsf_knn5 runs the registration's own pipeline: the per-thread search with deferral, then the deferred queries one
+// per warp.  ctr[0] = deferred so far, ctr[1] = work-queue head of the second kernel (zeroed by the host).
 __global__ void __launch_bounds__(KG_BLOCK) k_knn_hook(MapView mv, const float* __restrict__ q, int nq,
-                                                       int* __restrict__ idx, float* __restrict__ d2) {
-  __shared__ KnnScratch scratch[KG_QPB];
-  const WarpGroup8 x;
-  KnnScratch* s = &scratch[threadIdx.x >> 3];
-  const int i = blockIdx.x * KG_QPB + (threadIdx.x >> 3);
-  const bool active = i < nq;
-  const float qx = active ? q[3 * i] : 0.f, qy = active ? q[3 * i + 1] : 0.f, qz = active ? q[3 * i + 2] : 0.f;
-  const int n = kg_knn5(x, mv, s, qx, qy, qz, active, 0ull);
-  if (active && x.l < 5) {
-    const bool in = x.l < n;
-    idx[5 * i + x.l] = in ? kg_key_id(s->acc[x.l]) : -1;
-    d2[5 * i + x.l] = in ? kg_key_d2(s->acc[x.l]) : __int_as_float(0x7f800000);
+                                                       int* __restrict__ idx, float* __restrict__ d2,
+                                                       int* __restrict__ ctr, int* __restrict__ defer) {
+  __shared__ int s_seg[KQ_SMEM_INTS];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  KqTop top;
+  const int n = kq_knn5<true>(mv, kq_list(s_seg), q[3 * i], q[3 * i + 1], q[3 * i + 2], nullptr, top);
+  if (n < 0) {
+    defer[atomicAdd(&ctr[0], 1)] = i;
+    return;
+  }
+  for (int k = 0; k < 5; ++k) {
+    const bool in = k < n;
+    idx[5 * i + k] = in ? kg_key_id(top.k[k]) : -1;
+    d2[5 * i + k] = in ? kg_key_d2(top.k[k]) : __int_as_float(0x7f800000);
+  }
+}
+__global__ void __launch_bounds__(KG_BLOCK) k_knn_hook_sparse(MapView mv, const float* __restrict__ q,
+                                                              int* __restrict__ idx, float* __restrict__ d2,
+                                                              int* __restrict__ ctr, const int* __restrict__ defer) {
+  __shared__ KwScratch scratch[KG_BLOCK / 32];
+  const int n_def = ctr[0];
+  const Warp32 x;
+  KwScratch* s = &scratch[threadIdx.x >> 5];
+  while (true) {
+    int j = 0;
+    if (x.lane == 0) j = atomicAdd(&ctr[1], 1);
+    j = x.shfl(j, 0);
+    if (j >= n_def) break;
+    const int i = defer[j];
+    const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+    KqTop top;
+    int n = kw_knn5(x, mv, s, qx, qy, qz, top);
+    if (n < 0) {  // item list overflow: the complete per-thread search, by lane 0
+      if (x.lane == 0) {
+        KqList li;
+        li.seg = reinterpret_cast<int*>(s);
+        li.stride = 1;
+        n = kq_knn5<false>(mv, li, qx, qy, qz, nullptr, top);
+      }
+      n = x.shfl(n, 0);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) top.k[k] = x.shfl64(top.k[k], 0);
+    }
+    if (x.lane == 0) {
+      for (int k = 0; k < 5; ++k) {
+        const bool in = k < n;
+        idx[5 * i + k] = in ? kg_key_id(top.k[k]) : -1;
+        d2[5 * i + k] = in ? kg_key_d2(top.k[k]) : __int_as_float(0x7f800000);
+      }
+    }
+    x.sync();
   }
 }
 
 __global__ void __launch_bounds__(KG_BLOCK) k_match_hook(MapView mv, const float4* __restrict__ cat, int kind,
                                                          const float* __restrict__ q, int nq,
                                                          uint8_t* __restrict__ okv, double* __restrict__ out10) {
-  __shared__ KnnScratch scratch[KG_QPB];
-  const WarpGroup8 x;
-  KnnScratch* s = &scratch[threadIdx.x >> 3];
-  const int i = blockIdx.x * KG_QPB + (threadIdx.x >> 3);
-  const bool active = i < nq;
-  const float px = active ? q[3 * i] : 0.f, py = active ? q[3 * i + 1] : 0.f, pz = active ? q[3 * i + 2] : 0.f;
-  const int n = kg_knn5(x, mv, s, px, py, pz, active, 0ull);
-  if (!active || x.l != 0) return;
+  __shared__ int s_seg[KQ_SMEM_INTS];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
+  KqTop top;
+  const int n = kq_knn5<false>(mv, kq_list(s_seg), px, py, pz, nullptr, top);
   double o[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool ok = false;
   if (n == 5) {
     Top5 nb;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-      nb.id[k] = kg_key_id(s->acc[k]);
-      nb.d[k] = kg_key_d2(s->acc[k]);
+      nb.id[k] = kg_key_id(top.k[k]);
+      nb.d[k] = kg_key_d2(top.k[k]);
     }
     if (kind == LMSF_KIND_EDGE) {
       d3 nn, a, b;
@@ -1229,27 +1306,25 @@ struct Rigid12f {
 __global__ void __launch_bounds__(KG_BLOCK) k_align_score(MapView mv, const float4* __restrict__ pts, int n, Rigid12f T,
                                                           float thresh, double* __restrict__ part_sum,
                                                           int* __restrict__ part_cnt) {
-  __shared__ KnnScratch scratch[KG_QPB];
+  __shared__ int s_seg[KQ_SMEM_INTS];
   __shared__ double s_sum[4];
   __shared__ int s_cnt[4];
-  const WarpGroup8 x;
-  KnnScratch* s = &scratch[threadIdx.x >> 3];
-  const int i = blockIdx.x * KG_QPB + (threadIdx.x >> 3);  // one source point per group of eight lanes
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double v = 0.0;
   int in = 0;
-  float qx = 0.f, qy = 0.f, qz = 0.f;
   if (i < n) {
-    float4 p = pts[i];
-    qx = T.m[0] * p.x + T.m[1] * p.y + T.m[2] * p.z + T.m[3];
-    qy = T.m[4] * p.x + T.m[5] * p.y + T.m[6] * p.z + T.m[7];
-    qz = T.m[8] * p.x + T.m[9] * p.y + T.m[10] * p.z + T.m[11];
-  }
-  const int found = kg_knn5(x, mv, s, qx, qy, qz, i < n, 0ull);
-  if (i < n && x.l == 0 && found > 0) {
-    const float d0 = kg_key_d2(s->acc[0]);
-    if (d0 <= thresh) {
-      v = (double)d0;
-      in = 1;
+    const float4 p = pts[i];
+    const float qx = T.m[0] * p.x + T.m[1] * p.y + T.m[2] * p.z + T.m[3];
+    const float qy = T.m[4] * p.x + T.m[5] * p.y + T.m[6] * p.z + T.m[7];
+    const float qz = T.m[8] * p.x + T.m[9] * p.y + T.m[10] * p.z + T.m[11];
+    KqTop top;
+    const int found = kq_knn5<false>(mv, kq_list(s_seg), qx, qy, qz, nullptr, top);
+    if (found > 0) {
+      const float d0 = kg_key_d2(top.k[0]);
+      if (d0 <= thresh) {
+        v = (double)d0;
+        in = 1;
+      }
     }
   }
 #pragma unroll
@@ -1299,7 +1374,7 @@ __global__ void __launch_bounds__(256) k_align_finish(const double* __restrict__
 
 // ------------------------------------------------------------------ host side
 #ifndef KNN_GRID_PER_SM
-#define KNN_GRID_PER_SM 7
+#define KNN_GRID_PER_SM 4
 #endif
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -1328,6 +1403,7 @@ int solve_alloc(Ctx* c) {
   LM_CUDA(cudaMalloc(&c->q_vals_alt, cap * 4));
   LM_CUDA(cudaMalloc(&c->d_pw, cap * sizeof(float4)));
   LM_CUDA(cudaMalloc(&c->d_nbr, 5 * cap * sizeof(int)));
+  LM_CUDA(cudaMalloc(&c->d_defer, cap * sizeof(int)));
   c->partial_blocks = div_up((int)cap, MATCH_BLOCK);
   LM_CUDA(cudaMalloc(&c->d_partial, (size_t)c->partial_blocks * LM_NSUM * sizeof(double)));
   LM_CUDA(cudaMalloc(&c->d_state, sizeof(SolveState)));
@@ -1345,6 +1421,7 @@ void solve_free(Ctx* c) {
   cudaFree(c->q_vals_alt);
   cudaFree(c->d_pw);
   cudaFree(c->d_nbr);
+  cudaFree(c->d_defer);
   cudaFree(c->d_partial);
   cudaFree(c->d_state);
   cudaFree(c->hook_buf);
@@ -1363,10 +1440,17 @@ int hook_scratch(Ctx* c, size_t bytes, void** out) {
   return LMSF_OK;
 }
 
-int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2) {
+int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2, int* d_work) {
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
   if (nq == 0) return LMSF_OK;
-  LM_LAUNCH(c, k_knn_hook, div_up(nq, KG_QPB), KG_BLOCK, 0, view_of(c->map[kind]), d_q, nq, d_idx, d_d2);
+  // d_work: [2] counters, [nq] deferral list
+  int* ctr = d_work;
+  LM_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(int), c->stream));
+  LM_LAUNCH(c, k_knn_hook, div_up(nq, KG_BLOCK), KG_BLOCK, 0, view_of(c->map[kind]), d_q, nq, d_idx, d_d2, ctr,
+            d_work + 2);
+  int sgrid = div_up(nq, 4);
+  LM_LAUNCH(c, k_knn_hook_sparse, sgrid < 148 * 2 ? sgrid : 148 * 2, KG_BLOCK, 0, view_of(c->map[kind]), d_q, d_idx, d_d2,
+            ctr, d_work + 2);
   LM_CUDA(cudaGetLastError());
   return LMSF_OK;
 }
@@ -1374,7 +1458,7 @@ int knn_hook(Ctx* c, int kind, const float* d_q, int nq, int* d_idx, float* d_d2
 int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double* d_out10) {
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
   if (nq == 0) return LMSF_OK;
-  LM_LAUNCH(c, k_match_hook, div_up(nq, KG_QPB), KG_BLOCK, 0, view_of(c->map[kind]), c->map[kind].cat, kind, d_q, nq, d_ok,
+  LM_LAUNCH(c, k_match_hook, div_up(nq, KG_BLOCK), KG_BLOCK, 0, view_of(c->map[kind]), c->map[kind].cat, kind, d_q, nq, d_ok,
             d_out10);
   LM_CUDA(cudaGetLastError());
   return LMSF_OK;
@@ -1383,7 +1467,7 @@ int match_hook(Ctx* c, int kind, const float* d_q, int nq, uint8_t* d_ok, double
 // device cloud -> (sum of inlier squared distances, inlier count) read back with one sync
 int align_hook(Ctx* c, int kind, const float4* d_pts, int n, const float T12[12], float thresh, double* sum, int* cnt) {
   if (!c->map[kind].ready) return LMSF_ERR_STATE;
-  const int nblk = div_up(n, KG_QPB);
+  const int nblk = div_up(n, KG_BLOCK);
   // partial sums live behind the caller's points in the hook arena (d_pts is its first n float4)
   double* d_part = (double*)(d_pts + n);
   int* d_cnt = (int*)(d_part + nblk + 1);
@@ -1502,12 +1586,15 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       StageScope scope(c, LMSF_STAGE_MATCH);
       static const int knn_width = env_int("LMSF_KNN_WIDTH", 0);  // tuning experiments
       int chunk = 32;  // queries per warp: halve it while the sweep has fewer chunks than ~1.5x the resident warps
-      while (chunk > 8 && up / chunk < 148 * 24 * 3 / 2) chunk >>= 1;
+      while (chunk > 8 && up / chunk < 148 * knn_per_sm * (KG_BLOCK / 32) * 3 / 2) chunk >>= 1;
       if (knn_width == 8 || knn_width == 16 || knn_width == 32) chunk = knn_width;
       int knn_grid = div_up(up, 4 * chunk);
       if (knn_grid > 148 * knn_per_sm) knn_grid = 148 * knn_per_sm;  // persistent: every resident warp pulls work
       LM_LAUNCH(c, k_knn, knn_grid, KG_BLOCK, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, up,
-                solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_nbr);
+                solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
+      // the sparse cases of this pass, one warp each (nothing to do when k_knn deferred none)
+      LM_LAUNCH(c, k_knn_sparse, 148 * 2, KG_BLOCK, 0, perm, c->d_pw, c->ex.counts, c->d_state, maps, up, solver,
+                c->d_defer, c->d_nbr);
       c->match_bytes += alg_bytes;
       c->match_launches += 1;
     }
@@ -1565,3 +1652,20 @@ int solve_finish(Ctx* c, int solver, double pose[7], lmsf_reg_stats* stats, int 
 }
 
 }  // namespace lm
+
+#ifdef LMSF_KNN_CHECK
+// debugging builds (make EXTRA=-DLMSF_KNN_CHECK): the first index violation a search launched from match.cu met
+namespace lm {
+__global__ void k_knn_check_collect(int* __restrict__ out) {
+  if (threadIdx.x < 8) out[threadIdx.x] = g_knn_check[threadIdx.x];
+}
+}  // namespace lm
+extern "C" int lmsf_debug_knn_check(lmsf_ctx* c, int out[8]) {
+  int* d = nullptr;
+  LM_TRY(hook_scratch(c, 64, (void**)&d));
+  lm::k_knn_check_collect<<<1, 32, 0, c->stream>>>(d);
+  LM_CUDA(cudaMemcpyAsync(out, d, 32, cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  return LMSF_OK;
+}
+#endif

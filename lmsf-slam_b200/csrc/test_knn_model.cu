@@ -1,21 +1,19 @@
-// test_knn_model.cu — the cooperative 5-NN search of knn.cuh executed on the CPU against brute force.
+// test_knn_model.cu — the 5-NN search of knn.cuh executed on the CPU against brute force.
 //
-// Test infrastructure (run by tests/test_knn_model.py; no GPU needed).  The search is written once as templates over an
-// executor; here the same source runs (a) with one lane per query (HostGroup1) and (b) as a full emulated warp:
-// 32 host threads in lockstep, four groups of eight lanes, every ballot / shuffle / any a barrier-synchronised
-// exchange — the lane arithmetic (prefix sums, ballots, rank counting, list compression) is the code the device runs.
+// Test infrastructure (run by tests/test_knn_model.py; no GPU needed).  The search is plain per-thread code (HD): the
+// source the device runs is compiled for the host here, with the per-lane segment list laid out as in shared memory.
 // The index is built on the CPU in the layout mapindex.cu produces (hash table of 1 m cells, L1 records, L2 starts,
 // points grouped by (L0, L1, L2) with x fastest).
 //
 //   ./test_knn_model [n_map] [n_query] [seed]     exit code 0 = every query identical to brute force (ids and
-//                                                 distance bits), in both executors, unseeded and seeded
+//                                                 distance bits), unseeded and seeded
 #include <algorithm>
 #include <barrier>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <random>
-#include <thread>
 
 #include "knn.cuh"
 
@@ -135,110 +133,209 @@ static int brute5(const std::vector<float4>& pts, float qx, float qy, float qz, 
   return n;
 }
 
-// ---------------------------------------------------------------- emulated warp
+struct Query {
+  float x, y, z;
+  bool seeded;
+  unsigned long long seed[5];
+};
+
+// ---------------------------------------------------------------- emulated warp: 32 host threads in lockstep, every
+// ballot / shuffle a barrier-synchronised exchange (kw_knn5 is written over this interface)
 struct EmuWarp {
   std::barrier<> bar{32};
   unsigned long long buf[2][32];
 };
-struct EmuGroup8 {
-  static constexpr int G = 8;
-  int l;
-  unsigned gshift;
+struct Emu32 {
   int lane;
   EmuWarp* w;
   mutable int phase = 0;
-  EmuGroup8(EmuWarp* w_, int lane_) : l(lane_ & 7), gshift(lane_ & 24), lane(lane_), w(w_) {}
-  // every lane deposits a value, all wait, every lane may read any
-  HD const unsigned long long* exchange(unsigned long long v) const {
-#ifndef __CUDA_ARCH__
+  Emu32(EmuWarp* w_, int lane_) : lane(lane_), w(w_) {}
+  const unsigned long long* exchange(unsigned long long v) const {
     unsigned long long* b = w->buf[phase];
     phase ^= 1;
     b[lane] = v;
     w->bar.arrive_and_wait();
     return b;
-#else
-    return nullptr;
-#endif
   }
-  HD unsigned ballot(bool p) const {
+  unsigned ballot(bool p) const {
     const unsigned long long* b = exchange(p ? 1ull : 0ull);
     unsigned m = 0;
-    for (int i = 0; i < 8; ++i) m |= (unsigned)b[gshift + i] << i;
+    for (int i = 0; i < 32; ++i) m |= (unsigned)b[i] << i;
     return m;
   }
-  HD bool any(bool p) const {
-    const unsigned long long* b = exchange(p ? 1ull : 0ull);
-    for (int i = 0; i < 32; ++i)
-      if (b[i]) return true;
-    return false;
-  }
-  HD int shfl(int v, int src) const { return (int)(unsigned)exchange((unsigned)v)[gshift + (src & 7)]; }
-  HD int shfl_up(int v, int d) const {
+  int shfl(int v, int src) const { return (int)(unsigned)exchange((unsigned)v)[src & 31]; }
+  int shfl_up(int v, int d) const {
     const unsigned long long* b = exchange((unsigned)v);
-    return l >= d ? (int)(unsigned)b[lane - d] : v;
+    return lane >= d ? (int)(unsigned)b[lane - d] : v;
   }
-  HD unsigned long long shfl_xor64(unsigned long long v, int d) const { return exchange(v)[gshift + ((l ^ d) & 7)]; }
-  HD void sync() const { exchange(0ull); }
+  unsigned long long shfl64(unsigned long long v, int src) const { return exchange(v)[src & 31]; }
+  unsigned long long shfl_xor64(unsigned long long v, int d) const { return exchange(v)[(lane ^ d) & 31]; }
+  void sync() const { exchange(0ull); }
 };
 
-struct Query {
-  float x, y, z;
-  unsigned long long seed;
-};
-
-static long run_single(const HostIndex& ix, const std::vector<float4>& pts, const std::vector<Query>& qs, bool seeded) {
+// the registration kernel's pipeline: the per-thread search with deferral, the deferred queries by the (emulated) warp
+static long run_deferred(const HostIndex& ix, const std::vector<float4>& pts, const std::vector<Query>& qs, long* n_def) {
+  const MapView mv = ix.view();
+  std::vector<int> smem(32 * 2 * KQ_SEG_CAP, -1);
+  KqList li;
+  li.seg = smem.data();
+  li.stride = 32;
+  std::vector<int> deferred;
   long bad = 0;
-  const MapView mv = ix.view();
-  KnnScratch s;
-  HostGroup1 x;
-  for (const Query& q : qs) {
+  auto check = [&](size_t i, int n, const KqTop& top, const char* what) {
     unsigned long long ref[5];
-    const int nr = brute5(pts, q.x, q.y, q.z, ref);
-    const int n = kg_knn5(x, mv, &s, q.x, q.y, q.z, true, seeded ? q.seed : 0ull);
+    const int nr = brute5(pts, qs[i].x, qs[i].y, qs[i].z, ref);
     bool ok = n == nr;
-    for (int k = 0; ok && k < n; ++k) ok = s.acc[k] == ref[k];
-    if (!ok && bad++ < 5) fprintf(stderr, "single%s: query (%g %g %g): n %d vs %d\n", seeded ? " seeded" : "", q.x, q.y, q.z, n, nr);
+    for (int k = 0; ok && k < n; ++k) ok = top.k[k] == ref[k];
+    if (!ok && bad++ < 5) fprintf(stderr, "%s: query %zu (%g %g %g): n %d vs %d\n", what, i, qs[i].x, qs[i].y, qs[i].z, n, nr);
+  };
+  for (size_t i = 0; i < qs.size(); ++i) {
+    KqTop top;
+    const int n = kq_knn5<true>(mv, li, qs[i].x, qs[i].y, qs[i].z, nullptr, top);
+    if (n < 0)
+      deferred.push_back((int)i);
+    else
+      check(i, n, top, "thread");
   }
-  return bad;
-}
-
-static long run_warp(const HostIndex& ix, const std::vector<float4>& pts, const std::vector<Query>& qs, bool seeded) {
-  const MapView mv = ix.view();
+  *n_def = (long)deferred.size();
   EmuWarp w;
-  static KnnScratch scratch[4];
-  std::vector<int> n_out(qs.size(), -1);
-  std::vector<std::array<unsigned long long, 5>> res(qs.size());
+  static KwScratch scratch;
+  std::vector<KqTop> tops(deferred.size());
+  std::vector<int> ns(deferred.size(), -2);
   auto body = [&](int lane) {
-    EmuGroup8 x(&w, lane);
-    const int g = lane >> 3;
-    for (size_t base = 0; base < qs.size(); base += 4) {
-      const size_t qi = base + g;
-      const bool active = qi < qs.size();
-      const Query q = active ? qs[qi] : Query{0, 0, 0, 0};
-      const int n = kg_knn5(x, mv, &scratch[g], q.x, q.y, q.z, active, seeded ? q.seed : 0ull);
-      if (active && x.l == 0) {
-        n_out[qi] = n;
-        for (int k = 0; k < n; ++k) res[qi][k] = scratch[g].acc[k];
-      }
+    Emu32 x(&w, lane);
+    for (size_t d = 0; d < deferred.size(); ++d) {
+      const Query& q = qs[deferred[d]];
+      KqTop top;
+      const int n = kw_knn5(x, mv, &scratch, q.x, q.y, q.z, top);
+      if (lane == (int)(d % 32)) tops[d] = top, ns[d] = n;  // every lane holds the same list: take a different one each time
       x.sync();
     }
   };
   std::vector<std::thread> th;
   for (int lane = 0; lane < 32; ++lane) th.emplace_back(body, lane);
   for (auto& t : th) t.join();
-  long bad = 0;
-  for (size_t i = 0; i < qs.size(); ++i) {
-    unsigned long long ref[5];
-    const int nr = brute5(pts, qs[i].x, qs[i].y, qs[i].z, ref);
-    bool ok = n_out[i] == nr;
-    for (int k = 0; ok && k < nr; ++k) ok = res[i][k] == ref[k];
-    if (!ok && bad++ < 5)
-      fprintf(stderr, "warp%s: query %zu (%g %g %g): n %d vs %d\n", seeded ? " seeded" : "", i, qs[i].x, qs[i].y, qs[i].z, n_out[i], nr);
+  for (size_t d = 0; d < deferred.size(); ++d) {
+    if (ns[d] == -1) {  // item list overflow: the kernel falls back to the complete per-thread search
+      KqTop top;
+      const int n = kq_knn5<false>(mv, li, qs[deferred[d]].x, qs[deferred[d]].y, qs[deferred[d]].z, nullptr, top);
+      check(deferred[d], n, top, "fallback");
+    } else {
+      check(deferred[d], ns[d], tops[d], "warp");
+    }
   }
   return bad;
 }
 
+// lane `lane` of a 32-lane list (the device layout: stride 32), to exercise the indexing
+static long run(const HostIndex& ix, const std::vector<float4>& pts, const std::vector<Query>& qs, bool seeded) {
+  long bad = 0;
+  const MapView mv = ix.view();
+  std::vector<int> smem(32 * 2 * KQ_SEG_CAP, -1);
+  int lane = 0;
+  for (const Query& q : qs) {
+    KqList li;
+    li.seg = smem.data() + lane;
+    li.stride = 32;
+    lane = (lane + 7) & 31;
+    unsigned long long ref[5];
+    const int nr = brute5(pts, q.x, q.y, q.z, ref);
+    KqTop top;
+    const int n = kq_knn5<false>(mv, li, q.x, q.y, q.z, (seeded && q.seeded) ? q.seed : nullptr, top);
+    bool ok = n == nr;
+    for (int k = 0; ok && k < n; ++k) ok = top.k[k] == ref[k];
+    if (!ok && bad++ < 5)
+      fprintf(stderr, "%s: query (%g %g %g): n %d vs %d\n", seeded ? "seeded" : "unseeded", q.x, q.y, q.z, n, nr);
+  }
+  return bad;
+}
+
+// work profile on a recorded scene: file = int32 n_map, int32 n_q, n_map x float4, n_q x float3 (tests/make_knn_scene.py)
+#ifdef LMSF_KNN_STATS
+static int profile_file(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return 2;
+  int n_map = 0, n_q = 0;
+  if (fread(&n_map, 4, 1, f) != 1 || fread(&n_q, 4, 1, f) != 1) return 2;
+  std::vector<float4> pts(n_map);
+  std::vector<float> qf(3 * (size_t)n_q);
+  if (fread(pts.data(), 16, n_map, f) != (size_t)n_map || fread(qf.data(), 12, n_q, f) != (size_t)n_q) return 2;
+  fclose(f);
+  HostIndex ix;
+  build_index(pts, ix);
+  const MapView mv = ix.view();
+  std::vector<int> smem(32 * 2 * KQ_SEG_CAP, -1);
+  KqList li;
+  li.seg = smem.data();
+  li.stride = 32;
+  std::vector<std::array<unsigned long long, 5>> k5(n_q);
+  for (auto& a : k5) a.fill(0ull);
+  for (int pass = 0; pass < 2; ++pass) {
+    memset(g_knn_stat_host, 0, sizeof g_knn_stat_host);
+    std::vector<unsigned long long> cand(n_q), cost(n_q);
+    long full = 0;
+    for (int i = 0; i < n_q; ++i) {
+      const unsigned long long c0 = g_knn_stat_host[2];
+      unsigned long long g0[16];
+      memcpy(g0, g_knn_stat_host, sizeof g0);
+      KqTop top;
+      // pass 1 = seeded with the first pass's own 5th key (what the second outer iteration sees, the pose barely moved)
+      int n = kq_knn5<true>(mv, li, qf[3 * i], qf[3 * i + 1], qf[3 * i + 2], (pass && k5[i][4] != 0ull) ? k5[i].data() : nullptr, top);
+      if (n < 0) {
+        ++g_knn_stat_host[15];
+        KqTop t2;
+        const unsigned long long keep[16] = {g_knn_stat_host[0], g_knn_stat_host[1], g_knn_stat_host[2], g_knn_stat_host[3]};
+        n = kq_knn5<false>(mv, li, qf[3 * i], qf[3 * i + 1], qf[3 * i + 2], nullptr, t2);
+        top = t2;
+        for (int k = 0; k < 4; ++k) g_knn_stat_host[k] = keep[k];
+        for (int k = 8; k < 15; ++k) g_knn_stat_host[k] = g0[k];
+      }
+      if (n == 5) {
+        for (int k = 0; k < 5; ++k) k5[i][k] = top.k[k];
+        ++full;
+      }
+      cand[i] = g_knn_stat_host[2] - c0;
+      // serial cost model of one query (dependent-latency units): an L0 probe 1, an L1 cell 2, a sweep 2
+      unsigned long long sweeps = 0;
+      for (int k = 8; k < 16; ++k) sweeps += g_knn_stat_host[k] - g0[k];
+      cost[i] = (g_knn_stat_host[0] - g0[0]) + 2 * (g_knn_stat_host[1] - g0[1]) + 2 * sweeps + cand[i] / 8;
+      if (cost[i] > 150 && getenv("KNN_PROF_VERBOSE"))
+        printf("    query %d (%.2f %.2f %.2f): cost %llu = L0 %llu, L1 %llu, sweeps %llu, cand %llu, n %d d5 %.3f\n", i, qf[3 * i],
+               qf[3 * i + 1], qf[3 * i + 2], cost[i], g_knn_stat_host[0] - g0[0], g_knn_stat_host[1] - g0[1], sweeps, cand[i], n,
+               n == 5 ? sqrtf(kg_key_d2(top.k[4])) : -1.f);
+    }
+    {
+      std::vector<unsigned long long> cs(cost);
+      std::sort(cs.begin(), cs.end());
+      unsigned long long tot = 0;
+      for (auto v : cs) tot += v;
+      printf("  latency-chain model per query: mean %.1f p50 %llu p90 %llu p99 %llu p99.9 %llu max %llu\n", (double)tot / n_q,
+             cs[n_q / 2], cs[n_q * 9 / 10], cs[n_q * 99 / 100], cs[(size_t)(n_q * 0.999)], cs[n_q - 1]);
+    }
+    // per-warp cost of the flat candidate loop: the longest lane of every 32 consecutive queries
+    unsigned long long sum = 0, warp_max_sum = 0;
+    for (int i = 0; i < n_q; i += 32) {
+      unsigned long long mx = 0;
+      for (int j = i; j < std::min(n_q, i + 32); ++j) sum += cand[j], mx = std::max(mx, cand[j]);
+      warp_max_sum += mx * 32;
+    }
+    std::sort(cand.begin(), cand.end());
+    const unsigned long long* g = g_knn_stat_host;
+    printf("%s: %d queries, %ld full | per query: L0 lookups %.2f  L1 cells %.2f  segments %.2f  candidates %.1f "
+           "(p50 %llu p90 %llu p99 %llu max %llu) | lane efficiency of the scan %.2f | unseeded %llu seeded %llu "
+           "ball %llu sparse %llu deferred %llu\n",
+           pass ? "seeded" : "unseeded", n_q, full, (double)g[0] / n_q, (double)g[1] / n_q, (double)g[3] / n_q,
+           (double)g[2] / n_q, cand[n_q / 2], cand[n_q * 9 / 10], cand[n_q * 99 / 100], cand[n_q - 1],
+           (double)sum / (double)warp_max_sum, g[8], g[9], g[10], g[11], g[15]);
+  }
+  return 0;
+}
+#endif
+
 int main(int argc, char** argv) {
+#ifdef LMSF_KNN_STATS
+  if (argc > 2 && !strcmp(argv[1], "--file")) return profile_file(argv[2]);
+#endif
   const int n_map = argc > 1 ? atoi(argv[1]) : 60000;
   const int n_q = argc > 2 ? atoi(argv[2]) : 1500;
   const unsigned seed = argc > 3 ? (unsigned)atoi(argv[3]) : 1u;
@@ -279,7 +376,7 @@ int main(int argc, char** argv) {
     } else {  // far outside the grid
       q.x = 300.f * N(rng), q.y = 300.f * N(rng), q.z = 100.f * N(rng);
     }
-    q.seed = 0ull;
+    q.seeded = false;
     qs.push_back(q);
   }
   // seeds as the registration provides them: the five neighbours of a slightly moved query -> an inclusive bound
@@ -288,23 +385,22 @@ int main(int argc, char** argv) {
     unsigned long long nb[5];
     const float mx = q.x + 0.03f * N(rng), my = q.y + 0.03f * N(rng), mz = q.z + 0.03f * N(rng);
     if (brute5(pts, mx, my, mz, nb) == 5 && U(rng) < 0.9f) {
-      unsigned long long k5 = 0ull;
+      q.seeded = true;
       for (int k = 0; k < 5; ++k) {
         const float4 p = pts[kg_key_id(nb[k])];
         const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
         float r = dx * dx;
         r = r + dy * dy;
         r = r + dz * dz;
-        k5 = std::max(k5, kg_key(r, kg_key_id(nb[k])));
+        q.seed[k] = kg_key(r, kg_key_id(nb[k]));
       }
-      q.seed = k5;
     }
   }
   long bad = 0;
-  bad += run_single(ix, pts, qs, false);
-  bad += run_single(ix, pts, qs, true);
-  bad += run_warp(ix, pts, qs, false);
-  bad += run_warp(ix, pts, qs, true);
-  printf("map %zu points, %d queries x 4 runs: %ld mismatches\n", pts.size(), n_q, bad);
+  bad += run(ix, pts, qs, false);
+  bad += run(ix, pts, qs, true);
+  long n_def = 0;
+  bad += run_deferred(ix, pts, qs, &n_def);
+  printf("map %zu points, %d queries x 3 runs (%ld searched by the warp): %ld mismatches\n", pts.size(), n_q, n_def, bad);
   return bad ? 1 : 0;
 }

@@ -1,6 +1,5 @@
-"""The cooperative 5-NN search of csrc/knn.cuh executed on the CPU (csrc/test_knn_model.cu): the same template source
-the device runs, with one lane per query and as an emulated 32-lane warp (four groups of eight lanes in lockstep),
-unseeded and seeded, against brute force — ids and distance bits identical.  Replaces what pcl::KdTreeFLANN::
+"""The 5-NN search of csrc/knn.cuh executed on the CPU (csrc/test_knn_model.cu): the same per-thread source the
+device runs, unseeded and seeded, against brute force — ids and distance bits identical.  Replaces what pcl::KdTreeFLANN::
 nearestKSearch(point, 5, ...) answers for registration/FeatureMatch/EdgeFeatureMatch.hpp:38 and surfFeatureMatch.hpp:37."""
 import os
 import subprocess
@@ -17,7 +16,7 @@ def model_bin():
     return exe
 
 
-@pytest.mark.parametrize("n_map,n_q,seed", [(60000, 600, 1), (3000, 400, 7), (40, 100, 9)])
+@pytest.mark.parametrize("n_map,n_q,seed", [(60000, 4000, 1), (120000, 4000, 2), (3000, 2000, 7), (40, 300, 9)])
 def test_knn_model_matches_brute_force(model_bin, n_map, n_q, seed):
     r = subprocess.run([model_bin, str(n_map), str(n_q), str(seed)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
