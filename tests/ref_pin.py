@@ -190,3 +190,65 @@ def check_lm_register_against_reference(ctx, synth, exact):
         outers.append(st["outer_iters"])
     dll.ref_lm_destroy(h)
     return outers
+
+
+def check_tracker_against_reference(ctx, synth, exact, n_sweeps=14, window=3):
+    """ctx: a context (oracle or CUDA library; created with window=`window`, raw maps) with extract_features /
+    tracker_step_features / get_map.  `n_sweeps` consecutive sweeps through the reference's OWN tracker
+    (LidarTracker/LidarTrackerLocalMap.hpp compiled into oracle/_ref/libref_tracker.so, instantiated as its factory does,
+    with its own CeresEdgeSurfFeatureRegistration; ceres::Solve = the oracle's restated loop, the sliding window = the
+    inferred stand-in of oracle/shim_inferred) and through ctx: pose, motion increment, keyframe decisions (seen through
+    the local-map sizes) and the local maps themselves, every sweep.  The sequence holds the constant-motion prediction,
+    a caller-supplied prediction, motion keyframes, a window that fills and evicts, and a time keyframe (a 12 s gap).
+    exact: translations bit-identical, rotations to the last bit, maps bit-identical (oracle); otherwise BASELINE.json's
+    bar of 1e-4 m / 1e-5 rad and maps within 1e-4 m (CUDA library).  Returns the keyframe kinds ctx reported."""
+    from scipy.spatial.transform import Rotation
+    C.CDLL(entry.ORACLE_LIB, mode=C.RTLD_GLOBAL)
+    dll = C.CDLL(_ref_path("libref_tracker.so"))
+    dll.ref_tracker_create.restype = C.c_void_p
+    fp, dp, ip = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)
+    h = C.c_void_p(dll.ref_tracker_create(window))
+    sensor = synth.vlp16()
+    kinds = []
+    stamp = 0.0
+    for k in range(n_sweeps):
+        stamp += 12.0 if k == 9 else 0.1                    # sweep 9 arrives after TIME_INTERVAL_ = 10 s
+        _, e, s = ctx.extract_features(synth.make_sweep(sensor, k))
+        e, s = np.ascontiguousarray(e), np.ascontiguousarray(s[::2])     # thinned: the CPU side runs both trackers
+        # sweep 5: the caller predicts the motion itself (deltaT != Identity, LidarTrackerLocalMap.hpp:125-129) — a pure
+        # translation, so that both sides receive exactly the same transform (no quaternion -> matrix conversion between)
+        delta = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+        if k == 5:
+            delta[4:] = [0.14, 0.01, 0.0]
+        dR = np.eye(3).reshape(9).copy()
+        dt = delta[4:].copy()
+        pR, pt, nm = np.zeros(9), np.zeros(3), np.zeros(2, np.int32)
+        assert dll.ref_tracker_solve(h, e.ctypes.data_as(fp), len(e), s.ctypes.data_as(fp), len(s), C.c_double(stamp),
+                                     dR.ctypes.data_as(dp), dt.ctypes.data_as(dp), pR.ctypes.data_as(dp),
+                                     pt.ctypes.data_as(dp), nm.ctypes.data_as(ip)) == 0
+        po, do, st = ctx.tracker_step_features(e, s, stamp, delta=delta)
+        kinds.append(st["keyframe"])
+        Ro = Rotation.from_quat(po[:4]).as_matrix()
+        Rd = Rotation.from_quat(do[:4]).as_matrix()
+        if os.environ.get("LMSF_PIN_VERBOSE"):
+            print(k, "kind", st["keyframe"], "maps", st["map_edge"], st["map_surf"], list(nm), "dt", np.abs(pt - po[4:]).max(),
+                  "dR", np.abs(pR.reshape(3, 3) - Ro).max(), "delta", np.abs(dt - do[4:]).max(), flush=True)
+        if exact:
+            assert np.array_equal(pt.view(np.uint64), po[4:].view(np.uint64)), (k, pt, po[4:])
+            assert np.abs(pR.reshape(3, 3) - Ro).max() < 1e-15, k
+            assert np.abs(dt - do[4:]).max() < 1e-15 and np.abs(dR.reshape(3, 3) - Rd).max() < 1e-15, k
+        else:
+            assert np.linalg.norm(pt - po[4:]) < 1e-4, (k, pt, po[4:])
+            assert Rotation.from_matrix(pR.reshape(3, 3) @ Ro.T).magnitude() < 1e-5, k
+        assert (st["map_edge"], st["map_surf"]) == (int(nm[0]), int(nm[1])), (k, st, nm)   # same keyframe decisions
+        for kind in (0, 1):
+            m_o = ctx.get_map(kind)
+            m_r = np.zeros((max(int(nm[kind]), 1), 4), np.float32)
+            n = dll.ref_tracker_map(h, kind, m_r.ctypes.data_as(fp), len(m_r))
+            assert n == len(m_o), (k, kind)
+            if exact:
+                assert np.array_equal(m_r[:n].view(np.uint32), m_o.view(np.uint32)), (k, kind)
+            else:
+                assert np.abs(m_r[:n, :3] - m_o[:, :3]).max() < 1e-4, (k, kind)
+    dll.ref_tracker_destroy(h)
+    return kinds

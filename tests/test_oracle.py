@@ -889,6 +889,20 @@ def test_lm_register_vs_reference_code(oracle_lib, synth):
     assert outers == [9, 8, 7, 6, 5, 4, 3, 2, 2, 2, 2, 2]
 
 
+def test_tracker_vs_reference_code(oracle_lib, synth):
+    """Row a6 PINNED: the oracle's tracker against the reference's own LidarTrackerLocalMap::Solve / updateLocalMap /
+    needUpdataLocalMap (LidarTracker/LidarTrackerLocalMap.hpp:107-262), compiled from the unmodified header with the
+    reference's own CeresEdgeSurfFeatureRegistration into oracle/_ref/libref_tracker.so.  Fourteen sweeps: prediction by
+    the constant-motion model and by the caller, motion keyframes (translation norm / 2 acos(q.w) thresholds), a window of
+    three that fills and evicts, a TIME keyframe — poses and increments bit-identical, local maps bit-identical every
+    sweep.  Not part of the pin: the sliding window itself (factory/Map/LocalMap_factory.hpp is absent from the reference
+    tree; oracle/shim_inferred restates what the tracker requires of it) and ceres::Solve (the oracle's loop)."""
+    o = oracle_lib.context(0, n_scans=16, window=3, oracle_knn_mode=0, oracle_threads=os.cpu_count() or 1)
+    kinds = ref_pin.check_tracker_against_reference(o, synth, exact=True)
+    o.close()
+    assert kinds[0] == 1 and 2 in kinds and kinds.count(1) >= 4 and 0 in kinds    # all three update kinds occurred
+
+
 def _np_gn(me, ms, edge, surf, pose, max_iters=10):
     """EdgeSurfFeatureRegistration::Solve + GNOptimization (registration/edgeSurfFeatureRegistration.hpp:113-330):
     re-match every iteration, J = grad^T [-R skew(p) | I], float residual, QR solve of JTJ, first-iteration degeneracy

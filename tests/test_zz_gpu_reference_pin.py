@@ -44,3 +44,16 @@ def test_cuda_lm_register_vs_reference_code(gpu_lib, synth):
     outers = ref_pin.check_lm_register_against_reference(g, synth, exact=False)
     g.close()
     assert outers == [9, 8, 7, 6, 5, 4, 3, 2, 2, 2, 2, 2]
+
+
+def test_cuda_tracker_vs_reference_code(gpu_lib, synth):
+    """Row a6 against the reference's own code: fourteen lmsf_tracker_step_features calls against
+    LidarTrackerLocalMap::Solve (LidarTracker/LidarTrackerLocalMap.hpp:107-262, compiled from the unmodified header with
+    the reference's CeresEdgeSurfFeatureRegistration; sliding window = the inferred stand-in, ceres::Solve = the oracle's
+    loop) — every pose within 1e-4 m / 1e-5 rad, the same keyframe decisions (motion, time, none) seen through identical
+    local-map sizes, local maps within 1e-4 m every sweep; constant-motion and caller-supplied predictions, a window that
+    fills and evicts."""
+    g = gpu_lib.context(0, n_scans=16, window=3)
+    kinds = ref_pin.check_tracker_against_reference(g, synth, exact=False)
+    g.close()
+    assert kinds[0] == 1 and 2 in kinds and kinds.count(1) >= 4 and 0 in kinds
