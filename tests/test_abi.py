@@ -80,6 +80,12 @@ def test_cpp_adapter_binary_builds_and_fails_loudly_without_gpu():
         pytest.skip("a CUDA device is present")
     r = subprocess.run([exe, "/dev/null", "0", "0", "16"], capture_output=True, text=True)
     assert r.returncode == 4 and "no CPU path" in r.stderr
+    # the same program over the reference's own seam headers (LMSF_WITH_REFERENCE), where /root/reference exists
+    if os.path.isdir("/root/reference"):
+        ref_exe = exe + "_ref"
+        assert os.path.exists(ref_exe)
+        r = subprocess.run([ref_exe, "/dev/null", "0", "0", "16"], capture_output=True, text=True)
+        assert r.returncode == 4 and "no CPU path" in r.stderr
 
 
 def test_fmath_atan2f_has_the_c_librarys_bits(tmp_path):
