@@ -73,7 +73,11 @@ typedef struct {
   double kf_rot;             /* 0.1 rad */
   double kf_time;            /* 10 s */
   int32_t max_map_points;    /* capacity of one local map; default window * max_points */
-  int32_t reserved[11];      /* must be zero */
+  float rotary_scan_period;  /* 0 = off (sweeps arrive preprocessed); > 0: every sweep that enters the extraction first
+                                goes through the node's removeNaN + RotaryLidarPreProcess::Process
+                                (Preprocess/RotaryLidar_preprocessing.hpp:31-71: intensity := relative time in the
+                                sweep, SCAN_PERIOD_ = this value, 0.1 in the reference), fused into the ring pass */
+  int32_t reserved[10];      /* must be zero */
 } lmsf_params;
 
 typedef struct {
@@ -133,6 +137,12 @@ int lmsf_voxel_downsample(lmsf_ctx* c, const float* xyzi, int n, float leaf, flo
  * Order preserving.  out_xyzi needs room for n points. */
 int lmsf_common_process(lmsf_ctx* c, const float* xyzi, int n, int remove_nan, float leaf, float dist_near,
                         float dist_far, float* out_xyzi, int* n_out);
+/* Replaces what the node does to a raw sweep before the estimator sees it (src/apps/src/MultiLidarSLAM_node.cpp:126-133,
+ * Preprocess/RotaryLidar_preprocessing.hpp:31-104): pcl::removeNaNFromPointCloud (x, y, z finite; order kept), then
+ * RotaryLidarPreProcess<PointXYZI>::Process — the per-point relative time in the sweep, from the azimuth between the
+ * first and the last point (findStartEndAngle :80-94) with the half-sweep state machine of :38-69, written into the
+ * intensity channel (:100-104).  scan_period = SCAN_PERIOD_ (0.1).  out_xyzi needs room for n points. */
+int lmsf_rotary_preprocess(lmsf_ctx* c, const float* xyzi, int n, float scan_period, float* out_xyzi, int* n_out);
 
 /* ---- seam 3: registration ------------------------------------------- */
 /* = RegistrationBase::SetInputSource (registration/registration_base.hpp:31): upload a

@@ -209,6 +209,33 @@ class CudaPointCloudCommonProcess : public Algorithm::PointCloudProcessBase<_Poi
   std::vector<float> in_, out_;
 };
 
+// ---------------------------------------------------------------- sweep preprocessing (row f4)
+// Same surface as Algorithm::RotaryLidarPreProcess<P> (Preprocess/RotaryLidar_preprocessing.hpp:22-104): Process(LidarData&)
+// rewrites the cloud in place — the node's removeNaN (MultiLidarSLAM_node.cpp:126-133) folded in, intensity := relative time
+// of the point in the sweep.  A tracker context created with lmsf_params.rotary_scan_period > 0 does the same inside its
+// extraction and needs no separate call.
+template <typename _PointT>
+class CudaRotaryLidarPreProcess {
+ public:
+  explicit CudaRotaryLidarPreProcess(ContextPtr ctx, double SCAN_PERIOD = 0.1) : ctx_(std::move(ctx)), period_((float)SCAN_PERIOD) {}
+  virtual ~CudaRotaryLidarPreProcess() {}
+  virtual void Process(Slam3D::LidarData<_PointT>& lidar_data) {
+    detail::pack(lidar_data.point_cloud, in_);
+    const int n = (int)lidar_data.point_cloud.points.size();
+    out_.resize((std::size_t)(n > 0 ? n : 1) * 4);
+    int m = 0;
+    if (!detail::check(lmsf_rotary_preprocess(ctx_->get(), in_.data(), n, period_, out_.data(), &m), "lmsf_rotary_preprocess"))
+      return;  // the cloud is left as it came
+    lidar_data.point_cloud.points = detail::unpack<_PointT>(out_.data(), m)->points;
+    lidar_data.point_cloud.width = (std::uint32_t)m;
+    lidar_data.point_cloud.height = 1;
+  }
+ private:
+  ContextPtr ctx_;
+  float period_;
+  std::vector<float> in_, out_;
+};
+
 // ---------------------------------------------------------------- seam 2
 template <typename _PointType>
 class CudaVoxelGridFilter : public Algorithm::FilterBase<_PointType> {

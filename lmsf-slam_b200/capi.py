@@ -49,7 +49,8 @@ class Params(C.Structure):
         ("kf_rot", C.c_double),
         ("kf_time", C.c_double),
         ("max_map_points", C.c_int32),
-        ("reserved", C.c_int32 * 11),
+        ("rotary_scan_period", C.c_float),
+        ("reserved", C.c_int32 * 10),
     ]
 
 
@@ -198,6 +199,7 @@ class Library:
         f("extract_features").argtypes = [C.c_void_p, _f32p, C.c_int, _u8p, _f32p, _intp, _f32p, _intp]
         f("voxel_downsample").argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, _f32p, _intp, _i32p]
         f("map_set").argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int]
+        f("rotary_preprocess").argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, _f32p, _intp]
         f("knn5").argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int, _i32p, _f32p]
         f("match").argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int, _u8p, _f64p]
         f("register").argtypes = [C.c_void_p, _f32p, C.c_int, _f32p, C.c_int, C.c_int, _f64p, C.POINTER(RegStats)]
@@ -471,6 +473,14 @@ class Context:
         self._chk(self.lib.fn("tracker_register_aux")(self._h, _fp(a), a.shape[0], p.ctypes.data_as(_f64p),
                                                       C.byref(st)))
         return p, st.as_dict()
+
+    def rotary_preprocess(self, xyzi, scan_period: float = 0.1):
+        """removeNaN + RotaryLidarPreProcess::Process: the sweep with intensity := relative time."""
+        a = _xyzi(xyzi)
+        out = np.empty((max(a.shape[0], 1), 4), np.float32)
+        n = C.c_int(0)
+        self._chk(self.lib.fn("rotary_preprocess")(self._h, _fp(a), a.shape[0], float(scan_period), _fp(out), C.byref(n)))
+        return out[: n.value].copy()
 
     def get_map(self, kind: int):
         n = C.c_int(0)

@@ -638,6 +638,23 @@ int lmsf_voxel_downsample(lmsf_ctx* c, const float* xyzi, int n, float leaf, flo
   return LMSF_OK;
 }
 
+int lmsf_rotary_preprocess(lmsf_ctx* c, const float* xyzi, int n, float scan_period, float* out_xyzi, int* n_out) {
+  ENTER(c);
+  LM_TRY(wait_map(c));
+  if (n < 0 || !n_out || !(scan_period > 0.f) || (n > 0 && (!xyzi || !out_xyzi))) return LMSF_ERR_INVALID;
+  if (n > c->prm.max_points) return LMSF_ERR_CAPACITY;
+  *n_out = 0;
+  if (n == 0) return LMSF_OK;
+  LM_CUDA(cudaMemcpyAsync(c->d_tmp, xyzi, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  LM_TRY(rotary_apply(c, c->d_tmp, n, scan_period, c->stream));
+  int m = 0;
+  LM_TRY(filter_run(c, c->d_tmp, n, 0, 0.f, 0.f, c->v_out, &m));  // removeNaN: order-preserving
+  if (m > 0) LM_CUDA(cudaMemcpyAsync(out_xyzi, c->v_out, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  LM_CUDA(cudaStreamSynchronize(c->stream));
+  *n_out = m;
+  return LMSF_OK;
+}
+
 int lmsf_common_process(lmsf_ctx* c, const float* xyzi, int n, int remove_nan, float leaf, float dist_near,
                         float dist_far, float* out_xyzi, int* n_out) {
   ENTER(c);

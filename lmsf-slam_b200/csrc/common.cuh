@@ -65,6 +65,8 @@ struct ExtractBufs {
   uint8_t* label = nullptr;    // [cap] by original index
   int* surf_rank = nullptr;    // [cap] scratch: feature index of the surf at a ring-order position
   int* counts = nullptr;       // [4] n_edge, n_surf, n_valid
+  int* rotary = nullptr;       // [4] RotaryLidarPreProcess state of the sweep in flight: first / last finite point, the
+                               //     point at which half_passed turns true
 };
 
 // ---------------------------------------------------------------- local-map index
@@ -282,6 +284,9 @@ void extract_free(Ctx* c);
 // sweep d_in (n points, device) -> feat_out (edges, then surfs), counts_out[0..1], labels in ex.label; all launches
 // on stream `st`.  The scratch in ExtractBufs is shared: extractions must be ordered on one stream (the front end's).
 int extract_run(Ctx* c, const float4* d_in, int n, cudaStream_t st, float4* feat_out, int* counts_out, int* perm_out);
+// RotaryLidarPreProcess::Process on d_pts[0..n) in place (intensity := relative time; non-finite points are passed over as
+// if removeNaN had dropped them), on stream `st`
+int rotary_apply(Ctx* c, float4* d_pts, int n, float scan_period, cudaStream_t st);
 
 // ---- implemented in voxel.cu
 int voxel_alloc(Ctx* c);

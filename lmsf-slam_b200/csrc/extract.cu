@@ -54,13 +54,112 @@ __device__ __forceinline__ int ring_of(float4 p, const ExtractParams& prm) {
   return id;
 }
 
+// ---- RotaryLidarPreProcess<PointXYZI>::Process (Preprocess/RotaryLidar_preprocessing.hpp:31-104), fused into the ring
+// pass.  The reference walks the points in firing order with one bit of state (half_passed); that bit turns true at the
+// FIRST point whose branch-A angle is more than pi past the start, so the walk is: (1) first / last point, (2) a minimum
+// over the points of "would flip", (3) every point on its own.  float / double mixing as the reference's expressions
+// promote it: comparisons and the +- 2 pi in double, the angles stored back to float, rel_time in float.
+// Points with a non-finite coordinate are passed over: the node's removeNaNFromPointCloud drops them first
+// (MultiLidarSLAM_node.cpp:126-133).
+struct RotaryState {
+  int first, last, half, pad;
+};
+#define ROT_PI 3.14159265358979323846
+__device__ __forceinline__ bool rot_valid(float4 p) { return isfinite(p.x) && isfinite(p.y) && isfinite(p.z); }
+// findStartEndAngle :80-94
+__device__ __forceinline__ void rot_start_end(float4 p0, float4 pl, float& so, float& eo) {
+  so = -atan2f_fdlibm(p0.y, p0.x);
+  eo = (float)((double)(-atan2f_fdlibm(pl.y, pl.x)) + 2 * ROT_PI);
+  if ((double)(eo - so) > 3 * ROT_PI)
+    eo = (float)((double)eo - 2 * ROT_PI);
+  else if ((double)(eo - so) < ROT_PI)
+    eo = (float)((double)eo + 2 * ROT_PI);
+}
+// :42-55, the branch taken while half_passed is false; flips: this point turns it true
+__device__ __forceinline__ float rot_first_half(float4 p, float so, bool& flips) {
+  float ori = -atan2f_fdlibm(p.y, p.x);
+  if ((double)ori < (double)so - ROT_PI / 2)
+    ori = (float)((double)ori + 2 * ROT_PI);
+  else if ((double)ori > (double)so + ROT_PI * 3 / 2)
+    ori = (float)((double)ori - 2 * ROT_PI);
+  flips = (double)(ori - so) > ROT_PI;
+  return ori;
+}
+// :57-67
+__device__ __forceinline__ float rot_second_half(float4 p, float eo) {
+  float ori = -atan2f_fdlibm(p.y, p.x);
+  ori = (float)((double)ori + 2 * ROT_PI);
+  if ((double)ori < (double)eo - ROT_PI * 3 / 2)
+    ori = (float)((double)ori + 2 * ROT_PI);
+  else if ((double)ori > (double)eo + ROT_PI / 2)
+    ori = (float)((double)ori - 2 * ROT_PI);
+  return ori;
+}
+// relative time of point i (:68), given the sweep's state
+__device__ __forceinline__ float rot_rel_time(const float4* __restrict__ in, float4 p, int i, const RotaryState& rs,
+                                              float period) {
+  float so, eo;
+  rot_start_end(in[rs.first], in[rs.last], so, eo);
+  bool flips;
+  const float ori = (i <= rs.half) ? rot_first_half(p, so, flips) : rot_second_half(p, eo);
+  return (ori - so) / (eo - so) * period;
+}
+
+__global__ void k_rotary_init(RotaryState* rs) {
+  if (threadIdx.x == 0) {
+    rs->first = 0x7fffffff;
+    rs->last = -1;
+    rs->half = 0x7fffffff;
+    rs->pad = 0;
+  }
+}
+__device__ __forceinline__ void rot_note_bounds(bool valid, int i, RotaryState* rs) {
+  const unsigned m = __ballot_sync(0xffffffffu, valid);
+  if (m && (threadIdx.x & 31) == 0) {  // lanes are consecutive points: the warp's first and last finite point
+    const int base = i;                // lane 0's point
+    atomicMin(&rs->first, base + __ffs(m) - 1);
+    atomicMax(&rs->last, base + 31 - __clz(m));
+  }
+}
+// standalone bounds pass (lmsf_rotary_preprocess); the extraction does it inside k_ring_classify
+__global__ void __launch_bounds__(256) k_rotary_bounds(const float4* __restrict__ in, int n, RotaryState* rs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  rot_note_bounds(i < n && rot_valid(in[i]), i, rs);
+}
+__global__ void __launch_bounds__(256) k_rotary_half(const float4* __restrict__ in, int n, RotaryState* rs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int first = rs->first, last = rs->last;
+  bool flips = false;
+  if (i < n && last >= 0) {
+    const float4 p = in[i];
+    if (rot_valid(p)) {
+      float so, eo;
+      rot_start_end(in[first], in[last], so, eo);
+      rot_first_half(p, so, flips);
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, flips);
+  if (m && (threadIdx.x & 31) == 0) atomicMin(&rs->half, i + __ffs(m) - 1);
+}
+__global__ void __launch_bounds__(256) k_rotary_apply(float4* __restrict__ pts, int n, const RotaryState* __restrict__ rs,
+                                                      float period) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RotaryState st = *rs;
+  float4 p = pts[i];
+  if (!rot_valid(p)) return;
+  p.w = rot_rel_time(pts, p, i, st, period);
+  pts[i] = p;
+}
+
 __global__ void __launch_bounds__(RING_BLOCK) k_ring_classify(const float4* __restrict__ in, int n, ExtractParams prm,
                                                               int nblk, int* __restrict__ ring_id,
-                                                              int* __restrict__ blk_cnt) {
+                                                              int* __restrict__ blk_cnt, RotaryState* rotary) {
   __shared__ int hist[MAX_RINGS];
   if (threadIdx.x < MAX_RINGS) hist[threadIdx.x] = 0;
   __syncthreads();
   int i = blockIdx.x * RING_BLOCK + threadIdx.x;
+  if (rotary) rot_note_bounds(i < n && rot_valid(in[i]), i, rotary);  // first / last point of the NaN-free sweep
   if (i < n) {
     int id = ring_of(in[i], prm);
     ring_id[i] = id;
@@ -107,7 +206,8 @@ __global__ void __launch_bounds__(RING_BLOCK) k_ring_scatter(const float4* __res
                                                              const int* __restrict__ ring_id,
                                                              const int* __restrict__ blk_off,
                                                              const int* __restrict__ ring_off,
-                                                             float4* __restrict__ ring_pts, int* __restrict__ ring_src) {
+                                                             float4* __restrict__ ring_pts, int* __restrict__ ring_src,
+                                                             const RotaryState* __restrict__ rotary, float period) {
   __shared__ int wcnt[RING_BLOCK / 32][MAX_RINGS];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = threadIdx.x; k < (RING_BLOCK / 32) * MAX_RINGS; k += RING_BLOCK) (&wcnt[0][0])[k] = 0;
@@ -122,7 +222,9 @@ __global__ void __launch_bounds__(RING_BLOCK) k_ring_scatter(const float4* __res
     int base = 0;
     for (int w = 0; w < warp; ++w) base += wcnt[w][id];
     int pos = ring_off[id] + blk_off[id * nblk + blockIdx.x] + base + rank;
-    ring_pts[pos] = in[i];
+    float4 p = in[i];
+    if (rotary) p.w = rot_rel_time(in, p, i, *rotary, period);  // RotaryLidarPreProcess: intensity := relative time
+    ring_pts[pos] = p;
     ring_src[pos] = i;
   }
 }
@@ -476,6 +578,7 @@ int extract_alloc(Ctx* c) {
   x.nblk_cap = div_up(x.cap, RING_BLOCK);
   size_t cap = (size_t)x.cap;
   LM_CUDA(cudaMalloc(&x.ring_id, cap * sizeof(int)));
+  LM_CUDA(cudaMalloc(&x.rotary, 4 * sizeof(int)));
   LM_CUDA(cudaMalloc(&x.blk_cnt, (size_t)MAX_RINGS * x.nblk_cap * sizeof(int)));
   LM_CUDA(cudaMalloc(&x.ring_cnt, MAX_RINGS * sizeof(int)));
   LM_CUDA(cudaMalloc(&x.ring_off, (MAX_RINGS + 1) * sizeof(int)));
@@ -498,6 +601,7 @@ int extract_alloc(Ctx* c) {
 void extract_free(Ctx* c) {
   ExtractBufs& x = c->ex;
   cudaFree(x.ring_id);
+  cudaFree(x.rotary);
   cudaFree(x.blk_cnt);
   cudaFree(x.ring_cnt);
   cudaFree(x.ring_off);
@@ -526,16 +630,33 @@ int extract_run(Ctx* c, const float4* d_in, int n, cudaStream_t st, float4* feat
   const int R = c->prm.n_scans;
   int nblk = div_up(n > 0 ? n : 1, RING_BLOCK);
   LM_CUDA(cudaMemsetAsync(x.label, 0, n > 0 ? n : 1, st));
-  LM_LAUNCH_ON(c, st, k_ring_classify, nblk, RING_BLOCK, 0, d_in, n, prm, nblk, x.ring_id, x.blk_cnt);
+  // rotary_scan_period > 0: removeNaN + RotaryLidarPreProcess ride along (bounds in the classify pass, one small kernel
+  // for the half-sweep point, the relative time written while the points move into ring order)
+  const float period = c->prm.rotary_scan_period;
+  RotaryState* rot = (period > 0.f && n > 0) ? reinterpret_cast<RotaryState*>(x.rotary) : nullptr;
+  if (rot) LM_LAUNCH_ON(c, st, k_rotary_init, 1, 32, 0, rot);
+  LM_LAUNCH_ON(c, st, k_ring_classify, nblk, RING_BLOCK, 0, d_in, n, prm, nblk, x.ring_id, x.blk_cnt, rot);
+  if (rot) LM_LAUNCH_ON(c, st, k_rotary_half, div_up(n, 256), 256, 0, d_in, n, rot);
   LM_LAUNCH_ON(c, st, k_ring_scan, 1, 1024, 0, x.blk_cnt, nblk, x.ring_cnt, x.ring_off, counts_out);
   LM_LAUNCH_ON(c, st, k_ring_scatter, nblk, RING_BLOCK, 0, d_in, n, nblk, x.ring_id, x.blk_cnt, x.ring_off, x.ring_pts,
-               x.ring_src);
+               x.ring_src, rot, period);
   LM_LAUNCH_ON(c, st, k_sector_sort, dim3(6, R), 256, 0, x.ring_pts, x.ring_cnt, x.ring_off, x.curv, x.sorted,
                x.sort_key, x.sort_val);
   LM_LAUNCH_ON(c, st, k_ring_pick, R, 256, 0, x.ring_pts, x.ring_cnt, x.ring_off, x.curv, x.sorted, prm, x.flag,
                x.btype, x.is_edge, x.edge_ids, x.sec_cnt);
   LM_LAUNCH_ON(c, st, k_feat_scatter, dim3(6, R), 256, 0, x.ring_pts, x.ring_src, x.ring_cnt, x.ring_off, x.sorted,
                x.is_edge, x.edge_ids, x.sec_cnt, R, feat_out, x.label, counts_out, x.surf_rank, perm_out);
+  LM_CUDA(cudaGetLastError());
+  return LMSF_OK;
+}
+
+int rotary_apply(Ctx* c, float4* d_pts, int n, float scan_period, cudaStream_t st) {
+  if (n <= 0) return LMSF_OK;
+  RotaryState* rot = reinterpret_cast<RotaryState*>(c->ex.rotary);
+  LM_LAUNCH_ON(c, st, k_rotary_init, 1, 32, 0, rot);
+  LM_LAUNCH_ON(c, st, k_rotary_bounds, div_up(n, 256), 256, 0, d_pts, n, rot);
+  LM_LAUNCH_ON(c, st, k_rotary_half, div_up(n, 256), 256, 0, d_pts, n, rot);
+  LM_LAUNCH_ON(c, st, k_rotary_apply, div_up(n, 256), 256, 0, d_pts, n, rot, scan_period);
   LM_CUDA(cudaGetLastError());
   return LMSF_OK;
 }

@@ -951,6 +951,55 @@ static int need_update(lmsf_oracle_ctx* c, const Iso& curr, double stamp) {
   return 0;
 }
 
+// The node's removeNaNFromPointCloud (src/apps/src/MultiLidarSLAM_node.cpp:126-133) followed by
+// RotaryLidarPreProcess<PointXYZI>::Process (Preprocess/RotaryLidar_preprocessing.hpp:31-71, findStartEndAngle :80-94,
+// setPoint :100-104): intensity := relative time of the point in the sweep.  atan2 of two floats is the float overload
+// (the C library's atan2f); comparisons and the +- 2 pi happen in double and are stored back to float, as the
+// reference's expressions promote them; rel_time is float arithmetic.
+static void rotary_preprocess(const P4* in, int n, float period, std::vector<P4>& out) {
+  out.clear();
+  for (int i = 0; i < n; ++i)
+    if (std::isfinite(in[i].x) && std::isfinite(in[i].y) && std::isfinite(in[i].z)) out.push_back(in[i]);
+  if (out.empty()) return;
+  float start_ori = -std::atan2(out.front().y, out.front().x);
+  float end_ori = -std::atan2(out.back().y, out.back().x) + 2 * M_PI;
+  if (end_ori - start_ori > 3 * M_PI)
+    end_ori -= 2 * M_PI;
+  else if (end_ori - start_ori < M_PI)
+    end_ori += 2 * M_PI;
+  bool half_passed = false;
+  for (size_t i = 0; i < out.size(); ++i) {
+    float ori = -std::atan2(out[i].y, out[i].x);
+    if (!half_passed) {
+      if (ori < start_ori - M_PI / 2)
+        ori += 2 * M_PI;
+      else if (ori > start_ori + M_PI * 3 / 2)
+        ori -= 2 * M_PI;
+      if (ori - start_ori > M_PI) half_passed = true;
+    } else {
+      ori += 2 * M_PI;
+      if (ori < end_ori - M_PI * 3 / 2)
+        ori += 2 * M_PI;
+      else if (ori > end_ori + M_PI / 2)
+        ori -= 2 * M_PI;
+    }
+    out[i].i = (ori - start_ori) / (end_ori - start_ori) * period;
+  }
+}
+
+// rotary_scan_period > 0: the sweep the extraction sees is the preprocessed one.  The points keep their places (labels are
+// by input index); the non-finite ones, which removeNaN drops, are passed over by the extraction anyway (ring_of).
+static const P4* preprocessed(const lmsf_oracle_params& prm, const P4* in, int n, std::vector<P4>& work) {
+  if (!(prm.rotary_scan_period > 0.f) || n <= 0) return in;
+  std::vector<P4> dense;
+  rotary_preprocess(in, n, prm.rotary_scan_period, dense);
+  work.assign(in, in + n);
+  size_t k = 0;
+  for (int i = 0; i < n; ++i)
+    if (std::isfinite(in[i].x) && std::isfinite(in[i].y) && std::isfinite(in[i].z)) work[i].i = dense[k++].i;
+  return work.data();
+}
+
 static void scan_filter(lmsf_oracle_ctx* c, Features& f) {
   if (c->prm.scan_leaf_edge > 0.f) {
     std::vector<P4> ds;
@@ -1054,11 +1103,22 @@ int lmsf_oracle_extract_features(lmsf_oracle_ctx* c, const float* xyzi, int n, u
                                  int* n_edge, float* surf_xyzi, int* n_surf) {
   if (!c || n < 0 || (n > 0 && !xyzi)) return -1;
   Features f;
-  extract(c->prm, reinterpret_cast<const P4*>(xyzi), n, label_out, f);
+  std::vector<P4> work;
+  extract(c->prm, preprocessed(c->prm, reinterpret_cast<const P4*>(xyzi), n, work), n, label_out, f);
   if (edge_xyzi && !f.edge.empty()) std::memcpy(edge_xyzi, f.edge.data(), f.edge.size() * sizeof(P4));
   if (surf_xyzi && !f.surf.empty()) std::memcpy(surf_xyzi, f.surf.data(), f.surf.size() * sizeof(P4));
   if (n_edge) *n_edge = (int)f.edge.size();
   if (n_surf) *n_surf = (int)f.surf.size();
+  return 0;
+}
+
+int lmsf_oracle_rotary_preprocess(lmsf_oracle_ctx* c, const float* xyzi, int n, float scan_period, float* out_xyzi,
+                                  int* n_out) {
+  if (!c || n < 0 || !n_out || !(scan_period > 0.f) || (n > 0 && (!xyzi || !out_xyzi))) return -1;
+  std::vector<P4> out;
+  rotary_preprocess(reinterpret_cast<const P4*>(xyzi), n, scan_period, out);
+  if (!out.empty()) std::memcpy(out_xyzi, out.data(), out.size() * sizeof(P4));
+  *n_out = (int)out.size();
   return 0;
 }
 
@@ -1221,7 +1281,8 @@ int lmsf_oracle_tracker_step(lmsf_oracle_ctx* c, const float* xyzi, int n, doubl
                              double pose_out[7], lmsf_oracle_track_stats* st) {
   if (!c || !delta || !pose_out) return -1;
   Features f;
-  extract(c->prm, reinterpret_cast<const P4*>(xyzi), n, nullptr, f);
+  std::vector<P4> work;
+  extract(c->prm, preprocessed(c->prm, reinterpret_cast<const P4*>(xyzi), n, work), n, nullptr, f);
   scan_filter(c, f);
   tracker_solve(c, f, stamp, delta, pose_out, st);
   return 0;
@@ -1249,7 +1310,8 @@ int lmsf_oracle_tracker_register_aux(lmsf_oracle_ctx* c, const float* xyzi, int 
                                      lmsf_oracle_reg_stats* st) {
   if (!c || !pose) return -1;
   Features f;
-  extract(c->prm, reinterpret_cast<const P4*>(xyzi), n, nullptr, f);
+  std::vector<P4> work;
+  extract(c->prm, preprocessed(c->prm, reinterpret_cast<const P4*>(xyzi), n, work), n, nullptr, f);
   scan_filter(c, f);
   // Solve(Isometry3d&): quaternion -> matrix -> quaternion round trip of the adapter
   Iso T = iso_from_pose7(pose);

@@ -77,9 +77,10 @@ typedef struct {
   float huber_delta;
   double kf_trans, kf_rot, kf_time;
   int32_t max_map_points;
+  float rotary_scan_period; /* 0 = off; > 0: removeNaN + RotaryLidarPreProcess before every extraction */
   int32_t knn_mode; /* 0 = kd-tree (leaf 15), 1 = brute force */
   int32_t threads;  /* OpenMP threads over features in the match loops; <=1 = serial (the reference) */
-  int32_t reserved[9];
+  int32_t reserved[8];
 } lmsf_oracle_params;
 
 typedef struct {
@@ -106,6 +107,9 @@ const char* lmsf_oracle_strerror(int code);
 
 int lmsf_oracle_extract_features(lmsf_oracle_ctx* c, const float* xyzi, int n, uint8_t* label_out,
                                  float* edge_xyzi, int* n_edge, float* surf_xyzi, int* n_surf);
+/* removeNaN + RotaryLidarPreProcess<PointXYZI>::Process (Preprocess/RotaryLidar_preprocessing.hpp:31-104) */
+int lmsf_oracle_rotary_preprocess(lmsf_oracle_ctx* c, const float* xyzi, int n, float scan_period, float* out_xyzi,
+                                  int* n_out);
 int lmsf_oracle_voxel_downsample(lmsf_oracle_ctx* c, const float* xyzi, int n, float leaf,
                                  float* out_xyzi, int* n_out, int32_t* voxel_of_point);
 int lmsf_oracle_map_set(lmsf_oracle_ctx* c, int kind, const float* xyzi, int n);

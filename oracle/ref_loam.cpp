@@ -17,6 +17,8 @@
 using namespace std;  // the reference's headers use unqualified `string` / `make_pair` (an earlier using-directive)
 
 #include "Algorithm/PointClouds/processing/FeatureExtract/LOAMFeatureProcessor_base.hpp"
+#include "Algorithm/PointClouds/processing/Preprocess/RotaryLidar_preprocessing.hpp"
+#include <pcl/filters/filter.h>  // removeNaNFromPointCloud (the stand-in of oracle/shim: x, y, z finite, order kept)
 
 namespace {
 
@@ -92,4 +94,19 @@ int ref_common_process(const float* xyzi, int n, int remove_nan, float dist_near
   return 0;
 }
 
+
+// What the node does to a raw sweep before the estimator sees it: getCloudFromMsg's pcl::removeNaNFromPointCloud
+// (src/apps/src/MultiLidarSLAM_node.cpp:126-133), then RotaryLidarPreProcess<PointXYZI>::Process
+// (Preprocess/RotaryLidar_preprocessing.hpp:31-104).  Returns the number of points written (cap: capacity of out).
+int ref_rotary_preprocess(const float* xyzi, int n, double scan_period, int cap, float* out) {
+  Slam3D::LidarData<Point> data;
+  load(xyzi, n, data.point_cloud);
+  data.point_cloud.is_dense = false;  // as a driver publishes a cloud that may hold NaN returns (dense clouds are copied)
+  std::vector<int> indices;
+  pcl::removeNaNFromPointCloud(data.point_cloud, data.point_cloud, indices);
+  if (data.point_cloud.points.empty()) return 0;  // the reference would index points[0] of an empty cloud
+  Algorithm::RotaryLidarPreProcess<Point> pre(scan_period);
+  pre.Process(data);
+  return store(data.point_cloud, out, cap);
+}
 }  // extern "C"

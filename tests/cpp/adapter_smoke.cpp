@@ -89,6 +89,19 @@ int main(int argc, char** argv) {
     std::printf("common %zu\n", pc.pointcloud_data_["processed"]->size());
   }
 
+  // sweep preprocessing behind RotaryLidarPreProcess's surface: the relative times end up in the intensity channel
+  {
+    lmsf::CudaRotaryLidarPreProcess<Pt> rot(ctx, 0.1);
+    Slam3D::LidarData<Pt> d = load(buf.data(), n0);
+    rot.Process(d);
+    float lo = 1e9f, hi = -1e9f;
+    for (auto const& q : d.point_cloud.points) {
+      lo = q.intensity < lo ? q.intensity : lo;
+      hi = q.intensity > hi ? q.intensity : hi;
+    }
+    std::printf("rotary %zu %.6f %.6f\n", d.point_cloud.points.size(), lo, hi);
+  }
+
   // multi-LiDAR extrinsics: compile-and-run check of the calibration loop class (two contexts, same sweeps: the
   // increments are identical, so the pairs are accepted; identical LiDARs cannot excite the rotation -> status stays 0)
   {

@@ -252,3 +252,52 @@ def check_tracker_against_reference(ctx, synth, exact, n_sweeps=14, window=3):
                 assert np.abs(m_r[:n, :3] - m_o[:, :3]).max() < 1e-4, (k, kind)
     dll.ref_tracker_destroy(h)
     return kinds
+
+
+def rotary_cases(synth):
+    """Sweeps for the rotary preprocess: VLP-16 / HDL-64 as they arrive (a full turn starting at azimuth 0), a sweep that
+    starts mid-turn and one that wraps (start / end angle logic, findStartEndAngle :80-94), NaN / inf points that
+    removeNaN drops (among them the first and the last point), a partial sweep, tiny clouds."""
+    cases = []
+    for sensor, k in ((synth.vlp16(), 3), (synth.hdl64(), 7)):
+        cases.append(synth.make_sweep(sensor, k))
+    v = synth.make_sweep(synth.vlp16(), 5)
+    n = len(v)
+    cases.append(np.ascontiguousarray(np.roll(v, n // 3, axis=0)))            # starts a third of a turn in
+    cases.append(np.ascontiguousarray(np.roll(v, -(n // 7) * 1, axis=0)))
+    cases.append(np.ascontiguousarray(v[: n // 2]))                            # half a turn
+    cases.append(np.ascontiguousarray(v[n // 5: n - n // 9]))
+    w = v.copy()
+    w[0, 0] = np.nan                                                           # the first point is dropped
+    w[-1, 2] = np.inf                                                          # and the last
+    w[::13, 1] = np.nan
+    w[7, :3] = -np.inf
+    cases.append(w)
+    m = v[:, :].copy()
+    m[:, 1] *= -1.0                                                            # a LiDAR spinning the other way
+    cases.append(np.ascontiguousarray(m))
+    cases.append(np.ascontiguousarray(v[:1]))
+    cases.append(np.ascontiguousarray(v[:2]))
+    cases.append(np.full((5, 4), np.nan, np.float32))
+    return cases
+
+
+def check_rotary_against_reference(pre, synth, periods=(0.1, 0.05)):
+    """pre(xyzi, period) -> preprocessed cloud (oracle or CUDA library) against the reference's removeNaN +
+    RotaryLidarPreProcess<PointXYZI>::Process (Preprocess/RotaryLidar_preprocessing.hpp:31-104, compiled into
+    oracle/_ref/libref_loam.so), bit for bit, every case of rotary_cases."""
+    dll = C.CDLL(_ref_path("libref_loam.so"))
+    fp = C.POINTER(C.c_float)
+    n_pts = 0
+    for cloud in rotary_cases(synth):
+        cloud = np.ascontiguousarray(cloud, np.float32)
+        for period in periods:
+            ref = np.zeros((max(len(cloud), 1), 4), np.float32)
+            n = dll.ref_rotary_preprocess(cloud.ctypes.data_as(fp), len(cloud), C.c_double(period), len(ref),
+                                          ref.ctypes.data_as(fp))
+            assert n >= 0
+            out = pre(cloud, period)
+            assert len(out) == n, (len(cloud), period)
+            assert np.array_equal(bits(out), bits(ref[:n])), (len(cloud), period)
+            n_pts += n
+    return n_pts

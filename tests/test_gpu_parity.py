@@ -539,6 +539,32 @@ def test_device_algebra_bit_exact():
     assert "atan2f/sqrtf mismatches (4M arguments) 0" in r.stdout, r.stdout
 
 
+def test_extract_with_fused_rotary_preprocess(ctxs, synth):
+    """rotary_scan_period > 0: removeNaN + RotaryLidarPreProcess ride inside the extraction (bounds in the ring-classify
+    pass, relative time written while the points move into ring order).  Features — coordinates AND the relative time in
+    their intensity — and labels bit-identical to the oracle (which preprocesses, then extracts), for a clean sweep, a
+    shifted one and one with NaN points; and equal to extracting the separately preprocessed cloud."""
+    import ref_pin
+    for n_scans, sensor in ((16, synth.vlp16()), (64, synth.hdl64())):
+        g, o = ctxs(n_scans=n_scans, rotary_scan_period=0.1)
+        g0, _ = ctxs(n_scans=n_scans)
+        sw = synth.make_sweep(sensor, 4)
+        shifted = np.ascontiguousarray(np.roll(sw, len(sw) // 3, axis=0))
+        holes = sw.copy()
+        holes[0, 0] = np.nan
+        holes[-1, 1] = np.inf
+        holes[::17, 2] = np.nan
+        for cloud in (sw, shifted, holes):
+            lg, eg, sg = g.extract_features(cloud)
+            lo, eo, so = o.extract_features(cloud)
+            assert np.array_equal(lg, lo)
+            assert np.array_equal(bits(eg), bits(eo)) and np.array_equal(bits(sg), bits(so))
+            pre = g0.rotary_preprocess(cloud, 0.1)
+            _, e2, s2 = g0.extract_features(pre)
+            assert np.array_equal(bits(eg), bits(e2)) and np.array_equal(bits(sg), bits(s2))
+            assert len(sg) > 1000 and np.ptp(sg[:, 3]) > 0.05      # the intensity channel now holds times in [0, 0.1]
+
+
 @pytest.mark.parametrize("binary", ["adapter_smoke", "adapter_smoke_ref"])
 def test_cpp_adapters_match_ctypes_path(gpu_lib, sweeps, tmp_path, binary):
     """The reference-shaped C++ adapters (PointCloudProcessBase / FilterBase / RegistrationBase) give the
@@ -566,6 +592,9 @@ def test_cpp_adapters_match_ctypes_path(gpu_lib, sweeps, tmp_path, binary):
     assert lines["rig"] == ["1", "1", "0"]
     gc = gpu_lib.context(0, n_scans=16)
     assert int(lines["common"][0]) == len(gc.common_process(s0, True, 0.5, 3.0, 40.0))
+    pre = gc.rotary_preprocess(s0, 0.1)
+    assert int(lines["rotary"][0]) == len(pre)
+    assert abs(float(lines["rotary"][1]) - pre[:, 3].min()) < 1e-6 and abs(float(lines["rotary"][2]) - pre[:, 3].max()) < 1e-6
     gc.close()
     a_score, a_ov, self_score, self_ov = (float(x) for x in lines["align"])
     assert self_score == 0.0 and self_ov == 1.0 and 0.3 < a_ov <= 1.0 and a_score < 1.0

@@ -889,6 +889,16 @@ def test_lm_register_vs_reference_code(oracle_lib, synth):
     assert outers == [9, 8, 7, 6, 5, 4, 3, 2, 2, 2, 2, 2]
 
 
+def test_rotary_preprocess_vs_reference_code(oracle_lib, synth):
+    """Row f4 (first half) PINNED: the oracle's removeNaN + RotaryLidarPreProcess against the reference's own
+    Preprocess/RotaryLidar_preprocessing.hpp:31-104 (the per-point relative time written into the intensity channel) on
+    full, shifted, partial, reversed and NaN-ridden sweeps, bit for bit."""
+    o = oracle_lib.context(0, n_scans=16)
+    n = ref_pin.check_rotary_against_reference(o.rotary_preprocess, synth)
+    o.close()
+    assert n > 400000
+
+
 def test_tracker_vs_reference_code(oracle_lib, synth):
     """Row a6 PINNED: the oracle's tracker against the reference's own LidarTrackerLocalMap::Solve / updateLocalMap /
     needUpdataLocalMap (LidarTracker/LidarTrackerLocalMap.hpp:107-262), compiled from the unmodified header with the

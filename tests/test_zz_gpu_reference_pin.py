@@ -57,3 +57,13 @@ def test_cuda_tracker_vs_reference_code(gpu_lib, synth):
     kinds = ref_pin.check_tracker_against_reference(g, synth, exact=False)
     g.close()
     assert kinds[0] == 1 and 2 in kinds and kinds.count(1) >= 4 and 0 in kinds
+
+
+def test_cuda_rotary_preprocess_vs_reference_code(gpu_lib, synth):
+    """Row f4: lmsf_rotary_preprocess == removeNaN + RotaryLidarPreProcess<PointXYZI>::Process
+    (Preprocess/RotaryLidar_preprocessing.hpp:31-104), bit for bit, on full / shifted / partial / reversed / NaN-ridden
+    sweeps."""
+    g = gpu_lib.context(0, n_scans=64)
+    n = ref_pin.check_rotary_against_reference(g.rotary_preprocess, synth)
+    g.close()
+    assert n > 400000
