@@ -555,14 +555,16 @@ def run_loopdb(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    search = pkg.shard.loop_search_sharded if args.loop_exchange == 1 else pkg.shard.loop_search_sharded_2round
+
     def step_resident():
-        return pkg.shard.loop_search_sharded(ctx, d_qk, d_qd, limit, lo, hi, 0.2)
+        return search(ctx, d_qk, d_qd, limit, lo, hi, 0.2)
 
     def step_e2e():
         with torch.cuda.stream(stream):
             a = h_qk.to(dev, non_blocking=True)
             b = h_qd.to(dev, non_blocking=True)
-        ids, dd, sh = pkg.shard.loop_search_sharded(ctx, a, b, limit, lo, hi, 0.2)
+        ids, dd, sh = search(ctx, a, b, limit, lo, hi, 0.2)
         with torch.cuda.stream(stream):
             out = (ids.cpu(), dd.cpu(), sh.cpu())
         stream.synchronize()
@@ -603,8 +605,12 @@ def run_loopdb(args):
             "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "ScanContext loop search: 100 000-keyframe database sharded over the ranks, "
-                                   f"{LOOP_NQ} replicated queries per step, exact ring-key top-10 + SC distance per shard, "
-                                   "one all_gather of 24-byte candidates, identical selection on every rank",
+                                   f"{LOOP_NQ} replicated queries per step, exact ring-key top-10 per shard, " +
+                                   ("SC distance of the 10 local candidates on every rank, one all_gather of 24-byte "
+                                    "candidates" if args.loop_exchange == 1 else
+                                    "all_gather of the unscored candidates, SC distance of the global top-10 by their "
+                                    "owners only, second all_gather") + ", identical selection on every rank",
+                       "exchange_rounds": args.loop_exchange,
                        "database": LOOP_DB, "searched_prefix": int(limit), "queries_per_step": LOOP_NQ,
                        "shard": [int(lo), int(hi)], "recall_of_planted_revisits": hit,
                        "l2": f"{FLUSH_BYTES >> 20} MiB memset between timed steps (L2 flush), inside the timed region",
@@ -644,6 +650,9 @@ def main():
     ap.add_argument("--sensor", default="hdl64", choices=sorted(SENSORS), help="hdl64 = the headline configuration")
     ap.add_argument("--map-leaf", default="", help="E,S: voxel-filter the local map at these leaf sizes (LIO-SAM-style "
                     "0.2,0.4); default: the shipped tracker's raw window")
+    ap.add_argument("--loop-exchange", type=int, default=2, choices=[1, 2],
+                    help="loopdb: 1 = every rank scores its 10 local candidates, one all_gather; 2 = two rounds, only the "
+                         "global top-10 are scored, by their owners")
     ap.add_argument("--workload", default="registration", choices=["registration", "loopdb"],
                     help="registration = the headline metric (default); loopdb = sharded loop-closure descriptor search")
     args = ap.parse_args()

@@ -265,6 +265,16 @@ int lmsf_scdb_knn(lmsf_ctx* c, const float* q_keys, int nq, int limit, int32_t* 
  * limit = size of polarcontext_ringkeys_to_search_ (see lmsf_sc_tree_limit). */
 int lmsf_scdb_search(lmsf_ctx* c, const float* q_keys, const float* q_descs, int nq, int limit, double thresh,
                      int32_t* loop_id, double* loop_dist, int32_t* loop_shift);
+/* Two-round variant of the sharded search (the dominant per-shard cost of the one-round exchange is scoring 10
+ * candidates per query on EVERY rank): round 1 — lmsf_scdb_keys_shard_dev: the shard's ring-key top-10 as unscored
+ * lmsf_sc_cand records (sc_dist = 1e7), all-gathered by the caller; round 2 — lmsf_scdb_score_owned_dev: every rank
+ * derives the same global ring-key top-10 from the n_ranks x nq x 10 records and computes the ScanContext distance of
+ * the candidates it owns (global ids [id_base, id_base + n_local)), writing the others as empty slots; the scored
+ * blocks are all-gathered again and lmsf_scdb_pick_dev selects exactly as in the one-round scheme.  Device pointers,
+ * work enqueued on the context's stream. */
+int lmsf_scdb_keys_shard_dev(lmsf_ctx* c, const float* d_q_keys, int nq, int limit_local, int id_base, void* d_cand);
+int lmsf_scdb_score_owned_dev(lmsf_ctx* c, const void* d_cand_all, int n_ranks, int nq, const float* d_q_descs,
+                              int id_base, int n_local, void* d_scored);
 /* Sharded search (one database shard per GPU): ring-key top-10 and SC distances of nq DEVICE queries
  * against local ids [0, limit_local); d_cand receives nq x 10 lmsf_sc_cand with id = local id + id_base.
  * The caller all-gathers the candidate blocks of all ranks (NCCL) and calls lmsf_scdb_pick_dev on

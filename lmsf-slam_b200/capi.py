@@ -134,6 +134,7 @@ class Library:
         # loop-closure descriptor path (scancontext.cu)
         "sc_make", "sc_distance", "scdb_reserve", "scdb_clear", "scdb_size", "scdb_add", "scdb_add_cloud",
         "scdb_get", "scdb_knn", "scdb_search", "scdb_search_shard_dev", "scdb_pick_dev", "sc_tree_limit",
+        "scdb_keys_shard_dev", "scdb_score_owned_dev",
         # multi-LiDAR extrinsic initialisation (calib.cu, host arithmetic)
         "handeye_create", "handeye_destroy", "handeye_add_pose", "handeye_calibrate", "handeye_size",
     )
@@ -187,6 +188,9 @@ class Library:
                                                    C.c_void_p]
             f("scdb_pick_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
+            f("scdb_keys_shard_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+            f("scdb_score_owned_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                                  C.c_void_p]
             f("sc_tree_limit").argtypes = [C.c_int]
             f("handeye_create").argtypes = [C.POINTER(C.c_void_p)]
             f("handeye_destroy").argtypes = [C.c_void_p]
@@ -593,6 +597,15 @@ class Context:
                               d_cand: int):
         self._chk(self.lib.fn("scdb_search_shard_dev")(self._h, C.c_void_p(d_q_keys), C.c_void_p(d_q_descs), nq,
                                                        int(limit_local), int(id_base), C.c_void_p(d_cand)))
+
+    def scdb_keys_shard_dev(self, d_q_keys: int, nq: int, limit_local: int, id_base: int, d_cand: int):
+        self._chk(self.lib.fn("scdb_keys_shard_dev")(self._h, C.c_void_p(d_q_keys), nq, int(limit_local), int(id_base),
+                                                     C.c_void_p(d_cand)))
+
+    def scdb_score_owned_dev(self, d_cand_all: int, n_ranks: int, nq: int, d_q_descs: int, id_base: int, n_local: int,
+                             d_scored: int):
+        self._chk(self.lib.fn("scdb_score_owned_dev")(self._h, C.c_void_p(d_cand_all), n_ranks, nq, C.c_void_p(d_q_descs),
+                                                      int(id_base), int(n_local), C.c_void_p(d_scored)))
 
     def scdb_pick_dev(self, d_cand_all: int, n_ranks: int, nq: int, thresh: float, d_id: int, d_dist: int,
                       d_shift: int):

@@ -464,6 +464,93 @@ __global__ void __launch_bounds__(64) k_sc_dist_cand(const float* __restrict__ q
   }
 }
 
+// ---- two-round exchange (sharded search): round 1 gathers every shard's ring-key top-10 WITHOUT ScanContext distances,
+// every rank derives the same global top-10 and scores only the candidates it owns (about 10 / n_ranks per query
+// instead of 10), round 2 gathers the scored records and k_sc_pick selects as before.
+// the shard's ring-key top-10 as unscored candidate records
+__global__ void __launch_bounds__(256) k_sc_keys_to_cand(const float* __restrict__ top_d, const int* __restrict__ top_i,
+                                                         int n, int id_base, ScCand* __restrict__ cand) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  const int id = top_i[o];
+  ScCand r;
+  r.sc_dist = 10000000.0;
+  r.key_dist = top_d[o];
+  r.id = id >= 0 ? id + id_base : -1;
+  r.shift = 0;
+  r.pad = 0;
+  cand[o] = r;
+}
+// the global ring-key top-10 by (key distance, id) of every query out of n_ranks x 10 unscored records -> sel[q][10]
+__global__ void __launch_bounds__(128) k_sc_select_global(const ScCand* __restrict__ all, int n_ranks, int nq,
+                                                          ScCand* __restrict__ sel) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  float kd[SC_K];
+  int kid[SC_K];
+#pragma unroll
+  for (int k = 0; k < SC_K; ++k) {
+    kd[k] = __int_as_float(0x7f800000);
+    kid[k] = 0x7fffffff;
+  }
+  for (int r = 0; r < n_ranks; ++r)
+    for (int j = 0; j < SC_K; ++j) {
+      const ScCand& cnd = all[(r * nq + q) * SC_K + j];
+      if (cnd.id < 0) continue;
+      float dd = cnd.key_dist;
+      int ii = cnd.id;
+      if (dd < kd[SC_K - 1] || (dd == kd[SC_K - 1] && ii < kid[SC_K - 1])) {
+        kd[SC_K - 1] = dd;
+        kid[SC_K - 1] = ii;
+#pragma unroll
+        for (int k = SC_K - 1; k > 0; --k) {
+          bool sw = kd[k] < kd[k - 1] || (kd[k] == kd[k - 1] && kid[k] < kid[k - 1]);
+          if (sw) {
+            float td = kd[k];
+            kd[k] = kd[k - 1];
+            kd[k - 1] = td;
+            int ti = kid[k];
+            kid[k] = kid[k - 1];
+            kid[k - 1] = ti;
+          }
+        }
+      }
+    }
+#pragma unroll
+  for (int k = 0; k < SC_K; ++k) {
+    ScCand r;
+    r.sc_dist = 10000000.0;
+    r.key_dist = kd[k];
+    r.id = kid[k] == 0x7fffffff ? -1 : kid[k];
+    r.shift = 0;
+    r.pad = 0;
+    sel[(size_t)q * SC_K + k] = r;
+  }
+}
+// block (k, q): the ScanContext distance of sel[q][k] if this shard owns it (global ids [id_base, id_base + n_local));
+// a candidate of another shard is written as an empty slot — its owner reports it
+__global__ void __launch_bounds__(64) k_sc_dist_owned(const float* __restrict__ q_descs, const float* __restrict__ descs,
+                                                      const ScCand* __restrict__ sel, int id_base, int n_local,
+                                                      ScCand* __restrict__ out) {
+  const size_t o = (size_t)blockIdx.y * SC_K + blockIdx.x;
+  ScCand r = sel[o];
+  const int local = r.id - id_base;
+  const bool mine = r.id >= 0 && local >= 0 && local < n_local;
+  __shared__ double d;
+  __shared__ int sh;
+  if (mine) sc_distance_block(q_descs + (size_t)blockIdx.y * SC_CELLS, descs + (size_t)local * SC_CELLS, &d, &sh);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (mine) {
+      r.sc_dist = d;
+      r.shift = sh;
+    } else {
+      r.id = -1;
+    }
+    out[o] = r;
+  }
+}
+
 // descFindSimilar's selection (:296-323) over the candidates of `n_ranks` shards: the global ring-key top-10 by
 // (key distance, id) first, then the first strict minimum of the SC distance in that order, then the threshold.
 __global__ void __launch_bounds__(128) k_sc_pick(const ScCand* __restrict__ all, int n_ranks, int nq, double thresh,
@@ -818,6 +905,30 @@ int lmsf_scdb_search_shard_dev(lmsf_ctx* c, const float* d_q_keys, const float* 
     return LMSF_ERR_INVALID;
   if (nq == 0) return LMSF_OK;
   return search_shard_dev(c, d, d_q_keys, d_q_descs, nq, limit_local, id_base, (ScCand*)d_cand);
+}
+
+int lmsf_scdb_keys_shard_dev(lmsf_ctx* c, const float* d_q_keys, int nq, int limit_local, int id_base, void* d_cand) {
+  ENTER(c);
+  ScDb* d = scdb_of(c);
+  if (nq < 0 || limit_local < 0 || limit_local > d->n || (nq > 0 && (!d_q_keys || !d_cand))) return LMSF_ERR_INVALID;
+  if (nq == 0) return LMSF_OK;
+  LM_TRY(knn_dev(c, d, d_q_keys, nq, limit_local));
+  LM_LAUNCH(c, k_sc_keys_to_cand, div_up(nq * SC_K, 256), 256, 0, d->top_d, d->top_i, nq * SC_K, id_base, (ScCand*)d_cand);
+  return LMSF_OK;
+}
+
+int lmsf_scdb_score_owned_dev(lmsf_ctx* c, const void* d_cand_all, int n_ranks, int nq, const float* d_q_descs,
+                              int id_base, int n_local, void* d_scored) {
+  ENTER(c);
+  ScDb* d = scdb_of(c);
+  if (nq < 0 || n_ranks < 1 || n_local < 0 || n_local > d->n || (nq > 0 && (!d_cand_all || !d_q_descs || !d_scored)))
+    return LMSF_ERR_INVALID;
+  if (nq == 0) return LMSF_OK;
+  LM_TRY(ensure_query(c, d, nq, 1));
+  LM_LAUNCH(c, k_sc_select_global, div_up(nq, 128), 128, 0, (const ScCand*)d_cand_all, n_ranks, nq, d->cand);
+  dim3 grid(SC_K, nq);
+  LM_LAUNCH(c, k_sc_dist_owned, grid, 64, 0, d_q_descs, d->descs, d->cand, id_base, n_local, (ScCand*)d_scored);
+  return LMSF_OK;
 }
 
 int lmsf_scdb_pick_dev(lmsf_ctx* c, const void* d_cand_all, int n_ranks, int nq, double thresh, int32_t* d_loop_id,

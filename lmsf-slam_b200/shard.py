@@ -95,6 +95,39 @@ def gather_candidates(local_cand: torch.Tensor) -> torch.Tensor:
     return out.view(world, nq, 10, 24)
 
 
+def loop_search_sharded_2round(ctx, q_keys: torch.Tensor, q_descs: torch.Tensor, limit_global: int, lo: int, hi: int,
+                               thresh: float = 0.2):
+    """Sharded descFindSimilar with TWO exchange steps: the ScanContext distance — the dominant per-rank cost of the
+    one-step scheme, 10 candidates per query on every rank whatever the world size — is only computed for the
+    candidates that survive the GLOBAL ring-key top-10, by the rank that owns them (about 10 / world per query).
+
+      round 1  lmsf_scdb_keys_shard_dev: local ring-key top-10 (unscored records) -> all_gather
+      round 2  lmsf_scdb_score_owned_dev: every rank derives the same global top-10 and scores what it owns -> all_gather
+      pick     lmsf_scdb_pick_dev, as in the one-step scheme (each surviving candidate now appears exactly once)
+
+    Same arguments and results as loop_search_sharded (identical to the unsharded search)."""
+    if not (q_keys.is_cuda and q_descs.is_cuda):
+        raise ValueError("queries must be CUDA tensors (there is no CPU path)")
+    nq = int(q_keys.shape[0])
+    dev = q_keys.device
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    n_local = shard_limit(limit_global, lo, hi)   # only the searched prefix can be a candidate
+    with torch.cuda.stream(stream):
+        cand = torch.empty((nq, 10, 24), dtype=torch.uint8, device=dev)
+        ctx.scdb_keys_shard_dev(q_keys.data_ptr(), nq, n_local, lo, cand.data_ptr())
+        allc = gather_candidates(cand)
+        scored = torch.empty((nq, 10, 24), dtype=torch.uint8, device=dev)
+        ctx.scdb_score_owned_dev(allc.data_ptr(), world, nq, q_descs.data_ptr(), lo, n_local, scored.data_ptr())
+        alls = gather_candidates(scored)
+        loop_id = torch.empty(nq, dtype=torch.int32, device=dev)
+        loop_dist = torch.empty(nq, dtype=torch.float64, device=dev)
+        loop_shift = torch.empty(nq, dtype=torch.int32, device=dev)
+        ctx.scdb_pick_dev(alls.data_ptr(), world, nq, thresh, loop_id.data_ptr(), loop_dist.data_ptr(),
+                          loop_shift.data_ptr())
+    return loop_id, loop_dist, loop_shift
+
+
 def loop_search_sharded(ctx, q_keys: torch.Tensor, q_descs: torch.Tensor, limit_global: int, lo: int, hi: int,
                         thresh: float = 0.2):
     """Sharded descFindSimilar for a batch of DEVICE queries (replicated on every rank).

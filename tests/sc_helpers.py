@@ -197,6 +197,29 @@ def py_pick(all_cand, thresh=0.2):
     return lid, dist, sh
 
 
+def py_select_and_score(all_keys, lo, n_local, score):
+    """Round 2 of the two-round exchange on one rank, in numpy: the global ring-key top-10 of every query out of the
+    gathered unscored records (world, nq, 10); the candidates this rank owns (ids [lo, lo + n_local)) scored with
+    score(q, id) -> (dist, shift), the others written as empty slots.  Returns (nq, 10) records."""
+    w, nq, _ = all_keys.shape
+    out = np.zeros((nq, K), CAND_DTYPE)
+    out["id"] = -1
+    out["sc_dist"] = 10000000.0
+    out["key_dist"] = np.inf
+    for q in range(nq):
+        c = all_keys[:, q, :].reshape(-1)
+        c = c[c["id"] >= 0]
+        order = np.lexsort((c["id"], c["key_dist"]))[:K]
+        for k, j in enumerate(order):
+            gid = int(c["id"][j])
+            if lo <= gid < lo + n_local:
+                d, s = score(q, gid)
+                out[q, k] = (d, c["key_dist"][j], gid, s, 0)
+            else:
+                out[q, k]["key_dist"] = c["key_dist"][j]
+    return out
+
+
 # ---------------------------------------------------------------- seeded descriptor data
 def random_descs(n, seed, zero_cols=0.15):
     """Height-map-like descriptors: smooth-ish positive values, some empty bins and empty sectors."""

@@ -153,6 +153,31 @@ def test_sharded_selection_equals_unsharded(gpu_lib, sco):
         assert np.array_equal(out_id.cpu().numpy(), l_o)
         assert np.array_equal(out_d.cpu().numpy().view(np.uint64), d_o.view(np.uint64))
         assert np.array_equal(out_s.cpu().numpy(), s_o)
+        # the two-round exchange on the same shards: unscored ring-key records first, then every shard scores what it
+        # owns of the GLOBAL top-10, then the same pick — identical results, 10 scored candidates per query in total
+        kblocks = []
+        for c, (lo, hi) in zip(ctxs, bounds):
+            cand = torch.empty((nq, 10, 24), dtype=torch.uint8, device="cuda")
+            c.scdb_keys_shard_dev(tq_k.data_ptr(), nq, max(0, min(limit, hi) - lo), lo, cand.data_ptr())
+            torch.cuda.synchronize()
+            kblocks.append(cand)
+        allk = torch.stack(kblocks).contiguous()
+        sblocks = []
+        for c, (lo, hi) in zip(ctxs, bounds):
+            sc = torch.empty((nq, 10, 24), dtype=torch.uint8, device="cuda")
+            c.scdb_score_owned_dev(allk.data_ptr(), 3, nq, tq_d.data_ptr(), lo, max(0, min(limit, hi) - lo), sc.data_ptr())
+            torch.cuda.synchronize()
+            sblocks.append(sc)
+        alls = torch.stack(sblocks).contiguous()
+        o2_id = torch.empty(nq, dtype=torch.int32, device="cuda")
+        o2_d = torch.empty(nq, dtype=torch.float64, device="cuda")
+        o2_s = torch.empty(nq, dtype=torch.int32, device="cuda")
+        ctxs[1].scdb_pick_dev(alls.data_ptr(), 3, nq, 0.2, o2_id.data_ptr(), o2_d.data_ptr(), o2_s.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(o2_id, out_id) and torch.equal(o2_s, out_s)
+        assert np.array_equal(o2_d.cpu().numpy().view(np.uint64), d_o.view(np.uint64))
+        srec = alls.cpu().numpy().view(sch.CAND_DTYPE).reshape(3, nq, 10)
+        assert int((srec["id"] >= 0).sum()) == nq * 10
         # the numpy selection used by the gloo test agrees with the kernel on the same records
         rec = allc.cpu().numpy().view(sch.CAND_DTYPE).reshape(3, nq, 10)
         l_p, d_p, s_p = sch.py_pick(rec)

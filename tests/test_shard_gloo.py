@@ -125,7 +125,19 @@ def _loop_worker(rank, world, port, q):
     allc = shard.gather_candidates(block)
     rec = allc.numpy().view(sch.CAND_DTYPE).reshape(world, nq, 10)
     lid, dd, sh = sch.py_pick(rec)
-    q.put((rank, (lo, hi, lim_local, lid, dd, sh)))
+    # the two-round exchange (shard.loop_search_sharded_2round) with the kernels' work done by the CPU oracle: round 1
+    # gathers unscored records, every rank scores the survivors it owns, round 2 gathers them, the same pick
+    keys_only = cand.copy()
+    keys_only["sc_dist"] = 10000000.0
+    keys_only["shift"] = 0
+    all_keys = shard.gather_candidates(torch.from_numpy(keys_only.view(np.uint8).reshape(nq, 10, 24).copy()))
+    scored = sch.py_select_and_score(all_keys.numpy().view(sch.CAND_DTYPE).reshape(world, nq, 10), lo, lim_local,
+                                     lambda qi, gid: tuple(x[0] for x in sco.distance(qd[qi], descs[gid])))
+    all_scored = shard.gather_candidates(torch.from_numpy(scored.view(np.uint8).reshape(nq, 10, 24).copy()))
+    lid2, dd2, sh2 = sch.py_pick(all_scored.numpy().view(sch.CAND_DTYPE).reshape(world, nq, 10))
+    assert np.array_equal(lid2, lid) and np.array_equal(dd2, dd) and np.array_equal(sh2, sh)
+    owned = int((scored["id"] >= 0).sum())
+    q.put((rank, (lo, hi, lim_local, lid, dd, sh, owned)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -155,8 +167,10 @@ def test_two_rank_sharded_loop_search_equals_unsharded_oracle():
     qk = sch.keys_of_fast(qd)
     l_o, d_o, s_o = sco.search(keys, descs, limit, qk, qd)
     for r in (0, 1):
-        _, _, _, lid, dd, sh = res[r]
+        _, _, _, lid, dd, sh, owned = res[r]
         assert np.array_equal(lid, l_o) and np.array_equal(dd, d_o) and np.array_equal(sh, s_o)
+    # two rounds: every surviving candidate is scored exactly once, by its owner (10 per query in total, not per rank)
+    assert res[0][6] + res[1][6] == nq * 10
     assert (l_o >= 0).sum() >= 15
 
 
