@@ -432,7 +432,7 @@ def run_reference(args):
 # database sharded over the ranks, per-rank candidates merged with one NCCL all_gather (shard.loop_search_sharded).
 # Not the driver's default line; run explicitly:  python bench.py --workload loopdb [--gpus N]
 LOOP_METRIC = "loop-closure descriptor searches/sec (ScanContext, 100k-keyframe database)"
-LOOP_DB = 100_000
+LOOP_DB = int(os.environ.get("LMSF_LOOP_DB", "100000"))   # env: profiling one shard's kernels on one GPU
 LOOP_NQ = 1024
 
 
@@ -555,10 +555,22 @@ def run_loopdb(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    search = pkg.shard.loop_search_sharded if args.loop_exchange == 1 else pkg.shard.loop_search_sharded_2round
+    if args.loop_exchange == 1:
+        def search(c, a, b, lim, l, h, th):
+            return pkg.shard.loop_search_sharded(c, a, b, lim, l, h, th)
+    else:
+        searcher = pkg.shard.ShardedLoopSearch(ctx, LOOP_NQ, limit, lo, hi, 0.2, device=dev)
+
+        def search(c, a, b, lim, l, h, th):
+            return searcher.search(a, b)
+    host_ms = [0.0, 0]
 
     def step_resident():
-        return search(ctx, d_qk, d_qd, limit, lo, hi, 0.2)
+        t = time.perf_counter()
+        r = search(ctx, d_qk, d_qd, limit, lo, hi, 0.2)
+        host_ms[0] += (time.perf_counter() - t) * 1e3
+        host_ms[1] += 1
+        return r
 
     def step_e2e():
         with torch.cuda.stream(stream):
@@ -589,6 +601,7 @@ def run_loopdb(args):
 
     timed(step_resident)   # dress rehearsal (discarded): clocks, allocator pools and NCCL channels settle
     l0 = ctx.launch_count()
+    host_ms[0], host_ms[1] = 0.0, 0
     dev_ms, _, res = timed(step_resident)
     launches = ctx.launch_count() - l0
     _, e_wall_ms, res_e = timed(step_e2e)
@@ -611,6 +624,7 @@ def run_loopdb(args):
                                     "all_gather of the unscored candidates, SC distance of the global top-10 by their "
                                     "owners only, second all_gather") + ", identical selection on every rank",
                        "exchange_rounds": args.loop_exchange,
+                       "host_enqueue_ms_per_step": host_ms[0] / max(1, host_ms[1]),
                        "database": LOOP_DB, "searched_prefix": int(limit), "queries_per_step": LOOP_NQ,
                        "shard": [int(lo), int(hi)], "recall_of_planted_revisits": hit,
                        "l2": f"{FLUSH_BYTES >> 20} MiB memset between timed steps (L2 flush), inside the timed region",

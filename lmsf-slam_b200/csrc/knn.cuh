@@ -180,8 +180,11 @@ HD bool kq_check_fail(int code, int a, int b, int c) {
 }
 #define KQ_CHECK(ok, code, a, b, c) \
   if (!(ok) && kq_check_fail(code, a, b, c)) return
+#define KQ_CHECK_RET(ok, code, a, b, c, ret) \
+  if (!(ok) && kq_check_fail(code, a, b, c)) return ret
 #else
 #define KQ_CHECK(ok, code, a, b, c)
+#define KQ_CHECK_RET(ok, code, a, b, c, ret)
 #endif
 
 HD int kq_ffs64(unsigned long long v) {  // index of the lowest set bit; v != 0
@@ -250,8 +253,8 @@ HD unsigned long long kq_box_mask(int xl, int xh, int yl, int yh, int zl, int zh
   return ((unsigned long long)hi << 32) | lo;
 }
 
-// phase B: one flat loop over the `total` candidates of segments [first, ...) of the list, two loads ahead of the
-// judgement
+// phase B: one flat loop over the `total` candidates of segments [first, ...) of the list, KQ_DEPTH loads ahead of
+// the judgement
 HD void kq_scan(const MapView& mv, const KqList& li, int first, int total, float qx, float qy, float qz, KqTop& top,
                 bool dedup) {
   if (total <= 0) return;
@@ -271,12 +274,30 @@ HD void kq_scan(const MapView& mv, const KqList& li, int first, int total, float
     ++p;                                                            \
     ++fetched;                                                      \
   }
+#ifndef KQ_DEPTH
+#define KQ_DEPTH 2  // candidate loads in flight per lane (3 and 4 measured: no gain, r2l)
+#endif
+  float4 n2 = n0, n3 = n0;
   KQ_FETCH(n0);
   KQ_FETCH(n1);
+  if (KQ_DEPTH > 2) {
+    KQ_FETCH(n2);
+  }
+  if (KQ_DEPTH > 3) {
+    KQ_FETCH(n3);
+  }
   for (int i = 0; i < total; ++i) {
     const float4 m = n0;
     n0 = n1;
-    KQ_FETCH(n1);
+    if (KQ_DEPTH > 2) n1 = n2;
+    if (KQ_DEPTH > 3) n2 = n3;
+    if (KQ_DEPTH == 2) {
+      KQ_FETCH(n1);
+    } else if (KQ_DEPTH == 3) {
+      KQ_FETCH(n2);
+    } else {
+      KQ_FETCH(n3);
+    }
     const float dx = m.x - qx, dy = m.y - qy, dz = m.z - qz;
     float r = dx * dx;
     r = r + dy * dy;
@@ -365,7 +386,7 @@ HD int kq_collect(const MapView& mv, const MapDev& md, const KqList& li, float q
             continue;
           }
           KG_STAT(1, 1);
-          KQ_CHECK(fine_base >= 0 && fine_base <= md.n, 3, fine_base, f1, md.n) 0;
+          KQ_CHECK_RET(fine_base >= 0 && fine_base <= md.n, 3, fine_base, f1, md.n, 0);
           const L1Rec lr = ld_l1(mv, fine_base + KG_POPC64(m1 & kq_below(f1)));
           unsigned long long sel2 = lr.mask & kq_box_mask(sw.lo[0] - ox, sw.hi[0] - ox, sw.lo[1] - oy, sw.hi[1] - oy,
                                                           sw.lo[2] - oz, sw.hi[2] - oz);
@@ -397,10 +418,10 @@ HD int kq_collect(const MapView& mv, const MapDev& md, const KqList& li, float q
             const unsigned long long run = gap ? (sel2 & kq_below(kq_ffs64(gap))) : sel2;
             sel2 &= ~run;
             const int b0 = lr.first + KG_POPC64(lr.mask & kq_below(lb));
-            KQ_CHECK(b0 >= 0 && b0 + KG_POPC64(run) <= 2 * md.n, 4, b0, lr.first, (int)KG_POPC64(run)) 0;
+            KQ_CHECK_RET(b0 >= 0 && b0 + KG_POPC64(run) <= 2 * md.n, 4, b0, lr.first, (int)KG_POPC64(run), 0);
             const int s = KG_LD(&mv.l2_start[b0]);
             const int e = KG_LD(&mv.l2_start[b0 + KG_POPC64(run)]);
-            KQ_CHECK(s >= 0 && s < e && e <= md.n, 5, s, e, b0) 0;
+            KQ_CHECK_RET(s >= 0 && s < e && e <= md.n, 5, s, e, b0, 0);
             sw.count += e - s;
             KG_STAT(3, 1);
             if (sw.mode == KQ_SCAN) {
