@@ -223,6 +223,15 @@ int lmsf_tracker_reset(lmsf_ctx* c);
  * from xyzi and register them against this tracker's current local map. */
 int lmsf_tracker_register_aux(lmsf_ctx* c, const float* xyzi, int n, double pose[7],
                               lmsf_reg_stats* st);
+/* Multi-LiDAR rigs with one LiDAR per GPU (System/ML_System.hpp:296-310 on several devices): the auxiliary LiDAR's GPU
+ * extracts (lmsf_extract_features_to_dev: edges first, then surfs, into a DEVICE buffer of `cap` points — the caller
+ * ships that buffer to the primary's GPU, peer copy or NCCL), the primary's context registers the shipped features
+ * against its local map (lmsf_tracker_register_aux_features_dev = lmsf_tracker_register_aux without the extraction).
+ * The caller orders its transfer against the context's stream (lmsf_stream). */
+int lmsf_extract_features_to_dev(lmsf_ctx* c, const float* xyzi, int n, void* d_feat_out, int cap, int* n_edge,
+                                 int* n_surf);
+int lmsf_tracker_register_aux_features_dev(lmsf_ctx* c, const void* d_feat, int n_edge, int n_surf, double pose[7],
+                                           lmsf_reg_stats* st);
 /* = LidarTrackerLocalMap::GetLocalMap (:184-192) */
 int lmsf_get_map(lmsf_ctx* c, int kind, float* xyzi, int cap, int* n);
 

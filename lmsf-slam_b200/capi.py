@@ -129,7 +129,7 @@ class Library:
         "last_cuda_error", "launch_count", "stream", "tracker_step_dev", "tracker_prefetch", "tracker_prefetch_dev",
         "tracker_submit", "tracker_submit_dev", "tracker_wait", "tracker_prefetch_cancel", "tracker_step_ticket",
         "tracker_submit_ticket",
-        "dev_alloc", "dev_free",
+        "dev_alloc", "dev_free", "extract_features_to_dev", "tracker_register_aux_features_dev",
         "dev_upload", "profile_enable", "profile_read",
         # loop-closure descriptor path (scancontext.cu)
         "sc_make", "sc_distance", "scdb_reserve", "scdb_clear", "scdb_size", "scdb_add", "scdb_add_cloud",
@@ -166,6 +166,9 @@ class Library:
             f("tracker_submit").argtypes = [C.c_void_p, _f32p, C.c_int, C.c_double, _f64p]
             f("tracker_submit_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, _f64p]
             f("tracker_wait").argtypes = [C.c_void_p, _f64p, _f64p, C.POINTER(TrackStats)]
+            f("extract_features_to_dev").argtypes = [C.c_void_p, _f32p, C.c_int, C.c_void_p, C.c_int, _intp, _intp]
+            f("tracker_register_aux_features_dev").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _f64p,
+                                                               C.POINTER(RegStats)]
             f("dev_alloc").argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
             f("dev_free").argtypes = [C.c_void_p, C.c_void_p]
             f("dev_upload").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
@@ -485,6 +488,21 @@ class Context:
         n = C.c_int(0)
         self._chk(self.lib.fn("rotary_preprocess")(self._h, _fp(a), a.shape[0], float(scan_period), _fp(out), C.byref(n)))
         return out[: n.value].copy()
+
+    def extract_features_to_dev(self, xyzi, d_out: int, cap: int):
+        """Extraction with the features left on the device: edges then surfs into the buffer at d_out -> (n_edge, n_surf)."""
+        a = _xyzi(xyzi)
+        ne, ns = C.c_int(0), C.c_int(0)
+        self._chk(self.lib.fn("extract_features_to_dev")(self._h, _fp(a), a.shape[0], C.c_void_p(d_out), int(cap),
+                                                         C.byref(ne), C.byref(ns)))
+        return ne.value, ns.value
+
+    def tracker_register_aux_features_dev(self, d_feat: int, n_edge: int, n_surf: int, pose):
+        p = np.array(pose, dtype=np.float64)
+        st = RegStats()
+        self._chk(self.lib.fn("tracker_register_aux_features_dev")(self._h, C.c_void_p(d_feat), int(n_edge), int(n_surf),
+                                                                   p.ctypes.data_as(_f64p), C.byref(st)))
+        return p, st.as_dict()
 
     def get_map(self, kind: int):
         n = C.c_int(0)

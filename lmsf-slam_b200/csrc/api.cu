@@ -611,6 +611,22 @@ int lmsf_extract_features(lmsf_ctx* c, const float* xyzi, int n, uint8_t* label_
   return LMSF_OK;
 }
 
+int lmsf_extract_features_to_dev(lmsf_ctx* c, const float* xyzi, int n, void* d_feat_out, int cap, int* n_edge,
+                                 int* n_surf) {
+  ENTER(c);
+  if (!n_edge || !n_surf || (cap > 0 && !d_feat_out)) return LMSF_ERR_INVALID;
+  LM_TRY(extract_current(c, xyzi, n, true));
+  LM_TRY(fetch_counts(c));
+  const int ne = c->n_edge, ns = c->n_surf;
+  if (ne + ns > cap) return LMSF_ERR_CAPACITY;
+  if (ne + ns)
+    LM_CUDA(cudaMemcpyAsync(d_feat_out, c->d_feat, (size_t)(ne + ns) * sizeof(float4), cudaMemcpyDeviceToDevice,
+                            c->stream));
+  *n_edge = ne;
+  *n_surf = ns;
+  return LMSF_OK;
+}
+
 int lmsf_voxel_downsample(lmsf_ctx* c, const float* xyzi, int n, float leaf, float* out_xyzi, int* n_out,
                           int32_t* voxel_of_point) {
   ENTER(c);
@@ -924,6 +940,30 @@ int lmsf_tracker_register_aux(lmsf_ctx* c, const float* xyzi, int n, double pose
   rigid_to_pose(T, p);
   LM_TRY(wait_map(c));
   LM_TRY(run_solver(c, c->prm.solver, p, st, n));
+  T = rigid_from_pose(p);
+  rigid_to_pose(T, pose);
+  return LMSF_OK;
+}
+
+int lmsf_tracker_register_aux_features_dev(lmsf_ctx* c, const void* d_feat, int n_edge, int n_surf, double pose[7],
+                                           lmsf_reg_stats* st) {
+  ENTER(c);
+  if (!pose || n_edge < 0 || n_surf < 0 || (n_edge + n_surf > 0 && !d_feat)) return LMSF_ERR_INVALID;
+  if (n_edge + n_surf > c->prm.max_points) return LMSF_ERR_CAPACITY;
+  if (c->pending.active) return LMSF_ERR_STATE;
+  alias_slot(c, writable_slot(c));
+  LM_TRY(wait_feat(c));
+  c->feat_from_extract = false;
+  if (n_edge + n_surf)
+    LM_CUDA(cudaMemcpyAsync(c->d_feat, d_feat, (size_t)(n_edge + n_surf) * sizeof(float4), cudaMemcpyDeviceToDevice,
+                            c->stream));
+  LM_TRY(set_counts(c, n_edge, n_surf));
+  LM_TRY(scan_filter(c));
+  rigid T = rigid_from_pose(pose);  // Solve(Isometry3d&): quaternion <-> matrix round trip
+  double p[7];
+  rigid_to_pose(T, p);
+  LM_TRY(wait_map(c));
+  LM_TRY(run_solver(c, c->prm.solver, p, st, n_edge + n_surf));
   T = rigid_from_pose(p);
   rigid_to_pose(T, pose);
   return LMSF_OK;

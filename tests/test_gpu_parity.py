@@ -672,6 +672,64 @@ def test_multi_lidar_rig_config3(gpu_lib, oracle_lib, synth):
             c.close()
 
 
+def test_distributed_rig_feature_shipping_path(gpu_lib, oracle_lib, synth):
+    """BASELINE config 3 with one LiDAR per GPU (rig.DistributedRig), exercised here in its single-process form (the
+    library calls and their order are those of the multi-GPU run; the features move by a device copy instead of NCCL):
+    status 1 — the auxiliary context only extracts, into a device buffer (lmsf_extract_features_to_dev); the primary
+    registers the shipped features against ITS local map (lmsf_tracker_register_aux_features_dev).  The result equals
+    lmsf_tracker_register_aux on the primary alone to 1e-8 m / 1e-9 rad (same features, same solver), and lies within the pose
+    bar of three oracle contexts doing System/ML_System.hpp:296-310 on the CPU."""
+    import torch
+    from lmsf_slam_b200 import rig as rigmod
+
+    sensor = synth.vlp16()
+
+    def rz(deg):
+        a = np.radians(deg)
+        return np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+
+    ext = [(np.eye(3), np.zeros(3)), (rz(40.0), np.array([0.03, -0.54, -0.14])), (rz(-40.0), np.array([0.03, 0.54, -0.14]))]
+    nsw = 7
+    sw = [[np.ascontiguousarray(synth.make_sweep(sensor, k, extrinsic=(None if i == 0 else ext[i]))) for k in range(nsw)]
+          for i in range(3)]
+    g = [gpu_lib.context(0, n_scans=16) for _ in range(3)]
+    ref = gpu_lib.context(0, n_scans=16)                      # the primary alone, whole sweeps (the one-GPU path)
+    o = oracle_lib.context(0, n_scans=16, oracle_knn_mode=0, oracle_threads=8)
+    try:
+        r = rigmod.DistributedRig(gpu_lib, g[0], rank=0, world=1, peers=g[1:], device=torch.device("cuda", 0))
+        for k in range(4):                                   # status 0: every LiDAR tracks on its own context
+            assert r.process(sw[0][k], 0.1 * k, [sw[1][k], sw[2][k]]) == 0
+            ref.tracker_step(sw[0][k], 0.1 * k)
+            o.tracker_step(sw[0][k], 0.1 * k)
+        # the hand-eye gate needs more excitation than four sweeps give: switch by hand, from perturbed extrinsics
+        r.status = 1
+        for i in (1, 2):
+            Re, te = ext[i]
+            r.extrinsic[i] = synth.pose_to_qt(Re @ rz(1.0), te + np.array([0.04, -0.03, 0.02]))
+        ext_o = [None] + [r.extrinsic[i].copy() for i in (1, 2)]
+        ext_ref = [None] + [r.extrinsic[i].copy() for i in (1, 2)]
+        for k in range(4, nsw):
+            r.process(sw[0][k], 0.1 * k, [sw[1][k], sw[2][k]])
+            p_ref = ref.tracker_step(sw[0][k], 0.1 * k)[0]
+            p_o = o.tracker_step(sw[0][k], 0.1 * k)[0]
+            for i in (1, 2):
+                sub_ref, _ = ref.tracker_register_aux(sw[i][k], rigmod.pose_mul(p_ref, ext_ref[i]))
+                ext_ref[i] = rigmod.pose_mul(rigmod.pose_inv(p_ref), sub_ref)
+                sub_o, _ = o.tracker_register_aux(sw[i][k], rigmod.pose_mul(p_o, ext_o[i]))
+                ext_o[i] = rigmod.pose_mul(rigmod.pose_inv(p_o), sub_o)
+                # shipped features are processed in cell-sorted order, extracted ones in ring order: the fp64 sums of the
+                # normal equations differ in their last bits, nothing more
+                dt, dr = pose_err(r.extrinsic[i], ext_ref[i])
+                assert dt < 1e-8 and dr < 1e-9, (k, i, dt, dr)
+                dt, dr = pose_err(r.extrinsic[i], ext_o[i])
+                assert dt < POSE_TOL_M and dr < POSE_TOL_RAD, (k, i, dt, dr)
+        assert r.shipped_bytes > 3 * 2 * 100_000            # three steps, two auxiliary LiDARs, > 100 KB of features each
+        r.close()
+    finally:
+        for c in g + [ref, o]:
+            c.close()
+
+
 @pytest.mark.parametrize("name,ns", [("vlp16", 16), ("hdl64", 64)])
 def test_align_score_parity(ctxs, sweeps, synth, name, ns):
     """Row f2, PointCloudAlignmentEvaluate::AlignmentScore: inlier count and overlap identical to the oracle, the score
