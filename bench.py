@@ -300,7 +300,9 @@ def run_ours(args):
                            "lmsf_tracker_wait(pose out), wall clock around K steps, max over ranks"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": "k_knn (exact 5-NN of every scan feature over the local-map grid)",
+            "roofline": {"bound": "hbm", "kernel": "k_knn + k_knn_sparse (exact 5-NN of every scan feature over the local-map grid: one "
+                                                    "correspondence pass = the per-thread search and the warp-per-query "
+                                                    "search of the cases it defers; timed together)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": match_ms,

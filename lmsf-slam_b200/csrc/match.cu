@@ -902,6 +902,7 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
 // fp64, stored as fp32 in pw[] for k_fit — so no separate launch is needed.
 // seeded != 0 (outer iterations after the first): nbr[] holds the previous iteration's neighbours of the same position;
 // the largest of their keys at the query's new place bounds the 5th key from the start.
+template <bool DEFER>
 __global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __restrict__ perm, float4* __restrict__ pw,
                                              const float4* __restrict__ feat,
                                              const int* __restrict__ counts, SolveState* __restrict__ st,
@@ -962,7 +963,7 @@ __global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __re
           }
         }
       }
-      n = kq_knn5<true>(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, have_seed ? seed : nullptr, top);
+      n = kq_knn5<DEFER>(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, have_seed ? seed : nullptr, top);
     }
     if (n < 0) {  // a sparse case: left to k_knn_sparse (one warp per query)
       defer[atomicAdd(&st->n_defer, 1)] = t;
@@ -1590,11 +1591,22 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       if (knn_width == 8 || knn_width == 16 || knn_width == 32) chunk = knn_width;
       int knn_grid = div_up(up, 4 * chunk);
       if (knn_grid > 148 * knn_per_sm) knn_grid = 148 * knn_per_sm;  // persistent: every resident warp pulls work
-      LM_LAUNCH(c, k_knn, knn_grid, KG_BLOCK, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs, up,
-                solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
-      // the sparse cases of this pass, one warp each (nothing to do when k_knn deferred none)
-      LM_LAUNCH(c, k_knn_sparse, 148 * 2, KG_BLOCK, 0, perm, c->d_pw, c->ex.counts, c->d_state, maps, up, solver,
-                c->d_defer, c->d_nbr);
+      // Deferral pays when the sparse cases are the exception (a raw window: 0.6 % of the queries, but all of the long
+      // single-thread chains).  Over a voxel-filtered map (leaf >= 12.5 cm) nearly every query is such a case: a warp
+      // per query would be the slow way, and with uniform work there is no tail to remove — each thread searches its own.
+      static const int force_defer = env_int("LMSF_KNN_DEFER", 0);  // tuning: 1 = always, 2 = never
+      const bool sparse_map = c->prm.map_leaf_surf >= 0.125f;
+      const bool defer = force_defer == 1 || (force_defer != 2 && !sparse_map);
+      if (defer) {
+        LM_LAUNCH(c, k_knn<true>, knn_grid, KG_BLOCK, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,
+                  up, solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
+        // the sparse cases of this pass, one warp each (nothing to do when k_knn deferred none)
+        LM_LAUNCH(c, k_knn_sparse, 148 * 2, KG_BLOCK, 0, perm, c->d_pw, c->ex.counts, c->d_state, maps, up, solver,
+                  c->d_defer, c->d_nbr);
+      } else {
+        LM_LAUNCH(c, k_knn<false>, knn_grid, KG_BLOCK, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,
+                  up, solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
+      }
       c->match_bytes += alg_bytes;
       c->match_launches += 1;
     }

@@ -66,13 +66,29 @@ __global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ in, int
     }
     cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
   }
+  // one set of atomics per block, not per warp: 592 x 8 warps x 7 atomics on seven addresses serialised in L2 and made
+  // this the slowest kernel of the voxel path (29 us for 16 MB, profiles/r2n_voxel_ncu_summary.txt)
+  __shared__ unsigned s_v[8][7];
+  const int warp = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      atomicMin(&bbox[a], mn[a]);
-      atomicMax(&bbox[3 + a], mx[a]);
+      s_v[warp][a] = mn[a];
+      s_v[warp][3 + a] = mx[a];
     }
-    atomicAdd(&bbox[6], cnt);
+    s_v[warp][6] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    const int a = threadIdx.x;
+    unsigned v = s_v[0][a];
+    for (int w = 1; w < 8; ++w) v = a < 3 ? min(v, s_v[w][a]) : (a < 6 ? max(v, s_v[w][a]) : v + s_v[w][a]);
+    if (a < 3)
+      atomicMin(&bbox[a], v);
+    else if (a < 6)
+      atomicMax(&bbox[a], v);
+    else
+      atomicAdd(&bbox[6], v);
   }
 }
 
