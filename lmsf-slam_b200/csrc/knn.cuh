@@ -475,6 +475,9 @@ enum {
   KQ_ST_LAST = 6,    // sparse: the ball of the bound, everything (duplicates filtered)
   KQ_ST_DONE = 7
 };
+#ifndef KQ_OWN_ONLY_ABOVE
+#define KQ_OWN_ONLY_ABOVE 64  // START scans the own cell alone only when the 27 cells hold more points than this
+#endif
 constexpr int KQ_SHELL_MAX = 96;  // a grown box with more points than this is searched cell by cell, nearest first
 
 // Exact 5-NN within squared radius 1.0 of one query.  seed = nullptr: no prior knowledge; otherwise the keys of five
@@ -547,7 +550,7 @@ HD int kq_knn5(const MapView& mv, const KqList& li, float qx, float qy, float qz
       int first = 0;
       bool own_only = false;
       if (sw.own_first) {  // START, list intact: the own cell alone if it holds five points
-        own_only = sw.n_own >= 5;
+        own_only = sw.n_own >= 5 && sw.count > KQ_OWN_ONLY_ABOVE;
         first = sw.n_own > 0 ? 0 : 1;
         if (own_only) pending = sw.n_own;
       }
