@@ -177,6 +177,7 @@ struct Ctx {
   double* d_partial = nullptr; // [grid][LM_NSUM]
   int partial_blocks = 0;
   SolveState* d_state = nullptr;
+  unsigned* d_bar = nullptr;   // [1] generation word of k_solve's grid barrier
 
   // voxel scratch (sized for max(max_points, max_map_points))
   int vox_cap = 0;

@@ -41,6 +41,7 @@ struct SolveParams {
   int lm_max_iters;  // 4
   int gn_min_rows;   // 10
   double huber;      // 0.1
+  int poll_ns;       // k_solve: sleep between two polls of the barrier word (0 = spin)
 };
 
 struct MapPair {
@@ -891,6 +892,35 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
   }
 }
 
+// One deferred query, searched by the whole warp (kw_knn5); all lanes call with the same t.  pw[] holds the world point.
+__device__ __forceinline__ void knn_sparse_one(const Warp32& x, KwScratch* s, int t, const int* __restrict__ perm,
+                                               const float4* __restrict__ pw, int n_e, const MapPair& maps,
+                                               int upper, int* __restrict__ nbr) {
+  const int f = perm[t];
+  const bool is_edge = f < n_e;
+  const float4 w = pw[f];
+  KqTop top;
+  int n = kw_knn5(x, is_edge ? maps.edge : maps.surf, s, w.x, w.y, w.z, top);
+  if (n < 0) {
+    // more occupied cells around the query than the item list holds: the complete per-thread search, by lane 0
+    // (its segment list lives in the same shared memory)
+    if (x.lane == 0) {
+      KqList li;
+      li.seg = reinterpret_cast<int*>(s);
+      li.stride = 1;
+      n = kq_knn5<false>(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, nullptr, top);
+    }
+    n = x.shfl(n, 0);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) top.k[k] = x.shfl64(top.k[k], 0);
+  }
+  if (x.lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) nbr[k * upper + t] = (n == 5) ? kg_key_id(top.k[k]) : -1;
+  }
+  x.sync();
+}
+
 // exact 5-NN of every query, in processing order (t = position), one thread per query (knn.cuh).  Persistent warps pull
 // chunks of 32 consecutive positions from a device-side counter: queries of sparse regions cost several times more
 // than queries of dense ones and lie next to each other, so a static block->query map leaves a long tail of heavy
@@ -921,57 +951,57 @@ __global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __re
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= live) break;
     const int t = base + lane;
-    if (lane >= chunk || t >= upper || t >= live) continue;
-    const int f = perm[t];
-    if (f >= live) continue;
-    const bool is_edge = f < n_e;
-    float4 w;
-    if (assoc) {
-      quat q;
-      q.x = st->x[0];
-      q.y = st->x[1];
-      q.z = st->x[2];
-      q.w = st->x[3];
-      const d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
-      const float4 fp = feat[f];
-      const d3 pwd = add3(qrot(q, mk3((double)fp.x, (double)fp.y, (double)fp.z)), tr);
-      w = make_float4((float)pwd.x, (float)pwd.y, (float)pwd.z, 0.f);
-      pw[f] = w;
-    } else {
-      w = pw[f];
-    }
-    int n = 0;
-    KqTop top;
-    if (is_edge ? has_edge_map : has_surf_map) {
-      unsigned long long seed[5];
-      bool have_seed = false;
-      if (seeded) {
-        const float4* __restrict__ cat = is_edge ? maps.edge_cat : maps.surf_cat;
-        int sid[5];
+    const int f = (lane < chunk && t < upper && t < live) ? perm[t] : live;
+    if (f < live) {
+      const bool is_edge = f < n_e;
+      float4 w;
+      if (assoc) {
+        quat q;
+        q.x = st->x[0];
+        q.y = st->x[1];
+        q.z = st->x[2];
+        q.w = st->x[3];
+        const d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
+        const float4 fp = feat[f];
+        const d3 pwd = add3(qrot(q, mk3((double)fp.x, (double)fp.y, (double)fp.z)), tr);
+        w = make_float4((float)pwd.x, (float)pwd.y, (float)pwd.z, 0.f);
+        pw[f] = w;
+      } else {
+        w = pw[f];
+      }
+      int n = 0;
+      KqTop top;
+      if (is_edge ? has_edge_map : has_surf_map) {
+        unsigned long long seed[5];
+        bool have_seed = false;
+        if (seeded) {
+          const float4* __restrict__ cat = is_edge ? maps.edge_cat : maps.surf_cat;
+          int sid[5];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) sid[k] = nbr[k * upper + t];
-        if (sid[4] >= 0) {  // five or none
-          have_seed = true;
+          for (int k = 0; k < 5; ++k) sid[k] = nbr[k * upper + t];
+          if (sid[4] >= 0) {  // five or none
+            have_seed = true;
 #pragma unroll
-          for (int k = 0; k < 5; ++k) {
-            const float4 m = __ldg(&cat[sid[k]]);
-            const float dx = m.x - w.x, dy = m.y - w.y, dz = m.z - w.z;
-            float r = dx * dx;
-            r = r + dy * dy;
-            r = r + dz * dz;
-            seed[k] = kg_key(r, sid[k]);
+            for (int k = 0; k < 5; ++k) {
+              const float4 m = __ldg(&cat[sid[k]]);
+              const float dx = m.x - w.x, dy = m.y - w.y, dz = m.z - w.z;
+              float r = dx * dx;
+              r = r + dy * dy;
+              r = r + dz * dz;
+              seed[k] = kg_key(r, sid[k]);
+            }
           }
         }
+        n = kq_knn5<DEFER>(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, have_seed ? seed : nullptr, top);
       }
-      n = kq_knn5<DEFER>(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, have_seed ? seed : nullptr, top);
-    }
-    if (n < 0) {  // a sparse case: left to k_knn_sparse (one warp per query)
-      defer[atomicAdd(&st->n_defer, 1)] = t;
-      continue;
-    }
-    // -1 x 5 unless five neighbours lie within the search radius: both callers reject such a query
+      if (n < 0) {  // a sparse case: left to the warp-cooperative search (one warp per query)
+        defer[atomicAdd(&st->n_defer, 1)] = t;
+      } else {
+        // -1 x 5 unless five neighbours lie within the search radius: both callers reject such a query
 #pragma unroll
-    for (int k = 0; k < 5; ++k) nbr[k * upper + t] = (n == 5) ? kg_key_id(top.k[k]) : -1;
+        for (int k = 0; k < 5; ++k) nbr[k * upper + t] = (n == 5) ? kg_key_id(top.k[k]) : -1;
+      }
+    }
   }
 }
 
@@ -993,30 +1023,7 @@ __global__ void __launch_bounds__(KG_BLOCK) k_knn_sparse(const int* __restrict__
     if (x.lane == 0) i = atomicAdd(&st->defer_next, 1);
     i = x.shfl(i, 0);
     if (i >= n_def) break;
-    const int t = defer[i];
-    const int f = perm[t];
-    const bool is_edge = f < n_e;
-    const float4 w = pw[f];
-    KqTop top;
-    int n = kw_knn5(x, is_edge ? maps.edge : maps.surf, s, w.x, w.y, w.z, top);
-    if (n < 0) {
-      // more occupied cells around the query than the item list holds: the complete per-thread search, by lane 0
-      // (its segment list lives in the same shared memory)
-      if (x.lane == 0) {
-        KqList li;
-        li.seg = reinterpret_cast<int*>(s);
-        li.stride = 1;
-        n = kq_knn5<false>(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, nullptr, top);
-      }
-      n = x.shfl(n, 0);
-#pragma unroll
-      for (int k = 0; k < 5; ++k) top.k[k] = x.shfl64(top.k[k], 0);
-    }
-    if (x.lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) nbr[k * upper + t] = (n == 5) ? kg_key_id(top.k[k]) : -1;
-    }
-    x.sync();
+    knn_sparse_one(x, s, defer[i], perm, pw, n_e, maps, upper, nbr);
   }
 }
 
@@ -1027,26 +1034,12 @@ struct RecBufs {
   int stride;
 };
 
-// fit + residual/Jacobian + reduction, grid-stride over the sorted queries; the last block runs the 6x6 step
-__global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ feat, const int* __restrict__ perm,
-                                                     const float4* __restrict__ pw, const int* __restrict__ nbr,
-                                                     const int* __restrict__ counts, MapPair maps, int upper,
-                                                     SolveState* __restrict__ st, RecBufs rb,
-                                                     double* __restrict__ partial, SolveParams sp) {
-  __shared__ double tot[LM_NSUM];
-  if (sp.solver == LMSF_SOLVER_GN && st->gn_done) return;
-  TSTAMP(t_begin);
-  const int n_e = counts[0], n_s = counts[1];
-  quat q;
-  q.x = st->x[0];
-  q.y = st->x[1];
-  q.z = st->x[2];
-  q.w = st->x[3];
-  d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
-  double R[9];
-  quat_to_mat(q, R);
-  Acc acc;
-  acc_zero(acc);
+// The correspondences of this thread's positions (t = first, first + step, ...): fit, residual and Jacobian at (q, tr)
+// into acc; for the Huber-LM solver also the per-match records k_lm_eval / k_solve re-evaluate.
+__device__ __forceinline__ void fit_positions(const float4* __restrict__ feat, const int* __restrict__ perm,
+                                              const float4* __restrict__ pw, const int* __restrict__ nbr, int n_e,
+                                              int n_s, const MapPair& maps, int upper, const quat& q, d3 tr,
+                                              const double* R, const RecBufs& rb, const SolveParams& sp, Acc& acc) {
   for (int t = blockIdx.x * MATCH_BLOCK + threadIdx.x; t < upper; t += gridDim.x * MATCH_BLOCK) {
     int f = perm[t];
     const bool live = t < n_e + n_s && f < n_e + n_s;  // positions behind the live ones: kind cleared for k_lm_eval
@@ -1104,6 +1097,29 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
     }
     rb.kind[t] = kind;
   }
+}
+
+// fit + residual/Jacobian + reduction, grid-stride over the sorted queries; the last block runs the 6x6 step
+__global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ feat, const int* __restrict__ perm,
+                                                     const float4* __restrict__ pw, const int* __restrict__ nbr,
+                                                     const int* __restrict__ counts, MapPair maps, int upper,
+                                                     SolveState* __restrict__ st, RecBufs rb,
+                                                     double* __restrict__ partial, SolveParams sp) {
+  __shared__ double tot[LM_NSUM];
+  if (sp.solver == LMSF_SOLVER_GN && st->gn_done) return;
+  TSTAMP(t_begin);
+  const int n_e = counts[0], n_s = counts[1];
+  quat q;
+  q.x = st->x[0];
+  q.y = st->x[1];
+  q.z = st->x[2];
+  q.w = st->x[3];
+  d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
+  double R[9];
+  quat_to_mat(q, R);
+  Acc acc;
+  acc_zero(acc);
+  fit_positions(feat, perm, pw, nbr, n_e, n_s, maps, upper, q, tr, R, rb, sp, acc);
   TSTAMP(t_loop);
   if (!reduce_grid(acc, partial, st, tot)) return;
   TSTAMP(t_red);
@@ -1136,6 +1152,24 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
 #endif
 }
 
+// the stored correspondences of this thread's positions re-evaluated at (q, tr)
+__device__ __forceinline__ void eval_positions(int upper, const quat& q, d3 tr, const RecBufs& rb, const SolveParams& sp,
+                                               Acc& acc) {
+  for (int t = blockIdx.x * MATCH_BLOCK + threadIdx.x; t < upper; t += gridDim.x * MATCH_BLOCK) {
+    uint8_t kind = rb.kind[t];
+    if (!kind) continue;
+    d3 pl = mk3((double)rb.pl[0 * rb.stride + t], (double)rb.pl[1 * rb.stride + t], (double)rb.pl[2 * rb.stride + t]);
+    double r0 = rb.d[0 * rb.stride + t], r1 = rb.d[1 * rb.stride + t], r2 = rb.d[2 * rb.stride + t];
+    double r3 = rb.d[3 * rb.stride + t];
+    if (kind == 1) {
+      d3 b = mk3(r3, rb.d[4 * rb.stride + t], rb.d[5 * rb.stride + t]);
+      edge_factor(q, tr, pl, mk3(r0, r1, r2), b, sp.huber, acc);
+    } else {
+      surf_factor(q, tr, pl, mk3(r0, r1, r2), r3, sp.huber, acc);
+    }
+  }
+}
+
 // re-evaluate the stored correspondences at the LM candidate; last block accepts / rejects / proposes
 __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* __restrict__ st, RecBufs rb,
                                                          double* __restrict__ partial, SolveParams sp) {
@@ -1150,19 +1184,7 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* 
   d3 tr = mk3(st->cand[4], st->cand[5], st->cand[6]);
   Acc acc;
   acc_zero(acc);
-  for (int t = blockIdx.x * MATCH_BLOCK + threadIdx.x; t < upper; t += gridDim.x * MATCH_BLOCK) {
-    uint8_t kind = rb.kind[t];
-    if (!kind) continue;
-    d3 pl = mk3((double)rb.pl[0 * rb.stride + t], (double)rb.pl[1 * rb.stride + t], (double)rb.pl[2 * rb.stride + t]);
-    double r0 = rb.d[0 * rb.stride + t], r1 = rb.d[1 * rb.stride + t], r2 = rb.d[2 * rb.stride + t];
-    double r3 = rb.d[3 * rb.stride + t];
-    if (kind == 1) {
-      d3 b = mk3(r3, rb.d[4 * rb.stride + t], rb.d[5 * rb.stride + t]);
-      edge_factor(q, tr, pl, mk3(r0, r1, r2), b, sp.huber, acc);
-    } else {
-      surf_factor(q, tr, pl, mk3(r0, r1, r2), r3, sp.huber, acc);
-    }
-  }
+  eval_positions(upper, q, tr, rb, sp, acc);
   TSTAMP(t_loop);
   if (!reduce_grid(acc, partial, st, tot)) return;
   TSTAMP(t_red);
@@ -1178,6 +1200,138 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* 
     TACC(5, t_loop, t_red);
     TACC(6, t_red, t_end);
     TCOUNT(7);
+  }
+#endif
+}
+
+// ---- k_solve: one outer iteration of the Huber-LM solver in ONE persistent launch ------------------------------------
+// k_fit followed by up to lm_max_iters k_lm_eval launches is a chain of dependent kernels that all work on the same
+// correspondences: every launch boundary is a drain + a launch gap + (once the trust region has converged) an idle
+// launch.  Here the grid stays resident (cooperative launch, <= 2 CTAs per SM): every thread fits its own positions and
+// re-evaluates the same positions at each candidate, and between the phases the grid meets at a barrier whose last
+// arriver is the block that sums the partials and takes the 6x6 step (exactly reduce_grid + lm_*_warp of the split
+// kernels).  The other blocks wait on a generation word, read the verdict (lm_active, candidate pose) and go on or
+// leave.  Arithmetic and summation order per phase are those of the split kernels launched with this grid.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(MATCH_BLOCK) k_solve(const float4* __restrict__ feat, const int* __restrict__ perm,
+                                                       const float4* __restrict__ pw, const int* __restrict__ nbr,
+                                                       const int* __restrict__ counts, MapPair maps, int upper,
+                                                       SolveState* __restrict__ st, RecBufs rb,
+                                                       double* __restrict__ partial, SolveParams sp,
+                                                       unsigned* __restrict__ bar) {
+  __shared__ double tot[LM_NSUM];
+  __shared__ SolveState sh;
+  __shared__ LmScratch scratch;
+  __shared__ double s_cand[7];
+  __shared__ int s_go;
+  __shared__ unsigned s_gen;
+  TSTAMP(t_begin);
+  if (threadIdx.x == 0) s_gen = ld_acquire_u32(bar);  // no block can release before every block has read this
+  const int n_e = counts[0], n_s = counts[1];
+  Acc acc;
+  {
+    quat q;
+    q.x = st->x[0];
+    q.y = st->x[1];
+    q.z = st->x[2];
+    q.w = st->x[3];
+    const d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
+    acc_zero(acc);
+    fit_positions(feat, perm, pw, nbr, n_e, n_s, maps, upper, q, tr, nullptr, rb, sp, acc);
+  }
+  __syncthreads();
+  unsigned gen = s_gen;
+  TSTAMP(t_loop);
+  for (int k = 0;; ++k) {
+    // ---- barrier; the last block to arrive takes the step and opens the next generation
+    TSTAMP(t_arrive);
+    if (reduce_grid(acc, partial, st, tot)) {
+      TSTAMP(t_tot);
+      state_load(&sh, st);
+      TSTAMP(t_ld);
+      if (k == 0) {
+        if (threadIdx.x == 0) {
+          sh.n_edge_ok = (int)tot[29];
+          sh.n_surf_ok = (int)tot[28] - (int)tot[29];
+          sh.knn_next = 0;  // work queues of the next k_knn launch
+          sh.defer_next = 0;
+          sh.n_defer = 0;
+              }
+        if (threadIdx.x < 32) lm_begin_warp(&sh, &scratch, tot, sp);
+      } else {
+        if (threadIdx.x < 32) lm_update_warp(&sh, &scratch, tot, sp);
+      }
+      TSTAMP(t_up);
+      state_store(st, &sh);
+      TSTAMP(t_st);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_u32(bar, gen + 1u);
+#ifdef LMSF_TIMING
+      if (threadIdx.x == 0 && k >= 1) {
+        TSTAMP(t_done);
+        TACC(8, t_arrive, t_tot);
+        TACC(9, t_tot, t_done);
+        TCOUNT(10);
+        TACC(4, t_tot, t_ld);
+        TACC(5, t_ld, t_up);
+        TACC(6, t_up, t_st);
+        TACC(7, t_st, t_done);
+      }
+#endif
+    }
+    if (k == sp.lm_max_iters) break;  // the budget is spent: nothing left to wait for
+    ++gen;
+    TSTAMP(t_arr);
+    if (threadIdx.x == 0) {
+      while (ld_acquire_u32(bar) != gen)
+        if (sp.poll_ns) __nanosleep(sp.poll_ns);
+      const int go = __ldcg(&st->lm_active);
+      s_go = go;
+      if (go) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) s_cand[i] = __ldcg(&st->cand[i]);
+      }
+    }
+    __syncthreads();
+#ifdef LMSF_TIMING
+    TSTAMP(t_rel);
+    if (threadIdx.x == 0 && blockIdx.x == 0 && k < 5) TACC(18 + k, t_arr, t_rel);
+#endif
+    if (!s_go) break;
+    quat q;
+    q.x = s_cand[0];
+    q.y = s_cand[1];
+    q.z = s_cand[2];
+    q.w = s_cand[3];
+    const d3 tr = mk3(s_cand[4], s_cand[5], s_cand[6]);
+    acc_zero(acc);
+    eval_positions(upper, q, tr, rb, sp, acc);
+#ifdef LMSF_TIMING
+    TSTAMP(t_ev);
+    if (threadIdx.x == 0 && blockIdx.x == 0 && k < 5) {
+      TACC(23 + k, t_rel, t_ev);
+      TCOUNT(28);
+    }
+    if (threadIdx.x == 0 && k == 0) atomicMax(&g_dbg[11], t_ev - t_rel);
+    if (threadIdx.x == 0 && k == 0) atomicMax(&g_dbg[12], t_ev);
+    if (threadIdx.x == 0 && k == 0) atomicMin(&g_dbg[13], t_ev);
+#endif
+  }
+#ifdef LMSF_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    TSTAMP(t_end);
+    TACC(16, t_begin, t_loop);
+    TACC(29, t_begin, t_end);
+    TCOUNT(17);
   }
 #endif
 }
@@ -1409,6 +1563,8 @@ int solve_alloc(Ctx* c) {
   LM_CUDA(cudaMalloc(&c->d_partial, (size_t)c->partial_blocks * LM_NSUM * sizeof(double)));
   LM_CUDA(cudaMalloc(&c->d_state, sizeof(SolveState)));
   LM_CUDA(cudaMemset(c->d_state, 0, sizeof(SolveState)));
+  LM_CUDA(cudaMalloc(&c->d_bar, 64));
+  LM_CUDA(cudaMemset(c->d_bar, 0, 64));
   return LMSF_OK;
 }
 
@@ -1425,6 +1581,7 @@ void solve_free(Ctx* c) {
   cudaFree(c->d_defer);
   cudaFree(c->d_partial);
   cudaFree(c->d_state);
+  cudaFree(c->d_bar);
   cudaFree(c->hook_buf);
 }
 
@@ -1524,6 +1681,8 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
   sp.lm_max_iters = c->prm.lm_inner_iters;
   sp.gn_min_rows = 10;
   sp.huber = decimal_of_float(c->prm.huber_delta);
+  static const int poll_ns = env_int("LMSF_SOLVE_POLL_NS", 0);
+  sp.poll_ns = poll_ns;
   MapPair maps;
   maps.edge = view_of(c->map[0]);
   maps.surf = view_of(c->map[1]);
@@ -1548,6 +1707,9 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
   // permutation that walks the surfs along their rings (consecutive positions are neighbours in space): no sort.
   // Caller-supplied or voxel-filtered features are sorted by map cell once per solve instead.
   static const int force_qsort = env_int("LMSF_FORCE_QSORT", 0);  // tuning experiments
+  // 1 = k_solve (one persistent launch per outer iteration) instead of k_fit + k_lm_eval launches: built for round 2,
+  // measured equal in isolation and 12 us per launch slower inside the pipeline (r2p-r2r) — kept selectable, not default
+  static const bool fused_solve = env_int("LMSF_FUSED_SOLVE", 0) == 1;
   const bool ring_order = c->perm_valid && !force_qsort;
   const int* perm = ring_order ? c->d_perm : c->q_vals_alt;
   QueryBufs qb;
@@ -1600,9 +1762,11 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       if (defer) {
         LM_LAUNCH(c, k_knn<true>, knn_grid, KG_BLOCK, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,
                   up, solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
-        // the sparse cases of this pass, one warp each (nothing to do when k_knn deferred none)
+        // the sparse cases of this pass, one warp each (nothing to do when k_knn deferred none).  Serving them in the
+        // tail of k_knn itself (warps that find the chunk queue empty) was built and measured 3-8x SLOWER, with or without
+        // waiting for the producers (r2q, r2s): two large code paths alive on one SM at a time
         LM_LAUNCH(c, k_knn_sparse, 148 * 2, KG_BLOCK, 0, perm, c->d_pw, c->ex.counts, c->d_state, maps, up, solver,
-                  c->d_defer, c->d_nbr);
+                    c->d_defer, c->d_nbr);
       } else {
         LM_LAUNCH(c, k_knn<false>, knn_grid, KG_BLOCK, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,
                   up, solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
@@ -1610,15 +1774,35 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       c->match_bytes += alg_bytes;
       c->match_launches += 1;
     }
-    {
+    if (solver == LMSF_SOLVER_HUBER_LM && fused_solve) {
+      // fit + the whole trust-region loop of this outer iteration in one persistent cooperative launch
       StageScope scope(c, LMSF_STAGE_FIT);
-      LM_LAUNCH(c, k_fit, fit_grid, MATCH_BLOCK, 0, c->d_feat, perm, c->d_pw, c->d_nbr, c->ex.counts, maps,
-                up, c->d_state, rb, c->d_partial, sp);
-    }
-    if (solver == LMSF_SOLVER_HUBER_LM) {
-      StageScope scope(c, LMSF_STAGE_SOLVE);
-      for (int k = 0; k < c->prm.lm_inner_iters; ++k)
-        LM_LAUNCH(c, k_lm_eval, eval_grid, MATCH_BLOCK, 0, up, c->d_state, rb, c->d_partial, sp);
+      const float4* a_feat = c->d_feat;
+      const float4* a_pw = c->d_pw;
+      const int* a_nbr = c->d_nbr;
+      const int* a_counts = c->ex.counts;
+      int a_up = up;
+      void* args[] = {(void*)&a_feat, (void*)&perm,       (void*)&a_pw, (void*)&a_nbr,        (void*)&a_counts, (void*)&maps,
+                      (void*)&a_up,   (void*)&c->d_state, (void*)&rb,   (void*)&c->d_partial, (void*)&sp,       (void*)&c->d_bar};
+      static const bool coop = env_int("LMSF_SOLVE_COOP", 0) == 1;
+      if (coop) {
+        LM_CUDA(cudaLaunchCooperativeKernel((const void*)k_solve, dim3(fit_grid), dim3(MATCH_BLOCK), args, 0, c->stream));
+        c->launches++;
+      } else {
+        LM_LAUNCH(c, k_solve, fit_grid, MATCH_BLOCK, 0, a_feat, perm, a_pw, a_nbr, a_counts, maps, a_up, c->d_state, rb,
+                  c->d_partial, sp, c->d_bar);
+      }
+    } else {
+      {
+        StageScope scope(c, LMSF_STAGE_FIT);
+        LM_LAUNCH(c, k_fit, fit_grid, MATCH_BLOCK, 0, c->d_feat, perm, c->d_pw, c->d_nbr, c->ex.counts, maps,
+                  up, c->d_state, rb, c->d_partial, sp);
+      }
+      if (solver == LMSF_SOLVER_HUBER_LM) {
+        StageScope scope(c, LMSF_STAGE_SOLVE);
+        for (int k = 0; k < c->prm.lm_inner_iters; ++k)
+          LM_LAUNCH(c, k_lm_eval, eval_grid, MATCH_BLOCK, 0, up, c->d_state, rb, c->d_partial, sp);
+      }
     }
   }
   LM_CUDA(cudaGetLastError());

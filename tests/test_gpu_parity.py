@@ -2,6 +2,9 @@
 inputs.  Bars (BASELINE.json north_star): feature labels and voxel membership bit-exact, kNN index
 sets identical (the oracle and the kernel share the (distance, index) tie order, so they are
 compared exactly), per-scan pose within 1e-4 m and 1e-5 rad."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -430,6 +433,26 @@ def test_tracker_prefetch_pipeline_is_bit_identical(gpu_lib, sweeps, name, ns, n
         a.close()
         b.close()
         c.close()
+
+
+@pytest.mark.parametrize("name,n", [("vlp16", 8), ("hdl64", 5)])
+def test_fused_solve_kernel_matches_split_launches(gpu_lib, name, n):
+    """k_solve (LMSF_FUSED_SOLVE=1: fit + the trust-region loop of one outer iteration in one persistent launch with a
+    grid barrier) against the default k_fit + k_lm_eval launches: same correspondences, same step counts and keyframes;
+    poses equal up to the summation order of the candidate evaluations (the evaluation grid differs: 1e-12)."""
+    import json
+    import subprocess
+
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "track_dump.py")
+    runs = []
+    for fused in ("0", "1"):
+        env = dict(os.environ, LMSF_FUSED_SOLVE=fused)
+        r = subprocess.run([sys.executable, tool, name, str(n)], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        runs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    for k, (a, b) in enumerate(zip(*runs)):
+        assert a["stats"] == b["stats"], k
+        assert np.allclose(a["pose"], b["pose"], rtol=0, atol=1e-12), k
 
 
 def test_headline_hdl64_full_window_parity(gpu_lib, oracle_lib, synth):
