@@ -118,6 +118,88 @@ def test_handeye_window_of_300_replaces_smallest_rotation(gpu_lib, synth):
     h.close()
 
 
+def _ref_handeye():
+    """oracle/_ref/libref_handeye.so: the reference's own HandEyeCalibrationBase compiled from its unmodified header."""
+    import ctypes as C
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_handeye.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_handeye.so not built (no /root/reference at build time)")
+    dll = C.CDLL(path)
+    dll.ref_handeye_create.restype = C.c_void_p
+    dll.ref_handeye_destroy.argtypes = [C.c_void_p]
+    f64p = C.POINTER(C.c_double)
+    dll.ref_handeye_add_pose.argtypes = [C.c_void_p, f64p, f64p]
+    dll.ref_handeye_calibrate.argtypes = [C.c_void_p, f64p, f64p]
+    return dll, f64p
+
+
+def test_handeye_vs_reference_code(gpu_lib, synth):
+    """Row f3 pinned: lmsf_handeye_* against the reference's OWN HandEyeCalibrationBase (handeye_calibration_base.hpp:36-246,
+    compiled where it lies; Eigen's JacobiSVD / AngleAxisd answered by restatements in oracle/shim_fixed, a one-sided
+    Jacobi SVD — not the product's eigen-decomposition of Q^T Q).  One long stream of motion pairs with everything the
+    class reacts to: pairs rejected by the rotation gate and by the translation gate (which also drop the accumulated
+    motion), sub-threshold motions, more than 300 accepted pairs (the stored pair with the smallest rotation is replaced),
+    a degenerate start (planar rotations: rot_cov[2] <= 0.25 refuses) and calibrations at several points.  Same accept /
+    enough flag after every pair, same refusals, extrinsics equal to 1e-9."""
+    import ctypes as C
+    from lmsf_slam_b200 import capi
+    dll, f64p = _ref_handeye()
+    rng = np.random.default_rng(21)
+    Rx, tx = rot([0.2, -0.1, 1.0], np.radians(38.0)), np.array([0.03, -0.54, -0.14])
+    X = np.eye(4)
+    X[:3, :3], X[:3, 3] = Rx, tx
+
+    def pair(axis, ang, t, noise=0.0):
+        A = np.eye(4)
+        A[:3, :3], A[:3, 3] = rot(axis, ang), t
+        B = np.linalg.inv(X) @ A @ X
+        B[:3, 3] += rng.normal(0, noise, size=3) if noise > 0 else 0.0
+        return to_pose(A[:3, :3], A[:3, 3], synth), to_pose(B[:3, :3], B[:3, 3], synth)
+
+    stream = []
+    for k in range(6):                       # planar start: yaw only
+        stream.append(pair([0, 0, 1], 0.03 + 0.01 * k, [0.1, 0.0, 0.0]))
+    stream.append("calibrate")               # degenerate: refused by both
+    for k in range(340):
+        p, s = pair(rng.normal(size=3), rng.uniform(0.01, 0.3), rng.normal(0, 0.1, size=3), noise=0.002)
+        if k % 37 == 5:                      # rotation gate
+            s = np.array(s)
+            s[:4] = to_pose(rot(rng.normal(size=3), 0.5), [0, 0, 0], synth)[:4]
+        if k % 41 == 7:                      # translation gate
+            s = np.array(s)
+            s[4:] += [0.4, -0.4, 0.4]
+        stream.append((p, s))
+        if k in (2, 40, 299, 339):
+            stream.append("calibrate")
+
+    h = capi.HandEye(gpu_lib)
+    r = dll.ref_handeye_create()
+    n_cal = n_ok = n_rej = 0
+    try:
+        for item in stream:
+            if item == "calibrate":
+                ok, ext, sv = h.calibrate()
+                R9, t3 = np.zeros(9), np.zeros(3)
+                ok_ref = dll.ref_handeye_calibrate(r, R9.ctypes.data_as(f64p), t3.ctypes.data_as(f64p))
+                assert bool(ok_ref) == ok, (n_cal, sv)
+                n_cal += 1
+                if ok:
+                    n_ok += 1
+                    assert np.allclose(quat_to_R(ext[:4]), R9.reshape(3, 3), rtol=0, atol=1e-9)
+                    assert np.allclose(ext[4:], t3, rtol=0, atol=1e-9)
+                continue
+            p, s = (np.ascontiguousarray(v, dtype=np.float64) for v in item)
+            e_ref = dll.ref_handeye_add_pose(r, p.ctypes.data_as(f64p), s.ctypes.data_as(f64p))
+            e = h.add_pose(p, s)
+            assert bool(e_ref) == e
+            n_rej += 0 if e else 1
+        assert n_cal == 5 and n_ok >= 3 and n_rej >= 15 and h.size() == 300
+    finally:
+        h.close()
+        dll.ref_handeye_destroy(r)
+
+
 @pytest.mark.gpu
 def test_rig_calibrates_then_refines(gpu_lib, synth):
     """MultiLidarSystem::process() calibration branch on two HDL-64 (the 64-line sensor tracks accurately in the synthetic

@@ -478,6 +478,49 @@ def test_lm_solve_vs_numpy_ceres_restatement(oracle_lib):
         assert dt < 0.05 and dr < 0.01
 
 
+def test_lm_trust_region_schedule_with_rejected_steps(oracle_lib):
+    """The trust-region schedule itself (radius 1e4, rho > 1e-3 accepts, radius / max(1/3, 1 - (2 rho - 1)^3) on success,
+    radius / 2, / 4, / 8 ... on consecutive failures) on problems built to FAIL steps: a large initial rotation error and
+    gross outliers make the Gauss-Newton-like first steps overshoot, so the independently written numpy loop (DENSE_QR on
+    the augmented Jacobian, as Ceres solves it — the oracle goes through the Cholesky of the normal equations) and the oracle
+    must agree on which steps are rejected, i.e. on the whole radius sequence: same step and accept counts with
+    accepted < steps, same final pose and cost."""
+    rng = np.random.default_rng(11)
+    from scipy.spatial.transform import Rotation
+    rejected_somewhere = 0
+    for trial in range(8):
+        Rt = Rotation.from_rotvec(rng.normal(size=3) * (0.5 + 0.1 * trial))
+        tt = rng.normal(size=3) * 2.0
+        surf, edge = [], []
+        for _ in range(120):
+            n = rng.normal(size=3)
+            n /= np.linalg.norm(n)
+            pw = rng.uniform(-20, 20, 3)
+            pl = Rt.inv().apply(pw - tt)
+            noise = rng.normal() * 0.01 + (3.0 if rng.random() < 0.2 else 0.0)
+            surf.append(np.concatenate([pl, n, [-(n @ pw) + noise]]))
+        for _ in range(30):
+            u = rng.normal(size=3)
+            u /= np.linalg.norm(u)
+            pw = rng.uniform(-20, 20, 3)
+            c = pw + rng.normal(size=3) * 0.01
+            pl = Rt.inv().apply(pw - tt)
+            edge.append(np.concatenate([pl, c + 0.1 * u, c - 0.1 * u]))
+        surf, edge = np.array(surf), np.array(edge)
+        x0 = np.array([0, 0, 0, 1.0, 0, 0, 0])
+        xn, sn, an, cn = _np_lm(edge, surf, x0, 0.1, 16)
+        x = x0.copy()
+        steps, acc, cost = C.c_int(0), C.c_int(0), C.c_double(0)
+        oracle_lib.fn("lm_solve")(edge.ctypes.data_as(C.c_void_p), len(edge), surf.ctypes.data_as(C.c_void_p), len(surf),
+                                  C.c_double(0.1), 16, x.ctypes.data_as(C.c_void_p), C.byref(steps), C.byref(acc),
+                                  C.byref(cost))
+        assert (steps.value, acc.value) == (sn, an), trial
+        assert np.allclose(x, xn, rtol=0, atol=1e-7), trial
+        assert abs(cost.value - cn) <= 1e-7 * max(1.0, cn), trial
+        rejected_somewhere += int(an < sn)
+    assert rejected_somewhere >= 3
+
+
 # ---------------------------------------------------------------- registration / tracker behaviour
 def test_registration_recovers_known_motion(oracle_lib, synth):
     o = oracle_lib.context(0, n_scans=64, oracle_threads=8)
