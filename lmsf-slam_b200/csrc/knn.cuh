@@ -23,7 +23,7 @@
 //            while the current one is judged; a candidate enters the sorted five (64-bit keys = distance bits | index)
 //            only if it beats the current fifth.  The lanes of a warp differ in the trip count of this one loop only.
 // With seeds (the previous outer iteration's neighbours) one sweep of the ball's bounding box is enough; without,
-// the search adapts to the density around the query (own cell, 27 cells, then a counted growth: see kq_knn5).
+// the search adapts to the density around the query (the eight cells nearest to it, then a counted growth: see kq_knn5).
 //
 // Cell sizes are powers of two, so cell indices and cell bounds are exact in
 // fp32 and a box is a superset of the ball it covers (edges computed exactly, in fp64).
@@ -319,35 +319,25 @@ struct KqSweep {
   int xlo[3], xhi[3];  // cells searched before: left out (none when xlo[0] > xhi[0])
   float bound_d;       // L1 cells farther than this (squared) are skipped
   int mode;
-  bool own_first;      // KQ_SCAN: the cell own[] goes to list position 0 and is counted in n_own
-  int own[3];
   // KQ_NEAREST_L1: the occupied L1 cell of the box nearest to the query among those behind (after_d, after_id)
   float after_d;
   int after_id;
   // results
   int count;           // points in the swept cells
-  int n_own;
   float best_d;        // KQ_NEAREST_L1: squared distance, id and L2 origin of the cell found (best_id < 0: none)
   int best_id, best_o[3];
 };
 
-// Phase A of one sweep (see the header).  KQ_SCAN: segments to the list; when own_first, scanning is left to the
-// caller (kq_scan over the list: position 0 = the own cell, possibly empty, then `nseg - 1` others) as long as the
-// list does not overflow.  Returns the number of list entries that are waiting to be scanned.
+// Phase A of one sweep (see the header).  KQ_SCAN: segments to the list; scanning is left to the caller (kq_scan over
+// the list) as long as the list does not overflow.  Returns the number of list entries that are waiting to be scanned.
 HD int kq_collect(const MapView& mv, const MapDev& md, const KqList& li, float qx, float qy, float qz, KqSweep& sw,
                   KqTop& top, bool dedup, int& pending) {
   int nseg = 0;
   pending = 0;
   sw.count = 0;
-  sw.n_own = 0;
   sw.best_id = -1;
   sw.best_d = 3.0e38f;
   const bool excl = sw.xlo[0] <= sw.xhi[0];
-  if (sw.mode == KQ_SCAN && sw.own_first) {  // position 0 is the own cell's (empty until found)
-    li.seg[0] = 0;
-    li.seg[li.stride] = 0;
-    nseg = 1;
-  }
   for (int cz = sw.lo[2] >> 4; cz <= (sw.hi[2] >> 4); ++cz)
     for (int cy = sw.lo[1] >> 4; cy <= (sw.hi[1] >> 4); ++cy)
       for (int cx = sw.lo[0] >> 4; cx <= (sw.hi[0] >> 4); ++cx) {
@@ -393,24 +383,6 @@ HD int kq_collect(const MapView& mv, const MapDev& md, const KqList& li, float q
           if (excl)
             sel2 &= ~kq_box_mask(sw.xlo[0] - ox, sw.xhi[0] - ox, sw.xlo[1] - oy, sw.xhi[1] - oy, sw.xlo[2] - oz,
                                  sw.xhi[2] - oz);
-          if (sw.mode == KQ_SCAN && sw.own_first) {
-            // the own cell, if it lies in this L1 cell and is occupied, is taken out of the runs: position 0
-            const int rx = sw.own[0] - ox, ry = sw.own[1] - oy, rz = sw.own[2] - oz;
-            if ((unsigned)rx < 4u && (unsigned)ry < 4u && (unsigned)rz < 4u) {
-              const int f2 = (rz << 4) | (ry << 2) | rx;
-              if ((sel2 >> f2) & 1ull) {
-                sel2 &= ~(1ull << f2);
-                const int b = lr.first + KG_POPC64(lr.mask & kq_below(f2));
-                const int s = KG_LD(&mv.l2_start[b]);
-                const int e = KG_LD(&mv.l2_start[b + 1]);
-                li.seg[0] = s;
-                li.seg[li.stride] = e;
-                sw.n_own = e - s;
-                sw.count += e - s;
-                pending += e - s;
-              }
-            }
-          }
           while (sel2) {
             // a run: selected cells with no occupied unselected cell between them are contiguous in `sorted`
             const int lb = kq_ffs64(sel2);
@@ -425,9 +397,8 @@ HD int kq_collect(const MapView& mv, const MapDev& md, const KqList& li, float q
             sw.count += e - s;
             KG_STAT(3, 1);
             if (sw.mode == KQ_SCAN) {
-              if (nseg == KQ_SEG_CAP) {  // rare: a long list is scanned in pieces (the own-cell choice is off then)
-                kq_scan(mv, li, (sw.own_first && sw.n_own == 0) ? 1 : 0, pending, qx, qy, qz, top, dedup);
-                sw.own_first = false;
+              if (nseg == KQ_SEG_CAP) {  // rare: a long list is scanned in pieces
+                kq_scan(mv, li, 0, pending, qx, qy, qz, top, dedup);
                 nseg = 0;
                 pending = 0;
               }
@@ -466,7 +437,7 @@ HD float kq_gap2(const float q[3], const int lo[3], const int hi[3]) {
 }
 
 enum {
-  KQ_ST_START = 0,   // the 27 L2 cells around the query, the own cell first
+  KQ_ST_START = 0,   // the 2 x 2 x 2 block of L2 cells nearest to the query
   KQ_ST_BALL = 1,    // the ball of the known bound, minus what was searched
   KQ_ST_GROW = 2,    // sparse: count a larger box
   KQ_ST_SHELL = 3,   // sparse: scan the box that holds five points (few points)
@@ -475,9 +446,6 @@ enum {
   KQ_ST_LAST = 6,    // sparse: the ball of the bound, everything (duplicates filtered)
   KQ_ST_DONE = 7
 };
-#ifndef KQ_OWN_ONLY_ABOVE
-#define KQ_OWN_ONLY_ABOVE 64  // START scans the own cell alone only when the 27 cells hold more points than this
-#endif
 constexpr int KQ_SHELL_MAX = 96;  // a grown box with more points than this is searched cell by cell, nearest first
 
 // Exact 5-NN within squared radius 1.0 of one query.  seed = nullptr: no prior knowledge; otherwise the keys of five
@@ -486,10 +454,12 @@ constexpr int KQ_SHELL_MAX = 96;  // a grown box with more points than this is s
 //
 // Every step is one sweep (phase A + phase B) at ONE call site, so that the lanes of a warp stay together whatever
 // state their queries are in.  Without a seed the search adapts to the density around the query:
-//   START  the 27 L2 cells around the query are collected; if the query's own cell holds five points only that cell is
-//          scanned, else all 27.  Five points in hand and nothing unsearched nearer than the 5th: done.
+//   START  the 2 x 2 x 2 block of L2 cells nearest to the query is collected and scanned (every face of the block is at
+//          least half a cell away from the query).  Five points in hand and nothing unsearched nearer than the 5th: done.
+//          (Round 2 until r2t: the 27 cells around the own cell, or the own cell alone when it held five points — three
+//          times the candidates, or a second sweep for most queries; the block is 12 % faster per pass.)
 //   BALL   else what the ball of the 5th distance holds beyond the searched box settles the answer.
-//   sparse (fewer than five points in the 27 cells): the box grows — points are only COUNTED — until it holds five.
+//   sparse (fewer than five points in the block): the box grows — points are only COUNTED — until it holds five.
 //          Few points: they are scanned (SHELL) and BALL finishes.  Many (a dense surface has entered the box, which a
 //          box does with a whole face): the L1 cells of the box are scanned nearest first (FIND, CELL) until five
 //          points are known, and the ball of that bound is swept once more with duplicates filtered (LAST).
@@ -511,16 +481,21 @@ HD int kq_knn5(const MapView& mv, const KqList& li, float qx, float qy, float qz
   sw.xlo[1] = sw.xlo[2] = sw.xhi[1] = sw.xhi[2] = 0;
   sw.bound_d = 1.0f;
   sw.mode = KQ_SCAN;
-  sw.own_first = false;
   sw.after_d = -1.0f;
   sw.after_id = -1;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) sw.own[k] = a[k];
   int state;
   bool dedup = false;
   int total = 0;  // points in the boxes swept so far
   int grow = 0;   // sparse: next box width to try
   int glo[3] = {0, 0, 0}, ghi[3] = {0, 0, 0};  // sparse: the box that holds five points
+  // START's box: the 2 x 2 x 2 block of L2 cells nearest to the query — every face of it is at least half a cell
+  // (31 mm) away, and it holds a third of the candidates of the 27 cells around the query's own cell
+  int slo[3], shi[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int up = (q[k] * 16.0f - (float)a[k]) >= 0.5f ? 1 : 0;  // exact: x16 and the difference are exact in fp32
+    slo[k] = a[k] - 1 + up, shi[k] = a[k] + up;
+  }
   bool seeded = false;
   if (seed != nullptr) {
     // the five seeds ARE the list to beat: the sweep of their ball only inserts what is nearer than one of them (between
@@ -538,30 +513,19 @@ HD int kq_knn5(const MapView& mv, const KqList& li, float qx, float qy, float qz
     kq_ball_box(qx, qy, qz, sw.bound_d, sw.lo, sw.hi);
   } else {
     state = KQ_ST_START;
-    sw.own_first = true;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) sw.lo[k] = a[k] - 1, sw.hi[k] = a[k] + 1;
+    for (int k = 0; k < 3; ++k) sw.lo[k] = slo[k], sw.hi[k] = shi[k];
   }
   while (state != KQ_ST_DONE) {
     KG_STAT(8 + state, 1);
     int pending = 0;
     const int nseg = kq_collect(mv, md, li, qx, qy, qz, sw, top, dedup, pending);
     if (sw.mode == KQ_SCAN) {
-      int first = 0;
-      bool own_only = false;
-      if (sw.own_first) {  // START, list intact: the own cell alone if it holds five points
-        own_only = sw.n_own >= 5 && sw.count > KQ_OWN_ONLY_ABOVE;
-        first = sw.n_own > 0 ? 0 : 1;
-        if (own_only) pending = sw.n_own;
-      }
-      if (nseg > first) kq_scan(mv, li, first, pending, qx, qy, qz, top, dedup);
-      if (state == KQ_ST_START) {
-        // searched: the own cell or the 27 cells
-        const int w = own_only ? 0 : 1;
+      if (nseg > 0) kq_scan(mv, li, 0, pending, qx, qy, qz, top, dedup);
+      if (state == KQ_ST_START) {  // searched: START's box
 #pragma unroll
-        for (int k = 0; k < 3; ++k) sw.xlo[k] = a[k] - w, sw.xhi[k] = a[k] + w;
-        total = own_only ? sw.n_own : sw.count;
-        sw.own_first = false;
+        for (int k = 0; k < 3; ++k) sw.xlo[k] = slo[k], sw.xhi[k] = shi[k];
+        total = sw.count;
       }
     }
     // ---- transitions
@@ -625,9 +589,9 @@ HD int kq_knn5(const MapView& mv, const KqList& li, float qx, float qy, float qz
         for (int k = 0; k < 3; ++k) sw.lo[k] = a[k] - grow, sw.hi[k] = a[k] + grow;
       }
       if (state == KQ_ST_SHELL) {
-        // leave out what START searched (the 27 cells), not the boxes that were only counted
+        // leave out what START searched (its box), not the boxes that were only counted
 #pragma unroll
-        for (int k = 0; k < 3; ++k) sw.xlo[k] = a[k] - 1, sw.xhi[k] = a[k] + 1;
+        for (int k = 0; k < 3; ++k) sw.xlo[k] = slo[k], sw.xhi[k] = shi[k];
       }
     } else if (DEFER) {
       return -1;  // not reached
