@@ -141,6 +141,7 @@ HD float kg_key_d2(unsigned long long k) { return u2f((unsigned)(k >> 32)); }
 HD int kg_key_id(unsigned long long k) { return (int)(unsigned)(k & 0xffffffffull); }
 
 constexpr int KQ_SEG_CAP = 16;  // segments a lane collects before it scans them
+constexpr int KQ_SHELL_MAX = 96;  // a grown box with more points than this is searched cell by cell, nearest first
 constexpr unsigned long long KG_KEY_LT_1 = (0x3f800000ull << 32) - 1ull;  // largest key with d2 < 1.0f
 
 // where a lane keeps its segment list: seg[(2 k) * stride], seg[(2 k + 1) * stride] = start, end of segment k
@@ -312,7 +313,9 @@ HD void kq_scan(const MapView& mv, const KqList& li, int first, int total, float
 }
 
 // what one sweep does with the cells of its box
-enum { KQ_SCAN = 0, KQ_COUNT = 1, KQ_NEAREST_L1 = 2 };
+// KQ_SCAN_FEW: count, and keep the segments as long as they fit the list and hold at most KQ_SHELL_MAX points (few = true
+// on return: the caller scans them; otherwise the sweep was a count)
+enum { KQ_SCAN = 0, KQ_COUNT = 1, KQ_NEAREST_L1 = 2, KQ_SCAN_FEW = 3 };
 
 struct KqSweep {
   int lo[3], hi[3];    // box of L2 cells (inclusive)
@@ -324,6 +327,7 @@ struct KqSweep {
   int after_id;
   // results
   int count;           // points in the swept cells
+  bool few;            // KQ_SCAN_FEW: the segments of all `count` points are in the list
   float best_d;        // KQ_NEAREST_L1: squared distance, id and L2 origin of the cell found (best_id < 0: none)
   int best_id, best_o[3];
 };
@@ -335,6 +339,7 @@ HD int kq_collect(const MapView& mv, const MapDev& md, const KqList& li, float q
   int nseg = 0;
   pending = 0;
   sw.count = 0;
+  sw.few = true;
   sw.best_id = -1;
   sw.best_d = 3.0e38f;
   const bool excl = sw.xlo[0] <= sw.xhi[0];
@@ -396,7 +401,11 @@ HD int kq_collect(const MapView& mv, const MapDev& md, const KqList& li, float q
             KQ_CHECK_RET(s >= 0 && s < e && e <= md.n, 5, s, e, b0, 0);
             sw.count += e - s;
             KG_STAT(3, 1);
-            if (sw.mode == KQ_SCAN) {
+            if (sw.mode == KQ_SCAN_FEW) {
+              if (nseg == KQ_SEG_CAP || sw.count > KQ_SHELL_MAX) sw.few = false;
+              if (!sw.few) continue;
+            }
+            if (sw.mode == KQ_SCAN || sw.mode == KQ_SCAN_FEW) {
               if (nseg == KQ_SEG_CAP) {  // rare: a long list is scanned in pieces
                 kq_scan(mv, li, 0, pending, qx, qy, qz, top, dedup);
                 nseg = 0;
@@ -446,7 +455,6 @@ enum {
   KQ_ST_LAST = 6,    // sparse: the ball of the bound, everything (duplicates filtered)
   KQ_ST_DONE = 7
 };
-constexpr int KQ_SHELL_MAX = 96;  // a grown box with more points than this is searched cell by cell, nearest first
 
 // Exact 5-NN within squared radius 1.0 of one query.  seed = nullptr: no prior knowledge; otherwise the keys of five
 // distinct map points (any order) believed to be near the query.  Returns n <= 5 and the n nearest keys,
@@ -520,7 +528,7 @@ HD int kq_knn5(const MapView& mv, const KqList& li, float qx, float qy, float qz
     KG_STAT(8 + state, 1);
     int pending = 0;
     const int nseg = kq_collect(mv, md, li, qx, qy, qz, sw, top, dedup, pending);
-    if (sw.mode == KQ_SCAN) {
+    if (sw.mode == KQ_SCAN || (sw.mode == KQ_SCAN_FEW && sw.few)) {
       if (nseg > 0) kq_scan(mv, li, 0, pending, qx, qy, qz, top, dedup);
       if (state == KQ_ST_START) {  // searched: START's box
 #pragma unroll
@@ -547,7 +555,7 @@ HD int kq_knn5(const MapView& mv, const KqList& li, float qx, float qy, float qz
         }
       } else if (state == KQ_ST_START) {
         state = KQ_ST_GROW;
-        sw.mode = KQ_COUNT;
+        sw.mode = KQ_SCAN_FEW;  // the first grown box is scanned in the same sweep when it holds few points
         grow = 2;
 #pragma unroll
         for (int k = 0; k < 3; ++k) sw.lo[k] = a[k] - grow, sw.hi[k] = a[k] + grow;
@@ -563,8 +571,26 @@ HD int kq_knn5(const MapView& mv, const KqList& li, float qx, float qy, float qz
       }
     } else if (state == KQ_ST_GROW) {
       total += sw.count;
+      const bool scanned = sw.mode == KQ_SCAN_FEW && sw.few;
+      sw.mode = KQ_COUNT;
+      if (scanned) {  // the grown box is searched: it takes the place of START's block
+#pragma unroll
+        for (int k = 0; k < 3; ++k) slo[k] = sw.lo[k], shi[k] = sw.hi[k];
+      }
       if (DEFER && ((total < 5 && grow >= 4) || total - top.n > KQ_SHELL_MAX)) return -1;
-      if (total >= 5 || grow >= 16) {
+      if (scanned && top.n == 5) {
+        // as after SHELL: the ball of the 5th distance beyond the searched box settles the answer
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sw.xlo[k] = slo[k], sw.xhi[k] = shi[k];
+        if (top.d4 < kq_gap2(q, sw.xlo, sw.xhi)) {
+          state = KQ_ST_DONE;
+        } else {
+          state = KQ_ST_BALL;
+          sw.mode = KQ_SCAN;
+          sw.bound_d = top.d4;
+          kq_ball_box(qx, qy, qz, top.d4, sw.lo, sw.hi);
+        }
+      } else if (!scanned && (total >= 5 || grow >= 16)) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) glo[k] = sw.lo[k], ghi[k] = sw.hi[k];
         // the counted box becomes the searched one after the next step; what START searched stays left out

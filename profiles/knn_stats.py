@@ -1,4 +1,5 @@
-"""Tuning aid: distribution of kNN work per exit pass on a realistic tracker state (HDL-64, raw map)."""
+"""Tuning aid: work counters of the unseeded kNN search (csrc/debug_stats.cu, lmsf_debug_knn_stats) on a realistic
+tracker state (HDL-64, raw 10-keyframe window): sweeps started per state, cells and candidates per query."""
 import ctypes as C
 import os
 import sys
@@ -17,14 +18,14 @@ for k in range(nsw):
     p, d, st = ctx.tracker_step(synth.make_sweep(sensor, k), 0.1 * k)
 _, e, s = ctx.extract_features(synth.make_sweep(sensor, nsw))
 T = synth.qt_to_mat(p)
+names = ["START", "BALL", "GROW", "SHELL", "FIND", "CELL", "LAST"]
 for kind, f in ((0, e), (1, s)):
     q = np.ascontiguousarray((f[:, :3] @ T[:3, :3].T + T[:3, 3]).astype(np.float32))
     out = (C.c_ulonglong * 28)()
     rc = ctx.lib.dll.lmsf_debug_knn_stats(ctx._h, kind, q.ctypes.data_as(C.c_void_p), len(q), out)
     o = np.array(out[:], dtype=np.int64)
-    print(f"kind {kind}: map {st['map_edge'] if kind == 0 else st['map_surf']} pts, {len(q)} queries, rc={rc}")
-    for l, name in ((0, "no map / out of range"), (1, "A (27 L2 cells)"), (2, "ball sweep"), (3, "B (27 L1 cells)"), (4, "C (27 L0 cells)")):
-        n = o[l * 4]
-        if n:
-            print(f"  exit {name:24s}: {n:7d} queries ({100.0 * n / len(q):5.1f}%), full {o[20 + l]:7d}, per query: "
-                  f"cand {o[l * 4 + 1] / n:8.1f}  box tests {o[l * 4 + 2] / n:7.1f}  lookups {o[l * 4 + 3] / n:6.1f}")
+    n = max(1, int(o[16]))
+    print(f"kind {kind}: map {st['map_edge'] if kind == 0 else st['map_surf']} pts, {len(q)} queries, rc={rc}, "
+          f"with 5 neighbours {o[17]}")
+    print(f"  per query: L0 lookups {o[0] / n:.2f}, L1 cells {o[1] / n:.2f}, segments {o[3] / n:.2f}, candidates {o[2] / n:.1f}")
+    print("  sweeps per query by state: " + ", ".join(f"{nm} {o[8 + i] / n:.3f}" for i, nm in enumerate(names)))
