@@ -1750,7 +1750,7 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       static const int knn_width = env_int("LMSF_KNN_WIDTH", 0);  // tuning experiments
       int chunk = 32;  // queries per warp: halve it while the sweep has fewer chunks than ~1.5x the resident warps
       while (chunk > 8 && up / chunk < 148 * knn_per_sm * (KG_BLOCK / 32) * 3 / 2) chunk >>= 1;
-      if (knn_width == 8 || knn_width == 16 || knn_width == 32) chunk = knn_width;
+      if (knn_width >= 1 && knn_width <= 32) chunk = knn_width;
       int knn_grid = div_up(up, 4 * chunk);
       if (knn_grid > 148 * knn_per_sm) knn_grid = 148 * knn_per_sm;  // persistent: every resident warp pulls work
       // Deferral pays when the sparse cases are the exception (a raw window: 0.6 % of the queries, but all of the long
