@@ -797,6 +797,14 @@ __device__ __forceinline__ unsigned long long gtime() {
 #endif
 
 // ------------------------------------------------------------------ kernels
+// Programmatic dependent launch (sm_90+): a kernel of the solve chain launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may be scheduled while its predecessor is still draining; it must
+// not touch anything the predecessor reads or writes before pdl_wait() (griddepcontrol.wait: the predecessor grid has
+// completed and its memory is visible).  pdl_launch_next() then lets the successor be scheduled in turn — behind the
+// wait, so at most one successor grid sits resident at a time.  Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_next() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct QueryBufs {
   unsigned* keys;            // [upper] sort keys (kind | L0 | L1 | L2 cell of the world point, top 32 bits)
   int* vals;                 // [upper] feature index
@@ -848,6 +856,8 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
                                                SolveState* __restrict__ st, MapPair maps, int has_edge_map,
                                                int has_surf_map, QueryOrigin qorg,
                                                int upper, int solver, int with_keys, QueryBufs qb) {
+  pdl_wait();
+  pdl_launch_next();
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {  // work queues of the k_knn launch that follows
@@ -939,6 +949,8 @@ __global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __re
                                              MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
                                              int seeded, int assoc, int chunk, int* __restrict__ defer,
                                              int* __restrict__ nbr) {
+  pdl_wait();
+  pdl_launch_next();
   __shared__ int s_seg[KQ_SMEM_INTS];
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   const int n_e = counts[0], n_s = counts[1];
@@ -1011,6 +1023,8 @@ __global__ void __launch_bounds__(KG_BLOCK) k_knn_sparse(const int* __restrict__
                                                          const int* __restrict__ counts, SolveState* __restrict__ st,
                                                          MapPair maps, int upper, int solver,
                                                          const int* __restrict__ defer, int* __restrict__ nbr) {
+  pdl_wait();
+  pdl_launch_next();
   __shared__ KwScratch scratch[KG_BLOCK / 32];
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   const int n_def = st->n_defer;
@@ -1105,6 +1119,8 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
                                                      const int* __restrict__ counts, MapPair maps, int upper,
                                                      SolveState* __restrict__ st, RecBufs rb,
                                                      double* __restrict__ partial, SolveParams sp) {
+  pdl_wait();
+  pdl_launch_next();
   __shared__ double tot[LM_NSUM];
   if (sp.solver == LMSF_SOLVER_GN && st->gn_done) return;
   TSTAMP(t_begin);
@@ -1173,6 +1189,8 @@ __device__ __forceinline__ void eval_positions(int upper, const quat& q, d3 tr, 
 // re-evaluate the stored correspondences at the LM candidate; last block accepts / rejects / proposes
 __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* __restrict__ st, RecBufs rb,
                                                          double* __restrict__ partial, SolveParams sp) {
+  pdl_wait();
+  pdl_launch_next();
   __shared__ double tot[LM_NSUM];
   if (!st->lm_active) return;
   TSTAMP(t_begin);
@@ -1531,6 +1549,24 @@ __global__ void __launch_bounds__(256) k_align_finish(const double* __restrict__
 #ifndef KNN_GRID_PER_SM
 #define KNN_GRID_PER_SM 4
 #endif
+// launch on the context's stream with the programmatic-stream-serialization attribute (see pdl_wait) when `pdl`
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(Ctx* c, bool pdl, void (*kern)(KArgs...), int grid, int block, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  c->launches++;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#define LM_CHAIN(c, pdl, kern, grid, block, ...) LM_CUDA(launch_chain(c, pdl, kern, grid, block, __VA_ARGS__))
+
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   int x = v ? atoi(v) : 0;
@@ -1707,10 +1743,15 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
   // permutation that walks the surfs along their rings (consecutive positions are neighbours in space): no sort.
   // Caller-supplied or voxel-filtered features are sorted by map cell once per solve instead.
   static const int force_qsort = env_int("LMSF_FORCE_QSORT", 0);  // tuning experiments
+  static const bool want_pdl = env_int("LMSF_NO_PDL", 0) == 0;  // A/B: 1 = ordinary launches
   // 1 = k_solve (one persistent launch per outer iteration) instead of k_fit + k_lm_eval launches: built for round 2,
   // measured equal in isolation and 12 us per launch slower inside the pipeline (r2p-r2r) — kept selectable, not default
   static const bool fused_solve = env_int("LMSF_FUSED_SOLVE", 0) == 1;
   const bool ring_order = c->perm_valid && !force_qsort;
+  // programmatic dependent launches along the chain k_knn -> k_knn_sparse -> k_fit -> k_lm_eval x n -> k_knn ...: only when
+  // every launch of the chain is one of ours (the cell-sort path has a library sort in it) and no profiling event is
+  // recorded between them
+  const bool pdl = want_pdl && ring_order && !c->prof;
   const int* perm = ring_order ? c->d_perm : c->q_vals_alt;
   QueryBufs qb;
   qb.keys = (unsigned*)c->q_keys;
@@ -1760,16 +1801,16 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       const bool sparse_map = c->prm.map_leaf_surf >= 0.125f;
       const bool defer = force_defer == 1 || (force_defer != 2 && !sparse_map);
       if (defer) {
-        LM_LAUNCH(c, k_knn<true>, knn_grid, KG_BLOCK, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,
-                  up, solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
+        LM_CHAIN(c, pdl, k_knn<true>, knn_grid, KG_BLOCK, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,
+                 up, solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
         // the sparse cases of this pass, one warp each (nothing to do when k_knn deferred none).  Serving them in the
         // tail of k_knn itself (warps that find the chunk queue empty) was built and measured 3-8x SLOWER, with or without
         // waiting for the producers (r2q, r2s): two large code paths alive on one SM at a time
-        LM_LAUNCH(c, k_knn_sparse, 148 * 2, KG_BLOCK, 0, perm, c->d_pw, c->ex.counts, c->d_state, maps, up, solver,
-                    c->d_defer, c->d_nbr);
+        LM_CHAIN(c, pdl, k_knn_sparse, 148 * 2, KG_BLOCK, perm, c->d_pw, c->ex.counts, c->d_state, maps, up, solver,
+                 c->d_defer, c->d_nbr);
       } else {
-        LM_LAUNCH(c, k_knn<false>, knn_grid, KG_BLOCK, 0, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,
-                  up, solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
+        LM_CHAIN(c, pdl, k_knn<false>, knn_grid, KG_BLOCK, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,
+                 up, solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
       }
       c->match_bytes += alg_bytes;
       c->match_launches += 1;
@@ -1795,13 +1836,13 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
     } else {
       {
         StageScope scope(c, LMSF_STAGE_FIT);
-        LM_LAUNCH(c, k_fit, fit_grid, MATCH_BLOCK, 0, c->d_feat, perm, c->d_pw, c->d_nbr, c->ex.counts, maps,
-                  up, c->d_state, rb, c->d_partial, sp);
+        LM_CHAIN(c, pdl, k_fit, fit_grid, MATCH_BLOCK, c->d_feat, perm, c->d_pw, c->d_nbr, c->ex.counts, maps, up,
+                 c->d_state, rb, c->d_partial, sp);
       }
       if (solver == LMSF_SOLVER_HUBER_LM) {
         StageScope scope(c, LMSF_STAGE_SOLVE);
         for (int k = 0; k < c->prm.lm_inner_iters; ++k)
-          LM_LAUNCH(c, k_lm_eval, eval_grid, MATCH_BLOCK, 0, up, c->d_state, rb, c->d_partial, sp);
+          LM_CHAIN(c, pdl, k_lm_eval, eval_grid, MATCH_BLOCK, up, c->d_state, rb, c->d_partial, sp);
       }
     }
   }
