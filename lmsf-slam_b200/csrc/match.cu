@@ -1050,6 +1050,7 @@ struct RecBufs {
 
 // The correspondences of this thread's positions (t = first, first + step, ...): fit, residual and Jacobian at (q, tr)
 // into acc; for the Huber-LM solver also the per-match records k_lm_eval / k_solve re-evaluate.
+template <bool ACC>
 __device__ __forceinline__ void fit_positions(const float4* __restrict__ feat, const int* __restrict__ perm,
                                               const float4* __restrict__ pw, const int* __restrict__ nbr, int n_e,
                                               int n_s, const MapPair& maps, int upper, const quat& q, d3 tr,
@@ -1074,7 +1075,7 @@ __device__ __forceinline__ void fit_positions(const float4* __restrict__ feat, c
         double r;
         if (fit_edge(maps.edge_cat, nb, w.x, w.y, w.z, n, r, a, b)) {
           kind = 1;
-          acc.v[29] += 1.0;
+          if (ACC) acc.v[29] += 1.0;
           if (sp.solver == LMSF_SOLVER_GN) {
             gn_row(R, pl, n, r, acc);
           } else {
@@ -1084,7 +1085,7 @@ __device__ __forceinline__ void fit_positions(const float4* __restrict__ feat, c
             rb.d[3 * rb.stride + t] = b.x;
             rb.d[4 * rb.stride + t] = b.y;
             rb.d[5 * rb.stride + t] = b.z;
-            edge_factor(q, tr, pl, a, b, sp.huber, acc);
+            if (ACC) edge_factor(q, tr, pl, a, b, sp.huber, acc);
           }
         }
       } else {
@@ -1099,7 +1100,7 @@ __device__ __forceinline__ void fit_positions(const float4* __restrict__ feat, c
             rb.d[1 * rb.stride + t] = n.y;
             rb.d[2 * rb.stride + t] = n.z;
             rb.d[3 * rb.stride + t] = D;
-            surf_factor(q, tr, pl, n, D, sp.huber, acc);
+            if (ACC) surf_factor(q, tr, pl, n, D, sp.huber, acc);
           }
         }
       }
@@ -1135,7 +1136,7 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
   quat_to_mat(q, R);
   Acc acc;
   acc_zero(acc);
-  fit_positions(feat, perm, pw, nbr, n_e, n_s, maps, upper, q, tr, R, rb, sp, acc);
+  fit_positions<true>(feat, perm, pw, nbr, n_e, n_s, maps, upper, q, tr, R, rb, sp, acc);
   TSTAMP(t_loop);
   if (!reduce_grid(acc, partial, st, tot)) return;
   TSTAMP(t_red);
@@ -1169,6 +1170,7 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
 }
 
 // the stored correspondences of this thread's positions re-evaluated at (q, tr)
+template <bool COUNT_EDGES = false>
 __device__ __forceinline__ void eval_positions(int upper, const quat& q, d3 tr, const RecBufs& rb, const SolveParams& sp,
                                                Acc& acc) {
   for (int t = blockIdx.x * MATCH_BLOCK + threadIdx.x; t < upper; t += gridDim.x * MATCH_BLOCK) {
@@ -1179,11 +1181,60 @@ __device__ __forceinline__ void eval_positions(int upper, const quat& q, d3 tr, 
     double r3 = rb.d[3 * rb.stride + t];
     if (kind == 1) {
       d3 b = mk3(r3, rb.d[4 * rb.stride + t], rb.d[5 * rb.stride + t]);
+      if (COUNT_EDGES) acc.v[29] += 1.0;
       edge_factor(q, tr, pl, mk3(r0, r1, r2), b, sp.huber, acc);
     } else {
       surf_factor(q, tr, pl, mk3(r0, r1, r2), r3, sp.huber, acc);
     }
   }
+}
+
+// ---- the Huber-LM outer iteration in two launches instead of k_fit ----------------------------------------------
+// k_fit carries 30 fp64 accumulators through the fits (168 registers, two resident blocks per SM, every thread four
+// features one after the other: a 22 us loop of dependent fp64 chains).  k_fit_records only fits and stores the records
+// (one feature per thread, more resident warps), k_lm_eval0 then evaluates the records at x — the same sums k_fit forms,
+// in the order of the evaluation grid — and its last block opens the trust-region loop (lm_begin).
+__global__ void __launch_bounds__(MATCH_BLOCK) k_fit_records(const float4* __restrict__ feat, const int* __restrict__ perm,
+                                                             const float4* __restrict__ pw, const int* __restrict__ nbr,
+                                                             const int* __restrict__ counts, MapPair maps, int upper,
+                                                             RecBufs rb, SolveParams sp) {
+  pdl_wait();
+  pdl_launch_next();
+  const int n_e = counts[0], n_s = counts[1];
+  quat q;
+  q.x = q.y = q.z = 0.0;
+  q.w = 1.0;
+  Acc acc;  // unused (ACC = false)
+  fit_positions<false>(feat, perm, pw, nbr, n_e, n_s, maps, upper, q, mk3(0, 0, 0), nullptr, rb, sp, acc);
+}
+
+__global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval0(int upper, SolveState* __restrict__ st, RecBufs rb,
+                                                          double* __restrict__ partial, SolveParams sp) {
+  pdl_wait();
+  pdl_launch_next();
+  __shared__ double tot[LM_NSUM];
+  quat q;
+  q.x = st->x[0];
+  q.y = st->x[1];
+  q.z = st->x[2];
+  q.w = st->x[3];
+  d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
+  Acc acc;
+  acc_zero(acc);
+  eval_positions<true>(upper, q, tr, rb, sp, acc);
+  if (!reduce_grid(acc, partial, st, tot)) return;
+  __shared__ SolveState sh;
+  __shared__ LmScratch scratch;
+  state_load(&sh, st);
+  if (threadIdx.x == 0) {
+    sh.n_edge_ok = (int)tot[29];
+    sh.n_surf_ok = (int)tot[28] - (int)tot[29];
+    sh.knn_next = 0;  // work-queue heads of the next k_knn / k_knn_sparse launches
+    sh.defer_next = 0;
+    sh.n_defer = 0;
+  }
+  if (threadIdx.x < 32) lm_begin_warp(&sh, &scratch, tot, sp);
+  state_store(st, &sh);
 }
 
 // re-evaluate the stored correspondences at the LM candidate; last block accepts / rejects / proposes
@@ -1263,7 +1314,7 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_solve(const float4* __restrict_
     q.w = st->x[3];
     const d3 tr = mk3(st->x[4], st->x[5], st->x[6]);
     acc_zero(acc);
-    fit_positions(feat, perm, pw, nbr, n_e, n_s, maps, upper, q, tr, nullptr, rb, sp, acc);
+    fit_positions<true>(feat, perm, pw, nbr, n_e, n_s, maps, upper, q, tr, nullptr, rb, sp, acc);
   }
   __syncthreads();
   unsigned gen = s_gen;
@@ -1744,6 +1795,7 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
   // Caller-supplied or voxel-filtered features are sorted by map cell once per solve instead.
   static const int force_qsort = env_int("LMSF_FORCE_QSORT", 0);  // tuning experiments
   static const bool want_pdl = env_int("LMSF_NO_PDL", 0) == 0;  // A/B: 1 = ordinary launches
+  static const bool split_fit = env_int("LMSF_ONE_FIT", 0) == 0;  // A/B: 1 = k_fit (fit + evaluation at x in one launch)
   // 1 = k_solve (one persistent launch per outer iteration) instead of k_fit + k_lm_eval launches: built for round 2,
   // measured equal in isolation and 12 us per launch slower inside the pipeline (r2p-r2r) — kept selectable, not default
   static const bool fused_solve = env_int("LMSF_FUSED_SOLVE", 0) == 1;
@@ -1834,7 +1886,12 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
                   c->d_partial, sp, c->d_bar);
       }
     } else {
-      {
+      if (solver == LMSF_SOLVER_HUBER_LM && split_fit) {
+        StageScope scope(c, LMSF_STAGE_FIT);
+        LM_CHAIN(c, pdl, k_fit_records, div_up(up, MATCH_BLOCK), MATCH_BLOCK, c->d_feat, perm, c->d_pw, c->d_nbr,
+                 c->ex.counts, maps, up, rb, sp);
+        LM_CHAIN(c, pdl, k_lm_eval0, eval_grid, MATCH_BLOCK, up, c->d_state, rb, c->d_partial, sp);
+      } else {
         StageScope scope(c, LMSF_STAGE_FIT);
         LM_CHAIN(c, pdl, k_fit, fit_grid, MATCH_BLOCK, c->d_feat, perm, c->d_pw, c->d_nbr, c->ex.counts, maps, up,
                  c->d_state, rb, c->d_partial, sp);
