@@ -173,7 +173,7 @@ struct Ctx {
   int* q_vals_alt = nullptr;                 // sorted: position -> feature index
   float4* d_pw = nullptr;      // [max_points] fp32 world point by feature index
   int* d_nbr = nullptr;        // [5][max_points] neighbour indices by sorted query position
-  int* d_defer = nullptr;      // [max_points] positions of the queries k_knn left to k_knn_sparse
+  float4* d_defer = nullptr;   // [max_points] the queries k_knn left to k_knn_sparse: world point, .w = position | edge flag
   double* d_partial = nullptr; // [grid][LM_NSUM]
   int partial_blocks = 0;
   SolveState* d_state = nullptr;

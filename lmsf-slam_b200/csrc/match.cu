@@ -902,13 +902,13 @@ __global__ void __launch_bounds__(256) k_assoc(const float4* __restrict__ feat, 
   }
 }
 
-// One deferred query, searched by the whole warp (kw_knn5); all lanes call with the same t.  pw[] holds the world point.
-__device__ __forceinline__ void knn_sparse_one(const Warp32& x, KwScratch* s, int t, const int* __restrict__ perm,
-                                               const float4* __restrict__ pw, int n_e, const MapPair& maps,
-                                               int upper, int* __restrict__ nbr) {
-  const int f = perm[t];
-  const bool is_edge = f < n_e;
-  const float4 w = pw[f];
+// One deferred query, searched by the whole warp (kw_knn5); all lanes call with the same record (k_knn: world point,
+// .w = position | edge flag in bit 30).
+__device__ __forceinline__ void knn_sparse_one(const Warp32& x, KwScratch* s, float4 w, const MapPair& maps, int upper,
+                                               int* __restrict__ nbr) {
+  const int tw = __float_as_int(w.w);
+  const int t = tw & 0x3fffffff;
+  const bool is_edge = (tw & 0x40000000) != 0;
   KqTop top;
   int n = kw_knn5(x, is_edge ? maps.edge : maps.surf, s, w.x, w.y, w.z, top);
   if (n < 0) {
@@ -947,7 +947,7 @@ __global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __re
                                              const float4* __restrict__ feat,
                                              const int* __restrict__ counts, SolveState* __restrict__ st,
                                              MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
-                                             int seeded, int assoc, int chunk, int* __restrict__ defer,
+                                             int seeded, int assoc, int chunk, float4* __restrict__ defer,
                                              int* __restrict__ nbr) {
   pdl_wait();
   pdl_launch_next();
@@ -1007,7 +1007,8 @@ __global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __re
         n = kq_knn5<DEFER>(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, have_seed ? seed : nullptr, top);
       }
       if (n < 0) {  // a sparse case: left to the warp-cooperative search (one warp per query)
-        defer[atomicAdd(&st->n_defer, 1)] = t;
+        // one 16-byte record per deferred query: the warp search starts from a single load (position, kind and point)
+        defer[atomicAdd(&st->n_defer, 1)] = make_float4(w.x, w.y, w.z, __int_as_float(t | (is_edge ? (int)0x40000000 : 0)));
       } else {
         // -1 x 5 unless five neighbours lie within the search radius: both callers reject such a query
 #pragma unroll
@@ -1018,26 +1019,38 @@ __global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __re
 }
 
 // the queries k_knn deferred, one per warp (kw_knn5): the launch is enqueued behind every k_knn, its size is only
-// known on the device.  pw[] holds the world point already.
+// known on the device.
 __global__ void __launch_bounds__(KG_BLOCK) k_knn_sparse(const int* __restrict__ perm, const float4* __restrict__ pw,
                                                          const int* __restrict__ counts, SolveState* __restrict__ st,
                                                          MapPair maps, int upper, int solver,
-                                                         const int* __restrict__ defer, int* __restrict__ nbr) {
+                                                         const float4* __restrict__ defer, int* __restrict__ nbr) {
   pdl_wait();
   pdl_launch_next();
   __shared__ KwScratch scratch[KG_BLOCK / 32];
   if (solver == LMSF_SOLVER_GN && st->gn_done) return;
   const int n_def = st->n_defer;
   if (n_def == 0) return;
-  const int n_e = counts[0];
   const Warp32 x;
   KwScratch* s = &scratch[threadIdx.x >> 5];
-  while (true) {
-    int i = 0;
-    if (x.lane == 0) i = atomicAdd(&st->defer_next, 1);
-    i = x.shfl(i, 0);
+  // every warp starts with the query of its own number (no round trip to the queue head); further ones from the queue
+  const int n_warps = gridDim.x * (KG_BLOCK / 32);
+  int i = blockIdx.x * (KG_BLOCK / 32) + (threadIdx.x >> 5);
+  for (;;) {
     if (i >= n_def) break;
-    knn_sparse_one(x, s, defer[i], perm, pw, n_e, maps, upper, nbr);
+    TSTAMP(t_q0);
+    knn_sparse_one(x, s, defer[i], maps, upper, nbr);
+#ifdef LMSF_TIMING
+    if (x.lane == 0) {  // per-query time of the warp search: max, sum, count, histogram < 5 / 10 / 20 / 40 / >= 40 us
+      TSTAMP(t_q1);
+      const unsigned long long dt = t_q1 - t_q0;
+      atomicMax(&g_dbg[8], dt);
+      atomicAdd(&g_dbg[9], dt);
+      atomicAdd(&g_dbg[10], 1ull);
+      atomicAdd(&g_dbg[11 + (dt < 5000 ? 0 : (dt < 10000 ? 1 : (dt < 20000 ? 2 : (dt < 40000 ? 3 : 4))))], 1ull);
+    }
+#endif
+    if (x.lane == 0) i = n_warps + atomicAdd(&st->defer_next, 1);
+    i = x.shfl(i, 0);
   }
 }
 
@@ -1390,9 +1403,7 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_solve(const float4* __restrict_
       TACC(23 + k, t_rel, t_ev);
       TCOUNT(28);
     }
-    if (threadIdx.x == 0 && k == 0) atomicMax(&g_dbg[11], t_ev - t_rel);
-    if (threadIdx.x == 0 && k == 0) atomicMax(&g_dbg[12], t_ev);
-    if (threadIdx.x == 0 && k == 0) atomicMin(&g_dbg[13], t_ev);
+
 #endif
   }
 #ifdef LMSF_TIMING
@@ -1645,7 +1656,7 @@ int solve_alloc(Ctx* c) {
   LM_CUDA(cudaMalloc(&c->q_vals_alt, cap * 4));
   LM_CUDA(cudaMalloc(&c->d_pw, cap * sizeof(float4)));
   LM_CUDA(cudaMalloc(&c->d_nbr, 5 * cap * sizeof(int)));
-  LM_CUDA(cudaMalloc(&c->d_defer, cap * sizeof(int)));
+  LM_CUDA(cudaMalloc(&c->d_defer, cap * sizeof(float4)));
   c->partial_blocks = div_up((int)cap, MATCH_BLOCK);
   LM_CUDA(cudaMalloc(&c->d_partial, (size_t)c->partial_blocks * LM_NSUM * sizeof(double)));
   LM_CUDA(cudaMalloc(&c->d_state, sizeof(SolveState)));
@@ -1858,7 +1869,8 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
         // the sparse cases of this pass, one warp each (nothing to do when k_knn deferred none).  Serving them in the
         // tail of k_knn itself (warps that find the chunk queue empty) was built and measured 3-8x SLOWER, with or without
         // waiting for the producers (r2q, r2s): two large code paths alive on one SM at a time
-        LM_CHAIN(c, pdl, k_knn_sparse, 148 * 2, KG_BLOCK, perm, c->d_pw, c->ex.counts, c->d_state, maps, up, solver,
+        static const int sparse_per_sm = env_int("LMSF_SPARSE_GRID", 4);  // 2: 1 559, 3: 1 574, 4: 1 588, 6: 1 575 scans/s (r3j)
+        LM_CHAIN(c, pdl, k_knn_sparse, 148 * sparse_per_sm, KG_BLOCK, perm, c->d_pw, c->ex.counts, c->d_state, maps, up, solver,
                  c->d_defer, c->d_nbr);
       } else {
         LM_CHAIN(c, pdl, k_knn<false>, knn_grid, KG_BLOCK, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,

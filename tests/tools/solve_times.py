@@ -29,5 +29,4 @@ print("  barrier k (arrival -> release seen), summed over launches / launches:",
 print("  evaluation loop k, summed over launches / launches:", [round(o[23 + k] / c / 1e3, 1) for k in range(5)])
 c = max(1, o[10])
 print(f"  last block, barriers k >= 1 ({o[10]}): arrival -> totals ready {o[8] / c / 1e3:.1f} us, totals -> release {o[9] / c / 1e3:.1f} us")
-print(f"  evaluation 0: slowest thread-0 loop over all blocks and launches {o[11] / 1e3:.1f} us")
 print(f"    of which state load {o[4] / c / 1e3:.1f}, 6x6 update {o[5] / c / 1e3:.1f}, state store {o[6] / c / 1e3:.1f}, fence + release {o[7] / c / 1e3:.1f} us")
