@@ -95,6 +95,8 @@ struct MapDev {  // device-visible description of one map index (lives in device
   int bits[3];        // bits per axis in the packed key
   unsigned table_mask;  // slots - 1
   int n_fine;         // occupied fine cells
+  int grow0;          // kNN: first grown box (half width in L2 cells) when START's block holds fewer than five points;
+                      // 2 for raw clouds, wider over a voxel-filtered map whose points are a leaf apart (0 = 2)
 };
 
 struct MapIndex {
@@ -114,6 +116,7 @@ struct MapIndex {
   int* d_cnt = nullptr;                    // [8] device counters: L2 entries, L1 cells, L0 cells, insert-failed flag, point cursor
   unsigned* d_box = nullptr;               // [8] bbox scratch of this map (ordered-uint min/max, finite count)
   int* h_cnt = nullptr;                    // [4] pinned mirror of d_cnt (read back with the next pose)
+  int grow0 = 2;                           // density hint for the search (MapDev::grow0), set by the caller of map_build
   bool fixed = false;                      // grid origin / key width frozen (tracker maps): builds need no host sync
   int n_cells_seen = 0;                    // occupied L0 cells of the last build that was read back
   CellRec* table = nullptr;                // [table_cap]

@@ -556,7 +556,7 @@ HD int kq_knn5(const MapView& mv, const KqList& li, float qx, float qy, float qz
       } else if (state == KQ_ST_START) {
         state = KQ_ST_GROW;
         sw.mode = KQ_SCAN_FEW;  // the first grown box is scanned in the same sweep when it holds few points
-        grow = 2;
+        grow = md.grow0 > 2 ? (md.grow0 > 16 ? 16 : md.grow0) : 2;
 #pragma unroll
         for (int k = 0; k < 3; ++k) sw.lo[k] = a[k] - grow, sw.hi[k] = a[k] + grow;
       } else {
@@ -610,7 +610,7 @@ HD int kq_knn5(const MapView& mv, const KqList& li, float qx, float qy, float qz
         // next width: 2, 3, 4, 6, 8, 12, 16; the box counted so far is left out of the next count
 #pragma unroll
         for (int k = 0; k < 3; ++k) sw.xlo[k] = sw.lo[k], sw.xhi[k] = sw.hi[k];
-        grow = grow < 4 ? grow + 1 : (grow == 4 ? 6 : (grow == 6 ? 8 : (grow == 8 ? 12 : 16)));
+        grow = grow < 4 ? grow + 1 : (grow < 6 ? 6 : (grow < 8 ? 8 : (grow < 12 ? 12 : 16)));
 #pragma unroll
         for (int k = 0; k < 3; ++k) sw.lo[k] = a[k] - grow, sw.hi[k] = a[k] + grow;
       }

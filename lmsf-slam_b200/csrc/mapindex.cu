@@ -423,6 +423,7 @@ int map_build(Ctx* c, MapIndex& m, int n, cudaStream_t st, bool fixed_grid) {
   }
   md.table_mask = slots - 1;
   md.n_fine = 0;
+  md.grow0 = m.grow0;
   m.host = md;
   // the descriptor is passed through pinned memory owned by the map: the copy is asynchronous on `st`
   MapDev* hd = (MapDev*)(m.h_cnt + 32);

@@ -1020,9 +1020,7 @@ __global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __re
 
 // the queries k_knn deferred, one per warp (kw_knn5): the launch is enqueued behind every k_knn, its size is only
 // known on the device.
-__global__ void __launch_bounds__(KG_BLOCK) k_knn_sparse(const int* __restrict__ perm, const float4* __restrict__ pw,
-                                                         const int* __restrict__ counts, SolveState* __restrict__ st,
-                                                         MapPair maps, int upper, int solver,
+__global__ void __launch_bounds__(KG_BLOCK) k_knn_sparse(SolveState* __restrict__ st, MapPair maps, int upper, int solver,
                                                          const float4* __restrict__ defer, int* __restrict__ nbr) {
   pdl_wait();
   pdl_launch_next();
@@ -1870,8 +1868,7 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
         // tail of k_knn itself (warps that find the chunk queue empty) was built and measured 3-8x SLOWER, with or without
         // waiting for the producers (r2q, r2s): two large code paths alive on one SM at a time
         static const int sparse_per_sm = env_int("LMSF_SPARSE_GRID", 4);  // 2: 1 559, 3: 1 574, 4: 1 588, 6: 1 575 scans/s (r3j)
-        LM_CHAIN(c, pdl, k_knn_sparse, 148 * sparse_per_sm, KG_BLOCK, perm, c->d_pw, c->ex.counts, c->d_state, maps, up, solver,
-                 c->d_defer, c->d_nbr);
+        LM_CHAIN(c, pdl, k_knn_sparse, 148 * sparse_per_sm, KG_BLOCK, c->d_state, maps, up, solver, c->d_defer, c->d_nbr);
       } else {
         LM_CHAIN(c, pdl, k_knn<false>, knn_grid, KG_BLOCK, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,
                  up, solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);

@@ -339,6 +339,7 @@ int main(int argc, char** argv) {
   const int n_map = argc > 1 ? atoi(argv[1]) : 60000;
   const int n_q = argc > 2 ? atoi(argv[2]) : 1500;
   const unsigned seed = argc > 3 ? (unsigned)atoi(argv[3]) : 1u;
+  const int grow0 = argc > 4 ? atoi(argv[4]) : 0;  // MapDev::grow0 (the density hint of voxel-filtered maps)
   std::mt19937 rng(seed);
   std::uniform_real_distribution<float> U(0.f, 1.f);
   std::normal_distribution<float> N(0.f, 1.f);
@@ -359,6 +360,7 @@ int main(int argc, char** argv) {
   while ((int)pts.size() < n_map) add(-40.f + 80.f * U(rng), -40.f + 80.f * U(rng), -3.f + 10.f * U(rng));
   HostIndex ix;
   build_index(pts, ix);
+  ix.md.grow0 = grow0;
 
   std::vector<Query> qs;
   for (int i = 0; i < n_q; ++i) {

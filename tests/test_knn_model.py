@@ -16,8 +16,10 @@ def model_bin():
     return exe
 
 
-@pytest.mark.parametrize("n_map,n_q,seed", [(60000, 4000, 1), (120000, 4000, 2), (3000, 2000, 7), (40, 300, 9)])
-def test_knn_model_matches_brute_force(model_bin, n_map, n_q, seed):
-    r = subprocess.run([model_bin, str(n_map), str(n_q), str(seed)], capture_output=True, text=True, timeout=600)
+@pytest.mark.parametrize("n_map,n_q,seed,grow0", [(60000, 4000, 1, 0), (120000, 4000, 2, 0), (3000, 2000, 7, 0), (40, 300, 9, 0),
+                                                   (3000, 2000, 7, 8), (60000, 2000, 3, 4), (500, 2000, 5, 12)])
+def test_knn_model_matches_brute_force(model_bin, n_map, n_q, seed, grow0):
+    """grow0 = MapDev::grow0, the density hint of voxel-filtered maps (the first grown box of a sparse query)."""
+    r = subprocess.run([model_bin, str(n_map), str(n_q), str(seed), str(grow0)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 mismatches" in r.stdout
