@@ -652,6 +652,33 @@ HD int kq_knn5(const MapView& mv, const KqList& li, float qx, float qy, float qz
   }
   return top.n;
 }
+// The seeded search alone (outer iterations after the first, registration kernel): the five seeds are the list to beat and
+// one sweep of the bounding box of their ball settles the answer — no START / GROW states, so the kernel that calls only
+// this needs fewer registers.  Returns top.n == 5, or -1 when a seed lies beyond the search radius (no bound: the caller
+// hands the query to the warp-cooperative search).
+HD int kq_knn5_seeded(const MapView& mv, const KqList& li, float qx, float qy, float qz, const unsigned long long* seed,
+                      KqTop& top) {
+  const MapDev md = *mv.dev;
+  kq_top_reset(top, KG_KEY_LT_1 + 1ull);
+  if (!(md.n > 0) || !(fabsf(qx) < 2.0e5f && fabsf(qy) < 2.0e5f && fabsf(qz) < 2.0e5f)) return 0;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+    if (seed[k] < top.k[4]) kq_insert(top, seed[k], false);
+  if (top.n != 5) return -1;
+  KqSweep sw;
+  sw.xlo[0] = 1, sw.xhi[0] = 0;  // nothing left out
+  sw.xlo[1] = sw.xlo[2] = sw.xhi[1] = sw.xhi[2] = 0;
+  sw.bound_d = top.d4;
+  sw.mode = KQ_SCAN;
+  sw.after_d = -1.0f;
+  sw.after_id = -1;
+  kq_ball_box(qx, qy, qz, sw.bound_d, sw.lo, sw.hi);
+  int pending = 0;
+  const int nseg = kq_collect(mv, md, li, qx, qy, qz, sw, top, true, pending);
+  if (nseg > 0) kq_scan(mv, li, 0, pending, qx, qy, qz, top, true);
+  return top.n;
+}
+
 // ---- the sparse cases, searched by a whole warp -------------------------------------------------------------------
 // One query per warp: best-first over the occupied L1 cells within the search radius.  Every load a single thread
 // would chain (27 hash probes, one L1 record and two cell starts per L1 cell) is issued by its own lane.

@@ -941,12 +941,17 @@ __device__ __forceinline__ void knn_sparse_one(const Warp32& x, KwScratch* s, fl
 #ifndef KNN_MINBLOCKS
 #define KNN_MINBLOCKS 4
 #endif
+#ifndef KNN_SEEDED_MINBLOCKS
+#define KNN_SEEDED_MINBLOCKS 5  // seeded-only kernel, resident blocks per SM: 4: 1 620, 5: 1 632, 6: 1 626, 8 (spills): 1 552;
+#endif                          // the general kernel for the seeded pass: 1 608-1 617 scans/s (r3q)
 // assoc != 0 (ring-order launches): the kernel also does k_assoc's work for its own query — pointAssociateToMap in
 // fp64, stored as fp32 in pw[] for k_fit — so no separate launch is needed.
 // seeded != 0 (outer iterations after the first): nbr[] holds the previous iteration's neighbours of the same position;
 // the largest of their keys at the query's new place bounds the 5th key from the start.
-template <bool DEFER>
-__global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __restrict__ perm, float4* __restrict__ pw,
+// SEEDED_ONLY (with DEFER, seeded launches): only the seeded search is compiled in; a query without five usable seeds (it
+// had fewer than five neighbours within the radius in the previous pass) goes to the warp-cooperative search.
+template <bool DEFER, bool SEEDED_ONLY = false>
+__global__ void __launch_bounds__(KG_BLOCK, SEEDED_ONLY ? KNN_SEEDED_MINBLOCKS : KNN_MINBLOCKS) k_knn(const int* __restrict__ perm, float4* __restrict__ pw,
                                              const float4* __restrict__ feat,
                                              const int* __restrict__ counts, SolveState* __restrict__ st,
                                              MapPair maps, int has_edge_map, int has_surf_map, int upper, int solver,
@@ -1007,7 +1012,10 @@ __global__ void __launch_bounds__(KG_BLOCK, KNN_MINBLOCKS) k_knn(const int* __re
             }
           }
         }
-        n = kq_knn5<DEFER>(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, have_seed ? seed : nullptr, top);
+        if (SEEDED_ONLY)
+          n = have_seed ? kq_knn5_seeded(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, seed, top) : -1;
+        else
+          n = kq_knn5<DEFER>(is_edge ? maps.edge : maps.surf, li, w.x, w.y, w.z, have_seed ? seed : nullptr, top);
       }
       if (n < 0) {  // a sparse case: left to the warp-cooperative search (one warp per query)
         // one 16-byte record per deferred query: the warp search starts from a single load (position, kind and point)
@@ -1792,7 +1800,8 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
   // persistent-style grids: a few CTAs per SM, grid-stride over the queries (per-SM factors tunable through the
   // environment for profiling sweeps only)
   static const int fit_per_sm = env_int("LMSF_FIT_GRID", 1), eval_per_sm = env_int("LMSF_EVAL_GRID", 2),
-                   knn_per_sm = env_int("LMSF_KNN_GRID", KNN_GRID_PER_SM);
+                   knn_per_sm = env_int("LMSF_KNN_GRID", KNN_GRID_PER_SM),
+                   seeded_per_sm = env_int("LMSF_KNN_SEEDED_GRID", KNN_SEEDED_MINBLOCKS);
   int fit_grid = div_up(up, MATCH_BLOCK);
   if (fit_grid > 148 * fit_per_sm) fit_grid = 148 * fit_per_sm;
   int eval_grid = div_up(up, MATCH_BLOCK);
@@ -1865,8 +1874,16 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       const bool sparse_map = c->prm.map_leaf_surf >= 0.125f;
       const bool defer = force_defer == 1 || (force_defer != 2 && !sparse_map);
       if (defer) {
-        LM_CHAIN(c, pdl, k_knn<true>, knn_grid, KG_BLOCK, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,
-                 up, solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
+        static const bool seeded_kernel = env_int("LMSF_NO_SEEDED_KERNEL", 0) == 0;  // A/B: 1 = the general kernel throughout
+        if (it > 0 && seeded_kernel) {
+          int sgrid = div_up(up, 4 * chunk);
+          if (sgrid > 148 * seeded_per_sm) sgrid = 148 * seeded_per_sm;
+          LM_CHAIN(c, pdl, (k_knn<true, true>), sgrid, KG_BLOCK, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he,
+                   hs, up, solver, 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
+        } else {
+          LM_CHAIN(c, pdl, k_knn<true>, knn_grid, KG_BLOCK, perm, c->d_pw, c->d_feat, c->ex.counts, c->d_state, maps, he, hs,
+                   up, solver, it == 0 ? 0 : 1, ring_order ? 1 : 0, chunk, c->d_defer, c->d_nbr);
+        }
         // the sparse cases of this pass, one warp each (nothing to do when k_knn deferred none).  Serving them in the
         // tail of k_knn itself (warps that find the chunk queue empty) was built and measured 3-8x SLOWER, with or without
         // waiting for the producers (r2q, r2s): two large code paths alive on one SM at a time
