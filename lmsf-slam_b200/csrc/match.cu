@@ -37,6 +37,10 @@ namespace lm {
 #endif
 static constexpr int MATCH_BLOCK = LMSF_MATCH_BLOCK;
 static constexpr int MATCH_WARPS = MATCH_BLOCK / 32;
+#ifndef LMSF_EVAL_PREFETCH
+#define LMSF_EVAL_PREFETCH 2  // records per thread that k_lm_eval fetches before its griddepcontrol.wait (2 x 148 x 256 threads: all of an HDL-64 sweep)
+#endif
+static constexpr int EVAL_PREFETCH = LMSF_EVAL_PREFETCH;
 
 struct SolveParams {
   int solver;        // LMSF_SOLVER_*
@@ -225,12 +229,27 @@ __device__ __forceinline__ bool reduce_grid(const Acc& acc, double* __restrict__
   __shared__ bool last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned nblk = gridDim.x;
+  // Warp sums of the LM_NSUM quantities by a TRANSPOSING butterfly: at the exchange over distance d a lane keeps one
+  // half of the quantities it still holds and hands the other half to its partner, so the 32 (padded) quantities cost
+  // 16 + 8 + 4 + 2 + 1 = 31 exchanges instead of 30 x 5, and lane k ends up with the warp total of quantity k.  The
+  // additions are the ones of the plain xor butterfly (v[l] + v[l ^ d] at every level, the same tree for every
+  // quantity; fp addition commutes), so every bit of the result is what the 150-exchange form produced.
+  {
+    static_assert(LM_NSUM <= 32, "one quantity per lane after the transposing butterfly");
+    double a[32];
 #pragma unroll
-  for (int k = 0; k < LM_NSUM; ++k) {
-    double x = acc.v[k];
+    for (int k = 0; k < 32; ++k) a[k] = (k < LM_NSUM) ? acc.v[k] : 0.0;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-    if (lane == 0) wsum[warp][k] = x;
+    for (int d = 16; d > 0; d >>= 1) {
+      const bool hi = (lane & d) != 0;
+#pragma unroll
+      for (int i = 0; i < d; ++i) {
+        const double send = hi ? a[i] : a[i + d];
+        const double keep = hi ? a[i + d] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+      }
+    }
+    if (lane < LM_NSUM) wsum[warp][lane] = a[0];
   }
   __syncthreads();
   if (threadIdx.x < LM_NSUM) {
@@ -255,15 +274,27 @@ __device__ __forceinline__ bool reduce_grid(const Acc& acc, double* __restrict__
   double x[ROWS];
 #pragma unroll
   for (int j = 0; j < ROWS; ++j) x[j] = 0.0;
-  for (unsigned b = lane; b < nblk; b += 32) {
-    double v[ROWS];
+  // FINAL_BATCH strides of 32 blocks are loaded before the first of them is added (one L2 round trip per batch instead
+  // of one per stride: 296 blocks = 10 strides = 2 batches); the additions stay in ascending block order per lane
+  constexpr int FINAL_BATCH = 5;
+  for (unsigned b0 = lane; b0 < nblk; b0 += 32 * FINAL_BATCH) {
+    double v[FINAL_BATCH][ROWS];
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) {
-      const int k = warp + j * MATCH_WARPS;
-      v[j] = (k < LM_NSUM) ? __ldcg(&partial[(size_t)k * nblk + b]) : 0.0;
+    for (int u = 0; u < FINAL_BATCH; ++u) {
+      const unsigned b = b0 + 32u * u;
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) {
+        const int k = warp + j * MATCH_WARPS;
+        v[u][j] = (k < LM_NSUM && b < nblk) ? __ldcg(&partial[(size_t)k * nblk + b]) : 0.0;
+      }
     }
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) x[j] += v[j];
+    for (int u = 0; u < FINAL_BATCH; ++u) {
+      if (b0 + 32u * u < nblk) {
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) x[j] += v[u][j];
+      }
+    }
   }
 #pragma unroll
   for (int j = 0; j < ROWS; ++j) {
@@ -1192,22 +1223,49 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_fit(const float4* __restrict__ 
 }
 
 // the stored correspondences of this thread's positions re-evaluated at (q, tr)
+// one stored correspondence as k_fit_records left it (76 bytes: kind, scan point, a / b or n / D)
+struct RecRow {
+  uint8_t kind;
+  float pl[3];
+  double d[6];
+};
+
+__device__ __forceinline__ void rec_load(RecRow& r, const RecBufs& rb, int t, int upper) {
+  r.kind = 0;
+  if (t >= upper) return;
+  r.kind = rb.kind[t];
+  if (!r.kind) return;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r.pl[i] = rb.pl[i * rb.stride + t];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.d[i] = rb.d[i * rb.stride + t];
+  if (r.kind == 1) {
+    r.d[4] = rb.d[4 * rb.stride + t];
+    r.d[5] = rb.d[5 * rb.stride + t];
+  }
+}
+
+template <bool COUNT_EDGES>
+__device__ __forceinline__ void rec_eval(const RecRow& r, const quat& q, d3 tr, const SolveParams& sp, Acc& acc) {
+  if (!r.kind) return;
+  d3 pl = mk3((double)r.pl[0], (double)r.pl[1], (double)r.pl[2]);
+  if (r.kind == 1) {
+    if (COUNT_EDGES) acc.v[29] += 1.0;
+    edge_factor(q, tr, pl, mk3(r.d[0], r.d[1], r.d[2]), mk3(r.d[3], r.d[4], r.d[5]), sp.huber, acc);
+  } else {
+    surf_factor(q, tr, pl, mk3(r.d[0], r.d[1], r.d[2]), r.d[3], sp.huber, acc);
+  }
+}
+
+// the positions of this thread from `first` on, in steps of the grid
 template <bool COUNT_EDGES = false>
 __device__ __forceinline__ void eval_positions(int upper, const quat& q, d3 tr, const RecBufs& rb, const SolveParams& sp,
-                                               Acc& acc) {
-  for (int t = blockIdx.x * MATCH_BLOCK + threadIdx.x; t < upper; t += gridDim.x * MATCH_BLOCK) {
-    uint8_t kind = rb.kind[t];
-    if (!kind) continue;
-    d3 pl = mk3((double)rb.pl[0 * rb.stride + t], (double)rb.pl[1 * rb.stride + t], (double)rb.pl[2 * rb.stride + t]);
-    double r0 = rb.d[0 * rb.stride + t], r1 = rb.d[1 * rb.stride + t], r2 = rb.d[2 * rb.stride + t];
-    double r3 = rb.d[3 * rb.stride + t];
-    if (kind == 1) {
-      d3 b = mk3(r3, rb.d[4 * rb.stride + t], rb.d[5 * rb.stride + t]);
-      if (COUNT_EDGES) acc.v[29] += 1.0;
-      edge_factor(q, tr, pl, mk3(r0, r1, r2), b, sp.huber, acc);
-    } else {
-      surf_factor(q, tr, pl, mk3(r0, r1, r2), r3, sp.huber, acc);
-    }
+                                               Acc& acc, int skip = 0) {
+  const int step = gridDim.x * MATCH_BLOCK;
+  for (int t = blockIdx.x * MATCH_BLOCK + threadIdx.x + skip * step; t < upper; t += step) {
+    RecRow r;
+    rec_load(r, rb, t, upper);
+    rec_eval<COUNT_EDGES>(r, q, tr, sp, acc);
   }
 }
 
@@ -1261,9 +1319,24 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval0(int upper, SolveState*
 
 // re-evaluate the stored correspondences at the LM candidate; last block accepts / rejects / proposes
 __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* __restrict__ st, RecBufs rb,
-                                                         double* __restrict__ partial, SolveParams sp) {
+                                                         double* __restrict__ partial, SolveParams sp, int early_records) {
+  // The records were written by k_fit_records, which had completed before the launch that precedes this one passed
+  // its own griddepcontrol.wait (k_lm_eval0 or a k_lm_eval) — so this thread's first EVAL_PREFETCH records can be
+  // fetched BEFORE the wait, while the previous launch is still in its reduction and 6x6 step: the candidate pose is
+  // the only thing the wait protects.  (Ordinary launches: the wait is a no-op and this is a plain load.)  The launch
+  // that follows k_fit directly (LMSF_ONE_FIT=1: the records are still being written) passes early_records = 0.
+  RecRow pre[EVAL_PREFETCH];
+  const int step = gridDim.x * MATCH_BLOCK;
+  if (early_records) {
+#pragma unroll
+    for (int u = 0; u < EVAL_PREFETCH; ++u) rec_load(pre[u], rb, blockIdx.x * MATCH_BLOCK + threadIdx.x + u * step, upper);
+  }
   pdl_wait();
   pdl_launch_next();
+  if (!early_records) {
+#pragma unroll
+    for (int u = 0; u < EVAL_PREFETCH; ++u) rec_load(pre[u], rb, blockIdx.x * MATCH_BLOCK + threadIdx.x + u * step, upper);
+  }
   __shared__ double tot[LM_NSUM];
   if (!st->lm_active) return;
   TSTAMP(t_begin);
@@ -1275,7 +1348,9 @@ __global__ void __launch_bounds__(MATCH_BLOCK) k_lm_eval(int upper, SolveState* 
   d3 tr = mk3(st->cand[4], st->cand[5], st->cand[6]);
   Acc acc;
   acc_zero(acc);
-  eval_positions(upper, q, tr, rb, sp, acc);
+#pragma unroll
+  for (int u = 0; u < EVAL_PREFETCH; ++u) rec_eval<false>(pre[u], q, tr, sp, acc);
+  eval_positions(upper, q, tr, rb, sp, acc, EVAL_PREFETCH);
   TSTAMP(t_loop);
   if (!reduce_grid(acc, partial, st, tot)) return;
   TSTAMP(t_red);
@@ -1928,7 +2003,8 @@ int solve_enqueue(Ctx* c, int solver, const double pose[7], int upper, int outer
       if (solver == LMSF_SOLVER_HUBER_LM) {
         StageScope scope(c, LMSF_STAGE_SOLVE);
         for (int k = 0; k < c->prm.lm_inner_iters; ++k)
-          LM_CHAIN(c, pdl, k_lm_eval, eval_grid, MATCH_BLOCK, up, c->d_state, rb, c->d_partial, sp);
+          LM_CHAIN(c, pdl, k_lm_eval, eval_grid, MATCH_BLOCK, up, c->d_state, rb, c->d_partial, sp,
+                   (split_fit || k > 0) ? 1 : 0);
       }
     }
   }
