@@ -6,6 +6,8 @@
 // Build = bbox (only for maps set through lmsf_map_set) -> three-level counting sort: points grouped by 1 m cell
 // through the hash table, every cell's segment sorted by its 6-bit 0.25 m | 6-bit 0.0625 m sub-cell in shared
 // memory, which also yields the L1 masks, the L2 cell starts and the hash-table record of the cell.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "knn.cuh"
 
@@ -17,7 +19,7 @@ __global__ void k_bbox(const float4* __restrict__ in, int n, unsigned* __restric
 
 // d_cnt layout: [0] occupied L2 cells (+ one sentinel per L0 cell)  [1] occupied L1 cells  [2] occupied L0 cells
 //               [3] hash-table overflow flag  [4] point cursor (segment allocation)
-enum { CNT_L2 = 0, CNT_L1 = 1, CNT_L0 = 2, CNT_FAIL = 3, CNT_PTS = 4, CNT_WORDS = 8 };
+enum { CNT_L2 = 0, CNT_L1 = 1, CNT_L0 = 2, CNT_FAIL = 3, CNT_PTS = 4, CNT_CELLS = 5, CNT_WORDS = 8 };  // (CNT_PTS, CNT_CELLS): one 8-byte word
 
 // The index is built by a counting sort in three levels instead of a global radix sort: the order of the L0 cells
 // in memory is irrelevant (they are found through the hash table) and so is the order of the points inside one
@@ -87,10 +89,15 @@ __global__ void __launch_bounds__(256) k_cell_alloc(CellRec* __restrict__ table,
   }
   unsigned lv = __ballot_sync(0xffffffffu, live);
   int tot = __shfl_sync(0xffffffffu, inc, 31);
+  // ONE 64-bit atomic hands out the point range and the list positions together (points in the low word = CNT_PTS,
+  // cells in the high word = CNT_CELLS): list position and segment start then grow in the same order, which is what
+  // lets k_cell_sort place a cell's records at offsets derived from (start, list position) without a counter
   int pbase = 0, cbase = 0;
   if (lane == 0 && lv) {
-    pbase = atomicAdd(&d_cnt[CNT_PTS], tot);
-    cbase = atomicAdd(&d_cnt[CNT_L0], __popc(lv));
+    const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(&d_cnt[CNT_PTS]),
+                                             ((unsigned long long)__popc(lv) << 32) | (unsigned long long)(unsigned)tot);
+    pbase = (int)(unsigned)(old & 0xffffffffull);
+    cbase = (int)(unsigned)(old >> 32);
   }
   pbase = __shfl_sync(0xffffffffu, pbase, 0);
   cbase = __shfl_sync(0xffffffffu, cbase, 0);
@@ -135,26 +142,54 @@ constexpr int CS_BINS = 4096 / CS_THREADS;   // bins per thread
 constexpr int CS_LPL = 64 / CS_BINS;         // lanes per L1 cell
 constexpr int CS_WARPS = CS_THREADS / 32;
 constexpr int CS_L1W = 32 / CS_LPL;          // L1 cells per warp
-__global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict__ cell_list,
+constexpr int CS_HIST_WORDS = 4096 + 4096 / 32;
+__device__ __forceinline__ int cs_bin(int b) { return b + (b >> 5); }
+#ifndef CS_KEEP_N
+#define CS_KEEP_N 2  // 2: no spills at two resident blocks of 512 threads (3: 12 bytes, 4: 96 bytes)
+#endif
+constexpr int CS_KEEP = CS_KEEP_N;           // points per thread loaded together / kept in registers between the passes
+__global__ void __launch_bounds__(CS_THREADS, 2) k_cell_sort(const int* __restrict__ cell_list,
                                                           CellRec* __restrict__ table,
                                                           const float4* __restrict__ grouped,
                                                           float4* __restrict__ sorted,
                                                           L1Rec* __restrict__ l1, int* __restrict__ l2_start,
                                                           int* __restrict__ d_cnt) {
-  __shared__ int hist[4096];
+  // bin b lives at word b + b / 32: a thread's CS_BINS consecutive bins (stride CS_BINS words between lanes: an
+  // 8-way bank conflict on every one of the 2 x CS_BINS scan accesses of a cell) then fall into different banks for all
+  // 32 lanes; ncu had the kernel stalled on the shared-memory queue (mio_throttle) first, barriers second
+  __shared__ int hist[CS_HIST_WORDS];
   __shared__ int warp_pts[CS_WARPS], warp_n2[CS_WARPS], warp_n1[CS_WARPS];
-  __shared__ int s_base1, s_base2, s_tot1, s_tot2;
+  __shared__ int s_tot1, s_tot2;
   __shared__ unsigned long long s_m1[CS_WARPS];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int n_cells = d_cnt[CNT_L0];  // final: written by k_cell_alloc, the previous launch on this stream
+  const int n_cells = d_cnt[CNT_CELLS];  // final: written by k_cell_alloc, the previous launch on this stream
   for (int ci = blockIdx.x; ci < n_cells; ci += gridDim.x) {
   const int h = cell_list[ci];
   const int s = table[h].start, e = table[h].end;
   __syncthreads();  // the previous cell's scatter is done with the bins
+  for (int i = t; i < CS_HIST_WORDS; i += CS_THREADS) hist[i] = 0;
+  // The first CS_KEEP points of every thread are loaded together (one round trip instead of one per point: in a dense
+  // cell the chain of dependent loads was the kernel) and stay in registers for the scatter pass; cells with more
+  // than CS_KEEP * CS_THREADS points re-read the rest, again CS_KEEP loads at a time.
+  float4 keep[CS_KEEP];
 #pragma unroll
-  for (int k = 0; k < CS_BINS; ++k) hist[t + k * CS_THREADS] = 0;
+  for (int k = 0; k < CS_KEEP; ++k) {
+    const int i = s + t + k * CS_THREADS;
+    if (i < e) keep[k] = grouped[i];
+  }
   __syncthreads();
-  for (int i = s + t; i < e; i += CS_THREADS) atomicAdd(&hist[sub_cell(grouped[i])], 1);
+#pragma unroll
+  for (int k = 0; k < CS_KEEP; ++k)
+    if (s + t + k * CS_THREADS < e) atomicAdd(&hist[cs_bin((int)sub_cell(keep[k]))], 1);
+  for (int i0 = s + t + CS_KEEP * CS_THREADS; i0 < e; i0 += CS_KEEP * CS_THREADS) {
+    float4 q[CS_KEEP];
+#pragma unroll
+    for (int k = 0; k < CS_KEEP; ++k)
+      if (i0 + k * CS_THREADS < e) q[k] = grouped[i0 + k * CS_THREADS];
+#pragma unroll
+    for (int k = 0; k < CS_KEEP; ++k)
+      if (i0 + k * CS_THREADS < e) atomicAdd(&hist[cs_bin((int)sub_cell(q[k]))], 1);
+  }
   __syncthreads();
   // thread-local: points, occupied L2 cells and their mask
   int cnt[CS_BINS];
@@ -162,7 +197,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict_
   unsigned mloc = 0;
 #pragma unroll
   for (int k = 0; k < CS_BINS; ++k) {
-    cnt[k] = hist[t * CS_BINS + k];
+    cnt[k] = hist[cs_bin(t * CS_BINS + k)];
     pts += cnt[k];
     if (cnt[k]) {
       ++n2;
@@ -218,20 +253,22 @@ __global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict_
     if (lane == CS_WARPS - 1) {
       s_tot1 = s1;
       s_tot2 = s2;
-      s_base1 = atomicAdd(&d_cnt[CNT_L1], s1);
-      s_base2 = atomicAdd(&d_cnt[CNT_L2], s2 + 1);
+      atomicAdd(&d_cnt[CNT_L1], s1);  // statistics only (MapDev::n_fine): no value comes back, nobody waits
     }
   }
   __syncthreads();
   const int tot2 = s_tot2, tot1 = s_tot1;
   const int ex_p = warp_pts[warp] + ip - pts, ex_2 = warp_n2[warp] + i2 - n2, ex_1 = warp_n1[warp] + i1 - n1;
-  const int base1 = s_base1, base2 = s_base2;
+  // A cell with k points has at most k occupied L1 cells and at most k occupied L2 cells, and the cells' segments are
+  // disjoint and in list order (k_cell_alloc): its L1 records go to l1[s, ...) and its L2 starts + sentinel to
+  // l2_start[s + ci, e + ci] — no counter, no global round trip in the middle of a cell
+  const int base1 = s, base2 = s + ci;
   // L2 cell starts of this thread's occupied bins; the bins become running cursors for the scatter
   {
     int run = s + ex_p, r2 = base2 + ex_2;
 #pragma unroll
     for (int k = 0; k < CS_BINS; ++k) {
-      hist[t * CS_BINS + k] = run;
+      hist[cs_bin(t * CS_BINS + k)] = run;
       if (cnt[k]) l2_start[r2++] = run;
       run += cnt[k];
     }
@@ -262,15 +299,26 @@ __global__ void __launch_bounds__(CS_THREADS) k_cell_sort(const int* __restrict_
     table[h].fine_base = base1;
     table[h].pad = 0;
   }
-  for (int i = s + t; i < e; i += CS_THREADS) {
-    float4 p = grouped[i];
-    sorted[atomicAdd(&hist[sub_cell(p)], 1)] = p;
+#pragma unroll
+  for (int k = 0; k < CS_KEEP; ++k)
+    if (s + t + k * CS_THREADS < e) sorted[atomicAdd(&hist[cs_bin((int)sub_cell(keep[k]))], 1)] = keep[k];
+  for (int i0 = s + t + CS_KEEP * CS_THREADS; i0 < e; i0 += CS_KEEP * CS_THREADS) {
+    float4 q[CS_KEEP];
+#pragma unroll
+    for (int k = 0; k < CS_KEEP; ++k)
+      if (i0 + k * CS_THREADS < e) q[k] = grouped[i0 + k * CS_THREADS];
+#pragma unroll
+    for (int k = 0; k < CS_KEEP; ++k)
+      if (i0 + k * CS_THREADS < e) sorted[atomicAdd(&hist[cs_bin((int)sub_cell(q[k]))], 1)] = q[k];
   }
   }  // cells of this block
 }
 
-__global__ void k_map_finish(MapDev* __restrict__ dev, const int* __restrict__ d_cnt) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) dev->n_fine = d_cnt[CNT_L1];
+__global__ void k_map_finish(MapDev* __restrict__ dev, int* __restrict__ d_cnt) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    dev->n_fine = d_cnt[CNT_L1];
+    d_cnt[CNT_L0] = d_cnt[CNT_CELLS];  // the host reads the table occupancy from words [0, 4)
+  }
 }
 
 int map_alloc(Ctx* c, MapIndex& m, int cap) {
@@ -450,7 +498,12 @@ int map_build(Ctx* c, MapIndex& m, int n, cudaStream_t st, bool fixed_grid) {
   LM_LAUNCH_ON(c, st, k_cell_alloc, div_up((int)slots, 256), 256, 0, m.table, slots, m.cell_list, m.d_cnt);
   LM_LAUNCH_ON(c, st, k_cell_scatter, nb, 256, 0, m.cat, n, m.slot_rank, m.table, m.grouped);
   // persistent blocks stride over the occupied L0 cells (their number is only known on the device)
-  LM_LAUNCH_ON(c, st, k_cell_sort, 148 * (CS_THREADS >= 512 ? 4 : 6), CS_THREADS, 0, m.cell_list, m.table, m.grouped, m.sorted, m.l1,
+  static const int cs_per_sm = [] {  // tuning: LMSF_CS_GRID = blocks per SM
+    const char* v = getenv("LMSF_CS_GRID");
+    const int x = v ? atoi(v) : 0;
+    return x > 0 ? x : (CS_THREADS >= 512 ? 4 : 6);
+  }();
+  LM_LAUNCH_ON(c, st, k_cell_sort, 148 * cs_per_sm, CS_THREADS, 0, m.cell_list, m.table, m.grouped, m.sorted, m.l1,
                m.l2_start, m.d_cnt);
   LM_LAUNCH_ON(c, st, k_map_finish, 1, 32, 0, m.dev, m.d_cnt);
   // occupancy of the table (and the insert-failed flag) travel back with the next pose read-back
