@@ -1,4 +1,4 @@
-"""Tuning aid: host-side time per phase of lmsf_tracker_step_dev in steady state (HDL-64), next to the device step time."""
+"""Tuning aid: host-side time per phase of lmsf_tracker_submit_ticket / _prefetch_dev / _wait in steady state (HDL-64), next to the device step time."""
 import ctypes as C
 import os
 import sys
@@ -17,9 +17,11 @@ WARM = 34  # bench.py's SETTLE + default warm-up: full keyframe window, LM budge
 sweeps = [synth.make_sweep(sensor, k) for k in range(n + WARM + 2)]
 ctx = pkg.context(0, n_scans=64, max_points=1 << 18)
 d = [ctx.dev_upload_new(s) for s in sweeps]
-for k in range(WARM):
-    ctx.tracker_prefetch_dev(d[k + 1], len(sweeps[k + 1]))
-    ctx.tracker_step_dev(d[k], len(sweeps[k]), 0.1 * k)
+ticket = ctx.tracker_prefetch_dev(d[0], len(sweeps[0]))  # the calls bench.py times: every step consumes the ticket of its
+for k in range(WARM):                                      # sweep and prefetches the next one
+    ctx.tracker_submit_ticket(ticket, 0.1 * k)
+    ticket = ctx.tracker_prefetch_dev(d[k + 1], len(sweeps[k + 1]))
+    ctx.tracker_wait()
 us = (C.c_double * 4)()
 cnt = (C.c_int64 * 4)()
 ctx.lib.dll.lmsf_debug_host_times(ctx._h, us, cnt, 1)
@@ -28,8 +30,8 @@ kf = []
 t00 = time.perf_counter()
 for k in range(WARM, WARM + n):
     t0 = time.perf_counter()
-    ctx.tracker_submit_dev(d[k], len(sweeps[k]), 0.1 * k)
-    ctx.tracker_prefetch_dev(d[k + 1], len(sweeps[k + 1]))
+    ctx.tracker_submit_ticket(ticket, 0.1 * k)
+    ticket = ctx.tracker_prefetch_dev(d[k + 1], len(sweeps[k + 1]))
     t1 = time.perf_counter()
     _, _, st = ctx.tracker_wait()
     t2 = time.perf_counter()
